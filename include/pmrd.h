@@ -1,0 +1,306 @@
+/*
+ * pmrd.h -- C ABI of libpmrd_b200.so: the B200-native simulate -> UMI-collapse -> call
+ * hot path of precise-mrd (reference: altalanta/precise-mrd-mini).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers and sizes, returns an int32
+ * status (0 = ok, negative = error; text via pmrd_last_error) and never throws.  One
+ * context = one CUDA device + one CUDA stream; contexts are thread-compatible, not
+ * thread-safe.  Pointers named h_* are HOST buffers (the call copies host<->device on
+ * the context's stream and synchronises before returning); pointers named d_* are DEVICE
+ * buffers on the context's device (the call only enqueues work on the context's stream;
+ * the caller synchronises).  All output buffers are caller-allocated.
+ *
+ * The reference has no FFI for this path (its one native component, the pyo3/rayon crate
+ * `precise_mrd_ext`, is never imported: SURVEY.md §2.2).  Each function below cites the
+ * reference interface (file:line under /root/reference) whose arithmetic it replaces;
+ * INTEGRATION.md shows the ctypes stub a reference maintainer would add.
+ */
+#ifndef PMRD_H
+#define PMRD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMRD_ABI_VERSION 1
+
+/* status codes */
+#define PMRD_OK 0
+#define PMRD_ERR_CUDA (-1)      /* a CUDA runtime call failed (text in pmrd_last_error) */
+#define PMRD_ERR_ARG (-2)       /* invalid argument                                     */
+#define PMRD_ERR_CAPACITY (-3)  /* caller-provided output capacity too small            */
+#define PMRD_ERR_NO_DEVICE (-4) /* no usable sm_100 device                              */
+
+typedef struct pmrd_ctx pmrd_ctx;
+
+/* ---------------------------------------------------------------- context ---------- */
+int32_t pmrd_abi_version(void);
+/* device: CUDA ordinal.  seed: Philox key (config.seed; cli.py:63 makes the CLI seed
+ * authoritative).  Fails with PMRD_ERR_NO_DEVICE when no GPU is visible -- there is no
+ * CPU fallback anywhere in this library. */
+int32_t pmrd_create(int32_t device, uint64_t seed, pmrd_ctx** out);
+void pmrd_destroy(pmrd_ctx* ctx);
+const char* pmrd_last_error(const pmrd_ctx* ctx); /* ctx may be NULL: last create error */
+int32_t pmrd_set_seed(pmrd_ctx* ctx, uint64_t seed);
+/* Run on an externally owned stream (e.g. torch.cuda.current_stream().cuda_stream);
+ * NULL restores the context's own stream. */
+int32_t pmrd_set_stream(pmrd_ctx* ctx, void* cuda_stream);
+int32_t pmrd_sync(pmrd_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py: gpu_launches) */
+int64_t pmrd_launch_count(const pmrd_ctx* ctx);
+
+/* ---------------------------------------------------------------- K8: tail p-values - */
+/* test_type */
+#define PMRD_TEST_POISSON 0  /* call.py:14-25  poisson_test(observed, expected)          */
+#define PMRD_TEST_BINOMIAL 1 /* call.py:28-38  binomial_test(successes, trials, p)       */
+/* alternative */
+#define PMRD_ALT_TWO_SIDED 0 /* G-D: 2*min(cdf(k), sf(k-1)) / scipy binomtest "minlike"  */
+#define PMRD_ALT_GREATER 1   /* G-B: stats.py:47-133  1 - cdf(k-1) / binomtest 'greater' */
+
+/* p[i] = test(k[i], n[i], rate[i]).  Poisson: expected = n[i]*rate[i] is formed on the
+ * device exactly as call.py:179 does (one IEEE multiply); pass n=NULL to give `rate`
+ * directly as the expectation.  rate_stride 0 broadcasts rate[0]. */
+int32_t pmrd_pvalues(pmrd_ctx* ctx, const int64_t* h_k, const int64_t* h_n, const double* h_rate,
+                     int64_t rate_stride, int64_t m, int32_t test_type, int32_t alternative,
+                     double* h_p);
+int32_t pmrd_pvalues_dev(pmrd_ctx* ctx, const int64_t* d_k, const int64_t* d_n, const double* d_rate,
+                         int64_t rate_stride, int64_t m, int32_t test_type, int32_t alternative,
+                         double* d_p);
+
+/* ---------------------------------------------------------------- K9: BH FDR -------- */
+/* call.py:41-79 benjamini_hochberg_correction(p_values, alpha) -> (rejected, adjusted).
+ * Device radix sort of the fp64 bit patterns + reverse running-min scan.  m == 0 is ok. */
+int32_t pmrd_bh(pmrd_ctx* ctx, const double* h_p, int64_t m, double alpha, uint8_t* h_rejected,
+                double* h_q);
+int32_t pmrd_bh_dev(pmrd_ctx* ctx, const double* d_p, int64_t m, double alpha, uint8_t* d_rejected,
+                    double* d_q);
+
+/* ---------------------------------------------------------------- K7+K8+K9: call ---- */
+/* Per-sample result of call_mrd (call.py:161-229), one row per segment. */
+typedef struct pmrd_call_table {
+    int64_t* n_variants;       /* [S] sum(is_variant)                      call.py:171 */
+    int64_t* n_total;          /* [S] rows in segment                      call.py:172 */
+    double* variant_fraction;  /* [S] n_variants / n_total                              */
+    double* expected_variants; /* [S] n_total * mean_error_rate            call.py:179 */
+    double* fold_change;       /* [S] k/expected | inf | 1.0               call.py:190 */
+    double* p_value;           /* [S]                                      call.py:182 */
+    double* mean_quality;      /* [S] mean(quality_score)                  call.py:196 */
+    double* mean_consensus;    /* [S] mean(consensus_agreement)            call.py:197 */
+    double* p_adjusted;        /* [S] BH                                   call.py:220 */
+    uint8_t* significant;      /* [S] BH rejected (== variant_call)  */
+} pmrd_call_table;
+
+/* seg_offsets[S+1]: rows of segment s are [seg_offsets[s], seg_offsets[s+1]) -- the
+ * caller groups rows by sample in first-appearance order (call.py:161).  is_variant /
+ * quality / agreement have n_rows = seg_offsets[S] entries.  quality/agreement may be
+ * NULL (means are then NaN).  All table pointers are host (pmrd_call) or device
+ * (pmrd_call_dev) arrays of S entries. */
+int32_t pmrd_call(pmrd_ctx* ctx, const int64_t* h_seg_offsets, int64_t n_segments,
+                  const uint8_t* h_is_variant, const double* h_quality, const double* h_agreement,
+                  double mean_error_rate, int32_t test_type, double alpha, pmrd_call_table* h_out);
+int32_t pmrd_call_dev(pmrd_ctx* ctx, const int64_t* d_seg_offsets, int64_t n_segments,
+                      const uint8_t* d_is_variant, const double* d_quality, const double* d_agreement,
+                      double mean_error_rate, int32_t test_type, double alpha, pmrd_call_table* d_out);
+
+/* ---------------------------------------------------------------- K4: radix sort ---- */
+/* Stable LSD radix sort of (u64 key, u32 value) pairs; digit passes whose digit is
+ * constant over the whole input are skipped.  Exposed because BH, collapse and the
+ * read generator all use it and the tests pin it separately. */
+int32_t pmrd_sort_pairs(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_t* h_vals, int64_t n,
+                        uint64_t* h_keys_out, uint32_t* h_vals_out);
+int32_t pmrd_sort_pairs_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_vals, int64_t n,
+                            uint64_t* d_keys_tmp, uint32_t* d_vals_tmp, int32_t* out_in_tmp);
+
+/* ---------------------------------------------------------------- K4-K7: collapse --- */
+/* Read record (SoA, 12 B):
+ *   key     u64 = group:32 | umi:32      group = dense (sample, locus) code, by convention
+ *                                        sample:12 | locus:20; umi = 2 bit/base, <=16-mer
+ *   payload u32, by mode:
+ *     PMRD_MODE_WEIGHTED  allele[1:0] qual[7:2] strand[8] read_pos[16:9] is_alt[31]
+ *     PMRD_MODE_MAJORITY  sequence[19:0] (10-mer, 2 bit/base, base 0 in the top bits) is_alt[31]
+ *     PMRD_MODE_COUNT     is_alt[31] only
+ */
+#define PMRD_MODE_WEIGHTED 0 /* G-B UMIProcessor.call_consensus       src/precise_mrd/umi.py:146-179, rust_ext/src/lib.rs:25-74 */
+#define PMRD_MODE_MAJORITY 1 /* G-A _consensus_base                   precise-mrd-mini/src/mrd/umi.py:43-54 */
+#define PMRD_MODE_COUNT 2    /* G-C REF/ALT read counts per UMI       test_results/run/collapsed_umis.parquet */
+
+#define PMRD_CLUSTER_EXACT 0    /* exact UMI match   umi.py:111-115, lib.rs:7-22                  */
+#define PMRD_CLUSTER_FIRSTFIT 1 /* first-fit Hamming <= d to the representative  mrd/umi.py:29-40 */
+
+typedef struct pmrd_umi_params {
+    int32_t min_family_size;     /* families below are dropped (after consensus, on raw size: umi.py:181-203) */
+    int32_t max_family_size;     /* > this: reported via the oversize flag (reference down-samples with the global RNG) */
+    int32_t quality_threshold;   /* reads with qual < this do not vote            umi.py:152 */
+    double consensus_threshold;  /* w_best / w_total must be >= this              umi.py:172 */
+    int32_t mode;                /* PMRD_MODE_*                                               */
+    int32_t cluster;             /* PMRD_CLUSTER_*                                            */
+    int32_t max_distance;        /* Hamming radius for FIRSTFIT                               */
+    int32_t umi_len;             /* bases in the UMI (<=16)                                   */
+} pmrd_umi_params;
+
+/* family flags */
+#define PMRD_FAM_HAS_CONSENSUS 1u /* call_consensus returned an allele                  */
+#define PMRD_FAM_KEPT 2u          /* size >= min_family_size                            */
+#define PMRD_FAM_OVERSIZE 4u      /* size > max_family_size                             */
+
+typedef struct pmrd_family_table {
+    uint64_t* key;       /* [F] group:32 | representative umi:32; sorted ascending (EXACT) or
+                            group-sorted then cluster-creation order (FIRSTFIT)           */
+    uint32_t* size;      /* [F] reads in the family                                       */
+    uint32_t* n_alt;     /* [F] reads with is_alt set                                     */
+    uint32_t* consensus; /* [F] WEIGHTED: allele code; MAJORITY: 20-bit consensus sequence */
+    uint32_t* qsum;      /* [F] WEIGHTED: sum of qualities of voting reads that carry the
+                                consensus allele (consensus_quality = qsum / n_best)      */
+    uint32_t* n_best;    /* [F] WEIGHTED: number of those reads                           */
+    uint32_t* flags;     /* [F] PMRD_FAM_*                                                */
+} pmrd_family_table;
+
+typedef struct pmrd_group_table {
+    uint32_t* group;          /* [G] group id (ascending)                                        */
+    uint32_t* family_count;   /* [G] kept families                                               */
+    uint32_t* consensus_count;/* [G*4] WEIGHTED: kept families with consensus allele a (umi.py:241-266) */
+    uint64_t* alt_count;      /* [G] sum n_alt over kept families   (mrd/umi.py:97)              */
+    uint64_t* total_count;    /* [G] sum size over kept families    (mrd/umi.py:98)              */
+} pmrd_group_table;
+
+/* Collapse reads into UMI families and per-group (locus) summaries.
+ *   EXACT:    any input order; reads of a family vote in input order (stable sort).
+ *   FIRSTFIT: reads must arrive with each group's reads in the order the reference's
+ *             groupby would iterate them (input order within group is preserved).
+ * capacity_f / capacity_g: entries available in the output tables; *n_families /
+ * *n_groups receive the counts (PMRD_ERR_CAPACITY if too small; n <= n_reads always
+ * suffices).  The family table lists ALL families (flags tell kept/consensus), so that
+ * the host can apply either generation's filtering order. */
+int32_t pmrd_collapse_reads(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_t* h_payload,
+                            int64_t n_reads, const pmrd_umi_params* params,
+                            pmrd_family_table* h_fam, int64_t capacity_f, int64_t* n_families,
+                            pmrd_group_table* h_grp, int64_t capacity_g, int64_t* n_groups);
+/* Device-resident variant: d_keys/d_payload are clobbered (used as sort ping-pong with
+ * the *_tmp buffers).  n_families/n_groups are host pointers written after a sync. */
+int32_t pmrd_collapse_reads_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload,
+                                uint64_t* d_keys_tmp, uint32_t* d_payload_tmp, int64_t n_reads,
+                                const pmrd_umi_params* params, pmrd_family_table* d_fam,
+                                int64_t capacity_f, int64_t* n_families, pmrd_group_table* d_grp,
+                                int64_t capacity_g, int64_t* n_groups);
+
+/* umi_edit_distance (lib.rs:77-90, umi.py:90-95): Hamming on 2-bit packed UMIs of equal
+ * length.  d[i] = hamming(a[i], b[i]). */
+int32_t pmrd_umi_hamming(pmrd_ctx* ctx, const uint32_t* h_a, const uint32_t* h_b, int64_t n,
+                         int32_t umi_len, int32_t* h_d);
+
+/* ---------------------------------------------------------------- K1: simulate cells */
+/* simulate_reads (src/precise_mrd/simulate.py:133-180): one row per (AF, depth, rep)
+ * cell.  Philox4x32-10 keyed by ctx seed, counter (stream=1, cell, 0, draw).
+ * cell_id[i] is the global cell index (so results are identical under any sharding). */
+typedef struct pmrd_cell_table {
+    double* background_rate;     /* [C] U(1e-5, 1e-3)                     simulate.py:144 */
+    int64_t* mean_family_size;   /* [C] clip(Poisson(5), 1, max_fs)       simulate.py:147-148 */
+    int64_t* n_true_variants;    /* [C] Binom(depth, af)                  simulate.py:152 */
+    int64_t* n_false_positives;  /* [C] Binom(depth - n_true, bg)         simulate.py:155-158 */
+    double* mean_quality;        /* [C] clip(N(25,5), 10, 40)             simulate.py:161-162 */
+} pmrd_cell_table;
+int32_t pmrd_simulate_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
+                            const int64_t* h_depth, int64_t n_cells, int32_t max_family_size,
+                            pmrd_cell_table* h_out);
+
+/* ---------------------------------------------------------------- K2: G-D families -- */
+/* collapse_umis (src/precise_mrd/collapse.py:70-118): per (cell, family) Philox draws.
+ * variant 2 = G-D v2 constants, 1 = G-D v1 ("collapse 2.py").  Rows of cell i are
+ * written contiguously; row_offsets[C+1] (host) receives the CSR offsets.  Pass
+ * h_out == NULL to only count (row_offsets still filled). */
+typedef struct pmrd_gd_family_table {
+    int32_t* cell;          /* [R] index into the input cell arrays                      */
+    int32_t* family_id;     /* [R] family index within the cell (gaps where skipped)     */
+    int32_t* family_size;   /* [R]                                                       */
+    double* quality_score;  /* [R]                                                       */
+    double* consensus_agreement; /* [R]                                                  */
+    uint8_t* flags;         /* [R] bit0 passes_quality, bit1 passes_consensus, bit2 is_variant */
+} pmrd_gd_family_table;
+int32_t pmrd_collapse_families(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
+                               const int64_t* h_n_families, const double* h_background_rate,
+                               const double* h_mean_family_size, int64_t n_cells,
+                               const pmrd_umi_params* params, int32_t variant,
+                               int64_t* h_row_offsets, pmrd_gd_family_table* h_out, int64_t capacity);
+
+/* ---------------------------------------------------------------- K10: error model -- */
+/* fit_error_model (src/precise_mrd/error_model.py:139-186): rate_c = n_var/n_neg *
+ * U(0.5,2) for 64 contexts; CI = percentiles 2.5/97.5 of n_boot binomial-equivalent
+ * bootstrap resamples (Binom(n_neg, n_var/n_neg)/n_neg * modifier).  n_neg <= 10 uses
+ * the reference's (0.5x, 2x) fallback; n_neg == 0 draws U(1e-5,1e-3).  stream_id
+ * separates independent fits (e.g. the cell index in LoD grids). */
+int32_t pmrd_error_model(pmrd_ctx* ctx, int64_t n_neg, int64_t n_var, int32_t n_boot,
+                         uint64_t stream_id, double* h_rate64, double* h_ci_lo64, double* h_ci_hi64);
+
+/* ---------------------------------------------------------------- read-level simulate */
+/* G-B SyntheticReadGenerator.generate_reads_for_site (src/precise_mrd/io.py:79-123)
+ * re-keyed on Philox (seed; stream=3, cell, family, read): family size
+ * NegBinom(r=2, mean)+1 (family_model 0) or clip(Poisson(mean),1,max) (family_model 1),
+ * 12-mer UMI, has_variant ~ Bernoulli(af), optional contamination flip, per-read allele
+ * (0.9 concordance / 0.05 error), quality int(N(30,5)) in [10,40], strand, read_pos in
+ * [10,150).  Index hopping (re-key group bits of Binom(n_reads, hop) reads) and barcode
+ * collisions (re-key UMI bits of Binom(n_families, coll) families onto the previous
+ * family's UMI) implement sim/contamination.py:230-278 at read level.
+ * Reads are emitted tile-shuffled (Philox permutation) so that grouping is real work. */
+typedef struct pmrd_read_sim_params {
+    double mean_family_size;
+    int32_t family_model;       /* 0 negative binomial r=2 (io.py:71-77), 1 Poisson clipped */
+    int32_t max_family_size;
+    double contamination_rate;  /* io.py:100-101 */
+    double hop_rate;            /* contamination.py:230-254 */
+    double collision_rate;      /* contamination.py:256-278 */
+    int32_t shuffle;            /* 0: family-major order; 1: tile-shuffled */
+    int32_t reserved;
+} pmrd_read_sim_params;
+
+/* Counts reads: h_read_offsets[C+1] CSR of reads per cell (family-major layout). */
+int32_t pmrd_simulate_reads_count(pmrd_ctx* ctx, const int64_t* h_cell_id, const int64_t* h_n_families,
+                                  int64_t n_cells, const pmrd_read_sim_params* sp,
+                                  int64_t* h_read_offsets);
+/* Generates reads into device buffers (n_reads = total from the count call).  group id of
+ * cell i = group_base + i. */
+int32_t pmrd_simulate_reads_dev(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
+                                const int64_t* h_n_families, int64_t n_cells, uint32_t group_base,
+                                const pmrd_read_sim_params* sp, uint64_t* d_keys, uint32_t* d_payload,
+                                int64_t capacity, int64_t* n_reads);
+int32_t pmrd_simulate_reads(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
+                            const int64_t* h_n_families, int64_t n_cells, uint32_t group_base,
+                            const pmrd_read_sim_params* sp, uint64_t* h_keys, uint32_t* h_payload,
+                            int64_t capacity, int64_t* n_reads);
+
+/* ---------------------------------------------------------------- fused pipeline ---- */
+/* simulate -> collapse -> call for a batch of cells, reads never leaving the device:
+ * the bench "step" and the engine under eval-lod / eval-lob / eval-contamination.
+ * Per cell: k = kept consensus families carrying the alt allele, n = kept consensus
+ * families; error rate from the negative-control cells (af <= neg_af_max) of the batch
+ * exactly as fit_error_model/call_mrd do (rate = mean over 64 context rates);
+ * p (two-sided Poisson/binomial), BH over the batch. */
+typedef struct pmrd_pipeline_result {
+    int64_t* n_reads;     /* [C] reads generated for the cell                    */
+    int64_t* n_families;  /* [C] families formed (after UMI merging)             */
+    int64_t* n_total;     /* [C] kept consensus families                         */
+    int64_t* n_variants;  /* [C] of which alt                                    */
+    double* p_value;      /* [C]                                                 */
+    double* p_adjusted;   /* [C]                                                 */
+    uint8_t* significant; /* [C]                                                 */
+} pmrd_pipeline_result;
+
+int32_t pmrd_pipeline_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
+                            const int64_t* h_n_families, int64_t n_cells,
+                            const pmrd_read_sim_params* sp, const pmrd_umi_params* up,
+                            double neg_af_max, int32_t test_type, int32_t alternative, double alpha,
+                            pmrd_pipeline_result* h_out, double* h_mean_error_rate);
+
+/* ---------------------------------------------------------------- K11: LoD fit ------ */
+/* LODAnalyzer._fit_detection_curve + _bootstrap_lod_ci (src/precise_mrd/eval/lod.py:
+ * 351-408): 2-parameter logistic on log10(af) by Levenberg-Marquardt from (1,1), solved
+ * at `target`; n_boot Philox resamples of the (af, hit) pairs refit in parallel.
+ * out[0]=lod, out[1]=ci_lo (P2.5), out[2]=ci_hi (P97.5); NaN where the reference is NaN. */
+int32_t pmrd_fit_lod(pmrd_ctx* ctx, const double* h_af, const double* h_hit, int32_t n, double target,
+                     int32_t n_boot, uint64_t stream_id, double* h_out3);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMRD_H */

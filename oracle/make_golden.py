@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE in the build container.
+
+TEST INFRASTRUCTURE ONLY.  Needs /root/reference (absent on the GPU box) and
+``python oracle/build_ref.py`` first.  Outputs are small packed arrays -- inputs in the
+device record layout of include/pmrd.h plus the reference's own outputs -- so the GPU
+parity tests can run where the reference cannot travel.
+
+  call_smoke_v1.npz / call_smoke_v2.npz   reference fixtures data/det_a/smoke, data/smoke/smoke
+                                          (collapsed_umis + error_model -> mrd_calls), re-derived
+                                          here by running the reference call_mrd and checked
+                                          bit-equal to the committed mrd_calls.parquet
+  stats_kat.npz                           poisson_test / binomial_test / BH from call.py on the
+                                          KAT rows + seeded random grids
+  ga_reads.npz                            G-A reads -> mrd.umi.collapse_reads (== tmp/families.parquet)
+  gc_reads.npz                            G-C reads -> committed collapsed_umis / mrd_calls tables
+  gb_reads.npz                            G-B SyntheticReadGenerator reads -> UMIProcessor(max_edit_distance=0)
+  lod_fit.npz                             LODAnalyzer._fit_detection_curve/_bootstrap_lod_ci on given vectors
+  gd_dist.npz                             distribution samples from the reference simulate/collapse (KS targets)
+"""
+from __future__ import annotations
+
+import sys
+import warnings
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+
+HERE = Path(__file__).resolve().parent
+REF = Path("/root/reference")
+OUT = HERE.parent / "tests" / "golden"
+BASE = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def pack_seq(s: str) -> int:
+    v = 0
+    for ch in s:
+        v = (v << 2) | BASE[ch]
+    return v
+
+
+def _import_ref(which: str):
+    for k in [k for k in sys.modules if k == "precise_mrd" or k.startswith("precise_mrd.")]:
+        del sys.modules[k]
+    sys.path[:] = [p for p in sys.path if "/oracle/_ref/" not in p]
+    sys.path.insert(0, str(HERE / "_ref" / "stubs"))
+    sys.path.insert(0, str(HERE / "_ref" / which))
+
+
+# ------------------------------------------------------------------------------- call stage
+def golden_call(which: str, fixture: str, out_name: str) -> None:
+    _import_ref(which)
+    from precise_mrd.call import call_mrd
+    from precise_mrd.config import load_config
+
+    d = REF / "data" / fixture / "smoke"
+    collapsed = pd.read_parquet(d / "collapsed_umis.parquet")
+    em = pd.read_parquet(d / "error_model.parquet")
+    want = pd.read_parquet(d / "mrd_calls.parquet")
+    cfg = load_config(REF / "configs" / "smoke.yaml")
+    cfg.seed = 7
+    got = call_mrd(collapsed, em, cfg, np.random.default_rng(0))
+    for col in ("n_variants", "n_total", "variant_fraction", "expected_variants", "fold_change", "p_value",
+                "mean_quality", "mean_consensus", "p_adjusted", "significant"):
+        assert (got[col].values == want[col].values).all(), (which, col)
+    sid = collapsed["sample_id"].values
+    assert (np.diff(sid) >= 0).all()
+    uniq, start = np.unique(sid, return_index=True)
+    seg = np.concatenate([start, [len(sid)]]).astype(np.int64)
+    np.savez_compressed(
+        OUT / out_name,
+        seg_offsets=seg,
+        sample_id=uniq.astype(np.int64),
+        is_variant=collapsed["is_variant"].values.astype(np.uint8),
+        quality=collapsed["quality_score"].values,
+        agreement=collapsed["consensus_agreement"].values,
+        allele_fraction=want["allele_fraction"].values,
+        error_rate=em["error_rate"].values,
+        mean_error_rate=np.float64(em["error_rate"].mean()),
+        alpha=np.float64(0.05),
+        **{f"want_{c}": want[c].values for c in ("n_variants", "n_total", "variant_fraction", "expected_variants",
+                                                  "fold_change", "p_value", "mean_quality", "mean_consensus",
+                                                  "p_adjusted", "significant")},
+    )
+    print("  wrote", out_name, len(sid), "rows", len(uniq), "samples")
+
+
+def golden_stats() -> None:
+    _import_ref("gd_v1")
+    from precise_mrd.call import benjamini_hochberg_correction, binomial_test, poisson_test
+
+    rng = np.random.default_rng(20240901)
+    # Poisson: KAT rows + grid across 1e-4 .. 2e5 expectations, deep tails both sides
+    pk = [5, 1, 5, 0, 10, 0, 3, 100, 0]
+    pe = [1.0, 5.0, 5.0, 0.0, 0.1, -1.0, 1e-4, 1e-3, 1e5]
+    m = 3000
+    e = 10 ** rng.uniform(-4, 5.3, m)
+    k = np.maximum(0, np.round(e + rng.normal(0, 1, m) * np.sqrt(e) * rng.choice([0.3, 1, 3, 8, 20], m))).astype(np.int64)
+    k[:300] = rng.integers(0, 30, 300)
+    pk = np.concatenate([np.array(pk, np.int64), k])
+    pe = np.concatenate([np.array(pe, float), e])
+    pp = np.array([poisson_test(int(a), float(b)) for a, b in zip(pk, pe)])
+    # binomial
+    bk = [10, 1, 10, 0, 0, 1, 10, 9, 0, 5]
+    bn = [100, 100, 100, 0, 10, 10, 10, 10, 1, 5]
+    bp = [0.01, 0.1, 0.1, 0.5, 0.0, 0.0, 1.0, 1.0, 0.5, 0.5]
+    m = 2500
+    n = (10 ** rng.uniform(0, 5.2, m)).astype(np.int64)
+    pr = 10 ** rng.uniform(-5, -0.01, m)
+    mu = n * pr
+    kk = np.clip(np.round(mu + rng.normal(0, 1, m) * np.sqrt(mu * (1 - pr) + 0.3) * rng.choice([0.3, 1, 3, 8], m)), 0, n).astype(np.int64)
+    bk = np.concatenate([np.array(bk, np.int64), kk])
+    bn = np.concatenate([np.array(bn, np.int64), n])
+    bp = np.concatenate([np.array(bp, float), pr])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bpv = np.array([binomial_test(int(a), int(b), float(c)) for a, b, c in zip(bk, bn, bp)])
+    # BH cases: KAT, ties, all-ones, all-zeros, single, random sizes
+    cases = [np.array([0.001, 0.005, 0.01, 0.03, 0.05, 0.1]), np.array([0.5]), np.ones(7), np.zeros(5),
+             np.array([0.04, 0.04, 0.04, 0.9, 0.9]), np.array([1e-300, 0.0, 1.0, 0.049999, 0.05])]
+    for size in (2, 17, 60, 257, 5000, 20000):
+        p = rng.uniform(0, 1, size) ** rng.choice([1, 3, 8])
+        p[rng.integers(0, size, size // 10)] = 1.0
+        if size > 10:
+            p[rng.integers(0, size, size // 10)] = p[0]
+        cases.append(p)
+    alphas = [0.05, 0.05, 0.05, 0.05, 0.05, 0.05, 0.05, 0.1, 0.05, 0.01, 0.05, 0.2]
+    bh = {}
+    for i, (p, a) in enumerate(zip(cases, alphas)):
+        rej, adj = benjamini_hochberg_correction(p, a)
+        bh[f"bh{i}_p"] = p
+        bh[f"bh{i}_alpha"] = np.float64(a)
+        bh[f"bh{i}_rej"] = rej
+        bh[f"bh{i}_adj"] = adj
+    np.savez_compressed(OUT / "stats_kat.npz", pois_k=pk, pois_e=pe, pois_p=pp, bin_k=bk, bin_n=bn, bin_p=bp,
+                        bin_pv=bpv, n_bh=np.int64(len(cases)), **bh)
+    print("  wrote stats_kat.npz", len(pk), "poisson", len(bk), "binomial", len(cases), "BH cases")
+
+
+# ------------------------------------------------------------------------------- G-A
+def golden_ga() -> None:
+    sys.path.insert(0, str(HERE / "_ref" / "ga"))
+    from mrd.umi import collapse_reads
+
+    reads = pd.read_parquet(REF / "precise-mrd-mini" / "simulated_reads" / "reads.parquet")
+    fam, loc = collapse_reads(reads, min_family_size=2, max_distance=1)
+    want_f = pd.read_parquet(REF / "precise-mrd-mini" / "tmp" / "families.parquet")
+    want_l = pd.read_parquet(REF / "precise-mrd-mini" / "tmp" / "collapsed.parquet")
+    for c in want_f.columns:
+        assert (fam[c].astype(want_f[c].dtype).values == want_f[c].values).all(), c
+    for c in ("alt_count", "total_count", "family_count"):
+        assert (loc[c].values == want_l[c].values).all(), c
+    # groups = sorted (chrom, start, pos) -- pandas groupby order (mrd/umi.py:65)
+    gkeys = sorted(set(zip(reads.chrom, reads.start, reads.pos)))
+    gid = {g: i for i, g in enumerate(gkeys)}
+    g = np.array([gid[t] for t in zip(reads.chrom, reads.start, reads.pos)], np.uint64)
+    umi = np.array([pack_seq(u) for u in reads.umi], np.uint64)
+    keys = (g << np.uint64(32)) | umi
+    payload = np.array([pack_seq(s) for s in reads.sequence], np.uint32) | (reads.true_alt.values.astype(np.uint32) << np.uint32(31))
+    fg = np.array([gid[t] for t in zip(fam.chrom, fam.start, fam.pos)], np.uint64)
+    loci = sorted(set(zip(reads.chrom, reads.pos)))
+    lid = {l: i for i, l in enumerate(loci)}
+    np.savez_compressed(
+        OUT / "ga_reads.npz",
+        keys=keys, payload=payload,
+        group_locus=np.array([lid[(c, p)] for (c, s, p) in gkeys], np.int64),
+        want_fam_key=(fg << np.uint64(32)) | np.array([pack_seq(u) for u in fam.umi_representative], np.uint64),
+        want_fam_size=fam.family_size.values.astype(np.uint32),
+        want_fam_alt=fam.alt_count.values.astype(np.uint32),
+        want_fam_consensus=np.array([pack_seq(s) for s in fam.consensus], np.uint32),
+        want_locus=np.array([lid[(c, p)] for c, p in zip(loc.chrom, loc.pos)], np.int64),
+        want_locus_alt=loc.alt_count.values.astype(np.int64),
+        want_locus_total=loc.total_count.values.astype(np.int64),
+        want_locus_families=loc.family_count.values.astype(np.int64),
+    )
+    print("  wrote ga_reads.npz", len(keys), "reads", len(fam), "families", len(loc), "loci")
+
+
+# ------------------------------------------------------------------------------- G-C
+def golden_gc() -> None:
+    d = REF / "test_results" / "run"
+    reads = pd.read_parquet(d / "simulated_reads.parquet")
+    fam = pd.read_parquet(d / "collapsed_umis.parquet")
+    calls = pd.read_parquet(d / "mrd_calls.parquet")
+    gk = sorted(set(zip(reads.sample_id, reads.variant_id, reads.depth)))
+    gid = {g: i for i, g in enumerate(gk)}
+    g = np.array([gid[t] for t in zip(reads.sample_id, reads.variant_id, reads.depth)], np.uint64)
+    umi = np.array([int(u[3:]) for u in reads.umi_id], np.uint64)
+    keys = (g << np.uint64(32)) | umi
+    payload = (reads.allele.values == "ALT").astype(np.uint32) << np.uint32(31)
+    # shuffle reads: grouping must not depend on arrival order
+    perm = np.random.default_rng(5).permutation(len(keys))
+    fk = (np.array([gid[t] for t in zip(fam.sample_id, fam.variant_id, fam.depth)], np.uint64) << np.uint64(32)) | \
+        np.array([int(u[3:]) for u in fam.umi_id], np.uint64)
+    assert (calls.umi_id.values == fam.umi_id.values).all()
+    np.savez_compressed(
+        OUT / "gc_reads.npz", keys=keys[perm], payload=payload[perm],
+        want_fam_key=fk, want_ref=fam.ref_reads.values.astype(np.uint32), want_alt=fam.alt_reads.values.astype(np.uint32),
+        want_size=fam.family_size.values.astype(np.uint32),
+        call_alt=calls.alt_reads.values.astype(np.int64), call_total=calls.total_reads.values.astype(np.int64),
+        call_pvalue=calls.pvalue.values, call_detected=calls.detected.values,
+    )
+    print("  wrote gc_reads.npz", len(keys), "reads", len(fam), "families")
+
+
+# ------------------------------------------------------------------------------- G-B
+def golden_gb() -> None:
+    sys.path.insert(0, str(HERE / "_ref" / "gb"))
+    from precise_mrd_gb.io import SyntheticReadGenerator
+    from precise_mrd_gb.umi import UMIProcessor
+
+    gen = SyntheticReadGenerator(seed=11)
+    sites = gen.generate_target_sites(24)
+    reads = []
+    afs = [0.0, 0.01, 0.05, 0.2, 0.5, 0.9]
+    for i, s in enumerate(sites):
+        reads += gen.generate_reads_for_site(s, n_umi_families=400, allele_fraction=afs[i % 6],
+                                             contamination_rate=0.01 if i % 5 == 0 else 0.0, mean_family_size=5.0)
+    order = np.random.default_rng(3).permutation(len(reads))
+    reads = [reads[i] for i in order]
+    # a low-quality-heavy tail so the quality filter and the consensus threshold both bite
+    for r in reads[::7]:
+        r.quality = max(10, r.quality - 12)
+    proc = UMIProcessor(min_family_size=3, max_family_size=1000, max_edit_distance=0, quality_threshold=20,
+                        consensus_threshold=0.6)
+    # all families before the size filter (process_reads minus filter_family_size, umi.py:205-239)
+    site_groups = proc.group_umis_by_site(reads)
+    fams = []
+    for site_key, site_reads in site_groups.items():
+        for umi_reads in proc.group_umis_with_distance(site_reads):
+            ca, cq = proc.call_consensus(umi_reads)
+            fams.append((site_key, umi_reads[0].umi, len(umi_reads), ca, cq))
+    kept = proc.process_reads(reads)
+    counts = proc.get_consensus_counts(kept)
+    skeys = list(site_groups.keys())
+    sid = {k: i for i, k in enumerate(skeys)}
+    site_alt = {f"{s.chrom}:{s.pos}:{s.ref}": s.alt for s in sites}
+    g = np.array([sid[f"{r.chrom}:{r.pos}:{r.ref}"] for r in reads], np.uint64)
+    keys = (g << np.uint64(32)) | np.array([pack_seq(r.umi) for r in reads], np.uint64)
+    payload = np.array([
+        BASE[r.alt] | (r.quality << 2) | ((1 if r.strand == "+" else 0) << 8) | (r.read_position << 9) |
+        ((1 if r.alt == site_alt[f"{r.chrom}:{r.pos}:{r.ref}"] else 0) << 31) for r in reads], np.uint64).astype(np.uint32)
+    cc = np.zeros((len(skeys), 4), np.int64)
+    for _, row in counts.iterrows():
+        cc[sid[row.site_key], BASE[row.allele]] = row.consensus_count
+    np.savez_compressed(
+        OUT / "gb_reads.npz", keys=keys, payload=payload,
+        want_fam_key=(np.array([sid[f[0]] for f in fams], np.uint64) << np.uint64(32)) | np.array([pack_seq(f[1]) for f in fams], np.uint64),
+        want_fam_size=np.array([f[2] for f in fams], np.uint32),
+        want_fam_allele=np.array([-1 if f[3] is None else BASE[f[3]] for f in fams], np.int32),
+        want_fam_quality=np.array([np.nan if f[4] is None else f[4] for f in fams], np.float64),
+        want_kept=np.int64(len(kept)),
+        want_consensus_count=cc,
+        site_alt=np.array([BASE[site_alt[k]] for k in skeys], np.int32),
+        params=np.array([3, 1000, 20], np.int64), consensus_threshold=np.float64(0.6),
+    )
+    print("  wrote gb_reads.npz", len(reads), "reads", len(fams), "families", len(kept), "kept")
+
+
+# ------------------------------------------------------------------------------- LoD fit
+def golden_lod_fit() -> None:
+    _import_ref("gd_v1")
+    from precise_mrd.config import load_config
+    from precise_mrd.eval.lod import LODAnalyzer
+
+    cfg = load_config(REF / "configs" / "smoke.yaml")
+    af = np.logspace(-4, -2, 15)
+    curves = {
+        "mid": [0, 0, 0, 0, 0, .04, 0, .08, .2, .4, .6, .8, .92, 1, 1],
+        "steep": [0, 0, 0, 0, 0, 0, 0, 0, .04, .52, .96, 1, 1, 1, 1],
+        "shallow": [.04, .08, .08, .16, .2, .28, .4, .44, .56, .6, .72, .8, .84, .92, .96],
+        "zeros": [0] * 15,
+        "ones": [1] * 15,
+    }
+    out = {"af": af}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, hit in curves.items():
+            an = LODAnalyzer(cfg, np.random.default_rng(123))
+            lod = an._fit_detection_curve(list(af), list(hit), 0.95)
+            ci = an._bootstrap_lod_ci(list(af), list(hit), 0.95, n_bootstrap=200)
+            out[f"{name}_hit"] = np.array(hit, float)
+            out[f"{name}_lod"] = np.float64(lod)
+            out[f"{name}_ci"] = np.array(ci, float)
+            print("   ", name, lod, ci)
+    np.savez_compressed(OUT / "lod_fit.npz", **out)
+    print("  wrote lod_fit.npz")
+
+
+# ------------------------------------------------------------------------------- distributions
+def golden_gd_dist() -> None:
+    """Samples of the reference's G-D generator outputs: targets of the KS / chi-square gate."""
+    out = {}
+    for which in ("gd_v1", "gd_v2"):
+        _import_ref(which)
+        from precise_mrd.collapse import collapse_umis
+        from precise_mrd.config import LODConfig, PipelineConfig, SimulationConfig, StatsConfig, UMIConfig
+        from precise_mrd.simulate import simulate_reads
+
+        cfg = PipelineConfig(run_id="dist", seed=1, simulation=SimulationConfig([0.02, 0.001, 0.0001], [4000], 8, 10),
+                             umi=UMIConfig(3, 1000, 20, 0.6), stats=StatsConfig("poisson", 0.05, "benjamini_hochberg"),
+                             lod=LODConfig(0.95, 0.95))
+        rng = np.random.default_rng(99)
+        kw = {"use_cache": False} if which == "gd_v2" else {}
+        reads = simulate_reads(cfg, rng, **kw)
+        col = collapse_umis(reads, cfg, rng)
+        tag = which[-2:]
+        out[f"{tag}_cell_af"] = reads.allele_fraction.values
+        out[f"{tag}_cell_bg"] = reads.background_rate.values
+        out[f"{tag}_cell_mfs"] = reads.mean_family_size.values.astype(float)
+        out[f"{tag}_cell_ntrue"] = reads.n_true_variants.values
+        out[f"{tag}_cell_nfp"] = reads.n_false_positives.values
+        out[f"{tag}_cell_mq"] = reads.mean_quality.values
+        out[f"{tag}_sample"] = col.sample_id.values.astype(np.int32)
+        out[f"{tag}_family_size"] = col.family_size.values.astype(np.int32)
+        out[f"{tag}_quality"] = col.quality_score.values.astype(np.float32)
+        out[f"{tag}_agreement"] = col.consensus_agreement.values.astype(np.float32)
+        out[f"{tag}_flags"] = (col.passes_quality.values.astype(np.uint8) | (col.passes_consensus.values.astype(np.uint8) << 1) |
+                               (col.is_variant.values.astype(np.uint8) << 2))
+        print("   ", which, len(reads), "cells", len(col), "families")
+    np.savez_compressed(OUT / "gd_dist.npz", **out)
+    print("  wrote gd_dist.npz")
+
+
+def main() -> int:
+    if not REF.exists():
+        print("reference not present; golden vectors cannot be regenerated here")
+        return 1
+    OUT.mkdir(parents=True, exist_ok=True)
+    only = set(sys.argv[1:])
+    steps = {
+        "call": lambda: (golden_call("gd_v1", "det_a", "call_smoke_v1.npz"), golden_call("gd_v2", "smoke", "call_smoke_v2.npz")),
+        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "lod": golden_lod_fit,
+        "dist": golden_gd_dist,
+    }
+    for name, fn in steps.items():
+        if only and name not in only:
+            continue
+        print("[make_golden]", name)
+        fn()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

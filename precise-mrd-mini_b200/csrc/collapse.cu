@@ -1,0 +1,440 @@
+// collapse.cu -- K4..K7 for the read-level path: group reads into UMI families, vote a
+// consensus per family, summarise per (sample, locus) group.
+//
+//   grouping   : stable radix sort of the packed key (radix_sort.cu); EXACT UMI match
+//                (src/precise_mrd/umi.py:111-115, rust_ext/src/lib.rs:7-22) or first-fit
+//                Hamming clustering to the representative (precise-mrd-mini/src/mrd/umi.py:29-40)
+//   consensus  : WEIGHTED  = quality-weighted vote w = 10^(q/10)       (umi.py:146-179, lib.rs:25-74)
+//                MAJORITY  = per-column majority, first-seen wins ties  (mrd/umi.py:43-54)
+//                COUNT     = REF/ALT read counts per UMI                (G-C fixture)
+//   filter     : min/max family size on the RAW read count, after consensus (umi.py:181-203)
+//   group table: kept families, consensus counts per allele (umi.py:241-266), alt/total reads
+//                (mrd/umi.py:86-99)
+//
+// Bit-exactness: the reference accumulates fp64 weights sequentially in read order
+// (umi.py:161-164); the sort is stable, one thread walks one family in that order with
+// the same IEEE additions, and the weight table is computed on the host with the same
+// libm pow() Python uses, so the >= consensus_threshold decision is identical.
+#include "kernels.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+__constant__ double c_wtab[64];  // 10^(q/10), q = 0..63
+
+int32_t collapse_upload_weights(pmrd_ctx* ctx, const double* h_w64) {
+    PMRD_CUDA(ctx, cudaMemcpyToSymbolAsync(c_wtab, h_w64, 64 * sizeof(double), 0, cudaMemcpyHostToDevice, ctx->stream));
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- segments --------------
+#define SEG_THREADS 256
+#define SEG_ITEMS 8
+#define SEG_TILE (SEG_THREADS * SEG_ITEMS)
+
+__device__ __forceinline__ bool seg_is_head(const uint64_t* __restrict__ keys, int64_t i, int shift) {
+    return i == 0 || (keys[i] >> shift) != (keys[i - 1] >> shift);
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_count_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ tile_heads) {
+    __shared__ uint32_t sw[SEG_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * SEG_TILE;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < SEG_ITEMS; ++j) {
+        const int64_t i = base + j * SEG_THREADS + threadIdx.x;
+        if (i < n) c += seg_is_head(keys, i, shift) ? 1u : 0u;
+    }
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SEG_THREADS / 32; ++w) t += sw[w];
+        tile_heads[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(SEG_THREADS)
+seg_write_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, const uint32_t* __restrict__ tile_base,
+                 const uint32_t* __restrict__ total, uint32_t* __restrict__ seg_start) {
+    __shared__ uint32_t sw[33];
+    // blocked arrangement so that ranks follow memory order
+    const int64_t base = (int64_t)blockIdx.x * SEG_TILE + (int64_t)threadIdx.x * SEG_ITEMS;
+    uint32_t flags = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < SEG_ITEMS; ++j) {
+        const int64_t i = base + j;
+        if (i < n && seg_is_head(keys, i, shift)) {
+            flags |= 1u << j;
+            ++c;
+        }
+    }
+    uint32_t tot;
+    uint32_t r = tile_base[blockIdx.x] + block_exclusive_scan<uint32_t>(c, sw, tot);
+#pragma unroll
+    for (int j = 0; j < SEG_ITEMS; ++j)
+        if (flags & (1u << j)) seg_start[r++] = (uint32_t)(base + j);
+    if (blockIdx.x == 0 && threadIdx.x == 0) seg_start[*total] = (uint32_t)n;
+}
+
+// seg_start must hold n+1 entries in the worst case; *h_nseg is written after a sync.
+static int32_t find_segments(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, int shift, uint32_t* d_seg_start,
+                             int64_t* h_nseg) {
+    *h_nseg = 0;
+    if (n <= 0) return PMRD_OK;
+    const int n_tiles = (int)((n + SEG_TILE - 1) / SEG_TILE);
+    DevBuf th, tot;
+    PMRD_CUDA(ctx, th.alloc(ctx->stream, (size_t)n_tiles * 4));
+    PMRD_CUDA(ctx, tot.alloc(ctx->stream, 4));
+    PMRD_LAUNCH(ctx, seg_count_kernel, n_tiles, SEG_THREADS, 0, d_keys, n, shift, th.as<uint32_t>());
+    PMRD_TRY((exclusive_scan<uint32_t, uint32_t>(ctx, th.as<uint32_t>(), th.as<uint32_t>(), n_tiles, tot.as<uint32_t>())));
+    PMRD_LAUNCH(ctx, seg_write_kernel, n_tiles, SEG_THREADS, 0, d_keys, n, shift, (const uint32_t*)th.as<uint32_t>(),
+                (const uint32_t*)tot.as<uint32_t>(), d_seg_start);
+    uint32_t h = 0;
+    PMRD_CUDA(ctx, cudaMemcpyAsync(&h, tot.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *h_nseg = h;
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- K5 consensus ----------
+struct FamOut {
+    uint64_t* key;
+    uint32_t *size, *n_alt, *consensus, *qsum, *n_best, *flags;
+};
+
+template <int MODE, bool GATHER>
+__global__ void __launch_bounds__(128)
+family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload_or_idx,
+              const uint64_t* __restrict__ keys_orig, const uint32_t* __restrict__ payload_orig,
+              const uint32_t* __restrict__ fam_start, int64_t n_fam, pmrd_umi_params P, FamOut out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= n_fam) return;
+    const uint32_t lo = fam_start[f], hi = fam_start[f + 1];
+    const uint32_t size = hi - lo;
+    uint64_t key = keys[lo];
+    if (GATHER) key = (key & 0xffffffff00000000ull) | (keys_orig[payload_or_idx[lo]] & 0xffffffffull);
+
+    uint32_t n_alt = 0, consensus = 0, qsum_best = 0, n_best = 0, flags = 0;
+
+    if (MODE == PMRD_MODE_WEIGHTED) {
+        double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, total = 0.0;
+        uint32_t qs0 = 0, qs1 = 0, qs2 = 0, qs3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+        uint32_t order = 0, seen = 0, n_seen = 0;  // order: 2 bits per allele = rank of first appearance
+        for (uint32_t r = lo; r < hi; ++r) {
+            const uint32_t pl = GATHER ? payload_orig[payload_or_idx[r]] : payload_or_idx[r];
+            n_alt += pl >> 31;
+            const uint32_t a = pl & 3u, q = (pl >> 2) & 63u;
+            if ((int)q >= P.quality_threshold) {
+                const double w = c_wtab[q];
+                // same sequential IEEE additions as umi.py:161-164
+                w0 = __dadd_rn(w0, a == 0 ? w : 0.0);
+                w1 = __dadd_rn(w1, a == 1 ? w : 0.0);
+                w2 = __dadd_rn(w2, a == 2 ? w : 0.0);
+                w3 = __dadd_rn(w3, a == 3 ? w : 0.0);
+                total = __dadd_rn(total, w);
+                qs0 += a == 0 ? q : 0; qs1 += a == 1 ? q : 0; qs2 += a == 2 ? q : 0; qs3 += a == 3 ? q : 0;
+                c0 += a == 0; c1 += a == 1; c2 += a == 2; c3 += a == 3;
+                if (!((seen >> a) & 1u)) {
+                    seen |= 1u << a;
+                    order |= n_seen << (2 * a);
+                    ++n_seen;
+                }
+            }
+        }
+        if (n_seen > 0) {
+            // max(allele_weights, key=allele_weights.get): first-inserted wins ties (dict order)
+            int best = -1;
+            double bw = -1.0;
+            uint32_t brank = 4;
+            const double ws[4] = {w0, w1, w2, w3};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (!((seen >> a) & 1u)) continue;
+                const uint32_t rk = (order >> (2 * a)) & 3u;
+                if (ws[a] > bw || (ws[a] == bw && rk < brank)) {
+                    bw = ws[a];
+                    best = a;
+                    brank = rk;
+                }
+            }
+            const double frac = __ddiv_rn(bw, total);
+            if (total != 0.0 && !(frac < P.consensus_threshold)) {
+                flags |= PMRD_FAM_HAS_CONSENSUS;
+                consensus = (uint32_t)best;
+                const uint32_t qs[4] = {qs0, qs1, qs2, qs3}, cs[4] = {c0, c1, c2, c3};
+                qsum_best = qs[best];
+                n_best = cs[best];
+            }
+        }
+    } else if (MODE == PMRD_MODE_MAJORITY) {
+        // per column: 4 x 16-bit counters packed in a u64, first-seen ranks in a u32
+        uint64_t cnt[10];
+        uint32_t ord[10];
+#pragma unroll
+        for (int c = 0; c < 10; ++c) { cnt[c] = 0; ord[c] = 0; }
+        for (uint32_t r = lo; r < hi; ++r) {
+            const uint32_t pl = GATHER ? payload_orig[payload_or_idx[r]] : payload_or_idx[r];
+            n_alt += pl >> 31;
+#pragma unroll
+            for (int c = 0; c < 10; ++c) {
+                const uint32_t b = (pl >> (18 - 2 * c)) & 3u;  // base c, base 0 in the top bits
+                const uint64_t old = (cnt[c] >> (16 * b)) & 0xffffull;
+                if (old == 0) {
+                    // ord[c]: bits [7:0] ranks (2 bits per base), bits [10:8] = number seen
+                    const uint32_t ns = (ord[c] >> 8) & 7u;
+                    ord[c] = (ord[c] & ~(0x700u)) | ((ns + 1) << 8) | (ns << (2 * b));
+                }
+                if (old < 0xffffull) cnt[c] += 1ull << (16 * b);
+            }
+        }
+        uint32_t seq = 0;
+#pragma unroll
+        for (int c = 0; c < 10; ++c) {
+            uint32_t best = 0, bc = 0, brank = 4;
+#pragma unroll
+            for (uint32_t b = 0; b < 4; ++b) {
+                const uint32_t cb = (uint32_t)((cnt[c] >> (16 * b)) & 0xffffull);
+                const uint32_t rk = (ord[c] >> (2 * b)) & 3u;
+                if (cb > bc || (cb == bc && cb > 0 && rk < brank)) {
+                    bc = cb;
+                    best = b;
+                    brank = rk;
+                }
+            }
+            seq |= best << (18 - 2 * c);
+        }
+        consensus = seq;
+        flags |= PMRD_FAM_HAS_CONSENSUS;
+    } else {
+        for (uint32_t r = lo; r < hi; ++r) {
+            const uint32_t pl = GATHER ? payload_orig[payload_or_idx[r]] : payload_or_idx[r];
+            n_alt += pl >> 31;
+        }
+        flags |= PMRD_FAM_HAS_CONSENSUS;
+    }
+    if ((int64_t)size >= (int64_t)P.min_family_size) flags |= PMRD_FAM_KEPT;
+    if ((int64_t)size > (int64_t)P.max_family_size) flags |= PMRD_FAM_OVERSIZE;
+    out.key[f] = key;
+    out.size[f] = size;
+    out.n_alt[f] = n_alt;
+    out.consensus[f] = consensus;
+    out.qsum[f] = qsum_best;
+    out.n_best[f] = n_best;
+    out.flags[f] = flags;
+}
+
+// ---------------------------------------------------------------- K7 group table --------
+__global__ void __launch_bounds__(128)
+group_kernel(const uint64_t* __restrict__ fam_key, const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_nalt,
+             const uint32_t* __restrict__ fam_cons, const uint32_t* __restrict__ fam_flags,
+             const uint32_t* __restrict__ grp_start, int64_t n_groups, int weighted, pmrd_group_table G) {
+    __shared__ unsigned long long s[4][8];  // [warp][fc, alt, tot, c0..c3]
+    for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const uint32_t lo = grp_start[g], hi = grp_start[g + 1];
+        unsigned long long fc = 0, alt = 0, tot = 0, c[4] = {0, 0, 0, 0};
+        for (uint32_t f = lo + threadIdx.x; f < hi; f += blockDim.x) {
+            const uint32_t fl = fam_flags[f];
+            if (fl & PMRD_FAM_KEPT) {
+                ++fc;
+                alt += fam_nalt[f];
+                tot += fam_size[f];
+                if (weighted && (fl & PMRD_FAM_HAS_CONSENSUS)) {
+                    const uint32_t a = fam_cons[f] & 3u;
+                    c[0] += a == 0; c[1] += a == 1; c[2] += a == 2; c[3] += a == 3;
+                }
+            }
+        }
+        fc = warp_sum(fc); alt = warp_sum(alt); tot = warp_sum(tot);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) c[a] = warp_sum(c[a]);
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) {
+            s[w][0] = fc; s[w][1] = alt; s[w][2] = tot;
+            s[w][3] = c[0]; s[w][4] = c[1]; s[w][5] = c[2]; s[w][6] = c[3];
+        }
+        __syncthreads();
+        if (threadIdx.x < 7) {
+            unsigned long long v = 0;
+            for (int ww = 0; ww < 4; ++ww) v += s[ww][threadIdx.x];
+            if (threadIdx.x == 0) { G.family_count[g] = (uint32_t)v; G.group[g] = (uint32_t)(fam_key[lo] >> 32); }
+            else if (threadIdx.x == 1) G.alt_count[g] = v;
+            else if (threadIdx.x == 2) G.total_count[g] = v;
+            else G.consensus_count[g * 4 + (threadIdx.x - 3)] = (uint32_t)v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- K6 first-fit ----------
+__device__ __forceinline__ int umi_hamming(uint32_t a, uint32_t b) {
+    const uint32_t x = a ^ b;
+    return __popc((x | (x >> 1)) & 0x55555555u);
+}
+
+__global__ void __launch_bounds__(256) hamming_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int64_t n, int32_t* __restrict__ d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = umi_hamming(a[i], b[i]);
+}
+
+// One warp per group.  Reads are visited in input order; a read joins the FIRST cluster
+// whose representative (the UMI that opened it) is within max_distance, else opens a new
+// one (mrd/umi.py:29-40).  reps[] (scratch, n entries) holds each group's representatives
+// in its own [lo,hi) slice.  Writes new sort keys group:32 | cluster index.
+__global__ void __launch_bounds__(128)
+firstfit_kernel(const uint64_t* __restrict__ keys_sorted_by_group, const uint32_t* __restrict__ idx,
+                const uint64_t* __restrict__ keys_orig, const uint32_t* __restrict__ grp_start, int64_t n_groups,
+                int max_distance, uint32_t* __restrict__ reps, uint64_t* __restrict__ keys_out) {
+    const int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (g >= n_groups) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lo = grp_start[g], hi = grp_start[g + 1];
+    const uint64_t ghi = keys_sorted_by_group[lo] & 0xffffffff00000000ull;
+    uint32_t n_rep = 0;
+    for (uint32_t r = lo; r < hi; ++r) {
+        const uint32_t umi = (uint32_t)keys_orig[idx[r]];
+        uint32_t found = 0xffffffffu;
+        for (uint32_t c0 = 0; c0 < n_rep; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            const bool hit = c < n_rep && umi_hamming(umi, reps[lo + c]) <= max_distance;
+            const uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                found = c0 + (uint32_t)__ffs((int)m) - 1u;
+                break;
+            }
+        }
+        if (found == 0xffffffffu) {
+            found = n_rep;
+            if (lane == 0) reps[lo + n_rep] = umi;
+            ++n_rep;
+            __syncwarp();
+        }
+        if (lane == 0) keys_out[r] = ghi | found;
+    }
+}
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t* __restrict__ v, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+__global__ void __launch_bounds__(256) groupkey_kernel(const uint64_t* __restrict__ k, uint64_t* __restrict__ o, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = k[i] & 0xffffffff00000000ull;
+}
+
+int32_t k6_hamming(pmrd_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, int64_t n, int32_t* d_d) {
+    if (n <= 0) return PMRD_OK;
+    PMRD_LAUNCH(ctx, hamming_kernel, pmrd_blocks(n, 256), 256, 0, d_a, d_b, n, d_d);
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- driver ----------------
+template <bool GATHER>
+static int32_t launch_family(pmrd_ctx* ctx, int mode, const uint64_t* keys, const uint32_t* pl_or_idx,
+                             const uint64_t* keys_orig, const uint32_t* payload_orig, const uint32_t* fam_start,
+                             int64_t n_fam, const pmrd_umi_params& P, FamOut out) {
+    const int grid = pmrd_blocks(n_fam, 128);
+    if (mode == PMRD_MODE_WEIGHTED) {
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_WEIGHTED, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, n_fam, P, out);
+    } else if (mode == PMRD_MODE_MAJORITY) {
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_MAJORITY, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, n_fam, P, out);
+    } else {
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_COUNT, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, n_fam, P, out);
+    }
+    return PMRD_OK;
+}
+
+int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp, uint32_t* d_payload_tmp,
+                    int64_t n_reads, const pmrd_umi_params* params, const pmrd_family_table* d_fam, int64_t capacity_f,
+                    int64_t* n_families, const pmrd_group_table* d_grp, int64_t capacity_g, int64_t* n_groups) {
+    PMRD_ARG(ctx, params != nullptr, "params");
+    const pmrd_umi_params P = *params;
+    PMRD_ARG(ctx, P.mode >= 0 && P.mode <= 2, "mode");
+    PMRD_ARG(ctx, P.cluster == PMRD_CLUSTER_EXACT || P.cluster == PMRD_CLUSTER_FIRSTFIT, "cluster");
+    PMRD_ARG(ctx, ((uintptr_t)d_keys & 15) == 0 && ((uintptr_t)d_keys_tmp & 15) == 0, "key buffers must be 16-byte aligned");
+    *n_families = 0;
+    if (n_groups) *n_groups = 0;
+    if (n_reads <= 0) return PMRD_OK;
+    PMRD_ARG(ctx, n_reads < (1ll << 31), "n_reads must be < 2^31 per call (chunk the input)");
+
+    DevBuf fam_start;
+    PMRD_CUDA(ctx, fam_start.alloc(ctx->stream, (size_t)(n_reads + 1) * 4));
+    FamOut out{d_fam->key, d_fam->size, d_fam->n_alt, d_fam->consensus, d_fam->qsum, d_fam->n_best, d_fam->flags};
+    int64_t nf = 0;
+
+    if (P.cluster == PMRD_CLUSTER_EXACT) {
+        uint64_t varying = 0;
+        PMRD_TRY(radix_varying_bits(ctx, d_keys, n_reads, &varying));
+        int in_b = 0;
+        PMRD_TRY(radix_sort_pairs(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, varying, &in_b));
+        const uint64_t* sk = in_b ? d_keys_tmp : d_keys;
+        const uint32_t* sp = in_b ? d_payload_tmp : d_payload;
+        PMRD_TRY(find_segments(ctx, sk, n_reads, 0, fam_start.as<uint32_t>(), &nf));
+        if (nf > capacity_f) {
+            snprintf(ctx->err, sizeof(ctx->err), "family capacity %lld < %lld families", (long long)capacity_f, (long long)nf);
+            *n_families = nf;
+            return PMRD_ERR_CAPACITY;
+        }
+        PMRD_TRY(launch_family<false>(ctx, P.mode, sk, sp, nullptr, nullptr, fam_start.as<uint32_t>(), nf, P, out));
+    } else {
+        // FIRSTFIT: (1) stable sort read indices by group, (2) sequential first-fit per group,
+        // (3) stable sort by (group, cluster), (4) consensus with gather through the index.
+        DevBuf gk, idx, idx_tmp, reps, grp_start0;
+        PMRD_CUDA(ctx, gk.alloc(ctx->stream, (size_t)n_reads * 8));
+        PMRD_CUDA(ctx, idx.alloc(ctx->stream, (size_t)n_reads * 4));
+        PMRD_CUDA(ctx, idx_tmp.alloc(ctx->stream, (size_t)n_reads * 4));
+        PMRD_CUDA(ctx, reps.alloc(ctx->stream, (size_t)n_reads * 4));
+        PMRD_CUDA(ctx, grp_start0.alloc(ctx->stream, (size_t)(n_reads + 1) * 4));
+        const int g256 = pmrd_blocks(n_reads, 256);
+        PMRD_LAUNCH(ctx, iota_kernel, g256, 256, 0, idx.as<uint32_t>(), n_reads);
+        PMRD_LAUNCH(ctx, groupkey_kernel, g256, 256, 0, (const uint64_t*)d_keys, gk.as<uint64_t>(), n_reads);
+        uint64_t varying = 0;
+        PMRD_TRY(radix_varying_bits(ctx, gk.as<uint64_t>(), n_reads, &varying));
+        int in_b = 0;
+        PMRD_TRY(radix_sort_pairs(ctx, gk.as<uint64_t>(), idx.as<uint32_t>(), d_keys_tmp, idx_tmp.as<uint32_t>(), n_reads, varying, &in_b));
+        uint64_t* sk = in_b ? d_keys_tmp : gk.as<uint64_t>();
+        uint32_t* si = in_b ? idx_tmp.as<uint32_t>() : idx.as<uint32_t>();
+        uint64_t* ok = in_b ? gk.as<uint64_t>() : d_keys_tmp;
+        uint32_t* oi = in_b ? idx.as<uint32_t>() : idx_tmp.as<uint32_t>();
+        int64_t ng0 = 0;
+        PMRD_TRY(find_segments(ctx, sk, n_reads, 32, grp_start0.as<uint32_t>(), &ng0));
+        // new keys (group | cluster) are written into `ok`, at the same positions as sk/si
+        PMRD_LAUNCH(ctx, firstfit_kernel, pmrd_blocks(ng0 * 32, 128), 128, 0, (const uint64_t*)sk, (const uint32_t*)si,
+                    (const uint64_t*)d_keys, (const uint32_t*)grp_start0.as<uint32_t>(), ng0, P.max_distance,
+                    reps.as<uint32_t>(), ok);
+        // sort (ok, si) by cluster bits; group bits are already in order and constant-digit passes are skipped
+        PMRD_TRY(radix_varying_bits(ctx, ok, n_reads, &varying));
+        int in_b2 = 0;
+        PMRD_TRY(radix_sort_pairs(ctx, ok, si, sk, oi, n_reads, varying, &in_b2));
+        const uint64_t* fk = in_b2 ? sk : ok;
+        const uint32_t* fi = in_b2 ? oi : si;
+        PMRD_TRY(find_segments(ctx, fk, n_reads, 0, fam_start.as<uint32_t>(), &nf));
+        if (nf > capacity_f) {
+            snprintf(ctx->err, sizeof(ctx->err), "family capacity %lld < %lld families", (long long)capacity_f, (long long)nf);
+            *n_families = nf;
+            return PMRD_ERR_CAPACITY;
+        }
+        PMRD_TRY(launch_family<true>(ctx, P.mode, fk, fi, d_keys, d_payload, fam_start.as<uint32_t>(), nf, P, out));
+        PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // scratch buffers go out of scope below
+    }
+    *n_families = nf;
+
+    if (d_grp && n_groups) {
+        DevBuf grp_start;
+        PMRD_CUDA(ctx, grp_start.alloc(ctx->stream, (size_t)(nf + 1) * 4));
+        int64_t ng = 0;
+        PMRD_TRY(find_segments(ctx, d_fam->key, nf, 32, grp_start.as<uint32_t>(), &ng));
+        *n_groups = ng;
+        if (ng > capacity_g) {
+            snprintf(ctx->err, sizeof(ctx->err), "group capacity %lld < %lld groups", (long long)capacity_g, (long long)ng);
+            return PMRD_ERR_CAPACITY;
+        }
+        int grid = (int)(ng < (int64_t)ctx->sm_count * 32 ? ng : (int64_t)ctx->sm_count * 32);
+        PMRD_LAUNCH(ctx, group_kernel, grid, 128, 0, (const uint64_t*)d_fam->key, (const uint32_t*)d_fam->size,
+                    (const uint32_t*)d_fam->n_alt, (const uint32_t*)d_fam->consensus, (const uint32_t*)d_fam->flags,
+                    (const uint32_t*)grp_start.as<uint32_t>(), ng, P.mode == PMRD_MODE_WEIGHTED ? 1 : 0, *d_grp);
+        PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return PMRD_OK;
+}

@@ -1,0 +1,22 @@
+// kernels.cuh -- internal (device-pointer) entry points shared between translation units.
+#pragma once
+#include "common.cuh"
+
+// pvalues.cu
+int32_t k8_pvalues(pmrd_ctx* ctx, const int64_t* d_k, const int64_t* d_n, const double* d_rate, int64_t rate_stride,
+                   int64_t m, int32_t test_type, int32_t alternative, double* d_p);
+int32_t k9_bh(pmrd_ctx* ctx, const double* d_p, int64_t m, double alpha, uint8_t* d_rejected, double* d_q);
+
+// call.cu
+int32_t k7_call(pmrd_ctx* ctx, const int64_t* d_seg_offsets, int64_t n_segments, const uint8_t* d_is_variant,
+                const double* d_quality, const double* d_agreement, double mean_error_rate, int32_t test_type,
+                double alpha, const pmrd_call_table* d_out);
+
+// collapse.cu
+int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp, uint32_t* d_payload_tmp,
+                    int64_t n_reads, const pmrd_umi_params* params, const pmrd_family_table* d_fam, int64_t capacity_f,
+                    int64_t* n_families, const pmrd_group_table* d_grp, int64_t capacity_g, int64_t* n_groups);
+
+// simulate.cu
+int32_t k1_simulate_cells(pmrd_ctx* ctx, const int64_t* d_cell_id, const double* d_af, const int64_t* d_depth,
+                          int64_t n_cells, int32_t max_family_size, const pmrd_cell_table* d_out);

@@ -1,0 +1,185 @@
+// pvalues.cu -- K8 (tail p-values) and K9 (Benjamini-Hochberg) + their C-ABI entry points.
+//   K8 replaces call.py:14-38 / stats.py:47-133 (scipy.stats.poisson / binomtest)
+//   K9 replaces call.py:41-79 benjamini_hochberg_correction (models/statistical.py:108-140)
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "stats.cuh"
+#include "kernels.cuh"
+
+// ---------------------------------------------------------------- K8 --------------------
+__global__ void __launch_bounds__(128)
+pvalues_kernel(const int64_t* __restrict__ k, const int64_t* __restrict__ n, const double* __restrict__ rate,
+               int64_t rate_stride, int64_t m, int test_type, int alternative, double* __restrict__ p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t ki = k[i];
+    const double r = rate[i * rate_stride];
+    double out;
+    if (test_type == PMRD_TEST_POISSON) {
+        // call.py:179 expected = n_total * mean_error_rate: one IEEE multiply, no contraction
+        const double expected = n ? __dmul_rn((double)n[i], r) : r;
+        out = alternative == PMRD_ALT_TWO_SIDED ? pmrd_poisson_two_sided(ki, expected) : pmrd_poisson_greater(ki, expected);
+    } else {
+        const int64_t ni = n[i];
+        out = alternative == PMRD_ALT_TWO_SIDED ? pmrd_binomial_two_sided(ki, ni, r) : pmrd_binomial_greater(ki, ni, r);
+    }
+    p[i] = out;
+}
+
+int32_t k8_pvalues(pmrd_ctx* ctx, const int64_t* d_k, const int64_t* d_n, const double* d_rate, int64_t rate_stride,
+                   int64_t m, int32_t test_type, int32_t alternative, double* d_p) {
+    PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || test_type == PMRD_TEST_BINOMIAL, "Unknown test type");
+    PMRD_ARG(ctx, alternative == PMRD_ALT_TWO_SIDED || alternative == PMRD_ALT_GREATER, "unknown alternative");
+    PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || d_n != nullptr, "binomial test needs n");
+    if (m <= 0) return PMRD_OK;
+    PMRD_LAUNCH(ctx, pvalues_kernel, pmrd_blocks(m, 128), 128, 0, d_k, d_n, d_rate, rate_stride, m, test_type, alternative, d_p);
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- K9 --------------------
+#define BH_THREADS 256
+#define BH_ITEMS 8
+#define BH_TILE (BH_THREADS * BH_ITEMS)
+
+__global__ void __launch_bounds__(256) bh_pack_kernel(const double* __restrict__ p, int64_t m, uint64_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    // non-negative doubles order like their bit patterns; -0.0 is folded onto +0.0
+    double v = p[i];
+    if (v == 0.0) v = 0.0;
+    keys[i] = (uint64_t)__double_as_longlong(v);
+    idx[i] = (uint32_t)i;
+}
+
+// adj_i = p_(i) * m / (i+1)   (call.py:59-61: one multiply, one divide, in that order)
+__device__ __forceinline__ double bh_raw_adjusted(uint64_t key, int64_t i, double m) {
+    return __ddiv_rn(__dmul_rn(__longlong_as_double((long long)key), m), (double)(i + 1));
+}
+
+// per tile: minimum of the raw adjusted values; largest rank meeting p_(i) <= (i+1)/m*alpha
+__global__ void __launch_bounds__(BH_THREADS)
+bh_tile_kernel(const uint64_t* __restrict__ keys, int64_t m, double alpha, double* __restrict__ tile_min,
+               unsigned long long* __restrict__ kstar /* max (i+1) */) {
+    __shared__ double s_min[BH_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * BH_TILE;
+    const double md = (double)m;
+    double mn = INFINITY;
+    unsigned long long best = 0;
+#pragma unroll
+    for (int j = 0; j < BH_ITEMS; ++j) {
+        const int64_t i = base + j * BH_THREADS + threadIdx.x;
+        if (i < m) {
+            const uint64_t key = keys[i];
+            mn = fmin(mn, bh_raw_adjusted(key, i, md));
+            // call.py:55: sorted_p[i] <= (i + 1) / m * alpha
+            const double thr = __dmul_rn(__ddiv_rn((double)(i + 1), md), alpha);
+            if (__longlong_as_double((long long)key) <= thr) best = (unsigned long long)(i + 1);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        unsigned long long b2 = __shfl_xor_sync(0xffffffffu, best, o);
+        best = b2 > best ? b2 : best;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_min[threadIdx.x >> 5] = mn;
+        if (best) atomicMax(kstar, best);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = s_min[0];
+        for (int w = 1; w < BH_THREADS / 32; ++w) v = fmin(v, s_min[w]);
+        tile_min[blockIdx.x] = v;
+    }
+}
+
+// suffix-min over tile minima: tile_suffix[t] = min over tiles > t   (single block)
+__global__ void __launch_bounds__(256) bh_suffix_kernel(double* __restrict__ tile_min, int n_tiles) {
+    // chunked backwards scan; n_tiles is m/2048 so even 1e8 tests is 5e4 entries
+    __shared__ double s_part[256];
+    const int per = (n_tiles + 255) / 256;
+    const int lo = threadIdx.x * per, hi = min(lo + per, n_tiles);
+    double mn = INFINITY;
+    for (int t = hi - 1; t >= lo; --t) mn = fmin(mn, tile_min[t]);
+    s_part[threadIdx.x] = mn;
+    __syncthreads();
+    double carry = INFINITY;  // min over all chunks after mine
+    for (int c = threadIdx.x + 1; c < 256; ++c) carry = fmin(carry, s_part[c]);
+    __syncthreads();
+    for (int t = hi - 1; t >= lo; --t) {
+        const double v = tile_min[t];
+        tile_min[t] = carry;  // exclusive suffix min
+        carry = fmin(carry, v);
+    }
+}
+
+// apply: in-tile reverse running min (+ carry from later tiles), clip, scatter
+__global__ void __launch_bounds__(BH_THREADS)
+bh_apply_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idx, int64_t m,
+                const double* __restrict__ tile_suffix, const unsigned long long* __restrict__ kstar,
+                uint8_t* __restrict__ rejected, double* __restrict__ q) {
+    __shared__ double s_w[BH_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * BH_TILE + (int64_t)threadIdx.x * BH_ITEMS;  // blocked arrangement
+    const double md = (double)m;
+    double v[BH_ITEMS];
+    double mn = INFINITY;
+#pragma unroll
+    for (int j = BH_ITEMS - 1; j >= 0; --j) {
+        const int64_t i = base + j;
+        v[j] = (i < m) ? bh_raw_adjusted(keys[i], i, md) : INFINITY;
+        mn = fmin(mn, v[j]);
+    }
+    // suffix-min across threads of the block: thread t needs min over threads > t
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double incl = mn;  // inclusive suffix within warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double t = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl = fmin(incl, t);
+    }
+    if (lane == 0) s_w[warp] = incl;
+    __syncthreads();
+    double after = tile_suffix[blockIdx.x];
+    for (int w = warp + 1; w < BH_THREADS / 32; ++w) after = fmin(after, s_w[w]);
+    double next = __shfl_down_sync(0xffffffffu, incl, 1);
+    if (lane < 31) after = fmin(after, next);
+    const unsigned long long ks = *kstar;
+    double run = after;
+#pragma unroll
+    for (int j = BH_ITEMS - 1; j >= 0; --j) {
+        const int64_t i = base + j;
+        run = fmin(run, v[j]);
+        if (i < m) {
+            const uint32_t dst = idx[i];
+            q[dst] = fmin(fmax(run, 0.0), 1.0);
+            rejected[dst] = (unsigned long long)(i + 1) <= ks ? 1 : 0;
+        }
+    }
+}
+
+int32_t k9_bh(pmrd_ctx* ctx, const double* d_p, int64_t m, double alpha, uint8_t* d_rejected, double* d_q) {
+    if (m <= 0) return PMRD_OK;
+    PMRD_ARG(ctx, m < (1ll << 31), "BH: m must be < 2^31");
+    DevBuf ka, kb, va, vb, tmin, kstar;
+    PMRD_CUDA(ctx, ka.alloc(ctx->stream, (size_t)m * 8));
+    PMRD_CUDA(ctx, kb.alloc(ctx->stream, (size_t)m * 8));
+    PMRD_CUDA(ctx, va.alloc(ctx->stream, (size_t)m * 4));
+    PMRD_CUDA(ctx, vb.alloc(ctx->stream, (size_t)m * 4));
+    PMRD_LAUNCH(ctx, bh_pack_kernel, pmrd_blocks(m, 256), 256, 0, d_p, m, ka.as<uint64_t>(), va.as<uint32_t>());
+    uint64_t varying = 0;
+    PMRD_TRY(radix_varying_bits(ctx, ka.as<uint64_t>(), m, &varying));
+    int in_b = 0;
+    PMRD_TRY(radix_sort_pairs(ctx, ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), m, varying, &in_b));
+    const uint64_t* keys = in_b ? kb.as<uint64_t>() : ka.as<uint64_t>();
+    const uint32_t* idx = in_b ? vb.as<uint32_t>() : va.as<uint32_t>();
+    const int n_tiles = (int)((m + BH_TILE - 1) / BH_TILE);
+    PMRD_CUDA(ctx, tmin.alloc(ctx->stream, (size_t)n_tiles * 8));
+    PMRD_CUDA(ctx, kstar.alloc(ctx->stream, 8));
+    PMRD_CUDA(ctx, cudaMemsetAsync(kstar.p, 0, 8, ctx->stream));
+    PMRD_LAUNCH(ctx, bh_tile_kernel, n_tiles, BH_THREADS, 0, keys, m, alpha, tmin.as<double>(), kstar.as<unsigned long long>());
+    PMRD_LAUNCH(ctx, bh_suffix_kernel, 1, 256, 0, tmin.as<double>(), n_tiles);
+    PMRD_LAUNCH(ctx, bh_apply_kernel, n_tiles, BH_THREADS, 0, keys, idx, m, (const double*)tmin.as<double>(),
+                (const unsigned long long*)kstar.as<unsigned long long>(), d_rejected, d_q);
+    return PMRD_OK;
+}

@@ -1,0 +1,300 @@
+// radix_sort.cu -- kernel K4 (see radix_sort.cuh).  Replaces the reference's dict-of-lists
+// grouping: src/precise_mrd/umi.py:97-144 (group_umis_by_site / exact-UMI groups),
+// precise-mrd-mini/src/mrd/umi.py:65-67 (groupby), rust_ext/src/lib.rs:7-22 (FNV map).
+#include "radix_sort.cuh"
+
+// ---------------------------------------------------------------- varying bits ----------
+__global__ void __launch_bounds__(256) rs_varying_kernel(const uint64_t* __restrict__ keys, int64_t n,
+                                                         unsigned long long* __restrict__ or_and /*[2]*/) {
+    uint64_t o = 0, a = ~0ull;
+    const int64_t n2 = n >> 1;
+    const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        uint4 v = ld_stream_u4(k4 + i);
+        uint64_t x = ((uint64_t)v.y << 32) | v.x, y = ((uint64_t)v.w << 32) | v.z;
+        o |= x | y;
+        a &= x & y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint64_t x = keys[n - 1];
+        o |= x;
+        a &= x;
+    }
+    uint32_t olo = __reduce_or_sync(0xffffffffu, (uint32_t)o), ohi = __reduce_or_sync(0xffffffffu, (uint32_t)(o >> 32));
+    uint32_t alo = __reduce_and_sync(0xffffffffu, (uint32_t)a), ahi = __reduce_and_sync(0xffffffffu, (uint32_t)(a >> 32));
+    if ((threadIdx.x & 31) == 0) {
+        atomicOr(&or_and[0], ((unsigned long long)ohi << 32) | olo);
+        atomicAnd(&or_and[1], ((unsigned long long)ahi << 32) | alo);
+    }
+}
+
+int32_t radix_varying_bits(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, uint64_t* h_varying) {
+    *h_varying = 0;
+    if (n <= 1) return PMRD_OK;
+    DevBuf buf;
+    PMRD_CUDA(ctx, buf.alloc(ctx->stream, 16));
+    unsigned long long init[2] = {0ull, ~0ull};
+    PMRD_CUDA(ctx, cudaMemcpyAsync(buf.p, init, 16, cudaMemcpyHostToDevice, ctx->stream));
+    int grid = (int)((n / 2 + 255) / 256);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    PMRD_LAUNCH(ctx, rs_varying_kernel, grid, 256, 0, d_keys, n, buf.as<unsigned long long>());
+    unsigned long long res[2];
+    PMRD_CUDA(ctx, cudaMemcpyAsync(res, buf.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *h_varying = res[0] ^ res[1];
+    return PMRD_OK;
+}
+
+RadixPlan radix_make_plan(uint64_t varying) {
+    RadixPlan p;
+    p.n_passes = 0;
+    // greedy: an (up to) 8-bit window starting at the lowest varying bit not yet covered;
+    // at most 8 windows cover 64 bits.
+    int b = 0;
+    while (b < 64) {
+        if (!((varying >> b) & 1ull)) { ++b; continue; }
+        int w = 64 - b < 8 ? 64 - b : 8;
+        // trim non-varying bits off the top of the window
+        while (w > 1 && !((varying >> (b + w - 1)) & 1ull)) --w;
+        p.shift[p.n_passes] = b;
+        p.bits[p.n_passes] = w;
+        ++p.n_passes;
+        b += w;
+    }
+    return p;
+}
+
+// ---------------------------------------------------------------- upsweep ---------------
+// hist[tile][256] (tile-major: one coalesced 1 KB row per tile)
+__global__ void __launch_bounds__(RS_THREADS)
+rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ hist, int shift, uint32_t mask) {
+    __shared__ uint32_t s_hist[RS_WARPS][RS_MAX_BINS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+    const int64_t rem = n - tile_base;
+    const int tile_n = rem < RS_TILE ? (int)rem : RS_TILE;
+    // each warp owns 512 consecutive keys; 128-bit loads = 2 keys per lane per step
+    const int64_t wbase = tile_base + (int64_t)warp * (RS_TILE / RS_WARPS);
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS / 2; ++i) {
+        const int loc = (int)warp * (RS_TILE / RS_WARPS) + i * 64 + (int)lane * 2;
+        uint32_t d0 = 0xffffffffu, d1 = 0xffffffffu;
+        if (loc + 1 < tile_n) {
+            uint4 v = ld_stream_u4(keys + wbase + i * 64 + lane * 2);
+            uint64_t x = ((uint64_t)v.y << 32) | v.x, y = ((uint64_t)v.w << 32) | v.z;
+            d0 = (uint32_t)(x >> shift) & mask;
+            d1 = (uint32_t)(y >> shift) & mask;
+        } else if (loc < tile_n) {
+            d0 = (uint32_t)(keys[wbase + i * 64 + lane * 2] >> shift) & mask;
+        }
+        uint32_t m0 = __match_any_sync(0xffffffffu, d0);
+        uint32_t m1 = __match_any_sync(0xffffffffu, d1);
+        if (d0 != 0xffffffffu && (m0 & lanemask_lt()) == 0) s_hist[warp][d0] += __popc(m0);
+        __syncwarp();
+        if (d1 != 0xffffffffu && (m1 & lanemask_lt()) == 0) s_hist[warp][d1] += __popc(m1);
+        __syncwarp();
+    }
+    __syncthreads();
+    uint32_t c = 0;
+#pragma unroll
+    for (int w = 0; w < RS_WARPS; ++w) c += s_hist[w][threadIdx.x];
+    hist[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] = c;
+}
+
+// ---------------------------------------------------------------- column scan -----------
+// H[tile][d]  ->  exclusive over (d major, tile minor) order, computed column-wise.
+__global__ void __launch_bounds__(256)
+rs_colsum_kernel(const uint32_t* __restrict__ hist, int n_tiles, int chunk, uint32_t* __restrict__ colsum /*[n_chunks][256]*/) {
+    const int t0 = blockIdx.x * chunk;
+    const int t1 = min(t0 + chunk, n_tiles);
+    uint32_t acc = 0;
+#pragma unroll 8
+    for (int t = t0; t < t1; ++t) acc += hist[(int64_t)t * 256 + threadIdx.x];
+    colsum[(int64_t)blockIdx.x * 256 + threadIdx.x] = acc;
+}
+
+__global__ void __launch_bounds__(256) rs_colbase_kernel(uint32_t* __restrict__ colsum, int n_chunks) {
+    __shared__ uint32_t sw[33];
+    uint32_t run = 0;
+#pragma unroll 8
+    for (int c = 0; c < n_chunks; ++c) {
+        uint32_t v = colsum[(int64_t)c * 256 + threadIdx.x];
+        colsum[(int64_t)c * 256 + threadIdx.x] = run;
+        run += v;
+    }
+    uint32_t tot;
+    uint32_t base = block_exclusive_scan<uint32_t>(run, sw, tot);
+    for (int c = 0; c < n_chunks; ++c) colsum[(int64_t)c * 256 + threadIdx.x] += base;
+}
+
+__global__ void __launch_bounds__(256)
+rs_colapply_kernel(uint32_t* __restrict__ hist, int n_tiles, int chunk, const uint32_t* __restrict__ colsum) {
+    const int t0 = blockIdx.x * chunk;
+    const int t1 = min(t0 + chunk, n_tiles);
+    uint32_t run = colsum[(int64_t)blockIdx.x * 256 + threadIdx.x];
+    int t = t0;
+    for (; t + 8 <= t1; t += 8) {
+        uint32_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = hist[(int64_t)(t + j) * 256 + threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            hist[(int64_t)(t + j) * 256 + threadIdx.x] = run;
+            run += v[j];
+        }
+    }
+    for (; t < t1; ++t) {
+        uint32_t v = hist[(int64_t)t * 256 + threadIdx.x];
+        hist[(int64_t)t * 256 + threadIdx.x] = run;
+        run += v;
+    }
+}
+
+// ---------------------------------------------------------------- downsweep -------------
+struct RsSmem {
+    uint64_t keys[RS_TILE];
+    uint32_t vals[RS_TILE];
+    uint32_t warp_cnt[RS_WARPS][RS_MAX_BINS];
+    uint32_t bin_base[RS_MAX_BINS];
+    uint32_t glob_delta[RS_MAX_BINS];
+    uint32_t sw[33];
+};
+
+template <bool HAS_VALS>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                    uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
+                    const uint32_t* __restrict__ hist_scanned, int64_t n, int shift, uint32_t mask) {
+    extern __shared__ __align__(16) unsigned char rs_smem_raw[];
+    RsSmem& S = *reinterpret_cast<RsSmem*>(rs_smem_raw);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = lanemask_lt();
+    for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+    const int64_t rem = n - tile_base;
+    const int tile_n = rem < RS_TILE ? (int)rem : RS_TILE;
+    const int wloc = (int)warp * (RS_TILE / RS_WARPS);
+
+    // warp-striped load: item i of lane l = wloc + i*32 + l  (memory order = i-major, lane-minor)
+    uint64_t key[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int loc = wloc + i * 32 + (int)lane;
+        key[i] = (loc < tile_n) ? keys_in[tile_base + loc] : ~0ull;
+    }
+    __syncthreads();
+
+    // stable in-warp ranking per digit (match-any): rank = #earlier items of this warp with my digit
+    uint16_t rank[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int loc = wloc + i * 32 + (int)lane;
+        const bool valid = loc < tile_n;
+        const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & mask) : 0xffffffffu;
+        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        const uint32_t before = __popc(m & lt);
+        uint32_t old = 0;
+        if (valid) old = S.warp_cnt[warp][d];
+        __syncwarp();
+        if (valid && before == 0) S.warp_cnt[warp][d] = old + __popc(m);
+        __syncwarp();
+        rank[i] = (uint16_t)(old + before);
+    }
+    __syncthreads();
+
+    // per-bin: exclusive prefix over warps, then block scan over bins
+    {
+        const uint32_t b = threadIdx.x;  // RS_THREADS == RS_MAX_BINS
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t c = S.warp_cnt[w][b];
+            S.warp_cnt[w][b] = run;
+            run += c;
+        }
+        uint32_t tot;
+        uint32_t base = block_exclusive_scan<uint32_t>(run, S.sw, tot);
+        S.bin_base[b] = base;
+        S.glob_delta[b] = hist_scanned[(int64_t)blockIdx.x * RS_MAX_BINS + b] - base;
+    }
+    __syncthreads();
+
+    // reorder into shared memory by digit (stable)
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int loc = wloc + i * 32 + (int)lane;
+        if (loc < tile_n) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            const uint32_t pos = S.bin_base[d] + S.warp_cnt[warp][d] + rank[i];
+            S.keys[pos] = key[i];
+            if (HAS_VALS) S.vals[pos] = vals_in[tile_base + loc];
+        }
+    }
+    __syncthreads();
+
+    // coalesced per-digit run stores
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int j = i * RS_THREADS + (int)threadIdx.x;
+        if (j < tile_n) {
+            const uint64_t k = S.keys[j];
+            const uint32_t d = (uint32_t)(k >> shift) & mask;
+            const uint32_t g = (uint32_t)j + S.glob_delta[d];
+            keys_out[g] = k;
+            if (HAS_VALS) vals_out[g] = S.vals[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- driver ----------------
+int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
+                         int64_t n, uint64_t varying, int* in_b) {
+    *in_b = 0;
+    if (n <= 1) return PMRD_OK;
+    PMRD_ARG(ctx, n < (1ll << 32) - RS_TILE, "radix_sort_pairs: n must be < 2^32 (chunk the input)");
+    RadixPlan plan = radix_make_plan(varying);
+    if (plan.n_passes == 0) return PMRD_OK;
+
+    const int n_tiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    int chunk = 1;
+    while ((int64_t)chunk * chunk < n_tiles) ++chunk;
+    const int n_chunks = (n_tiles + chunk - 1) / chunk;
+
+    DevBuf hist, colsum;
+    PMRD_CUDA(ctx, hist.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
+    PMRD_CUDA(ctx, colsum.alloc(ctx->stream, (size_t)n_chunks * 256 * sizeof(uint32_t)));
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        attr_set = true;
+    }
+
+    uint64_t* kin = keys_a;
+    uint32_t* vin = vals_a;
+    uint64_t* kout = keys_b;
+    uint32_t* vout = vals_b;
+    for (int p = 0; p < plan.n_passes; ++p) {
+        const int shift = plan.shift[p];
+        const uint32_t mask = (1u << plan.bits[p]) - 1u;
+        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask);
+        PMRD_LAUNCH(ctx, rs_colsum_kernel, n_chunks, 256, 0, hist.as<uint32_t>(), n_tiles, chunk, colsum.as<uint32_t>());
+        PMRD_LAUNCH(ctx, rs_colbase_kernel, 1, 256, 0, colsum.as<uint32_t>(), n_chunks);
+        PMRD_LAUNCH(ctx, rs_colapply_kernel, n_chunks, 256, 0, hist.as<uint32_t>(), n_tiles, chunk, colsum.as<uint32_t>());
+        if (vals_a) {
+            PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout,
+                        hist.as<uint32_t>(), n, shift, mask);
+        } else {
+            PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout,
+                        hist.as<uint32_t>(), n, shift, mask);
+        }
+        uint64_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    *in_b = (plan.n_passes & 1);
+    return PMRD_OK;
+}
