@@ -292,6 +292,27 @@ int32_t pmrd_pipeline_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const doubl
                             double neg_af_max, int32_t test_type, int32_t alternative, double alpha,
                             pmrd_pipeline_result* h_out, double* h_mean_error_rate);
 
+/* The same pipeline as a prepared plan: create() uploads the cell table, sizes and
+ * allocates every buffer once; run() only enqueues kernels on the context's stream (no
+ * allocation, no host<->device copy, no sync -- safe to time with events or capture in a
+ * CUDA graph); results() copies the per-cell table back and synchronises.
+ * h_totals3 = {reads generated, families formed, groups (cells) with reads}. */
+typedef struct pmrd_plan pmrd_plan;
+int32_t pmrd_plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
+                         const int64_t* h_n_families, int64_t n_cells, const pmrd_read_sim_params* sp,
+                         const pmrd_umi_params* up, double neg_af_max, int32_t test_type,
+                         int32_t alternative, double alpha, pmrd_plan** out);
+int32_t pmrd_plan_run(pmrd_ctx* ctx, pmrd_plan* plan);
+int32_t pmrd_plan_results(pmrd_ctx* ctx, pmrd_plan* plan, pmrd_pipeline_result* h_out,
+                          double* h_mean_error_rate, int64_t* h_totals3);
+int64_t pmrd_plan_n_reads(const pmrd_plan* plan);
+int64_t pmrd_plan_n_families(const pmrd_plan* plan);
+void pmrd_plan_destroy(pmrd_plan* plan);
+/* Stage-by-stage entry points of a plan, for per-kernel timing (bench.py roofline): */
+int32_t pmrd_plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* plan); /* sizes + scan + reads  */
+int32_t pmrd_plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* plan); /* sort + families + groups */
+int32_t pmrd_plan_run_call(pmrd_ctx* ctx, pmrd_plan* plan);     /* counts + rate + p + BH */
+
 /* ---------------------------------------------------------------- K11: LoD fit ------ */
 /* LODAnalyzer._fit_detection_curve + _bootstrap_lod_ci (src/precise_mrd/eval/lod.py:
  * 351-408): 2-parameter logistic on log10(af) by Levenberg-Marquardt from (1,1), solved

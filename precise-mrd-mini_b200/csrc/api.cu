@@ -10,6 +10,26 @@ char g_pmrd_create_err[512] = "";
 
 int32_t collapse_upload_weights(pmrd_ctx* ctx, const double* h_w64);
 int32_t k6_hamming(pmrd_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, int64_t n, int32_t* d_d);
+int32_t k2_gd_families(pmrd_ctx* ctx, const int32_t* d_tile_cell, const int32_t* d_tile_fam0, int64_t n_tiles,
+                       const void* d_cells, const int64_t* d_n_families, const pmrd_umi_params* P, int variant,
+                       uint64_t* d_tile_base, const pmrd_gd_family_table* d_out);
+int32_t k10_error_model(pmrd_ctx* ctx, int64_t n_neg, int64_t n_var, int32_t n_boot, uint64_t stream_id, double* d_rate64,
+                        double* d_lo64, double* d_hi64);
+int32_t k11_fit_lod(pmrd_ctx* ctx, const double* d_af, const double* d_hit, int32_t n, double target, int32_t n_boot,
+                    uint64_t stream_id, double* d_out3);
+struct pmrd_plan;
+int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                    int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, double neg_af_max,
+                    int32_t test_type, int32_t alternative, double alpha, pmrd_plan** out);
+int32_t plan_run(pmrd_ctx* ctx, pmrd_plan* P);
+int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P);
+int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P);
+int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P);
+int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h, double* h_mean_rate, int64_t* h_totals);
+void plan_destroy(pmrd_plan* P);
+int64_t plan_n_reads(const pmrd_plan* P);
+int64_t plan_n_families(const pmrd_plan* P);
+#include "reads.cuh"
 
 extern "C" {
 
@@ -337,6 +357,268 @@ int32_t pmrd_umi_hamming(pmrd_ctx* ctx, const uint32_t* h_a, const uint32_t* h_b
     PMRD_CUDA(ctx, d.alloc(ctx->stream, (size_t)n * 4));
     PMRD_TRY(k6_hamming(ctx, a.as<uint32_t>(), b.as<uint32_t>(), n, d.as<int32_t>()));
     PMRD_TRY(down(ctx, h_d, d.p, (size_t)n * 4));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
+
+// ---------------------------------------------------------------- K1 --------------------
+int32_t pmrd_simulate_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_depth,
+                            int64_t n_cells, int32_t max_family_size, pmrd_cell_table* h_out) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n_cells >= 0, "n_cells");
+    if (n_cells == 0) return PMRD_OK;
+    PMRD_ARG(ctx, h_cell_id && h_af && h_depth && h_out, "null buffer");
+    const size_t c = (size_t)n_cells;
+    DevBuf id, af, dp, bg, mfs, nt, nfp, mq;
+    PMRD_TRY(up(ctx, id, h_cell_id, c * 8));
+    PMRD_TRY(up(ctx, af, h_af, c * 8));
+    PMRD_TRY(up(ctx, dp, h_depth, c * 8));
+    PMRD_CUDA(ctx, bg.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, mfs.alloc(ctx->stream, c * 8));
+    PMRD_CUDA(ctx, nt.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, nfp.alloc(ctx->stream, c * 8));
+    PMRD_CUDA(ctx, mq.alloc(ctx->stream, c * 8));
+    pmrd_cell_table d{bg.as<double>(), mfs.as<int64_t>(), nt.as<int64_t>(), nfp.as<int64_t>(), mq.as<double>()};
+    PMRD_TRY(k1_simulate_cells(ctx, id.as<int64_t>(), af.as<double>(), dp.as<int64_t>(), n_cells, max_family_size, &d));
+    PMRD_TRY(down(ctx, h_out->background_rate, d.background_rate, c * 8));
+    PMRD_TRY(down(ctx, h_out->mean_family_size, d.mean_family_size, c * 8));
+    PMRD_TRY(down(ctx, h_out->n_true_variants, d.n_true_variants, c * 8));
+    PMRD_TRY(down(ctx, h_out->n_false_positives, d.n_false_positives, c * 8));
+    PMRD_TRY(down(ctx, h_out->mean_quality, d.mean_quality, c * 8));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- K2 (G-D) --------------
+struct GdCellHost {
+    uint64_t cell_id;
+    double af, bg, lambda;
+};
+
+int32_t pmrd_collapse_families(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                               const double* h_background_rate, const double* h_mean_family_size, int64_t n_cells,
+                               const pmrd_umi_params* params, int32_t variant, int64_t* h_row_offsets,
+                               pmrd_gd_family_table* h_out, int64_t capacity) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n_cells >= 0 && params && h_row_offsets, "arguments");
+    PMRD_ARG(ctx, variant == 1 || variant == 2, "variant must be 1 (G-D v1) or 2 (G-D v2)");
+    h_row_offsets[0] = 0;
+    if (n_cells == 0) return PMRD_OK;
+    PMRD_ARG(ctx, h_cell_id && h_af && h_n_families && h_background_rate && h_mean_family_size, "null buffer");
+    const int TILE = 1024;
+    int64_t n_tiles = 0;
+    for (int64_t i = 0; i < n_cells; ++i) {
+        PMRD_ARG(ctx, h_n_families[i] >= 0 && h_n_families[i] < (1ll << 31), "n_families out of range");
+        n_tiles += (h_n_families[i] + TILE - 1) / TILE;
+    }
+    PMRD_ARG(ctx, n_tiles < (1ll << 31), "too many tiles; chunk the cells");
+    GdCellHost* hc = (GdCellHost*)malloc(sizeof(GdCellHost) * (size_t)n_cells);
+    int32_t* tcell = (int32_t*)malloc(4 * (size_t)(n_tiles + 1) * 2);
+    int64_t* first_tile = (int64_t*)malloc(8 * (size_t)(n_cells + 1));
+    uint64_t* tbase = (uint64_t*)malloc(8 * (size_t)(n_tiles + 1));
+    if (!hc || !tcell || !first_tile || !tbase) {
+        free(hc); free(tcell); free(first_tile); free(tbase);
+        PMRD_ARG(ctx, false, "out of host memory");
+    }
+    int32_t* tfam0 = tcell + (n_tiles + 1);
+    int64_t t = 0;
+    for (int64_t i = 0; i < n_cells; ++i) {
+        hc[i].cell_id = (uint64_t)h_cell_id[i];
+        hc[i].af = h_af[i];
+        hc[i].bg = h_background_rate[i];
+        // collapse.py:80 mean_size = max(3, mean_family_size)   ("collapse 2.py":56: poisson(5))
+        hc[i].lambda = variant == 1 ? 5.0 : (h_mean_family_size[i] > 3.0 ? h_mean_family_size[i] : 3.0);
+        first_tile[i] = t;
+        for (int64_t f0 = 0; f0 < h_n_families[i]; f0 += TILE) {
+            tcell[t] = (int32_t)i;
+            tfam0[t] = (int32_t)f0;
+            ++t;
+        }
+    }
+    first_tile[n_cells] = t;
+    int32_t st = PMRD_OK;
+    {
+        DevBuf dc, dtc, dtf, dnf, dbase, oc, ofid, ofs, oq, oa, ofl;
+        auto run = [&]() -> int32_t {
+            PMRD_TRY(up(ctx, dc, hc, sizeof(GdCellHost) * (size_t)n_cells));
+            PMRD_TRY(up(ctx, dtc, tcell, 4 * (size_t)n_tiles));
+            PMRD_TRY(up(ctx, dtf, tfam0, 4 * (size_t)n_tiles));
+            PMRD_TRY(up(ctx, dnf, h_n_families, 8 * (size_t)n_cells));
+            PMRD_CUDA(ctx, dbase.alloc(ctx->stream, 8 * (size_t)(n_tiles + 1)));
+            PMRD_CUDA(ctx, cudaMemsetAsync(dbase.p, 0, 8 * (size_t)(n_tiles + 1), ctx->stream));
+            PMRD_TRY(k2_gd_families(ctx, dtc.as<int32_t>(), dtf.as<int32_t>(), n_tiles, dc.p, dnf.as<int64_t>(), params, variant,
+                                    dbase.as<uint64_t>(), nullptr));
+            PMRD_CUDA(ctx, cudaMemcpyAsync(tbase, dbase.p, 8 * (size_t)(n_tiles + 1), cudaMemcpyDeviceToHost, ctx->stream));
+            PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int64_t i = 0; i <= n_cells; ++i) h_row_offsets[i] = (int64_t)tbase[first_tile[i]];
+            const int64_t R = (int64_t)tbase[n_tiles];
+            if (!h_out) return PMRD_OK;
+            if (R > capacity) {
+                snprintf(ctx->err, sizeof(ctx->err), "family capacity %lld < %lld rows", (long long)capacity, (long long)R);
+                return PMRD_ERR_CAPACITY;
+            }
+            if (R == 0) return PMRD_OK;
+            const size_t r = (size_t)R;
+            PMRD_CUDA(ctx, oc.alloc(ctx->stream, r * 4)); PMRD_CUDA(ctx, ofid.alloc(ctx->stream, r * 4));
+            PMRD_CUDA(ctx, ofs.alloc(ctx->stream, r * 4)); PMRD_CUDA(ctx, oq.alloc(ctx->stream, r * 8));
+            PMRD_CUDA(ctx, oa.alloc(ctx->stream, r * 8)); PMRD_CUDA(ctx, ofl.alloc(ctx->stream, r));
+            pmrd_gd_family_table d{oc.as<int32_t>(), ofid.as<int32_t>(), ofs.as<int32_t>(), oq.as<double>(), oa.as<double>(), ofl.as<uint8_t>()};
+            PMRD_TRY(k2_gd_families(ctx, dtc.as<int32_t>(), dtf.as<int32_t>(), n_tiles, dc.p, dnf.as<int64_t>(), params, variant,
+                                    dbase.as<uint64_t>(), &d));
+            PMRD_TRY(down(ctx, h_out->cell, d.cell, r * 4));
+            PMRD_TRY(down(ctx, h_out->family_id, d.family_id, r * 4));
+            PMRD_TRY(down(ctx, h_out->family_size, d.family_size, r * 4));
+            PMRD_TRY(down(ctx, h_out->quality_score, d.quality_score, r * 8));
+            PMRD_TRY(down(ctx, h_out->consensus_agreement, d.consensus_agreement, r * 8));
+            PMRD_TRY(down(ctx, h_out->flags, d.flags, r));
+            PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            return PMRD_OK;
+        };
+        st = run();
+        cudaStreamSynchronize(ctx->stream);
+    }
+    free(hc); free(tcell); free(first_tile); free(tbase);
+    return st;
+}
+
+// ---------------------------------------------------------------- K10 -------------------
+int32_t pmrd_error_model(pmrd_ctx* ctx, int64_t n_neg, int64_t n_var, int32_t n_boot, uint64_t stream_id,
+                         double* h_rate64, double* h_ci_lo64, double* h_ci_hi64) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, h_rate64 && h_ci_lo64 && h_ci_hi64, "null buffer");
+    DevBuf r, lo, hi;
+    PMRD_CUDA(ctx, r.alloc(ctx->stream, 512)); PMRD_CUDA(ctx, lo.alloc(ctx->stream, 512)); PMRD_CUDA(ctx, hi.alloc(ctx->stream, 512));
+    PMRD_TRY(k10_error_model(ctx, n_neg, n_var, n_boot, stream_id, r.as<double>(), lo.as<double>(), hi.as<double>()));
+    PMRD_TRY(down(ctx, h_rate64, r.p, 512));
+    PMRD_TRY(down(ctx, h_ci_lo64, lo.p, 512));
+    PMRD_TRY(down(ctx, h_ci_hi64, hi.p, 512));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- read-level simulate ---
+int32_t pmrd_simulate_reads_count(pmrd_ctx* ctx, const int64_t* h_cell_id, const int64_t* h_n_families, int64_t n_cells,
+                                  const pmrd_read_sim_params* sp, int64_t* h_read_offsets) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, h_read_offsets != nullptr, "h_read_offsets");
+    h_read_offsets[0] = 0;
+    if (n_cells <= 0) return PMRD_OK;
+    ReadPlan plan;
+    int32_t st = reads_plan_build(ctx, h_cell_id, nullptr, h_n_families, n_cells, 0, sp, &plan, h_read_offsets);
+    cudaStreamSynchronize(ctx->stream);
+    return st;
+}
+
+int32_t pmrd_simulate_reads_dev(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                                int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, uint64_t* d_keys,
+                                uint32_t* d_payload, int64_t capacity, int64_t* n_reads) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n_reads != nullptr, "n_reads");
+    *n_reads = 0;
+    if (n_cells <= 0) return PMRD_OK;
+    ReadPlan plan;
+    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, &plan, nullptr));
+    *n_reads = plan.n_reads;
+    if (plan.n_reads > capacity) {
+        snprintf(ctx->err, sizeof(ctx->err), "read capacity %lld < %lld reads", (long long)capacity, (long long)plan.n_reads);
+        return PMRD_ERR_CAPACITY;
+    }
+    PMRD_TRY(reads_plan_generate(ctx, &plan, d_keys, d_payload));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the plan's scratch dies with this scope
+    return PMRD_OK;
+}
+
+int32_t pmrd_simulate_reads(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                            int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, uint64_t* h_keys,
+                            uint32_t* h_payload, int64_t capacity, int64_t* n_reads) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n_reads != nullptr, "n_reads");
+    *n_reads = 0;
+    if (n_cells <= 0) return PMRD_OK;
+    ReadPlan plan;
+    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, &plan, nullptr));
+    *n_reads = plan.n_reads;
+    if (plan.n_reads > capacity) {
+        snprintf(ctx->err, sizeof(ctx->err), "read capacity %lld < %lld reads", (long long)capacity, (long long)plan.n_reads);
+        return PMRD_ERR_CAPACITY;
+    }
+    if (plan.n_reads == 0) return PMRD_OK;
+    DevBuf k, p;
+    PMRD_CUDA(ctx, k.alloc(ctx->stream, (size_t)plan.n_reads * 8));
+    PMRD_CUDA(ctx, p.alloc(ctx->stream, (size_t)plan.n_reads * 4));
+    PMRD_TRY(reads_plan_generate(ctx, &plan, k.as<uint64_t>(), p.as<uint32_t>()));
+    PMRD_TRY(down(ctx, h_keys, k.p, (size_t)plan.n_reads * 8));
+    PMRD_TRY(down(ctx, h_payload, p.p, (size_t)plan.n_reads * 4));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- pipeline / plan -------
+int32_t pmrd_plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                         int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up_, double neg_af_max,
+                         int32_t test_type, int32_t alternative, double alpha, pmrd_plan** out) {
+    ENTER(ctx);
+    return plan_create(ctx, h_cell_id, h_af, h_n_families, n_cells, sp, up_, neg_af_max, test_type, alternative, alpha, out);
+}
+int32_t pmrd_plan_run(pmrd_ctx* ctx, pmrd_plan* plan) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, plan != nullptr, "plan");
+    return plan_run(ctx, plan);
+}
+int32_t pmrd_plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* plan) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, plan != nullptr, "plan");
+    return plan_run_simulate(ctx, plan);
+}
+int32_t pmrd_plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* plan) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, plan != nullptr, "plan");
+    return plan_run_collapse(ctx, plan);
+}
+int32_t pmrd_plan_run_call(pmrd_ctx* ctx, pmrd_plan* plan) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, plan != nullptr, "plan");
+    return plan_run_call(ctx, plan);
+}
+int32_t pmrd_plan_results(pmrd_ctx* ctx, pmrd_plan* plan, pmrd_pipeline_result* h_out, double* h_mean_error_rate, int64_t* h_totals3) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, plan != nullptr, "plan");
+    return plan_results(ctx, plan, h_out, h_mean_error_rate, h_totals3);
+}
+int64_t pmrd_plan_n_reads(const pmrd_plan* plan) { return plan_n_reads(plan); }
+int64_t pmrd_plan_n_families(const pmrd_plan* plan) { return plan_n_families(plan); }
+void pmrd_plan_destroy(pmrd_plan* plan) {
+    if (plan) {
+        cudaDeviceSynchronize();
+        plan_destroy(plan);
+    }
+}
+
+int32_t pmrd_pipeline_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                            int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up_, double neg_af_max,
+                            int32_t test_type, int32_t alternative, double alpha, pmrd_pipeline_result* h_out,
+                            double* h_mean_error_rate) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, h_out != nullptr, "out");
+    pmrd_plan* plan = nullptr;
+    PMRD_TRY(plan_create(ctx, h_cell_id, h_af, h_n_families, n_cells, sp, up_, neg_af_max, test_type, alternative, alpha, &plan));
+    int32_t st = plan_run(ctx, plan);
+    if (st == PMRD_OK) st = plan_results(ctx, plan, h_out, h_mean_error_rate, nullptr);
+    cudaStreamSynchronize(ctx->stream);
+    plan_destroy(plan);
+    return st;
+}
+
+// ---------------------------------------------------------------- K11 -------------------
+int32_t pmrd_fit_lod(pmrd_ctx* ctx, const double* h_af, const double* h_hit, int32_t n, double target, int32_t n_boot,
+                     uint64_t stream_id, double* h_out3) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, h_af && h_hit && h_out3 && n >= 1, "arguments");
+    DevBuf af, hit, out;
+    PMRD_TRY(up(ctx, af, h_af, (size_t)n * 8));
+    PMRD_TRY(up(ctx, hit, h_hit, (size_t)n * 8));
+    PMRD_CUDA(ctx, out.alloc(ctx->stream, 24));
+    PMRD_TRY(k11_fit_lod(ctx, af.as<double>(), hit.as<double>(), n, target, n_boot, stream_id, out.as<double>()));
+    PMRD_TRY(down(ctx, h_out3, out.p, 24));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PMRD_OK;
 }

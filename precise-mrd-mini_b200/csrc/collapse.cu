@@ -27,6 +27,9 @@ int32_t collapse_upload_weights(pmrd_ctx* ctx, const double* h_w64) {
 }
 
 // ---------------------------------------------------------------- segments --------------
+// Segment starts of a sorted key array, with NO host round trip: the element count may
+// live on the device (d_n) and the number of segments found stays there (d_count), so the
+// whole collapse can be enqueued -- or captured in a CUDA graph -- without a sync.
 #define SEG_THREADS 256
 #define SEG_ITEMS 8
 #define SEG_TILE (SEG_THREADS * SEG_ITEMS)
@@ -36,8 +39,10 @@ __device__ __forceinline__ bool seg_is_head(const uint64_t* __restrict__ keys, i
 }
 
 __global__ void __launch_bounds__(SEG_THREADS)
-seg_count_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ tile_heads) {
+seg_count_kernel(const uint64_t* __restrict__ keys, int64_t n_cap, const uint32_t* __restrict__ d_n, int shift,
+                 uint32_t* __restrict__ tile_heads) {
     __shared__ uint32_t sw[SEG_THREADS / 32];
+    const int64_t n = d_n ? (int64_t)*d_n : n_cap;
     const int64_t base = (int64_t)blockIdx.x * SEG_TILE;
     uint32_t c = 0;
 #pragma unroll
@@ -56,9 +61,11 @@ seg_count_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32
 }
 
 __global__ void __launch_bounds__(SEG_THREADS)
-seg_write_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, const uint32_t* __restrict__ tile_base,
-                 const uint32_t* __restrict__ total, uint32_t* __restrict__ seg_start) {
+seg_write_kernel(const uint64_t* __restrict__ keys, int64_t n_cap, const uint32_t* __restrict__ d_n, int shift,
+                 const uint32_t* __restrict__ tile_base, const uint32_t* __restrict__ total, int64_t seg_cap,
+                 uint32_t* __restrict__ seg_start, uint32_t* __restrict__ d_count) {
     __shared__ uint32_t sw[33];
+    const int64_t n = d_n ? (int64_t)*d_n : n_cap;
     // blocked arrangement so that ranks follow memory order
     const int64_t base = (int64_t)blockIdx.x * SEG_TILE + (int64_t)threadIdx.x * SEG_ITEMS;
     uint32_t flags = 0, c = 0;
@@ -74,27 +81,42 @@ seg_write_kernel(const uint64_t* __restrict__ keys, int64_t n, int shift, const 
     uint32_t r = tile_base[blockIdx.x] + block_exclusive_scan<uint32_t>(c, sw, tot);
 #pragma unroll
     for (int j = 0; j < SEG_ITEMS; ++j)
-        if (flags & (1u << j)) seg_start[r++] = (uint32_t)(base + j);
-    if (blockIdx.x == 0 && threadIdx.x == 0) seg_start[*total] = (uint32_t)n;
+        if (flags & (1u << j)) {
+            if ((int64_t)r < seg_cap) seg_start[r] = (uint32_t)(base + j);
+            ++r;
+        }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const uint32_t t = *total;
+        if ((int64_t)t <= seg_cap) seg_start[t] = (uint32_t)n;
+        *d_count = t;
+    }
 }
 
-// seg_start must hold n+1 entries in the worst case; *h_nseg is written after a sync.
-static int32_t find_segments(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, int shift, uint32_t* d_seg_start,
-                             int64_t* h_nseg) {
-    *h_nseg = 0;
-    if (n <= 0) return PMRD_OK;
-    const int n_tiles = (int)((n + SEG_TILE - 1) / SEG_TILE);
+// seg_start holds seg_cap+1 entries; d_count (device) receives the number of segments
+// (which may exceed seg_cap: the caller checks).
+static int32_t find_segments_dev(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n_cap, const uint32_t* d_n, int shift,
+                                 int64_t seg_cap, uint32_t* d_seg_start, uint32_t* d_count) {
+    if (n_cap <= 0) {
+        PMRD_CUDA(ctx, cudaMemsetAsync(d_count, 0, 4, ctx->stream));
+        PMRD_CUDA(ctx, cudaMemsetAsync(d_seg_start, 0, 4, ctx->stream));
+        return PMRD_OK;
+    }
+    const int n_tiles = (int)((n_cap + SEG_TILE - 1) / SEG_TILE);
     DevBuf th, tot;
     PMRD_CUDA(ctx, th.alloc(ctx->stream, (size_t)n_tiles * 4));
     PMRD_CUDA(ctx, tot.alloc(ctx->stream, 4));
-    PMRD_LAUNCH(ctx, seg_count_kernel, n_tiles, SEG_THREADS, 0, d_keys, n, shift, th.as<uint32_t>());
+    PMRD_LAUNCH(ctx, seg_count_kernel, n_tiles, SEG_THREADS, 0, d_keys, n_cap, d_n, shift, th.as<uint32_t>());
     PMRD_TRY((exclusive_scan<uint32_t, uint32_t>(ctx, th.as<uint32_t>(), th.as<uint32_t>(), n_tiles, tot.as<uint32_t>())));
-    PMRD_LAUNCH(ctx, seg_write_kernel, n_tiles, SEG_THREADS, 0, d_keys, n, shift, (const uint32_t*)th.as<uint32_t>(),
-                (const uint32_t*)tot.as<uint32_t>(), d_seg_start);
-    uint32_t h = 0;
-    PMRD_CUDA(ctx, cudaMemcpyAsync(&h, tot.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PMRD_LAUNCH(ctx, seg_write_kernel, n_tiles, SEG_THREADS, 0, d_keys, n_cap, d_n, shift, (const uint32_t*)th.as<uint32_t>(),
+                (const uint32_t*)tot.as<uint32_t>(), seg_cap, d_seg_start, d_count);
+    return PMRD_OK;
+}
+
+static int32_t read_count(pmrd_ctx* ctx, const uint32_t* d_count, int64_t* h) {
+    uint32_t v = 0;
+    PMRD_CUDA(ctx, cudaMemcpyAsync(&v, d_count, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    *h_nseg = h;
+    *h = v;
     return PMRD_OK;
 }
 
@@ -108,9 +130,10 @@ template <int MODE, bool GATHER>
 __global__ void __launch_bounds__(128)
 family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload_or_idx,
               const uint64_t* __restrict__ keys_orig, const uint32_t* __restrict__ payload_orig,
-              const uint32_t* __restrict__ fam_start, int64_t n_fam, pmrd_umi_params P, FamOut out) {
+              const uint32_t* __restrict__ fam_start, const uint32_t* __restrict__ d_nfam, int64_t fam_cap,
+              pmrd_umi_params P, FamOut out) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n_fam) return;
+    if (f >= (int64_t)*d_nfam || f >= fam_cap) return;
     const uint32_t lo = fam_start[f], hi = fam_start[f + 1];
     const uint32_t size = hi - lo;
     uint64_t key = keys[lo];
@@ -229,8 +252,11 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
 __global__ void __launch_bounds__(128)
 group_kernel(const uint64_t* __restrict__ fam_key, const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_nalt,
              const uint32_t* __restrict__ fam_cons, const uint32_t* __restrict__ fam_flags,
-             const uint32_t* __restrict__ grp_start, int64_t n_groups, int weighted, pmrd_group_table G) {
+             const uint32_t* __restrict__ grp_start, const uint32_t* __restrict__ d_ngroups, int64_t grp_cap, int weighted,
+             pmrd_group_table G) {
     __shared__ unsigned long long s[4][8];  // [warp][fc, alt, tot, c0..c3]
+    int64_t n_groups = (int64_t)*d_ngroups;
+    if (n_groups > grp_cap) n_groups = grp_cap;
     for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const uint32_t lo = grp_start[g], hi = grp_start[g + 1];
         unsigned long long fc = 0, alt = 0, tot = 0, c[4] = {0, 0, 0, 0};
@@ -333,14 +359,42 @@ int32_t k6_hamming(pmrd_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, int6
 template <bool GATHER>
 static int32_t launch_family(pmrd_ctx* ctx, int mode, const uint64_t* keys, const uint32_t* pl_or_idx,
                              const uint64_t* keys_orig, const uint32_t* payload_orig, const uint32_t* fam_start,
-                             int64_t n_fam, const pmrd_umi_params& P, FamOut out) {
-    const int grid = pmrd_blocks(n_fam, 128);
+                             const uint32_t* d_nfam, int64_t fam_cap, const pmrd_umi_params& P, FamOut out) {
+    const int grid = pmrd_blocks(fam_cap, 128);
     if (mode == PMRD_MODE_WEIGHTED) {
-        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_WEIGHTED, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, n_fam, P, out);
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_WEIGHTED, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, out);
     } else if (mode == PMRD_MODE_MAJORITY) {
-        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_MAJORITY, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, n_fam, P, out);
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_MAJORITY, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, out);
     } else {
-        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_COUNT, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, n_fam, P, out);
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_COUNT, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, out);
+    }
+    return PMRD_OK;
+}
+
+// Sync-free core.  `varying` = mask of key bits that differ (0: find out, costs one sync).
+// d_counts[0] = families, d_counts[1] = groups (device).  EXACT clustering only.
+int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp,
+                                 uint32_t* d_payload_tmp, int64_t n_reads, uint64_t varying, const pmrd_umi_params* params,
+                                 const pmrd_family_table* d_fam, int64_t capacity_f, const pmrd_group_table* d_grp,
+                                 int64_t capacity_g, uint32_t* d_fam_start /*[capacity_f+1]*/,
+                                 uint32_t* d_grp_start /*[capacity_g+1]*/, uint32_t* d_counts) {
+    const pmrd_umi_params P = *params;
+    if (varying == 0) PMRD_TRY(radix_varying_bits(ctx, d_keys, n_reads, &varying));
+    int in_b = 0;
+    PMRD_TRY(radix_sort_pairs(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, varying, &in_b));
+    const uint64_t* sk = in_b ? d_keys_tmp : d_keys;
+    const uint32_t* sp = in_b ? d_payload_tmp : d_payload;
+    PMRD_TRY(find_segments_dev(ctx, sk, n_reads, nullptr, 0, capacity_f, d_fam_start, d_counts));
+    FamOut out{d_fam->key, d_fam->size, d_fam->n_alt, d_fam->consensus, d_fam->qsum, d_fam->n_best, d_fam->flags};
+    PMRD_TRY(launch_family<false>(ctx, P.mode, sk, sp, nullptr, nullptr, d_fam_start, d_counts, capacity_f, P, out));
+    if (d_grp) {
+        PMRD_TRY(find_segments_dev(ctx, d_fam->key, capacity_f, d_counts, 32, capacity_g, d_grp_start, d_counts + 1));
+        int grid = (int)(capacity_g < (int64_t)ctx->sm_count * 32 ? capacity_g : (int64_t)ctx->sm_count * 32);
+        if (grid < 1) grid = 1;
+        PMRD_LAUNCH(ctx, group_kernel, grid, 128, 0, (const uint64_t*)d_fam->key, (const uint32_t*)d_fam->size,
+                    (const uint32_t*)d_fam->n_alt, (const uint32_t*)d_fam->consensus, (const uint32_t*)d_fam->flags,
+                    (const uint32_t*)d_grp_start, (const uint32_t*)(d_counts + 1), capacity_g,
+                    P.mode == PMRD_MODE_WEIGHTED ? 1 : 0, *d_grp);
     }
     return PMRD_OK;
 }
@@ -357,35 +411,33 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
     if (n_groups) *n_groups = 0;
     if (n_reads <= 0) return PMRD_OK;
     PMRD_ARG(ctx, n_reads < (1ll << 31), "n_reads must be < 2^31 per call (chunk the input)");
+    const bool want_groups = d_grp && n_groups;
+    const int64_t fcap = capacity_f < n_reads ? capacity_f : n_reads;
+    const int64_t gcap = want_groups ? (capacity_g < n_reads ? capacity_g : n_reads) : 0;
 
-    DevBuf fam_start;
-    PMRD_CUDA(ctx, fam_start.alloc(ctx->stream, (size_t)(n_reads + 1) * 4));
-    FamOut out{d_fam->key, d_fam->size, d_fam->n_alt, d_fam->consensus, d_fam->qsum, d_fam->n_best, d_fam->flags};
-    int64_t nf = 0;
+    DevBuf fam_start, grp_start, counts;
+    PMRD_CUDA(ctx, fam_start.alloc(ctx->stream, (size_t)(fcap + 1) * 4));
+    PMRD_CUDA(ctx, grp_start.alloc(ctx->stream, (size_t)(gcap + 1) * 4));
+    PMRD_CUDA(ctx, counts.alloc(ctx->stream, 8));
+    PMRD_CUDA(ctx, cudaMemsetAsync(counts.p, 0, 8, ctx->stream));
+    int64_t nf = 0, ng = 0;
 
     if (P.cluster == PMRD_CLUSTER_EXACT) {
-        uint64_t varying = 0;
-        PMRD_TRY(radix_varying_bits(ctx, d_keys, n_reads, &varying));
-        int in_b = 0;
-        PMRD_TRY(radix_sort_pairs(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, varying, &in_b));
-        const uint64_t* sk = in_b ? d_keys_tmp : d_keys;
-        const uint32_t* sp = in_b ? d_payload_tmp : d_payload;
-        PMRD_TRY(find_segments(ctx, sk, n_reads, 0, fam_start.as<uint32_t>(), &nf));
-        if (nf > capacity_f) {
-            snprintf(ctx->err, sizeof(ctx->err), "family capacity %lld < %lld families", (long long)capacity_f, (long long)nf);
-            *n_families = nf;
-            return PMRD_ERR_CAPACITY;
-        }
-        PMRD_TRY(launch_family<false>(ctx, P.mode, sk, sp, nullptr, nullptr, fam_start.as<uint32_t>(), nf, P, out));
+        PMRD_TRY(k5_collapse_exact_nosync(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, 0, params, d_fam, fcap,
+                                          want_groups ? d_grp : nullptr, gcap, fam_start.as<uint32_t>(), grp_start.as<uint32_t>(),
+                                          counts.as<uint32_t>()));
+        PMRD_TRY(read_count(ctx, counts.as<uint32_t>(), &nf));
+        if (want_groups) PMRD_TRY(read_count(ctx, counts.as<uint32_t>() + 1, &ng));
     } else {
         // FIRSTFIT: (1) stable sort read indices by group, (2) sequential first-fit per group,
         // (3) stable sort by (group, cluster), (4) consensus with gather through the index.
-        DevBuf gk, idx, idx_tmp, reps, grp_start0;
+        DevBuf gk, idx, idx_tmp, reps, grp_start0, cnt0;
         PMRD_CUDA(ctx, gk.alloc(ctx->stream, (size_t)n_reads * 8));
         PMRD_CUDA(ctx, idx.alloc(ctx->stream, (size_t)n_reads * 4));
         PMRD_CUDA(ctx, idx_tmp.alloc(ctx->stream, (size_t)n_reads * 4));
         PMRD_CUDA(ctx, reps.alloc(ctx->stream, (size_t)n_reads * 4));
         PMRD_CUDA(ctx, grp_start0.alloc(ctx->stream, (size_t)(n_reads + 1) * 4));
+        PMRD_CUDA(ctx, cnt0.alloc(ctx->stream, 4));
         const int g256 = pmrd_blocks(n_reads, 256);
         PMRD_LAUNCH(ctx, iota_kernel, g256, 256, 0, idx.as<uint32_t>(), n_reads);
         PMRD_LAUNCH(ctx, groupkey_kernel, g256, 256, 0, (const uint64_t*)d_keys, gk.as<uint64_t>(), n_reads);
@@ -398,7 +450,8 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
         uint64_t* ok = in_b ? gk.as<uint64_t>() : d_keys_tmp;
         uint32_t* oi = in_b ? idx.as<uint32_t>() : idx_tmp.as<uint32_t>();
         int64_t ng0 = 0;
-        PMRD_TRY(find_segments(ctx, sk, n_reads, 32, grp_start0.as<uint32_t>(), &ng0));
+        PMRD_TRY(find_segments_dev(ctx, sk, n_reads, nullptr, 32, n_reads, grp_start0.as<uint32_t>(), cnt0.as<uint32_t>()));
+        PMRD_TRY(read_count(ctx, cnt0.as<uint32_t>(), &ng0));
         // new keys (group | cluster) are written into `ok`, at the same positions as sk/si
         PMRD_LAUNCH(ctx, firstfit_kernel, pmrd_blocks(ng0 * 32, 128), 128, 0, (const uint64_t*)sk, (const uint32_t*)si,
                     (const uint64_t*)d_keys, (const uint32_t*)grp_start0.as<uint32_t>(), ng0, P.max_distance,
@@ -409,32 +462,30 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
         PMRD_TRY(radix_sort_pairs(ctx, ok, si, sk, oi, n_reads, varying, &in_b2));
         const uint64_t* fk = in_b2 ? sk : ok;
         const uint32_t* fi = in_b2 ? oi : si;
-        PMRD_TRY(find_segments(ctx, fk, n_reads, 0, fam_start.as<uint32_t>(), &nf));
-        if (nf > capacity_f) {
-            snprintf(ctx->err, sizeof(ctx->err), "family capacity %lld < %lld families", (long long)capacity_f, (long long)nf);
-            *n_families = nf;
-            return PMRD_ERR_CAPACITY;
+        PMRD_TRY(find_segments_dev(ctx, fk, n_reads, nullptr, 0, fcap, fam_start.as<uint32_t>(), counts.as<uint32_t>()));
+        PMRD_TRY(read_count(ctx, counts.as<uint32_t>(), &nf));
+        FamOut out{d_fam->key, d_fam->size, d_fam->n_alt, d_fam->consensus, d_fam->qsum, d_fam->n_best, d_fam->flags};
+        if (nf <= fcap) {
+            PMRD_TRY(launch_family<true>(ctx, P.mode, fk, fi, d_keys, d_payload, fam_start.as<uint32_t>(), counts.as<uint32_t>(), fcap, P, out));
+            if (want_groups) {
+                PMRD_TRY(find_segments_dev(ctx, d_fam->key, nf, nullptr, 32, gcap, grp_start.as<uint32_t>(), counts.as<uint32_t>() + 1));
+                PMRD_TRY(read_count(ctx, counts.as<uint32_t>() + 1, &ng));
+                int grid = (int)(gcap < (int64_t)ctx->sm_count * 32 ? gcap : (int64_t)ctx->sm_count * 32);
+                if (grid < 1) grid = 1;
+                PMRD_LAUNCH(ctx, group_kernel, grid, 128, 0, (const uint64_t*)d_fam->key, (const uint32_t*)d_fam->size,
+                            (const uint32_t*)d_fam->n_alt, (const uint32_t*)d_fam->consensus, (const uint32_t*)d_fam->flags,
+                            (const uint32_t*)grp_start.as<uint32_t>(), (const uint32_t*)(counts.as<uint32_t>() + 1), gcap, 0, *d_grp);
+            }
         }
-        PMRD_TRY(launch_family<true>(ctx, P.mode, fk, fi, d_keys, d_payload, fam_start.as<uint32_t>(), nf, P, out));
-        PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // scratch buffers go out of scope below
-    }
-    *n_families = nf;
-
-    if (d_grp && n_groups) {
-        DevBuf grp_start;
-        PMRD_CUDA(ctx, grp_start.alloc(ctx->stream, (size_t)(nf + 1) * 4));
-        int64_t ng = 0;
-        PMRD_TRY(find_segments(ctx, d_fam->key, nf, 32, grp_start.as<uint32_t>(), &ng));
-        *n_groups = ng;
-        if (ng > capacity_g) {
-            snprintf(ctx->err, sizeof(ctx->err), "group capacity %lld < %lld groups", (long long)capacity_g, (long long)ng);
-            return PMRD_ERR_CAPACITY;
-        }
-        int grid = (int)(ng < (int64_t)ctx->sm_count * 32 ? ng : (int64_t)ctx->sm_count * 32);
-        PMRD_LAUNCH(ctx, group_kernel, grid, 128, 0, (const uint64_t*)d_fam->key, (const uint32_t*)d_fam->size,
-                    (const uint32_t*)d_fam->n_alt, (const uint32_t*)d_fam->consensus, (const uint32_t*)d_fam->flags,
-                    (const uint32_t*)grp_start.as<uint32_t>(), ng, P.mode == PMRD_MODE_WEIGHTED ? 1 : 0, *d_grp);
         PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    *n_families = nf;
+    if (n_groups) *n_groups = ng;
+    if (nf > capacity_f || (want_groups && ng > capacity_g)) {
+        snprintf(ctx->err, sizeof(ctx->err), "capacity too small: %lld families (cap %lld), %lld groups (cap %lld)",
+                 (long long)nf, (long long)capacity_f, (long long)ng, (long long)capacity_g);
+        return PMRD_ERR_CAPACITY;
+    }
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PMRD_OK;
 }

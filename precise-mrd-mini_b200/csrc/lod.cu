@@ -1,0 +1,488 @@
+// lod.cu -- K11: detection-curve fit and its bootstrap CI on the device.
+//
+// Replaces LODAnalyzer._fit_detection_curve / _bootstrap_lod_ci
+// (src/precise_mrd/eval/lod.py:351-408): scipy.optimize.curve_fit(logistic, log10(af), hit,
+// maxfev=2000) == MINPACK lmdif (forward-difference Jacobian, ftol = xtol = 1.49012e-8,
+// gtol = 0, factor = 100, automatic column scaling) from p0 = (1, 1); LoD = 10^((logit(t)-b)/a).
+// curve_fit raises unless lmdif ends with info in 1..4 and the reference then falls back to
+// scipy.interpolate.interp1d(hit, af, fill_value='extrapolate')(t) -- which is NaN for the
+// all-zero hit vectors the reference's own grids produce.  To get
+// the same convergence / fallback decisions this is a statement of the published lmdif
+// algorithm (More, Garbow, Hillstrom, "User Guide for MINPACK-1", ANL-80-74: lmdif, lmpar,
+// qrfac, qrsolv, fdjac2, enorm) specialised to n = 2 parameters, one thread per fit.
+// The 1 + n_boot fits (point estimate + Philox-resampled pairs) run in parallel.
+#include "kernels.cuh"
+#include "rng.cuh"
+
+#define LOD_MAX_M 64
+#define LM_N 2
+
+struct LmProblem {
+    int m;
+    double x[LOD_MAX_M];  // log10(af)
+    double y[LOD_MAX_M];  // hit rate
+};
+
+__host__ __device__ static double lm_enorm(int n, const double* x) {
+    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+    double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
+    const double agiant = rgiant / (double)n;
+    for (int i = 0; i < n; ++i) {
+        const double xabs = fabs(x[i]);
+        if (xabs > rdwarf && xabs < agiant) {
+            s2 += xabs * xabs;
+        } else if (xabs <= rdwarf) {
+            if (xabs > x3max) {
+                const double t = x3max / xabs;
+                s3 = 1.0 + s3 * (t * t);
+                x3max = xabs;
+            } else if (xabs != 0.0) {
+                const double t = xabs / x3max;
+                s3 += t * t;
+            }
+        } else {
+            if (xabs > x1max) {
+                const double t = x1max / xabs;
+                s1 = 1.0 + s1 * (t * t);
+                x1max = xabs;
+            } else {
+                const double t = xabs / x1max;
+                s1 += t * t;
+            }
+        }
+    }
+    if (s1 != 0.0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0.0) {
+        if (s2 >= x3max) return sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    }
+    return x3max * sqrt(s3);
+}
+
+// residuals: logistic(x; a, b) - y     (lod.py:360-361 through curve_fit's wrapper)
+__host__ __device__ static void lm_fcn(const LmProblem& P, const double* p, double* f) {
+    for (int i = 0; i < P.m; ++i) f[i] = 1.0 / (1.0 + exp(-(p[0] * P.x[i] + p[1]))) - P.y[i];
+}
+
+// column-major fjac[j*m + i]
+__host__ __device__ static void lm_qrfac(int m, double* a, int* ipvt, double* rdiag, double* acnorm, double* wa) {
+    const double epsmch = 2.220446049250313e-16;
+    for (int j = 0; j < LM_N; ++j) {
+        acnorm[j] = lm_enorm(m, a + j * m);
+        rdiag[j] = acnorm[j];
+        wa[j] = rdiag[j];
+        ipvt[j] = j;
+    }
+    for (int j = 0; j < LM_N; ++j) {
+        int kmax = j;
+        for (int k = j; k < LM_N; ++k)
+            if (rdiag[k] > rdiag[kmax]) kmax = k;
+        if (kmax != j) {
+            for (int i = 0; i < m; ++i) {
+                const double t = a[j * m + i];
+                a[j * m + i] = a[kmax * m + i];
+                a[kmax * m + i] = t;
+            }
+            rdiag[kmax] = rdiag[j];
+            wa[kmax] = wa[j];
+            const int k = ipvt[j];
+            ipvt[j] = ipvt[kmax];
+            ipvt[kmax] = k;
+        }
+        double ajnorm = lm_enorm(m - j, a + j * m + j);
+        if (ajnorm != 0.0) {
+            if (a[j * m + j] < 0.0) ajnorm = -ajnorm;
+            for (int i = j; i < m; ++i) a[j * m + i] /= ajnorm;
+            a[j * m + j] += 1.0;
+            for (int k = j + 1; k < LM_N; ++k) {
+                double sum = 0.0;
+                for (int i = j; i < m; ++i) sum += a[j * m + i] * a[k * m + i];
+                const double temp = sum / a[j * m + j];
+                for (int i = j; i < m; ++i) a[k * m + i] -= temp * a[j * m + i];
+                if (rdiag[k] != 0.0) {
+                    double t = a[k * m + j] / rdiag[k];
+                    rdiag[k] *= sqrt(fmax(0.0, 1.0 - t * t));
+                    t = rdiag[k] / wa[k];
+                    if (0.05 * (t * t) <= epsmch) {
+                        rdiag[k] = lm_enorm(m - j - 1, a + k * m + j + 1);
+                        wa[k] = rdiag[k];
+                    }
+                }
+            }
+        }
+        rdiag[j] = -ajnorm;
+    }
+}
+
+// r: n x n, r[j*ldr + i] column-major with ldr = m (the top of fjac)
+__host__ __device__ static void lm_qrsolv(double* r, int ldr, const int* ipvt, const double* diag, const double* qtb, double* x,
+                                 double* sdiag, double* wa) {
+    for (int j = 0; j < LM_N; ++j) {
+        for (int i = j; i < LM_N; ++i) r[j * ldr + i] = r[i * ldr + j];
+        x[j] = r[j * ldr + j];
+        wa[j] = qtb[j];
+    }
+    for (int j = 0; j < LM_N; ++j) {
+        const int l = ipvt[j];
+        if (diag[l] != 0.0) {
+            for (int k = j; k < LM_N; ++k) sdiag[k] = 0.0;
+            sdiag[j] = diag[l];
+            double qtbpj = 0.0;
+            for (int k = j; k < LM_N; ++k) {
+                if (sdiag[k] == 0.0) continue;
+                double sn, cs;
+                if (fabs(r[k * ldr + k]) < fabs(sdiag[k])) {
+                    const double cotan = r[k * ldr + k] / sdiag[k];
+                    sn = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
+                    cs = sn * cotan;
+                } else {
+                    const double tn = sdiag[k] / r[k * ldr + k];
+                    cs = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
+                    sn = cs * tn;
+                }
+                r[k * ldr + k] = cs * r[k * ldr + k] + sn * sdiag[k];
+                const double temp = cs * wa[k] + sn * qtbpj;
+                qtbpj = -sn * wa[k] + cs * qtbpj;
+                wa[k] = temp;
+                for (int i = k + 1; i < LM_N; ++i) {
+                    const double t2 = cs * r[k * ldr + i] + sn * sdiag[i];
+                    sdiag[i] = -sn * r[k * ldr + i] + cs * sdiag[i];
+                    r[k * ldr + i] = t2;
+                }
+            }
+        }
+        sdiag[j] = r[j * ldr + j];
+        r[j * ldr + j] = x[j];
+    }
+    int nsing = LM_N;
+    for (int j = 0; j < LM_N; ++j) {
+        if (sdiag[j] == 0.0 && nsing == LM_N) nsing = j;
+        if (nsing < LM_N) wa[j] = 0.0;
+    }
+    for (int k = 1; k <= nsing; ++k) {
+        const int j = nsing - k;
+        double sum = 0.0;
+        for (int i = j + 1; i < nsing; ++i) sum += r[j * ldr + i] * wa[i];
+        wa[j] = (wa[j] - sum) / sdiag[j];
+    }
+    for (int j = 0; j < LM_N; ++j) x[ipvt[j]] = wa[j];
+}
+
+__host__ __device__ static void lm_lmpar(double* r, int ldr, const int* ipvt, const double* diag, const double* qtb, double delta,
+                                double* par, double* x, double* sdiag, double* wa1, double* wa2) {
+    const double dwarf = 2.2250738585072014e-308;
+    int nsing = LM_N;
+    for (int j = 0; j < LM_N; ++j) {
+        wa1[j] = qtb[j];
+        if (r[j * ldr + j] == 0.0 && nsing == LM_N) nsing = j;
+        if (nsing < LM_N) wa1[j] = 0.0;
+    }
+    for (int k = 1; k <= nsing; ++k) {
+        const int j = nsing - k;
+        wa1[j] /= r[j * ldr + j];
+        const double temp = wa1[j];
+        for (int i = 0; i < j; ++i) wa1[i] -= r[j * ldr + i] * temp;
+    }
+    for (int j = 0; j < LM_N; ++j) x[ipvt[j]] = wa1[j];
+    int iter = 0;
+    for (int j = 0; j < LM_N; ++j) wa2[j] = diag[j] * x[j];
+    double dxnorm = lm_enorm(LM_N, wa2);
+    double fp = dxnorm - delta;
+    if (fp <= 0.1 * delta) {
+        *par = 0.0;
+        return;
+    }
+    double parl = 0.0;
+    if (nsing >= LM_N) {
+        for (int j = 0; j < LM_N; ++j) {
+            const int l = ipvt[j];
+            wa1[j] = diag[l] * (wa2[l] / dxnorm);
+        }
+        for (int j = 0; j < LM_N; ++j) {
+            double sum = 0.0;
+            for (int i = 0; i < j; ++i) sum += r[j * ldr + i] * wa1[i];
+            wa1[j] = (wa1[j] - sum) / r[j * ldr + j];
+        }
+        const double temp = lm_enorm(LM_N, wa1);
+        parl = ((fp / delta) / temp) / temp;
+    }
+    for (int j = 0; j < LM_N; ++j) {
+        double sum = 0.0;
+        for (int i = 0; i <= j; ++i) sum += r[j * ldr + i] * qtb[i];
+        wa1[j] = sum / diag[ipvt[j]];
+    }
+    const double gnorm = lm_enorm(LM_N, wa1);
+    double paru = gnorm / delta;
+    if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
+    *par = fmax(*par, parl);
+    *par = fmin(*par, paru);
+    if (*par == 0.0) *par = gnorm / dxnorm;
+    for (;;) {
+        ++iter;
+        if (*par == 0.0) *par = fmax(dwarf, 0.001 * paru);
+        double temp = sqrt(*par);
+        for (int j = 0; j < LM_N; ++j) wa1[j] = temp * diag[j];
+        lm_qrsolv(r, ldr, ipvt, wa1, qtb, x, sdiag, wa2);
+        for (int j = 0; j < LM_N; ++j) wa2[j] = diag[j] * x[j];
+        dxnorm = lm_enorm(LM_N, wa2);
+        temp = fp;
+        fp = dxnorm - delta;
+        if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        for (int j = 0; j < LM_N; ++j) {
+            const int l = ipvt[j];
+            wa1[j] = diag[l] * (wa2[l] / dxnorm);
+        }
+        for (int j = 0; j < LM_N; ++j) {
+            wa1[j] /= sdiag[j];
+            const double t = wa1[j];
+            for (int i = j + 1; i < LM_N; ++i) wa1[i] -= r[j * ldr + i] * t;
+        }
+        temp = lm_enorm(LM_N, wa1);
+        const double parc = ((fp / delta) / temp) / temp;
+        if (fp > 0.0) parl = fmax(parl, *par);
+        if (fp < 0.0) paru = fmin(paru, *par);
+        *par = fmax(parl, *par + parc);
+    }
+}
+
+// returns MINPACK info; p holds the final parameters
+__host__ __device__ static int lm_lmdif(const LmProblem& P, double* x, int maxfev) {
+    const double epsmch = 2.220446049250313e-16;
+    const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
+    const int m = P.m;
+    double fvec[LOD_MAX_M], wa4[LOD_MAX_M], fjac[LM_N * LOD_MAX_M];
+    double diag[LM_N], qtf[LM_N], wa1[LM_N], wa2[LM_N], wa3[LM_N];
+    int ipvt[LM_N];
+    int info = 0, nfev = 0;
+    lm_fcn(P, x, fvec);
+    nfev = 1;
+    double fnorm = lm_enorm(m, fvec);
+    double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
+    int iter = 1;
+    for (;;) {
+        // fdjac2: forward differences, epsfcn = machine epsilon
+        {
+            const double eps = sqrt(epsmch);
+            for (int j = 0; j < LM_N; ++j) {
+                const double temp = x[j];
+                double h = eps * fabs(temp);
+                if (h == 0.0) h = eps;
+                x[j] = temp + h;
+                lm_fcn(P, x, wa4);
+                x[j] = temp;
+                for (int i = 0; i < m; ++i) fjac[j * m + i] = (wa4[i] - fvec[i]) / h;
+            }
+            nfev += LM_N;
+        }
+        lm_qrfac(m, fjac, ipvt, wa1, wa2, wa3);
+        if (iter == 1) {
+            for (int j = 0; j < LM_N; ++j) {
+                diag[j] = wa2[j];
+                if (wa2[j] == 0.0) diag[j] = 1.0;
+            }
+            for (int j = 0; j < LM_N; ++j) wa3[j] = diag[j] * x[j];
+            xnorm = lm_enorm(LM_N, wa3);
+            delta = factor * xnorm;
+            if (delta == 0.0) delta = factor;
+        }
+        for (int i = 0; i < m; ++i) wa4[i] = fvec[i];
+        for (int j = 0; j < LM_N; ++j) {
+            if (fjac[j * m + j] != 0.0) {
+                double sum = 0.0;
+                for (int i = j; i < m; ++i) sum += fjac[j * m + i] * wa4[i];
+                const double temp = -sum / fjac[j * m + j];
+                for (int i = j; i < m; ++i) wa4[i] += fjac[j * m + i] * temp;
+            }
+            fjac[j * m + j] = wa1[j];
+            qtf[j] = wa4[j];
+        }
+        gnorm = 0.0;
+        if (fnorm != 0.0) {
+            for (int j = 0; j < LM_N; ++j) {
+                const int l = ipvt[j];
+                if (wa2[l] != 0.0) {
+                    double sum = 0.0;
+                    for (int i = 0; i <= j; ++i) sum += fjac[j * m + i] * (qtf[i] / fnorm);
+                    gnorm = fmax(gnorm, fabs(sum / wa2[l]));
+                }
+            }
+        }
+        if (gnorm <= gtol) info = 4;
+        if (info != 0) break;
+        for (int j = 0; j < LM_N; ++j) diag[j] = fmax(diag[j], wa2[j]);
+        double ratio;
+        do {
+            lm_lmpar(fjac, m, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wa4);
+            for (int j = 0; j < LM_N; ++j) {
+                wa1[j] = -wa1[j];
+                wa2[j] = x[j] + wa1[j];
+                wa3[j] = diag[j] * wa1[j];
+            }
+            const double pnorm = lm_enorm(LM_N, wa3);
+            if (iter == 1) delta = fmin(delta, pnorm);
+            lm_fcn(P, wa2, wa4);
+            ++nfev;
+            const double fnorm1 = lm_enorm(m, wa4);
+            double actred = -1.0;
+            if (0.1 * fnorm1 < fnorm) {
+                const double t = fnorm1 / fnorm;
+                actred = 1.0 - t * t;
+            }
+            for (int j = 0; j < LM_N; ++j) {
+                wa3[j] = 0.0;
+                const double temp = wa1[ipvt[j]];
+                for (int i = 0; i <= j; ++i) wa3[i] += fjac[j * m + i] * temp;
+            }
+            const double temp1 = lm_enorm(LM_N, wa3) / fnorm;
+            const double temp2 = (sqrt(par) * pnorm) / fnorm;
+            const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+            const double dirder = -(temp1 * temp1 + temp2 * temp2);
+            ratio = 0.0;
+            if (prered != 0.0) ratio = actred / prered;
+            if (ratio <= 0.25) {
+                double temp;
+                if (actred >= 0.0) temp = 0.5;
+                else temp = 0.5 * dirder / (dirder + 0.5 * actred);
+                if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+                delta = temp * fmin(delta, pnorm / 0.1);
+                par /= temp;
+            } else if (par == 0.0 || ratio >= 0.75) {
+                delta = pnorm / 0.5;
+                par *= 0.5;
+            }
+            if (ratio >= 1e-4) {
+                for (int j = 0; j < LM_N; ++j) {
+                    x[j] = wa2[j];
+                    wa2[j] = diag[j] * x[j];
+                }
+                for (int i = 0; i < m; ++i) fvec[i] = wa4[i];
+                xnorm = lm_enorm(LM_N, wa2);
+                fnorm = fnorm1;
+                ++iter;
+            }
+            if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) info = 1;
+            if (delta <= xtol * xnorm) info = 2;
+            if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && info == 2) info = 3;
+            if (info != 0) break;
+            if (nfev >= maxfev) info = 5;
+            if (fabs(actred) <= epsmch && prered <= epsmch && 0.5 * ratio <= 1.0) info = 6;
+            if (delta <= epsmch * xnorm) info = 7;
+            if (gnorm <= epsmch) info = 8;
+            if (info != 0) break;
+        } while (ratio < 1e-4);
+        if (info != 0) break;
+    }
+    return info;
+}
+
+// scipy.interpolate.interp1d(hit, af, bounds_error=False, fill_value='extrapolate')(target)
+__host__ __device__ static double lod_interp_fallback(const LmProblem& P, const double* af, double target) {
+    const int m = P.m;
+    if (m <= 1) return af[0];
+    int ord[LOD_MAX_M];
+    for (int i = 0; i < m; ++i) ord[i] = i;
+    for (int i = 1; i < m; ++i) {  // stable insertion sort by hit rate (interp1d: mergesort argsort)
+        const int v = ord[i];
+        int j = i - 1;
+        while (j >= 0 && P.y[ord[j]] > P.y[v]) { ord[j + 1] = ord[j]; --j; }
+        ord[j + 1] = v;
+    }
+    int idx = 0;  // searchsorted(x, target) side='left'
+    while (idx < m && P.y[ord[idx]] < target) ++idx;
+    idx = idx < 1 ? 1 : (idx > m - 1 ? m - 1 : idx);
+    const double xlo = P.y[ord[idx - 1]], xhi = P.y[ord[idx]];
+    const double ylo = af[ord[idx - 1]], yhi = af[ord[idx]];
+    // scipy _call_linear: ((x - x_lo)/(x_hi - x_lo)) * y_hi + ((x_hi - x)/(x_hi - x_lo)) * y_lo
+    // (inf - inf = NaN when the bracketing hit rates coincide -- the reference's all-zero case)
+    return ((target - xlo) / (xhi - xlo)) * yhi + ((xhi - target) / (xhi - xlo)) * ylo;
+}
+
+__host__ __device__ static double lod_fit_one(const LmProblem& P, const double* af, double target) {
+    double p[2] = {1.0, 1.0};
+    bool finite_in = true;
+    for (int i = 0; i < P.m; ++i) finite_in &= isfinite(P.x[i]) && isfinite(P.y[i]);
+    int info = finite_in ? lm_lmdif(P, p, 2000) : 0;
+    if (info >= 1 && info <= 4) {
+        // lod.py:365-371
+        const double logit_target = log(target / (1.0 - target));
+        return pow(10.0, (logit_target - p[1]) / p[0]);
+    }
+    return lod_interp_fallback(P, af, target);
+}
+
+// thread 0 of the grid: point estimate; threads 1..n_boot: resampled pairs (lod.py:389-399)
+__global__ void __launch_bounds__(64)
+lod_fit_kernel(uint64_t seed, uint64_t stream_id, const double* __restrict__ af, const double* __restrict__ hit, int m,
+               double target, int n_boot, double* __restrict__ fits /*[1+n_boot]*/) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_boot) return;
+    LmProblem P;
+    double afs[LOD_MAX_M];
+    P.m = m;
+    const Philox ph(seed);
+    for (int i = 0; i < m; ++i) {
+        int src = i;
+        if (t > 0) {
+            const uint4 r = ph((uint32_t)i, (uint32_t)t, (uint32_t)stream_id, (PMRD_STREAM_LODBOOT << 24) | (uint32_t)((stream_id >> 32) & 0xffffffu));
+            src = (int)(u53(r.x, r.y) * (double)m);
+            if (src >= m) src = m - 1;
+        }
+        afs[i] = af[src];
+        P.x[i] = log10(af[src]);
+        P.y[i] = hit[src];
+    }
+    fits[t] = lod_fit_one(P, afs, target);
+}
+
+// numpy.percentile(method='linear') incl. its lerp form; NaN in -> NaN out
+__host__ __device__ static double np_percentile_sorted(const double* s, int n, double q) {
+    const double pos = q / 100.0 * (double)(n - 1);
+    const int lo = (int)floor(pos);
+    const int hi = lo + 1 < n ? lo + 1 : n - 1;
+    const double t = pos - (double)lo;
+    const double a = s[lo], b = s[hi], d = b - a;
+    return t >= 0.5 ? b - d * (1.0 - t) : a + d * t;
+}
+
+__global__ void __launch_bounds__(256) lod_ci_kernel(const double* __restrict__ fits, int n_boot, double* __restrict__ out3) {
+    extern __shared__ double s_v[];
+    __shared__ int s_nan;
+    if (threadIdx.x == 0) s_nan = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_boot; i += blockDim.x) {
+        const double v = fits[1 + i];
+        if (isnan(v)) s_nan = 1;
+        // rank by counting (ties broken by index): O(n^2) but n_boot is a few hundred
+        int rank = 0;
+        for (int j = 0; j < n_boot; ++j) {
+            const double w = fits[1 + j];
+            rank += (w < v) || (w == v && j < i);
+        }
+        if (!isnan(v)) s_v[rank] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out3[0] = fits[0];
+        if (n_boot <= 0) {
+            out3[1] = out3[2] = NAN;
+        } else if (s_nan) {
+            out3[1] = out3[2] = NAN;  // np.percentile propagates NaN
+        } else {
+            out3[1] = np_percentile_sorted(s_v, n_boot, 2.5);
+            out3[2] = np_percentile_sorted(s_v, n_boot, 97.5);
+        }
+    }
+}
+
+int32_t k11_fit_lod(pmrd_ctx* ctx, const double* d_af, const double* d_hit, int32_t n, double target, int32_t n_boot,
+                    uint64_t stream_id, double* d_out3) {
+    PMRD_ARG(ctx, n >= 1 && n <= LOD_MAX_M, "1 <= n <= 64 curve points");
+    PMRD_ARG(ctx, n_boot >= 0 && n_boot <= 4096, "0 <= n_boot <= 4096");
+    PMRD_ARG(ctx, target > 0.0 && target < 1.0, "0 < target < 1");
+    DevBuf fits;
+    PMRD_CUDA(ctx, fits.alloc(ctx->stream, (size_t)(n_boot + 1) * 8));
+    PMRD_LAUNCH(ctx, lod_fit_kernel, pmrd_blocks(n_boot + 1, 64), 64, 0, ctx->seed, stream_id, d_af, d_hit, (int)n, target,
+                (int)n_boot, fits.as<double>());
+    PMRD_LAUNCH(ctx, lod_ci_kernel, 1, 256, (size_t)(n_boot > 0 ? n_boot : 1) * 8, (const double*)fits.as<double>(), (int)n_boot, d_out3);
+    return PMRD_OK;
+}

@@ -1,0 +1,258 @@
+// pipeline.cu -- simulate -> collapse -> call for a batch of cells with reads resident in HBM.
+// This is the bench "step" and the engine under eval-lob / eval-lod / eval-contamination:
+//   reads.cu  (K2/K3)  generate reads of every cell of the batch, scrambled
+//   collapse  (K4-K7)  radix sort -> families -> weighted consensus -> per-cell counts
+//   K10-lite           error rate from the negative-control cells exactly as
+//                      fit_error_model + call_mrd combine them: mean over 64 contexts of
+//                      (n_var/n_neg) * U(0.5,2)      (error_model.py:153-156, call.py:178)
+//   K8, K9             two-sided tail p per cell, BH over the batch (call.py:182-229)
+#include "kernels.cuh"
+#include "rng.cuh"
+#include <new>
+
+#include "reads.cuh"
+
+int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp,
+                                 uint32_t* d_payload_tmp, int64_t n_reads, uint64_t varying, const pmrd_umi_params* params,
+                                 const pmrd_family_table* d_fam, int64_t capacity_f, const pmrd_group_table* d_grp,
+                                 int64_t capacity_g, uint32_t* d_fam_start, uint32_t* d_grp_start, uint32_t* d_counts);
+
+// scatter the group table into per-cell arrays (cells without reads keep zeros)
+__global__ void __launch_bounds__(256)
+cell_counts_kernel(const uint32_t* __restrict__ grp_id, const uint32_t* __restrict__ grp_cons /*[G*4]*/,
+                   const uint32_t* __restrict__ d_ngroups, uint32_t group_base, int64_t n_cells,
+                   const uint8_t* __restrict__ alt_allele, int64_t* __restrict__ n_total, int64_t* __restrict__ n_variants) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (int64_t)*d_ngroups || g >= n_cells) return;
+    const int64_t c = (int64_t)grp_id[g] - (int64_t)group_base;
+    if (c < 0 || c >= n_cells) return;
+    const uint32_t* cc = grp_cons + g * 4;
+    n_total[c] = (int64_t)cc[0] + cc[1] + cc[2] + cc[3];
+    n_variants[c] = cc[alt_allele[c]];
+}
+
+// per-cell family counts: number of family-table rows per group
+__global__ void __launch_bounds__(256)
+cell_family_count_kernel(const uint64_t* __restrict__ fam_key, const uint32_t* __restrict__ d_nfam, uint32_t group_base,
+                         int64_t n_cells, unsigned long long* __restrict__ n_families) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = f < (int64_t)*d_nfam;
+    const uint32_t g = valid ? (uint32_t)(fam_key[f] >> 32) : 0xffffffffu;
+    const uint32_t m = __match_any_sync(0xffffffffu, g);
+    if (valid && (m & lanemask_lt()) == 0) {
+        const int64_t c = (int64_t)g - (int64_t)group_base;
+        if (c >= 0 && c < n_cells) atomicAdd(&n_families[c], (unsigned long long)__popc(m));
+    }
+}
+
+// single block: rate = sum(n_var)/sum(n_tot) over negative cells; mean of 64 context rates
+__global__ void __launch_bounds__(256)
+error_rate_kernel(uint64_t seed, uint64_t stream_id, const int64_t* __restrict__ n_total, const int64_t* __restrict__ n_variants,
+                  const uint8_t* __restrict__ is_negative, int64_t n_cells, double* __restrict__ mean_rate /*[1]*/,
+                  int64_t* __restrict__ neg_counts /*[2]*/) {
+    __shared__ unsigned long long s_n[8], s_v[8];
+    __shared__ double s_mod[64];
+    unsigned long long n = 0, v = 0;
+    for (int64_t i = threadIdx.x; i < n_cells; i += blockDim.x) {
+        if (is_negative[i]) {
+            n += (unsigned long long)n_total[i];
+            v += (unsigned long long)n_variants[i];
+        }
+    }
+    n = warp_sum(n);
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) { s_n[threadIdx.x >> 5] = n; s_v[threadIdx.x >> 5] = v; }
+    if (threadIdx.x < 64) {
+        const Philox ph(seed);
+        const uint4 b = ph(0, threadIdx.x, (uint32_t)stream_id, (PMRD_STREAM_ERRMODEL << 24) | (uint32_t)((stream_id >> 32) & 0xffffffu));
+        s_mod[threadIdx.x] = 0.5 + 1.5 * u53(b.x, b.y);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long nn = 0, vv = 0;
+        for (int w = 0; w < 8; ++w) { nn += s_n[w]; vv += s_v[w]; }
+        const double vr = nn > 0 ? (double)vv / (double)nn : 0.0;
+        // error_rate.mean() over the 64 contexts (call.py:178), summed in context order
+        double acc = 0.0;
+        for (int c = 0; c < 64; ++c) acc += vr * s_mod[c];
+        mean_rate[0] = acc / 64.0;
+        neg_counts[0] = (int64_t)nn;
+        neg_counts[1] = (int64_t)vv;
+    }
+}
+
+// ---------------------------------------------------------------- plan -------------------
+// A plan owns every buffer of one batch of cells, so that run() only enqueues kernels:
+// no allocation, no host sync, no host<->device copy inside the step.
+struct pmrd_plan {
+    ReadPlan reads;
+    pmrd_umi_params up;
+    double neg_af_max, alpha;
+    int32_t test_type, alternative;
+    int64_t n_cells, fcap;
+    uint64_t varying;
+    uint64_t stream_id;
+    DevBuf keys, keys_tmp, pl, pl_tmp;
+    DevBuf fk, fs, fa, fc, fq, fn, ff, fam_start;
+    DevBuf gg, gf, gc, ga, gt, grp_start, counts;
+    DevBuf alt, neg, negc, mean_rate;
+    DevBuf o_reads, o_fam, o_tot, o_var, o_p, o_q, o_sig;
+};
+
+static uint64_t varying_mask_for(int64_t n_cells) {
+    uint64_t m = 0xffffffull;  // 24 UMI bits
+    int gb = 0;
+    while ((1ll << gb) < n_cells) ++gb;
+    if (gb > 0) m |= ((1ull << gb) - 1ull) << 32;
+    return m;
+}
+
+int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                    int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, double neg_af_max,
+                    int32_t test_type, int32_t alternative, double alpha, pmrd_plan** out) {
+    PMRD_ARG(ctx, out != nullptr, "out");
+    *out = nullptr;
+    PMRD_ARG(ctx, n_cells > 0 && n_cells < (1ll << 30), "n_cells");
+    PMRD_ARG(ctx, h_cell_id && h_n_families, "null cell arrays");
+    PMRD_ARG(ctx, up && up->mode == PMRD_MODE_WEIGHTED && up->cluster == PMRD_CLUSTER_EXACT, "pipeline needs WEIGHTED/EXACT umi params");
+    PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || test_type == PMRD_TEST_BINOMIAL, "Unknown test type");
+    pmrd_plan* P = new (std::nothrow) pmrd_plan();
+    PMRD_ARG(ctx, P != nullptr, "out of host memory");
+    P->up = *up; P->neg_af_max = neg_af_max; P->alpha = alpha; P->test_type = test_type; P->alternative = alternative;
+    P->n_cells = n_cells;
+    P->stream_id = (uint64_t)h_cell_id[0];
+    int32_t st = reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, 0, sp, &P->reads, nullptr);
+    if (st != PMRD_OK) { delete P; return st; }
+    if (P->reads.n_reads >= (1ll << 31)) {
+        delete P;
+        PMRD_ARG(ctx, false, "batch too large: chunk the cells so that reads < 2^31");
+    }
+    P->varying = varying_mask_for(n_cells);
+    const size_t n = (size_t)(P->reads.n_reads > 0 ? P->reads.n_reads : 1);
+    // UMI merging can only lower the family count; hopped reads can open new (cell, UMI) families
+    P->fcap = (sp->hop_rate > 0.0 ? P->reads.n_reads : P->reads.n_fam);
+    if (P->fcap < 1) P->fcap = 1;
+    const size_t f = (size_t)P->fcap, c = (size_t)n_cells;
+    cudaError_t e = cudaSuccess;
+    auto A = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.alloc(ctx->stream, bytes); };
+    A(P->keys, n * 8); A(P->keys_tmp, n * 8); A(P->pl, n * 4); A(P->pl_tmp, n * 4);
+    A(P->fk, f * 8); A(P->fs, f * 4); A(P->fa, f * 4); A(P->fc, f * 4); A(P->fq, f * 4); A(P->fn, f * 4); A(P->ff, f * 4);
+    A(P->fam_start, (f + 1) * 4);
+    A(P->gg, c * 4); A(P->gf, c * 4); A(P->gc, c * 16); A(P->ga, c * 8); A(P->gt, c * 8); A(P->grp_start, (c + 1) * 4);
+    A(P->counts, 8); A(P->alt, c); A(P->neg, c); A(P->negc, 16); A(P->mean_rate, 8);
+    A(P->o_reads, c * 8); A(P->o_fam, c * 8); A(P->o_tot, c * 8); A(P->o_var, c * 8); A(P->o_p, c * 8); A(P->o_q, c * 8); A(P->o_sig, c);
+    uint8_t* h_alt = (uint8_t*)malloc(c * 2);
+    if (e == cudaSuccess && h_alt) {
+        uint8_t* h_neg = h_alt + c;
+        bool any_neg = false;
+        double min_af = INFINITY;
+        for (int64_t i = 0; i < n_cells; ++i) {
+            h_alt[i] = (uint8_t)pmrd_cell_alt_allele((uint64_t)h_cell_id[i]);
+            const double a = h_af ? h_af[i] : 0.0;
+            h_neg[i] = a <= neg_af_max;
+            any_neg |= h_neg[i] != 0;
+            if (a < min_af) min_af = a;
+        }
+        if (!any_neg)  // error_model.py:146-149 fallback: the lowest-AF samples
+            for (int64_t i = 0; i < n_cells; ++i) h_neg[i] = (h_af ? h_af[i] : 0.0) == min_af;
+        e = cudaMemcpyAsync(P->alt.p, h_alt, c, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(P->neg.p, h_neg, c, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    }
+    const bool oom = h_alt == nullptr;
+    free(h_alt);
+    if (e != cudaSuccess || oom) {
+        snprintf(ctx->err, sizeof(ctx->err), "plan_create: %s", oom ? "out of host memory" : cudaGetErrorString(e));
+        delete P;
+        return oom ? PMRD_ERR_ARG : PMRD_ERR_CUDA;
+    }
+    *out = P;
+    return PMRD_OK;
+}
+
+// ---- the three stages of one step; each only enqueues kernels (no sync, no allocation of
+// plan buffers) ------------------------------------------------------------------------
+int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P) {
+    // family sizes -> read offsets -> reads (scrambled)
+    PMRD_TRY(reads_plan_sizes(ctx, &P->reads));
+    PMRD_TRY(reads_plan_generate(ctx, &P->reads, P->keys.as<uint64_t>(), P->pl.as<uint32_t>()));
+    return PMRD_OK;
+}
+
+int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P) {
+    const int64_t n_cells = P->n_cells, n_reads = P->reads.n_reads;
+    pmrd_family_table fam{P->fk.as<uint64_t>(), P->fs.as<uint32_t>(), P->fa.as<uint32_t>(), P->fc.as<uint32_t>(),
+                          P->fq.as<uint32_t>(), P->fn.as<uint32_t>(), P->ff.as<uint32_t>()};
+    pmrd_group_table grp{P->gg.as<uint32_t>(), P->gf.as<uint32_t>(), P->gc.as<uint32_t>(), P->ga.as<uint64_t>(), P->gt.as<uint64_t>()};
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->counts.p, 0, 8, ctx->stream));
+    if (n_reads > 0)
+        PMRD_TRY(k5_collapse_exact_nosync(ctx, P->keys.as<uint64_t>(), P->pl.as<uint32_t>(), P->keys_tmp.as<uint64_t>(),
+                                          P->pl_tmp.as<uint32_t>(), n_reads, P->varying, &P->up, &fam, P->fcap, &grp, n_cells,
+                                          P->fam_start.as<uint32_t>(), P->grp_start.as<uint32_t>(), P->counts.as<uint32_t>()));
+    return PMRD_OK;
+}
+
+int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
+    const int64_t n_cells = P->n_cells;
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_tot.p, 0, 8 * (size_t)n_cells, ctx->stream));
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_var.p, 0, 8 * (size_t)n_cells, ctx->stream));
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_fam.p, 0, 8 * (size_t)n_cells, ctx->stream));
+    // per-cell counts (grids sized by capacity; kernels read the true counts from the device)
+    PMRD_LAUNCH(ctx, cell_counts_kernel, pmrd_blocks(n_cells, 256), 256, 0, (const uint32_t*)P->gg.as<uint32_t>(),
+                (const uint32_t*)P->gc.as<uint32_t>(), (const uint32_t*)(P->counts.as<uint32_t>() + 1), 0u, n_cells,
+                (const uint8_t*)P->alt.as<uint8_t>(), P->o_tot.as<int64_t>(), P->o_var.as<int64_t>());
+    PMRD_LAUNCH(ctx, cell_family_count_kernel, pmrd_blocks(P->fcap, 256), 256, 0, (const uint64_t*)P->fk.as<uint64_t>(),
+                (const uint32_t*)P->counts.as<uint32_t>(), 0u, n_cells, (unsigned long long*)P->o_fam.as<int64_t>());
+    // error rate from the negative controls, tail p per cell, BH over the batch
+    PMRD_LAUNCH(ctx, error_rate_kernel, 1, 256, 0, ctx->seed, P->stream_id, (const int64_t*)P->o_tot.as<int64_t>(),
+                (const int64_t*)P->o_var.as<int64_t>(), (const uint8_t*)P->neg.as<uint8_t>(), n_cells, P->mean_rate.as<double>(),
+                P->negc.as<int64_t>());
+    PMRD_TRY(k8_pvalues(ctx, P->o_var.as<int64_t>(), P->o_tot.as<int64_t>(), P->mean_rate.as<double>(), 0, n_cells, P->test_type,
+                        P->alternative, P->o_p.as<double>()));
+    PMRD_TRY(k9_bh(ctx, P->o_p.as<double>(), n_cells, P->alpha, P->o_sig.as<uint8_t>(), P->o_q.as<double>()));
+    return PMRD_OK;
+}
+
+int32_t plan_run(pmrd_ctx* ctx, pmrd_plan* P) {
+    PMRD_TRY(plan_run_simulate(ctx, P));
+    PMRD_TRY(plan_run_collapse(ctx, P));
+    return plan_run_call(ctx, P);
+}
+
+// per-cell read counts from the plan's read offsets (cheap; not part of the timed step)
+__global__ void __launch_bounds__(256)
+cell_read_count_kernel(const uint64_t* __restrict__ read_offset, const int64_t* __restrict__ fam_offsets, int64_t n_cells,
+                       int64_t n_fam, int64_t n_reads, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const int64_t f0 = fam_offsets[i], f1 = fam_offsets[i + 1];
+    const int64_t r0 = f0 < n_fam ? (int64_t)read_offset[f0] : n_reads;
+    const int64_t r1 = f1 < n_fam ? (int64_t)read_offset[f1] : n_reads;
+    out[i] = r1 - r0;
+}
+
+int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h, double* h_mean_rate, int64_t* h_totals /*[3]: reads, families, groups*/) {
+    const size_t c = (size_t)P->n_cells;
+    PMRD_LAUNCH(ctx, cell_read_count_kernel, pmrd_blocks(P->n_cells, 256), 256, 0, (const uint64_t*)P->reads.read_offset.as<uint64_t>(),
+                (const int64_t*)P->reads.fam_offsets.as<int64_t>(), P->n_cells, P->reads.n_fam, P->reads.n_reads, P->o_reads.as<int64_t>());
+    auto D = [&](void* dst, const DevBuf& b, size_t bytes) -> cudaError_t {
+        return dst ? cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
+    };
+    if (h) {
+        PMRD_CUDA(ctx, D(h->n_reads, P->o_reads, c * 8)); PMRD_CUDA(ctx, D(h->n_families, P->o_fam, c * 8));
+        PMRD_CUDA(ctx, D(h->n_total, P->o_tot, c * 8)); PMRD_CUDA(ctx, D(h->n_variants, P->o_var, c * 8));
+        PMRD_CUDA(ctx, D(h->p_value, P->o_p, c * 8)); PMRD_CUDA(ctx, D(h->p_adjusted, P->o_q, c * 8));
+        PMRD_CUDA(ctx, D(h->significant, P->o_sig, c));
+    }
+    PMRD_CUDA(ctx, D(h_mean_rate, P->mean_rate, 8));
+    uint32_t cnt[2] = {0, 0};
+    PMRD_CUDA(ctx, cudaMemcpyAsync(cnt, P->counts.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_totals) { h_totals[0] = P->reads.n_reads; h_totals[1] = cnt[0]; h_totals[2] = cnt[1]; }
+    return PMRD_OK;
+}
+
+void plan_destroy(pmrd_plan* P) { delete P; }
+
+int64_t plan_n_reads(const pmrd_plan* P) { return P ? P->reads.n_reads : 0; }
+int64_t plan_n_families(const pmrd_plan* P) { return P ? P->reads.n_fam : 0; }

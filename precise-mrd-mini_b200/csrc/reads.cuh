@@ -1,0 +1,32 @@
+// reads.cuh -- host-visible pieces of the read-level generator (reads.cu).
+#pragma once
+#include "common.cuh"
+
+struct ReadCell {
+    uint64_t cell_id;
+    double af;
+    int64_t fam_offset;  // first global family index of this cell in the batch
+    uint32_t group;
+    uint32_t ref_allele, alt_allele;
+    uint32_t pad;
+};
+
+struct ReadPlan {
+    DevBuf cells, fam_offsets, fam_size, read_offset, total;
+    pmrd_read_sim_params sp;
+    int64_t n_cells = 0;
+    int64_t n_fam = 0;
+    int64_t n_reads = 0;
+};
+
+// allele convention of the generator: ref = cell_id & 3, alt = one of the other three
+static inline uint32_t pmrd_cell_ref_allele(uint64_t cell_id) { return (uint32_t)(cell_id & 3u); }
+static inline uint32_t pmrd_cell_alt_allele(uint64_t cell_id) {
+    return (pmrd_cell_ref_allele(cell_id) + 1u + (uint32_t)((cell_id >> 2) % 3u)) & 3u;
+}
+
+int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                         int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, ReadPlan* plan,
+                         int64_t* h_read_offsets);
+int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan);
+int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload);

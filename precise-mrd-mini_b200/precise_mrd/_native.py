@@ -263,6 +263,153 @@ class Context:
         return d
 
 
+    # -- K1 ------------------------------------------------------------------------------
+    def simulate_cells(self, cell_id, af, depth, max_family_size: int) -> Dict[str, np.ndarray]:
+        cell_id = _arr(cell_id, np.int64)
+        af = _arr(af, np.float64)
+        depth = _arr(depth, np.int64)
+        c = cell_id.shape[0]
+        out = {"background_rate": np.zeros(c), "mean_family_size": np.zeros(c, np.int64),
+               "n_true_variants": np.zeros(c, np.int64), "n_false_positives": np.zeros(c, np.int64),
+               "mean_quality": np.zeros(c)}
+        t = CellTable(*[out[n].ctypes.data for n, _ in CellTable._fields_])
+        self._check(self.lib.pmrd_simulate_cells(self.h, _ptr(cell_id), _ptr(af), _ptr(depth), C.c_int64(c),
+                                                 C.c_int32(max_family_size), C.byref(t)))
+        return out
+
+    # -- K2 (G-D) ------------------------------------------------------------------------
+    def collapse_families(self, cell_id, af, n_families, background_rate, mean_family_size, params: UmiParams,
+                          variant: int = 2, count_only: bool = False):
+        cell_id = _arr(cell_id, np.int64)
+        af = _arr(af, np.float64)
+        nf = _arr(n_families, np.int64)
+        bg = _arr(background_rate, np.float64)
+        mfs = _arr(mean_family_size, np.float64)
+        c = cell_id.shape[0]
+        offs = np.zeros(c + 1, np.int64)
+        args = (self.h, _ptr(cell_id), _ptr(af), _ptr(nf), _ptr(bg), _ptr(mfs), C.c_int64(c), C.byref(params), C.c_int32(variant))
+        self._check(self.lib.pmrd_collapse_families(*args, _ptr(offs), None, C.c_int64(0)))
+        if count_only:
+            return offs, None
+        R = int(offs[-1])
+        cap = max(R, 1)
+        out = {"cell": np.zeros(cap, np.int32), "family_id": np.zeros(cap, np.int32), "family_size": np.zeros(cap, np.int32),
+               "quality_score": np.zeros(cap), "consensus_agreement": np.zeros(cap), "flags": np.zeros(cap, np.uint8)}
+        t = GdFamilyTable(*[out[n].ctypes.data for n, _ in GdFamilyTable._fields_])
+        self._check(self.lib.pmrd_collapse_families(*args, _ptr(offs), C.byref(t), C.c_int64(cap)))
+        return offs, {k: v[:R] for k, v in out.items()}
+
+    # -- K10 -----------------------------------------------------------------------------
+    def error_model(self, n_neg: int, n_var: int, n_boot: int = 100, stream_id: int = 0):
+        r, lo, hi = np.zeros(64), np.zeros(64), np.zeros(64)
+        self._check(self.lib.pmrd_error_model(self.h, C.c_int64(n_neg), C.c_int64(n_var), C.c_int32(n_boot),
+                                              C.c_uint64(stream_id), _ptr(r), _ptr(lo), _ptr(hi)))
+        return r, lo, hi
+
+    # -- read-level simulate -------------------------------------------------------------
+    def simulate_reads_count(self, cell_id, n_families, sp: ReadSimParams) -> np.ndarray:
+        cell_id = _arr(cell_id, np.int64)
+        nf = _arr(n_families, np.int64)
+        offs = np.zeros(cell_id.shape[0] + 1, np.int64)
+        self._check(self.lib.pmrd_simulate_reads_count(self.h, _ptr(cell_id), _ptr(nf), C.c_int64(cell_id.shape[0]),
+                                                       C.byref(sp), _ptr(offs)))
+        return offs
+
+    def simulate_reads(self, cell_id, af, n_families, sp: ReadSimParams, group_base: int = 0):
+        cell_id = _arr(cell_id, np.int64)
+        af = _arr(af, np.float64)
+        nf = _arr(n_families, np.int64)
+        n = int(self.simulate_reads_count(cell_id, nf, sp)[-1])
+        keys = np.zeros(max(n, 1), np.uint64)
+        payload = np.zeros(max(n, 1), np.uint32)
+        got = C.c_int64(0)
+        self._check(self.lib.pmrd_simulate_reads(self.h, _ptr(cell_id), _ptr(af), _ptr(nf), C.c_int64(cell_id.shape[0]),
+                                                 C.c_uint32(group_base), C.byref(sp), _ptr(keys), _ptr(payload),
+                                                 C.c_int64(max(n, 1)), C.byref(got)))
+        return keys[:got.value], payload[:got.value]
+
+    # -- fused pipeline ------------------------------------------------------------------
+    def pipeline_cells(self, cell_id, af, n_families, sp: ReadSimParams, up: UmiParams, neg_af_max: float = 1e-4,
+                       test_type: int = TEST_POISSON, alternative: int = ALT_TWO_SIDED, alpha: float = 0.05):
+        plan = Plan(self, cell_id, af, n_families, sp, up, neg_af_max, test_type, alternative, alpha)
+        try:
+            plan.run()
+            return plan.results()
+        finally:
+            plan.close()
+
+    # -- K11 -----------------------------------------------------------------------------
+    def fit_lod(self, af, hit, target: float = 0.95, n_boot: int = 200, stream_id: int = 0):
+        af = _arr(af, np.float64)
+        hit = _arr(hit, np.float64)
+        out = np.zeros(3)
+        self._check(self.lib.pmrd_fit_lod(self.h, _ptr(af), _ptr(hit), C.c_int32(af.shape[0]), C.c_double(target),
+                                          C.c_int32(n_boot), C.c_uint64(stream_id), _ptr(out)))
+        return float(out[0]), float(out[1]), float(out[2])
+
+
+class Plan:
+    """Prepared simulate -> collapse -> call pipeline over a batch of cells (``pmrd_plan``)."""
+
+    def __init__(self, ctx: Context, cell_id, af, n_families, sp: ReadSimParams, up: UmiParams, neg_af_max: float = 1e-4,
+                 test_type: int = TEST_POISSON, alternative: int = ALT_TWO_SIDED, alpha: float = 0.05):
+        self.ctx = ctx
+        self.cell_id = _arr(cell_id, np.int64)
+        self.af = _arr(af, np.float64)
+        self.nf = _arr(n_families, np.int64)
+        self.n_cells = self.cell_id.shape[0]
+        h = C.c_void_p()
+        ctx.lib.pmrd_plan_n_reads.restype = C.c_int64
+        ctx.lib.pmrd_plan_n_reads.argtypes = [C.c_void_p]
+        ctx.lib.pmrd_plan_n_families.restype = C.c_int64
+        ctx.lib.pmrd_plan_n_families.argtypes = [C.c_void_p]
+        ctx.lib.pmrd_plan_destroy.restype = None
+        ctx.lib.pmrd_plan_destroy.argtypes = [C.c_void_p]
+        ctx._check(ctx.lib.pmrd_plan_create(ctx.h, _ptr(self.cell_id), _ptr(self.af), _ptr(self.nf), C.c_int64(self.n_cells),
+                                            C.byref(sp), C.byref(up), C.c_double(neg_af_max), C.c_int32(test_type),
+                                            C.c_int32(alternative), C.c_double(alpha), C.byref(h)))
+        self.h = h
+        self.n_reads = int(ctx.lib.pmrd_plan_n_reads(h))
+        self.n_families = int(ctx.lib.pmrd_plan_n_families(h))
+
+    def run(self) -> None:
+        self.ctx._check(self.ctx.lib.pmrd_plan_run(self.ctx.h, self.h))
+
+    def run_simulate(self) -> None:
+        self.ctx._check(self.ctx.lib.pmrd_plan_run_simulate(self.ctx.h, self.h))
+
+    def run_collapse(self) -> None:
+        self.ctx._check(self.ctx.lib.pmrd_plan_run_collapse(self.ctx.h, self.h))
+
+    def run_call(self) -> None:
+        self.ctx._check(self.ctx.lib.pmrd_plan_run_call(self.ctx.h, self.h))
+
+    def results(self) -> Dict[str, np.ndarray]:
+        c = self.n_cells
+        out = {"n_reads": np.zeros(c, np.int64), "n_families": np.zeros(c, np.int64), "n_total": np.zeros(c, np.int64),
+               "n_variants": np.zeros(c, np.int64), "p_value": np.zeros(c), "p_adjusted": np.zeros(c),
+               "significant": np.zeros(c, np.uint8)}
+        t = PipelineResult(*[out[n].ctypes.data for n, _ in PipelineResult._fields_])
+        rate = np.zeros(1)
+        totals = np.zeros(3, np.int64)
+        self.ctx._check(self.ctx.lib.pmrd_plan_results(self.ctx.h, self.h, C.byref(t), _ptr(rate), _ptr(totals)))
+        out["significant"] = out["significant"].astype(bool)
+        out["mean_error_rate"] = float(rate[0])
+        out["totals"] = totals
+        return out
+
+    def close(self) -> None:
+        if getattr(self, "h", None):
+            self.ctx.lib.pmrd_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 _default_ctx: Optional[Context] = None
 
 

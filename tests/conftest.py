@@ -43,3 +43,10 @@ def ctx():
     c = _native.Context(device=int(os.environ.get("LOCAL_RANK", "0")), seed=7)
     yield c
     c.close()
+
+
+@pytest.fixture(scope="session")
+def native():
+    from precise_mrd import _native
+
+    return _native

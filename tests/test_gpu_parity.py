@@ -1,0 +1,312 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libpmrd_b200.so),
+against (a) the golden vectors exported from the reference and (b) the oracle on seeded
+inputs.  Integer / index work is bit-exact; fp64 tails are compared at the tolerances
+stated (and justified) inline."""
+import numpy as np
+import pytest
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+
+
+def _params(native, **kw):
+    d = dict(min_family_size=1, max_family_size=1 << 30, quality_threshold=0, consensus_threshold=0.0,
+             mode=native.MODE_COUNT, cluster=native.CLUSTER_EXACT, max_distance=0, umi_len=12)
+    d.update(kw)
+    return native.UmiParams(**d)
+
+
+# ------------------------------------------------------------------------------ K4 sort
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 4095, 4096, 4097, 70_001, 1_500_000])
+@pytest.mark.parametrize("pattern", ["full64", "umi24_group11", "few_distinct", "constant"])
+def test_sort_pairs_stable(ctx, n, pattern):
+    rng = np.random.default_rng(n * 7 + len(pattern))
+    if pattern == "full64":
+        keys = rng.integers(0, 2**63, n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, n, dtype=np.uint64)
+    elif pattern == "umi24_group11":
+        keys = (rng.integers(0, 2000, n, dtype=np.uint64) << np.uint64(32)) | rng.integers(0, 1 << 24, n, dtype=np.uint64)
+    elif pattern == "few_distinct":
+        keys = rng.integers(0, 7, n, dtype=np.uint64) * np.uint64(0x0101010101010101)
+    else:
+        keys = np.full(n, 0xDEADBEEF12345678, dtype=np.uint64)
+    vals = np.arange(n, dtype=np.uint32)
+    ko, vo = ctx.sort_pairs(keys, vals)
+    wk, wv = port.sort_pairs(keys, vals)
+    assert (ko == wk).all()
+    assert (vo == wv).all()          # stability: equal keys keep input order
+    ko2, _ = ctx.sort_pairs(keys)    # keys-only variant
+    assert (ko2 == wk).all()
+
+
+# ------------------------------------------------------------------------------ K8 p-values
+def test_poisson_two_sided_vs_reference_golden(ctx, golden, native):
+    g = golden("stats_kat.npz")
+    got = ctx.pvalues(g["pois_k"], None, g["pois_e"], native.TEST_POISSON, native.ALT_TWO_SIDED)
+    want = g["pois_p"]
+    rel = _rel(got, want)
+    # 1e-12 relative down to p = 1e-50.  Deeper, SciPy's own igam/igamc drifts (checked against
+    # mpmath, 60 digits: (k=5495, mu=8255.353) exact 1.09942091479873e-229, SciPy ...47866e-229
+    # = 1.1e-11 off, this kernel ...47990e-229 = 2e-13 off; (1380, 763.79): SciPy 3.2e-12 off,
+    # kernel 6e-14 off), so below 1e-50 the gate against the reference is 2e-11 and
+    # test_tails_against_mpmath holds the kernel itself to 1e-12 there.
+    shallow = want >= 1e-50
+    assert rel[shallow].max() < 1e-12
+    assert rel[~shallow & (want > 0)].max() < 2e-11
+    assert (got[want == 0] < 1e-300).all()
+    assert (got[want == 1.0] == 1.0).all()
+    # KAT rows: edge cases are exact
+    assert got[2] == 1.0 and got[3] == 1.0 and got[5] == 1.0
+
+
+def test_binomial_two_sided_vs_reference_golden(ctx, golden, native):
+    g = golden("stats_kat.npz")
+    got = ctx.pvalues(g["bin_k"], g["bin_n"], g["bin_p"], native.TEST_BINOMIAL, native.ALT_TWO_SIDED)
+    want = g["bin_pv"]
+    rel = _rel(got, want)
+    # scipy.stats.binomtest goes through Boost ibeta, which is itself only ~3e-12 accurate for
+    # n ~ 1e5 (mpmath: binomtest(7, 88655, 6.8095e-05) exact 0.679765642907125639, SciPy
+    # ...9061246 (1.5e-12 off), this kernel ...9071257 (1e-16 off)).  Gate: 1e-12 for n <= 2e4,
+    # 1e-11 above.
+    small = g["bin_n"] <= 20000
+    assert rel[small].max() < 1e-12
+    assert rel[~small].max() < 1e-11
+    # special cases of call.py:30-37
+    assert list(got[3:8]) == [1.0, 1.0, 0.0, 1.0, 0.0]
+
+
+def test_pvalues_one_sided_and_n_times_rate(ctx, native):
+    rng = np.random.default_rng(5)
+    m = 2000
+    n = rng.integers(1, 60000, m)
+    rate = 10 ** rng.uniform(-5, -1.5, m)
+    k = rng.poisson(n * rate * rng.choice([0.5, 1, 2, 5], m))
+    got = ctx.pvalues(k, n, rate, native.TEST_POISSON, native.ALT_TWO_SIDED)
+    want = np.array([port.poisson_test(int(a), int(b) * float(c)) for a, b, c in zip(k, n, rate)])
+    assert _rel(got, want)[want >= 1e-50].max() < 1e-12
+    got = ctx.pvalues(k, n, rate, native.TEST_POISSON, native.ALT_GREATER)
+    want = np.array([port.poisson_greater(int(a), int(b) * float(c)) for a, b, c in zip(k, n, rate)])
+    assert _rel(got, want)[want >= 1e-50].max() < 1e-12
+    k = np.minimum(k, n)
+    got = ctx.pvalues(k, n, rate, native.TEST_BINOMIAL, native.ALT_GREATER)
+    want = np.array([port.binomial_greater(int(a), int(b), float(c)) for a, b, c in zip(k, n, rate)])
+    ok = want >= 1e-50
+    assert _rel(got, want)[ok & (n <= 20000)].max() < 1e-12
+    assert _rel(got, want)[ok].max() < 1e-11
+    # scalar rate broadcast
+    got = ctx.pvalues(k[:50], n[:50], 1e-3, native.TEST_POISSON)
+    want = np.array([port.poisson_test(int(a), int(b) * 1e-3) for a, b in zip(k[:50], n[:50])])
+    assert _rel(got, want).max() < 1e-12
+    with pytest.raises(native.NativeError):
+        ctx.pvalues(k[:5], n[:5], 1e-3, 7)       # "Unknown test type" (call.py:187)
+
+
+def test_tails_against_mpmath(ctx, native):
+    """Where the reference (SciPy) is itself inexact, hold the kernel to the true value."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 60
+
+    def pois2(k, mu):
+        mu = mp.mpf(mu)
+        t = mp.e ** (-mu) * mu ** k / mp.factorial(k)
+        s, j, tt = mp.mpf(0), k, t
+        if k > mu:
+            while tt > s * mp.mpf(10) ** -40:
+                s += tt; j += 1; tt = tt * mu / j
+            return min(1, 2 * min(s, 1 - s + t))
+        while True:
+            s += tt
+            if j == 0 or tt < s * mp.mpf(10) ** -40:
+                break
+            tt = tt * j / mu; j -= 1
+        return min(1, 2 * min(s, 1 - s + t))
+
+    cases = [(5495, 8255.35343336275), (5620, 8299.835485743746), (1380, 763.788540437689), (3567, 2012.154107293812),
+             (10, 0.1), (5, 1.0), (0, 30.0), (100000, 99000.0)]
+    got = ctx.pvalues([c[0] for c in cases], None, [c[1] for c in cases], native.TEST_POISSON)
+    for (k, mu), v in zip(cases, got):
+        ex = pois2(k, mu)
+        assert abs(mp.mpf(float(v)) - ex) / ex < mp.mpf("1e-12"), (k, mu, v)
+
+    def binom_minlike(k, n, p):
+        pm = lambda i: mp.binomial(n, i) * mp.mpf(p) ** i * (1 - mp.mpf(p)) ** (n - i)
+        d = pm(k) * (1 + mp.mpf("1e-7"))
+        sd = int(60 * (n * p) ** 0.5 + 60)
+        return min(1, sum(f for f in (pm(i) for i in range(max(0, int(n * p) - sd), min(n, int(n * p) + sd) + 1)) if f <= d))
+
+    cases = [(7, 88655, 6.809545321347221e-05), (16, 100767, 0.00014704516006750236), (9, 131776, 0.00017227525854530073)]
+    got = ctx.pvalues([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], native.TEST_BINOMIAL)
+    for (k, n, p), v in zip(cases, got):
+        ex = binom_minlike(k, n, p)
+        assert abs(mp.mpf(float(v)) - ex) / ex < mp.mpf("1e-12"), (k, n, p, v)
+
+
+# ------------------------------------------------------------------------------ K9 BH
+def test_bh_vs_reference_golden(ctx, golden):
+    g = golden("stats_kat.npz")
+    for i in range(int(g["n_bh"])):
+        rej, adj = ctx.bh(g[f"bh{i}_p"], float(g[f"bh{i}_alpha"]))
+        assert (rej == g[f"bh{i}_rej"]).all(), i
+        assert (adj == g[f"bh{i}_adj"]).all(), i      # same IEEE ops in the same order: bit-equal
+    rej, adj = ctx.bh(np.array([]), 0.05)
+    assert rej.shape == (0,) and adj.shape == (0,)
+
+
+@pytest.mark.parametrize("m", [1, 2047, 2048, 2049, 300_000])
+def test_bh_vs_oracle_random(ctx, m):
+    rng = np.random.default_rng(m)
+    p = rng.uniform(0, 1, m) ** 4
+    p[rng.integers(0, m, max(1, m // 7))] = 1.0
+    for alpha in (0.0, 0.05, 1.0):
+        rej, adj = ctx.bh(p, alpha)
+        wrej, wadj = port.benjamini_hochberg(p, alpha)
+        assert (rej == wrej).all() and (adj == wadj).all()
+    # properties (tests/stat_tests/test_bh_fdr.py): monotone in p, adj >= p, idempotent decisions
+    order = np.argsort(p, kind="stable")
+    assert (np.diff(adj[order]) >= 0).all() and (adj >= p).all()
+
+
+# ------------------------------------------------------------------------------ call stage
+@pytest.mark.parametrize("name", ["call_smoke_v1.npz", "call_smoke_v2.npz"])
+def test_call_stage_vs_reference_fixture(ctx, golden, native, name):
+    g = golden(name)
+    out = ctx.call(g["seg_offsets"], g["is_variant"], g["quality"], g["agreement"], float(g["mean_error_rate"]),
+                   native.TEST_POISSON, float(g["alpha"]))
+    for col in ("n_variants", "n_total", "significant"):
+        assert (out[col] == g[f"want_{col}"]).all(), col             # bit-exact class
+    for col in ("variant_fraction", "expected_variants", "fold_change"):
+        assert (out[col] == g[f"want_{col}"]).all(), col             # single IEEE ops: also bit-exact
+    for col in ("p_value", "p_adjusted", "mean_quality", "mean_consensus"):
+        assert _rel(out[col], g[f"want_{col}"]).max() < 1e-12, col   # 1e-12 relative class
+
+
+def test_call_stage_binomial_and_ragged(ctx, native):
+    rng = np.random.default_rng(9)
+    lens = np.array([1, 2, 255, 256, 257, 5000, 1, 40000, 3])
+    so = np.concatenate([[0], np.cumsum(lens)])
+    R = so[-1]
+    iv = (rng.uniform(size=R) < 0.002).astype(np.uint8)
+    q = rng.normal(25, 3, R)
+    a = rng.uniform(0.7, 1, R)
+    for tt, name in ((native.TEST_POISSON, "poisson"), (native.TEST_BINOMIAL, "binomial")):
+        out = ctx.call(so, iv, q, a, 1.3e-3, tt, 0.05)
+        want = port.call_segments(so, iv, q, a, 1.3e-3, name, 0.05)
+        assert (out["n_variants"] == want["n_variants"]).all() and (out["n_total"] == want["n_total"]).all()
+        assert (out["significant"] == want["significant"]).all()
+        for col in ("p_value", "p_adjusted", "mean_quality", "mean_consensus", "fold_change", "expected_variants"):
+            assert _rel(out[col], want[col]).max() < 1e-12, (name, col)
+    # expected == 0 -> p = 1, fold_change inf / 1.0 (call.py:190-193)
+    out = ctx.call(so, iv, None, None, 0.0, native.TEST_POISSON, 0.05)
+    assert (out["p_value"] == 1.0).all()
+    assert np.isinf(out["fold_change"][out["n_variants"] > 0]).all()
+    assert (out["fold_change"][out["n_variants"] == 0] == 1.0).all()
+    # determinism: fp64 means are bit-identical run to run
+    o1 = ctx.call(so, iv, q, a, 1.3e-3, native.TEST_POISSON, 0.05)
+    o2 = ctx.call(so, iv, q, a, 1.3e-3, native.TEST_POISSON, 0.05)
+    assert (o1["mean_quality"] == o2["mean_quality"]).all() and (o1["p_adjusted"] == o2["p_adjusted"]).all()
+
+
+# ------------------------------------------------------------------------------ collapse
+def _assert_tables_equal(fam, grp, wfam, wgrp):
+    for k in ("key", "size", "n_alt", "consensus", "qsum", "n_best", "flags"):
+        assert (fam[k] == wfam[k]).all(), k
+    for k in ("group", "family_count", "consensus_count", "alt_count", "total_count"):
+        assert (grp[k] == wgrp[k]).all(), k
+
+
+def test_collapse_ga_firstfit_majority_vs_reference(ctx, golden, native):
+    g = golden("ga_reads.npz")
+    P = _params(native, min_family_size=2, mode=native.MODE_MAJORITY, cluster=native.CLUSTER_FIRSTFIT, max_distance=1, umi_len=8)
+    fam, grp = ctx.collapse_reads(g["keys"], g["payload"], P)
+    kept = (fam["flags"] & native.FAM_KEPT) != 0
+    assert (fam["key"][kept] == g["want_fam_key"]).all()          # representative UMI, reference order
+    assert (fam["size"][kept] == g["want_fam_size"]).all()
+    assert (fam["n_alt"][kept] == g["want_fam_alt"]).all()
+    assert (fam["consensus"][kept] == g["want_fam_consensus"]).all()
+    locus = g["group_locus"][grp["group"]]
+    for name, col in (("want_locus_alt", "alt_count"), ("want_locus_total", "total_count"), ("want_locus_families", "family_count")):
+        agg = np.zeros(locus.max() + 1, np.int64)
+        np.add.at(agg, locus, grp[col].astype(np.int64))
+        assert (agg[g["want_locus"]] == g[name]).all(), name
+    wfam, wgrp = port.collapse_firstfit(g["keys"], g["payload"], 1, 2, 1 << 30, 1)
+    _assert_tables_equal(fam, grp, wfam, wgrp)
+
+
+def test_collapse_gc_counts_vs_reference(ctx, golden, native):
+    g = golden("gc_reads.npz")
+    fam, grp = ctx.collapse_reads(g["keys"], g["payload"], _params(native))
+    order = np.argsort(g["want_fam_key"], kind="stable")
+    assert (fam["key"] == g["want_fam_key"][order]).all()
+    assert (fam["size"] == g["want_size"][order]).all()
+    assert (fam["n_alt"] == g["want_alt"][order]).all()
+    assert (fam["size"] - fam["n_alt"] == g["want_ref"][order]).all()
+
+
+def test_collapse_gb_weighted_vs_reference(ctx, golden, native):
+    g = golden("gb_reads.npz")
+    mn, mx, qthr = [int(v) for v in g["params"]]
+    P = _params(native, min_family_size=mn, max_family_size=mx, quality_threshold=qthr,
+                consensus_threshold=float(g["consensus_threshold"]), mode=native.MODE_WEIGHTED)
+    fam, grp = ctx.collapse_reads(g["keys"], g["payload"], P)
+    order = np.argsort(g["want_fam_key"], kind="stable")
+    assert (fam["key"] == g["want_fam_key"][order]).all()
+    assert (fam["size"] == g["want_fam_size"][order]).all()
+    has = (fam["flags"] & native.FAM_HAS_CONSENSUS) != 0
+    want_allele = g["want_fam_allele"][order]
+    assert (has == (want_allele >= 0)).all()                      # same >= threshold decisions, bit-exact
+    assert (fam["consensus"][has] == want_allele[has]).all()
+    assert (fam["qsum"][has] / fam["n_best"][has] == g["want_fam_quality"][order][has]).all()
+    assert int(((fam["flags"] & native.FAM_KEPT) != 0).sum()) == int(g["want_kept"])
+    assert (grp["consensus_count"] == g["want_consensus_count"][grp["group"]]).all()
+    wfam, wgrp = port.collapse_exact(g["keys"], g["payload"], 0, mn, mx, qthr, float(g["consensus_threshold"]))
+    _assert_tables_equal(fam, grp, wfam, wgrp)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 4097, 60_000])
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_collapse_exact_vs_oracle_random(ctx, native, n, mode):
+    rng = np.random.default_rng(100 * n + mode)
+    groups = rng.integers(0, 9, n, dtype=np.uint64) * np.uint64(131)          # sparse group ids
+    umis = rng.integers(0, max(2, n // 4), n, dtype=np.uint64) * np.uint64(2654435761) % np.uint64(1 << 24)
+    keys = (groups << np.uint64(32)) | umis
+    payload = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    if mode == 0:   # qualities in 0..63 with equal-quality ties being common
+        q = rng.choice([5, 10, 20, 20, 30, 30, 30, 37, 40, 63], n).astype(np.uint32)
+        payload = (payload & np.uint32(0xFFFFFF03)) | (q << np.uint32(2))
+    P = _params(native, min_family_size=3, max_family_size=6, quality_threshold=20, consensus_threshold=0.6, mode=mode)
+    fam, grp = ctx.collapse_reads(keys, payload, P)
+    wfam, wgrp = port.collapse_exact(keys, payload, mode, 3, 6, 20, 0.6)
+    _assert_tables_equal(fam, grp, wfam, wgrp)
+
+
+def test_collapse_one_giant_family_and_firstfit_random(ctx, native):
+    n = 20_000
+    keys = np.full(n, (5 << 32) | 77, dtype=np.uint64)
+    payload = np.random.default_rng(1).integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    P = _params(native, mode=native.MODE_WEIGHTED, quality_threshold=20, consensus_threshold=0.3, max_family_size=1000)
+    fam, grp = ctx.collapse_reads(keys, payload, P)
+    wfam, wgrp = port.collapse_exact(keys, payload, 0, 1, 1000, 20, 0.3)
+    _assert_tables_equal(fam, grp, wfam, wgrp)
+    assert fam["flags"][0] & native.FAM_OVERSIZE
+    rng = np.random.default_rng(2)
+    n = 6000
+    keys = (rng.integers(0, 40, n, dtype=np.uint64) << np.uint64(32)) | rng.integers(0, 1 << 10, n, dtype=np.uint64)
+    payload = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    for d in (0, 1, 2):
+        P = _params(native, min_family_size=2, mode=native.MODE_MAJORITY, cluster=native.CLUSTER_FIRSTFIT, max_distance=d, umi_len=5)
+        fam, grp = ctx.collapse_reads(keys, payload, P)
+        wfam, wgrp = port.collapse_firstfit(keys, payload, 1, 2, 1 << 30, d)
+        _assert_tables_equal(fam, grp, wfam, wgrp)
+
+
+def test_umi_hamming(ctx):
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 1 << 24, 5000, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 1 << 24, 5000, dtype=np.uint64).astype(np.uint32)
+    b[:100] = a[:100]
+    assert (ctx.umi_hamming(a, b, 12) == port.umi_hamming(a, b)).all()

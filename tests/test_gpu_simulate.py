@@ -1,0 +1,315 @@
+"""GPU tests of the Philox generators and of the fused pipeline.
+
+Parity class for anything that consumed the reference's PCG64 stream is DISTRIBUTIONAL
+(north_star): chi-square / KS at alpha = 0.01 against the closed forms of the
+reference's draws and against samples of the reference itself
+(tests/golden/gd_dist.npz).  Everything downstream of the generated reads is checked
+bit-exactly against the oracle run on the very same reads."""
+import numpy as np
+import pytest
+from scipy import stats
+
+from oracle import port
+
+pytestmark = pytest.mark.gpu
+ALPHA = 0.01
+
+
+def _umi(native, **kw):
+    d = dict(min_family_size=3, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6,
+             mode=native.MODE_WEIGHTED, cluster=native.CLUSTER_EXACT, max_distance=0, umi_len=12)
+    d.update(kw)
+    return native.UmiParams(**d)
+
+
+def _sp(native, **kw):
+    d = dict(mean_family_size=5.0, family_model=0, max_family_size=1000, contamination_rate=0.0, hop_rate=0.0,
+             collision_rate=0.0, shuffle=1, reserved=0)
+    d.update(kw)
+    return native.ReadSimParams(**d)
+
+
+def _chi2_pvalue(obs, exp):
+    obs, exp = np.asarray(obs, float), np.asarray(exp, float)
+    keep = exp >= 5
+    o = np.append(obs[keep], obs[~keep].sum())
+    e = np.append(exp[keep], exp[~keep].sum())
+    if e[-1] == 0:
+        o, e = o[:-1], e[:-1]
+    return stats.chisquare(o, e * o.sum() / e.sum()).pvalue
+
+
+# ------------------------------------------------------------------------------ K1 cells
+def test_simulate_cells_distributions(ctx):
+    c = 200_000
+    cid = np.arange(c)
+    af = np.tile([0.01, 0.001, 0.0001, 0.05], c // 4)
+    depth = np.tile([1000, 5000, 20000, 50000, 100000], c // 5)
+    out = ctx.simulate_cells(cid, af, depth, 1000)
+    # simulate.py:144 U(1e-5,1e-3); :147 clip(Poisson(5),1,max); :161 clip(N(25,5),10,40)
+    assert stats.kstest(out["background_rate"], stats.uniform(1e-5, 1e-3 - 1e-5).cdf).pvalue > ALPHA
+    ks = np.arange(0, 25)
+    exp = stats.poisson.pmf(ks, 5) * c
+    exp[1] += exp[0]; exp[0] = 0
+    assert _chi2_pvalue(np.bincount(out["mean_family_size"], minlength=25)[:25], exp) > ALPHA
+    q = out["mean_quality"]
+    inner = (q > 10) & (q < 40)
+    assert abs((q == 10).mean() - stats.norm.cdf(-3)) < 3e-4 and abs((q == 40).mean() - stats.norm.sf(3)) < 3e-4
+    tn = stats.truncnorm(-3, 3, loc=25, scale=5)
+    assert stats.kstest(q[inner], tn.cdf).pvalue > ALPHA
+    # simulate.py:152 Binom(depth, af): probability-integral transform with a randomised tie-break
+    rng = np.random.default_rng(0)
+    for a, d in ((0.0001, 1000), (0.01, 5000), (0.05, 100000), (0.001, 20000)):
+        sel = (af == a) & (depth == d)
+        k = out["n_true_variants"][sel]
+        if sel.sum() == 0:
+            continue
+        u = stats.binom.cdf(k - 1, d, a) + rng.uniform(size=k.size) * stats.binom.pmf(k, d, a)
+        assert stats.kstest(u, "uniform").pvalue > ALPHA, (a, d)
+    # :155 Binom(depth - n_true, bg): mean check at 5 sigma
+    nfp, bg, nt = out["n_false_positives"], out["background_rate"], out["n_true_variants"]
+    z = (nfp - (depth - nt) * bg) / np.sqrt((depth - nt) * bg * (1 - bg))
+    assert abs(z.mean()) < 5 / np.sqrt(c) and abs(z.std() - 1) < 0.02
+    # counter-based: a cell's draw does not depend on what else is in the batch
+    sub = ctx.simulate_cells(cid[1000:1010], af[1000:1010], depth[1000:1010], 1000)
+    for k_ in out:
+        assert (sub[k_] == out[k_][1000:1010]).all()
+
+
+# ------------------------------------------------------------------------------ K2 G-D families
+@pytest.mark.parametrize("variant", [1, 2])
+def test_gd_families_match_reference_distributions(ctx, golden, native, variant):
+    g = golden("gd_dist.npz")
+    tag = f"v{variant}"
+    af, bg, mfs = g[f"{tag}_cell_af"], g[f"{tag}_cell_bg"], g[f"{tag}_cell_mfs"]
+    c = af.shape[0]
+    reps = 12                                 # 12 x the reference's 24 cells, different cell ids
+    cid = np.arange(c * reps) + 1000
+    AF, BG, MFS = np.tile(af, reps), np.tile(bg, reps), np.tile(mfs, reps)
+    NF = np.full(c * reps, 4000)
+    P = _umi(native)
+    offs, fam = ctx.collapse_families(cid, AF, NF, BG, MFS, P, variant=variant)
+    assert offs[-1] == fam["cell"].shape[0] and (np.diff(offs) >= 0).all()
+    cnt_only, _ = ctx.collapse_families(cid, AF, NF, BG, MFS, P, variant=variant, count_only=True)
+    assert (cnt_only == offs).all()
+    assert (fam["family_size"] >= 3).all()    # collapse.py:85-86
+    # rows are cell-major with ascending family ids (gaps where skipped)
+    assert (np.diff(fam["cell"]) >= 0).all()
+    same = np.diff(fam["cell"]) == 0
+    assert (np.diff(fam["family_id"])[same] > 0).all()
+    ref_fs, ref_q, ref_a, ref_fl = g[f"{tag}_family_size"], g[f"{tag}_quality"], g[f"{tag}_agreement"], g[f"{tag}_flags"]
+    ref_cell = g[f"{tag}_sample"]
+    # two-sample tests against the reference's own draws, per AF level (quality depends on AF in v2)
+    for a in np.unique(af):
+        m_ref = af[ref_cell] == a
+        m_new = AF[fam["cell"]] == a
+        assert stats.ks_2samp(fam["quality_score"][m_new], ref_q[m_ref]).pvalue > ALPHA, ("quality", a)
+        assert stats.ks_2samp(fam["consensus_agreement"][m_new], ref_a[m_ref]).pvalue > ALPHA, ("agreement", a)
+    # family size: per lambda group, chi-square new-vs-reference histogram
+    lam = np.maximum(3, mfs) if variant == 2 else np.full(c, 5.0)
+    for L in np.unique(lam):
+        m_ref = lam[ref_cell] == L
+        m_new = np.tile(lam, reps)[fam["cell"]] == L
+        hr = np.bincount(ref_fs[m_ref], minlength=40)[:40].astype(float)
+        hn = np.bincount(fam["family_size"][m_new], minlength=40)[:40].astype(float)
+        keep = (hr + hn) >= 10
+        tab = np.vstack([np.append(hr[keep], hr[~keep].sum()), np.append(hn[keep], hn[~keep].sum())])
+        tab = tab[:, tab.sum(0) > 0]
+        assert stats.chi2_contingency(tab)[1] > ALPHA, ("family_size", L)
+        # kept fraction = P[clip(Poisson(L)) >= 3]
+        kept_new = m_new.sum() / (4000 * reps * (lam == L).sum())
+        assert abs(kept_new - stats.poisson.sf(2, L)) < 4e-3
+    # flags: pass rates and is_variant rate (binomial z-test vs the reference's rate)
+    for bit, name in ((0, "passes_quality"), (1, "passes_consensus")):
+        pn, pr = ((fam["flags"] >> bit) & 1).mean(), ((ref_fl >> bit) & 1).mean()
+        se = np.sqrt(pr * (1 - pr) * (1 / len(ref_fl) + 1 / len(fam["flags"])) + 1e-12)
+        assert abs(pn - pr) < 4 * se + 1e-9, name
+    for a in np.unique(af):
+        m_ref, m_new = af[ref_cell] == a, AF[fam["cell"]] == a
+        kr, kn = ((ref_fl[m_ref] >> 2) & 1).sum(), ((fam["flags"][m_new] >> 2) & 1).sum()
+        tab = np.array([[kr, m_ref.sum() - kr], [kn, m_new.sum() - kn]])
+        if (tab.sum(0) > 0).all():
+            assert stats.fisher_exact(tab)[1] > ALPHA / 3, ("is_variant", a)   # AF acts only through AF > 0.01 (App. A #12)
+
+
+# ------------------------------------------------------------------------------ K10 error model
+def test_error_model_rates_and_bootstrap(ctx):
+    n_neg, n_var = 50523, 31
+    rate, lo, hi = ctx.error_model(n_neg, n_var, 100, stream_id=5)
+    vr = n_var / n_neg
+    mod = rate / vr
+    assert (mod >= 0.5).all() and (mod <= 2.0).all() and mod.std() > 0.2          # error_model.py:155
+    # bootstrap percentiles bracket the binomial-equivalent 2.5 / 97.5 quantiles (100 resamples: loose)
+    qlo, qhi = stats.binom.ppf([0.025, 0.975], n_neg, vr) / n_neg
+    assert (lo <= rate).all() and (hi >= rate * 0.999).all()
+    assert abs(np.median(lo / mod) - qlo) < 0.35 * vr and abs(np.median(hi / mod) - qhi) < 0.35 * vr
+    # many independent fits: modifiers are U(0.5, 2)
+    mods = np.concatenate([ctx.error_model(n_neg, n_var, 8, stream_id=s)[0] / vr for s in range(40)])
+    assert stats.kstest(mods, stats.uniform(0.5, 1.5).cdf).pvalue > ALPHA
+    # fallbacks (error_model.py:157-159,175-177)
+    r, l, h = ctx.error_model(5, 1, 100, 0)
+    assert np.allclose(l, r * 0.5) and np.allclose(h, r * 2.0)
+    r, l, h = ctx.error_model(0, 0, 100, 0)
+    assert (r >= 1e-5).all() and (r <= 1e-3).all()
+
+
+# ------------------------------------------------------------------------------ read generator
+def test_read_generator_distributions(ctx, native):
+    c = 64
+    cid = np.arange(c) + 17
+    af = np.tile([0.0, 0.05, 0.3, 0.8], c // 4)
+    nf = np.full(c, 20000)
+    for model in (0, 1):
+        sp = _sp(native, family_model=model, shuffle=0)
+        offs = ctx.simulate_reads_count(cid, nf, sp)
+        keys, pl = ctx.simulate_reads(cid, af, nf, sp)
+        assert keys.shape[0] == offs[-1]
+        # family-major, unshuffled: runs of equal key are the families
+        change = np.flatnonzero(np.diff(keys.astype(np.int64)) != 0) + 1
+        starts = np.concatenate([[0], change])
+        sizes = np.diff(np.concatenate([starts, [len(keys)]]))
+        # (adjacent families with the same UMI in the same cell merge: negligible at 24-bit UMIs)
+        ks = np.arange(1, 60)
+        if model == 0:   # io.py:71-77  NegBinom(2, 2/(2+mean)) + 1
+            exp = stats.nbinom.pmf(ks - 1, 2, 2 / 7.0)
+        else:            # clip(Poisson(5), 1, max)
+            exp = stats.poisson.pmf(ks, 5.0)
+            exp[0] += stats.poisson.pmf(0, 5.0)
+        assert _chi2_pvalue(np.bincount(sizes, minlength=60)[1:60], exp * len(sizes)) > ALPHA, model
+        grp = (keys >> np.uint64(32)).astype(np.int64)
+        umi = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        assert grp.min() == 0 and grp.max() == c - 1 and umi.max() < (1 << 24)
+        assert stats.kstest(umi[starts] / float(1 << 24), "uniform").pvalue > ALPHA          # io.py:60-63
+        q = ((pl >> 2) & 63).astype(int)
+        # io.py:65-69  max(10, min(40, int(N(30,5))))
+        edges = np.arange(10, 42)
+        cdf = stats.norm.cdf(edges, 30, 5)
+        exp_q = np.diff(cdf)
+        exp_q[0] += cdf[0]
+        exp_q[-1] += 1 - cdf[-1]                     # q == 40 collects [40, inf)
+        # int() truncation: for x in [k, k+1) -> k (x > 0 here)
+        assert _chi2_pvalue(np.bincount(q, minlength=41)[10:41], exp_q[:31] * len(q)) > ALPHA
+        assert abs(((pl >> 8) & 1).mean() - 0.5) < 4 * 0.5 / np.sqrt(len(pl))
+        rp = ((pl >> 9) & 255).astype(int)
+        assert rp.min() >= 10 and rp.max() <= 149 and _chi2_pvalue(np.bincount(rp, minlength=150)[10:150], np.full(140, len(rp) / 140)) > ALPHA
+        # alleles: io.py:97,105-108
+        is_alt = (pl >> 31).astype(int)
+        fam_of_read = np.repeat(np.arange(len(sizes)), sizes)
+        for a in (0.0, 0.05, 0.3, 0.8):
+            m = af[grp] == a
+            expect = a * 0.9 + (1 - a) * 0.05
+            # reads within a family are correlated (shared has_variant): compare family-level
+            # alt fractions with the two-component mixture instead of a per-read binomial
+            fam_alt = np.bincount(fam_of_read[m], weights=is_alt[m], minlength=len(sizes))
+            fam_n = np.bincount(fam_of_read[m], minlength=len(sizes))
+            big = fam_n >= 8                       # large families separate the two components cleanly
+            if big.sum() > 200:
+                assert abs(((fam_alt[big] / fam_n[big]) > 0.5).mean() - a) < 4 * np.sqrt(max(a * (1 - a), 1e-3) / big.sum()) + 2e-3, a
+            assert abs(is_alt[m].mean() - expect) < 0.01, a
+        allele = (pl & 3).astype(int)
+        ref = (cid & 3)[grp]
+        alt = ((ref + 1 + ((cid >> 2) % 3)[grp]) & 3)
+        assert ((allele == ref) | (allele == alt)).all() and ((allele == alt) == (is_alt == 1)).all()
+
+
+def test_read_generator_shuffle_is_a_permutation_and_contamination(ctx, native):
+    cid = np.arange(40) + 3
+    af = np.full(40, 0.1)
+    nf = np.full(40, 3000)
+    k0, p0 = ctx.simulate_reads(cid, af, nf, _sp(native, shuffle=0))
+    k1, p1 = ctx.simulate_reads(cid, af, nf, _sp(native, shuffle=1))
+    assert len(k0) == len(k1) and (k0 != k1).mean() > 0.9
+    o0, o1 = np.lexsort((p0, k0)), np.lexsort((p1, k1))
+    assert (k0[o0] == k1[o1]).all() and (p0[o0] == p1[o1]).all()
+    # index hopping: ~hop_rate of the reads change group; UMI and payload allele survive
+    kh, ph = ctx.simulate_reads(cid, af, nf, _sp(native, shuffle=0, hop_rate=0.02))
+    moved = (kh >> np.uint64(32)) != (k0 >> np.uint64(32))
+    assert abs(moved.mean() - 0.02) < 4 * np.sqrt(0.02 * 0.98 / len(k0))
+    assert ((kh & np.uint64(0xFFFFFFFF)) == (k0 & np.uint64(0xFFFFFFFF))).all() and ((ph & 0xFF) == (p0 & 0xFF)).all()
+    # barcode collisions: ~rate of the families share the previous family's UMI -> fewer distinct keys
+    kc, _ = ctx.simulate_reads(cid, af, nf, _sp(native, shuffle=0, collision_rate=0.05))
+    lost = len(np.unique(k0)) - len(np.unique(kc))
+    assert abs(lost / (40 * 3000) - 0.05) < 0.01
+    # contamination flip (io.py:100-101): at af = 0 a fraction `rate` of the families turns variant
+    kz, pz = ctx.simulate_reads(cid, np.zeros(40), nf, _sp(native, shuffle=0, contamination_rate=0.2))
+    assert abs((pz >> 31).mean() - (0.2 * 0.9 + 0.8 * 0.05)) < 0.01
+
+
+# ------------------------------------------------------------------------------ fused pipeline
+@pytest.mark.parametrize("test_type", ["poisson", "binomial"])
+def test_pipeline_equals_oracle_on_the_same_reads(ctx, native, test_type):
+    rng = np.random.default_rng(3)
+    c = 96
+    cid = np.arange(c) * 7 + 11
+    af = np.tile([0.0, 0.0, 1e-4, 0.01, 0.05, 0.2], c // 6)
+    nf = rng.integers(50, 3000, c)
+    nf[5] = 0                                            # a cell with no families at all
+    sp, up = _sp(native), _umi(native)
+    tt = native.TEST_TYPES[test_type]
+    res = ctx.pipeline_cells(cid, af, nf, sp, up, neg_af_max=1e-4, test_type=tt, alpha=0.05)
+    keys, pl = ctx.simulate_reads(cid, af, nf, sp)          # the very reads the pipeline generated
+    assert res["n_reads"].sum() == len(keys) == res["totals"][0]
+    fam, grp = port.collapse_exact(keys, pl, 0, 3, 1000, 20, 0.6)
+    alt = ((cid & 3) + 1 + ((cid >> 2) % 3)) & 3
+    n_total, n_var, n_fam = np.zeros(c, np.int64), np.zeros(c, np.int64), np.zeros(c, np.int64)
+    n_total[grp["group"]] = grp["consensus_count"].sum(1)
+    n_var[grp["group"]] = grp["consensus_count"][np.arange(len(grp["group"])), alt[grp["group"]]]
+    np.add.at(n_fam, (fam["key"] >> np.uint64(32)).astype(np.int64), 1)
+    assert (res["n_total"] == n_total).all() and (res["n_variants"] == n_var).all() and (res["n_families"] == n_fam).all()
+    assert (res["n_reads"] == np.bincount((keys >> np.uint64(32)).astype(np.int64), minlength=c)).all()
+    # error rate: mean over 64 contexts of (n_var/n_neg) * U(0.5, 2)   (error_model.py:153-156, call.py:178)
+    neg = af <= 1e-4
+    vr = n_var[neg].sum() / n_total[neg].sum()
+    assert 0.5 * vr <= res["mean_error_rate"] <= 2.0 * vr
+    rate = res["mean_error_rate"]
+    if test_type == "poisson":
+        want_p = np.array([port.poisson_test(int(k), int(n) * rate) for k, n in zip(n_var, n_total)])
+    else:
+        want_p = np.array([port.binomial_test(int(k), int(n), rate) for k, n in zip(n_var, n_total)])
+    ok = want_p >= 1e-50
+    assert np.max(np.abs(res["p_value"][ok] - want_p[ok]) / want_p[ok]) < 1e-12
+    assert (res["p_value"][~ok] < 1e-49).all()
+    rej, adj = port.benjamini_hochberg(res["p_value"], 0.05)
+    assert (res["significant"] == rej).all() and (res["p_adjusted"] == adj).all()
+    assert res["significant"][(af >= 0.05) & (nf >= 1000)].all() and not res["significant"][af == 0.0].any()
+    # deterministic and independent of batch composition: rerun, and a sub-batch containing the negatives
+    res2 = ctx.pipeline_cells(cid, af, nf, sp, up, neg_af_max=1e-4, test_type=tt, alpha=0.05)
+    for k_ in ("n_total", "n_variants", "p_value", "p_adjusted"):
+        assert (res[k_] == res2[k_]).all()
+    sub = np.arange(0, c, 2)
+    res3 = ctx.pipeline_cells(cid[sub], af[sub], nf[sub], sp, up, neg_af_max=1e-4, test_type=tt, alpha=0.05)
+    assert (res3["n_total"] == res["n_total"][sub]).all() and (res3["n_variants"] == res["n_variants"][sub]).all()
+
+
+def test_plan_stage_entry_points_compose(ctx, native):
+    cid = np.arange(32)
+    af = np.tile([0.0, 0.02], 16)
+    nf = np.full(32, 2000)
+    plan = native.Plan(ctx, cid, af, nf, _sp(native), _umi(native))
+    plan.run_simulate(); plan.run_collapse(); plan.run_call()
+    a = plan.results()
+    plan.run()
+    b = plan.results()
+    plan.close()
+    for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+        assert (a[k_] == b[k_]).all(), k_
+    assert a["totals"][0] == plan.n_reads and a["totals"][2] == 32
+
+
+# ------------------------------------------------------------------------------ K11 LoD fit
+def test_fit_lod_matches_reference_golden(ctx, golden):
+    g = golden("lod_fit.npz")
+    af = g["af"]
+    for name in ("mid", "steep", "shallow"):
+        lod, lo, hi = ctx.fit_lod(af, g[f"{name}_hit"], 0.95, 200, stream_id=1)
+        assert abs(lod - float(g[f"{name}_lod"])) / float(g[f"{name}_lod"]) < 1e-6, name   # same LM optimum
+        rlo, rhi = g[f"{name}_ci"]
+        # bootstrap CI of 200 resamples of 15 points: within bootstrap noise of the reference's
+        assert lo <= lod * 1.0001 and hi >= lod * 0.9999
+        assert abs(np.log(lo / rlo)) < 0.35 and abs(np.log(hi / rhi)) < 0.6, (name, lo, hi, rlo, rhi)
+    # the reference's own grids give all-zero hit rates -> curve_fit fails -> interp1d fallback -> NaN
+    lod, lo, hi = ctx.fit_lod(af, g["zeros_hit"], 0.95, 200)
+    assert np.isnan(lod) and np.isnan(lo) and np.isnan(hi)
+    assert np.isnan(float(g["zeros_lod"]))
+    # determinism
+    assert ctx.fit_lod(af, g["mid_hit"], 0.95, 50, 9) == ctx.fit_lod(af, g["mid_hit"], 0.95, 50, 9)
