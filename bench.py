@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- UMI reads/s through simulate -> collapse -> call on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host CPUs
+
+Workload (config.workload): the reference's configs/default.yaml grid -- 5 AF x 4 depths x 1000
+replicates = 20 000 cells, 4.25e8 UMI families, ~2.1e9 reads per GPU (C2 of SURVEY.md §8d).
+One STEP = one pass of the hot path over that grid: Philox read generation -> radix sort ->
+quality-weighted consensus -> per-cell counts -> error model -> fp64 tail p-values -> BH.
+A "UMI read" is one member of one generated UMI family (before the min-family-size filter).
+
+Multi-GPU: the replicate axis shards (rank r owns replicates [r*1000, (r+1)*1000)); there is no
+data-path collective, per-GPU work is fixed => "scaling": "weak".  Philox streams are keyed by
+the GLOBAL cell id, so a cell's result is independent of the GPU count.
+
+Timing: CUDA events on the launching stream, W >= 3 warm-up steps, barrier + synchronize on
+both sides, max over ranks.  Every chunk the kernels touch (>= 1.9 GB) is far larger than the
+126 MB L2, so no L2 flush is needed between iterations (config.l2: "inputs larger than L2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT / "precise-mrd-mini_b200"), str(ROOT)):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "umi_reads_per_sec_simulate_collapse_call"
+UNIT = "reads/s"
+B_READ_PIPELINE = 54.4  # algorithmic bytes per read of the whole path (48 + 32/f, f = 5)
+B_READ_SORT_PASS = 24.0  # one radix pass: read 12 B, write 12 B per read
+HBM_FALLBACK_GBS = 6650.0
+
+
+# ------------------------------------------------------------------------------- workload
+def workload(name: str, rank: int, world: int):
+    from precise_mrd.config import load_config
+    from precise_mrd.grid import grid_cells
+
+    cfg_dir = ROOT / "precise-mrd-mini_b200" / "precise_mrd" / "assets" / "configs"
+    if name == "default":
+        cfg = load_config(cfg_dir / "default.yaml")
+        label = "configs/default.yaml C2 grid: 5 AF x 4 depths x 1000 replicates = 20000 cells per GPU"
+    elif name == "smoke":
+        cfg = load_config(cfg_dir / "smoke.yaml")
+        label = "configs/smoke.yaml C1 grid: 3 AF x 2 depths x 10 replicates = 60 cells per GPU"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    sim = cfg.simulation
+    reps = int(os.environ.get("PMRD_BENCH_REPS", sim.n_replicates))
+    cell_id, af, depth, rep = grid_cells(sim.allele_fractions, sim.umi_depths, reps, rep_offset=rank * reps,
+                                         rep_stride=world * reps)
+    return cfg, label, cell_id, af, depth
+
+
+def peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.samples, self._stop, self._t = device, [], threading.Event(), None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0])); mx = max(mx, float(s[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- CPU port
+def cpu_sample_cells(cell_id, af, depth, n):
+    """A bounded, depth-balanced sample of the workload's cells (every k-th cell)."""
+    step = max(1, len(cell_id) // n)
+    idx = np.arange(0, len(cell_id), step)[:n]
+    return cell_id[idx], af[idx], depth[idx]
+
+
+def cpu_pipeline_once(cfg, cid, af, depth, threads):
+    """The oracle port (oracle/pmrd_oracle.c): simulate -> collapse -> count -> call."""
+    from oracle import cport
+
+    t0 = time.perf_counter()
+    r = cport.pipeline_cells(cid, af, depth, seed=int(cfg.seed), mean_family_size=5.0, family_model=1,
+                             max_family_size=cfg.umi.max_family_size, min_fs=cfg.umi.min_family_size,
+                             qthr=cfg.umi.quality_threshold, cthr=cfg.umi.consensus_threshold, n_threads=threads)
+    neg = af <= 1e-4
+    if not neg.any():
+        neg = af == af.min()
+    cport.call_cells(r["n_total"], r["n_variants"], neg, seed=int(cfg.seed), alpha=cfg.stats.alpha)
+    return r["total_reads"], time.perf_counter() - t0
+
+
+def cpu_baseline(cfg, cell_id, af, depth, budget_s=12.0):
+    from oracle import cport
+
+    threads = cport.max_threads()
+    n = 64
+    reads, dt = cpu_pipeline_once(cfg, *cpu_sample_cells(cell_id, af, depth, n), threads)   # warm-up + rate estimate
+    rate = reads / max(dt, 1e-6)
+    per_cell = reads / n
+    n = int(min(len(cell_id), max(64, budget_s * rate / per_cell)))
+    reads, dt = cpu_pipeline_once(cfg, *cpu_sample_cells(cell_id, af, depth, n), threads)
+    return {"value": reads / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} of {len(cell_id)} cells (every {max(1, len(cell_id) // n)}th), {reads} reads in {dt:.2f} s; "
+                      "oracle/pmrd_oracle.c, OpenMP over cells"}
+
+
+# ------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank, world):
+    if rank != 0:
+        return 0
+    cfg, label, cell_id, af, depth = workload(args.workload, 0, 1)
+    from oracle import cport
+
+    threads = cport.max_threads()
+    n = int(os.environ.get("PMRD_REF_CELLS", 256))
+    cid, a, d = cpu_sample_cells(cell_id, af, depth, n)
+    for _ in range(args.warmup):
+        cpu_pipeline_once(cfg, cid, a, d, threads)
+    t0 = time.perf_counter()
+    reads = 0
+    for _ in range(args.steps):
+        r, _dt = cpu_pipeline_once(cfg, cid, a, d, threads)
+        reads += r
+    dt = time.perf_counter() - t0
+    value = reads / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 keys / u32 payload / f64 tests", "data": "synthetic",
+        "config": {"workload": label, "sample": f"{len(cid)} cells per step (every {max(1, len(cell_id) // n)}th cell of the grid)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{len(cid)} cells, {reads // args.steps} reads per step; oracle/pmrd_oracle.c (C + OpenMP "
+                                   "restatement of io.py / umi.py / call.py; the Python reference cannot travel to the GPU box)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------- main arm
+def main() -> int:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("PMRD_BENCH_WORKLOAD", "default"))
+    ap.add_argument("--chunk-log2", type=int, default=int(os.environ.get("PMRD_CHUNK_LOG2", "0")))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    from precise_mrd import _native as nv
+    from precise_mrd import grid
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cfg, label, cell_id, af, depth = workload(args.workload, rank, world)
+    ctx = nv.Context(device=local_rank, seed=int(cfg.seed))
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    sim = grid.read_sim_params(cfg, mean_family_size=5.0, family_model=1, chunk_log2=args.chunk_log2)
+    up = grid.umi_params(cfg)
+    tt = nv.TEST_TYPES[cfg.stats.test_type]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: the plan owns all buffers; run() only enqueues kernels ----------
+    plan = nv.Plan(ctx, cell_id, af, depth, sim, up, neg_af_max=1e-4, test_type=tt, alpha=float(cfg.stats.alpha))
+    n_reads = plan.n_reads
+    for _ in range(max(args.warmup, 3)):
+        plan.run()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = ctx.launch_count
+    ctx.profile_enable(True)
+    with ClockSampler(local_rank) as clocks:
+        ev0.record(stream)
+        for _ in range(args.steps):
+            plan.run()
+        ev1.record(stream)
+        barrier()
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+    launches = ctx.launch_count - launches0
+    ms = ev0.elapsed_time(ev1)
+    res = plan.results()
+    chunk_reads = [plan.chunk_reads(i) for i in range(plan.n_chunks)]
+    n_chunks = plan.n_chunks
+    plan.close()
+
+    # ---- end-to-end arm: public API, host buffers in, host table out, every step ------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h_cid, h_af, h_depth = pin(cell_id), pin(af), pin(depth)
+    out = grid.run_cells(cfg, h_cid, h_af, h_depth, ctx=ctx, sim=sim)      # warm the allocator pool
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = grid.run_cells(cfg, h_cid, h_af, h_depth, ctx=ctx, sim=sim)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = int(h_cid.nbytes + h_af.nbytes + h_depth.nbytes)
+    d2h = int(sum(v.nbytes for k, v in out.items() if isinstance(v, np.ndarray) and k != "variant_call"))
+    assert (out["n_total"] == res["n_total"]).all() and (out["p_adjusted"] == res["p_adjusted"]).all()
+
+    # ---- reduce over ranks: max time, sum of reads ---------------------------------------------
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    r = torch.tensor([float(n_reads)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = [float(x) for x in t.tolist()]
+    total_reads = float(r.item())
+    value = total_reads * args.steps / (ms_max * 1e-3)
+    e2e_value = total_reads * args.steps / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        # dominant kernel of the step by device time
+        top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (0, 0.0))
+        total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
+        kname, (kcount, kms) = top
+        reads_per_launch = float(np.mean(chunk_reads)) if chunk_reads else 0.0
+        bytes_per_launch = B_READ_SORT_PASS * reads_per_launch if kname.startswith("rs_") else None
+        if kname.startswith("rs_upsweep"):
+            bytes_per_launch = 8.0 * reads_per_launch
+        roof = {"bound": "hbm", "kernel": kname, "launches": kcount, "avg_launch_ms": kms / max(kcount, 1),
+                "share_of_step": kms / total_prof_ms, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None}
+        if bytes_per_launch:
+            ach = bytes_per_launch / (kms / kcount * 1e-3) / 1e9
+            roof.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": bytes_per_launch})
+        else:
+            roof.update({"achieved": None, "frac": None})
+        tj = ROOT / "profiles" / "traffic.json"
+        if tj.exists():
+            try:
+                per_read = json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_read")
+                if per_read:
+                    roof["traffic"] = per_read * reads_per_launch
+            except Exception:
+                pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 keys / u32 payload / f64 tests", "data": "synthetic",
+            "config": {"workload": label, "cells_per_gpu": int(len(cell_id)), "reads_per_gpu_per_step": int(n_reads),
+                       "families_per_gpu_per_step": int(depth.sum()), "chunks": n_chunks, "family_sizes": "clip(Poisson(5),1,1000)",
+                       "umi": "12-mer (24 bit)", "input_order": "window-shuffled (Philox-keyed affine permutation)",
+                       "l2": "inputs larger than L2 (>= 1.9 GB per chunk vs 126 MB)", "parallelism": f"replicate axis sharded over {world} GPU(s)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "precise_mrd.grid.run_cells (plan create + H2D + run + D2H per step)"},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "pipeline_roofline": {"algorithmic_bytes_per_read": B_READ_PIPELINE, "achieved": value / world * B_READ_PIPELINE / 1e9,
+                                  "peak": peak, "unit": "GB/s", "frac": value / world * B_READ_PIPELINE / 1e9 / peak},
+            "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
+            "clocks": clocks.summary(),
+            "result_check": {"significant_cells": int(res["significant"].sum()), "mean_error_rate": res["mean_error_rate"],
+                             "families_formed": int(res["totals"][1])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(cfg, cell_id, af, depth)
+            except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

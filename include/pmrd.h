@@ -50,6 +50,11 @@ int32_t pmrd_set_stream(pmrd_ctx* ctx, void* cuda_stream);
 int32_t pmrd_sync(pmrd_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py: gpu_launches) */
 int64_t pmrd_launch_count(const pmrd_ctx* ctx);
+/* Per-kernel device timing: while enabled, every launch is bracketed by CUDA events on the
+ * launching stream.  pmrd_profile_report synchronises and writes "<kernel> <launches>
+ * <total_ms>\n" lines into buf (returns bytes written) and clears the records. */
+int32_t pmrd_profile_enable(pmrd_ctx* ctx, int32_t on);
+int64_t pmrd_profile_report(pmrd_ctx* ctx, char* buf, int64_t cap);
 
 /* ---------------------------------------------------------------- K8: tail p-values - */
 /* test_type */
@@ -251,7 +256,7 @@ typedef struct pmrd_read_sim_params {
     double hop_rate;            /* contamination.py:230-254 */
     double collision_rate;      /* contamination.py:256-278 */
     int32_t shuffle;            /* 0: family-major order; 1: tile-shuffled */
-    int32_t reserved;
+    int32_t chunk_log2;         /* pipeline plans: cells are streamed in chunks of <= 2^chunk_log2 reads (0 = 28) */
 } pmrd_read_sim_params;
 
 /* Counts reads: h_read_offsets[C+1] CSR of reads per cell (family-major layout). */
@@ -307,11 +312,14 @@ int32_t pmrd_plan_results(pmrd_ctx* ctx, pmrd_plan* plan, pmrd_pipeline_result* 
                           double* h_mean_error_rate, int64_t* h_totals3);
 int64_t pmrd_plan_n_reads(const pmrd_plan* plan);
 int64_t pmrd_plan_n_families(const pmrd_plan* plan);
+int64_t pmrd_plan_n_chunks(const pmrd_plan* plan);
+int64_t pmrd_plan_chunk_reads(const pmrd_plan* plan, int64_t chunk);
 void pmrd_plan_destroy(pmrd_plan* plan);
-/* Stage-by-stage entry points of a plan, for per-kernel timing (bench.py roofline): */
-int32_t pmrd_plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* plan); /* sizes + scan + reads  */
-int32_t pmrd_plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* plan); /* sort + families + groups */
-int32_t pmrd_plan_run_call(pmrd_ctx* ctx, pmrd_plan* plan);     /* counts + rate + p + BH */
+/* Stage-by-stage entry points, for per-stage timing (bench.py): the stage for ONE chunk
+ * (chunks share the read buffers, so stages of different chunks cannot be separated). */
+int32_t pmrd_plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* plan, int64_t chunk); /* sizes + scan + reads        */
+int32_t pmrd_plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* plan, int64_t chunk); /* sort + families + cell counts */
+int32_t pmrd_plan_run_call(pmrd_ctx* ctx, pmrd_plan* plan);                    /* error rate + p + BH, all cells */
 
 /* ---------------------------------------------------------------- K11: LoD fit ------ */
 /* LODAnalyzer._fit_detection_curve + _bootstrap_lod_ci (src/precise_mrd/eval/lod.py:

@@ -8,6 +8,44 @@
 
 char g_pmrd_create_err[512] = "";
 
+// ---------------------------------------------------------------- per-kernel timing -----
+// CUDA events recorded around every launch on the launching stream while enabled; the
+// report aggregates by kernel name.  bench.py uses it INSIDE the timed region to get the
+// dominant kernel's average launch duration for the roofline line.
+#include <map>
+#include <string>
+#include <vector>
+struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+};
+struct PmrdProf {
+    std::vector<ProfRec> recs;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t take() {
+        if (!pool.empty()) {
+            cudaEvent_t e = pool.back();
+            pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+};
+void pmrd_prof_begin(pmrd_ctx* ctx, const char* kernel_name) {
+    PmrdProf* p = (PmrdProf*)ctx->prof;
+    if (!p) return;
+    ProfRec r{kernel_name, p->take(), p->take()};
+    cudaEventRecord(r.a, ctx->stream);
+    p->recs.push_back(r);
+}
+void pmrd_prof_end(pmrd_ctx* ctx) {
+    PmrdProf* p = (PmrdProf*)ctx->prof;
+    if (!p || p->recs.empty()) return;
+    cudaEventRecord(p->recs.back().b, ctx->stream);
+}
+
 int32_t collapse_upload_weights(pmrd_ctx* ctx, const double* h_w64);
 int32_t k6_hamming(pmrd_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, int64_t n, int32_t* d_d);
 int32_t k2_gd_families(pmrd_ctx* ctx, const int32_t* d_tile_cell, const int32_t* d_tile_fam0, int64_t n_tiles,
@@ -22,8 +60,10 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
                     int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, double neg_af_max,
                     int32_t test_type, int32_t alternative, double alpha, pmrd_plan** out);
 int32_t plan_run(pmrd_ctx* ctx, pmrd_plan* P);
-int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P);
-int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P);
+int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P, int64_t which);
+int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P, int64_t which);
+int64_t plan_n_chunks(const pmrd_plan* P);
+int64_t plan_chunk_reads(const pmrd_plan* P, int64_t which);
 int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P);
 int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h, double* h_mean_rate, int64_t* h_totals);
 void plan_destroy(pmrd_plan* P);
@@ -67,6 +107,8 @@ int32_t pmrd_create(int32_t device, uint64_t seed, pmrd_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : PMRD_SM_COUNT_DEFAULT;
     ctx->seed = seed;
     ctx->launches = 0;
+    ctx->prof_on = 0;
+    ctx->prof = nullptr;
     ctx->err[0] = 0;
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
@@ -102,6 +144,12 @@ void pmrd_destroy(pmrd_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->own_stream);
+    if (ctx->prof) {
+        PmrdProf* p = (PmrdProf*)ctx->prof;
+        for (ProfRec& r : p->recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        for (cudaEvent_t e : p->pool) cudaEventDestroy(e);
+        delete p;
+    }
     delete ctx;
 }
 
@@ -126,6 +174,50 @@ int32_t pmrd_sync(pmrd_ctx* ctx) {
 }
 
 int64_t pmrd_launch_count(const pmrd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t pmrd_profile_enable(pmrd_ctx* ctx, int32_t on) {
+    if (!ctx) return PMRD_ERR_ARG;
+    if (on && !ctx->prof) ctx->prof = new (std::nothrow) PmrdProf();
+    ctx->prof_on = (on && ctx->prof) ? 1 : 0;
+    return PMRD_OK;
+}
+
+// Synchronises, then writes one line per kernel: "<name> <launches> <total_ms>\n" and clears
+// the records.  Returns the number of bytes written (truncated to cap-1).
+int64_t pmrd_profile_report(pmrd_ctx* ctx, char* buf, int64_t cap) {
+    if (!ctx || !buf || cap <= 0) return 0;
+    buf[0] = 0;
+    PmrdProf* p = (PmrdProf*)ctx->prof;
+    if (!p) return 0;
+    cudaStreamSynchronize(ctx->stream);
+    std::map<std::string, std::pair<long long, double>> agg;
+    std::vector<std::string> order;
+    for (ProfRec& r : p->recs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+        std::string name(r.name);
+        const size_t lt = name.find('<');
+        if (name.size() && name[0] == '(') name = name.substr(1, name.size() - 2);
+        (void)lt;
+        if (!agg.count(name)) order.push_back(name);
+        agg[name].first += 1;
+        agg[name].second += ms;
+        p->pool.push_back(r.a);
+        p->pool.push_back(r.b);
+    }
+    p->recs.clear();
+    cudaGetLastError();
+    int64_t off = 0;
+    for (const std::string& n : order) {
+        char line[256];
+        const int w = snprintf(line, sizeof(line), "%s %lld %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        if (off + w >= cap) break;
+        memcpy(buf + off, line, (size_t)w);
+        off += w;
+    }
+    buf[off] = 0;
+    return off;
+}
 
 }  // extern "C"
 
@@ -564,16 +656,18 @@ int32_t pmrd_plan_run(pmrd_ctx* ctx, pmrd_plan* plan) {
     PMRD_ARG(ctx, plan != nullptr, "plan");
     return plan_run(ctx, plan);
 }
-int32_t pmrd_plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* plan) {
+int32_t pmrd_plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* plan, int64_t chunk) {
     ENTER(ctx);
     PMRD_ARG(ctx, plan != nullptr, "plan");
-    return plan_run_simulate(ctx, plan);
+    return plan_run_simulate(ctx, plan, chunk);
 }
-int32_t pmrd_plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* plan) {
+int32_t pmrd_plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* plan, int64_t chunk) {
     ENTER(ctx);
     PMRD_ARG(ctx, plan != nullptr, "plan");
-    return plan_run_collapse(ctx, plan);
+    return plan_run_collapse(ctx, plan, chunk);
 }
+int64_t pmrd_plan_n_chunks(const pmrd_plan* plan) { return plan_n_chunks(plan); }
+int64_t pmrd_plan_chunk_reads(const pmrd_plan* plan, int64_t chunk) { return plan_chunk_reads(plan, chunk); }
 int32_t pmrd_plan_run_call(pmrd_ctx* ctx, pmrd_plan* plan) {
     ENTER(ctx);
     PMRD_ARG(ctx, plan != nullptr, "plan");

@@ -17,8 +17,13 @@ struct pmrd_ctx {
     cudaStream_t own_stream;
     cudaStream_t stream;
     int64_t launches;
+    int prof_on;   // per-kernel CUDA-event timing (pmrd_profile_enable)
+    void* prof;    // opaque: api.cu
     char err[512];
 };
+
+void pmrd_prof_begin(pmrd_ctx* ctx, const char* kernel_name);
+void pmrd_prof_end(pmrd_ctx* ctx);
 
 extern char g_pmrd_create_err[512];
 
@@ -50,7 +55,9 @@ extern char g_pmrd_create_err[512];
 // launch + count + check
 #define PMRD_LAUNCH(ctx, kernel, grid, block, smem, ...)                                      \
     do {                                                                                      \
+        if ((ctx)->prof_on) pmrd_prof_begin(ctx, #kernel);                                    \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
+        if ((ctx)->prof_on) pmrd_prof_end(ctx);                                               \
         (ctx)->launches++;                                                                    \
         PMRD_CUDA(ctx, cudaGetLastError());                                                   \
     } while (0)

@@ -20,28 +20,29 @@ int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pa
 // scatter the group table into per-cell arrays (cells without reads keep zeros)
 __global__ void __launch_bounds__(256)
 cell_counts_kernel(const uint32_t* __restrict__ grp_id, const uint32_t* __restrict__ grp_cons /*[G*4]*/,
-                   const uint32_t* __restrict__ d_ngroups, uint32_t group_base, int64_t n_cells,
+                   const uint32_t* __restrict__ d_ngroups, int64_t cell0, int64_t n_cells,
                    const uint8_t* __restrict__ alt_allele, int64_t* __restrict__ n_total, int64_t* __restrict__ n_variants) {
+    // group id = cell index inside the chunk; outputs are indexed by cell0 + group
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= (int64_t)*d_ngroups || g >= n_cells) return;
-    const int64_t c = (int64_t)grp_id[g] - (int64_t)group_base;
+    const int64_t c = (int64_t)grp_id[g];
     if (c < 0 || c >= n_cells) return;
     const uint32_t* cc = grp_cons + g * 4;
-    n_total[c] = (int64_t)cc[0] + cc[1] + cc[2] + cc[3];
-    n_variants[c] = cc[alt_allele[c]];
+    n_total[cell0 + c] = (int64_t)cc[0] + cc[1] + cc[2] + cc[3];
+    n_variants[cell0 + c] = cc[alt_allele[cell0 + c]];
 }
 
 // per-cell family counts: number of family-table rows per group
 __global__ void __launch_bounds__(256)
-cell_family_count_kernel(const uint64_t* __restrict__ fam_key, const uint32_t* __restrict__ d_nfam, uint32_t group_base,
+cell_family_count_kernel(const uint64_t* __restrict__ fam_key, const uint32_t* __restrict__ d_nfam, int64_t cell0,
                          int64_t n_cells, unsigned long long* __restrict__ n_families) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = f < (int64_t)*d_nfam;
     const uint32_t g = valid ? (uint32_t)(fam_key[f] >> 32) : 0xffffffffu;
     const uint32_t m = __match_any_sync(0xffffffffu, g);
     if (valid && (m & lanemask_lt()) == 0) {
-        const int64_t c = (int64_t)g - (int64_t)group_base;
-        if (c >= 0 && c < n_cells) atomicAdd(&n_families[c], (unsigned long long)__popc(m));
+        const int64_t c = (int64_t)g;
+        if (c >= 0 && c < n_cells) atomicAdd(&n_families[cell0 + c], (unsigned long long)__popc(m));
     }
 }
 
@@ -82,21 +83,37 @@ error_rate_kernel(uint64_t seed, uint64_t stream_id, const int64_t* __restrict__
 }
 
 // ---------------------------------------------------------------- plan -------------------
-// A plan owns every buffer of one batch of cells, so that run() only enqueues kernels:
-// no allocation, no host sync, no host<->device copy inside the step.
-struct pmrd_plan {
+// A plan owns every buffer of one grid of cells, so that run() only enqueues kernels: no
+// allocation, no host sync, no host<->device copy inside the step.  The grid is cut into
+// CHUNKS of consecutive cells (<= 2^chunk_log2 reads each, default 2^28) that stream through
+// ONE set of read / family buffers sized for the largest chunk -- 180 GB of HBM is plenty, but
+// a chunk must stay below 2^31 reads (32-bit positions in the sort) and small chunks keep
+// the working set of a radix pass closer to L2.  Per-cell counts land in grid-wide arrays;
+// the error model, the tail tests and BH then run ONCE over all cells, as call_mrd does.
+#include <vector>
+
+struct PlanChunk {
     ReadPlan reads;
+    int64_t cell0 = 0, n_cells = 0, fcap = 0;
+    uint64_t varying = 0;
+};
+
+struct pmrd_plan {
+    std::vector<PlanChunk*> chunks;
     pmrd_umi_params up;
     double neg_af_max, alpha;
     int32_t test_type, alternative;
-    int64_t n_cells, fcap;
-    uint64_t varying;
-    uint64_t stream_id;
+    int64_t n_cells = 0, n_reads = 0, n_fam = 0;
+    int64_t max_reads = 0, max_fcap = 0, max_cells = 0;
+    uint64_t stream_id = 0;
     DevBuf keys, keys_tmp, pl, pl_tmp;
     DevBuf fk, fs, fa, fc, fq, fn, ff, fam_start;
-    DevBuf gg, gf, gc, ga, gt, grp_start, counts;
+    DevBuf gg, gf, gc, ga, gt, grp_start, counts, totals;
     DevBuf alt, neg, negc, mean_rate;
     DevBuf o_reads, o_fam, o_tot, o_var, o_p, o_q, o_sig;
+    ~pmrd_plan() {
+        for (PlanChunk* c : chunks) delete c;
+    }
 };
 
 static uint64_t varying_mask_for(int64_t n_cells) {
@@ -107,39 +124,74 @@ static uint64_t varying_mask_for(int64_t n_cells) {
     return m;
 }
 
+__global__ void add_counts_kernel(const uint32_t* __restrict__ counts, unsigned long long* __restrict__ totals) {
+    totals[0] += counts[0];
+    totals[1] += counts[1];
+}
+
 int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
                     int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, double neg_af_max,
                     int32_t test_type, int32_t alternative, double alpha, pmrd_plan** out) {
     PMRD_ARG(ctx, out != nullptr, "out");
     *out = nullptr;
     PMRD_ARG(ctx, n_cells > 0 && n_cells < (1ll << 30), "n_cells");
-    PMRD_ARG(ctx, h_cell_id && h_n_families, "null cell arrays");
+    PMRD_ARG(ctx, h_cell_id && h_n_families && sp, "null cell arrays / params");
     PMRD_ARG(ctx, up && up->mode == PMRD_MODE_WEIGHTED && up->cluster == PMRD_CLUSTER_EXACT, "pipeline needs WEIGHTED/EXACT umi params");
     PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || test_type == PMRD_TEST_BINOMIAL, "Unknown test type");
+    PMRD_ARG(ctx, sp->chunk_log2 == 0 || (sp->chunk_log2 >= 16 && sp->chunk_log2 <= 30), "chunk_log2 must be 0 or in [16, 30]");
     pmrd_plan* P = new (std::nothrow) pmrd_plan();
     PMRD_ARG(ctx, P != nullptr, "out of host memory");
     P->up = *up; P->neg_af_max = neg_af_max; P->alpha = alpha; P->test_type = test_type; P->alternative = alternative;
     P->n_cells = n_cells;
     P->stream_id = (uint64_t)h_cell_id[0];
-    int32_t st = reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, 0, sp, &P->reads, nullptr);
-    if (st != PMRD_OK) { delete P; return st; }
-    if (P->reads.n_reads >= (1ll << 31)) {
-        delete P;
-        PMRD_ARG(ctx, false, "batch too large: chunk the cells so that reads < 2^31");
+    // cut into chunks by expected reads (mean size with 25% head room; exact counts follow)
+    const double budget = (double)(1ll << (sp->chunk_log2 ? sp->chunk_log2 : 28));
+    const double per_family = (sp->mean_family_size + 1.0) * 1.25;
+    int64_t c0 = 0;
+    int32_t st = PMRD_OK;
+    while (c0 < n_cells && st == PMRD_OK) {
+        double acc = 0.0;
+        int64_t c1 = c0;
+        while (c1 < n_cells) {
+            const double add = (double)(h_n_families[c1] > 0 ? h_n_families[c1] : 0) * per_family;
+            if (c1 > c0 && acc + add > budget) break;
+            acc += add;
+            ++c1;
+        }
+        PlanChunk* ch = new (std::nothrow) PlanChunk();
+        if (!ch) { st = PMRD_ERR_ARG; snprintf(ctx->err, sizeof(ctx->err), "out of host memory"); break; }
+        P->chunks.push_back(ch);
+        ch->cell0 = c0;
+        ch->n_cells = c1 - c0;
+        st = reads_plan_build(ctx, h_cell_id + c0, h_af ? h_af + c0 : nullptr, h_n_families + c0, c1 - c0, 0, sp, &ch->reads, nullptr);
+        if (st != PMRD_OK) break;
+        if (ch->reads.n_reads >= (1ll << 31) - 8192) {
+            snprintf(ctx->err, sizeof(ctx->err), "a chunk of %lld cells holds %lld reads (>= 2^31): lower chunk_log2 or split the cell",
+                     (long long)ch->n_cells, (long long)ch->reads.n_reads);
+            st = PMRD_ERR_ARG;
+            break;
+        }
+        // UMI merging can only lower the family count; hopped reads can open new (cell, UMI) families
+        ch->fcap = sp->hop_rate > 0.0 ? ch->reads.n_reads : ch->reads.n_fam;
+        if (ch->fcap < 1) ch->fcap = 1;
+        ch->varying = varying_mask_for(ch->n_cells);
+        P->n_reads += ch->reads.n_reads;
+        P->n_fam += ch->reads.n_fam;
+        if (ch->reads.n_reads > P->max_reads) P->max_reads = ch->reads.n_reads;
+        if (ch->fcap > P->max_fcap) P->max_fcap = ch->fcap;
+        if (ch->n_cells > P->max_cells) P->max_cells = ch->n_cells;
+        c0 = c1;
     }
-    P->varying = varying_mask_for(n_cells);
-    const size_t n = (size_t)(P->reads.n_reads > 0 ? P->reads.n_reads : 1);
-    // UMI merging can only lower the family count; hopped reads can open new (cell, UMI) families
-    P->fcap = (sp->hop_rate > 0.0 ? P->reads.n_reads : P->reads.n_fam);
-    if (P->fcap < 1) P->fcap = 1;
-    const size_t f = (size_t)P->fcap, c = (size_t)n_cells;
+    if (st != PMRD_OK) { delete P; return st; }
+    const size_t n = (size_t)(P->max_reads > 0 ? P->max_reads : 1);
+    const size_t f = (size_t)(P->max_fcap > 0 ? P->max_fcap : 1), g = (size_t)P->max_cells, c = (size_t)n_cells;
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.alloc(ctx->stream, bytes); };
     A(P->keys, n * 8); A(P->keys_tmp, n * 8); A(P->pl, n * 4); A(P->pl_tmp, n * 4);
     A(P->fk, f * 8); A(P->fs, f * 4); A(P->fa, f * 4); A(P->fc, f * 4); A(P->fq, f * 4); A(P->fn, f * 4); A(P->ff, f * 4);
     A(P->fam_start, (f + 1) * 4);
-    A(P->gg, c * 4); A(P->gf, c * 4); A(P->gc, c * 16); A(P->ga, c * 8); A(P->gt, c * 8); A(P->grp_start, (c + 1) * 4);
-    A(P->counts, 8); A(P->alt, c); A(P->neg, c); A(P->negc, 16); A(P->mean_rate, 8);
+    A(P->gg, g * 4); A(P->gf, g * 4); A(P->gc, g * 16); A(P->ga, g * 8); A(P->gt, g * 8); A(P->grp_start, (g + 1) * 4);
+    A(P->counts, 8); A(P->totals, 16); A(P->alt, c); A(P->neg, c); A(P->negc, 16); A(P->mean_rate, 8);
     A(P->o_reads, c * 8); A(P->o_fam, c * 8); A(P->o_tot, c * 8); A(P->o_var, c * 8); A(P->o_p, c * 8); A(P->o_q, c * 8); A(P->o_sig, c);
     uint8_t* h_alt = (uint8_t*)malloc(c * 2);
     if (e == cudaSuccess && h_alt) {
@@ -157,6 +209,10 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
             for (int64_t i = 0; i < n_cells; ++i) h_neg[i] = (h_af ? h_af[i] : 0.0) == min_af;
         e = cudaMemcpyAsync(P->alt.p, h_alt, c, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(P->neg.p, h_neg, c, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(P->totals.p, 0, 16, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(P->o_tot.p, 0, c * 8, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(P->o_var.p, 0, c * 8, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(P->o_fam.p, 0, c * 8, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     }
     const bool oom = h_alt == nullptr;
@@ -170,40 +226,49 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     return PMRD_OK;
 }
 
-// ---- the three stages of one step; each only enqueues kernels (no sync, no allocation of
-// plan buffers) ------------------------------------------------------------------------
-int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P) {
+// ---- stages of one chunk; each only enqueues kernels --------------------------------------
+static int32_t chunk_simulate(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
     // family sizes -> read offsets -> reads (scrambled)
-    PMRD_TRY(reads_plan_sizes(ctx, &P->reads));
-    PMRD_TRY(reads_plan_generate(ctx, &P->reads, P->keys.as<uint64_t>(), P->pl.as<uint32_t>()));
-    return PMRD_OK;
+    PMRD_TRY(reads_plan_sizes(ctx, &ch->reads));
+    return reads_plan_generate(ctx, &ch->reads, P->keys.as<uint64_t>(), P->pl.as<uint32_t>());
 }
 
-int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P) {
-    const int64_t n_cells = P->n_cells, n_reads = P->reads.n_reads;
+static int32_t chunk_collapse(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
     pmrd_family_table fam{P->fk.as<uint64_t>(), P->fs.as<uint32_t>(), P->fa.as<uint32_t>(), P->fc.as<uint32_t>(),
                           P->fq.as<uint32_t>(), P->fn.as<uint32_t>(), P->ff.as<uint32_t>()};
     pmrd_group_table grp{P->gg.as<uint32_t>(), P->gf.as<uint32_t>(), P->gc.as<uint32_t>(), P->ga.as<uint64_t>(), P->gt.as<uint64_t>()};
     PMRD_CUDA(ctx, cudaMemsetAsync(P->counts.p, 0, 8, ctx->stream));
-    if (n_reads > 0)
+    if (ch->reads.n_reads > 0)
         PMRD_TRY(k5_collapse_exact_nosync(ctx, P->keys.as<uint64_t>(), P->pl.as<uint32_t>(), P->keys_tmp.as<uint64_t>(),
-                                          P->pl_tmp.as<uint32_t>(), n_reads, P->varying, &P->up, &fam, P->fcap, &grp, n_cells,
-                                          P->fam_start.as<uint32_t>(), P->grp_start.as<uint32_t>(), P->counts.as<uint32_t>()));
+                                          P->pl_tmp.as<uint32_t>(), ch->reads.n_reads, ch->varying, &P->up, &fam, ch->fcap, &grp,
+                                          ch->n_cells, P->fam_start.as<uint32_t>(), P->grp_start.as<uint32_t>(),
+                                          P->counts.as<uint32_t>()));
     return PMRD_OK;
 }
 
+// per-cell counts of the chunk into the grid-wide arrays (K7)
+static int32_t chunk_counts(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
+    PMRD_LAUNCH(ctx, cell_counts_kernel, pmrd_blocks(ch->n_cells, 256), 256, 0, (const uint32_t*)P->gg.as<uint32_t>(),
+                (const uint32_t*)P->gc.as<uint32_t>(), (const uint32_t*)(P->counts.as<uint32_t>() + 1), ch->cell0, ch->n_cells,
+                (const uint8_t*)P->alt.as<uint8_t>(), P->o_tot.as<int64_t>(), P->o_var.as<int64_t>());
+    PMRD_LAUNCH(ctx, cell_family_count_kernel, pmrd_blocks(ch->fcap, 256), 256, 0, (const uint64_t*)P->fk.as<uint64_t>(),
+                (const uint32_t*)P->counts.as<uint32_t>(), ch->cell0, ch->n_cells, (unsigned long long*)P->o_fam.as<int64_t>());
+    PMRD_LAUNCH(ctx, add_counts_kernel, 1, 1, 0, (const uint32_t*)P->counts.as<uint32_t>(), P->totals.as<unsigned long long>());
+    return PMRD_OK;
+}
+
+static int32_t plan_reset_outputs(pmrd_ctx* ctx, pmrd_plan* P) {
+    const size_t c = (size_t)P->n_cells;
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_tot.p, 0, 8 * c, ctx->stream));
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_var.p, 0, 8 * c, ctx->stream));
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_fam.p, 0, 8 * c, ctx->stream));
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->totals.p, 0, 16, ctx->stream));
+    return PMRD_OK;
+}
+
+// call stage over ALL cells: error rate from the negative controls, tail p per cell, BH (K8, K9)
 int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
     const int64_t n_cells = P->n_cells;
-    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_tot.p, 0, 8 * (size_t)n_cells, ctx->stream));
-    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_var.p, 0, 8 * (size_t)n_cells, ctx->stream));
-    PMRD_CUDA(ctx, cudaMemsetAsync(P->o_fam.p, 0, 8 * (size_t)n_cells, ctx->stream));
-    // per-cell counts (grids sized by capacity; kernels read the true counts from the device)
-    PMRD_LAUNCH(ctx, cell_counts_kernel, pmrd_blocks(n_cells, 256), 256, 0, (const uint32_t*)P->gg.as<uint32_t>(),
-                (const uint32_t*)P->gc.as<uint32_t>(), (const uint32_t*)(P->counts.as<uint32_t>() + 1), 0u, n_cells,
-                (const uint8_t*)P->alt.as<uint8_t>(), P->o_tot.as<int64_t>(), P->o_var.as<int64_t>());
-    PMRD_LAUNCH(ctx, cell_family_count_kernel, pmrd_blocks(P->fcap, 256), 256, 0, (const uint64_t*)P->fk.as<uint64_t>(),
-                (const uint32_t*)P->counts.as<uint32_t>(), 0u, n_cells, (unsigned long long*)P->o_fam.as<int64_t>());
-    // error rate from the negative controls, tail p per cell, BH over the batch
     PMRD_LAUNCH(ctx, error_rate_kernel, 1, 256, 0, ctx->seed, P->stream_id, (const int64_t*)P->o_tot.as<int64_t>(),
                 (const int64_t*)P->o_var.as<int64_t>(), (const uint8_t*)P->neg.as<uint8_t>(), n_cells, P->mean_rate.as<double>(),
                 P->negc.as<int64_t>());
@@ -213,9 +278,28 @@ int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
     return PMRD_OK;
 }
 
+// Stage entry points for per-stage timing.  With more than one chunk the read buffers are
+// reused, so simulate / collapse of different chunks cannot be separated: these run the
+// stage for chunk `which` only (bench.py times chunk 0), plan_run() is the real step.
+int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P, int64_t which) {
+    PMRD_ARG(ctx, which >= 0 && which < (int64_t)P->chunks.size(), "chunk index");
+    return chunk_simulate(ctx, P, P->chunks[(size_t)which]);
+}
+int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P, int64_t which) {
+    PMRD_ARG(ctx, which >= 0 && which < (int64_t)P->chunks.size(), "chunk index");
+    PlanChunk* ch = P->chunks[(size_t)which];
+    if (which == 0) PMRD_TRY(plan_reset_outputs(ctx, P));
+    PMRD_TRY(chunk_collapse(ctx, P, ch));
+    return chunk_counts(ctx, P, ch);
+}
+
 int32_t plan_run(pmrd_ctx* ctx, pmrd_plan* P) {
-    PMRD_TRY(plan_run_simulate(ctx, P));
-    PMRD_TRY(plan_run_collapse(ctx, P));
+    PMRD_TRY(plan_reset_outputs(ctx, P));
+    for (PlanChunk* ch : P->chunks) {
+        PMRD_TRY(chunk_simulate(ctx, P, ch));
+        PMRD_TRY(chunk_collapse(ctx, P, ch));
+        PMRD_TRY(chunk_counts(ctx, P, ch));
+    }
     return plan_run_call(ctx, P);
 }
 
@@ -233,8 +317,10 @@ cell_read_count_kernel(const uint64_t* __restrict__ read_offset, const int64_t* 
 
 int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h, double* h_mean_rate, int64_t* h_totals /*[3]: reads, families, groups*/) {
     const size_t c = (size_t)P->n_cells;
-    PMRD_LAUNCH(ctx, cell_read_count_kernel, pmrd_blocks(P->n_cells, 256), 256, 0, (const uint64_t*)P->reads.read_offset.as<uint64_t>(),
-                (const int64_t*)P->reads.fam_offsets.as<int64_t>(), P->n_cells, P->reads.n_fam, P->reads.n_reads, P->o_reads.as<int64_t>());
+    for (PlanChunk* ch : P->chunks)
+        PMRD_LAUNCH(ctx, cell_read_count_kernel, pmrd_blocks(ch->n_cells, 256), 256, 0, (const uint64_t*)ch->reads.read_offset.as<uint64_t>(),
+                    (const int64_t*)ch->reads.fam_offsets.as<int64_t>(), ch->n_cells, ch->reads.n_fam, ch->reads.n_reads,
+                    P->o_reads.as<int64_t>() + ch->cell0);
     auto D = [&](void* dst, const DevBuf& b, size_t bytes) -> cudaError_t {
         return dst ? cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
     };
@@ -245,14 +331,17 @@ int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h,
         PMRD_CUDA(ctx, D(h->significant, P->o_sig, c));
     }
     PMRD_CUDA(ctx, D(h_mean_rate, P->mean_rate, 8));
-    uint32_t cnt[2] = {0, 0};
-    PMRD_CUDA(ctx, cudaMemcpyAsync(cnt, P->counts.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long tot[2] = {0, 0};
+    PMRD_CUDA(ctx, cudaMemcpyAsync(tot, P->totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (h_totals) { h_totals[0] = P->reads.n_reads; h_totals[1] = cnt[0]; h_totals[2] = cnt[1]; }
+    if (h_totals) { h_totals[0] = P->n_reads; h_totals[1] = (int64_t)tot[0]; h_totals[2] = (int64_t)tot[1]; }
     return PMRD_OK;
 }
 
 void plan_destroy(pmrd_plan* P) { delete P; }
-
-int64_t plan_n_reads(const pmrd_plan* P) { return P ? P->reads.n_reads : 0; }
-int64_t plan_n_families(const pmrd_plan* P) { return P ? P->reads.n_fam : 0; }
+int64_t plan_n_reads(const pmrd_plan* P) { return P ? P->n_reads : 0; }
+int64_t plan_n_families(const pmrd_plan* P) { return P ? P->n_fam : 0; }
+int64_t plan_n_chunks(const pmrd_plan* P) { return P ? (int64_t)P->chunks.size() : 0; }
+int64_t plan_chunk_reads(const pmrd_plan* P, int64_t which) {
+    return (P && which >= 0 && which < (int64_t)P->chunks.size()) ? P->chunks[(size_t)which]->reads.n_reads : 0;
+}

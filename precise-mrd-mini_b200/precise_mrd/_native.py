@@ -62,7 +62,7 @@ class ReadSimParams(C.Structure):
         ("hop_rate", C.c_double),
         ("collision_rate", C.c_double),
         ("shuffle", C.c_int32),
-        ("reserved", C.c_int32),
+        ("chunk_log2", C.c_int32),
     ]
 
 
@@ -173,6 +173,21 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(self.lib.pmrd_launch_count(self.h))
+
+    def profile_enable(self, on: bool = True) -> None:
+        self._check(self.lib.pmrd_profile_enable(self.h, C.c_int32(1 if on else 0)))
+
+    def profile_report(self) -> Dict[str, Tuple[int, float]]:
+        """{kernel name: (launches, total device ms)} since the last report (synchronises)."""
+        buf = C.create_string_buffer(1 << 16)
+        self.lib.pmrd_profile_report.restype = C.c_int64
+        self.lib.pmrd_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        self.lib.pmrd_profile_report(self.h, buf, C.c_int64(len(buf)))
+        out: Dict[str, Tuple[int, float]] = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name] = (int(cnt), float(ms))
+        return out
 
     # -- K8 ------------------------------------------------------------------------------
     def pvalues(self, k, n, rate, test_type: int, alternative: int = ALT_TWO_SIDED) -> np.ndarray:
@@ -375,11 +390,22 @@ class Plan:
     def run(self) -> None:
         self.ctx._check(self.ctx.lib.pmrd_plan_run(self.ctx.h, self.h))
 
-    def run_simulate(self) -> None:
-        self.ctx._check(self.ctx.lib.pmrd_plan_run_simulate(self.ctx.h, self.h))
+    def run_simulate(self, chunk: int = 0) -> None:
+        self.ctx._check(self.ctx.lib.pmrd_plan_run_simulate(self.ctx.h, self.h, C.c_int64(chunk)))
 
-    def run_collapse(self) -> None:
-        self.ctx._check(self.ctx.lib.pmrd_plan_run_collapse(self.ctx.h, self.h))
+    def run_collapse(self, chunk: int = 0) -> None:
+        self.ctx._check(self.ctx.lib.pmrd_plan_run_collapse(self.ctx.h, self.h, C.c_int64(chunk)))
+
+    @property
+    def n_chunks(self) -> int:
+        self.ctx.lib.pmrd_plan_n_chunks.restype = C.c_int64
+        self.ctx.lib.pmrd_plan_n_chunks.argtypes = [C.c_void_p]
+        return int(self.ctx.lib.pmrd_plan_n_chunks(self.h))
+
+    def chunk_reads(self, chunk: int) -> int:
+        self.ctx.lib.pmrd_plan_chunk_reads.restype = C.c_int64
+        self.ctx.lib.pmrd_plan_chunk_reads.argtypes = [C.c_void_p, C.c_int64]
+        return int(self.ctx.lib.pmrd_plan_chunk_reads(self.h, C.c_int64(chunk)))
 
     def run_call(self) -> None:
         self.ctx._check(self.ctx.lib.pmrd_plan_run_call(self.ctx.h, self.h))

@@ -24,7 +24,7 @@ def _umi(native, **kw):
 
 def _sp(native, **kw):
     d = dict(mean_family_size=5.0, family_model=0, max_family_size=1000, contamination_rate=0.0, hop_rate=0.0,
-             collision_rate=0.0, shuffle=1, reserved=0)
+             collision_rate=0.0, shuffle=1, chunk_log2=0)
     d.update(kw)
     return native.ReadSimParams(**d)
 
@@ -286,7 +286,8 @@ def test_plan_stage_entry_points_compose(ctx, native):
     af = np.tile([0.0, 0.02], 16)
     nf = np.full(32, 2000)
     plan = native.Plan(ctx, cid, af, nf, _sp(native), _umi(native))
-    plan.run_simulate(); plan.run_collapse(); plan.run_call()
+    assert plan.n_chunks == 1 and plan.chunk_reads(0) == plan.n_reads
+    plan.run_simulate(0); plan.run_collapse(0); plan.run_call()
     a = plan.results()
     plan.run()
     b = plan.results()
@@ -294,6 +295,29 @@ def test_plan_stage_entry_points_compose(ctx, native):
     for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
         assert (a[k_] == b[k_]).all(), k_
     assert a["totals"][0] == plan.n_reads and a["totals"][2] == 32
+
+
+def test_chunked_plan_equals_single_chunk(ctx, native):
+    """Streaming the grid through small chunks must not change a single count or p-value."""
+    rng = np.random.default_rng(8)
+    c = 300
+    cid = np.arange(c) + 5
+    af = np.tile([0.0, 1e-4, 0.01, 0.05, 0.0005], c // 5)
+    nf = rng.integers(100, 2500, c)
+    one = ctx.pipeline_cells(cid, af, nf, _sp(native), _umi(native))
+    plan = native.Plan(ctx, cid, af, nf, _sp(native, chunk_log2=16), _umi(native))
+    assert plan.n_chunks > 5 and sum(plan.chunk_reads(i) for i in range(plan.n_chunks)) == plan.n_reads
+    plan.run()
+    many = plan.results()
+    ctx.profile_enable(True)
+    plan.run()
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+    plan.close()
+    for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+        assert (one[k_] == many[k_]).all(), k_
+    assert one["mean_error_rate"] == many["mean_error_rate"] and (one["totals"] == many["totals"]).all()
+    assert prof["rs_downsweep_kernel<true>"][0] >= plan.n_chunks and prof["reads_gen_kernel"][1] > 0
 
 
 # ------------------------------------------------------------------------------ K11 LoD fit

@@ -97,3 +97,43 @@ def test_gb_weighted_consensus_matches_reference(golden):
     assert (q == g["want_fam_quality"][order][has]).all()          # mean of ints: exact
     assert int(((fam["flags"] & port.FAM_KEPT) != 0).sum()) == int(g["want_kept"])
     assert (grp["consensus_count"] == g["want_consensus_count"][grp["group"]]).all()
+
+
+def test_c_oracle_collapse_matches_reference_and_port(golden):
+    """oracle/pmrd_oracle.c (the cpu_baseline port) reproduces the reference-generated G-B fixture."""
+    from oracle import cport
+
+    g = golden("gb_reads.npz")
+    mn, mx, qthr = [int(v) for v in g["params"]]
+    fam = cport.collapse_weighted(g["keys"], g["payload"], mn, mx, qthr, float(g["consensus_threshold"]))
+    want, _ = port.collapse_exact(g["keys"], g["payload"], 0, mn, mx, qthr, float(g["consensus_threshold"]))
+    for k in want:
+        assert (fam[k] == want[k]).all(), k
+    order = np.argsort(g["want_fam_key"], kind="stable")
+    has = (fam["flags"] & port.FAM_HAS_CONSENSUS) != 0
+    assert (has == (g["want_fam_allele"][order] >= 0)).all()
+
+
+def test_c_oracle_statistics_and_pipeline_sanity():
+    from oracle import cport
+
+    lib = cport.load()
+    rng = np.random.default_rng(4)
+    for _ in range(300):
+        mu = 10 ** rng.uniform(-3, 3)
+        k = int(rng.poisson(mu * rng.choice([0.5, 1, 2])))
+        want = port.poisson_test(k, mu)
+        got = lib.oracle_poisson_two_sided(k, mu)
+        assert abs(got - want) <= 1e-9 * max(want, 1e-300) + 1e-15
+    p = rng.uniform(size=500) ** 3
+    c = cport.call_cells(np.full(500, 1000), rng.poisson(1.0, 500), np.ones(500), seed=1)
+    rej, adj = port.benjamini_hochberg(c["p_value"], 0.05)
+    assert (rej == c["significant"]).all() and np.allclose(adj, c["p_adjusted"], rtol=1e-15, atol=0)
+    cells = np.arange(24)
+    af = np.tile([0.0, 0.1], 12)
+    r1 = cport.pipeline_cells(cells, af, np.full(24, 2000), seed=3, n_threads=1)
+    r2 = cport.pipeline_cells(cells, af, np.full(24, 2000), seed=3, n_threads=4)
+    assert (r1["n_total"] == r2["n_total"]).all() and (r1["n_variants"] == r2["n_variants"]).all()   # thread-count independent
+    assert abs(r1["total_reads"] / (24 * 2000) - 5.03) < 0.1
+    frac = r1["n_variants"] / r1["n_total"]
+    assert frac[af == 0].max() < 0.03 and abs(frac[af > 0].mean() - 0.1) < 0.03   # 5% per-read error leaks ~1.4% alt consensus at AF 0
