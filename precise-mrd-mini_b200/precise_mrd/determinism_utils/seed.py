@@ -1,0 +1,62 @@
+"""``set_global_seed`` / ``env_fingerprint`` (``determinism_utils/seed.py:15-121``)."""
+from __future__ import annotations
+
+import os
+import platform
+import random
+import subprocess
+import sys
+from typing import Any
+
+import numpy as np
+
+
+def set_global_seed(seed: int, deterministic_ops: bool = True) -> np.random.Generator:
+    """Seeds Python / NumPy (and torch when present) and returns ``np.random.default_rng(seed)``.
+    The returned generator is what the stage functions draw their Philox salt from."""
+    os.environ["PYTHONHASHSEED"] = str(seed)      # no effect after start-up; kept for parity
+    random.seed(seed)
+    rng = np.random.default_rng(seed)
+    try:
+        import torch
+
+        torch.manual_seed(seed)
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed_all(seed)
+    except Exception:
+        pass
+    return rng
+
+
+def env_fingerprint() -> dict[str, Any]:
+    def git_sha() -> str:
+        try:
+            return subprocess.check_output(["git", "rev-parse", "HEAD"], text=True, timeout=5, stderr=subprocess.DEVNULL).strip()
+        except Exception:
+            return "unknown"
+
+    fp: dict[str, Any] = {"python_version": sys.version, "platform": platform.platform(), "git_sha": git_sha(),
+                          "numpy_version": np.__version__}
+    try:
+        import pandas as pd
+
+        fp["pandas_version"] = pd.__version__
+    except ImportError:
+        pass
+    try:
+        import scipy
+
+        fp["scipy_version"] = scipy.__version__
+    except ImportError:
+        pass
+    try:
+        import torch
+
+        fp["torch_version"] = torch.__version__
+        fp["cuda_available"] = bool(torch.cuda.is_available())
+    except ImportError:
+        fp["torch_version"] = None
+        fp["cuda_available"] = False
+    fp["cpu_count"] = os.cpu_count() or 1
+    fp["machine"] = platform.machine()
+    return fp

@@ -271,7 +271,7 @@ def test_pipeline_equals_oracle_on_the_same_reads(ctx, native, test_type):
     assert (res["p_value"][~ok] < 1e-49).all()
     rej, adj = port.benjamini_hochberg(res["p_value"], 0.05)
     assert (res["significant"] == rej).all() and (res["p_adjusted"] == adj).all()
-    assert res["significant"][(af >= 0.05) & (nf >= 1000)].all() and not res["significant"][af == 0.0].any()
+    assert res["significant"][(af >= 0.05) & (nf >= 1000)].all()      # (two-sided: blanks may be flagged LOW, App. A #13)
     # deterministic and independent of batch composition: rerun, and a sub-batch containing the negatives
     res2 = ctx.pipeline_cells(cid, af, nf, sp, up, neg_af_max=1e-4, test_type=tt, alpha=0.05)
     for k_ in ("n_total", "n_variants", "p_value", "p_adjusted"):

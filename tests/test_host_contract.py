@@ -1,0 +1,130 @@
+"""Host-side contract tests (no GPU): config hashing, tolerant loader, cell grid order, artifact
+validation, manifest format, CLI wiring, packing helpers.  Modelled on the reference's
+tests/test_determinism_hashes.py, tests/test_artifact_contract.py and tests/test_rng_api.py."""
+import ast
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "precise-mrd-mini_b200" / "precise_mrd"
+
+
+def test_config_hash_matches_reference_value():
+    from precise_mrd.config import load_config
+
+    cfg = load_config(PKG / "assets" / "configs" / "smoke.yaml")
+    cfg.seed = 7
+    assert cfg.config_hash() == "0b42f9b03f3fd555"
+    assert cfg.fastq is None and "fastq" in cfg.to_dict()
+
+
+def test_default_yaml_with_unknown_keys_loads():
+    from precise_mrd.config import load_config, section
+
+    cfg = load_config(PKG / "assets" / "configs" / "default.yaml")      # carries max_edit_distance, min_alt_umi, lob_replicates
+    assert cfg.simulation.n_replicates == 1000 and cfg.umi.max_family_size == 1000
+    assert section(cfg, "umi")["min_family_size"] == 3
+    # dict sub-sections are accepted too (tests/test_rng_api.py:151-172)
+    class C:  # noqa: D401
+        umi = {"min_family_size": 2}
+    assert section(C(), "umi")["min_family_size"] == 2
+
+
+def test_grid_cells_meshgrid_order_and_global_ids():
+    from precise_mrd.grid import grid_cells
+
+    cid, af, depth, rep = grid_cells([0.1, 0.2], [10, 20, 30], 2)
+    a, d, r = np.meshgrid([0.1, 0.2], [10, 20, 30], np.arange(2), indexing="ij")
+    assert (af == a.ravel()).all() and (depth == d.ravel()).all() and (rep == r.ravel()).all()   # simulate.py:133-141
+    assert (cid == np.arange(12)).all()
+    # sharding the replicate axis over 2 ranks covers every global cell id exactly once
+    c0 = grid_cells([0.1, 0.2], [10, 20, 30], 2, rep_offset=0, rep_stride=4)[0]
+    c1 = grid_cells([0.1, 0.2], [10, 20, 30], 2, rep_offset=2, rep_stride=4)[0]
+    assert sorted(np.concatenate([c0, c1]).tolist()) == list(range(24))
+
+
+def test_manifest_and_validation_roundtrip(tmp_path):
+    from precise_mrd.determinism_utils import hash_file, write_manifest
+    from precise_mrd.validation import assert_hashes_stable, validate_artifacts
+
+    reports = tmp_path / "reports"
+    reports.mkdir()
+    metrics = {"schema_version": "1.0.0", "roc_auc": 0.5, "average_precision": 0.3, "detected_cases": 0, "total_cases": 2, "calibration": []}
+    ctx = {"schema_version": "1.0.0", "seed": 7, "timestamp": "2024-10-03T12:00:00", "config_hash": "x", "git_sha": "y", "python_version": "3"}
+    (reports / "metrics.json").write_text(json.dumps(metrics))
+    (reports / "run_context.json").write_text(json.dumps(ctx))
+    write_manifest([reports / "metrics.json", reports / "run_context.json"], reports / "hash_manifest.txt")
+    line = (reports / "hash_manifest.txt").read_text().splitlines()[0]
+    assert line == f"{hash_file(reports / 'metrics.json')}  {reports / 'metrics.json'}"           # "<sha256>  <path>"
+    validate_artifacts(reports)
+    (reports / "lob.json").write_text(json.dumps({"schema_version": "1.0.0", "lob_value": -1}))
+    with pytest.raises(Exception):
+        validate_artifacts(reports)
+    (reports / "lob.json").unlink()
+    (reports / "lod_table.csv").write_text("depth,lod_af\n1000,0.1\n")
+    with pytest.raises(ValueError):
+        validate_artifacts(reports)
+    (reports / "lod_table.csv").unlink()
+    write_manifest([reports / "metrics.json"], reports / "m2.txt")
+    with pytest.raises(AssertionError):
+        assert_hashes_stable(reports / "hash_manifest.txt", reports / "m2.txt")
+    with pytest.raises(AssertionError):
+        validate_artifacts(tmp_path / "nope")
+
+
+def test_cli_surface():
+    from click.testing import CliRunner
+
+    from precise_mrd.cli import main
+
+    r = CliRunner().invoke(main, ["--help"])
+    for cmd in ("smoke", "determinism", "eval-lob", "eval-lod", "eval-loq", "eval-contamination"):
+        assert cmd in r.output
+    r = CliRunner().invoke(main, ["--config", "/nonexistent.yaml", "smoke"])
+    assert r.exit_code != 0 and "Configuration file not found" in r.output                        # cli.py:51
+
+
+def test_no_legacy_global_rng_in_package():
+    """tests/test_rng_api.py:9-114: no np.random.<legacy> calls; stages take an explicit rng."""
+    banned = {"seed", "rand", "randn", "randint", "random_sample", "choice", "normal", "uniform", "poisson", "binomial", "RandomState"}
+    for path in PKG.rglob("*.py"):
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and node.attr in banned:
+                v = node.value
+                if isinstance(v, ast.Attribute) and v.attr == "random" and isinstance(v.value, ast.Name) and v.value.id in ("np", "numpy"):
+                    raise AssertionError(f"{path}: np.random.{node.attr}")
+
+
+def test_pack_unpack_bases():
+    from precise_mrd.umi import pack_bases, unpack_bases
+
+    seqs = ["ACGT", "TTTT", "AAAA", "CAGT"]
+    p = pack_bases(seqs)
+    assert [unpack_bases(v, 4) for v in p] == seqs
+    assert list(np.argsort(p)) == list(np.argsort(seqs))
+    with pytest.raises(ValueError):
+        pack_bases(["ACGN"])
+
+
+def test_metrics_match_sklearn_definitions():
+    from sklearn.metrics import average_precision_score, roc_auc_score
+
+    from precise_mrd.metrics import average_precision, bootstrap_metric, calibration_analysis
+    from precise_mrd.metrics import roc_auc_score as auc
+
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        y = rng.integers(0, 2, 120)
+        s = np.round(rng.random(120), 1)          # heavy ties
+        assert abs(auc(y, s) - roc_auc_score(y, s)) < 1e-12
+        assert abs(average_precision(y, s) - average_precision_score(y, s)) < 1e-12
+    assert auc(np.zeros(5), np.arange(5)) == 0.5                               # metrics.py:18-24 fallback
+    a = bootstrap_metric(y, s, auc, 50, np.random.default_rng(3))
+    b = bootstrap_metric(y, s, auc, 50, np.random.default_rng(3))
+    assert a == b and a["lower"] <= a["mean"] <= a["upper"]                    # test_lob_lod_bootstrap.py:148-168
+    cal = calibration_analysis(np.array([0, 1, 1]), np.array([0.05, 0.95, 1.0]))
+    assert cal[-1]["bin"] == 9 and cal[-1]["count"] == 2                       # last bin closed
