@@ -57,7 +57,7 @@ def _load_pipeline_config(config_option: Optional[Path], seed: int) -> PipelineC
     return config
 
 
-def _run_smoke_pipeline(config: PipelineConfig, seed: int, output_dir: Path) -> Dict[str, Path]:
+def _run_smoke_pipeline(config: PipelineConfig, seed: int, output_dir: Path, context_dir: Optional[Path] = None) -> Dict[str, Path]:
     from .call import call_mrd
     from .collapse import collapse_umis
     from .error_model import fit_error_model
@@ -84,7 +84,8 @@ def _run_smoke_pipeline(config: PipelineConfig, seed: int, output_dir: Path) -> 
         "schema_version": "1.0.0", "seed": seed,
         "timestamp": datetime(2024, 10, 3, 12, 0, 0).isoformat(),     # constant, for hash stability (cli.py:136)
         "config_hash": config.config_hash(),
-        "cli_args": {"command": "smoke", "seed": seed, "config_run_id": config.run_id, "output_dir": str(stage_dir)},
+        "cli_args": {"command": "smoke", "seed": seed, "config_run_id": config.run_id,
+                     "output_dir": str(context_dir if context_dir is not None else stage_dir)},
         **env_fingerprint(),
     }
     PipelineIO.save_json(metrics, paths["metrics"])
@@ -123,11 +124,13 @@ def smoke_cmd(ctx: CLIContext, out_dir: Path) -> None:
 def determinism_cmd(ctx: CLIContext, out_dir: Path) -> None:
     """Run the smoke pipeline twice and assert identical artifacts."""
     config = _load_pipeline_config(ctx.config_override, ctx.seed)
-    first = _run_smoke_pipeline(config, ctx.seed, out_dir / "run1")
+    # both runs record the same output_dir in run_context.json, which is part of the manifest
+    # (the reference records run1/ and run2/ there, so its own `determinism` can never pass)
+    first = _run_smoke_pipeline(config, ctx.seed, out_dir / "run1", context_dir=out_dir)
     validate_artifacts(REPORTS_DIR)
     snap = Path(first["manifest"]).with_name("hash_manifest_run1.txt")
     shutil.copy2(first["manifest"], snap)
-    second = _run_smoke_pipeline(config, ctx.seed, out_dir / "run2")
+    second = _run_smoke_pipeline(config, ctx.seed, out_dir / "run2", context_dir=out_dir)
     validate_artifacts(REPORTS_DIR)
     assert_hashes_stable(snap, Path(second["manifest"]))
     click.echo(json.dumps({"stage": "determinism", "seed": ctx.seed, "status": "hashes-identical",

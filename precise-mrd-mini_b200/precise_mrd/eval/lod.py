@@ -87,7 +87,10 @@ class LODAnalyzer:
         from .. import grid
 
         ctx = nv.default_context(int(self.config.seed))
-        return grid.run_cells(self.config, cell_id, af, depth, ctx=ctx, neg_af_max=0.0)
+        # one-sided (greater) test: a read-level "detection" is an EXCESS of alt families over the
+        # blank-derived background (G-B stats.py:135-157); the two-sided G-D test also fires when a
+        # cell sits significantly BELOW the U(0.5,2)-inflated expectation
+        return grid.run_cells(self.config, cell_id, af, depth, ctx=ctx, neg_af_max=0.0, alternative=nv.ALT_GREATER)
 
     # ------------------------------------------------------------------ LoB
     def estimate_lob(self, n_blank_runs: int = 100) -> Dict[str, Any]:

@@ -100,7 +100,7 @@ class ContaminationSimulator:
             afs[:n_rep] = (1 - rate) * af + rate * min(0.1, af * 10)
         sim = grid.read_sim_params(self.config, hop_rate=rate if kind == "hop" else 0.0,
                                    collision_rate=rate if kind == "collision" else 0.0)
-        res = grid.run_cells(self.config, cid, afs, np.full(n_rep + n_blank, depth, dtype=np.int64), ctx=ctx, sim=sim, neg_af_max=0.0)
+        res = grid.run_cells(self.config, cid, afs, np.full(n_rep + n_blank, depth, dtype=np.int64), ctx=ctx, sim=sim, neg_af_max=0.0, alternative=nv.ALT_GREATER)
         return [int(v) for v in (res["p_value"][:n_rep] <= float(self.config.stats.alpha))]
 
     # ------------------------------------------------------------------ reference perturbations (stages engine)
