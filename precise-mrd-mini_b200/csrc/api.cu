@@ -595,7 +595,7 @@ int32_t pmrd_simulate_reads_count(pmrd_ctx* ctx, const int64_t* h_cell_id, const
     h_read_offsets[0] = 0;
     if (n_cells <= 0) return PMRD_OK;
     ReadPlan plan;
-    int32_t st = reads_plan_build(ctx, h_cell_id, nullptr, h_n_families, n_cells, 0, sp, &plan, h_read_offsets);
+    int32_t st = reads_plan_build(ctx, h_cell_id, nullptr, h_n_families, n_cells, 0, sp, 0, &plan, h_read_offsets);
     cudaStreamSynchronize(ctx->stream);
     return st;
 }
@@ -608,7 +608,7 @@ int32_t pmrd_simulate_reads_dev(pmrd_ctx* ctx, const int64_t* h_cell_id, const d
     *n_reads = 0;
     if (n_cells <= 0) return PMRD_OK;
     ReadPlan plan;
-    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, &plan, nullptr));
+    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, 0, &plan, nullptr));
     *n_reads = plan.n_reads;
     if (plan.n_reads > capacity) {
         snprintf(ctx->err, sizeof(ctx->err), "read capacity %lld < %lld reads", (long long)capacity, (long long)plan.n_reads);
@@ -627,7 +627,7 @@ int32_t pmrd_simulate_reads(pmrd_ctx* ctx, const int64_t* h_cell_id, const doubl
     *n_reads = 0;
     if (n_cells <= 0) return PMRD_OK;
     ReadPlan plan;
-    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, &plan, nullptr));
+    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, 0, &plan, nullptr));
     *n_reads = plan.n_reads;
     if (plan.n_reads > capacity) {
         snprintf(ctx->err, sizeof(ctx->err), "read capacity %lld < %lld reads", (long long)capacity, (long long)plan.n_reads);

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(128)
 family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload_or_idx,
               const uint64_t* __restrict__ keys_orig, const uint32_t* __restrict__ payload_orig,
               const uint32_t* __restrict__ fam_start, const uint32_t* __restrict__ d_nfam, int64_t fam_cap,
-              pmrd_umi_params P, FamOut out) {
+              pmrd_umi_params P, uint32_t sentinel_umi, FamOut out) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= (int64_t)*d_nfam || f >= fam_cap) return;
     const uint32_t lo = fam_start[f], hi = fam_start[f + 1];
@@ -239,6 +239,7 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
     }
     if ((int64_t)size >= (int64_t)P.min_family_size) flags |= PMRD_FAM_KEPT;
     if ((int64_t)size > (int64_t)P.max_family_size) flags |= PMRD_FAM_OVERSIZE;
+    if (sentinel_umi != 0u && (uint32_t)key == sentinel_umi) flags = 0;  // padding of a tile-aligned cell
     out.key[f] = key;
     out.size[f] = size;
     out.n_alt[f] = n_alt;
@@ -359,14 +360,15 @@ int32_t k6_hamming(pmrd_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, int6
 template <bool GATHER>
 static int32_t launch_family(pmrd_ctx* ctx, int mode, const uint64_t* keys, const uint32_t* pl_or_idx,
                              const uint64_t* keys_orig, const uint32_t* payload_orig, const uint32_t* fam_start,
-                             const uint32_t* d_nfam, int64_t fam_cap, const pmrd_umi_params& P, FamOut out) {
+                             const uint32_t* d_nfam, int64_t fam_cap, const pmrd_umi_params& P, FamOut out,
+                             uint32_t sentinel_umi = 0u) {
     const int grid = pmrd_blocks(fam_cap, 128);
     if (mode == PMRD_MODE_WEIGHTED) {
-        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_WEIGHTED, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, out);
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_WEIGHTED, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, sentinel_umi, out);
     } else if (mode == PMRD_MODE_MAJORITY) {
-        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_MAJORITY, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, out);
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_MAJORITY, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, sentinel_umi, out);
     } else {
-        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_COUNT, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, out);
+        PMRD_LAUNCH(ctx, (family_kernel<PMRD_MODE_COUNT, GATHER>), grid, 128, 0, keys, pl_or_idx, keys_orig, payload_orig, fam_start, d_nfam, fam_cap, P, sentinel_umi, out);
     }
     return PMRD_OK;
 }
@@ -377,16 +379,25 @@ int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pa
                                  uint32_t* d_payload_tmp, int64_t n_reads, uint64_t varying, const pmrd_umi_params* params,
                                  const pmrd_family_table* d_fam, int64_t capacity_f, const pmrd_group_table* d_grp,
                                  int64_t capacity_g, uint32_t* d_fam_start /*[capacity_f+1]*/,
-                                 uint32_t* d_grp_start /*[capacity_g+1]*/, uint32_t* d_counts) {
+                                 uint32_t* d_grp_start /*[capacity_g+1]*/, uint32_t* d_counts,
+                                 const int64_t* d_cell_tile_start /* non-null: cell-major, tile-padded input */,
+                                 int64_t n_seg_cells, int seg_key_bits) {
     const pmrd_umi_params P = *params;
-    if (varying == 0) PMRD_TRY(radix_varying_bits(ctx, d_keys, n_reads, &varying));
     int in_b = 0;
-    PMRD_TRY(radix_sort_pairs(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, varying, &in_b));
+    if (d_cell_tile_start) {
+        // every cell is sorted on its own over the UMI bits only: 3 passes for a 12-mer UMI
+        PMRD_TRY(radix_sort_pairs_segmented(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, d_cell_tile_start,
+                                            n_seg_cells, seg_key_bits, &in_b));
+    } else {
+        if (varying == 0) PMRD_TRY(radix_varying_bits(ctx, d_keys, n_reads, &varying));
+        PMRD_TRY(radix_sort_pairs(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, varying, &in_b));
+    }
     const uint64_t* sk = in_b ? d_keys_tmp : d_keys;
     const uint32_t* sp = in_b ? d_payload_tmp : d_payload;
     PMRD_TRY(find_segments_dev(ctx, sk, n_reads, nullptr, 0, capacity_f, d_fam_start, d_counts));
     FamOut out{d_fam->key, d_fam->size, d_fam->n_alt, d_fam->consensus, d_fam->qsum, d_fam->n_best, d_fam->flags};
-    PMRD_TRY(launch_family<false>(ctx, P.mode, sk, sp, nullptr, nullptr, d_fam_start, d_counts, capacity_f, P, out));
+    PMRD_TRY(launch_family<false>(ctx, P.mode, sk, sp, nullptr, nullptr, d_fam_start, d_counts, capacity_f, P, out,
+                                  d_cell_tile_start ? 0xffffffffu : 0u));
     if (d_grp) {
         PMRD_TRY(find_segments_dev(ctx, d_fam->key, capacity_f, d_counts, 32, capacity_g, d_grp_start, d_counts + 1));
         int grid = (int)(capacity_g < (int64_t)ctx->sm_count * 32 ? capacity_g : (int64_t)ctx->sm_count * 32);
@@ -425,7 +436,7 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
     if (P.cluster == PMRD_CLUSTER_EXACT) {
         PMRD_TRY(k5_collapse_exact_nosync(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, 0, params, d_fam, fcap,
                                           want_groups ? d_grp : nullptr, gcap, fam_start.as<uint32_t>(), grp_start.as<uint32_t>(),
-                                          counts.as<uint32_t>()));
+                                          counts.as<uint32_t>(), nullptr, 0, 0));
         PMRD_TRY(read_count(ctx, counts.as<uint32_t>(), &nf));
         if (want_groups) PMRD_TRY(read_count(ctx, counts.as<uint32_t>() + 1, &ng));
     } else {

@@ -15,7 +15,8 @@
 int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp,
                                  uint32_t* d_payload_tmp, int64_t n_reads, uint64_t varying, const pmrd_umi_params* params,
                                  const pmrd_family_table* d_fam, int64_t capacity_f, const pmrd_group_table* d_grp,
-                                 int64_t capacity_g, uint32_t* d_fam_start, uint32_t* d_grp_start, uint32_t* d_counts);
+                                 int64_t capacity_g, uint32_t* d_fam_start, uint32_t* d_grp_start, uint32_t* d_counts,
+                                 const int64_t* d_cell_tile_start, int64_t n_seg_cells, int seg_key_bits);
 
 // scatter the group table into per-cell arrays (cells without reads keep zeros)
 __global__ void __launch_bounds__(256)
@@ -37,7 +38,8 @@ __global__ void __launch_bounds__(256)
 cell_family_count_kernel(const uint64_t* __restrict__ fam_key, const uint32_t* __restrict__ d_nfam, int64_t cell0,
                          int64_t n_cells, unsigned long long* __restrict__ n_families) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = f < (int64_t)*d_nfam;
+    // (families whose UMI is the padding sentinel of a tile-aligned cell are not families)
+    const bool valid = f < (int64_t)*d_nfam && (uint32_t)fam_key[f] != READS_SENTINEL_UMI;
     const uint32_t g = valid ? (uint32_t)(fam_key[f] >> 32) : 0xffffffffu;
     const uint32_t m = __match_any_sync(0xffffffffu, g);
     if (valid && (m & lanemask_lt()) == 0) {
@@ -163,21 +165,22 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
         P->chunks.push_back(ch);
         ch->cell0 = c0;
         ch->n_cells = c1 - c0;
-        st = reads_plan_build(ctx, h_cell_id + c0, h_af ? h_af + c0 : nullptr, h_n_families + c0, c1 - c0, 0, sp, &ch->reads, nullptr);
+        st = reads_plan_build(ctx, h_cell_id + c0, h_af ? h_af + c0 : nullptr, h_n_families + c0, c1 - c0, 0, sp, /*segmented=*/1,
+                              &ch->reads, nullptr);
         if (st != PMRD_OK) break;
-        if (ch->reads.n_reads >= (1ll << 31) - 8192) {
+        if (ch->reads.n_out >= (1ll << 31) - 8192) {
             snprintf(ctx->err, sizeof(ctx->err), "a chunk of %lld cells holds %lld reads (>= 2^31): lower chunk_log2 or split the cell",
                      (long long)ch->n_cells, (long long)ch->reads.n_reads);
             st = PMRD_ERR_ARG;
             break;
         }
         // UMI merging can only lower the family count; hopped reads can open new (cell, UMI) families
-        ch->fcap = sp->hop_rate > 0.0 ? ch->reads.n_reads : ch->reads.n_fam;
+        ch->fcap = sp->hop_rate > 0.0 ? ch->reads.n_reads : ch->reads.n_fam + ch->n_cells /* padding sentinels */;
         if (ch->fcap < 1) ch->fcap = 1;
         ch->varying = varying_mask_for(ch->n_cells);
         P->n_reads += ch->reads.n_reads;
         P->n_fam += ch->reads.n_fam;
-        if (ch->reads.n_reads > P->max_reads) P->max_reads = ch->reads.n_reads;
+        if (ch->reads.n_out > P->max_reads) P->max_reads = ch->reads.n_out;
         if (ch->fcap > P->max_fcap) P->max_fcap = ch->fcap;
         if (ch->n_cells > P->max_cells) P->max_cells = ch->n_cells;
         c0 = c1;
@@ -240,9 +243,11 @@ static int32_t chunk_collapse(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
     PMRD_CUDA(ctx, cudaMemsetAsync(P->counts.p, 0, 8, ctx->stream));
     if (ch->reads.n_reads > 0)
         PMRD_TRY(k5_collapse_exact_nosync(ctx, P->keys.as<uint64_t>(), P->pl.as<uint32_t>(), P->keys_tmp.as<uint64_t>(),
-                                          P->pl_tmp.as<uint32_t>(), ch->reads.n_reads, ch->varying, &P->up, &fam, ch->fcap, &grp,
+                                          P->pl_tmp.as<uint32_t>(), ch->reads.n_out, ch->varying, &P->up, &fam, ch->fcap, &grp,
                                           ch->n_cells, P->fam_start.as<uint32_t>(), P->grp_start.as<uint32_t>(),
-                                          P->counts.as<uint32_t>()));
+                                          P->counts.as<uint32_t>(),
+                                          ch->reads.segmented ? (const int64_t*)ch->reads.cell_tile_start.as<int64_t>() : nullptr,
+                                          ch->n_cells, 24));
     return PMRD_OK;
 }
 
@@ -303,24 +308,16 @@ int32_t plan_run(pmrd_ctx* ctx, pmrd_plan* P) {
     return plan_run_call(ctx, P);
 }
 
-// per-cell read counts from the plan's read offsets (cheap; not part of the timed step)
-__global__ void __launch_bounds__(256)
-cell_read_count_kernel(const uint64_t* __restrict__ read_offset, const int64_t* __restrict__ fam_offsets, int64_t n_cells,
-                       int64_t n_fam, int64_t n_reads, int64_t* __restrict__ out) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_cells) return;
-    const int64_t f0 = fam_offsets[i], f1 = fam_offsets[i + 1];
-    const int64_t r0 = f0 < n_fam ? (int64_t)read_offset[f0] : n_reads;
-    const int64_t r1 = f1 < n_fam ? (int64_t)read_offset[f1] : n_reads;
-    out[i] = r1 - r0;
+__global__ void __launch_bounds__(256) sum_i64_kernel(const int64_t* __restrict__ v, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long a = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a += (unsigned long long)v[i];
+    a = warp_sum(a);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, a);
 }
 
 int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h, double* h_mean_rate, int64_t* h_totals /*[3]: reads, families, groups*/) {
     const size_t c = (size_t)P->n_cells;
-    for (PlanChunk* ch : P->chunks)
-        PMRD_LAUNCH(ctx, cell_read_count_kernel, pmrd_blocks(ch->n_cells, 256), 256, 0, (const uint64_t*)ch->reads.read_offset.as<uint64_t>(),
-                    (const int64_t*)ch->reads.fam_offsets.as<int64_t>(), ch->n_cells, ch->reads.n_fam, ch->reads.n_reads,
-                    P->o_reads.as<int64_t>() + ch->cell0);
+    for (PlanChunk* ch : P->chunks) PMRD_TRY(reads_plan_cell_counts(ctx, &ch->reads, P->o_reads.as<int64_t>() + ch->cell0));
     auto D = [&](void* dst, const DevBuf& b, size_t bytes) -> cudaError_t {
         return dst ? cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
     };
@@ -332,6 +329,9 @@ int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h,
     }
     PMRD_CUDA(ctx, D(h_mean_rate, P->mean_rate, 8));
     unsigned long long tot[2] = {0, 0};
+    // families formed = sum of the per-cell counts (the family table also holds padding sentinels)
+    PMRD_CUDA(ctx, cudaMemsetAsync(P->totals.p, 0, 8, ctx->stream));
+    PMRD_LAUNCH(ctx, sum_i64_kernel, 64, 256, 0, (const int64_t*)P->o_fam.as<int64_t>(), P->n_cells, P->totals.as<unsigned long long>());
     PMRD_CUDA(ctx, cudaMemcpyAsync(tot, P->totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (h_totals) { h_totals[0] = P->n_reads; h_totals[1] = (int64_t)tot[0]; h_totals[2] = (int64_t)tot[1]; }

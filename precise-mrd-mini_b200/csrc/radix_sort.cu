@@ -90,18 +90,18 @@ rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __rest
         } else if (loc < tile_n) {
             d0 = (uint32_t)(keys[wbase + i * 64 + lane * 2] >> shift) & mask;
         }
-        uint32_t m0 = __match_any_sync(0xffffffffu, d0);
-        uint32_t m1 = __match_any_sync(0xffffffffu, d1);
-        if (d0 != 0xffffffffu && (m0 & lanemask_lt()) == 0) s_hist[warp][d0] += __popc(m0);
-        __syncwarp();
-        if (d1 != 0xffffffffu && (m1 & lanemask_lt()) == 0) s_hist[warp][d1] += __popc(m1);
-        __syncwarp();
+        // one shared-memory atomic per key on a warp-private histogram: digits of a scrambled
+        // input are spread over the 256 bins, so same-address conflicts inside a warp are rare
+        if (d0 != 0xffffffffu) atomicAdd(&s_hist[warp][d0], 1u);
+        if (d1 != 0xffffffffu) atomicAdd(&s_hist[warp][d1], 1u);
     }
     __syncthreads();
-    uint32_t c = 0;
+    if (threadIdx.x < RS_MAX_BINS) {
+        uint32_t c = 0;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) c += s_hist[w][threadIdx.x];
-    hist[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] = c;
+        for (int w = 0; w < RS_WARPS; ++w) c += s_hist[w][threadIdx.x];
+        hist[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] = c;
+    }
 }
 
 // ---------------------------------------------------------------- column scan -----------
@@ -164,7 +164,7 @@ struct RsSmem {
 };
 
 template <bool HAS_VALS>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 3)
 rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                     const uint32_t* __restrict__ hist_scanned, int64_t n, int shift, uint32_t mask) {
@@ -207,18 +207,22 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
 
     // per-bin: exclusive prefix over warps, then block scan over bins
     {
-        const uint32_t b = threadIdx.x;  // RS_THREADS == RS_MAX_BINS
+        const uint32_t b = threadIdx.x;  // threads 0..255 own one bin each
         uint32_t run = 0;
+        if (b < RS_MAX_BINS) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            uint32_t c = S.warp_cnt[w][b];
-            S.warp_cnt[w][b] = run;
-            run += c;
+            for (int w = 0; w < RS_WARPS; ++w) {
+                uint32_t c = S.warp_cnt[w][b];
+                S.warp_cnt[w][b] = run;
+                run += c;
+            }
         }
         uint32_t tot;
         uint32_t base = block_exclusive_scan<uint32_t>(run, S.sw, tot);
-        S.bin_base[b] = base;
-        S.glob_delta[b] = hist_scanned[(int64_t)blockIdx.x * RS_MAX_BINS + b] - base;
+        if (b < RS_MAX_BINS) {
+            S.bin_base[b] = base;
+            S.glob_delta[b] = hist_scanned[(int64_t)blockIdx.x * RS_MAX_BINS + b] - base;
+        }
     }
     __syncthreads();
 
@@ -249,6 +253,78 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
     }
 }
 
+// ---------------------------------------------------------------- segmented scan --------
+// Cell-major input (each cell = whole tiles [t0, t1)): every cell is an independent sort, so
+// the scan restarts at each cell -- one block per cell, thread d owns digit d.
+//   base(d, t) = t0 * RS_TILE + sum_{d' < d} sum_{t' in cell} H[t'][d'] + sum_{t0 <= t' < t} H[t'][d]
+__global__ void __launch_bounds__(256)
+rs_cellscan_kernel(uint32_t* __restrict__ hist, const int64_t* __restrict__ cell_tile_start, int n_cells) {
+    __shared__ uint32_t sw[33];
+    const int c = blockIdx.x;
+    if (c >= n_cells) return;
+    const int64_t t0 = cell_tile_start[c], t1 = cell_tile_start[c + 1];
+    uint32_t acc = 0;
+#pragma unroll 4
+    for (int64_t t = t0; t < t1; ++t) acc += hist[t * 256 + threadIdx.x];
+    uint32_t tot;
+    uint32_t run = (uint32_t)(t0 * RS_TILE) + block_exclusive_scan<uint32_t>(acc, sw, tot);
+    int64_t t = t0;
+    for (; t + 4 <= t1; t += 4) {
+        uint32_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = hist[(t + j) * 256 + threadIdx.x];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hist[(t + j) * 256 + threadIdx.x] = run;
+            run += v[j];
+        }
+    }
+    for (; t < t1; ++t) {
+        const uint32_t v = hist[t * 256 + threadIdx.x];
+        hist[t * 256 + threadIdx.x] = run;
+        run += v;
+    }
+}
+
+static int32_t rs_set_attrs(pmrd_ctx* ctx) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        attr_set = true;
+    }
+    return PMRD_OK;
+}
+
+// Per-cell sort of the low `key_bits` key bits; n must be a whole number of tiles and
+// d_cell_tile_start[n_cells] == n / RS_TILE.  The bits above key_bits must be constant
+// inside a cell (they are: the cell index).
+int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
+                                   int64_t n, const int64_t* d_cell_tile_start, int64_t n_cells, int key_bits, int* in_b) {
+    *in_b = 0;
+    if (n <= 0 || n_cells <= 0) return PMRD_OK;
+    PMRD_ARG(ctx, n % RS_TILE == 0 && n < (1ll << 32) - RS_TILE, "segmented sort: n must be a multiple of the tile size and < 2^32");
+    PMRD_ARG(ctx, key_bits >= 1 && key_bits <= 32, "segmented sort: key_bits");
+    PMRD_TRY(rs_set_attrs(ctx));
+    const int n_tiles = (int)(n / RS_TILE);
+    DevBuf hist;
+    PMRD_CUDA(ctx, hist.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
+    uint64_t* kin = keys_a; uint32_t* vin = vals_a; uint64_t* kout = keys_b; uint32_t* vout = vals_b;
+    const int n_passes = (key_bits + 7) / 8;
+    for (int p = 0; p < n_passes; ++p) {
+        const int shift = p * 8;
+        const int w = key_bits - shift < 8 ? key_bits - shift : 8;
+        const uint32_t mask = (1u << w) - 1u;
+        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask);
+        PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256, 0, hist.as<uint32_t>(), d_cell_tile_start, (int)n_cells);
+        PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
+        uint64_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    *in_b = n_passes & 1;
+    return PMRD_OK;
+}
+
 // ---------------------------------------------------------------- driver ----------------
 int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                          int64_t n, uint64_t varying, int* in_b) {
@@ -267,12 +343,7 @@ int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint
     PMRD_CUDA(ctx, hist.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
     PMRD_CUDA(ctx, colsum.alloc(ctx->stream, (size_t)n_chunks * 256 * sizeof(uint32_t)));
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        attr_set = true;
-    }
+    PMRD_TRY(rs_set_attrs(ctx));
 
     uint64_t* kin = keys_a;
     uint32_t* vin = vals_a;

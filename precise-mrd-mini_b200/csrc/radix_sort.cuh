@@ -11,9 +11,9 @@
 #include "common.cuh"
 #include "scan.cuh"
 
-#define RS_THREADS 256
+#define RS_THREADS 512
 #define RS_WARPS (RS_THREADS / 32)
-#define RS_ITEMS 16
+#define RS_ITEMS 8
 #define RS_TILE (RS_THREADS * RS_ITEMS) /* 4096 pairs per tile */
 #define RS_MAX_BINS 256
 
@@ -30,3 +30,5 @@ RadixPlan radix_make_plan(uint64_t varying);
 // to sort on every bit).
 int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                          int64_t n, uint64_t varying, int* in_b);
+int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
+                                   int64_t n, const int64_t* d_cell_tile_start, int64_t n_cells, int key_bits, int* in_b);

@@ -73,61 +73,148 @@ reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64
 
 #define SHUF_WINDOW 4096u
 
-__device__ __forceinline__ int64_t shuffle_slot(int64_t x, int64_t n_reads, int shuffle) {
+// bijection of [0, n): an affine permutation inside each complete 4096-slot window and an
+// affine permutation of the complete windows themselves; the tail window stays in place
+__device__ __forceinline__ uint32_t shuffle_slot(uint32_t x, uint32_t n, int shuffle) {
     if (!shuffle) return x;
-    const int64_t n_full = n_reads / SHUF_WINDOW;  // complete windows; the tail window stays in place
-    int64_t w = x / SHUF_WINDOW;
-    uint32_t l = (uint32_t)(x % SHUF_WINDOW);
+    const uint32_t n_full = n / SHUF_WINDOW;
+    uint32_t w = x / SHUF_WINDOW, l = x % SHUF_WINDOW;
     if (w >= n_full) return x;
-    l = (l * 2654435761u + 0x9e37u * (uint32_t)w) & (SHUF_WINDOW - 1);  // odd multiplier: bijection mod 4096
-    // window permutation: multiply by a prime that does not divide n_full
-    const int64_t A = 1000003;
-    if (n_full % A != 0) w = (w * A + 12345) % n_full;
+    l = (l * 2654435761u + 0x9e37u * w) & (SHUF_WINDOW - 1);  // odd multiplier: bijection mod 4096
+    const uint32_t A = 1000003u;                               // prime: coprime with n_full unless it divides it
+    if (n_full % A != 0) w = (uint32_t)(((uint64_t)w * A + 12345u) % n_full);
     return w * SHUF_WINDOW + l;
 }
+
+// per-cell read counts from the family-major read offsets
+__global__ void __launch_bounds__(256)
+cell_read_count_kernel(const uint64_t* __restrict__ read_offset, const int64_t* __restrict__ fam_offsets, int64_t n_cells,
+                       int64_t n_fam, int64_t n_reads, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cells) return;
+    const int64_t f0 = fam_offsets[i], f1 = fam_offsets[i + 1];
+    const int64_t r0 = f0 < n_fam ? (int64_t)read_offset[f0] : n_reads;
+    const int64_t r1 = f1 < n_fam ? (int64_t)read_offset[f1] : n_reads;
+    out[i] = r1 - r0;
+}
+
+// One warp generates the reads of 32 consecutive families, FLATTENED: lane l first draws
+// family (warp_base + l) and parks its attributes in shared memory; the warp then walks the
+// contiguous range of reads those families own, one read per lane per step, so lanes stay
+// busy whatever the family sizes are (a per-family loop leaves ~45 % of the lanes idle).
+struct FamSlot {
+    uint32_t local_off;   // first read of the family, relative to the warp's first read
+    uint32_t cell_off;    // first read of the family, relative to its cell (or to the chunk)
+    uint32_t cell_n;      // reads in that cell (or chunk): range of the shuffle
+    uint32_t fam;         // family index inside the cell (Philox counter word)
+    uint32_t c2, c3;      // Philox counter words of the cell
+    uint32_t word;        // umi[23:0] | has_variant[24] | ref[27:26] | alt[29:28]
+    uint32_t group;
+    int64_t out_start;    // output position of the cell's (chunk's) first read
+    int32_t ci;
+    int32_t pad;
+};
 
 __global__ void __launch_bounds__(256)
 reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                  int64_t n_fam, pmrd_read_sim_params sp, const uint64_t* __restrict__ read_offset /*[n_fam]*/,
-                 int64_t n_reads, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= n_fam) return;
+                 int64_t n_reads, int segmented, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+    __shared__ FamSlot s_slot[8][32];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t f = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
     const Philox ph(seed);
-    const int ci = find_cell(fam_offsets, n_cells, f);
-    const ReadCell c = cells[ci];
-    const uint32_t fam = (uint32_t)(f - c.fam_offset);
-    const FamDraw d = draw_family(ph, c, fam, sp);
-    const uint32_t c2 = (uint32_t)c.cell_id, c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((c.cell_id >> 32) & 0xffffffu);
-    const int64_t off = (int64_t)read_offset[f];
-    const uint64_t key_home = ((uint64_t)c.group << 32) | d.umi;
-    for (int j = 0; j < d.size; ++j) {
-        const uint4 r = ph((uint32_t)j, fam, c2, c3);
+    const bool valid = f < n_fam;
+    int64_t off = 0;
+    uint32_t size = 0;
+    if (valid) {
+        const int ci = find_cell(fam_offsets, n_cells, f);
+        const ReadCell c = cells[ci];
+        const uint32_t fam = (uint32_t)(f - c.fam_offset);
+        const FamDraw d = draw_family(ph, c, fam, sp);
+        off = (int64_t)read_offset[f];
+        size = (uint32_t)d.size;
+        FamSlot& S = s_slot[warp][lane];
+        S.fam = fam;
+        S.c2 = (uint32_t)c.cell_id;
+        S.c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((c.cell_id >> 32) & 0xffffffu);
+        S.word = d.umi | ((d.has_variant ? 1u : 0u) << 24) | (c.ref_allele << 26) | (c.alt_allele << 28);
+        S.group = c.group;
+        S.ci = ci;
+        if (segmented) {
+            S.cell_off = (uint32_t)(off - c.read_start);
+            S.cell_n = c.n_reads;
+            S.out_start = c.out_start;
+        } else {
+            S.cell_off = (uint32_t)off;
+            S.cell_n = (uint32_t)n_reads;
+            S.out_start = 0;
+        }
+    }
+    const int64_t r0 = __shfl_sync(0xffffffffu, off, 0);
+    const uint32_t loc = valid ? (uint32_t)(off - r0) : 0xffffffffu;   // sorted ascending over the lanes
+    if (valid) s_slot[warp][lane].local_off = loc;
+    // reads owned by the warp: [0, total)
+    const uint32_t end = valid ? loc + size : 0u;
+    uint32_t total = end;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
+    __syncwarp();
+    for (uint32_t k = lane; k < total; k += 32) {
+        // owner = last lane whose first read is <= k (binary search over the lanes' offsets)
+        uint32_t lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t cand = lo + step;
+            const uint32_t oc = s_slot[warp][cand & 31].local_off;
+            const bool ok = cand < 32 && (((int64_t)blockIdx.x * 8 + warp) * 32 + cand) < n_fam && oc <= k;
+            lo = ok ? cand : lo;
+        }
+        const FamSlot S = s_slot[warp][lo];
+        const uint32_t j = k - S.local_off;
+        const uint32_t umi = S.word & 0xffffffu, ref = (S.word >> 26) & 3u, alt = (S.word >> 28) & 3u;
+        const bool has_variant = (S.word >> 24) & 1u;
+        const uint4 r = ph(j, S.fam, S.c2, S.c3);
         // io.py:105-108
         const float ua = u24(r.x);
         uint32_t allele;
-        if (d.has_variant) allele = ua < 0.9f ? c.alt_allele : c.ref_allele;
-        else allele = ua < 0.95f ? c.ref_allele : c.alt_allele;
+        if (has_variant) allele = ua < 0.9f ? alt : ref;
+        else allele = ua < 0.95f ? ref : alt;
         // io.py:65-69: max(10, min(40, int(normal(30, 5))))  -- int() truncates toward zero
         const float z = sample_normal2f(u24(r.y), u24(r.z)).x;
         int q = (int)(30.0f + 5.0f * z);
         q = q < 10 ? 10 : (q > 40 ? 40 : q);
         const uint32_t strand = r.w & 1u;
         const uint32_t rpos = 10u + ((r.w >> 1) & 0xffffu) % 140u;  // io.py:119 randint(10, 150)
-        uint32_t pl = allele | ((uint32_t)q << 2) | (strand << 8) | (rpos << 9) | ((allele == c.alt_allele ? 1u : 0u) << 31);
-        uint64_t key = key_home;
+        uint32_t pl = allele | ((uint32_t)q << 2) | (strand << 8) | (rpos << 9) | ((allele == alt ? 1u : 0u) << 31);
+        uint64_t key = ((uint64_t)S.group << 32) | umi;
         if (sp.hop_rate > 0.0 && n_cells > 1) {
             // index hopping: the read is assigned to another sample's index (contamination.py:230-254)
-            const uint4 h = ph(0x80000000u | (uint32_t)j, fam, c2, c3);
+            const uint4 h = ph(0x80000000u | j, S.fam, S.c2, S.c3);
             if (u24(h.x) < (float)sp.hop_rate) {
-                const uint32_t other = (uint32_t)ci + 1u + h.y % (uint32_t)(n_cells - 1);
+                const uint32_t other = (uint32_t)S.ci + 1u + h.y % (uint32_t)(n_cells - 1);
                 const ReadCell oc = cells[other % (uint32_t)n_cells];
-                key = ((uint64_t)oc.group << 32) | d.umi;
+                key = ((uint64_t)oc.group << 32) | umi;
                 pl = (pl & 0x7fffffffu) | ((allele == oc.alt_allele ? 1u : 0u) << 31);
             }
         }
-        const int64_t dst = shuffle_slot(off + j, n_reads, sp.shuffle);
+        const int64_t dst = S.out_start + (int64_t)shuffle_slot(S.cell_off + j, S.cell_n, sp.shuffle);
         keys[dst] = key;
         payload[dst] = pl;
+    }
+}
+
+// segmented layout: fill each cell's padding (up to the next 4096 boundary) with sentinel
+// reads that sort to the end of the cell and are ignored downstream
+__global__ void __launch_bounds__(256)
+reads_pad_kernel(const ReadCell* __restrict__ cells, int n_cells, const int64_t* __restrict__ cell_tile_start,
+                 uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+    const int ci = blockIdx.x;
+    if (ci >= n_cells) return;
+    const ReadCell c = cells[ci];
+    const int64_t lo = c.out_start + c.n_reads, hi = cell_tile_start[ci + 1] * READS_SEG_TILE;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        keys[i] = ((uint64_t)c.group << 32) | READS_SENTINEL_UMI;
+        payload[i] = 0u;
     }
 }
 
@@ -136,12 +223,13 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
 // the device cell table, the family CSR and the total read count (a pure function of the
 // Philox key, so it can be known before the timed step allocates anything).
 int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
-                         int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, ReadPlan* plan,
+                         int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, int segmented, ReadPlan* plan,
                          int64_t* h_read_offsets /* optional [C+1] */) {
     PMRD_ARG(ctx, sp != nullptr && sp->mean_family_size > 0.0 && sp->max_family_size >= 1, "read sim params");
     PMRD_ARG(ctx, n_cells >= 0 && n_cells < (1ll << 31), "n_cells");
     plan->sp = *sp;
     plan->n_cells = n_cells;
+    plan->segmented = (segmented && sp->hop_rate == 0.0) ? 1 : 0;   // hopped reads leave their cell's region
     ReadCell* hc = (ReadCell*)malloc(sizeof(ReadCell) * (size_t)(n_cells + 1));
     int64_t* ho = (int64_t*)malloc(8 * (size_t)(n_cells + 1));
     if (!hc || !ho) { free(hc); free(ho); PMRD_ARG(ctx, false, "out of host memory"); }
@@ -153,7 +241,9 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         hc[i].group = group_base + (uint32_t)i;
         hc[i].ref_allele = (uint32_t)(hc[i].cell_id & 3u);
         hc[i].alt_allele = (hc[i].ref_allele + 1u + (uint32_t)((hc[i].cell_id >> 2) % 3u)) & 3u;
-        hc[i].pad = 0;
+        hc[i].read_start = 0;
+        hc[i].out_start = 0;
+        hc[i].n_reads = 0;
         ho[i] = nf;
         nf += h_n_families[i] > 0 ? h_n_families[i] : 0;
     }
@@ -167,35 +257,55 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
     if (e == cudaSuccess) e = plan->total.alloc(ctx->stream, 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->fam_offsets.p, ho, 8 * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = plan->cell_tile_start.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    free(hc);
     if (e != cudaSuccess) {
-        free(ho);
+        free(hc); free(ho);
         snprintf(ctx->err, sizeof(ctx->err), "read plan: %s", cudaGetErrorString(e));
         return PMRD_ERR_CUDA;
     }
     int32_t st = reads_plan_sizes(ctx, plan);
-    if (st == PMRD_OK && nf > 0) {
+    int64_t* h_cnt = (int64_t*)malloc(8 * (size_t)(n_cells + 1));
+    int64_t* h_tile = (int64_t*)malloc(8 * (size_t)(n_cells + 1));
+    if (!h_cnt || !h_tile) { free(hc); free(ho); free(h_cnt); free(h_tile); PMRD_ARG(ctx, false, "out of host memory"); }
+    if (st == PMRD_OK) {
+        // exact read count per cell (a pure function of the Philox key), gathered on the device
         uint64_t tot = 0;
-        e = cudaMemcpyAsync(&tot, plan->total.p, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        DevBuf cnt;
+        e = cnt.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
+        if (e == cudaSuccess && nf > 0) e = cudaMemcpyAsync(&tot, plan->total.p, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        plan->n_reads = (int64_t)tot;
+        if (e == cudaSuccess && n_cells > 0) {
+            cell_read_count_kernel<<<pmrd_blocks(n_cells, 256), 256, 0, ctx->stream>>>(
+                plan->read_offset.as<uint64_t>(), plan->fam_offsets.as<int64_t>(), n_cells, nf, plan->n_reads, cnt.as<int64_t>());
+            ctx->launches++;
+            e = cudaMemcpyAsync(h_cnt, cnt.p, 8 * (size_t)n_cells, cudaMemcpyDeviceToHost, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
+        if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "read plan: %s", cudaGetErrorString(e)); st = PMRD_ERR_CUDA; }
+    }
+    if (st == PMRD_OK) {
+        int64_t rs = 0, tile = 0;
+        for (int64_t i = 0; i < n_cells; ++i) {
+            if (h_cnt[i] >= (1ll << 32)) { st = PMRD_ERR_ARG; snprintf(ctx->err, sizeof(ctx->err), "a cell holds >= 2^32 reads"); break; }
+            hc[i].read_start = rs;
+            hc[i].n_reads = (uint32_t)h_cnt[i];
+            h_tile[i] = tile;
+            hc[i].out_start = plan->segmented ? tile * READS_SEG_TILE : rs;
+            if (h_read_offsets) h_read_offsets[i] = rs;
+            rs += h_cnt[i];
+            tile += (h_cnt[i] + READS_SEG_TILE - 1) / READS_SEG_TILE;
+        }
+        h_tile[n_cells] = tile;
+        if (h_read_offsets) h_read_offsets[n_cells] = rs;
+        plan->n_out = plan->segmented ? tile * READS_SEG_TILE : plan->n_reads;
+        e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cell_tile_start.p, h_tile, 8 * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "read plan: %s", cudaGetErrorString(e)); st = PMRD_ERR_CUDA; }
-        plan->n_reads = (int64_t)tot;
     }
-    if (st == PMRD_OK && h_read_offsets) {
-        // per-cell CSR of reads (family-major layout): read_offset at each cell's first family
-        uint64_t* tmp = (uint64_t*)malloc(8 * (size_t)(nf + 1));
-        if (!tmp) { free(ho); PMRD_ARG(ctx, false, "out of host memory"); }
-        e = cudaSuccess;
-        if (nf > 0) e = cudaMemcpy(tmp, plan->read_offset.p, 8 * (size_t)nf, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "%s", cudaGetErrorString(e)); st = PMRD_ERR_CUDA; }
-        else {
-            for (int64_t i = 0; i < n_cells; ++i) h_read_offsets[i] = ho[i] < nf ? (int64_t)tmp[ho[i]] : plan->n_reads;
-            h_read_offsets[n_cells] = plan->n_reads;
-        }
-        free(tmp);
-    }
-    free(ho);
+    free(hc); free(ho); free(h_cnt); free(h_tile);
     return st;
 }
 
@@ -208,11 +318,22 @@ int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
                                               plan->total.as<uint64_t>());
 }
 
-// generate the reads (device only, no sync); capacity must be >= plan->n_reads
+// generate the reads (device only, no sync); capacity must be >= plan->n_out
 int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload) {
     if (plan->n_fam <= 0) return PMRD_OK;
     PMRD_LAUNCH(ctx, reads_gen_kernel, pmrd_blocks(plan->n_fam, 256), 256, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
-                (const uint64_t*)plan->read_offset.as<uint64_t>(), plan->n_reads, d_keys, d_payload);
+                (const uint64_t*)plan->read_offset.as<uint64_t>(), plan->n_reads, plan->segmented, d_keys, d_payload);
+    if (plan->segmented && plan->n_out > plan->n_reads)
+        PMRD_LAUNCH(ctx, reads_pad_kernel, (int)plan->n_cells, 256, 0, plan->cells.as<ReadCell>(), (int)plan->n_cells,
+                    (const int64_t*)plan->cell_tile_start.as<int64_t>(), d_keys, d_payload);
+    return PMRD_OK;
+}
+
+// per-cell read counts into d_out[n_cells] (not part of the timed step)
+int32_t reads_plan_cell_counts(pmrd_ctx* ctx, ReadPlan* plan, int64_t* d_out) {
+    if (plan->n_cells <= 0) return PMRD_OK;
+    PMRD_LAUNCH(ctx, cell_read_count_kernel, pmrd_blocks(plan->n_cells, 256), 256, 0, (const uint64_t*)plan->read_offset.as<uint64_t>(),
+                (const int64_t*)plan->fam_offsets.as<int64_t>(), plan->n_cells, plan->n_fam, plan->n_reads, d_out);
     return PMRD_OK;
 }

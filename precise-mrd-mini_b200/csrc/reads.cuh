@@ -6,17 +6,24 @@ struct ReadCell {
     uint64_t cell_id;
     double af;
     int64_t fam_offset;  // first global family index of this cell in the batch
+    int64_t read_start;  // first read of the cell in family-major (unpadded) numbering
+    int64_t out_start;   // where the cell's reads start in the output arrays (tile-aligned when segmented)
+    uint32_t n_reads;    // reads of the cell
     uint32_t group;
     uint32_t ref_allele, alt_allele;
-    uint32_t pad;
 };
 
+#define READS_SEG_TILE 4096 /* == RS_TILE: cells are padded to whole sort tiles when segmented */
+#define READS_SENTINEL_UMI 0xffffffffu
+
 struct ReadPlan {
-    DevBuf cells, fam_offsets, fam_size, read_offset, total;
+    DevBuf cells, fam_offsets, fam_size, read_offset, total, cell_tile_start;
     pmrd_read_sim_params sp;
     int64_t n_cells = 0;
     int64_t n_fam = 0;
-    int64_t n_reads = 0;
+    int64_t n_reads = 0;      // reads generated
+    int64_t n_out = 0;        // slots in the output arrays (== n_reads unless segmented: + padding)
+    int segmented = 0;        // cell-major, tile-padded layout (enables the per-cell 3-pass sort)
 };
 
 // allele convention of the generator: ref = cell_id & 3, alt = one of the other three
@@ -26,7 +33,8 @@ static inline uint32_t pmrd_cell_alt_allele(uint64_t cell_id) {
 }
 
 int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
-                         int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, ReadPlan* plan,
+                         int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, int segmented, ReadPlan* plan,
                          int64_t* h_read_offsets);
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan);
 int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload);
+int32_t reads_plan_cell_counts(pmrd_ctx* ctx, ReadPlan* plan, int64_t* d_out);
