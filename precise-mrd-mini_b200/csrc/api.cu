@@ -128,6 +128,7 @@ int32_t pmrd_create(int32_t device, uint64_t seed, pmrd_ctx** out) {
     double w[64];
     for (int q = 0; q < 64; ++q) w[q] = pow(10.0, (double)q / 10.0);
     int32_t s = collapse_upload_weights(ctx, w);
+    if (s == PMRD_OK) s = reads_upload_tables(ctx);
     if (s == PMRD_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = PMRD_ERR_CUDA;
     if (s != PMRD_OK) {
         snprintf(g_pmrd_create_err, sizeof(g_pmrd_create_err), "pmrd_create: %s", ctx->err);

@@ -239,7 +239,7 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
     }
     if ((int64_t)size >= (int64_t)P.min_family_size) flags |= PMRD_FAM_KEPT;
     if ((int64_t)size > (int64_t)P.max_family_size) flags |= PMRD_FAM_OVERSIZE;
-    if (sentinel_umi != 0u && (uint32_t)key == sentinel_umi) flags = 0;  // padding of a tile-aligned cell
+    if (sentinel_umi != 0u && (((uint32_t)key) >> 24) == 0xffu) flags = 0;  // padding of a tile-aligned cell
     out.key[f] = key;
     out.size[f] = size;
     out.n_alt[f] = n_alt;
@@ -247,6 +247,202 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
     out.qsum[f] = qsum_best;
     out.n_best[f] = n_best;
     out.flags[f] = flags;
+}
+
+// ---------------------------------------------------------------- fused consensus+count -
+// Plan pipeline, cell-major tile-padded input: one block per 4096-read tile (a tile lies inside
+// ONE cell).  Finds the family heads of the tile, votes each family that STARTS in the tile (one
+// thread per family, reads in input order, same IEEE additions as family_kernel) and reduces
+// straight to the three per-cell counts call_mrd needs -- no family table, no segment arrays,
+// no group table: the 12 B/read are read once.
+struct Vote {
+    double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, total = 0.0;
+    uint32_t order = 0, seen = 0, n_seen = 0;
+    __device__ __forceinline__ void add(uint32_t pl, int qthr) {
+        const uint32_t a = pl & 3u, q = (pl >> 2) & 63u;
+        if ((int)q >= qthr) {
+            const double w = c_wtab[q];
+            w0 = __dadd_rn(w0, a == 0 ? w : 0.0);
+            w1 = __dadd_rn(w1, a == 1 ? w : 0.0);
+            w2 = __dadd_rn(w2, a == 2 ? w : 0.0);
+            w3 = __dadd_rn(w3, a == 3 ? w : 0.0);
+            total = __dadd_rn(total, w);
+            if (!((seen >> a) & 1u)) {
+                seen |= 1u << a;
+                order |= n_seen << (2 * a);
+                ++n_seen;
+            }
+        }
+    }
+    // consensus allele, or -1 (umi.py:166-174)
+    __device__ __forceinline__ int result(double cthr) const {
+        if (n_seen == 0 || total == 0.0) return -1;
+        int best = -1;
+        double bw = -1.0;
+        uint32_t brank = 4;
+        const double ws[4] = {w0, w1, w2, w3};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            if (!((seen >> a) & 1u)) continue;
+            const uint32_t rk = (order >> (2 * a)) & 3u;
+            if (ws[a] > bw || (ws[a] == bw && rk < brank)) { bw = ws[a]; best = a; brank = rk; }
+        }
+        return (__ddiv_rn(bw, total) < cthr) ? -1 : best;
+    }
+};
+
+#define CC_THREADS 256
+#define CC_TILE 4096
+#define CC_ITEMS (CC_TILE / CC_THREADS)
+
+// Input: packed 8-byte records  rec = payload:32 | umi:32  in cell-major, tile-padded order,
+// each cell sorted on the low `run_mask` bits of the UMI.  `run_mask` selects the UMI bits the
+// sort ordered; a RUN is a maximal sequence of reads that agree on those bits and holds the
+// reads of the (few) families whose UMIs differ only in the unsorted high bits, interleaved
+// but each in input order (the sort is stable).  One thread owns a run and peels its families.
+template <bool FULL>
+__global__ void __launch_bounds__(CC_THREADS)
+cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restrict__ cell_tile_start, int n_cells,
+                      pmrd_umi_params P, uint32_t run_mask, int64_t cell0, const uint8_t* __restrict__ alt_allele,
+                      unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot,
+                      unsigned long long* __restrict__ o_var) {
+    __shared__ uint64_t s_rec[CC_TILE];
+    __shared__ uint16_t s_head[CC_TILE];
+    __shared__ uint32_t sw[33];
+    __shared__ unsigned long long s_acc[3];
+    __shared__ int s_cell;
+    const int64_t tile = blockIdx.x;
+    const int64_t base = tile * CC_TILE;
+    if (threadIdx.x < 3) s_acc[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) {   // which cell owns this tile
+        int lo = 0, hi = n_cells;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (cell_tile_start[mid] <= tile) lo = mid; else hi = mid;
+        }
+        s_cell = lo;
+    }
+#pragma unroll
+    for (int j = 0; j < CC_ITEMS; ++j) {
+        const int i = j * CC_THREADS + threadIdx.x;
+        s_rec[i] = rec[base + i];
+    }
+    __syncthreads();
+    const int cell = s_cell;
+    const int64_t cell_lo = cell_tile_start[cell] * CC_TILE, cell_hi = cell_tile_start[cell + 1] * CC_TILE;
+    // heads, blocked so that the compacted list follows memory order
+    uint32_t flags = 0, cnt = 0;
+    const int i0 = threadIdx.x * CC_ITEMS;
+#pragma unroll
+    for (int j = 0; j < CC_ITEMS; ++j) {
+        const int i = i0 + j;
+        bool head;
+        if (i > 0) head = ((((uint32_t)s_rec[i]) ^ ((uint32_t)s_rec[i - 1])) & run_mask) != 0u;
+        else head = base == cell_lo || ((((uint32_t)rec[base - 1]) ^ ((uint32_t)s_rec[0])) & run_mask) != 0u;
+        if (head) { flags |= 1u << j; ++cnt; }
+    }
+    uint32_t n_heads;
+    uint32_t r = block_exclusive_scan<uint32_t>(cnt, sw, n_heads);
+#pragma unroll
+    for (int j = 0; j < CC_ITEMS; ++j)
+        if (flags & (1u << j)) s_head[r++] = (uint16_t)(i0 + j);
+    __syncthreads();
+    const uint32_t alt = alt_allele[cell0 + cell];
+    uint32_t n_fam = 0, n_tot = 0, n_var = 0;
+    for (uint32_t h = threadIdx.x; h < n_heads; h += CC_THREADS) {
+        const int lo = s_head[h];
+        const int hi = (h + 1 < n_heads) ? (int)s_head[h + 1] : CC_TILE;
+        const int n_in = hi - lo;
+        // the tile's last run may continue into the next tile(s) of the same cell
+        int64_t g_hi = base + CC_TILE;
+        if (h + 1 == n_heads) {
+            const uint32_t rk = ((uint32_t)s_rec[lo]) & run_mask;
+            while (g_hi < cell_hi && ((((uint32_t)rec[g_hi]) & run_mask) == rk)) ++g_hi;
+        }
+        const int len = n_in + (int)(g_hi - (base + CC_TILE));
+        auto rec_at = [&](int i) -> uint64_t { return i < n_in ? s_rec[lo + i] : rec[base + CC_TILE + (i - n_in)]; };
+        if (FULL) {
+            // the sort ordered every UMI bit: a run IS a family
+            const uint32_t umi = (uint32_t)s_rec[lo];
+            if ((umi >> 24) == 0xffu) continue;                  // padding of the tile-aligned cell
+            Vote v;
+            for (int c = 0; c < len; ++c) v.add((uint32_t)(rec_at(c) >> 32), P.quality_threshold);
+            ++n_fam;
+            if (len >= P.min_family_size) {
+                const int best = v.result(P.consensus_threshold);
+                if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt; }
+            }
+            continue;
+        }
+        // peel families: read a opens a family iff no earlier read of the run carries its UMI.
+        // The UMIs already peeled are remembered in four registers (a run rarely holds more
+        // families than that); beyond four the check falls back to scanning the run.
+        uint32_t seen0 = 0, seen1 = 0, seen2 = 0, seen3 = 0;
+        int n_seen_umi = 0;
+        for (int a = 0; a < len; ++a) {
+            const uint32_t umi = (uint32_t)rec_at(a);
+            if ((umi >> 24) == 0xffu) continue;                  // padding of the tile-aligned cell
+            bool first;
+            if (n_seen_umi <= 4) {
+                first = !((n_seen_umi > 0 && umi == seen0) || (n_seen_umi > 1 && umi == seen1) ||
+                          (n_seen_umi > 2 && umi == seen2) || (n_seen_umi > 3 && umi == seen3));
+            } else {
+                first = true;
+                for (int b = 0; b < a && first; ++b) first = (uint32_t)rec_at(b) != umi;
+            }
+            if (!first) continue;
+            if (n_seen_umi == 0) seen0 = umi;
+            else if (n_seen_umi == 1) seen1 = umi;
+            else if (n_seen_umi == 2) seen2 = umi;
+            else if (n_seen_umi == 3) seen3 = umi;
+            ++n_seen_umi;
+            Vote v;
+            uint32_t size = 0;
+            for (int c = a; c < len; ++c) {
+                const uint64_t rc = rec_at(c);
+                if ((uint32_t)rc == umi) { v.add((uint32_t)(rc >> 32), P.quality_threshold); ++size; }
+            }
+            ++n_fam;
+            if ((int)size >= P.min_family_size) {
+                const int best = v.result(P.consensus_threshold);
+                if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt; }
+            }
+        }
+    }
+    n_fam = warp_sum(n_fam); n_tot = warp_sum(n_tot); n_var = warp_sum(n_var);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_acc[0], (unsigned long long)n_fam);
+        atomicAdd(&s_acc[1], (unsigned long long)n_tot);
+        atomicAdd(&s_acc[2], (unsigned long long)n_var);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_acc[0]) atomicAdd(&o_fam[cell0 + cell], s_acc[0]);
+        if (s_acc[1]) atomicAdd(&o_tot[cell0 + cell], s_acc[1]);
+        if (s_acc[2]) atomicAdd(&o_var[cell0 + cell], s_acc[2]);
+    }
+}
+
+// segmented sort of packed records + fused consensus/count; outputs accumulate into the per-cell arrays
+int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d_rec_tmp, int64_t n_out,
+                                     const pmrd_umi_params* params, const int64_t* d_cell_tile_start, int64_t n_cells,
+                                     int sort_bits, int umi_bits, int64_t cell0, const uint8_t* d_alt_allele, int64_t* d_o_fam,
+                                     int64_t* d_o_tot, int64_t* d_o_var) {
+    if (n_out <= 0) return PMRD_OK;
+    PMRD_ARG(ctx, n_out % CC_TILE == 0, "segmented collapse: input must be whole tiles");
+    int in_b = 0;
+    PMRD_TRY(radix_sort_pairs_segmented(ctx, d_rec, nullptr, d_rec_tmp, nullptr, n_out, d_cell_tile_start, n_cells, sort_bits, &in_b));
+    const uint64_t* sr = in_b ? d_rec_tmp : d_rec;
+    const uint32_t run_mask = sort_bits >= 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
+    const int grid = (int)(n_out / CC_TILE);
+    if (sort_bits >= umi_bits) {
+        PMRD_LAUNCH(ctx, cell_consensus_kernel<true>, grid, CC_THREADS, 0, sr, d_cell_tile_start, (int)n_cells, *params, 0xffffffffu,
+                    cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot, (unsigned long long*)d_o_var);
+    } else {
+        PMRD_LAUNCH(ctx, cell_consensus_kernel<false>, grid, CC_THREADS, 0, sr, d_cell_tile_start, (int)n_cells, *params, run_mask,
+                    cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot, (unsigned long long*)d_o_var);
+    }
+    return PMRD_OK;
 }
 
 // ---------------------------------------------------------------- K7 group table --------

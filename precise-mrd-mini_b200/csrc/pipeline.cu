@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "rng.cuh"
 #include <new>
+#include <stdlib.h>
 
 #include "reads.cuh"
 
@@ -17,6 +18,11 @@ int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pa
                                  const pmrd_family_table* d_fam, int64_t capacity_f, const pmrd_group_table* d_grp,
                                  int64_t capacity_g, uint32_t* d_fam_start, uint32_t* d_grp_start, uint32_t* d_counts,
                                  const int64_t* d_cell_tile_start, int64_t n_seg_cells, int seg_key_bits);
+
+int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d_rec_tmp, int64_t n_out,
+                                     const pmrd_umi_params* params, const int64_t* d_cell_tile_start, int64_t n_cells,
+                                     int sort_bits, int umi_bits, int64_t cell0, const uint8_t* d_alt_allele, int64_t* d_o_fam,
+                                     int64_t* d_o_tot, int64_t* d_o_var);
 
 // scatter the group table into per-cell arrays (cells without reads keep zeros)
 __global__ void __launch_bounds__(256)
@@ -39,7 +45,7 @@ cell_family_count_kernel(const uint64_t* __restrict__ fam_key, const uint32_t* _
                          int64_t n_cells, unsigned long long* __restrict__ n_families) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // (families whose UMI is the padding sentinel of a tile-aligned cell are not families)
-    const bool valid = f < (int64_t)*d_nfam && (uint32_t)fam_key[f] != READS_SENTINEL_UMI;
+    const bool valid = f < (int64_t)*d_nfam && !READS_IS_PAD_UMI((uint32_t)fam_key[f]);
     const uint32_t g = valid ? (uint32_t)(fam_key[f] >> 32) : 0xffffffffu;
     const uint32_t m = __match_any_sync(0xffffffffu, g);
     if (valid && (m & lanemask_lt()) == 0) {
@@ -107,6 +113,7 @@ struct pmrd_plan {
     int32_t test_type, alternative;
     int64_t n_cells = 0, n_reads = 0, n_fam = 0;
     int64_t max_reads = 0, max_fcap = 0, max_cells = 0;
+    int sort_bits = 24;   // UMI bits ordered by the radix sort; the consensus kernel resolves the rest (16: 2 passes, 24: 3)
     uint64_t stream_id = 0;
     DevBuf keys, keys_tmp, pl, pl_tmp;
     DevBuf fk, fs, fa, fc, fq, fn, ff, fam_start;
@@ -146,6 +153,10 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     P->up = *up; P->neg_af_max = neg_af_max; P->alpha = alpha; P->test_type = test_type; P->alternative = alternative;
     P->n_cells = n_cells;
     P->stream_id = (uint64_t)h_cell_id[0];
+    if (const char* sb = getenv("PMRD_SORT_BITS")) {   // tuning knob: 16 (2 radix passes) or 24 (3 passes)
+        const int v = atoi(sb);
+        if (v == 8 || v == 16 || v == 24) P->sort_bits = v;
+    }
     // cut into chunks by expected reads (mean size with 25% head room; exact counts follow)
     const double budget = (double)(1ll << (sp->chunk_log2 ? sp->chunk_log2 : 28));
     const double per_family = (sp->mean_family_size + 1.0) * 1.25;
@@ -190,10 +201,13 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     const size_t f = (size_t)(P->max_fcap > 0 ? P->max_fcap : 1), g = (size_t)P->max_cells, c = (size_t)n_cells;
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.alloc(ctx->stream, bytes); };
-    A(P->keys, n * 8); A(P->keys_tmp, n * 8); A(P->pl, n * 4); A(P->pl_tmp, n * 4);
-    A(P->fk, f * 8); A(P->fs, f * 4); A(P->fa, f * 4); A(P->fc, f * 4); A(P->fq, f * 4); A(P->fn, f * 4); A(P->ff, f * 4);
-    A(P->fam_start, (f + 1) * 4);
-    A(P->gg, g * 4); A(P->gf, g * 4); A(P->gc, g * 16); A(P->ga, g * 8); A(P->gt, g * 8); A(P->grp_start, (g + 1) * 4);
+    A(P->keys, n * 8); A(P->keys_tmp, n * 8);
+    if (sp->hop_rate > 0.0) { A(P->pl, n * 4); A(P->pl_tmp, n * 4); }
+    if (sp->hop_rate > 0.0) {   // only the general (non cell-major) path materialises the family / group tables
+        A(P->fk, f * 8); A(P->fs, f * 4); A(P->fa, f * 4); A(P->fc, f * 4); A(P->fq, f * 4); A(P->fn, f * 4); A(P->ff, f * 4);
+        A(P->fam_start, (f + 1) * 4);
+        A(P->gg, g * 4); A(P->gf, g * 4); A(P->gc, g * 16); A(P->ga, g * 8); A(P->gt, g * 8); A(P->grp_start, (g + 1) * 4);
+    }
     A(P->counts, 8); A(P->totals, 16); A(P->alt, c); A(P->neg, c); A(P->negc, 16); A(P->mean_rate, 8);
     A(P->o_reads, c * 8); A(P->o_fam, c * 8); A(P->o_tot, c * 8); A(P->o_var, c * 8); A(P->o_p, c * 8); A(P->o_q, c * 8); A(P->o_sig, c);
     uint8_t* h_alt = (uint8_t*)malloc(c * 2);
@@ -233,10 +247,19 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
 static int32_t chunk_simulate(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
     // family sizes -> read offsets -> reads (scrambled)
     PMRD_TRY(reads_plan_sizes(ctx, &ch->reads));
-    return reads_plan_generate(ctx, &ch->reads, P->keys.as<uint64_t>(), P->pl.as<uint32_t>());
+    // cell-major chunks are generated as packed 8-byte records (payload:32 | umi:32)
+    return reads_plan_generate(ctx, &ch->reads, P->keys.as<uint64_t>(), ch->reads.segmented ? nullptr : P->pl.as<uint32_t>());
 }
 
 static int32_t chunk_collapse(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
+    if (ch->reads.segmented) {
+        // cell-major input: per-cell 3-pass sort, then ONE kernel from sorted reads to per-cell counts
+        // (packed 8-byte records: P->keys / P->keys_tmp are the ping-pong pair, no payload arrays)
+        return k5_collapse_counts_segmented(ctx, P->keys.as<uint64_t>(), P->keys_tmp.as<uint64_t>(), ch->reads.n_out, &P->up,
+                                            (const int64_t*)ch->reads.cell_tile_start.as<int64_t>(), ch->n_cells, P->sort_bits, 24,
+                                            ch->cell0, (const uint8_t*)P->alt.as<uint8_t>(), P->o_fam.as<int64_t>(),
+                                            P->o_tot.as<int64_t>(), P->o_var.as<int64_t>());
+    }
     pmrd_family_table fam{P->fk.as<uint64_t>(), P->fs.as<uint32_t>(), P->fa.as<uint32_t>(), P->fc.as<uint32_t>(),
                           P->fq.as<uint32_t>(), P->fn.as<uint32_t>(), P->ff.as<uint32_t>()};
     pmrd_group_table grp{P->gg.as<uint32_t>(), P->gf.as<uint32_t>(), P->gc.as<uint32_t>(), P->ga.as<uint64_t>(), P->gt.as<uint64_t>()};
@@ -245,14 +268,13 @@ static int32_t chunk_collapse(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
         PMRD_TRY(k5_collapse_exact_nosync(ctx, P->keys.as<uint64_t>(), P->pl.as<uint32_t>(), P->keys_tmp.as<uint64_t>(),
                                           P->pl_tmp.as<uint32_t>(), ch->reads.n_out, ch->varying, &P->up, &fam, ch->fcap, &grp,
                                           ch->n_cells, P->fam_start.as<uint32_t>(), P->grp_start.as<uint32_t>(),
-                                          P->counts.as<uint32_t>(),
-                                          ch->reads.segmented ? (const int64_t*)ch->reads.cell_tile_start.as<int64_t>() : nullptr,
-                                          ch->n_cells, 24));
+                                          P->counts.as<uint32_t>(), nullptr, 0, 0));
     return PMRD_OK;
 }
 
-// per-cell counts of the chunk into the grid-wide arrays (K7)
+// per-cell counts of the chunk into the grid-wide arrays (K7); the segmented path already did it
 static int32_t chunk_counts(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
+    if (ch->reads.segmented) return PMRD_OK;
     PMRD_LAUNCH(ctx, cell_counts_kernel, pmrd_blocks(ch->n_cells, 256), 256, 0, (const uint32_t*)P->gg.as<uint32_t>(),
                 (const uint32_t*)P->gc.as<uint32_t>(), (const uint32_t*)(P->counts.as<uint32_t>() + 1), ch->cell0, ch->n_cells,
                 (const uint8_t*)P->alt.as<uint8_t>(), P->o_tot.as<int64_t>(), P->o_var.as<int64_t>());
@@ -334,7 +356,14 @@ int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h,
     PMRD_LAUNCH(ctx, sum_i64_kernel, 64, 256, 0, (const int64_t*)P->o_fam.as<int64_t>(), P->n_cells, P->totals.as<unsigned long long>());
     PMRD_CUDA(ctx, cudaMemcpyAsync(tot, P->totals.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (h_totals) { h_totals[0] = P->n_reads; h_totals[1] = (int64_t)tot[0]; h_totals[2] = (int64_t)tot[1]; }
+    if (h_totals) {
+        h_totals[0] = P->n_reads;
+        h_totals[1] = (int64_t)tot[0];
+        int64_t groups = (int64_t)tot[1];
+        for (PlanChunk* ch : P->chunks)
+            if (ch->reads.segmented) groups += ch->reads.n_groups_with_reads;
+        h_totals[2] = groups;
+    }
     return PMRD_OK;
 }
 

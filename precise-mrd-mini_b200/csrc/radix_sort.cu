@@ -317,7 +317,11 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         const uint32_t mask = (1u << w) - 1u;
         PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask);
         PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256, 0, hist.as<uint32_t>(), d_cell_tile_start, (int)n_cells);
-        PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
+        if (vals_a) {
+            PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
+        } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits
+            PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
+        }
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
     }

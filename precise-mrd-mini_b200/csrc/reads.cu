@@ -62,16 +62,33 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
 
 __global__ void __launch_bounds__(256)
 reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
-                  int64_t n_fam, pmrd_read_sim_params sp, uint32_t* __restrict__ fam_size) {
+                  int64_t n_fam, pmrd_read_sim_params sp, uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_fam) return;
     const Philox ph(seed);
     const int ci = find_cell(fam_offsets, n_cells, f);
     const ReadCell c = cells[ci];
-    fam_size[f] = (uint32_t)draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp).size;
+    const FamDraw d = draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp);
+    fam_size[f] = (uint32_t)d.size;
+    fam_word[f] = d.umi | ((d.has_variant ? 1u : 0u) << 24);   // the generator re-reads this instead of re-drawing
 }
 
 #define SHUF_WINDOW 4096u
+
+// cdf of q = max(10, min(40, int(N(30,5)))) in units of 2^-24: c_qual_thr[k] = P(q <= 10 + k), k = 0..29
+__constant__ uint32_t c_qual_thr[32];
+
+int32_t reads_upload_tables(pmrd_ctx* ctx) {
+    uint32_t h[32];
+    for (int k = 0; k < 32; ++k) {
+        // int() truncates toward zero and 30 + 5 z > 0 here, so q <= 10 + k  <=>  30 + 5 z < 11 + k
+        const double zc = ((double)(11 + k) - 30.0) / 5.0;
+        const double cdf = 0.5 * erfc(-zc / sqrt(2.0));
+        h[k] = k < 30 ? (uint32_t)llround(cdf * 16777216.0) : 0xffffffffu;
+    }
+    PMRD_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qual_thr, h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
+    return PMRD_OK;
+}
 
 // bijection of [0, n): an affine permutation inside each complete 4096-slot window and an
 // affine permutation of the complete windows themselves; the tail window stays in place
@@ -118,8 +135,11 @@ struct FamSlot {
 __global__ void __launch_bounds__(256)
 reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                  int64_t n_fam, pmrd_read_sim_params sp, const uint64_t* __restrict__ read_offset /*[n_fam]*/,
+                 const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_word,
                  int64_t n_reads, int segmented, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
     __shared__ FamSlot s_slot[8][32];
+    __shared__ uint32_t s_qthr[32];
+    if (threadIdx.x < 32) s_qthr[threadIdx.x] = c_qual_thr[threadIdx.x];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t f = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
     const Philox ph(seed);
@@ -130,14 +150,14 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         const int ci = find_cell(fam_offsets, n_cells, f);
         const ReadCell c = cells[ci];
         const uint32_t fam = (uint32_t)(f - c.fam_offset);
-        const FamDraw d = draw_family(ph, c, fam, sp);
         off = (int64_t)read_offset[f];
-        size = (uint32_t)d.size;
+        size = fam_size[f];
+        const uint32_t fw = fam_word[f];
         FamSlot& S = s_slot[warp][lane];
         S.fam = fam;
         S.c2 = (uint32_t)c.cell_id;
         S.c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((c.cell_id >> 32) & 0xffffffu);
-        S.word = d.umi | ((d.has_variant ? 1u : 0u) << 24) | (c.ref_allele << 26) | (c.alt_allele << 28);
+        S.word = fw | (c.ref_allele << 26) | (c.alt_allele << 28);
         S.group = c.group;
         S.ci = ci;
         if (segmented) {
@@ -158,7 +178,7 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
     uint32_t total = end;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
-    __syncwarp();
+    __syncthreads();
     for (uint32_t k = lane; k < total; k += 32) {
         // owner = last lane whose first read is <= k (binary search over the lanes' offsets)
         uint32_t lo = 0;
@@ -173,23 +193,31 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         const uint32_t j = k - S.local_off;
         const uint32_t umi = S.word & 0xffffffu, ref = (S.word >> 26) & 3u, alt = (S.word >> 28) & 3u;
         const bool has_variant = (S.word >> 24) & 1u;
-        const uint4 r = ph(j, S.fam, S.c2, S.c3);
-        // io.py:105-108
-        const float ua = u24(r.x);
+        // one Philox block feeds TWO reads: 64 random bits per read
+        const uint4 r4 = ph(j >> 1, S.fam, S.c2, S.c3);
+        const uint32_t ra = (j & 1u) ? r4.z : r4.x, rb = (j & 1u) ? r4.w : r4.y;
+        // io.py:105-108 (16-bit uniform: thresholds 0.9 / 0.95 are hit to 7e-6)
+        const uint32_t ua = rb & 0xffffu;
         uint32_t allele;
-        if (has_variant) allele = ua < 0.9f ? alt : ref;
-        else allele = ua < 0.95f ? ref : alt;
-        // io.py:65-69: max(10, min(40, int(normal(30, 5))))  -- int() truncates toward zero
-        const float z = sample_normal2f(u24(r.y), u24(r.z)).x;
-        int q = (int)(30.0f + 5.0f * z);
-        q = q < 10 ? 10 : (q > 40 ? 40 : q);
-        const uint32_t strand = r.w & 1u;
-        const uint32_t rpos = 10u + ((r.w >> 1) & 0xffffu) % 140u;  // io.py:119 randint(10, 150)
+        if (has_variant) allele = ua < 58982u ? alt : ref;
+        else allele = ua < 62259u ? ref : alt;
+        // io.py:65-69: max(10, min(40, int(normal(30, 5)))) by inversion of its exact 31-point cdf
+        // (thresholds in units of 2^-24, built on the host from erfc): q = 10 + #{k : u >= T[k]}
+        const uint32_t uq = ra >> 8;
+        uint32_t qi = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t cand = qi + step;
+            qi = (cand <= 30u && uq >= s_qthr[cand - 1]) ? cand : qi;
+        }
+        const int q = 10 + (int)qi;
+        const uint32_t strand = ra & 1u;
+        const uint32_t rpos = 10u + (((rb >> 16) * 140u) >> 16);     // io.py:119 randint(10, 150)
         uint32_t pl = allele | ((uint32_t)q << 2) | (strand << 8) | (rpos << 9) | ((allele == alt ? 1u : 0u) << 31);
         uint64_t key = ((uint64_t)S.group << 32) | umi;
         if (sp.hop_rate > 0.0 && n_cells > 1) {
             // index hopping: the read is assigned to another sample's index (contamination.py:230-254)
-            const uint4 h = ph(0x80000000u | j, S.fam, S.c2, S.c3);
+            const uint4 h = ph(0x80000000u | j, S.fam, S.c2, S.c3);  // (a block of its own: hopping is rare)
             if (u24(h.x) < (float)sp.hop_rate) {
                 const uint32_t other = (uint32_t)S.ci + 1u + h.y % (uint32_t)(n_cells - 1);
                 const ReadCell oc = cells[other % (uint32_t)n_cells];
@@ -198,8 +226,13 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
             }
         }
         const int64_t dst = S.out_start + (int64_t)shuffle_slot(S.cell_off + j, S.cell_n, sp.shuffle);
-        keys[dst] = key;
-        payload[dst] = pl;
+        if (payload) {
+            keys[dst] = key;
+            payload[dst] = pl;
+        } else {
+            // packed 8-byte record (cell-major layout: the cell is implied by the position)
+            keys[dst] = ((uint64_t)pl << 32) | umi;
+        }
     }
 }
 
@@ -213,8 +246,13 @@ reads_pad_kernel(const ReadCell* __restrict__ cells, int n_cells, const int64_t*
     const ReadCell c = cells[ci];
     const int64_t lo = c.out_start + c.n_reads, hi = cell_tile_start[ci + 1] * READS_SEG_TILE;
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        keys[i] = ((uint64_t)c.group << 32) | READS_SENTINEL_UMI;
-        payload[i] = 0u;
+        const uint32_t pad_umi = 0xff000000u | (((uint32_t)i * 40503u) & 0xffffffu);
+        if (payload) {
+            keys[i] = ((uint64_t)c.group << 32) | pad_umi;
+            payload[i] = 0u;
+        } else {
+            keys[i] = pad_umi;
+        }
     }
 }
 
@@ -253,6 +291,7 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
     cudaError_t e = plan->cells.alloc(ctx->stream, sizeof(ReadCell) * (size_t)(n_cells + 1));
     if (e == cudaSuccess) e = plan->fam_offsets.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
     if (e == cudaSuccess) e = plan->fam_size.alloc(ctx->stream, 4 * (size_t)(nf + 1));
+    if (e == cudaSuccess) e = plan->fam_word.alloc(ctx->stream, 4 * (size_t)(nf + 1));
     if (e == cudaSuccess) e = plan->read_offset.alloc(ctx->stream, 8 * (size_t)(nf + 1));
     if (e == cudaSuccess) e = plan->total.alloc(ctx->stream, 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
@@ -291,6 +330,7 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
             if (h_cnt[i] >= (1ll << 32)) { st = PMRD_ERR_ARG; snprintf(ctx->err, sizeof(ctx->err), "a cell holds >= 2^32 reads"); break; }
             hc[i].read_start = rs;
             hc[i].n_reads = (uint32_t)h_cnt[i];
+            plan->n_groups_with_reads += h_cnt[i] > 0;
             h_tile[i] = tile;
             hc[i].out_start = plan->segmented ? tile * READS_SEG_TILE : rs;
             if (h_read_offsets) h_read_offsets[i] = rs;
@@ -313,7 +353,8 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
     if (plan->n_fam <= 0) return PMRD_OK;
     PMRD_LAUNCH(ctx, reads_size_kernel, pmrd_blocks(plan->n_fam, 256), 256, 0, ctx->seed, plan->cells.as<ReadCell>(),
-                plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp, plan->fam_size.as<uint32_t>());
+                plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp, plan->fam_size.as<uint32_t>(),
+                plan->fam_word.as<uint32_t>());
     return exclusive_scan<uint32_t, uint64_t>(ctx, plan->fam_size.as<uint32_t>(), plan->read_offset.as<uint64_t>(), plan->n_fam,
                                               plan->total.as<uint64_t>());
 }
@@ -323,7 +364,8 @@ int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uin
     if (plan->n_fam <= 0) return PMRD_OK;
     PMRD_LAUNCH(ctx, reads_gen_kernel, pmrd_blocks(plan->n_fam, 256), 256, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
-                (const uint64_t*)plan->read_offset.as<uint64_t>(), plan->n_reads, plan->segmented, d_keys, d_payload);
+                (const uint64_t*)plan->read_offset.as<uint64_t>(), (const uint32_t*)plan->fam_size.as<uint32_t>(),
+                (const uint32_t*)plan->fam_word.as<uint32_t>(), plan->n_reads, plan->segmented, d_keys, d_payload);
     if (plan->segmented && plan->n_out > plan->n_reads)
         PMRD_LAUNCH(ctx, reads_pad_kernel, (int)plan->n_cells, 256, 0, plan->cells.as<ReadCell>(), (int)plan->n_cells,
                     (const int64_t*)plan->cell_tile_start.as<int64_t>(), d_keys, d_payload);

@@ -14,15 +14,18 @@ struct ReadCell {
 };
 
 #define READS_SEG_TILE 4096 /* == RS_TILE: cells are padded to whole sort tiles when segmented */
-#define READS_SENTINEL_UMI 0xffffffffu
+/* padding reads carry a UMI with the top byte set (no 12-mer reaches it) and spread low bits, so
+ * that they never pile up into one long run */
+#define READS_IS_PAD_UMI(u) (((u) >> 24) == 0xffu)
 
 struct ReadPlan {
-    DevBuf cells, fam_offsets, fam_size, read_offset, total, cell_tile_start;
+    DevBuf cells, fam_offsets, fam_size, fam_word, read_offset, total, cell_tile_start;
     pmrd_read_sim_params sp;
     int64_t n_cells = 0;
     int64_t n_fam = 0;
     int64_t n_reads = 0;      // reads generated
     int64_t n_out = 0;        // slots in the output arrays (== n_reads unless segmented: + padding)
+    int64_t n_groups_with_reads = 0;  // cells that own at least one read
     int segmented = 0;        // cell-major, tile-padded layout (enables the per-cell 3-pass sort)
 };
 
@@ -38,3 +41,4 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan);
 int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload);
 int32_t reads_plan_cell_counts(pmrd_ctx* ctx, ReadPlan* plan, int64_t* d_out);
+int32_t reads_upload_tables(pmrd_ctx* ctx);
