@@ -39,7 +39,14 @@ for _p in (str(ROOT / "precise-mrd-mini_b200"), str(ROOT)):
 METRIC = "umi_reads_per_sec_simulate_collapse_call"
 UNIT = "reads/s"
 B_READ_PIPELINE = 54.4  # algorithmic bytes per read of the whole path (48 + 32/f, f = 5)
-B_READ_SORT_PASS = 24.0  # one radix pass: read 12 B, write 12 B per read
+# algorithmic bytes per record slot and launch of each hot kernel (rec = record bytes: 8 packed, 12 split)
+KERNEL_BYTES = {
+    "rs_downsweep_kernel": lambda rec: 2.0 * rec,        # one radix pass: read + write every record
+    "rs_downsweep_direct_kernel": lambda rec: 2.0 * rec,
+    "rs_upsweep_kernel": lambda rec: 8.0,                # digit histogram: reads the 8-byte key / record
+    "reads_gen_kernel": lambda rec: float(rec),          # writes every record once
+    "cell_consensus_kernel": lambda rec: float(rec),     # reads every record once
+}
 HBM_FALLBACK_GBS = 6650.0
 
 
@@ -254,6 +261,7 @@ def main() -> int:
     res = plan.results()
     chunk_reads = [plan.chunk_reads(i) for i in range(plan.n_chunks)]
     n_chunks = plan.n_chunks
+    pinfo = plan.info()
     plan.close()
 
     # ---- end-to-end arm: public API, host buffers in, host table out, every step ------------
@@ -283,21 +291,29 @@ def main() -> int:
 
     if rank == 0:
         peak, peak_src = peak_hbm()
-        # dominant kernel of the step by device time
+        # dominant kernel of the step by device time (per-kernel CUDA events inside the timed region)
         top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ("none", (0, 0.0))
         total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
         kname, (kcount, kms) = top
-        reads_per_launch = float(np.mean(chunk_reads)) if chunk_reads else 0.0
-        bytes_per_launch = B_READ_SORT_PASS * reads_per_launch if kname.startswith("rs_") else None
-        if kname.startswith("rs_upsweep"):
-            bytes_per_launch = 8.0 * reads_per_launch
+        kbase = kname.split("<")[0]
+        rec = pinfo["record_bytes"]
+        slots = pinfo["n_slots"]                                       # record slots per step (reads + tile padding)
+        launches_per_step = {"rs_downsweep_kernel": pinfo["sort_passes"] * n_chunks, "rs_downsweep_direct_kernel": pinfo["sort_passes"] * n_chunks,
+                             "rs_upsweep_kernel": pinfo["sort_passes"] * n_chunks,
+                             "reads_gen_kernel": n_chunks, "cell_consensus_kernel": n_chunks}.get(kbase)
         roof = {"bound": "hbm", "kernel": kname, "launches": kcount, "avg_launch_ms": kms / max(kcount, 1),
                 "share_of_step": kms / total_prof_ms, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None}
-        if bytes_per_launch:
-            ach = bytes_per_launch / (kms / kcount * 1e-3) / 1e9
-            roof.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": bytes_per_launch})
+        if kbase in KERNEL_BYTES and launches_per_step:
+            # algorithmic bytes of ALL launches of this kernel in a step / their summed device time
+            # (== bytes per launch / average launch duration; launches of the same kernel inside the
+            # tiny BH sort have their own template instance and are not mixed in)
+            bytes_per_step = KERNEL_BYTES[kbase](rec) * slots * (pinfo["sort_passes"] if kbase.startswith("rs_") else 1)
+            ach = bytes_per_step * args.steps / (kms * 1e-3) / 1e9
+            roof.update({"achieved": ach, "frac": ach / peak, "algorithmic_bytes_per_launch": bytes_per_step / launches_per_step,
+                         "bytes_per_record": KERNEL_BYTES[kbase](rec), "records_per_launch": slots / n_chunks})
         else:
             roof.update({"achieved": None, "frac": None})
+        reads_per_launch = slots / max(n_chunks, 1)
         tj = ROOT / "profiles" / "traffic.json"
         if tj.exists():
             try:
@@ -311,7 +327,8 @@ def main() -> int:
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 keys / u32 payload / f64 tests", "data": "synthetic",
             "config": {"workload": label, "cells_per_gpu": int(len(cell_id)), "reads_per_gpu_per_step": int(n_reads),
-                       "families_per_gpu_per_step": int(depth.sum()), "chunks": n_chunks, "family_sizes": "clip(Poisson(5),1,1000)",
+                       "families_per_gpu_per_step": int(depth.sum()), "chunks": n_chunks, "record_bytes": pinfo["record_bytes"],
+                       "radix_passes": pinfo["sort_passes"], "family_sizes": "clip(Poisson(5),1,1000)",
                        "umi": "12-mer (24 bit)", "input_order": "window-shuffled (Philox-keyed affine permutation)",
                        "l2": "inputs larger than L2 (>= 1.9 GB per chunk vs 126 MB)", "parallelism": f"replicate axis sharded over {world} GPU(s)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

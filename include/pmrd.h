@@ -314,6 +314,11 @@ int64_t pmrd_plan_n_reads(const pmrd_plan* plan);
 int64_t pmrd_plan_n_families(const pmrd_plan* plan);
 int64_t pmrd_plan_n_chunks(const pmrd_plan* plan);
 int64_t pmrd_plan_chunk_reads(const pmrd_plan* plan, int64_t chunk);
+/* Byte-accounting facts for roofline reporting: out[0] reads generated, [1] record slots
+ * written (reads + tile padding), [2] families drawn, [3] chunks, [4] radix passes per chunk,
+ * [5] bytes per read record in the sort (8 packed / 12 key+payload), [6] largest chunk (slots),
+ * [7] 1 if the cell-major (segmented) path is used. */
+int32_t pmrd_plan_info(const pmrd_plan* plan, int64_t* out8);
 void pmrd_plan_destroy(pmrd_plan* plan);
 /* Stage-by-stage entry points, for per-stage timing (bench.py): the stage for ONE chunk
  * (chunks share the read buffers, so stages of different chunks cannot be separated). */

@@ -64,6 +64,7 @@ int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P, int64_t which);
 int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P, int64_t which);
 int64_t plan_n_chunks(const pmrd_plan* P);
 int64_t plan_chunk_reads(const pmrd_plan* P, int64_t which);
+int32_t plan_info(const pmrd_plan* P, int64_t* o);
 int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P);
 int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h, double* h_mean_rate, int64_t* h_totals);
 void plan_destroy(pmrd_plan* P);
@@ -669,6 +670,7 @@ int32_t pmrd_plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* plan, int64_t chunk) {
 }
 int64_t pmrd_plan_n_chunks(const pmrd_plan* plan) { return plan_n_chunks(plan); }
 int64_t pmrd_plan_chunk_reads(const pmrd_plan* plan, int64_t chunk) { return plan_chunk_reads(plan, chunk); }
+int32_t pmrd_plan_info(const pmrd_plan* plan, int64_t* out8) { return plan_info(plan, out8); }
 int32_t pmrd_plan_run_call(pmrd_ctx* ctx, pmrd_plan* plan) {
     ENTER(ctx);
     PMRD_ARG(ctx, plan != nullptr, "plan");

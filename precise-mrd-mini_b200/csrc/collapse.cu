@@ -306,7 +306,8 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
                       pmrd_umi_params P, uint32_t run_mask, int64_t cell0, const uint8_t* __restrict__ alt_allele,
                       unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot,
                       unsigned long long* __restrict__ o_var) {
-    __shared__ uint64_t s_rec[CC_TILE];
+    __shared__ uint32_t s_umi[CC_TILE];   // split halves: the vote walks only the payloads (32-bit, half the
+    __shared__ uint32_t s_pl[CC_TILE];    // shared-memory traffic and bank conflicts of walking 64-bit records)
     __shared__ uint16_t s_head[CC_TILE];
     __shared__ uint32_t sw[33];
     __shared__ unsigned long long s_acc[3];
@@ -325,7 +326,9 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
 #pragma unroll
     for (int j = 0; j < CC_ITEMS; ++j) {
         const int i = j * CC_THREADS + threadIdx.x;
-        s_rec[i] = rec[base + i];
+        const uint64_t v = rec[base + i];
+        s_umi[i] = (uint32_t)v;
+        s_pl[i] = (uint32_t)(v >> 32);
     }
     __syncthreads();
     const int cell = s_cell;
@@ -337,8 +340,8 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     for (int j = 0; j < CC_ITEMS; ++j) {
         const int i = i0 + j;
         bool head;
-        if (i > 0) head = ((((uint32_t)s_rec[i]) ^ ((uint32_t)s_rec[i - 1])) & run_mask) != 0u;
-        else head = base == cell_lo || ((((uint32_t)rec[base - 1]) ^ ((uint32_t)s_rec[0])) & run_mask) != 0u;
+        if (i > 0) head = ((s_umi[i] ^ s_umi[i - 1]) & run_mask) != 0u;
+        else head = base == cell_lo || ((((uint32_t)rec[base - 1]) ^ s_umi[0]) & run_mask) != 0u;
         if (head) { flags |= 1u << j; ++cnt; }
     }
     uint32_t n_heads;
@@ -356,17 +359,19 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         // the tile's last run may continue into the next tile(s) of the same cell
         int64_t g_hi = base + CC_TILE;
         if (h + 1 == n_heads) {
-            const uint32_t rk = ((uint32_t)s_rec[lo]) & run_mask;
+            const uint32_t rk = s_umi[lo] & run_mask;
             while (g_hi < cell_hi && ((((uint32_t)rec[g_hi]) & run_mask) == rk)) ++g_hi;
         }
         const int len = n_in + (int)(g_hi - (base + CC_TILE));
-        auto rec_at = [&](int i) -> uint64_t { return i < n_in ? s_rec[lo + i] : rec[base + CC_TILE + (i - n_in)]; };
+        auto umi_at = [&](int i) -> uint32_t { return i < n_in ? s_umi[lo + i] : (uint32_t)rec[base + CC_TILE + (i - n_in)]; };
+        auto pl_at = [&](int i) -> uint32_t { return i < n_in ? s_pl[lo + i] : (uint32_t)(rec[base + CC_TILE + (i - n_in)] >> 32); };
         if (FULL) {
             // the sort ordered every UMI bit: a run IS a family
-            const uint32_t umi = (uint32_t)s_rec[lo];
+            const uint32_t umi = s_umi[lo];
             if ((umi >> 24) == 0xffu) continue;                  // padding of the tile-aligned cell
             Vote v;
-            for (int c = 0; c < len; ++c) v.add((uint32_t)(rec_at(c) >> 32), P.quality_threshold);
+            for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], P.quality_threshold);
+            for (int c = n_in; c < len; ++c) v.add(pl_at(c), P.quality_threshold);
             ++n_fam;
             if (len >= P.min_family_size) {
                 const int best = v.result(P.consensus_threshold);
@@ -380,7 +385,7 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         uint32_t seen0 = 0, seen1 = 0, seen2 = 0, seen3 = 0;
         int n_seen_umi = 0;
         for (int a = 0; a < len; ++a) {
-            const uint32_t umi = (uint32_t)rec_at(a);
+            const uint32_t umi = umi_at(a);
             if ((umi >> 24) == 0xffu) continue;                  // padding of the tile-aligned cell
             bool first;
             if (n_seen_umi <= 4) {
@@ -388,7 +393,7 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
                           (n_seen_umi > 2 && umi == seen2) || (n_seen_umi > 3 && umi == seen3));
             } else {
                 first = true;
-                for (int b = 0; b < a && first; ++b) first = (uint32_t)rec_at(b) != umi;
+                for (int b = 0; b < a && first; ++b) first = umi_at(b) != umi;
             }
             if (!first) continue;
             if (n_seen_umi == 0) seen0 = umi;
@@ -398,10 +403,8 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
             ++n_seen_umi;
             Vote v;
             uint32_t size = 0;
-            for (int c = a; c < len; ++c) {
-                const uint64_t rc = rec_at(c);
-                if ((uint32_t)rc == umi) { v.add((uint32_t)(rc >> 32), P.quality_threshold); ++size; }
-            }
+            for (int c = a; c < len; ++c)
+                if (umi_at(c) == umi) { v.add(pl_at(c), P.quality_threshold); ++size; }
             ++n_fam;
             if ((int)size >= P.min_family_size) {
                 const int best = v.result(P.consensus_threshold);

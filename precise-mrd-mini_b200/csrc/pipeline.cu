@@ -374,3 +374,28 @@ int64_t plan_n_chunks(const pmrd_plan* P) { return P ? (int64_t)P->chunks.size()
 int64_t plan_chunk_reads(const pmrd_plan* P, int64_t which) {
     return (P && which >= 0 && which < (int64_t)P->chunks.size()) ? P->chunks[(size_t)which]->reads.n_reads : 0;
 }
+
+int32_t plan_info(const pmrd_plan* P, int64_t* o) {
+    if (!P || !o) return PMRD_ERR_ARG;
+    int64_t n_out = 0, max_out = 0, seg = 1, passes = 0;
+    for (const PlanChunk* ch : P->chunks) {
+        n_out += ch->reads.n_out;
+        if (ch->reads.n_out > max_out) max_out = ch->reads.n_out;
+        if (!ch->reads.segmented) seg = 0;
+    }
+    if (seg) passes = (P->sort_bits + 7) / 8;
+    else if (!P->chunks.empty()) {
+        uint64_t v = P->chunks[0]->varying;
+        int b = 0;
+        while (b < 64) {
+            if (!((v >> b) & 1ull)) { ++b; continue; }
+            int w = 64 - b < 8 ? 64 - b : 8;
+            while (w > 1 && !((v >> (b + w - 1)) & 1ull)) --w;
+            ++passes;
+            b += w;
+        }
+    }
+    o[0] = P->n_reads; o[1] = n_out; o[2] = P->n_fam; o[3] = (int64_t)P->chunks.size(); o[4] = passes; o[5] = seg ? 8 : 12;
+    o[6] = max_out; o[7] = seg;
+    return PMRD_OK;
+}

@@ -2,6 +2,7 @@
 // grouping: src/precise_mrd/umi.py:97-144 (group_umis_by_site / exact-UMI groups),
 // precise-mrd-mini/src/mrd/umi.py:65-67 (groupby), rust_ext/src/lib.rs:7-22 (FNV map).
 #include "radix_sort.cuh"
+#include <stdlib.h>
 
 // ---------------------------------------------------------------- varying bits ----------
 __global__ void __launch_bounds__(256) rs_varying_kernel(const uint64_t* __restrict__ keys, int64_t n,
@@ -194,13 +195,25 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
         const int loc = wloc + i * 32 + (int)lane;
         const bool valid = loc < tile_n;
         const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & mask) : 0xffffffffu;
-        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        // peers = lanes holding the same digit.  MATCH.ANY runs on the address-divergence unit at a
+        // cost proportional to the number of distinct values (~30 for a random 8-bit digit; ncu: ADU
+        // pipe 88 % busy); eight ballots + logic ops on the ALU build the same mask off that pipe.
+        uint32_t m = __ballot_sync(0xffffffffu, valid);
+        if (!valid) m = ~m;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? bal : ~bal;
+        }
         const uint32_t before = __popc(m & lt);
+        // the lowest lane of each digit group bumps the warp's counter once for the whole group and
+        // hands the old value to its peers by shuffle: one shared atomic + one shuffle per item,
+        // no read-modify-write hazard and therefore no warp barriers in the loop
+        const int leader = __ffs((int)m) - 1;
         uint32_t old = 0;
-        if (valid) old = S.warp_cnt[warp][d];
-        __syncwarp();
-        if (valid && before == 0) S.warp_cnt[warp][d] = old + __popc(m);
-        __syncwarp();
+        if (valid && before == 0) old = atomicAdd(&S.warp_cnt[warp][d], (uint32_t)__popc(m));
+        old = __shfl_sync(0xffffffffu, old, leader);
         rank[i] = (uint16_t)(old + before);
     }
     __syncthreads();
@@ -249,6 +262,73 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
             const uint32_t g = (uint32_t)j + S.glob_delta[d];
             keys_out[g] = k;
             if (HAS_VALS) vals_out[g] = S.vals[j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------- direct downsweep ------
+// Keys-only variant for cell-major input: ranks are computed exactly as above, but every record is
+// stored straight from registers to its final position.  A cell's output region is at most a
+// few MB and its tiles are processed back to back, so the partially written 32-byte sectors meet
+// in L2 before they are evicted (DRAM write traffic stays at 8 B / record -- checked with ncu),
+// and the shared-memory reorder (a bank-conflicted 64-bit scatter + a gather + a barrier) is gone.
+__global__ void __launch_bounds__(RS_THREADS, 3)
+rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
+                           const uint32_t* __restrict__ hist_scanned, int64_t n, int shift, uint32_t mask) {
+    __shared__ uint32_t s_cnt[RS_WARPS][RS_MAX_BINS];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = lanemask_lt();
+    for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
+    const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
+    const int64_t rem = n - tile_base;
+    const int tile_n = rem < RS_TILE ? (int)rem : RS_TILE;
+    const int wloc = (int)warp * (RS_TILE / RS_WARPS);
+    uint64_t key[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int loc = wloc + i * 32 + (int)lane;
+        key[i] = (loc < tile_n) ? keys_in[tile_base + loc] : ~0ull;
+    }
+    __syncthreads();
+    uint16_t rank[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int loc = wloc + i * 32 + (int)lane;
+        const bool valid = loc < tile_n;
+        const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & mask) : 0xffffffffu;
+        uint32_t m = __ballot_sync(0xffffffffu, valid);
+        if (!valid) m = ~m;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            m &= bit ? bal : ~bal;
+        }
+        const uint32_t before = __popc(m & lt);
+        const int leader = __ffs((int)m) - 1;
+        uint32_t old = 0;
+        if (valid && before == 0) old = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(m));
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[i] = (uint16_t)(old + before);
+    }
+    __syncthreads();
+    // per bin: global start of this tile's run + exclusive prefix over the warps
+    if (threadIdx.x < RS_MAX_BINS) {
+        uint32_t run = hist_scanned[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t c = s_cnt[w][threadIdx.x];
+            s_cnt[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const int loc = wloc + i * 32 + (int)lane;
+        if (loc < tile_n) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+            keys_out[s_cnt[warp][d] + rank[i]] = key[i];
         }
     }
 }
@@ -311,6 +391,11 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
     PMRD_CUDA(ctx, hist.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
     uint64_t* kin = keys_a; uint32_t* vin = vals_a; uint64_t* kout = keys_b; uint32_t* vout = vals_b;
     const int n_passes = (key_bits + 7) / 8;
+    static int direct = -1;
+    if (direct < 0) {
+        const char* e = getenv("PMRD_RS_DIRECT");
+        direct = e ? atoi(e) : 1;
+    }
     for (int p = 0; p < n_passes; ++p) {
         const int shift = p * 8;
         const int w = key_bits - shift < 8 ? key_bits - shift : 8;
@@ -319,6 +404,8 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256, 0, hist.as<uint32_t>(), d_cell_tile_start, (int)n_cells);
         if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
+        } else if (direct) {   // packed 8-byte records, stored straight to their final place (L2 merges the sectors)
+            PMRD_LAUNCH(ctx, rs_downsweep_direct_kernel, n_tiles, RS_THREADS, 0, kin, kout, hist.as<uint32_t>(), n, shift, mask);
         } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
         }

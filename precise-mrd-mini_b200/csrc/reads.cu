@@ -43,8 +43,18 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
         const double p = 2.0 / (2.0 + sp.mean_family_size);
         d.size = sample_negbin_r2(u, p) + 1;
     } else {
-        int s = sample_poisson_small(u, sp.mean_family_size);
-        d.size = s < 1 ? 1 : s;
+        // Poisson(mean) by inversion of its cdf, accumulated in fp32 from a 24-bit uniform when the
+        // mean is small (the sizes only steer a simulation; fp64 exp + recurrence costs 3x as much)
+        if (sp.mean_family_size <= 16.0) {
+            const float lam = (float)sp.mean_family_size, uf = u24(b.x);
+            float p = __expf(-lam), F = p;
+            int k = 0;
+            while (uf > F && k < 96) { ++k; p *= lam / (float)k; F += p; }
+            d.size = k < 1 ? 1 : k;
+        } else {
+            int s = sample_poisson_small(u, sp.mean_family_size);
+            d.size = s < 1 ? 1 : s;
+        }
     }
     if (d.size > sp.max_family_size) d.size = sp.max_family_size;
     d.umi = b.z & 0xffffffu;

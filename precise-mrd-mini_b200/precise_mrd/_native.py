@@ -402,6 +402,12 @@ class Plan:
         self.ctx.lib.pmrd_plan_n_chunks.argtypes = [C.c_void_p]
         return int(self.ctx.lib.pmrd_plan_n_chunks(self.h))
 
+    def info(self) -> Dict[str, int]:
+        o = np.zeros(8, np.int64)
+        self.ctx._check(self.ctx.lib.pmrd_plan_info(self.h, _ptr(o)))
+        names = ("n_reads", "n_slots", "n_families", "n_chunks", "sort_passes", "record_bytes", "max_chunk_slots", "segmented")
+        return {k: int(v) for k, v in zip(names, o)}
+
     def chunk_reads(self, chunk: int) -> int:
         self.ctx.lib.pmrd_plan_chunk_reads.restype = C.c_int64
         self.ctx.lib.pmrd_plan_chunk_reads.argtypes = [C.c_void_p, C.c_int64]
