@@ -146,10 +146,17 @@ def cpu_pipeline_once(cfg, cid, af, depth, threads):
     return r["total_reads"], time.perf_counter() - t0
 
 
-def cpu_baseline(cfg, cell_id, af, depth, budget_s=12.0):
-    from oracle import cport
+def host_threads() -> int:
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1; the CPU arm
+    sets the OpenMP team size explicitly instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
 
-    threads = cport.max_threads()
+
+def cpu_baseline(cfg, cell_id, af, depth, budget_s=12.0):
+    threads = host_threads()
     n = 64
     reads, dt = cpu_pipeline_once(cfg, *cpu_sample_cells(cell_id, af, depth, n), threads)   # warm-up + rate estimate
     rate = reads / max(dt, 1e-6)
@@ -166,9 +173,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return 0
     cfg, label, cell_id, af, depth = workload(args.workload, 0, 1)
-    from oracle import cport
-
-    threads = cport.max_threads()
+    threads = host_threads()
     n = int(os.environ.get("PMRD_REF_CELLS", 256))
     cid, a, d = cpu_sample_cells(cell_id, af, depth, n)
     for _ in range(args.warmup):
