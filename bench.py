@@ -168,6 +168,41 @@ def cpu_baseline(cfg, cell_id, af, depth, budget_s=12.0):
                       "oracle/pmrd_oracle.c, OpenMP over cells"}
 
 
+# ------------------------------------------------------------------------------- LoD grid
+def lod_grid_wall(cfg):
+    """Second half of BASELINE.json's metric: wall time of the eval-lod grid (C3 of SURVEY.md §8d:
+    LoB blanks + 15 log-spaced AF in [1e-4, 1e-2] x depths {1k,5k,10k,50k,100k} x 25 replicates, 200-resample
+    logistic bootstrap per depth) from LODAnalyzer entry to the finished tables, host wall clock."""
+    import copy
+    import tempfile
+
+    from precise_mrd.eval import LODAnalyzer
+
+    out = {}
+    depths = [1000, 5000, 10000, 50000, 100000]
+    for engine, reps in (("grid", 25), ("stages", 2)):
+        c = copy.deepcopy(cfg)
+        c.seed = 7
+        t0 = time.perf_counter()
+        an = LODAnalyzer(c, np.random.default_rng(7), engine=engine)
+        import contextlib
+        import io
+
+        with contextlib.redirect_stdout(io.StringIO()):
+            an.estimate_lob(n_blank_runs=max(10, reps // 2))
+            res = an.estimate_lod(depth_values=depths if engine == "grid" else depths[:3], n_replicates=reps)
+            with tempfile.TemporaryDirectory() as td:
+                an.generate_reports(td)
+        wall = time.perf_counter() - t0
+        n_dep = len(res["depth_results"])
+        out[engine] = {"wall_s": wall, "cells": 15 * n_dep * reps, "depths": n_dep, "replicates": reps,
+                       "lod_af": {str(d): r["lod_af"] for d, r in res["depth_results"].items()}}
+    out["note"] = ("grid = read-level fused device plan over the whole C3 grid (1875 cells + blanks); stages = the reference's own "
+                   "per-cell simulate->collapse->fit_error_model->call_mrd loop with every stage on the GPU (parity engine; 90 cells "
+                   "timed here, the reference's default 1125-cell grid scales linearly; the reference itself needs 3-7 s per cell)")
+    return out
+
+
 # ------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world):
     if rank != 0:
@@ -210,6 +245,7 @@ def main() -> int:
     ap.add_argument("--workload", default=os.environ.get("PMRD_BENCH_WORKLOAD", "default"))
     ap.add_argument("--chunk-log2", type=int, default=int(os.environ.get("PMRD_CHUNK_LOG2", "0")))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lod", action="store_true", help="skip the LoD-grid wall-time leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -347,6 +383,8 @@ def main() -> int:
             "result_check": {"significant_cells": int(res["significant"].sum()), "mean_error_rate": res["mean_error_rate"],
                              "families_formed": int(res["totals"][1])},
         }
+        if world == 1 and not args.no_lod:
+            line["lod_grid"] = lod_grid_wall(cfg)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(cfg, cell_id, af, depth)
