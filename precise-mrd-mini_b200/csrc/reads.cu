@@ -18,14 +18,23 @@
 #include "scan.cuh"
 #include "reads.cuh"
 
-__device__ __forceinline__ int find_cell(const int64_t* __restrict__ fam_offsets, int n_cells, int64_t f) {
-    int lo = 0, hi = n_cells;  // fam_offsets[lo] <= f < fam_offsets[hi]
-    while (hi - lo > 1) {
+__device__ __forceinline__ int find_cell_in(const int64_t* __restrict__ fam_offsets, int lo, int hi, int64_t f) {
+    while (hi - lo > 1) {  // fam_offsets[lo] <= f < fam_offsets[hi]
         const int mid = (lo + hi) >> 1;
         if (fam_offsets[mid] <= f) lo = mid;
         else hi = mid;
     }
     return lo;
+}
+__device__ __forceinline__ int find_cell(const int64_t* __restrict__ fam_offsets, int n_cells, int64_t f) {
+    return find_cell_in(fam_offsets, 0, n_cells, f);
+}
+// A block owns consecutive families [f0, f1]: two threads bracket the cells they can fall in,
+// so that the per-family search runs over (almost always) one or two cells, not all of them.
+__device__ __forceinline__ void block_cell_range(const int64_t* __restrict__ fam_offsets, int n_cells, int64_t f0, int64_t f1,
+                                                 int* s_range /* shared int[2] */) {
+    if (threadIdx.x < 2) s_range[threadIdx.x] = find_cell(fam_offsets, n_cells, threadIdx.x == 0 ? f0 : f1);
+    __syncthreads();
 }
 
 struct FamDraw {
@@ -34,31 +43,41 @@ struct FamDraw {
     bool has_variant;
 };
 
-__device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell& c, uint32_t fam, const pmrd_read_sim_params& sp) {
+// s_cdf: Poisson cdf table in shared memory (128 floats, padded with 2.0f) or nullptr
+__device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell& c, uint32_t fam, const pmrd_read_sim_params& sp,
+                                               const float* s_cdf) {
     const uint32_t c2 = (uint32_t)c.cell_id, c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((c.cell_id >> 32) & 0xffffffu);
     const uint4 b = ph(0xffffffffu, fam, c2, c3);
     FamDraw d;
-    const double u = u53(b.x, b.y);
-    if (sp.family_model == 0) {
-        const double p = 2.0 / (2.0 + sp.mean_family_size);
-        d.size = sample_negbin_r2(u, p) + 1;
+    if (s_cdf) {
+        // Poisson(mean <= 16) by inversion of a 24-bit uniform against the fp32 cdf table the plan
+        // built on the host (the sizes only steer a simulation): size = #{k : F[k] < u}
+        const float uf = u24(b.x);
+        int k = 0;
+#pragma unroll
+        for (int step = 64; step > 0; step >>= 1) k += (s_cdf[k + step - 1] < uf) ? step : 0;
+        d.size = k < 1 ? 1 : k;
     } else {
-        // Poisson(mean) by inversion of its cdf, accumulated in fp32 from a 24-bit uniform when the
-        // mean is small (the sizes only steer a simulation; fp64 exp + recurrence costs 3x as much)
-        if (sp.mean_family_size <= 16.0) {
-            const float lam = (float)sp.mean_family_size, uf = u24(b.x);
-            float p = __expf(-lam), F = p;
-            int k = 0;
-            while (uf > F && k < 96) { ++k; p *= lam / (float)k; F += p; }
-            d.size = k < 1 ? 1 : k;
+        const double u = u53(b.x, b.y);
+        if (sp.family_model == 0) {
+            const double p = 2.0 / (2.0 + sp.mean_family_size);
+            d.size = sample_negbin_r2(u, p) + 1;
         } else {
-            int s = sample_poisson_small(u, sp.mean_family_size);
+            const int s = sample_poisson_small(u, sp.mean_family_size);
             d.size = s < 1 ? 1 : s;
         }
     }
     if (d.size > sp.max_family_size) d.size = sp.max_family_size;
     d.umi = b.z & 0xffffffu;
-    // io.py:97 / :100-101
+    // io.py:97: has_variant = u53(b.w, b2.x) < af.  The top 32 bits settle it unless b.w sits on the
+    // cell's threshold word (probability 2^-32), so the second Philox block is drawn only then, or
+    // when a contamination knob needs its other words (io.py:100-101).
+    const bool extras = sp.contamination_rate > 0.0 || sp.collision_rate > 0.0;
+    const int64_t hw = (int64_t)b.w;
+    if (!extras && (hw < c.af_lt || hw >= c.af_ge)) {
+        d.has_variant = hw < c.af_lt;
+        return d;
+    }
     const uint4 b2 = ph(0xfffffffeu, fam, c2, c3);
     d.has_variant = u53(b.w, b2.x) < c.af;
     if (sp.contamination_rate > 0.0 && u53(b2.y, b2.z) < sp.contamination_rate) d.has_variant = !d.has_variant;
@@ -72,13 +91,18 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
 
 __global__ void __launch_bounds__(256)
 reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
-                  int64_t n_fam, pmrd_read_sim_params sp, uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                  int64_t n_fam, pmrd_read_sim_params sp, const float* __restrict__ size_cdf /* [128] or NULL */,
+                  uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word) {
+    __shared__ int s_range[2];
+    __shared__ float s_cdf[128];
+    const int64_t f0 = (int64_t)blockIdx.x * blockDim.x, f = f0 + threadIdx.x;
+    if (size_cdf && threadIdx.x < 128) s_cdf[threadIdx.x] = size_cdf[threadIdx.x];
+    block_cell_range(fam_offsets, n_cells, f0, min(f0 + (int64_t)blockDim.x, n_fam) - 1, s_range);
     if (f >= n_fam) return;
     const Philox ph(seed);
-    const int ci = find_cell(fam_offsets, n_cells, f);
+    const int ci = find_cell_in(fam_offsets, s_range[0], s_range[1] + 1, f);
     const ReadCell c = cells[ci];
-    const FamDraw d = draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp);
+    const FamDraw d = draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp, size_cdf ? s_cdf : nullptr);
     fam_size[f] = (uint32_t)d.size;
     fam_word[f] = d.umi | ((d.has_variant ? 1u : 0u) << 24);   // the generator re-reads this instead of re-drawing
 }
@@ -87,29 +111,51 @@ reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64
 
 // cdf of q = max(10, min(40, int(N(30,5)))) in units of 2^-24: c_qual_thr[k] = P(q <= 10 + k), k = 0..29
 __constant__ uint32_t c_qual_thr[32];
+// coarse inverse of that cdf: c_qual_lut[b] = #{k < 30 : T[k] <= b << 16}
+__constant__ uint8_t c_qual_lut[256];
 
 int32_t reads_upload_tables(pmrd_ctx* ctx) {
     uint32_t h[32];
+    uint8_t lut[256];
     for (int k = 0; k < 32; ++k) {
         // int() truncates toward zero and 30 + 5 z > 0 here, so q <= 10 + k  <=>  30 + 5 z < 11 + k
         const double zc = ((double)(11 + k) - 30.0) / 5.0;
         const double cdf = 0.5 * erfc(-zc / sqrt(2.0));
         h[k] = k < 30 ? (uint32_t)llround(cdf * 16777216.0) : 0xffffffffu;
     }
+    for (uint32_t b = 0; b < 256; ++b) {
+        int cnt = 0;
+        for (int k = 0; k < 30; ++k) cnt += h[k] <= (b << 16);
+        lut[b] = (uint8_t)cnt;
+    }
     PMRD_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qual_thr, h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
+    PMRD_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qual_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, ctx->stream));
     return PMRD_OK;
 }
 
 // bijection of [0, n): an affine permutation inside each complete 4096-slot window and an
-// affine permutation of the complete windows themselves; the tail window stays in place
-__device__ __forceinline__ uint32_t shuffle_slot(uint32_t x, uint32_t n, int shuffle) {
+// affine permutation w -> (97 w + 13) mod n_full of the complete windows themselves (97 is prime:
+// a bijection unless it divides n_full); the tail window stays in place.  inv_full = 1 / n_full as
+// fp32 when the window permutation applies (n_full <= 2^16, so 97 w + 13 < 2^24 is exact in fp32
+// and the quotient estimate is off by at most one), else 0.
+#define SHUF_MUL 97u
+__device__ __forceinline__ float shuffle_inv(uint32_t n) {
+    const uint32_t n_full = n / SHUF_WINDOW;
+    return (n_full > 1u && n_full <= 65536u && n_full % SHUF_MUL != 0u) ? 1.0f / (float)n_full : 0.0f;
+}
+__device__ __forceinline__ uint32_t shuffle_slot(uint32_t x, uint32_t n, float inv_full, int shuffle) {
     if (!shuffle) return x;
     const uint32_t n_full = n / SHUF_WINDOW;
     uint32_t w = x / SHUF_WINDOW, l = x % SHUF_WINDOW;
     if (w >= n_full) return x;
     l = (l * 2654435761u + 0x9e37u * w) & (SHUF_WINDOW - 1);  // odd multiplier: bijection mod 4096
-    const uint32_t A = 1000003u;                               // prime: coprime with n_full unless it divides it
-    if (n_full % A != 0) w = (uint32_t)(((uint64_t)w * A + 12345u) % n_full);
+    if (inv_full != 0.0f) {
+        const uint32_t y = w * SHUF_MUL + 13u;
+        int32_t r = (int32_t)(y - (uint32_t)((float)y * inv_full) * n_full);
+        r += r < 0 ? (int32_t)n_full : 0;
+        r -= r >= (int32_t)n_full ? (int32_t)n_full : 0;
+        w = (uint32_t)r;
+    }
     return w * SHUF_WINDOW + l;
 }
 
@@ -139,7 +185,7 @@ struct FamSlot {
     uint32_t group;
     int64_t out_start;    // output position of the cell's (chunk's) first read
     int32_t ci;
-    int32_t pad;
+    float inv_full;       // shuffle_inv(cell_n)
 };
 
 __global__ void __launch_bounds__(256)
@@ -149,15 +195,19 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
                  int64_t n_reads, int segmented, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
     __shared__ FamSlot s_slot[8][32];
     __shared__ uint32_t s_qthr[32];
+    __shared__ uint8_t s_qlut[256];
+    __shared__ int s_range[2];
     if (threadIdx.x < 32) s_qthr[threadIdx.x] = c_qual_thr[threadIdx.x];
+    s_qlut[threadIdx.x] = c_qual_lut[threadIdx.x];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t f = ((int64_t)blockIdx.x * 8 + warp) * 32 + lane;
+    const int64_t f0 = (int64_t)blockIdx.x * 256, f = f0 + threadIdx.x;
+    block_cell_range(fam_offsets, n_cells, f0, min(f0 + 256, n_fam) - 1, s_range);
     const Philox ph(seed);
     const bool valid = f < n_fam;
     int64_t off = 0;
     uint32_t size = 0;
     if (valid) {
-        const int ci = find_cell(fam_offsets, n_cells, f);
+        const int ci = find_cell_in(fam_offsets, s_range[0], s_range[1] + 1, f);
         const ReadCell c = cells[ci];
         const uint32_t fam = (uint32_t)(f - c.fam_offset);
         off = (int64_t)read_offset[f];
@@ -179,10 +229,12 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
             S.cell_n = (uint32_t)n_reads;
             S.out_start = 0;
         }
+        S.inv_full = shuffle_inv(S.cell_n);
     }
     const int64_t r0 = __shfl_sync(0xffffffffu, off, 0);
-    const uint32_t loc = valid ? (uint32_t)(off - r0) : 0xffffffffu;   // sorted ascending over the lanes
-    if (valid) s_slot[warp][lane].local_off = loc;
+    // sorted ascending over the lanes; lanes past the last family never own a read
+    const uint32_t loc = valid ? (uint32_t)(off - r0) : 0xffffffffu;
+    s_slot[warp][lane].local_off = loc;
     // reads owned by the warp: [0, total)
     const uint32_t end = valid ? loc + size : 0u;
     uint32_t total = end;
@@ -194,10 +246,8 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         uint32_t lo = 0;
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
-            const uint32_t cand = lo + step;
-            const uint32_t oc = s_slot[warp][cand & 31].local_off;
-            const bool ok = cand < 32 && (((int64_t)blockIdx.x * 8 + warp) * 32 + cand) < n_fam && oc <= k;
-            lo = ok ? cand : lo;
+            const uint32_t cand = lo + step;   // <= 31
+            lo = s_slot[warp][cand].local_off <= k ? cand : lo;
         }
         const FamSlot S = s_slot[warp][lo];
         const uint32_t j = k - S.local_off;
@@ -213,13 +263,13 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         else allele = ua < 62259u ? ref : alt;
         // io.py:65-69: max(10, min(40, int(normal(30, 5)))) by inversion of its exact 31-point cdf
         // (thresholds in units of 2^-24, built on the host from erfc): q = 10 + #{k : u >= T[k]}
+        // (coarse 256-bucket table, then a walk that almost never takes more than two steps;
+        // T[30] = T[31] = 2^32 - 1 stops it)
         const uint32_t uq = ra >> 8;
-        uint32_t qi = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const uint32_t cand = qi + step;
-            qi = (cand <= 30u && uq >= s_qthr[cand - 1]) ? cand : qi;
-        }
+        uint32_t qi = s_qlut[uq >> 16];
+        qi += uq >= s_qthr[qi] ? 1u : 0u;
+        qi += uq >= s_qthr[qi] ? 1u : 0u;
+        while (uq >= s_qthr[qi]) ++qi;
         const int q = 10 + (int)qi;
         const uint32_t strand = ra & 1u;
         const uint32_t rpos = 10u + (((rb >> 16) * 140u) >> 16);     // io.py:119 randint(10, 150)
@@ -235,7 +285,7 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
                 pl = (pl & 0x7fffffffu) | ((allele == oc.alt_allele ? 1u : 0u) << 31);
             }
         }
-        const int64_t dst = S.out_start + (int64_t)shuffle_slot(S.cell_off + j, S.cell_n, sp.shuffle);
+        const int64_t dst = S.out_start + (int64_t)shuffle_slot(S.cell_off + j, S.cell_n, S.inv_full, sp.shuffle);
         if (payload) {
             keys[dst] = key;
             payload[dst] = pl;
@@ -292,6 +342,17 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         hc[i].read_start = 0;
         hc[i].out_start = 0;
         hc[i].n_reads = 0;
+        {
+            // words w of the has_variant uniform that settle u53(w, .) < af on their own:
+            // w < af_lt: true whatever the low word; w >= af_ge: false whatever the low word
+            const double a = hc[i].af;
+            int64_t g = a <= 0.0 ? 0 : (a >= 1.0 ? (1ll << 32) : (int64_t)(a * 4294967296.0));
+            while (g > 0 && !(u53((uint32_t)(g - 1), 0xffffffffu) < a)) --g;
+            while (g < (1ll << 32) && u53((uint32_t)g, 0xffffffffu) < a) ++g;
+            hc[i].af_lt = g;
+            while (g < (1ll << 32) && u53((uint32_t)g, 0u) < a) ++g;
+            hc[i].af_ge = g;
+        }
         ho[i] = nf;
         nf += h_n_families[i] > 0 ? h_n_families[i] : 0;
     }
@@ -307,6 +368,19 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->fam_offsets.p, ho, 8 * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = plan->cell_tile_start.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
+    float h_cdf[128];
+    plan->has_size_cdf = sp->family_model == 1 && sp->mean_family_size <= 16.0;
+    if (plan->has_size_cdf) {
+        // fp32 Poisson cdf F[k] = P(X <= k), k < 96, by the pmf recurrence; padded so the search stops
+        const float lam = (float)sp->mean_family_size;
+        float p = expf(-lam), F = p;
+        for (int k = 0; k < 128; ++k) {
+            if (k > 0 && k < 96) { p *= lam / (float)k; F += p; }
+            h_cdf[k] = k < 96 ? F : 2.0f;
+        }
+        if (e == cudaSuccess) e = plan->size_cdf.alloc(ctx->stream, sizeof(h_cdf));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(plan->size_cdf.p, h_cdf, sizeof(h_cdf), cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
         free(hc); free(ho);
@@ -363,8 +437,9 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
     if (plan->n_fam <= 0) return PMRD_OK;
     PMRD_LAUNCH(ctx, reads_size_kernel, pmrd_blocks(plan->n_fam, 256), 256, 0, ctx->seed, plan->cells.as<ReadCell>(),
-                plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp, plan->fam_size.as<uint32_t>(),
-                plan->fam_word.as<uint32_t>());
+                plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
+                plan->has_size_cdf ? (const float*)plan->size_cdf.as<float>() : (const float*)nullptr,
+                plan->fam_size.as<uint32_t>(), plan->fam_word.as<uint32_t>());
     return exclusive_scan<uint32_t, uint64_t>(ctx, plan->fam_size.as<uint32_t>(), plan->read_offset.as<uint64_t>(), plan->n_fam,
                                               plan->total.as<uint64_t>());
 }

@@ -11,6 +11,7 @@ struct ReadCell {
     uint32_t n_reads;    // reads of the cell
     uint32_t group;
     uint32_t ref_allele, alt_allele;
+    int64_t af_lt, af_ge;  // has_variant threshold words (see draw_family)
 };
 
 #define READS_SEG_TILE 4096 /* == RS_TILE: cells are padded to whole sort tiles when segmented */
@@ -19,7 +20,8 @@ struct ReadCell {
 #define READS_IS_PAD_UMI(u) (((u) >> 24) == 0xffu)
 
 struct ReadPlan {
-    DevBuf cells, fam_offsets, fam_size, fam_word, read_offset, total, cell_tile_start;
+    DevBuf cells, fam_offsets, fam_size, fam_word, read_offset, total, cell_tile_start, size_cdf;
+    bool has_size_cdf = false;  // Poisson sizes with mean <= 16: inverted against an fp32 cdf table
     pmrd_read_sim_params sp;
     int64_t n_cells = 0;
     int64_t n_fam = 0;
