@@ -258,21 +258,24 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
 struct Vote {
     double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, total = 0.0;
     uint32_t order = 0, seen = 0, n_seen = 0;
-    __device__ __forceinline__ void add(uint32_t pl, int qthr) {
-        const uint32_t a = pl & 3u, q = (pl >> 2) & 63u;
-        if ((int)q >= qthr) {
-            const double w = c_wtab[q];
-            w0 = __dadd_rn(w0, a == 0 ? w : 0.0);
-            w1 = __dadd_rn(w1, a == 1 ? w : 0.0);
-            w2 = __dadd_rn(w2, a == 2 ? w : 0.0);
-            w3 = __dadd_rn(w3, a == 3 ? w : 0.0);
-            total = __dadd_rn(total, w);
-            if (!((seen >> a) & 1u)) {
-                seen |= 1u << a;
-                order |= n_seen << (2 * a);
-                ++n_seen;
-            }
-        }
+    // wt[q] = 10^(q/10) for q >= quality_threshold, else 0.0 (shared memory: the lanes of a warp look up
+    // different q, which a __constant__ table would serialise).  A read below the threshold adds +0.0 --
+    // the identity on these non-negative sums -- and sets no bit, so the walk is branch-free and still
+    // performs exactly the IEEE additions of the reference loop, in the same order.
+    __device__ __forceinline__ void add(uint32_t pl, const double* wt) {
+        const uint32_t a = pl & 3u;
+        const double w = wt[(pl >> 2) & 63u];
+        total = __dadd_rn(total, w);
+        asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+            "setp.eq.u32 p0, %4, 0;\n\tsetp.eq.u32 p1, %4, 1;\n\tsetp.eq.u32 p2, %4, 2;\n\tsetp.eq.u32 p3, %4, 3;\n\t"
+            "@p0 add.rn.f64 %0, %0, %5;\n\t@p1 add.rn.f64 %1, %1, %5;\n\t"
+            "@p2 add.rn.f64 %2, %2, %5;\n\t@p3 add.rn.f64 %3, %3, %5;\n\t}"
+            : "+d"(w0), "+d"(w1), "+d"(w2), "+d"(w3) : "r"(a), "d"(w));
+        const uint32_t bit = (__double2hiint(w) != 0 ? 1u : 0u) << a;   // w is 0.0 or >= 1
+        const uint32_t fresh = bit & ~seen;
+        order |= fresh ? n_seen << (2 * a) : 0u;
+        n_seen += fresh ? 1u : 0u;
+        seen |= bit;
     }
     // consensus allele, or -1 (umi.py:166-174)
     __device__ __forceinline__ int result(double cthr) const {
@@ -293,6 +296,45 @@ struct Vote {
 
 #define CC_THREADS 256
 #define CC_TILE 4096
+
+// The same walk with the four per-allele sums kept in shared memory (acc[a * CC_THREADS], one
+// column per thread): "sum[a] += w" is then one load, one DADD and one store instead of four
+// DADDs and four 64-bit selects -- the allele picks the address, not the instruction.
+struct VoteS {
+    double* acc;
+    double total = 0.0;
+    uint32_t order = 0, seen = 0, n_seen = 0;
+    __device__ __forceinline__ explicit VoteS(double* column) : acc(column) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a * CC_THREADS] = 0.0;
+    }
+    __device__ __forceinline__ void add(uint32_t pl, const double* wt) {
+        const uint32_t a = pl & 3u;
+        const double w = wt[(pl >> 2) & 63u];
+        total = __dadd_rn(total, w);
+        double* p = acc + a * CC_THREADS;
+        *p = __dadd_rn(*p, w);
+        const uint32_t bit = (__double2hiint(w) != 0 ? 1u : 0u) << a;   // w is 0.0 or >= 1
+        const uint32_t fresh = bit & ~seen;
+        order |= fresh ? n_seen << (2 * a) : 0u;
+        n_seen += fresh ? 1u : 0u;
+        seen |= bit;
+    }
+    __device__ __forceinline__ int result(double cthr) const {
+        if (n_seen == 0 || total == 0.0) return -1;
+        int best = -1;
+        double bw = -1.0;
+        uint32_t brank = 4;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            if (!((seen >> a) & 1u)) continue;
+            const double wa = acc[a * CC_THREADS];
+            const uint32_t rk = (order >> (2 * a)) & 3u;
+            if (wa > bw || (wa == bw && rk < brank)) { bw = wa; best = a; brank = rk; }
+        }
+        return (__ddiv_rn(bw, total) < cthr) ? -1 : best;
+    }
+};
 #define CC_ITEMS (CC_TILE / CC_THREADS)
 
 // Input: packed 8-byte records  rec = payload:32 | umi:32  in cell-major, tile-padded order,
@@ -306,15 +348,17 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
                       pmrd_umi_params P, uint32_t run_mask, int64_t cell0, const uint8_t* __restrict__ alt_allele,
                       unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot,
                       unsigned long long* __restrict__ o_var) {
-    __shared__ uint32_t s_umi[CC_TILE];   // split halves: the vote walks only the payloads (32-bit, half the
+    __shared__ __align__(16) uint32_t s_umi[CC_TILE];   // split halves: the vote walks only the payloads (32-bit, half the
     __shared__ uint32_t s_pl[CC_TILE];    // shared-memory traffic and bank conflicts of walking 64-bit records)
     __shared__ uint16_t s_head[CC_TILE];
     __shared__ uint32_t sw[33];
     __shared__ unsigned long long s_acc[3];
+    __shared__ double s_wt[64];
     __shared__ int s_cell;
     const int64_t tile = blockIdx.x;
     const int64_t base = tile * CC_TILE;
     if (threadIdx.x < 3) s_acc[threadIdx.x] = 0ull;
+    if (threadIdx.x < 64) s_wt[threadIdx.x] = (int)threadIdx.x >= P.quality_threshold ? c_wtab[threadIdx.x] : 0.0;
     if (threadIdx.x == 0) {   // which cell owns this tile
         int lo = 0, hi = n_cells;
         while (hi - lo > 1) {
@@ -348,18 +392,25 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     uint32_t r = block_exclusive_scan<uint32_t>(cnt, sw, n_heads);
 #pragma unroll
     for (int j = 0; j < CC_ITEMS; ++j)
-        if (flags & (1u << j)) s_head[r++] = (uint16_t)(i0 + j);
+        if (flags & (1u << j)) {
+            // FULL: bit 15 marks a run of padding reads (s_umi is recycled below)
+            const uint32_t pad = (FULL && (s_umi[i0 + j] >> 24) == 0xffu) ? 0x8000u : 0u;
+            s_head[r++] = (uint16_t)((uint32_t)(i0 + j) | pad);
+        }
     __syncthreads();
+    // FULL: the UMI halves are not needed past this point; their 16 KB now hold the votes' allele sums
+    double* const s_sum = reinterpret_cast<double*>(s_umi) + threadIdx.x;
     const uint32_t alt = alt_allele[cell0 + cell];
     uint32_t n_fam = 0, n_tot = 0, n_var = 0;
     for (uint32_t h = threadIdx.x; h < n_heads; h += CC_THREADS) {
-        const int lo = s_head[h];
-        const int hi = (h + 1 < n_heads) ? (int)s_head[h + 1] : CC_TILE;
+        const uint32_t hv = s_head[h];
+        const int lo = (int)(hv & 0xfffu);
+        const int hi = (h + 1 < n_heads) ? (int)(s_head[h + 1] & 0xfffu) : CC_TILE;
         const int n_in = hi - lo;
         // the tile's last run may continue into the next tile(s) of the same cell
         int64_t g_hi = base + CC_TILE;
         if (h + 1 == n_heads) {
-            const uint32_t rk = s_umi[lo] & run_mask;
+            const uint32_t rk = (FULL ? (uint32_t)rec[base + lo] : s_umi[lo]) & run_mask;
             while (g_hi < cell_hi && ((((uint32_t)rec[g_hi]) & run_mask) == rk)) ++g_hi;
         }
         const int len = n_in + (int)(g_hi - (base + CC_TILE));
@@ -367,11 +418,10 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         auto pl_at = [&](int i) -> uint32_t { return i < n_in ? s_pl[lo + i] : (uint32_t)(rec[base + CC_TILE + (i - n_in)] >> 32); };
         if (FULL) {
             // the sort ordered every UMI bit: a run IS a family
-            const uint32_t umi = s_umi[lo];
-            if ((umi >> 24) == 0xffu) continue;                  // padding of the tile-aligned cell
-            Vote v;
-            for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], P.quality_threshold);
-            for (int c = n_in; c < len; ++c) v.add(pl_at(c), P.quality_threshold);
+            if (hv & 0x8000u) continue;                          // padding of the tile-aligned cell
+            VoteS v(s_sum);
+            for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], s_wt);
+            for (int c = n_in; c < len; ++c) v.add(pl_at(c), s_wt);
             ++n_fam;
             if (len >= P.min_family_size) {
                 const int best = v.result(P.consensus_threshold);
@@ -404,7 +454,7 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
             Vote v;
             uint32_t size = 0;
             for (int c = a; c < len; ++c)
-                if (umi_at(c) == umi) { v.add(pl_at(c), P.quality_threshold); ++size; }
+                if (umi_at(c) == umi) { v.add(pl_at(c), s_wt); ++size; }
             ++n_fam;
             if ((int)size >= P.min_family_size) {
                 const int best = v.result(P.consensus_threshold);
