@@ -63,6 +63,7 @@ int64_t pmrd_profile_report(pmrd_ctx* ctx, char* buf, int64_t cap);
 /* alternative */
 #define PMRD_ALT_TWO_SIDED 0 /* G-D: 2*min(cdf(k), sf(k-1)) / scipy binomtest "minlike"  */
 #define PMRD_ALT_GREATER 1   /* G-B: stats.py:47-133  1 - cdf(k-1) / binomtest 'greater' */
+#define PMRD_ALT_LESS 2      /* G-B: stats.py:61-63   cdf(k)       / binomtest 'less'    */
 
 /* p[i] = test(k[i], n[i], rate[i]).  Poisson: expected = n[i]*rate[i] is formed on the
  * device exactly as call.py:179 does (one IEEE multiply); pass n=NULL to give `rate`
@@ -209,6 +210,13 @@ typedef struct pmrd_cell_table {
 int32_t pmrd_simulate_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
                             const int64_t* h_depth, int64_t n_cells, int32_t max_family_size,
                             pmrd_cell_table* h_out);
+/* StratifiedAnalyzer._simulate_with_context (src/precise_mrd/eval/stratified.py:180-203): the same
+ * draws with a per-cell trinucleotide-context multiplier m (CpG 1.5, CHG 1.2, CHH 1.0, NpN 0.8):
+ * background_rate *= m, and n_false_positives ~ Binom(depth - n_true, background_rate * m) -- the
+ * reference applies m twice (:193 and :199).  h_bg_multiplier == NULL: m = 1 everywhere. */
+int32_t pmrd_simulate_cells_stratified(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
+                                       const int64_t* h_depth, const double* h_bg_multiplier,
+                                       int64_t n_cells, int32_t max_family_size, pmrd_cell_table* h_out);
 
 /* ---------------------------------------------------------------- K2: G-D families -- */
 /* collapse_umis (src/precise_mrd/collapse.py:70-118): per (cell, family) Philox draws.

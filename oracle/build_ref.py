@@ -22,8 +22,9 @@ Layouts produced:
                                    missing ``performance`` symbols and the two missing
                                    ``advanced_stats`` symbols
   oracle/_ref/ga/mrd/              G-A read-level package (precise-mrd-mini/src/mrd)
-  oracle/_ref/gb/precise_mrd_gb/   G-B read-level modules io/umi (validation stubbed)
-  oracle/_ref/stubs/               matplotlib / seaborn stand-ins (PNG writers only)
+  oracle/_ref/gb/precise_mrd_gb/   G-B read-level modules io/umi/context/errors/stats (validation stubbed)
+  oracle/_ref/stubs/               matplotlib / seaborn stand-ins (PNG writers only); statsmodels.multipletests
+                                   stand-in backed by oracle/port.py
 """
 from __future__ import annotations
 
@@ -95,8 +96,8 @@ def build_ga() -> None:
 def build_gb() -> None:
     src = REF / "src" / "precise_mrd"
     pkg = OUT / "gb" / "precise_mrd_gb"
-    _link(src / "io.py", pkg / "io.py")
-    _link(src / "umi.py", pkg / "umi.py")
+    for name in ("io", "umi", "context", "errors", "stats"):
+        _link(src / f"{name}.py", pkg / f"{name}.py")
     _write(pkg / "__init__.py", "")
     # umi.py:16 imports a validate_umi_output that exists nowhere in the tree
     _write(pkg / "validation.py", "def validate_umi_output(df):\n    return True\n")
@@ -118,6 +119,17 @@ def build_stubs() -> None:
         "def __getattr__(n): return _Any()\n",
     )
     _write(st / "seaborn" / "__init__.py", "def __getattr__(n):\n    return lambda *a, **k: None\n")
+    # statsmodels is not installed: stats.py:15 imports multipletests; the stand-in is the
+    # restatement of its three methods in oracle/port.py
+    _write(st / "statsmodels" / "__init__.py", "")
+    _write(st / "statsmodels" / "stats" / "__init__.py", "")
+    _write(
+        st / "statsmodels" / "stats" / "multitest.py",
+        "from oracle import port as _port\n\n"
+        "def multipletests(pvals, alpha=0.05, method='hs', **k):\n"
+        "    reject, corrected = _port.multipletests(pvals, alpha, method)\n"
+        "    return reject, corrected, None, None\n",
+    )
 
 
 def main() -> int:

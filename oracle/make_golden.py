@@ -15,6 +15,8 @@ parity tests can run where the reference cannot travel.
   ga_reads.npz                            G-A reads -> mrd.umi.collapse_reads (== tmp/families.parquet)
   gc_reads.npz                            G-C reads -> committed collapsed_umis / mrd_calls tables
   gb_reads.npz                            G-B SyntheticReadGenerator reads -> UMIProcessor(max_edit_distance=0)
+  gb_stats.json                           G-B StatisticalTester (one-sided tests, CIs, BH/Bonferroni/Holm),
+                                          ContextAnalyzer and ErrorModel on seeded inputs
   lod_fit.npz                             LODAnalyzer._fit_detection_curve/_bootstrap_lod_ci on given vectors
   gd_dist.npz                             distribution samples from the reference simulate/collapse (KS targets)
 """
@@ -258,6 +260,92 @@ def golden_gb() -> None:
     print("  wrote gb_reads.npz", len(reads), "reads", len(fams), "families", len(kept), "kept")
 
 
+# ------------------------------------------------------------------------------- G-B stats / context / errors
+def golden_gb_stats() -> None:
+    """StatisticalTester (one-sided tests, BH / Bonferroni / Holm), ContextAnalyzer and ErrorModel
+    of the reference, run on seeded inputs -> tests/golden/gb_stats.json (text: it holds strings)."""
+    import json
+
+    sys.path.insert(0, str(HERE.parent))                 # the statsmodels stand-in imports oracle.port
+    sys.path.insert(0, str(HERE / "_ref" / "stubs"))
+    sys.path.insert(0, str(HERE / "_ref" / "gb"))
+    from precise_mrd_gb.context import ContextAnalyzer
+    from precise_mrd_gb.errors import ErrorModel
+    from precise_mrd_gb.stats import StatisticalTester
+
+    rng = np.random.default_rng(2024)
+    out = {}
+    # scalar tests, every alternative
+    rows = []
+    for test in ("poisson", "binomial"):
+        t = StatisticalTester(test_type=test)
+        for _ in range(60):
+            n = int(rng.integers(1, 60000))
+            rate = float(10 ** rng.uniform(-6, -1))
+            k = int(min(n, rng.poisson(n * rate * rng.choice([0.3, 1.0, 3.0, 10.0]))))
+            for alt in ("greater", "less", "two-sided"):
+                if test == "poisson":
+                    r = t.poisson_test(k, rate * n, alternative=alt)
+                    ci = None
+                else:
+                    r = t.binomial_test(k, n, rate, alternative=alt)
+                    ci = [float(r.confidence_interval.low), float(r.confidence_interval.high)]
+                rows.append({"test": test, "k": k, "n": n, "rate": rate, "alternative": alt, "statistic": float(r.statistic),
+                             "pvalue": float(r.pvalue), "effect_size": None if r.effect_size is None else float(r.effect_size),
+                             "ci": ci})
+    rows.append({"test": "poisson", "k": 3, "n": 10, "rate": 0.0, "alternative": "greater", "statistic": 3.0, "pvalue":
+                 float(StatisticalTester().poisson_test(3, 0.0).pvalue), "effect_size": None, "ci": None})
+    out["scalar"] = rows
+    # test_multiple_variants, both test types
+    contexts = ["ACG", "CCG", "TCA", "GCA", "default"]
+    m = 400
+    depth = rng.integers(200, 80000, m)
+    ctx = rng.choice(contexts + ["ZZZ"], m)
+    rates = {"ACG": 3e-4, "CCG": 1e-4, "TCA": 5e-5, "GCA": 2.5e-4, "default": 1e-4}
+    lam = depth * np.array([rates.get(c, 1e-4) for c in ctx]) * rng.choice([1.0, 1.0, 1.0, 4.0, 12.0], m)
+    alt_count = np.minimum(rng.poisson(lam), depth)
+    table = pd.DataFrame({"site_key": [f"chr1:{1000 + i}:A" for i in range(m)], "context": ctx, "alt_count": alt_count,
+                          "total_depth": depth})
+    out["table"] = {"site_key": table.site_key.tolist(), "context": table.context.tolist(),
+                    "alt_count": [int(v) for v in alt_count], "total_depth": [int(v) for v in depth], "rates": rates}
+    for test in ("poisson", "binomial"):
+        res = StatisticalTester(test_type=test, alpha=0.05).test_multiple_variants(table, rates)
+        out[f"multi_{test}"] = {c: (res[c].astype(float).tolist() if res[c].dtype.kind in "fiub" else [str(v) for v in res[c]])
+                                for c in res.columns}
+    # multiple_testing_correction, three methods
+    p = np.concatenate([rng.uniform(0, 1, 150), 10 ** rng.uniform(-9, -2, 50)])
+    out["mtc"] = {"p": p.tolist()}
+    for method in ("benjamini_hochberg", "bonferroni", "holm"):
+        rej, q = StatisticalTester(alpha=0.05).multiple_testing_correction(p.tolist(), method)
+        out["mtc"][method] = {"rejected": [bool(v) for v in rej], "corrected": [float(v) for v in q]}
+    # ContextAnalyzer
+    bases = "ACGT"
+    norm = []
+    for a in bases:
+        for b in bases:
+            for c in bases:
+                for r in bases:
+                    for al in bases:
+                        norm.append([a + b + c, r, al, *ContextAnalyzer.normalize_context(a + b + c, r, al)])
+    out["normalize"] = norm
+    n_rows = 600
+    cons = pd.DataFrame({
+        "context": rng.choice([x + y + z for x in bases for y in bases for z in bases], n_rows),
+        "ref": rng.choice(list(bases), n_rows), "allele": rng.choice(list(bases), n_rows),
+        "consensus_count": rng.integers(1, 5000, n_rows)})
+    an = ContextAnalyzer()
+    rates_est = an.estimate_context_error_rates(cons)
+    lookups = [["ACG", "C", "T"], ["CGT", "G", "A"], ["TTT", "T", "G"], ["AAA", "A", "C"], ["GCA", "C", "A"], ["NCN", "C", "T"]]
+    out["context"] = {"table": {c: ([int(v) for v in cons[c]] if c == "consensus_count" else [str(v) for v in cons[c]]) for c in cons.columns},
+                      "rates": rates_est, "lookups": [[*q, float(an.get_expected_error_rate(*q))] for q in lookups],
+                      "lookup_unfitted": float(ContextAnalyzer().get_expected_error_rate("ACG", "C", "T"))}
+    em = ErrorModel()
+    out["background"] = {"min_depth": 100, "rates": em.estimate_background_errors(cons, min_depth=100)}
+    with open(OUT / "gb_stats.json", "w") as f:
+        json.dump(out, f)
+    print("  wrote gb_stats.json", len(rows), "scalar rows,", m, "loci")
+
+
 # ------------------------------------------------------------------------------- LoD fit
 def golden_lod_fit() -> None:
     _import_ref("gd_v1")
@@ -331,7 +419,8 @@ def main() -> int:
     only = set(sys.argv[1:])
     steps = {
         "call": lambda: (golden_call("gd_v1", "det_a", "call_smoke_v1.npz"), golden_call("gd_v2", "smoke", "call_smoke_v2.npz")),
-        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "lod": golden_lod_fit,
+        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbstats": golden_gb_stats,
+        "lod": golden_lod_fit,
         "dist": golden_gd_dist,
     }
     for name, fn in steps.items():

@@ -459,20 +459,28 @@ int32_t pmrd_umi_hamming(pmrd_ctx* ctx, const uint32_t* h_a, const uint32_t* h_b
 // ---------------------------------------------------------------- K1 --------------------
 int32_t pmrd_simulate_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_depth,
                             int64_t n_cells, int32_t max_family_size, pmrd_cell_table* h_out) {
+    return pmrd_simulate_cells_stratified(ctx, h_cell_id, h_af, h_depth, nullptr, n_cells, max_family_size, h_out);
+}
+
+int32_t pmrd_simulate_cells_stratified(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_depth,
+                                       const double* h_bg_multiplier, int64_t n_cells, int32_t max_family_size,
+                                       pmrd_cell_table* h_out) {
     ENTER(ctx);
     PMRD_ARG(ctx, n_cells >= 0, "n_cells");
     if (n_cells == 0) return PMRD_OK;
     PMRD_ARG(ctx, h_cell_id && h_af && h_depth && h_out, "null buffer");
     const size_t c = (size_t)n_cells;
-    DevBuf id, af, dp, bg, mfs, nt, nfp, mq;
+    DevBuf id, af, dp, bg, mfs, nt, nfp, mq, mult;
     PMRD_TRY(up(ctx, id, h_cell_id, c * 8));
     PMRD_TRY(up(ctx, af, h_af, c * 8));
     PMRD_TRY(up(ctx, dp, h_depth, c * 8));
+    if (h_bg_multiplier) PMRD_TRY(up(ctx, mult, h_bg_multiplier, c * 8));
     PMRD_CUDA(ctx, bg.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, mfs.alloc(ctx->stream, c * 8));
     PMRD_CUDA(ctx, nt.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, nfp.alloc(ctx->stream, c * 8));
     PMRD_CUDA(ctx, mq.alloc(ctx->stream, c * 8));
     pmrd_cell_table d{bg.as<double>(), mfs.as<int64_t>(), nt.as<int64_t>(), nfp.as<int64_t>(), mq.as<double>()};
-    PMRD_TRY(k1_simulate_cells(ctx, id.as<int64_t>(), af.as<double>(), dp.as<int64_t>(), n_cells, max_family_size, &d));
+    PMRD_TRY(k1_simulate_cells(ctx, id.as<int64_t>(), af.as<double>(), dp.as<int64_t>(),
+                               h_bg_multiplier ? (const double*)mult.as<double>() : (const double*)nullptr, n_cells, max_family_size, &d));
     PMRD_TRY(down(ctx, h_out->background_rate, d.background_rate, c * 8));
     PMRD_TRY(down(ctx, h_out->mean_family_size, d.mean_family_size, c * 8));
     PMRD_TRY(down(ctx, h_out->n_true_variants, d.n_true_variants, c * 8));

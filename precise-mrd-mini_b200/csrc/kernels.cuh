@@ -19,4 +19,4 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
 
 // simulate.cu
 int32_t k1_simulate_cells(pmrd_ctx* ctx, const int64_t* d_cell_id, const double* d_af, const int64_t* d_depth,
-                          int64_t n_cells, int32_t max_family_size, const pmrd_cell_table* d_out);
+                          const double* d_bg_mult, int64_t n_cells, int32_t max_family_size, const pmrd_cell_table* d_out);

@@ -18,10 +18,12 @@ pvalues_kernel(const int64_t* __restrict__ k, const int64_t* __restrict__ n, con
     if (test_type == PMRD_TEST_POISSON) {
         // call.py:179 expected = n_total * mean_error_rate: one IEEE multiply, no contraction
         const double expected = n ? __dmul_rn((double)n[i], r) : r;
-        out = alternative == PMRD_ALT_TWO_SIDED ? pmrd_poisson_two_sided(ki, expected) : pmrd_poisson_greater(ki, expected);
+        out = alternative == PMRD_ALT_TWO_SIDED ? pmrd_poisson_two_sided(ki, expected)
+              : alternative == PMRD_ALT_GREATER ? pmrd_poisson_greater(ki, expected) : pmrd_poisson_less(ki, expected);
     } else {
         const int64_t ni = n[i];
-        out = alternative == PMRD_ALT_TWO_SIDED ? pmrd_binomial_two_sided(ki, ni, r) : pmrd_binomial_greater(ki, ni, r);
+        out = alternative == PMRD_ALT_TWO_SIDED ? pmrd_binomial_two_sided(ki, ni, r)
+              : alternative == PMRD_ALT_GREATER ? pmrd_binomial_greater(ki, ni, r) : pmrd_binomial_less(ki, ni, r);
     }
     p[i] = out;
 }
@@ -29,7 +31,8 @@ pvalues_kernel(const int64_t* __restrict__ k, const int64_t* __restrict__ n, con
 int32_t k8_pvalues(pmrd_ctx* ctx, const int64_t* d_k, const int64_t* d_n, const double* d_rate, int64_t rate_stride,
                    int64_t m, int32_t test_type, int32_t alternative, double* d_p) {
     PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || test_type == PMRD_TEST_BINOMIAL, "Unknown test type");
-    PMRD_ARG(ctx, alternative == PMRD_ALT_TWO_SIDED || alternative == PMRD_ALT_GREATER, "unknown alternative");
+    PMRD_ARG(ctx, alternative == PMRD_ALT_TWO_SIDED || alternative == PMRD_ALT_GREATER || alternative == PMRD_ALT_LESS,
+             "unknown alternative");
     PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || d_n != nullptr, "binomial test needs n");
     if (m <= 0) return PMRD_OK;
     PMRD_LAUNCH(ctx, pvalues_kernel, pmrd_blocks(m, 128), 128, 0, d_k, d_n, d_rate, rate_stride, m, test_type, alternative, d_p);

@@ -13,7 +13,8 @@
 // ---------------------------------------------------------------- K1 --------------------
 __global__ void __launch_bounds__(128)
 sim_cells_kernel(uint64_t seed, const int64_t* __restrict__ cell_id, const double* __restrict__ af,
-                 const int64_t* __restrict__ depth, int64_t n_cells, int max_family_size, pmrd_cell_table out) {
+                 const int64_t* __restrict__ depth, const double* __restrict__ bg_mult /* or NULL */, int64_t n_cells,
+                 int max_family_size, pmrd_cell_table out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cells) return;
     const Philox ph(seed);
@@ -21,14 +22,19 @@ sim_cells_kernel(uint64_t seed, const int64_t* __restrict__ cell_id, const doubl
     const uint32_t c2 = (uint32_t)cid, c3 = (PMRD_STREAM_CELLS << 24) | (uint32_t)((cid >> 32) & 0xffffffu);
     const uint4 b0 = ph(0, 0, c2, c3), b1 = ph(1, 0, c2, c3), b2 = ph(2, 0, c2, c3);
     // simulate.py:144  background_rates = rng.uniform(1e-5, 1e-3)
-    const double bg = 1e-5 + (1e-3 - 1e-5) * u53(b0.x, b0.y);
+    double bg = 1e-5 + (1e-3 - 1e-5) * u53(b0.x, b0.y);
+    // eval/stratified.py:186-201: the context multiplier scales the stored rate, and the false
+    // positives are drawn at rate * multiplier again (the reference applies it twice)
+    const double m = bg_mult ? bg_mult[i] : 1.0;
+    bg *= m;
+    const double fp_rate = fmin(bg * m, 1.0);
     // simulate.py:147-148  clip(poisson(5), 1, max_family_size)
     int fs = sample_poisson_small(u53(b0.z, b0.w), 5.0);
     fs = fs < 1 ? 1 : (fs > max_family_size ? max_family_size : fs);
     // simulate.py:152,155-158
     const int64_t d = depth[i];
     const int64_t n_true = sample_binomial(u53(b1.x, b1.y), d, af[i]);
-    const int64_t n_fp = sample_binomial(u53(b1.z, b1.w), d - n_true, bg);
+    const int64_t n_fp = sample_binomial(u53(b1.z, b1.w), d - n_true, fp_rate);
     // simulate.py:161-162  clip(normal(25, 5), 10, 40)
     double q = 25.0 + 5.0 * sample_normal(u53(b2.x, b2.y), u53(b2.z, b2.w));
     q = fmin(fmax(q, 10.0), 40.0);
@@ -40,10 +46,10 @@ sim_cells_kernel(uint64_t seed, const int64_t* __restrict__ cell_id, const doubl
 }
 
 int32_t k1_simulate_cells(pmrd_ctx* ctx, const int64_t* d_cell_id, const double* d_af, const int64_t* d_depth,
-                          int64_t n_cells, int32_t max_family_size, const pmrd_cell_table* d_out) {
+                          const double* d_bg_mult, int64_t n_cells, int32_t max_family_size, const pmrd_cell_table* d_out) {
     if (n_cells <= 0) return PMRD_OK;
-    PMRD_LAUNCH(ctx, sim_cells_kernel, pmrd_blocks(n_cells, 128), 128, 0, ctx->seed, d_cell_id, d_af, d_depth, n_cells,
-                max_family_size, *d_out);
+    PMRD_LAUNCH(ctx, sim_cells_kernel, pmrd_blocks(n_cells, 128), 128, 0, ctx->seed, d_cell_id, d_af, d_depth, d_bg_mult,
+                n_cells, max_family_size, *d_out);
     return PMRD_OK;
 }
 

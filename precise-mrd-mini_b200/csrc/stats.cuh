@@ -145,6 +145,15 @@ __host__ __device__ static inline double pmrd_poisson_greater(int64_t observed, 
     return hi;
 }
 
+// stats.py:61-63 alternative == "less": cdf(k)
+__host__ __device__ static inline double pmrd_poisson_less(int64_t observed, double expected) {
+    if (observed < 0) return 0.0;
+    if (!(expected > 0.0)) return 1.0;
+    double lo, hi;
+    pmrd_pois_tails((double)observed, expected, &lo, &hi);
+    return lo;
+}
+
 // Binomial point mass P(X = x | n, p), integers 0 <= x <= n, 0 < p < 1
 __host__ __device__ static inline double pmrd_dbinom(double x, double n, double p) {
     const double q = 1.0 - p;
@@ -237,6 +246,13 @@ __host__ __device__ static inline double pmrd_binomial_two_sided(int64_t k_, int
         pval = pmrd_binom_cdf(y - 1.0, n, p) + pmrd_binom_sf(k - 1.0, n, p);
     }
     return pval < 1.0 ? pval : 1.0;
+}
+// stats.py:109-114 binomtest(alternative='less') = cdf(k)
+__host__ __device__ static inline double pmrd_binomial_less(int64_t k_, int64_t n_, double p) {
+    if (n_ == 0) return 1.0;
+    if (p <= 0.0) return 1.0;
+    if (p >= 1.0) return k_ < n_ ? 0.0 : 1.0;
+    return pmrd_binom_cdf((double)k_, (double)n_, p);
 }
 // stats.py:109-114 binomtest(alternative='greater') = sf(k-1)
 __host__ __device__ static inline double pmrd_binomial_greater(int64_t k_, int64_t n_, double p) {

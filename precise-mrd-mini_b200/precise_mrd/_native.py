@@ -19,7 +19,7 @@ LIB_PATH = Path(os.environ.get("PMRD_B200_LIB", _PKG_ROOT / "lib" / "libpmrd_b20
 PMRD_OK = 0
 ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_NO_DEVICE = -1, -2, -3, -4
 TEST_POISSON, TEST_BINOMIAL = 0, 1
-ALT_TWO_SIDED, ALT_GREATER = 0, 1
+ALT_TWO_SIDED, ALT_GREATER, ALT_LESS = 0, 1, 2
 MODE_WEIGHTED, MODE_MAJORITY, MODE_COUNT = 0, 1, 2
 CLUSTER_EXACT, CLUSTER_FIRSTFIT = 0, 1
 FAM_HAS_CONSENSUS, FAM_KEPT, FAM_OVERSIZE = 1, 2, 4
@@ -279,17 +279,19 @@ class Context:
 
 
     # -- K1 ------------------------------------------------------------------------------
-    def simulate_cells(self, cell_id, af, depth, max_family_size: int) -> Dict[str, np.ndarray]:
+    def simulate_cells(self, cell_id, af, depth, max_family_size: int, bg_multiplier=None) -> Dict[str, np.ndarray]:
         cell_id = _arr(cell_id, np.int64)
         af = _arr(af, np.float64)
         depth = _arr(depth, np.int64)
         c = cell_id.shape[0]
+        mult = None if bg_multiplier is None else _arr(np.broadcast_to(bg_multiplier, (c,)), np.float64)
         out = {"background_rate": np.zeros(c), "mean_family_size": np.zeros(c, np.int64),
                "n_true_variants": np.zeros(c, np.int64), "n_false_positives": np.zeros(c, np.int64),
                "mean_quality": np.zeros(c)}
         t = CellTable(*[out[n].ctypes.data for n, _ in CellTable._fields_])
-        self._check(self.lib.pmrd_simulate_cells(self.h, _ptr(cell_id), _ptr(af), _ptr(depth), C.c_int64(c),
-                                                 C.c_int32(max_family_size), C.byref(t)))
+        self._check(self.lib.pmrd_simulate_cells_stratified(self.h, _ptr(cell_id), _ptr(af), _ptr(depth),
+                                                            None if mult is None else _ptr(mult), C.c_int64(c),
+                                                            C.c_int32(max_family_size), C.byref(t)))
         return out
 
     # -- K2 (G-D) ------------------------------------------------------------------------

@@ -1,10 +1,11 @@
 """MRD calling -- drop-in for ``src/precise_mrd/call.py`` (statistical branch).
 
-``call_mrd`` runs K7 (per-sample segmented counts and fp64 means), K8 (two-sided Poisson /
-binomial tail p-values) and K9 (Benjamini-Hochberg: device radix sort + reverse running-min
-scan) through ``pmrd_call``; the scalar helpers go through ``pmrd_pvalues`` / ``pmrd_bh``.
-Adds the ``variant_call`` column every ``eval-*`` consumer indexes but no reference producer
-emits: ``variant_call == significant``."""
+``call_mrd`` dispatches to a ``VariantCaller`` plugin (``models/``); the statistical one runs K7
+(per-sample segmented counts and fp64 means), K8 (two-sided Poisson / binomial tail p-values)
+and K9 (Benjamini-Hochberg: device radix sort + reverse running-min scan) through ``pmrd_call``;
+the scalar helpers go through ``pmrd_pvalues`` / ``pmrd_bh``.  The result carries the
+``variant_call`` column every ``eval-*`` consumer indexes but no reference producer emits
+(SURVEY.md §0.3-2): ``variant_call == significant``."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
@@ -13,7 +14,7 @@ import numpy as np
 import pandas as pd
 
 from . import _native as nv
-from .config import section
+from .models import B200StatisticalVariantCaller, VariantCaller
 
 
 def poisson_test(observed: int, expected: float) -> float:
@@ -34,48 +35,23 @@ def benjamini_hochberg_correction(p_values: np.ndarray, alpha: float) -> Tuple[n
     return nv.default_context().bh(p_values, float(alpha))
 
 
-def call_mrd(collapsed_df: pd.DataFrame, error_model_df: pd.DataFrame, config, rng: np.random.Generator,
-             output_path: Optional[str] = None, use_ml_calling: bool = False) -> pd.DataFrame:
-    if use_ml_calling:
+def get_variant_caller(config, use_ml_calling: bool = False, ml_model_type: str = "ensemble",
+                       use_deep_learning: bool = False, dl_model_type: str = "cnn_lstm") -> VariantCaller:
+    """Factory of ``precise_mrd/call.py:21-34``.  The ML / deep-learning callers are outside the
+    B200 hot path; a third-party ``VariantCaller`` subclass can be used directly."""
+    if use_ml_calling or use_deep_learning:
         raise NotImplementedError("ML-based calling is outside the B200 hot path (SURVEY.md §2.5)")
-    st = section(config, "stats")
-    test_type, alpha, fdr_method = st["test_type"], float(st["alpha"]), st["fdr_method"]
-    if test_type not in nv.TEST_TYPES:
-        raise ValueError(f"Unknown test type: {test_type}")                     # call.py:187
-    if len(collapsed_df) == 0:
-        return pd.DataFrame()                                                   # call.py:214-215
-    # call.py:161: samples in first-appearance order; rows of a sample need not be contiguous
-    codes, uniques = pd.factorize(collapsed_df["sample_id"], sort=False)
-    is_variant = collapsed_df["is_variant"].values.astype(np.uint8)
-    quality = collapsed_df["quality_score"].values.astype(np.float64)
-    agreement = collapsed_df["consensus_agreement"].values.astype(np.float64)
-    af = collapsed_df["allele_fraction"].values
-    if (np.diff(codes) < 0).any():
-        order = np.argsort(codes, kind="stable")
-        codes, is_variant, quality, agreement, af = codes[order], is_variant[order], quality[order], agreement[order], af[order]
-    seg = np.concatenate([[0], np.flatnonzero(np.diff(codes)) + 1, [len(codes)]]).astype(np.int64)
-    mean_error_rate = float(error_model_df["error_rate"].mean())                # call.py:178
-    ctx = nv.default_context()
-    out = ctx.call(seg, is_variant, quality, agreement, mean_error_rate, nv.TEST_TYPES[test_type], alpha)
-    df = pd.DataFrame({
-        "sample_id": np.asarray(uniques),
-        "allele_fraction": af[seg[:-1]],
-        "n_variants": out["n_variants"],
-        "n_total": out["n_total"],
-        "variant_fraction": out["variant_fraction"],
-        "expected_variants": out["expected_variants"],
-        "fold_change": out["fold_change"],
-        "p_value": out["p_value"],
-        "mean_quality": out["mean_quality"],
-        "mean_consensus": out["mean_consensus"],
-        "test_type": test_type,
-        "config_hash": config.config_hash(),
-        "p_adjusted": out["p_adjusted"],
-        "significant": out["significant"],
-        "alpha": alpha,
-        "fdr_method": fdr_method,
-    })
-    df["variant_call"] = df["significant"]
+    return B200StatisticalVariantCaller(config)
+
+
+def call_mrd(collapsed_df: pd.DataFrame, error_model_df: pd.DataFrame, config, rng: np.random.Generator,
+             output_path: Optional[str] = None, use_ml_calling: bool = False, ml_model_type: str = "ensemble",
+             use_deep_learning: bool = False, dl_model_type: str = "cnn_lstm") -> pd.DataFrame:
+    """Dispatch to the pluggable caller (train is a no-op for the statistical one), write parquet
+    iff ``output_path``."""
+    caller = get_variant_caller(config, use_ml_calling, ml_model_type, use_deep_learning, dl_model_type)
+    caller.train(collapsed_df, rng)
+    df = caller.predict(collapsed_df, error_model_df)
     if output_path:
         df.to_parquet(output_path, index=False)
     return df

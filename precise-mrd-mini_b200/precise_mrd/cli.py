@@ -2,7 +2,7 @@
 
     precise-mrd [--seed S] [--config C] smoke [--out-dir D]
     precise-mrd ... determinism | eval-lob [--n-blank N] | eval-lod [--replicates R]
-                   | eval-loq [--replicates R] | eval-contamination
+                   | eval-loq [--replicates R] | eval-contamination | eval-stratified
 
 Group options come BEFORE the sub-command; artifacts go to ``reports/`` and ``data/`` under the
 current directory; every command ends by echoing a JSON summary.  ``--engine grid`` switches the
@@ -21,7 +21,7 @@ import click
 from .config import LODConfig, PipelineConfig, SimulationConfig, StatsConfig, UMIConfig, load_config
 from .determinism_utils import env_fingerprint, set_global_seed, write_manifest
 from .utils import PipelineIO, json_ready
-from .validation import assert_hashes_stable, validate_artifacts
+from .validation import assert_hashes_stable, validate_artifacts, validate_json
 
 DEFAULT_CONFIG = Path(__file__).resolve().parent / "assets" / "configs" / "smoke.yaml"
 REPORTS_DIR = Path("reports")
@@ -197,6 +197,23 @@ def eval_contamination_cmd(ctx: CLIContext) -> None:
     PipelineIO.ensure_dir(REPORTS_DIR)
     run_contamination_stress_test(config, rng, output_dir=str(REPORTS_DIR), engine=ctx.engine)
     _echo("eval-contamination", ctx, contam=REPORTS_DIR / "contam_sensitivity.json", heatmap=REPORTS_DIR / "contam_heatmap.png")
+
+
+@main.command("eval-stratified")
+@click.pass_obj
+def eval_stratified_cmd(ctx: CLIContext) -> None:
+    """Conduct stratified power and calibration analysis (cli.py:354-374)."""
+    from .eval.stratified import run_stratified_analysis
+
+    config = _load_pipeline_config(ctx.config_override, ctx.seed)
+    rng = set_global_seed(ctx.seed, deterministic_ops=True)
+    PipelineIO.ensure_dir(REPORTS_DIR)
+    power, _ = run_stratified_analysis(config, rng, output_dir=str(REPORTS_DIR))
+    validate_json(REPORTS_DIR / "power_by_stratum.json", "power.schema.json")
+    validate_json(REPORTS_DIR / "calibration_by_bin.json", "calibration.schema.json")
+    click.echo(json.dumps({"stage": "eval-stratified", "power_results": str(REPORTS_DIR / "power_by_stratum.json"),
+                           "calibration_csv": str(REPORTS_DIR / "calibration_by_bin.csv"),
+                           "contexts": power.get("contexts", []), "depths": power.get("depth_values", [])}, indent=2))
 
 
 def cli() -> None:  # pragma: no cover

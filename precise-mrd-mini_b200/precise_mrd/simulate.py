@@ -13,10 +13,12 @@ from .config import section
 
 
 def simulate_reads(config, rng: np.random.Generator, output_path: Optional[str] = None, use_cache: bool = True,
-                   chunked_processing: bool = False) -> pd.DataFrame:
+                   chunked_processing: bool = False, background_multiplier: Optional[float] = None) -> pd.DataFrame:
     """Same signature as the reference.  ``use_cache`` / ``chunked_processing`` are accepted and
     ignored: the reference's 1-hour TTL cache silently changes later draws and
-    the chunked branch only exists to bound host memory."""
+    the chunked branch only exists to bound host memory.  ``background_multiplier`` (not in the
+    reference signature) is the trinucleotide-context factor of ``eval/stratified.py:180-203``,
+    applied inside the kernel."""
     sim = section(config, "simulation")
     umi = section(config, "umi")
     afs, depths, n_rep = sim["allele_fractions"], sim["umi_depths"], int(sim["n_replicates"])
@@ -27,7 +29,8 @@ def simulate_reads(config, rng: np.random.Generator, output_path: Optional[str] 
     print(f"  Simulating {total:,} samples with {len(afs)} AF levels, {len(depths)} depths, {n_rep} replicates")
     ctx = stage_context(config, rng)
     sample_ids = np.arange(total, dtype=np.int64)
-    cells = ctx.simulate_cells(sample_ids, af_flat, depth_flat, int(umi["max_family_size"]))
+    cells = ctx.simulate_cells(sample_ids, af_flat, depth_flat, int(umi["max_family_size"]),
+                               bg_multiplier=background_multiplier)
     df = pd.DataFrame({
         "sample_id": sample_ids,
         "allele_fraction": af_flat,

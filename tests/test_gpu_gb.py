@@ -1,0 +1,227 @@
+"""GPU tests of the G-B surface and the stratified / plugin rows of SURVEY.md §8a (a11, a12, a15)
+and §8b (``VariantCaller`` seam): every tail, BH and draw runs in the CUDA library; expectations
+are vectors produced by RUNNING the reference (``tests/golden/gb_stats.json``) or, for the
+Monte-Carlo generators, its distributions."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+from scipy import stats as sps
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+PKG_DIR = ROOT / "precise-mrd-mini_b200"
+GOLD = json.loads((ROOT / "tests" / "golden" / "gb_stats.json").read_text())
+ALPHA = 1e-3
+
+
+@pytest.fixture(scope="module")
+def smoke_cfg():
+    from precise_mrd.config import load_config
+
+    cfg = load_config(PKG_DIR / "precise_mrd" / "assets" / "configs" / "smoke.yaml")
+    cfg.seed = 7
+    return cfg
+
+
+def _close(got, want, poisson_upper, n=0):
+    # stats.py:66,74 form the Poisson upper tail as 1 - cdf(k-1) (absolute error ~1e-16); the device
+    # evaluates the survival function -- see tests/test_gb_host.py.  Beyond n = 2e4 SciPy's incomplete
+    # beta is itself only good to ~1e-11 (mpmath check in tests/test_gpu_parity.py): 2e-11 there.
+    return got == pytest.approx(want, rel=1e-12 if n <= 20000 else 2e-11, abs=1e-15 if poisson_upper else 1e-300)
+
+
+def test_statistical_tester_scalar_tests_match_reference(ctx):
+    from precise_mrd.stats import StatisticalTester, TestResult
+
+    for r in GOLD["scalar"]:
+        t = StatisticalTester(test_type=r["test"])
+        if r["test"] == "poisson":
+            res = t.poisson_test(r["k"], r["rate"] * r["n"], alternative=r["alternative"])
+        else:
+            res = t.binomial_test(r["k"], r["n"], r["rate"], alternative=r["alternative"])
+        assert isinstance(res, TestResult) and res.method == r["test"] and res.alternative == r["alternative"]
+        assert _close(res.pvalue, r["pvalue"], r["test"] == "poisson" and r["alternative"] != "less", r["n"]), r
+        assert res.statistic == pytest.approx(r["statistic"], rel=1e-15)
+        if r["effect_size"] is None:
+            assert res.effect_size is None
+        else:
+            assert res.effect_size == pytest.approx(r["effect_size"], rel=1e-12, abs=1e-12)
+        if r["ci"] is not None:     # exact Clopper-Pearson bounds: scipy solves them with brentq (xtol 2e-12)
+            assert res.confidence_interval[0] == pytest.approx(r["ci"][0], rel=1e-8, abs=1e-11)
+            assert res.confidence_interval[1] == pytest.approx(r["ci"][1], rel=1e-8, abs=1e-11)
+    with pytest.raises(ValueError, match="test_type must be"):
+        StatisticalTester(test_type="t-test")
+    with pytest.raises(ValueError, match="alternative must be"):
+        StatisticalTester().poisson_test(3, 1.0, alternative="sideways")
+    assert StatisticalTester().binomial_test(0, 0, 0.1).pvalue == 1.0
+
+
+@pytest.mark.parametrize("test_type", ["poisson", "binomial"])
+def test_test_multiple_variants_matches_reference(ctx, test_type):
+    from precise_mrd.stats import StatisticalTester
+
+    t = GOLD["table"]
+    table = pd.DataFrame({"site_key": t["site_key"], "context": t["context"], "alt_count": t["alt_count"], "total_depth": t["total_depth"]})
+    want = GOLD[f"multi_{test_type}"]
+    got = StatisticalTester(test_type=test_type, alpha=0.05).test_multiple_variants(table, t["rates"])
+    assert list(got.columns) == list(want.keys())
+    for col in ("site_key", "context", "method"):
+        assert got[col].tolist() == want[col]
+    for col in ("observed_alt", "total_depth", "significant", "significant_uncorrected"):
+        assert (got[col].values.astype(float) == np.array(want[col])).all(), col
+    np.testing.assert_allclose(got["expected_rate"], want["expected_rate"], rtol=0)
+    np.testing.assert_allclose(got["test_statistic"], want["test_statistic"], rtol=1e-15)
+    np.testing.assert_allclose(got["effect_size"], want["effect_size"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(got["pvalue"], want["pvalue"], rtol=2e-11, atol=1e-15 if test_type == "poisson" else 0)
+    np.testing.assert_allclose(got["qvalue"], want["qvalue"], rtol=2e-11, atol=4e-13 if test_type == "poisson" else 0)
+    # validation errors of stats.py:205-226
+    tester = StatisticalTester()
+    assert tester.test_multiple_variants(pd.DataFrame(), {}).empty
+    with pytest.raises(ValueError, match="Missing required columns"):
+        tester.test_multiple_variants(pd.DataFrame({"alt_count": [1]}), {})
+    with pytest.raises(ValueError, match="cannot exceed"):
+        tester.test_multiple_variants(pd.DataFrame({"alt_count": [5], "total_depth": [3]}), {})
+    with pytest.raises(ValueError, match="must be positive"):
+        tester.test_multiple_variants(pd.DataFrame({"alt_count": [0], "total_depth": [0]}), {})
+
+
+def test_multiple_testing_correction_methods(ctx):
+    from precise_mrd.stats import StatisticalTester
+
+    p = GOLD["mtc"]["p"]
+    for method in ("benjamini_hochberg", "bonferroni", "holm"):
+        rej, corr = StatisticalTester(alpha=0.05).multiple_testing_correction(p, method)
+        assert rej.tolist() == GOLD["mtc"][method]["rejected"], method
+        np.testing.assert_allclose(corr, GOLD["mtc"][method]["corrected"], rtol=4e-16)   # p*m/k vs p/(k/m): 1 ulp
+    rej, corr = StatisticalTester().multiple_testing_correction([])
+    assert len(rej) == 0 and len(corr) == 0
+
+
+def test_variant_caller_plugin_seam(ctx, golden, smoke_cfg):
+    """§8b: VariantCaller.__init__(config) / train -> {} / predict; get_variant_caller returns the B200 caller."""
+    from precise_mrd.call import call_mrd, get_variant_caller
+    from precise_mrd.models import B200StatisticalVariantCaller, StatisticalVariantCaller, VariantCaller
+
+    g = golden("call_smoke_v2.npz")
+    seg = g["seg_offsets"]
+    collapsed = pd.DataFrame({"sample_id": np.repeat(g["sample_id"], np.diff(seg)), "is_variant": g["is_variant"].astype(bool),
+                              "quality_score": g["quality"], "consensus_agreement": g["agreement"],
+                              "allele_fraction": np.repeat(g["allele_fraction"], np.diff(seg))})
+    em = pd.DataFrame({"error_rate": g["error_rate"]})
+    caller = get_variant_caller(smoke_cfg, False, "ensemble", False, "cnn_lstm")
+    assert isinstance(caller, B200StatisticalVariantCaller) and isinstance(caller, VariantCaller)
+    assert StatisticalVariantCaller is B200StatisticalVariantCaller
+    assert caller.train(collapsed, np.random.default_rng(0)) == {} and caller.model is None
+    pred = caller.predict(collapsed, em)
+    assert pred.equals(call_mrd(collapsed, em, smoke_cfg, np.random.default_rng(0)))
+    assert (pred["n_variants"].values == g["want_n_variants"]).all() and (pred["significant"].values == g["want_significant"]).all()
+    with pytest.raises(NotImplementedError):
+        get_variant_caller(smoke_cfg, True, "ensemble", False, "cnn_lstm")
+    with pytest.raises(TypeError):
+        VariantCaller(smoke_cfg)                      # abstract
+
+    class Veto(VariantCaller):                        # a third-party plugin against the same interface
+        def predict(self, collapsed_df, error_model_df):
+            return pd.DataFrame({"sample_id": collapsed_df["sample_id"].unique(), "significant": False})
+
+    assert not Veto(smoke_cfg).predict(collapsed, em)["significant"].any()
+
+
+def test_synthetic_read_generator_matches_reference_distributions(ctx):
+    """io.py:79-123 on the device: NegBinom(r=2)+1 sizes, allele concordance 0.9 / 0.95, quality
+    int(N(30,5)) clipped [10,40], strand, read position [10,150), family ids, site alleles."""
+    from precise_mrd.io import Read, SyntheticReadGenerator, TargetSite, site_cell_id
+
+    site = TargetSite("chr7", 55249071, "C", "T", "ACG", gene="EGFR")
+    assert site.key == "chr7:55249071:C>T" and hash(site) == hash(site.key)
+    cid = site_cell_id(site)
+    assert cid & 3 == 1 and ((cid & 3) + 1 + (cid >> 2) % 3) & 3 == 3          # C -> T
+    gen = SyntheticReadGenerator(seed=5)
+    reads = gen.generate_reads_for_site(site, n_umi_families=20000, allele_fraction=0.3, mean_family_size=5.0)
+    assert isinstance(reads[0], Read) and {r.ref for r in reads[:2000]} == {"C"} and {r.alt for r in reads} == {"C", "T"}
+    df = pd.DataFrame([r.__dict__ for r in reads])
+    assert df["family_id"].nunique() == 20000 and df["family_id"].iloc[0] == "fam_000000"
+    sizes = df.groupby("family_id", sort=False).size().values
+    p = 2.0 / (2.0 + 5.0)
+    ks = np.arange(1, 40)
+    exp = sps.nbinom.pmf(ks - 1, 2, p) * len(sizes)
+    obs = np.bincount(sizes, minlength=40)[1:40].astype(float)
+    keep = exp > 5
+    assert sps.chisquare(obs[keep] * exp[keep].sum() / obs[keep].sum(), exp[keep])[1] > ALPHA
+    fam_alt = df.groupby("family_id", sort=False)["alt"].agg(lambda s: (s == "T").mean()).values
+    variant = fam_alt > 0.5
+    assert abs(variant.mean() - 0.3) < 4 * np.sqrt(0.3 * 0.7 / 20000) + 0.01      # majority vote blurs tiny families
+    big = sizes >= 8
+    assert abs(fam_alt[big & variant].mean() - 0.9) < 0.01 and abs(fam_alt[big & ~variant].mean() - 0.05) < 0.01
+    q = df["quality"].values
+    assert q.min() >= 10 and q.max() <= 40
+    grid = np.arange(10, 41)
+    cdf = sps.norm.cdf((grid + 1 - 30) / 5.0)
+    cdf[-1] = 1.0
+    exp_q = np.diff(np.r_[0.0, cdf]) * len(q)
+    obs_q = np.bincount(q, minlength=41)[10:41].astype(float)
+    keep = exp_q > 5
+    assert sps.chisquare(obs_q[keep] * exp_q[keep].sum() / obs_q[keep].sum(), exp_q[keep])[1] > ALPHA
+    assert abs((df["strand"] == "+").mean() - 0.5) < 0.01
+    assert df["read_position"].min() >= 10 and df["read_position"].max() <= 149
+    assert all(len(u) == 12 and set(u) <= set("ACGT") for u in df["umi"].iloc[:500])
+    # successive calls draw fresh reads; a new generator with the same seed repeats the sequence
+    again = gen.generate_reads_for_site(site, 50)
+    fresh = SyntheticReadGenerator(seed=5)
+    first = fresh.generate_reads_for_site(site, n_umi_families=20000, allele_fraction=0.3, mean_family_size=5.0)
+    assert [r.umi for r in first[:200]] == [r.umi for r in reads[:200]] and [r.umi for r in again[:20]] != [r.umi for r in reads[:20]]
+    # contamination flips the family's variant status (io.py:100-101)
+    flipped = gen.generate_reads_for_site(site, 20000, allele_fraction=0.0, contamination_rate=0.25)
+    d2 = pd.DataFrame([r.__dict__ for r in flipped])
+    v2 = d2.groupby("family_id", sort=False)["alt"].agg(lambda s: (s == "T").mean()).values
+    assert abs((v2 > 0.5).mean() - 0.25) < 0.02
+    # the packed records feed UMIProcessor directly
+    from precise_mrd.umi import UMIProcessor
+
+    fams = UMIProcessor(min_family_size=3).process_reads(first[:5000])
+    assert 0 < len(fams) < 5000 and all(f.family_size >= 3 for f in fams)
+
+
+def test_stratified_analyzer(ctx, smoke_cfg, tmp_path):
+    """eval/stratified.py: same result structure, context multipliers, calibration bins, artifacts."""
+    from precise_mrd.eval.stratified import CONTEXT_ERROR_MULTIPLIER, StratifiedAnalyzer, context_seed_offset, run_stratified_analysis
+    from precise_mrd.validation import validate_json
+
+    an = StratifiedAnalyzer(smoke_cfg, np.random.default_rng(7))
+    power = an.analyze_stratified_power(af_values=[0.001, 0.05], depth_values=[1000, 5000], contexts=["CpG", "NpN"], n_replicates=6)
+    assert set(power) == {"stratified_results", "af_values", "depth_values", "contexts", "config_hash"}
+    cell = power["stratified_results"]["CpG"][5000][0.05]
+    assert set(cell) == {"mean_detection_rate", "std_detection_rate", "detection_rates", "n_replicates"}
+    assert cell["n_replicates"] == 6 and len(cell["detection_rates"]) == 6 and set(cell["detection_rates"]) <= {0.0, 1.0}
+    assert cell["mean_detection_rate"] == 1.0                                      # AF 0.05 >> background: always called
+    assert power["stratified_results"]["NpN"][1000][0.001]["mean_detection_rate"] <= 0.5
+    # deterministic: the reference's hash(context) is replaced by a fixed offset
+    again = StratifiedAnalyzer(smoke_cfg, np.random.default_rng(7)).analyze_stratified_power(
+        af_values=[0.001, 0.05], depth_values=[1000, 5000], contexts=["CpG", "NpN"], n_replicates=6)
+    assert again == power and context_seed_offset("CpG") == context_seed_offset("CpG") < 1000
+    # the context multiplier reaches the kernel: stored rate scaled once, false positives at rate * m^2
+    cfg = an._create_context_config(0.0, 50000, "CpG")
+    base = [an._simulate_with_context(cfg, np.random.default_rng(s), "CHH") for s in range(200)]
+    cpg = [an._simulate_with_context(cfg, np.random.default_rng(s), "CpG") for s in range(200)]
+    b_rate = np.array([d["background_rate"].iloc[0] for d in base])
+    c_rate = np.array([d["background_rate"].iloc[0] for d in cpg])
+    np.testing.assert_allclose(c_rate, b_rate * CONTEXT_ERROR_MULTIPLIER["CpG"], rtol=1e-15)
+    assert (cpg[0]["context"] == "CpG").all() and cfg.run_id.endswith("_context_CpG")
+    ratio = sum(d["n_false_positives"].iloc[0] for d in cpg) / sum(d["n_false_positives"].iloc[0] for d in base)
+    assert abs(ratio - 1.5 ** 2) < 0.15
+    # calibration: (lo, hi] bins, ECE / MCE definitions
+    m = an._compute_calibration_metrics(np.array([0.0, 0.05, 0.1, 0.95, 1.0]), np.array([0, 0, 1, 1, 1]), 10)
+    assert m["bin_counts"] == [2, 0, 0, 0, 0, 0, 0, 0, 0, 2]                        # 0.0 falls in no bin; 0.1 in the first
+    assert m["bin_accuracies"][0] == 0.5 and m["bin_confidences"][0] == pytest.approx(0.075)
+    assert m["ece"] == pytest.approx(0.425 * 0.4 + 0.025 * 0.4) and m["max_ce"] == pytest.approx(0.425)
+    calib = an.analyze_calibration_by_bins(af_values=[0.01], depth_values=[1000], n_bins=10, n_replicates=8)
+    row = calib["calibration_data"][0]
+    assert row["n_samples"] == 8 and len(row["bin_counts"]) == 10 and 0.0 <= row["ece"] <= 1.0
+    an.generate_stratified_reports(str(tmp_path))
+    validate_json(tmp_path / "power_by_stratum.json", "power.schema.json")
+    validate_json(tmp_path / "calibration_by_bin.json", "calibration.schema.json")
+    assert list(pd.read_csv(tmp_path / "calibration_by_bin.csv").columns)[:4] == ["depth", "af", "ece", "max_ce"]
+    assert callable(run_stratified_analysis)
