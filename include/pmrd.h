@@ -218,6 +218,18 @@ int32_t pmrd_simulate_cells_stratified(pmrd_ctx* ctx, const int64_t* h_cell_id, 
                                        const int64_t* h_depth, const double* h_bg_multiplier,
                                        int64_t n_cells, int32_t max_family_size, pmrd_cell_table* h_out);
 
+/* ---------------------------------------------------------------- K12: metrics ------- */
+/* roc_auc_score / average_precision (src/precise_mrd/metrics.py:18-33, sklearn definitions:
+ * trapezoidal AUC over the distinct thresholds, AP = sum (R_i - R_{i-1}) P_i; one class only ->
+ * 0.5 / mean(y_true)) of (y_true, y_score) under n_boot resamples -- bootstrap_metric,
+ * metrics.py:48-118.  h_indices [n_boot * n] are the resample rows exactly as the reference
+ * draws them up-front (rng.choice(n, n, replace=True), :76-79); NULL: Philox draws keyed
+ * (seed, stream_id, resample, draw).  h_point (optional) receives {auc, ap} of the sample itself. */
+int32_t pmrd_bootstrap_metrics(pmrd_ctx* ctx, const uint8_t* h_y_true, const double* h_y_score, int64_t n,
+                               const int64_t* h_indices, int64_t n_boot, uint64_t stream_id,
+                               double* h_point /* [2] or NULL */, double* h_auc /* [n_boot] */,
+                               double* h_ap /* [n_boot] */);
+
 /* ---------------------------------------------------------------- K2: G-D families -- */
 /* collapse_umis (src/precise_mrd/collapse.py:70-118): per (cell, family) Philox draws.
  * variant 2 = G-D v2 constants, 1 = G-D v1 ("collapse 2.py").  Rows of cell i are

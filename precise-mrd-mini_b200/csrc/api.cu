@@ -456,6 +456,35 @@ int32_t pmrd_umi_hamming(pmrd_ctx* ctx, const uint32_t* h_a, const uint32_t* h_b
 }
 
 
+// ---------------------------------------------------------------- K12 -------------------
+int32_t pmrd_bootstrap_metrics(pmrd_ctx* ctx, const uint8_t* h_y_true, const double* h_y_score, int64_t n,
+                               const int64_t* h_indices, int64_t n_boot, uint64_t stream_id, double* h_point,
+                               double* h_auc, double* h_ap) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n > 0 && h_y_true && h_y_score, "bootstrap metrics: empty input");
+    PMRD_ARG(ctx, n_boot >= 0 && (n_boot == 0 || (h_auc && h_ap)), "bootstrap metrics: outputs");
+    const int want_point = h_point != nullptr;
+    const int64_t n_res = n_boot + want_point;
+    if (n_res == 0) return PMRD_OK;
+    DevBuf y, sc, ix, auc, ap;
+    PMRD_TRY(up(ctx, y, h_y_true, (size_t)n));
+    PMRD_TRY(up(ctx, sc, h_y_score, (size_t)n * 8));
+    if (h_indices && n_boot > 0) PMRD_TRY(up(ctx, ix, h_indices, (size_t)n_boot * (size_t)n * 8));
+    PMRD_CUDA(ctx, auc.alloc(ctx->stream, (size_t)n_res * 8));
+    PMRD_CUDA(ctx, ap.alloc(ctx->stream, (size_t)n_res * 8));
+    PMRD_TRY(k12_bootstrap_metrics(ctx, y.as<uint8_t>(), sc.as<double>(), n,
+                                   (h_indices && n_boot > 0) ? (const int64_t*)ix.as<int64_t>() : (const int64_t*)nullptr, n_boot,
+                                   want_point, stream_id, auc.as<double>(), ap.as<double>()));
+    PMRD_TRY(down(ctx, h_auc, auc.p, (size_t)n_boot * 8));
+    PMRD_TRY(down(ctx, h_ap, ap.p, (size_t)n_boot * 8));
+    if (want_point) {
+        PMRD_TRY(down(ctx, h_point, auc.as<double>() + n_boot, 8));
+        PMRD_TRY(down(ctx, h_point + 1, ap.as<double>() + n_boot, 8));
+    }
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
 // ---------------------------------------------------------------- K1 --------------------
 int32_t pmrd_simulate_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_depth,
                             int64_t n_cells, int32_t max_family_size, pmrd_cell_table* h_out) {

@@ -17,6 +17,10 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
                     int64_t n_reads, const pmrd_umi_params* params, const pmrd_family_table* d_fam, int64_t capacity_f,
                     int64_t* n_families, const pmrd_group_table* d_grp, int64_t capacity_g, int64_t* n_groups);
 
+// metrics.cu
+int32_t k12_bootstrap_metrics(pmrd_ctx* ctx, const uint8_t* d_y, const double* d_score, int64_t n, const int64_t* d_indices,
+                              int64_t n_boot, int want_point, uint64_t stream_id, double* d_auc, double* d_ap);
+
 // simulate.cu
 int32_t k1_simulate_cells(pmrd_ctx* ctx, const int64_t* d_cell_id, const double* d_af, const int64_t* d_depth,
                           const double* d_bg_mult, int64_t n_cells, int32_t max_family_size, const pmrd_cell_table* d_out);

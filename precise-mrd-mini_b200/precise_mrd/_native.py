@@ -355,6 +355,22 @@ class Context:
         finally:
             plan.close()
 
+    # -- K12 -----------------------------------------------------------------------------
+    def bootstrap_metrics(self, y_true, y_score, indices=None, n_boot: int = 0, stream_id: int = 0, point: bool = True):
+        """(point {auc, ap} or None, auc[n_boot], ap[n_boot]).  ``indices``: [n_boot, n] resample rows."""
+        y = _arr(np.asarray(y_true) != 0, np.uint8)
+        sc = _arr(y_score, np.float64)
+        n = y.shape[0]
+        ix = None
+        if indices is not None:
+            ix = _arr(indices, np.int64).reshape(-1, n)
+            n_boot = ix.shape[0]
+        auc, ap = np.zeros(max(n_boot, 1)), np.zeros(max(n_boot, 1))
+        pt = np.zeros(2) if point else None
+        self._check(self.lib.pmrd_bootstrap_metrics(self.h, _ptr(y), _ptr(sc), C.c_int64(n), _ptr(ix), C.c_int64(n_boot),
+                                                    C.c_uint64(stream_id), _ptr(pt), _ptr(auc), _ptr(ap)))
+        return pt, auc[:n_boot], ap[:n_boot]
+
     # -- K11 -----------------------------------------------------------------------------
     def fit_lod(self, af, hit, target: float = 0.95, n_boot: int = 200, stream_id: int = 0):
         af = _arr(af, np.float64)

@@ -1,9 +1,11 @@
 """Performance metrics -- ``src/precise_mrd/metrics.py:18-316``.
 
 ROC-AUC / average precision follow sklearn's definitions (trapezoidal AUC over distinct
-thresholds; AP = sum (R_n - R_{n-1}) P_n) in vectorised numpy; the bootstrap draws all resample
-indices up front from the caller's generator (``metrics.py:76-79``) so the result is a pure
-function of the generator state.  [SURVEY.md §8(f)-2 lists the device version as the next row.]"""
+thresholds; AP = sum (R_n - R_{n-1}) P_n) and run on the device (kernel K12,
+``pmrd_bootstrap_metrics``): one sort of the scores, then every bootstrap resample is a histogram
+over the threshold groups and one block-wide walk.  The bootstrap draws all resample indices up
+front from the caller's generator (``metrics.py:76-79``), so the result is a pure function of the
+generator state and resample-for-resample the reference's [SURVEY.md §8(f)-2]."""
 from __future__ import annotations
 
 from typing import Any, Dict, Optional
@@ -11,54 +13,57 @@ from typing import Any, Dict, Optional
 import numpy as np
 import pandas as pd
 
+from . import _native as nv
 
-def _binary_curve(y_true: np.ndarray, y_score: np.ndarray):
-    order = np.argsort(-y_score, kind="mergesort")
-    y_true, y_score = y_true[order], y_score[order]
-    distinct = np.flatnonzero(np.diff(y_score)) if len(y_score) > 1 else np.array([], dtype=int)
-    idx = np.r_[distinct, len(y_true) - 1]
-    tps = np.cumsum(y_true)[idx].astype(float)
-    fps = (1 + idx - tps).astype(float)
-    return tps, fps
+
+def _as_binary(y_true) -> np.ndarray:
+    y = np.asarray(y_true)
+    return (y != 0).astype(np.uint8)
 
 
 def roc_auc_score(y_true: np.ndarray, y_score: np.ndarray) -> float:
-    """metrics.py:18-24: single-class input -> 0.5."""
-    y_true, y_score = np.asarray(y_true).astype(int), np.asarray(y_score, dtype=float)
-    if len(np.unique(y_true)) != 2:
+    """metrics.py:18-24 (sklearn ``roc_auc_score``; single-class input -> 0.5), kernel K12."""
+    if len(y_true) == 0:
         return 0.5
-    tps, fps = _binary_curve(y_true, y_score)
-    tpr, fpr = np.r_[0.0, tps] / tps[-1], np.r_[0.0, fps] / fps[-1]
-    return float(np.trapezoid(tpr, fpr)) if hasattr(np, "trapezoid") else float(np.trapz(tpr, fpr))
+    pt, _, _ = nv.default_context().bootstrap_metrics(_as_binary(y_true), np.asarray(y_score, dtype=float))
+    return float(pt[0])
 
 
 def average_precision(y_true: np.ndarray, y_score: np.ndarray) -> float:
-    """metrics.py:27-33: degenerate input -> mean(y_true)."""
-    y_true, y_score = np.asarray(y_true).astype(int), np.asarray(y_score, dtype=float)
-    if y_true.sum() == 0 or len(y_true) == 0:
-        return float(np.mean(y_true)) if len(y_true) else 0.0
-    tps, fps = _binary_curve(y_true, y_score)
-    precision = tps / (tps + fps)
-    recall = tps / tps[-1]
-    return float(np.sum(np.diff(np.r_[0.0, recall]) * precision))
+    """metrics.py:27-33 (sklearn ``average_precision_score``; no positives -> mean(y_true) = 0), kernel K12."""
+    if len(y_true) == 0:
+        return 0.0
+    pt, _, _ = nv.default_context().bootstrap_metrics(_as_binary(y_true), np.asarray(y_score, dtype=float))
+    return float(pt[1])
 
 
 def bootstrap_metric(y_true, y_score, metric_func, n_bootstrap: int = 1000, rng: Optional[np.random.Generator] = None,
                      n_jobs: int = -1) -> Dict[str, float]:
+    """metrics.py:48-118.  The resample rows are drawn up-front from the caller's generator exactly
+    as the reference does (``rng.choice(n, n, replace=True)`` per resample, ``:76-79``), so the
+    generator ends in the same state and every resample is the reference's; all ``n_bootstrap``
+    AUC / AP evaluations are then ONE device call (kernel K12).  A ``metric_func`` other than this
+    module's two is a Python callable and is evaluated per resample on the host, as in the
+    reference; ``n_jobs`` is accepted and ignored."""
     if rng is None:
         rng = np.random.default_rng(42)
     y_true, y_score = np.asarray(y_true), np.asarray(y_score)
     n = len(y_true)
-    idx = [rng.choice(n, size=n, replace=True) for _ in range(n_bootstrap)]       # metrics.py:76-79
-    scores = []
-    for ii in idx:
-        try:
-            scores.append(metric_func(y_true[ii], y_score[ii]))
-        except Exception:
-            continue
-    if not scores:
+    idx = [rng.choice(n, size=n, replace=True) for _ in range(n_bootstrap)]
+    if metric_func in (roc_auc_score, average_precision) and n > 0 and n_bootstrap > 0:
+        _, auc, ap = nv.default_context().bootstrap_metrics(_as_binary(y_true), y_score.astype(float), indices=np.stack(idx),
+                                                            point=False)
+        s = auc if metric_func is roc_auc_score else ap
+    else:
+        scores = []
+        for ii in idx:
+            try:
+                scores.append(metric_func(y_true[ii], y_score[ii]))
+            except Exception:
+                continue
+        s = np.array(scores)
+    if len(s) == 0:
         return {"mean": 0.0, "lower": 0.0, "upper": 0.0, "std": 0.0}
-    s = np.array(scores)
     return {"mean": float(np.mean(s)), "lower": float(np.percentile(s, 2.5)), "upper": float(np.percentile(s, 97.5)),
             "std": float(np.std(s))}
 

@@ -225,3 +225,59 @@ def test_stratified_analyzer(ctx, smoke_cfg, tmp_path):
     validate_json(tmp_path / "calibration_by_bin.json", "calibration.schema.json")
     assert list(pd.read_csv(tmp_path / "calibration_by_bin.csv").columns)[:4] == ["depth", "af", "ece", "max_ce"]
     assert callable(run_stratified_analysis)
+
+
+def test_bootstrap_metrics_kernel_matches_sklearn_resample_for_resample(ctx):
+    """K12 (metrics.py:18-118): point AUC / AP and every bootstrap resample against the oracle
+    (itself pinned to sklearn in the CPU suite), on tie-heavy, tie-free, one-class and tiny inputs;
+    the public ``bootstrap_metric`` consumes the caller's generator exactly as the reference does."""
+    from sklearn.metrics import average_precision_score
+    from sklearn.metrics import roc_auc_score as sk_auc
+
+    from oracle import port
+    from precise_mrd import metrics
+
+    rng = np.random.default_rng(11)
+    cases = [(rng.integers(0, 2, 500), np.round(rng.random(500), 2)),                  # heavy ties
+             (rng.integers(0, 2, 3000), rng.normal(size=3000)),                        # no ties, negative scores
+             ((rng.random(20000) < 0.01).astype(int), rng.random(20000) ** 3),         # C2-sized, rare positives
+             (np.array([0, 1]), np.array([0.3, 0.3])), (np.array([1, 0, 1]), np.array([-0.0, 0.0, 1.0]))]
+    for y, s in cases:
+        pt, _, _ = ctx.bootstrap_metrics(y, s)
+        assert pt[0] == pytest.approx(sk_auc(y, s), rel=1e-12) and pt[1] == pytest.approx(average_precision_score(y, s), rel=1e-12)
+        idx = np.stack([rng.choice(len(y), len(y), replace=True) for _ in range(40)])
+        _, auc, ap = ctx.bootstrap_metrics(y, s, indices=idx, point=False)
+        want_auc = np.array([port.roc_auc(y[i], s[i]) for i in idx])
+        want_ap = np.array([port.average_precision(y[i], s[i]) for i in idx])
+        np.testing.assert_allclose(auc, want_auc, rtol=1e-12)
+        np.testing.assert_allclose(ap, want_ap, rtol=1e-12, atol=1e-300)
+    # one class only: the reference's fallbacks (metrics.py:18-33)
+    pt, auc, ap = ctx.bootstrap_metrics(np.zeros(50), rng.random(50), n_boot=8)
+    assert pt.tolist() == [0.5, 0.0] and (auc == 0.5).all() and (ap == 0.0).all()
+    pt, _, _ = ctx.bootstrap_metrics(np.ones(50), rng.random(50))
+    assert pt.tolist() == [0.5, 1.0]
+    # Philox resampling (no indices given): deterministic per (seed, stream), distribution matches numpy's
+    y, s = cases[0]
+    _, a1, _ = ctx.bootstrap_metrics(y, s, n_boot=2000, stream_id=3, point=False)
+    _, a2, _ = ctx.bootstrap_metrics(y, s, n_boot=2000, stream_id=3, point=False)
+    _, a3, _ = ctx.bootstrap_metrics(y, s, n_boot=2000, stream_id=4, point=False)
+    assert (a1 == a2).all() and (a1 != a3).any()
+    _, ref_scores = port.bootstrap_metric(y, s, port.roc_auc, 2000, np.random.default_rng(5))
+    assert sps.ks_2samp(a1, ref_scores)[1] > ALPHA
+    with pytest.raises(Exception, match="out of range"):
+        ctx.bootstrap_metrics(y, s, indices=np.full((1, len(y)), len(y)), point=False)
+    # public API: same generator consumption and the same summary as the reference formula
+    y, s = cases[1]
+    got = metrics.bootstrap_metric(y, s, metrics.roc_auc_score, 200, np.random.default_rng(3))
+    want, _ = port.bootstrap_metric(y, s, port.roc_auc, 200, np.random.default_rng(3))
+    assert got == pytest.approx(want, rel=1e-12)
+    got = metrics.bootstrap_metric(y, s, metrics.average_precision, 200, np.random.default_rng(3))
+    want, _ = port.bootstrap_metric(y, s, port.average_precision, 200, np.random.default_rng(3))
+    assert got == pytest.approx(want, rel=1e-12)
+    g1, g2 = np.random.default_rng(9), np.random.default_rng(9)
+    metrics.bootstrap_metric(y, s, metrics.roc_auc_score, 7, g1)
+    port.bootstrap_metric(y, s, port.roc_auc, 7, g2)
+    assert g1.random() == g2.random()
+    assert metrics.roc_auc_score(y, s) == pytest.approx(sk_auc(y, s), rel=1e-12)
+    assert metrics.average_precision(y, s) == pytest.approx(average_precision_score(y, s), rel=1e-12)
+    assert metrics.bootstrap_metric(y, s, lambda a, b: float(np.mean(a)), 5, np.random.default_rng(0))["mean"] > 0   # host callable

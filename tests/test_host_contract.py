@@ -110,21 +110,23 @@ def test_pack_unpack_bases():
         pack_bases(["ACGN"])
 
 
-def test_metrics_match_sklearn_definitions():
+def test_metrics_oracle_matches_sklearn_and_calibration_bins():
+    """The restatement the GPU metrics kernel (K12) is checked against, pinned to sklearn itself."""
     from sklearn.metrics import average_precision_score, roc_auc_score
 
-    from precise_mrd.metrics import average_precision, bootstrap_metric, calibration_analysis
-    from precise_mrd.metrics import roc_auc_score as auc
+    from oracle import port
+    from precise_mrd.metrics import calibration_analysis
 
     rng = np.random.default_rng(0)
     for _ in range(20):
         y = rng.integers(0, 2, 120)
         s = np.round(rng.random(120), 1)          # heavy ties
-        assert abs(auc(y, s) - roc_auc_score(y, s)) < 1e-12
-        assert abs(average_precision(y, s) - average_precision_score(y, s)) < 1e-12
-    assert auc(np.zeros(5), np.arange(5)) == 0.5                               # metrics.py:18-24 fallback
-    a = bootstrap_metric(y, s, auc, 50, np.random.default_rng(3))
-    b = bootstrap_metric(y, s, auc, 50, np.random.default_rng(3))
+        assert abs(port.roc_auc(y, s) - roc_auc_score(y, s)) < 1e-12
+        assert abs(port.average_precision(y, s) - average_precision_score(y, s)) < 1e-12
+    assert port.roc_auc(np.zeros(5), np.arange(5)) == 0.5                      # metrics.py:18-24 fallback
+    assert port.average_precision(np.zeros(5), np.arange(5)) == 0.0            # metrics.py:27-33 fallback
+    a, _ = port.bootstrap_metric(y, s, port.roc_auc, 50, np.random.default_rng(3))
+    b, _ = port.bootstrap_metric(y, s, port.roc_auc, 50, np.random.default_rng(3))
     assert a == b and a["lower"] <= a["mean"] <= a["upper"]                    # test_lob_lod_bootstrap.py:148-168
     cal = calibration_analysis(np.array([0, 1, 1]), np.array([0.05, 0.95, 1.0]))
     assert cal[-1]["bin"] == 9 and cal[-1]["count"] == 2                       # last bin closed
