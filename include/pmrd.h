@@ -218,6 +218,47 @@ int32_t pmrd_simulate_cells_stratified(pmrd_ctx* ctx, const int64_t* h_cell_id, 
                                        const int64_t* h_depth, const double* h_bg_multiplier,
                                        int64_t n_cells, int32_t max_family_size, pmrd_cell_table* h_out);
 
+/* ---------------------------------------------------------------- K13: FASTQ ingest -- */
+/* FASTQReader.read_fastq + the per-UMI grouping of process_fastq_to_dataframe
+ * (src/precise_mrd/fastq.py:66-110, :176-220).  pmrd_fastq_scan takes the file's bytes (already
+ * decompressed) and returns one row per 4-line record, in file order; offsets index the caller's
+ * buffer, so strings are sliced on the host only for the rows that are kept. */
+#define PMRD_FQ_END 0        /* stripped header empty: read_fastq stops here (fastq.py:85-86)       */
+#define PMRD_FQ_MALFORMED 1  /* another line empty after strip(): record skipped (:93-94)           */
+#define PMRD_FQ_NO_UMI 2     /* valid record, none of the three header patterns matched (:28-32)    */
+#define PMRD_FQ_OK 3         /* valid record with a UMI of <= 12 letters                            */
+#define PMRD_FQ_LONG_UMI 4   /* valid record, "UMI:" capture longer than 12 letters (not packable)  */
+typedef struct pmrd_fastq_records {
+    int32_t* status;    /* [R] PMRD_FQ_*                                                           */
+    uint64_t* umi_key;  /* [R] letters 5 bit each (A=1), left-aligned in bits 63..4, length in 3..0 */
+    int64_t* hdr_off;   /* [R] stripped header line (incl. '@')                                    */
+    int32_t* hdr_len;
+    int64_t* umi_off;   /* [R] the regex capture                                                   */
+    int32_t* umi_len;
+    int64_t* seq_off;   /* [R] stripped sequence line                                              */
+    int32_t* seq_len;
+    int64_t* qual_off;  /* [R] stripped quality line                                               */
+    int32_t* qual_len;
+    int64_t* qual_sum;  /* [R] sum of (byte - 33) over the quality line (:64)                      */
+} pmrd_fastq_records;
+/* *n_records = ceil(lines / 4); PMRD_ERR_CAPACITY (with *n_records set) if capacity is smaller. */
+int32_t pmrd_fastq_scan(pmrd_ctx* ctx, const uint8_t* h_bytes, int64_t n_bytes, int64_t capacity,
+                        pmrd_fastq_records* h_out, int64_t* n_records);
+
+/* Families of the kept reads: group by UMI key, rows ordered by first appearance (dict order,
+ * fastq.py:186-196).  h_qual_sum / h_qual_len / h_umi_key are per kept read, in file order. */
+typedef struct pmrd_fastq_families {
+    uint64_t* umi_key;     /* [F]                                                        */
+    uint32_t* first_read;  /* [F] index (into the kept reads) of the family's first read   */
+    uint32_t* best_read;   /* [F] first read with the highest mean quality (:213 argmax) */
+    int64_t* family_size;  /* [F]                                                        */
+    int64_t* qual_sum;     /* [F] over all bases of all reads (:210,:222)                */
+    int64_t* n_bases;      /* [F]                                                        */
+} pmrd_fastq_families;
+int32_t pmrd_fastq_families_of(pmrd_ctx* ctx, const uint64_t* h_umi_key, const int64_t* h_qual_sum,
+                               const int32_t* h_qual_len, int64_t n_reads, pmrd_fastq_families* h_out,
+                               int64_t capacity, int64_t* n_families);
+
 /* ---------------------------------------------------------------- K12: metrics ------- */
 /* roc_auc_score / average_precision (src/precise_mrd/metrics.py:18-33, sklearn definitions:
  * trapezoidal AUC over the distinct thresholds, AP = sum (R_i - R_{i-1}) P_i; one class only ->

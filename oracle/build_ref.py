@@ -63,7 +63,7 @@ def build_gd_v1() -> None:
 def build_gd_v2() -> None:
     src = REF / "src" / "precise_mrd"
     pkg = OUT / "gd_v2" / "precise_mrd"
-    for name in ("simulate", "collapse", "error_model", "call", "config", "utils"):
+    for name in ("simulate", "collapse", "error_model", "call", "config", "utils", "fastq"):
         _link(src / f"{name}.py", pkg / f"{name}.py")
     _write(pkg / "__init__.py", "# shim: the reference's own __init__ fails to import (SURVEY.md §0.2)\n")
     # the four symbols simulate.py:10 imports that src/precise_mrd/performance.py lacks

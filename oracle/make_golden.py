@@ -17,6 +17,8 @@ parity tests can run where the reference cannot travel.
   gb_reads.npz                            G-B SyntheticReadGenerator reads -> UMIProcessor(max_edit_distance=0)
   gb_stats.json                           G-B StatisticalTester (one-sided tests, CIs, BH/Bonferroni/Holm),
                                           ContextAnalyzer and ErrorModel on seeded inputs
+  fastq_mixed.fastq / fastq_mixed.json    a synthetic FASTQ with every header convention and parser edge
+                                          case + the reference's read list / family table / validation for it
   lod_fit.npz                             LODAnalyzer._fit_detection_curve/_bootstrap_lod_ci on given vectors
   gd_dist.npz                             distribution samples from the reference simulate/collapse (KS targets)
 """
@@ -346,6 +348,77 @@ def golden_gb_stats() -> None:
     print("  wrote gb_stats.json", len(rows), "scalar rows,", m, "loci")
 
 
+# ------------------------------------------------------------------------------- FASTQ ingest
+def golden_fastq() -> None:
+    """A seeded synthetic FASTQ exercising every header convention and parser edge case
+    (tests/golden/fastq_mixed.fastq) + what the reference's fastq.py makes of it (fastq_mixed.json)."""
+    import json
+
+    _import_ref("gd_v2")
+    from precise_mrd.config import load_config
+    from precise_mrd.fastq import FASTQReader, detect_umi_format, process_fastq_to_dataframe
+
+    rng = np.random.default_rng(77)
+    bases = np.array(list("ACGT"))
+    umis = ["".join(rng.choice(bases, int(rng.integers(8, 13)))) for _ in range(60)]
+
+    def rec(i, header):
+        n = int(rng.integers(30, 90))
+        seq = "".join(rng.choice(bases, n))
+        qual = "".join(chr(33 + int(q)) for q in np.clip(rng.normal(28, 9, n), 2, 41).astype(int))
+        return [header, seq, "+", qual]
+
+    lines = []
+    for i in range(900):
+        u = umis[int(rng.integers(0, len(umis)))]
+        style = int(rng.integers(0, 9))
+        if style <= 2:
+            h = f"@READ_{i:05d} UMI:{u}"
+        elif style == 3:
+            h = f"@INST:{i}:FC_{u}_L001 1:N:0"
+        elif style == 4:
+            h = f"@INST:{i}:FC:1:{i % 97}:{u}"
+        elif style == 5:
+            h = f"@READ_{i:05d} no umi here"                     # no pattern matches
+        elif style == 6:
+            h = f"@R{i} UMI: UMI:{u} extra"                      # first 'UMI:' has no capital after it
+        elif style == 7:
+            h = f"@R{i}_{u}X_tail:{u}"                            # '_' run may be 9..13 letters; ':' tail decides
+        else:
+            h = f"  @READ_{i:05d} UMI:{u}ACGTNNNNNNNNNNNN"[: 24 + len(u)] + "  "   # padded, capture cut to <= 12 letters
+        r = rec(i, h)
+        if i % 131 == 5:
+            r[1] = "   "                                          # malformed: whitespace-only sequence line
+        if i % 171 == 9:
+            r = [x + "\r" for x in r]                             # CRLF record
+        lines += r
+    lines += ["", "@AFTER_BLANK UMI:AAAAAAAA", "ACGT", "+", "IIII"]   # an empty header line ends the file
+    text = "\n".join(lines) + "\n"
+    path = OUT / "fastq_mixed.fastq"
+    path.write_text(text)
+    cfg = load_config(REF / "configs" / "smoke.yaml")
+    out = {}
+    reader = FASTQReader(path)
+    reads = list(reader.read_fastq())
+    out["reads"] = [{"read_id": r["read_id"], "sequence": r["sequence"], "umi": r["umi"], "mean_quality": float(r["mean_quality"]),
+                     "sequence_length": r["sequence_length"], "qual_sum": int(sum(r["quality_scores"]))} for r in reads]
+    out["reads_max_50"] = [r["read_id"] for r in reader.read_fastq(max_reads=50)]
+    out["validate"] = {k: (float(v) if isinstance(v, (float, np.floating)) else v) for k, v in reader.validate_fastq().items()}
+    for tag, mr in (("all", None), ("max_300", 300)):
+        df = process_fastq_to_dataframe(path, cfg, np.random.default_rng(0), max_reads=mr)
+        out[f"table_{tag}"] = {"sample_id": [int(v) for v in df.sample_id], "umi": df.umi.tolist(), "family_size": [int(v) for v in df.family_size],
+                               "consensus_sequence": df.consensus_sequence.tolist(), "mean_quality": [float(v) for v in df.mean_quality],
+                               "quality_scores_sum": [int(sum(v)) for v in df.quality_scores],
+                               "quality_scores_head": [[int(x) for x in v[:5]] for v in df.quality_scores],
+                               "consensus_agreement": [float(v) for v in df.consensus_agreement],
+                               "passes_quality": [bool(v) for v in df.passes_quality],
+                               "passes_consensus": [bool(v) for v in df.passes_consensus], "columns": list(df.columns)}
+    out["format"] = detect_umi_format(path, 100)
+    with open(OUT / "fastq_mixed.json", "w") as f:
+        json.dump(out, f)
+    print("  wrote fastq_mixed.fastq / .json:", len(reads), "reads,", len(out["table_all"]["umi"]), "families, format", out["format"])
+
+
 # ------------------------------------------------------------------------------- LoD fit
 def golden_lod_fit() -> None:
     _import_ref("gd_v1")
@@ -419,7 +492,7 @@ def main() -> int:
     only = set(sys.argv[1:])
     steps = {
         "call": lambda: (golden_call("gd_v1", "det_a", "call_smoke_v1.npz"), golden_call("gd_v2", "smoke", "call_smoke_v2.npz")),
-        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbstats": golden_gb_stats,
+        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbstats": golden_gb_stats, "fastq": golden_fastq,
         "lod": golden_lod_fit,
         "dist": golden_gd_dist,
     }

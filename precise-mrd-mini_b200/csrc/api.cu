@@ -456,6 +456,61 @@ int32_t pmrd_umi_hamming(pmrd_ctx* ctx, const uint32_t* h_a, const uint32_t* h_b
 }
 
 
+// ---------------------------------------------------------------- K13 -------------------
+int32_t pmrd_fastq_scan(pmrd_ctx* ctx, const uint8_t* h_bytes, int64_t n_bytes, int64_t capacity, pmrd_fastq_records* h_out,
+                        int64_t* n_records) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n_bytes >= 0 && n_records && (n_bytes == 0 || h_bytes), "fastq: buffer");
+    *n_records = 0;
+    if (n_bytes == 0) return PMRD_OK;
+    PMRD_ARG(ctx, capacity >= 0 && h_out, "fastq: outputs");
+    const size_t c = (size_t)(capacity > 0 ? capacity : 1);
+    DevBuf buf, st, key, ho, hl, uo, ul, so, sl, qo, ql, qs;
+    PMRD_TRY(up(ctx, buf, h_bytes, (size_t)n_bytes));
+    PMRD_CUDA(ctx, st.alloc(ctx->stream, c * 4)); PMRD_CUDA(ctx, key.alloc(ctx->stream, c * 8));
+    PMRD_CUDA(ctx, ho.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, hl.alloc(ctx->stream, c * 4));
+    PMRD_CUDA(ctx, uo.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, ul.alloc(ctx->stream, c * 4));
+    PMRD_CUDA(ctx, so.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, sl.alloc(ctx->stream, c * 4));
+    PMRD_CUDA(ctx, qo.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, ql.alloc(ctx->stream, c * 4));
+    PMRD_CUDA(ctx, qs.alloc(ctx->stream, c * 8));
+    pmrd_fastq_records d{st.as<int32_t>(), key.as<uint64_t>(), ho.as<int64_t>(), hl.as<int32_t>(), uo.as<int64_t>(), ul.as<int32_t>(),
+                         so.as<int64_t>(), sl.as<int32_t>(), qo.as<int64_t>(), ql.as<int32_t>(), qs.as<int64_t>()};
+    PMRD_TRY(k13_fastq_scan(ctx, buf.as<uint8_t>(), n_bytes, capacity, &d, n_records));
+    const size_t r = (size_t)*n_records;
+    PMRD_TRY(down(ctx, h_out->status, d.status, r * 4)); PMRD_TRY(down(ctx, h_out->umi_key, d.umi_key, r * 8));
+    PMRD_TRY(down(ctx, h_out->hdr_off, d.hdr_off, r * 8)); PMRD_TRY(down(ctx, h_out->hdr_len, d.hdr_len, r * 4));
+    PMRD_TRY(down(ctx, h_out->umi_off, d.umi_off, r * 8)); PMRD_TRY(down(ctx, h_out->umi_len, d.umi_len, r * 4));
+    PMRD_TRY(down(ctx, h_out->seq_off, d.seq_off, r * 8)); PMRD_TRY(down(ctx, h_out->seq_len, d.seq_len, r * 4));
+    PMRD_TRY(down(ctx, h_out->qual_off, d.qual_off, r * 8)); PMRD_TRY(down(ctx, h_out->qual_len, d.qual_len, r * 4));
+    PMRD_TRY(down(ctx, h_out->qual_sum, d.qual_sum, r * 8));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
+int32_t pmrd_fastq_families_of(pmrd_ctx* ctx, const uint64_t* h_umi_key, const int64_t* h_qual_sum, const int32_t* h_qual_len,
+                               int64_t n_reads, pmrd_fastq_families* h_out, int64_t capacity, int64_t* n_families) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n_families != nullptr && n_reads >= 0 && n_reads < (1ll << 31), "fastq families: n_reads");
+    *n_families = 0;
+    if (n_reads == 0) return PMRD_OK;
+    PMRD_ARG(ctx, h_umi_key && h_qual_sum && h_qual_len && h_out && capacity >= 0, "fastq families: buffers");
+    const size_t n = (size_t)n_reads, c = (size_t)(capacity > 0 ? capacity : 1);
+    DevBuf keys, qs, ql, fk, ff, fb, fs, fq, fn;
+    PMRD_TRY(up(ctx, keys, h_umi_key, n * 8));
+    PMRD_TRY(up(ctx, qs, h_qual_sum, n * 8));
+    PMRD_TRY(up(ctx, ql, h_qual_len, n * 4));
+    PMRD_CUDA(ctx, fk.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, ff.alloc(ctx->stream, c * 4)); PMRD_CUDA(ctx, fb.alloc(ctx->stream, c * 4));
+    PMRD_CUDA(ctx, fs.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, fq.alloc(ctx->stream, c * 8)); PMRD_CUDA(ctx, fn.alloc(ctx->stream, c * 8));
+    pmrd_fastq_families d{fk.as<uint64_t>(), ff.as<uint32_t>(), fb.as<uint32_t>(), fs.as<int64_t>(), fq.as<int64_t>(), fn.as<int64_t>()};
+    PMRD_TRY(k13_fastq_families(ctx, keys.as<uint64_t>(), n_reads, qs.as<int64_t>(), ql.as<int32_t>(), &d, capacity, n_families));
+    const size_t F = (size_t)*n_families;
+    PMRD_TRY(down(ctx, h_out->umi_key, d.umi_key, F * 8)); PMRD_TRY(down(ctx, h_out->first_read, d.first_read, F * 4));
+    PMRD_TRY(down(ctx, h_out->best_read, d.best_read, F * 4)); PMRD_TRY(down(ctx, h_out->family_size, d.family_size, F * 8));
+    PMRD_TRY(down(ctx, h_out->qual_sum, d.qual_sum, F * 8)); PMRD_TRY(down(ctx, h_out->n_bases, d.n_bases, F * 8));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
 // ---------------------------------------------------------------- K12 -------------------
 int32_t pmrd_bootstrap_metrics(pmrd_ctx* ctx, const uint8_t* h_y_true, const double* h_y_score, int64_t n,
                                const int64_t* h_indices, int64_t n_boot, uint64_t stream_id, double* h_point,

@@ -17,6 +17,12 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
                     int64_t n_reads, const pmrd_umi_params* params, const pmrd_family_table* d_fam, int64_t capacity_f,
                     int64_t* n_families, const pmrd_group_table* d_grp, int64_t capacity_g, int64_t* n_groups);
 
+// fastq.cu
+int32_t k13_fastq_scan(pmrd_ctx* ctx, const uint8_t* d_buf, int64_t n_bytes, int64_t capacity, const pmrd_fastq_records* d_out,
+                       int64_t* h_n_records);
+int32_t k13_fastq_families(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n, const int64_t* d_qual_sum, const int32_t* d_qual_len,
+                           const pmrd_fastq_families* d_out, int64_t capacity, int64_t* h_n_fam);
+
 // metrics.cu
 int32_t k12_bootstrap_metrics(pmrd_ctx* ctx, const uint8_t* d_y, const double* d_score, int64_t n, const int64_t* d_indices,
                               int64_t n_boot, int want_point, uint64_t stream_id, double* d_auc, double* d_ap);

@@ -17,7 +17,8 @@ def __getattr__(name):
         "simulate_reads": ".simulate", "collapse_umis": ".collapse", "fit_error_model": ".error_model",
         "call_mrd": ".call", "poisson_test": ".call", "binomial_test": ".call",
         "benjamini_hochberg_correction": ".call", "roc_auc_score": ".metrics", "average_precision": ".metrics",
-        "calculate_metrics": ".metrics",
+        "calculate_metrics": ".metrics", "process_fastq_to_dataframe": ".fastq", "detect_umi_format": ".fastq",
+        "get_variant_caller": ".call",
     }
     if name in table:
         return getattr(importlib.import_module(table[name], __name__), name)

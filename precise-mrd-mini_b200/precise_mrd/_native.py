@@ -355,6 +355,37 @@ class Context:
         finally:
             plan.close()
 
+    # -- K13 -----------------------------------------------------------------------------
+    _FQ_REC = (("status", np.int32), ("umi_key", np.uint64), ("hdr_off", np.int64), ("hdr_len", np.int32), ("umi_off", np.int64),
+               ("umi_len", np.int32), ("seq_off", np.int64), ("seq_len", np.int32), ("qual_off", np.int64), ("qual_len", np.int32),
+               ("qual_sum", np.int64))
+    _FQ_FAM = (("umi_key", np.uint64), ("first_read", np.uint32), ("best_read", np.uint32), ("family_size", np.int64),
+               ("qual_sum", np.int64), ("n_bases", np.int64))
+
+    def fastq_scan(self, data: bytes) -> Dict[str, np.ndarray]:
+        """One row per 4-line FASTQ record of ``data`` (``pmrd_fastq_scan``)."""
+        buf = np.frombuffer(data, dtype=np.uint8)
+        cap = buf.shape[0] // 8 + 2           # a record has >= 4 newlines; an upper bound that needs no second call
+        out = {k: np.zeros(cap, dt) for k, dt in self._FQ_REC}
+        t = (C.c_void_p * len(self._FQ_REC))(*[out[k].ctypes.data for k, _ in self._FQ_REC])
+        n = C.c_int64(0)
+        self._check(self.lib.pmrd_fastq_scan(self.h, _ptr(buf) if buf.shape[0] else None, C.c_int64(buf.shape[0]), C.c_int64(cap),
+                                             C.byref(t), C.byref(n)))
+        return {k: v[:n.value] for k, v in out.items()}
+
+    def fastq_families(self, umi_key, qual_sum, qual_len) -> Dict[str, np.ndarray]:
+        """Per-UMI families of the kept reads, in first-appearance order (``pmrd_fastq_families_of``)."""
+        key = _arr(umi_key, np.uint64)
+        qs = _arr(qual_sum, np.int64)
+        ql = _arr(qual_len, np.int32)
+        n = key.shape[0]
+        out = {k: np.zeros(max(n, 1), dt) for k, dt in self._FQ_FAM}
+        t = (C.c_void_p * len(self._FQ_FAM))(*[out[k].ctypes.data for k, _ in self._FQ_FAM])
+        nf = C.c_int64(0)
+        self._check(self.lib.pmrd_fastq_families_of(self.h, _ptr(key), _ptr(qs), _ptr(ql), C.c_int64(n), C.byref(t), C.c_int64(n),
+                                                    C.byref(nf)))
+        return {k: v[:nf.value] for k, v in out.items()}
+
     # -- K12 -----------------------------------------------------------------------------
     def bootstrap_metrics(self, y_true, y_score, indices=None, n_boot: int = 0, stream_id: int = 0, point: bool = True):
         """(point {auc, ap} or None, auc[n_boot], ap[n_boot]).  ``indices``: [n_boot, n] resample rows."""

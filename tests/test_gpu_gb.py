@@ -281,3 +281,55 @@ def test_bootstrap_metrics_kernel_matches_sklearn_resample_for_resample(ctx):
     assert metrics.roc_auc_score(y, s) == pytest.approx(sk_auc(y, s), rel=1e-12)
     assert metrics.average_precision(y, s) == pytest.approx(average_precision_score(y, s), rel=1e-12)
     assert metrics.bootstrap_metric(y, s, lambda a, b: float(np.mean(a)), 5, np.random.default_rng(0))["mean"] > 0   # host callable
+
+
+def test_fastq_ingest_matches_reference(ctx, smoke_cfg, tmp_path):
+    """K13 (fastq.py): the device scan + family table on a synthetic FASTQ with every header
+    convention, CRLF records, malformed records, UMI-less reads, >12-letter UMIs and a blank-line
+    end -- against what the reference's own fastq.py produced for the same file."""
+    import gzip
+
+    from precise_mrd.collapse import collapse_umis
+    from precise_mrd.fastq import FASTQReader, detect_umi_format, process_fastq_to_dataframe
+
+    path = ROOT / "tests" / "golden" / "fastq_mixed.fastq"
+    want = json.loads((ROOT / "tests" / "golden" / "fastq_mixed.json").read_text())
+    reader = FASTQReader(path)
+    reads = list(reader.read_fastq())
+    assert len(reads) == len(want["reads"])
+    for got, w in zip(reads, want["reads"]):
+        assert (got["read_id"], got["sequence"], got["umi"], got["sequence_length"]) == (w["read_id"], w["sequence"], w["umi"], w["sequence_length"])
+        assert got["mean_quality"] == w["mean_quality"] and sum(got["quality_scores"]) == w["qual_sum"]
+    assert [r["read_id"] for r in reader.read_fastq(max_reads=50)] == want["reads_max_50"]
+    v = reader.validate_fastq()
+    for k, w in want["validate"].items():
+        assert v[k] == (pytest.approx(w, rel=1e-15) if isinstance(w, float) else w), k
+    for tag, mr in (("all", None), ("max_300", 300)):
+        df = process_fastq_to_dataframe(path, smoke_cfg, np.random.default_rng(0), max_reads=mr)
+        w = want[f"table_{tag}"]
+        assert list(df.columns) == w["columns"]
+        for col in ("sample_id", "umi", "family_size", "consensus_sequence", "consensus_agreement", "passes_quality", "passes_consensus"):
+            assert df[col].tolist() == w[col], (tag, col)
+        assert df["mean_quality"].tolist() == w["mean_quality"]                       # exact: integer sums, one division
+        assert [sum(q) for q in df["quality_scores"]] == w["quality_scores_sum"]
+        assert [q[:5] for q in df["quality_scores"]] == w["quality_scores_head"]
+        assert (df["config_hash"] == smoke_cfg.config_hash()).all()
+    assert detect_umi_format(path, 100) == want["format"]
+    # gzip input and the hand-off to collapse_umis(is_fastq_data=True) (collapse.py:46-64)
+    gz = tmp_path / "mixed.fastq.gz"
+    gz.write_bytes(gzip.compress(path.read_bytes()))
+    df_gz = process_fastq_to_dataframe(gz, smoke_cfg, np.random.default_rng(0), output_path=str(tmp_path / "fq.parquet"))
+    assert df_gz["umi"].tolist() == want["table_all"]["umi"] and (tmp_path / "fq.parquet").exists()
+    collapsed = collapse_umis(df_gz, smoke_cfg, np.random.default_rng(0), is_fastq_data=True)
+    assert len(collapsed) == len(df_gz) and collapsed["family_size"].tolist() == want["table_all"]["family_size"]
+    # scalar helpers and empty / UMI-less input
+    assert reader.extract_umi("@x UMI: UMI:ACGT z") == "ACGT" and reader.extract_umi("@a_ACGTACGTA_b") == "ACGTACGTA"
+    assert reader.extract_umi("@a:b:ACGTACGTAC") == "ACGTACGTAC" and reader.extract_umi("@a_ACGTACGTACGTA_") is None
+    assert reader.parse_quality_string("I5!") == [40, 20, 0]
+    empty = tmp_path / "empty.fastq"
+    empty.write_text("")
+    assert list(FASTQReader(empty).read_fastq()) == [] and detect_umi_format(empty) == "No UMI detected in sample"
+    plain = tmp_path / "plain.fastq"
+    plain.write_text("@r1\nACGT\n+\nIIII\n@r2\nAC\n+\nII")                            # no UMIs, no trailing newline
+    assert [r["read_id"] for r in FASTQReader(plain).read_fastq()] == ["r1", "r2"]
+    assert process_fastq_to_dataframe(plain, smoke_cfg, np.random.default_rng(0)).empty
