@@ -3,14 +3,29 @@
 // precise-mrd-mini/src/mrd/umi.py:65-67 (groupby), rust_ext/src/lib.rs:7-22 (FNV map).
 #include "radix_sort.cuh"
 #include <stdlib.h>
-// peer masks: MATCH.ANY on the top RS_HYBRID_MATCH_BITS digit bits + ballots on the rest (measured on
-// B200, 1.85e8 records: 0 bits 3.70 ms / 3 passes, 2 bits 3.58, 3 bits 3.49, 4 bits 3.81, 8 bits (pure MATCH) 4.07)
-#ifndef RS_HYBRID_MATCH_BITS
-#define RS_HYBRID_MATCH_BITS 3
-#endif
 #ifndef RS_DIRECT_MIN_BLOCKS
 #define RS_DIRECT_MIN_BLOCKS 3
 #endif
+
+// Peer mask of a warp-wide digit: the lanes holding the same 8-bit digit as the caller.
+// Eight ballots, each written so that ONE predicate feeds both the vote and the select -- ptxas then
+// moves all eight digit bits into predicates with a single R2P and spends three instructions per bit
+// (VOTE, SEL, LOP3).  The C++ form `m &= bit ? bal : ~bal` costs six per bit, and MATCH.ANY on the
+// whole digit saturates the ADU pipe (ncu: 88 %).  Measured on B200, direct downsweep, 2.13e9 records x 3
+// passes: C++ ballots + MATCH on the top 3 bits 34.5 ms; this form 28.3 ms (MATCH on the top 1-2 bits: same;
+// 3 bits 29.1; 4 bits 31.1).
+__device__ __forceinline__ uint32_t rs_peer_mask(uint32_t d, uint32_t m) {
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, bal, x;\n\t"
+                     "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+                     "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+                     "selp.b32 x, 0, 0xffffffff, p;\n\t"
+                     "lop3.b32 %0, %0, bal, x, 0x60;\n\t}"      // m & (bal ^ x)
+                     : "+r"(m) : "r"(d), "r"(1u << b));
+    }
+    return m;
+}
 
 // ---------------------------------------------------------------- varying bits ----------
 __global__ void __launch_bounds__(256) rs_varying_kernel(const uint64_t* __restrict__ keys, int64_t n,
@@ -203,16 +218,9 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
         const int loc = wloc + i * 32 + (int)lane;
         const bool valid = loc < tile_n;
         const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & mask) : 0xffffffffu;
-        // peers = lanes holding the same digit.  MATCH.ANY runs on the address-divergence unit at a
-        // cost proportional to the number of distinct values (~30 for a random 8-bit digit; ncu: ADU
-        // pipe 88 % busy), ballots + logic ops run on the ALU: match the top bits, ballot the rest.
-        uint32_t m = __match_any_sync(0xffffffffu, valid ? (d >> (8 - RS_HYBRID_MATCH_BITS)) : 0xffffffffu);
-#pragma unroll
-        for (int b = 0; b < 8 - RS_HYBRID_MATCH_BITS; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-            m &= bit ? bal : ~bal;
-        }
+        // peers = lanes holding the same digit (lanes past the end of the input form their own group)
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        const uint32_t m = rs_peer_mask(d, valid ? vmask : ~vmask);
         const uint32_t before = __popc(m & lt);
         // the lowest lane of each digit group bumps the warp's counter once for the whole group and
         // hands the old value to its peers by shuffle: one shared atomic + one shuffle per item,
@@ -279,55 +287,32 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
 // few MB and its tiles are processed back to back, so the partially written 32-byte sectors meet
 // in L2 before they are evicted (DRAM write traffic stays at 8 B / record -- checked with ncu),
 // and the shared-memory reorder (a bank-conflicted 64-bit scatter + a gather + a barrier) is gone.
+// (whole tiles only: the cell-major layout pads every cell to a multiple of RS_TILE)
 __global__ void __launch_bounds__(RS_THREADS, RS_DIRECT_MIN_BLOCKS)
 rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
-                           const uint32_t* __restrict__ hist_scanned, int64_t n, int shift, uint32_t mask) {
+                           const uint32_t* __restrict__ hist_scanned, int shift, uint32_t mask) {
     __shared__ uint32_t s_cnt[RS_WARPS][RS_MAX_BINS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = lanemask_lt();
     for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
-    const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
-    const int64_t rem = n - tile_base;
-    const int tile_n = rem < RS_TILE ? (int)rem : RS_TILE;
-    const int wloc = (int)warp * (RS_TILE / RS_WARPS);
+    const uint64_t* __restrict__ src = keys_in + (int64_t)blockIdx.x * RS_TILE + warp * (RS_TILE / RS_WARPS) + lane;
     uint64_t key[RS_ITEMS];
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const int loc = wloc + i * 32 + (int)lane;
-        key[i] = (loc < tile_n) ? keys_in[tile_base + loc] : ~0ull;
-    }
+    for (int i = 0; i < RS_ITEMS; ++i) key[i] = src[i * 32];
     __syncthreads();
-    uint16_t rank[RS_ITEMS];
+    uint32_t rank2[RS_ITEMS / 2];   // two 16-bit ranks per register
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const int loc = wloc + i * 32 + (int)lane;
-        const bool valid = loc < tile_n;
-        const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & mask) : 0xffffffffu;
-#if RS_HYBRID_MATCH_BITS > 0
-        // hybrid: MATCH.ANY on the top bits (few distinct values => cheap on the ADU pipe), ballots below
-        uint32_t m = __match_any_sync(0xffffffffu, valid ? (d >> (8 - RS_HYBRID_MATCH_BITS)) : 0xffffffffu);
-#pragma unroll
-        for (int b = 0; b < 8 - RS_HYBRID_MATCH_BITS; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-            m &= bit ? bal : ~bal;
-        }
-#else
-        uint32_t m = __ballot_sync(0xffffffffu, valid);
-        if (!valid) m = ~m;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) {
-            const bool bit = (d >> b) & 1u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-            m &= bit ? bal : ~bal;
-        }
-#endif
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        const uint32_t m = rs_peer_mask(d, 0xffffffffu);
         const uint32_t before = __popc(m & lt);
         const int leader = __ffs((int)m) - 1;
         uint32_t old = 0;
-        if (valid && before == 0) old = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(m));
+        if (before == 0) old = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(m));
         old = __shfl_sync(0xffffffffu, old, leader);
-        rank[i] = (uint16_t)(old + before);
+        const uint32_t r = old + before;
+        if (i & 1) rank2[i >> 1] |= r << 16;
+        else rank2[i >> 1] = r;
     }
     __syncthreads();
     // per bin: global start of this tile's run + exclusive prefix over the warps
@@ -343,11 +328,9 @@ rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const int loc = wloc + i * 32 + (int)lane;
-        if (loc < tile_n) {
-            const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
-            keys_out[s_cnt[warp][d] + rank[i]] = key[i];
-        }
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        const uint32_t r = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
+        keys_out[s_cnt[warp][d] + r] = key[i];
     }
 }
 
@@ -423,7 +406,7 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
         } else if (direct) {   // packed 8-byte records, stored straight to their final place (L2 merges the sectors)
-            PMRD_LAUNCH(ctx, rs_downsweep_direct_kernel, n_tiles, RS_THREADS, 0, kin, kout, hist.as<uint32_t>(), n, shift, mask);
+            PMRD_LAUNCH(ctx, rs_downsweep_direct_kernel, n_tiles, RS_THREADS, 0, kin, kout, hist.as<uint32_t>(), shift, mask);
         } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
         }
