@@ -53,29 +53,75 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const TIn* __
     if (threadIdx.x == 0) sums[blockIdx.x] = tot;
 }
 
+// Layout of the apply pass: a warp owns 512 consecutive items as 4 groups of 128; lane l holds the 4
+// consecutive items [group * 128 + 4 l, +4) of each group, so a 4-byte input is one 16-byte load per
+// group and the outputs of a warp form contiguous 512-byte (u32) / 1-KB (u64) runs.
 template <typename TIn, typename T>
 __global__ void __launch_bounds__(SCAN_THREADS)
 scan_apply_kernel(const TIn* __restrict__ in, T* __restrict__ out, const T* __restrict__ block_offsets, int64_t n, T* __restrict__ total_out) {
-    __shared__ T sw[33];
-    const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-    T v[SCAN_ITEMS];
-    T acc = 0;
+    __shared__ T s_warp[SCAN_THREADS / 32 + 1];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t wbase = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)warp * (SCAN_TILE / (SCAN_THREADS / 32));
+    T v[4][4], s[4], incl[4];
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        int64_t idx = base + i;
-        v[i] = (idx < n) ? (T)in[idx] : T(0);
-        acc += v[i];
-    }
-    T tot;
-    T excl = block_exclusive_scan<T>(acc, sw, tot);
-    T off = (block_offsets ? block_offsets[blockIdx.x] : T(0)) + excl;
+    for (int j = 0; j < 4; ++j) {
+        const int64_t idx = wbase + j * 128 + lane * 4;
+        if (sizeof(TIn) == 4 && idx + 3 < n) {
+            const uint4 q = *reinterpret_cast<const uint4*>(in + idx);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        int64_t idx = base + i;
-        if (idx < n) out[idx] = off;
-        off += v[i];
+            for (int k = 0; k < 4; ++k) { TIn t; memcpy(&t, &w[k], sizeof(TIn) < 4 ? sizeof(TIn) : 4); v[j][k] = (T)t; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[j][k] = (idx + k < n) ? (T)in[idx + k] : T(0);
+        }
+        s[j] = v[j][0] + v[j][1] + v[j][2] + v[j][3];
+        incl[j] = s[j];
     }
-    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1) *total_out = off;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const T t = __shfl_up_sync(0xffffffffu, incl[j], o);
+            if (lane >= (uint32_t)o) incl[j] += t;
+        }
+    }
+    T carry[4], wtot = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        carry[j] = wtot;
+        wtot += __shfl_sync(0xffffffffu, incl[j], 31);
+    }
+    if (lane == 0) s_warp[warp] = wtot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T run = block_offsets ? block_offsets[blockIdx.x] : T(0);
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) { const T c = s_warp[w]; s_warp[w] = run; run += c; }
+        s_warp[SCAN_THREADS / 32] = run;
+    }
+    __syncthreads();
+    const T wexcl = s_warp[warp];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int64_t idx = wbase + j * 128 + lane * 4;
+        T off = wexcl + carry[j] + incl[j] - s[j];
+        T o4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { o4[k] = off; off += v[j][k]; }
+        if (idx + 3 < n && sizeof(T) == 8) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + idx);
+            dst[0] = make_ulonglong2((unsigned long long)o4[0], (unsigned long long)o4[1]);
+            dst[1] = make_ulonglong2((unsigned long long)o4[2], (unsigned long long)o4[3]);
+        } else if (idx + 3 < n && sizeof(T) == 4) {
+            *reinterpret_cast<uint4*>(out + idx) = make_uint4((uint32_t)o4[0], (uint32_t)o4[1], (uint32_t)o4[2], (uint32_t)o4[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (idx + k < n) out[idx + k] = o4[k];
+        }
+    }
+    if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) *total_out = s_warp[SCAN_THREADS / 32];
 }
 
 // out[i] = sum_{j<i} in[j]; in == out allowed when TIn == T.  total_out (device, optional)
