@@ -344,7 +344,8 @@ struct VoteS {
 // but each in input order (the sort is stable).  One thread owns a run and peels its families.
 template <bool FULL>
 __global__ void __launch_bounds__(CC_THREADS)
-cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restrict__ cell_tile_start, int n_cells,
+cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restrict__ cell_tile_start,
+                      const int32_t* __restrict__ tile_cell /* cell of every tile (host-built) or NULL */, int n_cells,
                       pmrd_umi_params P, uint32_t run_mask, int64_t cell0, const uint8_t* __restrict__ alt_allele,
                       unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot,
                       unsigned long long* __restrict__ o_var) {
@@ -359,7 +360,9 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     const int64_t base = tile * CC_TILE;
     if (threadIdx.x < 3) s_acc[threadIdx.x] = 0ull;
     if (threadIdx.x < 64) s_wt[threadIdx.x] = (int)threadIdx.x >= P.quality_threshold ? c_wtab[threadIdx.x] : 0.0;
-    if (threadIdx.x == 0) {   // which cell owns this tile
+    if (tile_cell) {
+        if (threadIdx.x == 0) s_cell = tile_cell[tile];
+    } else if (threadIdx.x == 0) {   // which cell owns this tile
         int lo = 0, hi = n_cells;
         while (hi - lo > 1) {
             const int mid = (lo + hi) >> 1;
@@ -478,9 +481,9 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
 
 // segmented sort of packed records + fused consensus/count; outputs accumulate into the per-cell arrays
 int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d_rec_tmp, int64_t n_out,
-                                     const pmrd_umi_params* params, const int64_t* d_cell_tile_start, int64_t n_cells,
-                                     int sort_bits, int umi_bits, int64_t cell0, const uint8_t* d_alt_allele, int64_t* d_o_fam,
-                                     int64_t* d_o_tot, int64_t* d_o_var) {
+                                     const pmrd_umi_params* params, const int64_t* d_cell_tile_start, const int32_t* d_tile_cell,
+                                     int64_t n_cells, int sort_bits, int umi_bits, int64_t cell0, const uint8_t* d_alt_allele,
+                                     int64_t* d_o_fam, int64_t* d_o_tot, int64_t* d_o_var) {
     if (n_out <= 0) return PMRD_OK;
     PMRD_ARG(ctx, n_out % CC_TILE == 0, "segmented collapse: input must be whole tiles");
     int in_b = 0;
@@ -489,10 +492,10 @@ int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d
     const uint32_t run_mask = sort_bits >= 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
     const int grid = (int)(n_out / CC_TILE);
     if (sort_bits >= umi_bits) {
-        PMRD_LAUNCH(ctx, cell_consensus_kernel<true>, grid, CC_THREADS, 0, sr, d_cell_tile_start, (int)n_cells, *params, 0xffffffffu,
+        PMRD_LAUNCH(ctx, cell_consensus_kernel<true>, grid, CC_THREADS, 0, sr, d_cell_tile_start, d_tile_cell, (int)n_cells, *params, 0xffffffffu,
                     cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot, (unsigned long long*)d_o_var);
     } else {
-        PMRD_LAUNCH(ctx, cell_consensus_kernel<false>, grid, CC_THREADS, 0, sr, d_cell_tile_start, (int)n_cells, *params, run_mask,
+        PMRD_LAUNCH(ctx, cell_consensus_kernel<false>, grid, CC_THREADS, 0, sr, d_cell_tile_start, d_tile_cell, (int)n_cells, *params, run_mask,
                     cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot, (unsigned long long*)d_o_var);
     }
     return PMRD_OK;

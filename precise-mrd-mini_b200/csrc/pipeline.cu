@@ -20,7 +20,8 @@ int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pa
                                  const int64_t* d_cell_tile_start, int64_t n_seg_cells, int seg_key_bits);
 
 int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d_rec_tmp, int64_t n_out,
-                                     const pmrd_umi_params* params, const int64_t* d_cell_tile_start, int64_t n_cells,
+                                     const pmrd_umi_params* params, const int64_t* d_cell_tile_start, const int32_t* d_tile_cell,
+                                     int64_t n_cells,
                                      int sort_bits, int umi_bits, int64_t cell0, const uint8_t* d_alt_allele, int64_t* d_o_fam,
                                      int64_t* d_o_tot, int64_t* d_o_var);
 
@@ -256,7 +257,8 @@ static int32_t chunk_collapse(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
         // cell-major input: per-cell 3-pass sort, then ONE kernel from sorted reads to per-cell counts
         // (packed 8-byte records: P->keys / P->keys_tmp are the ping-pong pair, no payload arrays)
         return k5_collapse_counts_segmented(ctx, P->keys.as<uint64_t>(), P->keys_tmp.as<uint64_t>(), ch->reads.n_out, &P->up,
-                                            (const int64_t*)ch->reads.cell_tile_start.as<int64_t>(), ch->n_cells, P->sort_bits, 24,
+                                            (const int64_t*)ch->reads.cell_tile_start.as<int64_t>(),
+                                            (const int32_t*)ch->reads.tile_cell.as<int32_t>(), ch->n_cells, P->sort_bits, 24,
                                             ch->cell0, (const uint8_t*)P->alt.as<uint8_t>(), P->o_fam.as<int64_t>(),
                                             P->o_tot.as<int64_t>(), P->o_var.as<int64_t>());
     }

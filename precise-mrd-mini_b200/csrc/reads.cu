@@ -29,13 +29,10 @@ __device__ __forceinline__ int find_cell_in(const int64_t* __restrict__ fam_offs
 __device__ __forceinline__ int find_cell(const int64_t* __restrict__ fam_offsets, int n_cells, int64_t f) {
     return find_cell_in(fam_offsets, 0, n_cells, f);
 }
-// A block owns consecutive families [f0, f1]: two threads bracket the cells they can fall in,
-// so that the per-family search runs over (almost always) one or two cells, not all of them.
-__device__ __forceinline__ void block_cell_range(const int64_t* __restrict__ fam_offsets, int n_cells, int64_t f0, int64_t f1,
-                                                 int* s_range /* shared int[2] */) {
-    if (threadIdx.x < 2) s_range[threadIdx.x] = find_cell(fam_offsets, n_cells, threadIdx.x == 0 ? f0 : f1);
-    __syncthreads();
-}
+// A block owns READS_FAM_BLOCK consecutive families.  blk_cell[b] = cell of the block's first family
+// (built once on the host with the plan), so the per-family search runs over the cells
+// [blk_cell[b], blk_cell[b + 1]] -- almost always one or two -- instead of all of them.
+#define READS_FAM_BLOCK 256
 
 struct FamDraw {
     int size;
@@ -92,15 +89,14 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
 __global__ void __launch_bounds__(256)
 reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                   int64_t n_fam, pmrd_read_sim_params sp, const float* __restrict__ size_cdf /* [128] or NULL */,
-                  uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word) {
-    __shared__ int s_range[2];
+                  const int32_t* __restrict__ blk_cell, uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word) {
     __shared__ float s_cdf[128];
-    const int64_t f0 = (int64_t)blockIdx.x * blockDim.x, f = f0 + threadIdx.x;
+    const int64_t f = (int64_t)blockIdx.x * READS_FAM_BLOCK + threadIdx.x;
     if (size_cdf && threadIdx.x < 128) s_cdf[threadIdx.x] = size_cdf[threadIdx.x];
-    block_cell_range(fam_offsets, n_cells, f0, min(f0 + (int64_t)blockDim.x, n_fam) - 1, s_range);
+    __syncthreads();
     if (f >= n_fam) return;
     const Philox ph(seed);
-    const int ci = find_cell_in(fam_offsets, s_range[0], s_range[1] + 1, f);
+    const int ci = find_cell_in(fam_offsets, blk_cell[blockIdx.x], blk_cell[blockIdx.x + 1] + 1, f);
     const ReadCell c = cells[ci];
     const FamDraw d = draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp, size_cdf ? s_cdf : nullptr);
     fam_size[f] = (uint32_t)d.size;
@@ -191,23 +187,21 @@ struct FamSlot {
 __global__ void __launch_bounds__(256)
 reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                  int64_t n_fam, pmrd_read_sim_params sp, const uint64_t* __restrict__ read_offset /*[n_fam]*/,
-                 const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_word,
+                 const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_word, const int32_t* __restrict__ blk_cell,
                  int64_t n_reads, int segmented, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
     __shared__ FamSlot s_slot[8][32];
     __shared__ uint32_t s_qthr[32];
     __shared__ uint8_t s_qlut[256];
-    __shared__ int s_range[2];
     if (threadIdx.x < 32) s_qthr[threadIdx.x] = c_qual_thr[threadIdx.x];
     s_qlut[threadIdx.x] = c_qual_lut[threadIdx.x];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t f0 = (int64_t)blockIdx.x * 256, f = f0 + threadIdx.x;
-    block_cell_range(fam_offsets, n_cells, f0, min(f0 + 256, n_fam) - 1, s_range);
+    const int64_t f = (int64_t)blockIdx.x * READS_FAM_BLOCK + threadIdx.x;
     const Philox ph(seed);
     const bool valid = f < n_fam;
     int64_t off = 0;
     uint32_t size = 0;
     if (valid) {
-        const int ci = find_cell_in(fam_offsets, s_range[0], s_range[1] + 1, f);
+        const int ci = find_cell_in(fam_offsets, blk_cell[blockIdx.x], blk_cell[blockIdx.x + 1] + 1, f);
         const ReadCell c = cells[ci];
         const uint32_t fam = (uint32_t)(f - c.fam_offset);
         off = (int64_t)read_offset[f];
@@ -368,6 +362,21 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->fam_offsets.p, ho, 8 * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = plan->cell_tile_start.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
+    // cell of the first family of every READS_FAM_BLOCK-family block (+ a closing entry)
+    const int64_t n_blk = (nf + READS_FAM_BLOCK - 1) / READS_FAM_BLOCK;
+    int32_t* h_blk = (int32_t*)malloc(4 * (size_t)(n_blk + 1));
+    if (!h_blk) { free(hc); free(ho); PMRD_ARG(ctx, false, "out of host memory"); }
+    {
+        int64_t c = 0;
+        for (int64_t b = 0; b < n_blk; ++b) {
+            const int64_t f = b * READS_FAM_BLOCK;
+            while (c + 1 < n_cells && ho[c + 1] <= f) ++c;     // last cell whose first family is <= f
+            h_blk[b] = (int32_t)c;
+        }
+        h_blk[n_blk] = (int32_t)(n_cells > 0 ? n_cells - 1 : 0);
+    }
+    if (e == cudaSuccess) e = plan->blk_cell.alloc(ctx->stream, 4 * (size_t)(n_blk + 1));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(plan->blk_cell.p, h_blk, 4 * (size_t)(n_blk + 1), cudaMemcpyHostToDevice, ctx->stream);
     float h_cdf[128];
     plan->has_size_cdf = sp->family_model == 1 && sp->mean_family_size <= 16.0;
     if (plan->has_size_cdf) {
@@ -382,6 +391,7 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         if (e == cudaSuccess) e = cudaMemcpyAsync(plan->size_cdf.p, h_cdf, sizeof(h_cdf), cudaMemcpyHostToDevice, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    free(h_blk);
     if (e != cudaSuccess) {
         free(hc); free(ho);
         snprintf(ctx->err, sizeof(ctx->err), "read plan: %s", cudaGetErrorString(e));
@@ -426,7 +436,17 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         plan->n_out = plan->segmented ? tile * READS_SEG_TILE : plan->n_reads;
         e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cell_tile_start.p, h_tile, 8 * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, ctx->stream);
+        // cell of every tile (the consensus kernel would otherwise binary-search it, one thread per block)
+        int32_t* h_tc = (int32_t*)malloc(4 * (size_t)(tile + 1));
+        if (!h_tc) e = cudaErrorMemoryAllocation;
+        else {
+            for (int64_t i = 0; i < n_cells; ++i)
+                for (int64_t t = h_tile[i]; t < h_tile[i + 1]; ++t) h_tc[t] = (int32_t)i;
+            if (e == cudaSuccess) e = plan->tile_cell.alloc(ctx->stream, 4 * (size_t)(tile + 1));
+            if (e == cudaSuccess) e = cudaMemcpyAsync(plan->tile_cell.p, h_tc, 4 * (size_t)tile, cudaMemcpyHostToDevice, ctx->stream);
+        }
         if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        free(h_tc);
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "read plan: %s", cudaGetErrorString(e)); st = PMRD_ERR_CUDA; }
     }
     free(hc); free(ho); free(h_cnt); free(h_tile);
@@ -436,10 +456,10 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
 // family sizes + read offsets (device only, no sync): part of every simulate step
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
     if (plan->n_fam <= 0) return PMRD_OK;
-    PMRD_LAUNCH(ctx, reads_size_kernel, pmrd_blocks(plan->n_fam, 256), 256, 0, ctx->seed, plan->cells.as<ReadCell>(),
+    PMRD_LAUNCH(ctx, reads_size_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
                 plan->has_size_cdf ? (const float*)plan->size_cdf.as<float>() : (const float*)nullptr,
-                plan->fam_size.as<uint32_t>(), plan->fam_word.as<uint32_t>());
+                (const int32_t*)plan->blk_cell.as<int32_t>(), plan->fam_size.as<uint32_t>(), plan->fam_word.as<uint32_t>());
     return exclusive_scan<uint32_t, uint64_t>(ctx, plan->fam_size.as<uint32_t>(), plan->read_offset.as<uint64_t>(), plan->n_fam,
                                               plan->total.as<uint64_t>());
 }
@@ -447,10 +467,11 @@ int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
 // generate the reads (device only, no sync); capacity must be >= plan->n_out
 int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload) {
     if (plan->n_fam <= 0) return PMRD_OK;
-    PMRD_LAUNCH(ctx, reads_gen_kernel, pmrd_blocks(plan->n_fam, 256), 256, 0, ctx->seed, plan->cells.as<ReadCell>(),
+    PMRD_LAUNCH(ctx, reads_gen_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
                 (const uint64_t*)plan->read_offset.as<uint64_t>(), (const uint32_t*)plan->fam_size.as<uint32_t>(),
-                (const uint32_t*)plan->fam_word.as<uint32_t>(), plan->n_reads, plan->segmented, d_keys, d_payload);
+                (const uint32_t*)plan->fam_word.as<uint32_t>(), (const int32_t*)plan->blk_cell.as<int32_t>(), plan->n_reads,
+                plan->segmented, d_keys, d_payload);
     if (plan->segmented && plan->n_out > plan->n_reads)
         PMRD_LAUNCH(ctx, reads_pad_kernel, (int)plan->n_cells, 256, 0, plan->cells.as<ReadCell>(), (int)plan->n_cells,
                     (const int64_t*)plan->cell_tile_start.as<int64_t>(), d_keys, d_payload);
