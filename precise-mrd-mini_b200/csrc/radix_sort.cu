@@ -92,8 +92,10 @@ RadixPlan radix_make_plan(uint64_t varying) {
 // ---------------------------------------------------------------- upsweep ---------------
 // hist[tile][256] (tile-major: one coalesced 1 KB row per tile)
 __global__ void __launch_bounds__(RS_THREADS)
-rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ hist, int shift, uint32_t mask) {
+rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ hist, int shift, uint32_t mask,
+                  uint16_t* __restrict__ tile_excl /* optional: exclusive scan of the tile's own histogram */) {
     __shared__ uint32_t s_hist[RS_WARPS][RS_MAX_BINS];
+    __shared__ uint32_t sw[33];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -120,11 +122,16 @@ rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __rest
         if (d1 != 0xffffffffu) atomicAdd(&s_hist[warp][d1], 1u);
     }
     __syncthreads();
+    uint32_t c = 0;
     if (threadIdx.x < RS_MAX_BINS) {
-        uint32_t c = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) c += s_hist[w][threadIdx.x];
         hist[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] = c;
+    }
+    if (tile_excl) {   // (uniform) where each digit's run starts inside the tile: the staged downsweep needs it
+        uint32_t tot;
+        const uint32_t e = block_exclusive_scan<uint32_t>(c, sw, tot);
+        if (threadIdx.x < RS_MAX_BINS) tile_excl[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] = (uint16_t)e;
     }
 }
 
@@ -334,6 +341,75 @@ rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
     }
 }
 
+// ---------------------------------------------------------------- staged downsweep ------
+// Same ranking, but the tile is first put in digit order in shared memory and then written out
+// position by position, so that a warp's store covers a few contiguous digit runs instead of 32
+// scattered records.  Worth its shared-memory round trip only when the INPUT is scattered: on the
+// first pass over generator output a direct warp store touches 30.5 distinct 32-byte sectors
+// (the kernel is bound by that L1->L2 sector rate), here ~10; on later passes the first pass has
+// already clustered each family's reads and the direct kernel is the faster one.
+struct RsStage {
+    uint32_t cnt[RS_WARPS][RS_MAX_BINS];
+    uint64_t rec[RS_TILE];
+    uint32_t delta[RS_MAX_BINS];
+};
+__global__ void __launch_bounds__(RS_THREADS, RS_DIRECT_MIN_BLOCKS)
+rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
+                           const uint32_t* __restrict__ hist_scanned, const uint16_t* __restrict__ tile_excl, int shift,
+                           uint32_t mask) {
+    extern __shared__ __align__(16) unsigned char rs_stage_raw[];
+    RsStage& S = *reinterpret_cast<RsStage*>(rs_stage_raw);
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = lanemask_lt();
+    for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&S.cnt[0][0])[i] = 0;
+    const uint64_t* __restrict__ src = keys_in + (int64_t)blockIdx.x * RS_TILE + warp * (RS_TILE / RS_WARPS) + lane;
+    uint64_t key[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) key[i] = src[i * 32];
+    __syncthreads();
+    uint32_t rank2[RS_ITEMS / 2];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        const uint32_t m = rs_peer_mask(d, 0xffffffffu);
+        const uint32_t before = __popc(m & lt);
+        const int leader = __ffs((int)m) - 1;
+        uint32_t old = 0;
+        if (before == 0) old = atomicAdd(&S.cnt[warp][d], (uint32_t)__popc(m));
+        old = __shfl_sync(0xffffffffu, old, leader);
+        const uint32_t r = old + before;
+        if (i & 1) rank2[i >> 1] |= r << 16;
+        else rank2[i >> 1] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < RS_MAX_BINS) {
+        const int64_t row = (int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x;
+        uint32_t run = tile_excl[row];                           // start of the digit's run inside the tile
+        S.delta[threadIdx.x] = hist_scanned[row] - run;          // tile position -> global position
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            const uint32_t c = S.cnt[w][threadIdx.x];
+            S.cnt[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
+        const uint32_t r = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
+        S.rec[S.cnt[warp][d] + r] = key[i];
+    }
+    __syncthreads();
+    uint64_t* __restrict__ dst = keys_out;
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint32_t j = i * RS_THREADS + threadIdx.x;
+        const uint64_t k = S.rec[j];
+        dst[j + S.delta[(uint32_t)(k >> shift) & mask]] = k;
+    }
+}
+
 // ---------------------------------------------------------------- segmented scan --------
 // Cell-major input (each cell = whole tiles [t0, t1)): every cell is an independent sort, so
 // the scan restarts at each cell -- one block per cell, thread d owns digit d.
@@ -372,6 +448,7 @@ static int32_t rs_set_attrs(pmrd_ctx* ctx) {
     if (!attr_set) {
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage)));
         attr_set = true;
     }
     return PMRD_OK;
@@ -392,19 +469,29 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
     PMRD_CUDA(ctx, hist.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
     uint64_t* kin = keys_a; uint32_t* vin = vals_a; uint64_t* kout = keys_b; uint32_t* vout = vals_b;
     const int n_passes = (key_bits + 7) / 8;
-    static int direct = -1;
+    static int direct = -1, staged = 1;
     if (direct < 0) {
         const char* e = getenv("PMRD_RS_DIRECT");
         direct = e ? atoi(e) : 1;
+        e = getenv("PMRD_RS_STAGED");
+        if (e) staged = atoi(e);
     }
+    DevBuf texcl;
+    if (!vals_a && direct && staged) PMRD_CUDA(ctx, texcl.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint16_t)));
     for (int p = 0; p < n_passes; ++p) {
         const int shift = p * 8;
         const int w = key_bits - shift < 8 ? key_bits - shift : 8;
         const uint32_t mask = (1u << w) - 1u;
-        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask);
+        // bit p of `staged`: pass p goes through the shared-memory staged scatter (default: the first pass only)
+        const bool stage = !vals_a && direct && ((staged >> p) & 1);
+        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask,
+                    stage ? texcl.as<uint16_t>() : (uint16_t*)nullptr);
         PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256, 0, hist.as<uint32_t>(), d_cell_tile_start, (int)n_cells);
         if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
+        } else if (stage) {
+            PMRD_LAUNCH(ctx, rs_downsweep_staged_kernel, n_tiles, RS_THREADS, sizeof(RsStage), kin, kout, hist.as<uint32_t>(),
+                        (const uint16_t*)texcl.as<uint16_t>(), shift, mask);
         } else if (direct) {   // packed 8-byte records, stored straight to their final place (L2 merges the sectors)
             PMRD_LAUNCH(ctx, rs_downsweep_direct_kernel, n_tiles, RS_THREADS, 0, kin, kout, hist.as<uint32_t>(), shift, mask);
         } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits
@@ -444,7 +531,7 @@ int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint
     for (int p = 0; p < plan.n_passes; ++p) {
         const int shift = plan.shift[p];
         const uint32_t mask = (1u << plan.bits[p]) - 1u;
-        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask);
+        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask, (uint16_t*)nullptr);
         PMRD_LAUNCH(ctx, rs_colsum_kernel, n_chunks, 256, 0, hist.as<uint32_t>(), n_tiles, chunk, colsum.as<uint32_t>());
         PMRD_LAUNCH(ctx, rs_colbase_kernel, 1, 256, 0, colsum.as<uint32_t>(), n_chunks);
         PMRD_LAUNCH(ctx, rs_colapply_kernel, n_chunks, 256, 0, hist.as<uint32_t>(), n_tiles, chunk, colsum.as<uint32_t>());
