@@ -107,21 +107,23 @@ reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64
 
 // cdf of q = max(10, min(40, int(N(30,5)))) in units of 2^-24: c_qual_thr[k] = P(q <= 10 + k), k = 0..29
 __constant__ uint32_t c_qual_thr[32];
-// coarse inverse of that cdf: c_qual_lut[b] = #{k < 30 : T[k] <= b << 16}
-__constant__ uint8_t c_qual_lut[256];
+// 4096-bucket inverse of that cdf: c_qual_lut[b] = #{k < 30 : T[k] <= b << 12}; a bucket holds a
+// threshold with probability 30 / 4096, so the walk after the lookup almost never takes a step
+#define QUAL_LUT_BITS 12
+__device__ __align__(16) uint8_t c_qual_lut[1 << QUAL_LUT_BITS];   // global, not __constant__: every thread copies its own 16 bytes
 
 int32_t reads_upload_tables(pmrd_ctx* ctx) {
     uint32_t h[32];
-    uint8_t lut[256];
+    static uint8_t lut[1 << QUAL_LUT_BITS];
     for (int k = 0; k < 32; ++k) {
         // int() truncates toward zero and 30 + 5 z > 0 here, so q <= 10 + k  <=>  30 + 5 z < 11 + k
         const double zc = ((double)(11 + k) - 30.0) / 5.0;
         const double cdf = 0.5 * erfc(-zc / sqrt(2.0));
         h[k] = k < 30 ? (uint32_t)llround(cdf * 16777216.0) : 0xffffffffu;
     }
-    for (uint32_t b = 0; b < 256; ++b) {
+    for (uint32_t b = 0; b < (1u << QUAL_LUT_BITS); ++b) {
         int cnt = 0;
-        for (int k = 0; k < 30; ++k) cnt += h[k] <= (b << 16);
+        for (int k = 0; k < 30; ++k) cnt += h[k] <= (b << (24 - QUAL_LUT_BITS));
         lut[b] = (uint8_t)cnt;
     }
     PMRD_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qual_thr, h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -191,9 +193,10 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
                  int64_t n_reads, int segmented, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
     __shared__ FamSlot s_slot[8][32];
     __shared__ uint32_t s_qthr[32];
-    __shared__ uint8_t s_qlut[256];
+    __shared__ __align__(16) uint8_t s_qlut[1 << QUAL_LUT_BITS];
     if (threadIdx.x < 32) s_qthr[threadIdx.x] = c_qual_thr[threadIdx.x];
-    s_qlut[threadIdx.x] = c_qual_lut[threadIdx.x];
+    static_assert((1 << QUAL_LUT_BITS) == 16 * READS_FAM_BLOCK, "one 16-byte LUT slice per thread");
+    reinterpret_cast<uint4*>(s_qlut)[threadIdx.x] = reinterpret_cast<const uint4*>(c_qual_lut)[threadIdx.x];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t f = (int64_t)blockIdx.x * READS_FAM_BLOCK + threadIdx.x;
     const Philox ph(seed);
@@ -235,14 +238,18 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
     __syncthreads();
-    for (uint32_t k = lane; k < total; k += 32) {
-        // owner = last lane whose first read is <= k (binary search over the lanes' offsets)
-        uint32_t lo = 0;
-#pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const uint32_t cand = lo + step;   // <= 31
-            lo = s_slot[warp][cand].local_off <= k ? cand : lo;
-        }
+    const uint32_t le = lanemask_lt() | (1u << lane);
+    for (uint32_t k0 = 0; k0 < total; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        // owner of read k = (number of families whose first read is <= k) - 1.  Lane s still holds
+        // family s's first read `loc` (ascending, distinct: every family has >= 1 read): the
+        // families that started before this step are counted by one ballot, those that start inside
+        // it are marked in a 32-bit mask by one warp OR-reduction, and a popcount finishes the job.
+        const uint32_t rel = loc - k0;
+        const uint32_t before = __popc(__ballot_sync(0xffffffffu, loc < k0));
+        const uint32_t heads = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+        if (k >= total) continue;
+        const uint32_t lo = before + __popc(heads & le) - 1u;
         const FamSlot S = s_slot[warp][lo];
         const uint32_t j = k - S.local_off;
         const uint32_t umi = S.word & 0xffffffu, ref = (S.word >> 26) & 3u, alt = (S.word >> 28) & 3u;
@@ -257,12 +264,9 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         else allele = ua < 62259u ? ref : alt;
         // io.py:65-69: max(10, min(40, int(normal(30, 5)))) by inversion of its exact 31-point cdf
         // (thresholds in units of 2^-24, built on the host from erfc): q = 10 + #{k : u >= T[k]}
-        // (coarse 256-bucket table, then a walk that almost never takes more than two steps;
-        // T[30] = T[31] = 2^32 - 1 stops it)
+        // (4096-bucket table, then a walk that almost never takes a step; T[30] = T[31] = 2^32 - 1 stops it)
         const uint32_t uq = ra >> 8;
-        uint32_t qi = s_qlut[uq >> 16];
-        qi += uq >= s_qthr[qi] ? 1u : 0u;
-        qi += uq >= s_qthr[qi] ? 1u : 0u;
+        uint32_t qi = s_qlut[uq >> (24 - QUAL_LUT_BITS)];
         while (uq >= s_qthr[qi]) ++qi;
         const int q = 10 + (int)qi;
         const uint32_t strand = ra & 1u;
