@@ -218,6 +218,13 @@ int32_t pmrd_simulate_cells_stratified(pmrd_ctx* ctx, const int64_t* h_cell_id, 
                                        const int64_t* h_depth, const double* h_bg_multiplier,
                                        int64_t n_cells, int32_t max_family_size, pmrd_cell_table* h_out);
 
+/* ---------------------------------------------------------------- K14: strand bias ---- */
+/* QualityFilter.test_strand_bias (src/precise_mrd/filters.py:50-100): scipy.stats.fisher_exact(
+ * [[c00, c01], [c10, c11]], 'two-sided') on m tables, h_table = [m][4] row-major.  Sample odds
+ * ratio c00 c11 / (c10 c01) (inf when c10 c01 == 0; NaN and p = 1 when a row or column is empty);
+ * p = sum of the hypergeometric point masses no larger than the observed one (relative slack 1e-14). */
+int32_t pmrd_fisher_exact(pmrd_ctx* ctx, const int64_t* h_table, int64_t m, double* h_odds_ratio, double* h_p);
+
 /* ---------------------------------------------------------------- K13: FASTQ ingest -- */
 /* FASTQReader.read_fastq + the per-UMI grouping of process_fastq_to_dataframe
  * (src/precise_mrd/fastq.py:66-110, :176-220).  pmrd_fastq_scan takes the file's bytes (already

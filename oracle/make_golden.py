@@ -17,6 +17,7 @@ parity tests can run where the reference cannot travel.
   gb_reads.npz                            G-B SyntheticReadGenerator reads -> UMIProcessor(max_edit_distance=0)
   gb_stats.json                           G-B StatisticalTester (one-sided tests, CIs, BH/Bonferroni/Holm),
                                           ContextAnalyzer and ErrorModel on seeded inputs
+  gb_filters.json                         G-B QualityFilter (Fisher strand bias, end-repair, depth, quality) on a seeded table
   fastq_mixed.fastq / fastq_mixed.json    a synthetic FASTQ with every header convention and parser edge
                                           case + the reference's read list / family table / validation for it
   lod_fit.npz                             LODAnalyzer._fit_detection_curve/_bootstrap_lod_ci on given vectors
@@ -348,6 +349,54 @@ def golden_gb_stats() -> None:
     print("  wrote gb_stats.json", len(rows), "scalar rows,", m, "loci")
 
 
+# ------------------------------------------------------------------------------- G-B quality filters
+def golden_filters() -> None:
+    """QualityFilter of the reference (Fisher strand bias, end-repair enrichment, depth, quality) on
+    a seeded variant table -> tests/golden/gb_filters.json."""
+    import json
+
+    sys.path.insert(0, str(HERE / "_ref" / "gb"))
+    from precise_mrd_gb.filters import QualityFilter
+
+    rng = np.random.default_rng(404)
+    m = 500
+    depth = rng.integers(4, 30000, m)
+    alt = np.minimum(rng.poisson(depth * rng.choice([1e-4, 1e-3, 1e-2, 0.2], m)), depth)
+    af = np.array([rng.binomial(a, rng.choice([0.5, 0.5, 0.5, 0.02, 0.97])) for a in alt])
+    rf = np.array([rng.binomial(d - a, 0.5) for d, a in zip(depth, alt)])
+    rows = []
+    for i in range(m):
+        n_pos = int(alt[i])
+        ends = rng.random() < 0.3
+        pos = np.where(rng.random(n_pos) < (0.7 if ends else 0.13), rng.choice(np.r_[np.arange(1, 11), np.arange(140, 151)], n_pos),
+                       rng.integers(11, 140, n_pos))
+        ref, al = rng.choice([("G", "T"), ("C", "A"), ("C", "T"), ("A", "G")])
+        q = rng.integers(8, 41, int(rng.integers(0, 12))).tolist()
+        rows.append({"alt_count": int(alt[i]), "total_depth": int(depth[i]), "alt_forward": int(af[i]), "alt_reverse": int(alt[i] - af[i]),
+                     "ref_forward": int(rf[i]), "ref_reverse": int(depth[i] - alt[i] - rf[i]), "ref": str(ref), "alt": str(al),
+                     "read_positions": [int(v) for v in pos], "quality_scores": q})
+    rows[0].update(alt_forward=1, alt_reverse=0, ref_forward=1, ref_reverse=1)          # < 4 reads: no strand test
+    rows[1].update(alt_forward=0, alt_reverse=0, alt_count=0)                            # empty alt row: odds nan, p 1
+    qf = QualityFilter()
+    df = pd.DataFrame(rows)
+    out_df = qf.filter_variant_dataframe(df)
+    scal = []
+    for r in rows[:120]:
+        sb = qf.test_strand_bias(r["alt_forward"], r["alt_reverse"], r["ref_forward"], r["ref_reverse"])
+        er = qf.test_end_repair_artifact(r["ref"], r["alt"], r["read_positions"])
+        scal.append({"sb": [bool(sb.passed), sb.reason, None if sb.statistic is None else float(sb.statistic), None if sb.pvalue is None else float(sb.pvalue)],
+                     "er": [bool(er.passed), er.reason, None if er.statistic is None else float(er.statistic), None if er.pvalue is None else float(er.pvalue)]})
+    rep = qf.generate_filter_report(out_df)
+    out = {"rows": rows, "scalar": scal,
+           "table": {c: [None if (v is None or (isinstance(v, float) and np.isnan(v))) else (bool(v) if isinstance(v, (bool, np.bool_)) else v)
+                         for v in out_df[c]] for c in out_df.columns if c.endswith("_filter") or c.endswith("_reason") or c == "all_filters_passed"},
+           "report": {k: (int(v) if isinstance(v, (np.integer, int)) and not isinstance(v, bool) else (float(v) if isinstance(v, (float, np.floating)) else v))
+                      for k, v in rep.items()}}
+    with open(OUT / "gb_filters.json", "w") as f:
+        json.dump(out, f)
+    print("  wrote gb_filters.json", m, "variants;", int(out_df.all_filters_passed.sum()), "pass;", rep["failure_reasons"])
+
+
 # ------------------------------------------------------------------------------- FASTQ ingest
 def golden_fastq() -> None:
     """A seeded synthetic FASTQ exercising every header convention and parser edge case
@@ -492,7 +541,7 @@ def main() -> int:
     only = set(sys.argv[1:])
     steps = {
         "call": lambda: (golden_call("gd_v1", "det_a", "call_smoke_v1.npz"), golden_call("gd_v2", "smoke", "call_smoke_v2.npz")),
-        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbstats": golden_gb_stats, "fastq": golden_fastq,
+        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbstats": golden_gb_stats, "filters": golden_filters, "fastq": golden_fastq,
         "lod": golden_lod_fit,
         "dist": golden_gd_dist,
     }

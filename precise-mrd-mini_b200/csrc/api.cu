@@ -456,6 +456,24 @@ int32_t pmrd_umi_hamming(pmrd_ctx* ctx, const uint32_t* h_a, const uint32_t* h_b
 }
 
 
+// ---------------------------------------------------------------- K14 -------------------
+int32_t pmrd_fisher_exact(pmrd_ctx* ctx, const int64_t* h_table, int64_t m, double* h_odds_ratio, double* h_p) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, m >= 0, "fisher: m");
+    if (m == 0) return PMRD_OK;
+    PMRD_ARG(ctx, h_table && h_odds_ratio && h_p, "fisher: null buffer");
+    for (int64_t i = 0; i < 4 * m; ++i) PMRD_ARG(ctx, h_table[i] >= 0, "All values in `table` must be nonnegative.");
+    DevBuf t, o, p;
+    PMRD_TRY(up(ctx, t, h_table, (size_t)m * 32));
+    PMRD_CUDA(ctx, o.alloc(ctx->stream, (size_t)m * 8));
+    PMRD_CUDA(ctx, p.alloc(ctx->stream, (size_t)m * 8));
+    PMRD_TRY(k14_fisher(ctx, t.as<int64_t>(), m, o.as<double>(), p.as<double>()));
+    PMRD_TRY(down(ctx, h_odds_ratio, o.p, (size_t)m * 8));
+    PMRD_TRY(down(ctx, h_p, p.p, (size_t)m * 8));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
 // ---------------------------------------------------------------- K13 -------------------
 int32_t pmrd_fastq_scan(pmrd_ctx* ctx, const uint8_t* h_bytes, int64_t n_bytes, int64_t capacity, pmrd_fastq_records* h_out,
                         int64_t* n_records) {

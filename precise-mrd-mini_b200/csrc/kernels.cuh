@@ -17,6 +17,8 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
                     int64_t n_reads, const pmrd_umi_params* params, const pmrd_family_table* d_fam, int64_t capacity_f,
                     int64_t* n_families, const pmrd_group_table* d_grp, int64_t capacity_g, int64_t* n_groups);
 
+int32_t k14_fisher(pmrd_ctx* ctx, const int64_t* d_table, int64_t m, double* d_odds, double* d_p);
+
 // fastq.cu
 int32_t k13_fastq_scan(pmrd_ctx* ctx, const uint8_t* d_buf, int64_t n_bytes, int64_t capacity, const pmrd_fastq_records* d_out,
                        int64_t* h_n_records);

@@ -39,6 +39,24 @@ int32_t k8_pvalues(pmrd_ctx* ctx, const int64_t* d_k, const int64_t* d_n, const 
     return PMRD_OK;
 }
 
+// ---------------------------------------------------------------- K14 -------------------
+// Fisher's exact test on m 2x2 tables (filters.py:50-100 strand bias): one thread per table
+__global__ void __launch_bounds__(128)
+fisher_kernel(const int64_t* __restrict__ table /* [m][4] = c00 c01 c10 c11 */, int64_t m, double* __restrict__ odds,
+              double* __restrict__ p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double o;
+    p[i] = pmrd_fisher_two_sided(table[4 * i], table[4 * i + 1], table[4 * i + 2], table[4 * i + 3], &o);
+    odds[i] = o;
+}
+
+int32_t k14_fisher(pmrd_ctx* ctx, const int64_t* d_table, int64_t m, double* d_odds, double* d_p) {
+    if (m <= 0) return PMRD_OK;
+    PMRD_LAUNCH(ctx, fisher_kernel, pmrd_blocks(m, 128), 128, 0, d_table, m, d_odds, d_p);
+    return PMRD_OK;
+}
+
 // ---------------------------------------------------------------- K9 --------------------
 #define BH_THREADS 256
 #define BH_ITEMS 8

@@ -261,3 +261,93 @@ __host__ __device__ static inline double pmrd_binomial_greater(int64_t k_, int64
     if (p >= 1.0) return 1.0;
     return pmrd_binom_sf((double)k_ - 1.0, (double)n_, p);
 }
+
+// ----------------------------------------------------------------------------------------
+// Hypergeometric point mass and tails; Fisher's exact test (filters.py:50-100 -> scipy fisher_exact)
+// ----------------------------------------------------------------------------------------
+// P(X = x) for x white balls in n draws from r white + b black (R's dhyper: three binomial
+// point masses at p = n / (r + b), each through the saddle-point pmrd_dbinom)
+__host__ __device__ static inline double pmrd_dhyper(double x, double r, double b, double n) {
+    if (x < 0.0 || x > r || n - x > b || x > n) return 0.0;
+    if (n == 0.0) return x == 0.0 ? 1.0 : 0.0;
+    if (n == r + b) return x == r ? 1.0 : 0.0;
+    const double p = n / (r + b);
+    return pmrd_dbinom(x, r, p) * pmrd_dbinom(n - x, b, p) / pmrd_dbinom(n, r + b, p);
+}
+// P(X <= x): point masses summed downward from x (ratio recurrence), or 1 - upward sum past the mode
+__host__ __device__ static inline double pmrd_hyper_lower(double x, double r, double b, double n) {
+    const double lo = fmax(0.0, n - b);
+    if (x < lo) return 0.0;
+    double term = pmrd_dhyper(x, r, b, n), sum = term;
+    for (double k = x; k > lo; k -= 1.0) {
+        term *= (k * (b - n + k)) / ((r - k + 1.0) * (n - k + 1.0));   // pmf(k-1) / pmf(k)
+        const double s1 = sum + term;
+        if (s1 == sum) break;
+        sum = s1;
+    }
+    return sum;
+}
+__host__ __device__ static inline double pmrd_hyper_upper(double x, double r, double b, double n) {   // P(X >= x)
+    const double hi = fmin(r, n);
+    if (x > hi) return 0.0;
+    double term = pmrd_dhyper(x, r, b, n), sum = term;
+    for (double k = x; k < hi; k += 1.0) {
+        term *= ((r - k) * (n - k)) / ((k + 1.0) * (b - n + k + 1.0));   // pmf(k+1) / pmf(k)
+        const double s1 = sum + term;
+        if (s1 == sum) break;
+        sum = s1;
+    }
+    return sum;
+}
+__host__ __device__ static inline double pmrd_hyper_cdf(double x, double r, double b, double n, double mode) {
+    if (x >= fmin(r, n)) return 1.0;
+    if (x < mode) return pmrd_hyper_lower(x, r, b, n);
+    const double v = 1.0 - pmrd_hyper_upper(x + 1.0, r, b, n);
+    return v < 0.0 ? 0.0 : v;
+}
+__host__ __device__ static inline double pmrd_hyper_sf(double x, double r, double b, double n, double mode) {   // P(X > x)
+    if (x < fmax(0.0, n - b)) return 1.0;
+    if (x + 1.0 > mode) return pmrd_hyper_upper(x + 1.0, r, b, n);
+    const double v = 1.0 - pmrd_hyper_lower(x, r, b, n);
+    return v < 0.0 ? 0.0 : v;
+}
+// scipy's _binary_search_for_binom_tst on sign * pmf: i in [lo, hi] with a(i) <= d < a(i+1)
+__host__ __device__ static inline double pmrd_hyper_search(double sign, double d, double lo, double hi, double r, double b, double n) {
+    while (lo < hi) {
+        const double mid = lo + floor((hi - lo) * 0.5);
+        const double v = sign * pmrd_dhyper(mid, r, b, n);
+        if (v < d) lo = mid + 1.0;
+        else if (v > d) hi = mid - 1.0;
+        else { lo = mid; hi = mid; }
+    }
+    return (sign * pmrd_dhyper(lo, r, b, n) <= d) ? lo : lo - 1.0;
+}
+// scipy.stats.fisher_exact(table, 'two-sided') on [[c00, c01], [c10, c11]]: sample odds ratio and
+// the sum of the tables no more likely than the observed one (relative slack 1e-14)
+__host__ __device__ static inline double pmrd_fisher_two_sided(int64_t c00_, int64_t c01_, int64_t c10_, int64_t c11_, double* odds) {
+    const double c00 = (double)c00_, c01 = (double)c01_, c10 = (double)c10_, c11 = (double)c11_;
+    if (c00 + c10 == 0.0 || c01 + c11 == 0.0 || c00 + c01 == 0.0 || c10 + c11 == 0.0) {
+        *odds = NAN;
+        return 1.0;
+    }
+    *odds = (c10 > 0.0 && c01 > 0.0) ? (c00 * c11) / (c10 * c01) : INFINITY;
+    const double n1 = c00 + c01, n2 = c10 + c11, n = c00 + c10;
+    const double mode = floor((n + 1.0) * (n1 + 1.0) / (n1 + n2 + 2.0));
+    const double pexact = pmrd_dhyper(c00, n1, n2, n), pmode = pmrd_dhyper(mode, n1, n2, n);
+    const double gamma = 1.0 + 1e-14;
+    if (fabs(pexact - pmode) / fmax(pexact, pmode) <= 1e-14) return 1.0;
+    double pv;
+    if (c00 < mode) {
+        const double plower = pmrd_hyper_cdf(c00, n1, n2, n, mode);
+        if (pmrd_dhyper(n, n1, n2, n) > pexact * gamma) return plower < 1.0 ? plower : 1.0;
+        const double g = pmrd_hyper_search(-1.0, -pexact * gamma, mode, n, n1, n2, n);
+        pv = plower + pmrd_hyper_sf(g, n1, n2, n, mode);
+    } else {
+        const double pupper = pmrd_hyper_sf(c00 - 1.0, n1, n2, n, mode);
+        if (pmrd_dhyper(0.0, n1, n2, n) > pexact * gamma) return pupper < 1.0 ? pupper : 1.0;
+        const double g = pmrd_hyper_search(1.0, pexact * gamma, 0.0, mode, n1, n2, n);
+        pv = pupper + pmrd_hyper_cdf(g, n1, n2, n, mode);
+    }
+    return pv < 1.0 ? pv : 1.0;
+}
+

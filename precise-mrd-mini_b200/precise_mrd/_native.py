@@ -355,6 +355,15 @@ class Context:
         finally:
             plan.close()
 
+    # -- K14 -----------------------------------------------------------------------------
+    def fisher_exact(self, tables) -> Tuple[np.ndarray, np.ndarray]:
+        """(odds_ratio[m], p[m]) of m 2x2 tables given as [m, 4] = c00 c01 c10 c11 (two-sided)."""
+        t = _arr(tables, np.int64).reshape(-1, 4)
+        m = t.shape[0]
+        odds, p = np.zeros(m), np.zeros(m)
+        self._check(self.lib.pmrd_fisher_exact(self.h, _ptr(t), C.c_int64(m), _ptr(odds), _ptr(p)))
+        return odds, p
+
     # -- K13 -----------------------------------------------------------------------------
     _FQ_REC = (("status", np.int32), ("umi_key", np.uint64), ("hdr_off", np.int64), ("hdr_len", np.int32), ("umi_off", np.int64),
                ("umi_len", np.int32), ("seq_off", np.int64), ("seq_len", np.int32), ("qual_off", np.int64), ("qual_len", np.int32),

@@ -333,3 +333,54 @@ def test_fastq_ingest_matches_reference(ctx, smoke_cfg, tmp_path):
     plain.write_text("@r1\nACGT\n+\nIIII\n@r2\nAC\n+\nII")                            # no UMIs, no trailing newline
     assert [r["read_id"] for r in FASTQReader(plain).read_fastq()] == ["r1", "r2"]
     assert process_fastq_to_dataframe(plain, smoke_cfg, np.random.default_rng(0)).empty
+
+
+def test_quality_filters_match_reference(ctx):
+    """K14 Fisher strand bias + K8 end-repair enrichment behind QualityFilter (filters.py), against
+    the reference's own outputs on a seeded 500-variant table (tests/golden/gb_filters.json)."""
+    from scipy.stats import fisher_exact
+
+    from precise_mrd.filters import FilterResult, QualityFilter
+
+    g = json.loads((ROOT / "tests" / "golden" / "gb_filters.json").read_text())
+    qf = QualityFilter()
+    df = pd.DataFrame(g["rows"])
+    out = qf.filter_variant_dataframe(df)
+    for col, want in g["table"].items():
+        got = [None if (v is None or (isinstance(v, float) and np.isnan(v))) else (bool(v) if isinstance(v, (bool, np.bool_)) else v)
+               for v in out[col]]
+        assert got == want, col
+    assert list(df.columns) == [c for c in out.columns if c in df.columns]          # the input frame is not mutated
+    rep = qf.generate_filter_report(out)
+    for k, w in g["report"].items():
+        assert (rep[k] == w) if not isinstance(w, float) else rep[k] == pytest.approx(w, rel=1e-15), k
+    for r, w in zip(g["rows"], g["scalar"]):
+        sb = qf.test_strand_bias(r["alt_forward"], r["alt_reverse"], r["ref_forward"], r["ref_reverse"])
+        assert isinstance(sb, FilterResult) and (bool(sb.passed), sb.reason) == (w["sb"][0], w["sb"][1])
+        if w["sb"][3] is not None:
+            # beyond ~2e4 reads SciPy's hypergeometric tails are good to ~3e-11 only (mpmath check in DESIGN.md)
+            assert sb.pvalue == pytest.approx(w["sb"][3], rel=1e-12 if r["total_depth"] <= 20000 else 5e-11, abs=1e-300)
+            assert (np.isnan(sb.statistic) and np.isnan(w["sb"][2])) or sb.statistic == pytest.approx(w["sb"][2], rel=1e-15)
+        er = qf.test_end_repair_artifact(r["ref"], r["alt"], r["read_positions"])
+        assert (bool(er.passed), er.reason) == (w["er"][0], w["er"][1])
+        if w["er"][3] is not None:
+            assert er.pvalue == pytest.approx(w["er"][3], rel=1e-12, abs=1e-300) and er.statistic == pytest.approx(w["er"][2], rel=1e-15)
+    # the raw kernel against scipy over a wide range of tables, incl. empty rows / columns
+    rng = np.random.default_rng(8)
+    tabs = np.array([rng.integers(0, s, 4) for s in rng.choice([3, 30, 300, 3000], 600)], dtype=np.int64)
+    tabs[::17, 2:] = 0
+    tabs[::19, 1] = 0
+    odds, p = ctx.fisher_exact(tabs)
+    for t, o, pv in zip(tabs, odds, p):
+        w = fisher_exact(t.reshape(2, 2))
+        assert pv == pytest.approx(w.pvalue, rel=1e-12, abs=1e-300), t
+        assert (np.isnan(o) and np.isnan(w.statistic)) or o == w.statistic, t
+    with pytest.raises(Exception, match="nonnegative"):
+        ctx.fisher_exact([[1, -1, 2, 3]])
+    # contract of the simple filters and the summary (filters.py:168-203, 245-260)
+    assert qf.filter_by_depth(1, 100).reason == "insufficient_alt_count" and qf.filter_by_depth(5, 3).reason == "insufficient_total_depth"
+    assert qf.filter_by_quality([]).reason == "no_quality_scores" and qf.filter_by_quality([10, 12]).reason == "low_quality"
+    res = qf.apply_all_filters({"alt_count": 5, "total_depth": 100, "quality_scores": [30, 35]})
+    assert set(res) == {"depth", "quality"} and qf.summarize_filters(res)["all_filters_passed"]
+    assert QualityFilter(end_repair_filter=False).test_end_repair_artifact("G", "T", [1, 2, 3]).passed
+    assert qf.filter_variant_dataframe(pd.DataFrame()).empty and qf.generate_filter_report(pd.DataFrame()) == {"total_variants": 0}

@@ -9,3 +9,6 @@ void dev_binom2(const int64_t* k, const int64_t* n, const double* pr, int64_t m,
 void dev_binom_gt(const int64_t* k, const int64_t* n, const double* pr, int64_t m, double* p) { for (int64_t i = 0; i < m; ++i) p[i] = pmrd_binomial_greater(k[i], n[i], pr[i]); }
 void dev_dbinom(const int64_t* k, const int64_t* n, const double* pr, int64_t m, double* p) { for (int64_t i = 0; i < m; ++i) p[i] = pmrd_dbinom((double)k[i], (double)n[i], pr[i]); }
 }
+extern "C" void dev_fisher(const int64_t* t, int64_t m, double* odds, double* p) {
+    for (int64_t i = 0; i < m; ++i) p[i] = pmrd_fisher_two_sided(t[4 * i], t[4 * i + 1], t[4 * i + 2], t[4 * i + 3], &odds[i]);
+}
