@@ -355,10 +355,12 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     __shared__ uint32_t sw[33];
     __shared__ unsigned long long s_acc[3];
     __shared__ double s_wt[64];
+    __shared__ uint32_t s_bkt[32];
     __shared__ int s_cell;
     const int64_t tile = blockIdx.x;
     const int64_t base = tile * CC_TILE;
     if (threadIdx.x < 3) s_acc[threadIdx.x] = 0ull;
+    if (threadIdx.x < 32) s_bkt[threadIdx.x] = 0u;
     if (threadIdx.x < 64) s_wt[threadIdx.x] = (int)threadIdx.x >= P.quality_threshold ? c_wtab[threadIdx.x] : 0.0;
     if (tile_cell) {
         if (threadIdx.x == 0) s_cell = tile_cell[tile];
@@ -402,10 +404,38 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         }
     __syncthreads();
     // FULL: the UMI halves are not needed past this point; their 16 KB now hold the votes' allele sums
-    double* const s_sum = reinterpret_cast<double*>(s_umi) + threadIdx.x;
+    double* const s_sum = reinterpret_cast<double*>(s_umi) + threadIdx.x;          // 8 KB: [4 alleles][CC_THREADS]
+    uint16_t* const s_order = reinterpret_cast<uint16_t*>(s_umi + 2 * CC_THREADS * 4);   // the other 8 KB: [CC_TILE]
+    if (FULL) {
+        // One thread votes one family, and a warp is as slow as its longest family (sizes are Poisson:
+        // a plain head-order assignment keeps 17 of 32 lanes busy).  Bucket the heads by family length,
+        // longest first, padding runs last, so that the lanes of a warp walk families of equal length.
+        auto bucket = [&](uint32_t h) -> uint32_t {
+            const uint32_t hv = s_head[h];
+            const uint32_t hi = (h + 1 < n_heads) ? (uint32_t)(s_head[h + 1] & 0xfffu) : (uint32_t)CC_TILE;
+            const uint32_t len = hi - (hv & 0xfffu);
+            return (hv & 0x8000u) ? 31u : 30u - (len < 30u ? len : 30u);
+        };
+        for (uint32_t h = threadIdx.x; h < n_heads; h += CC_THREADS) atomicAdd(&s_bkt[bucket(h)], 1u);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t c = s_bkt[threadIdx.x];
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (threadIdx.x >= (uint32_t)o) incl += t;
+            }
+            s_bkt[threadIdx.x] = incl - c;
+        }
+        __syncthreads();
+        for (uint32_t h = threadIdx.x; h < n_heads; h += CC_THREADS) s_order[atomicAdd(&s_bkt[bucket(h)], 1u)] = (uint16_t)h;
+        __syncthreads();
+    }
     const uint32_t alt = alt_allele[cell0 + cell];
     uint32_t n_fam = 0, n_tot = 0, n_var = 0;
-    for (uint32_t h = threadIdx.x; h < n_heads; h += CC_THREADS) {
+    for (uint32_t hh = threadIdx.x; hh < n_heads; hh += CC_THREADS) {
+        const uint32_t h = FULL ? (uint32_t)s_order[hh] : hh;
         const uint32_t hv = s_head[h];
         const int lo = (int)(hv & 0xfffu);
         const int hi = (h + 1 < n_heads) ? (int)(s_head[h + 1] & 0xfffu) : CC_TILE;
