@@ -246,8 +246,11 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
 
 // ---- stages of one chunk; each only enqueues kernels --------------------------------------
 static int32_t chunk_simulate(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
-    // family sizes -> read offsets -> reads (scrambled)
-    PMRD_TRY(reads_plan_sizes(ctx, &ch->reads));
+    // family sizes -> read offsets -> reads (scrambled).  The plan build has just run the first two for
+    // this seed (it needs the read counts to size the buffers): the first step after a build does not
+    // repeat them; every later step does the full work.
+    if (!(ch->reads.sizes_fresh && ch->reads.sizes_seed == ctx->seed)) PMRD_TRY(reads_plan_sizes(ctx, &ch->reads));
+    ch->reads.sizes_fresh = false;
     // cell-major chunks are generated as packed 8-byte records (payload:32 | umi:32)
     return reads_plan_generate(ctx, &ch->reads, P->keys.as<uint64_t>(), ch->reads.segmented ? nullptr : P->pl.as<uint32_t>());
 }

@@ -402,6 +402,8 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         return PMRD_ERR_CUDA;
     }
     int32_t st = reads_plan_sizes(ctx, plan);
+    plan->sizes_fresh = st == PMRD_OK;
+    plan->sizes_seed = ctx->seed;
     int64_t* h_cnt = (int64_t*)malloc(8 * (size_t)(n_cells + 1));
     int64_t* h_tile = (int64_t*)malloc(8 * (size_t)(n_cells + 1));
     if (!h_cnt || !h_tile) { free(hc); free(ho); free(h_cnt); free(h_tile); PMRD_ARG(ctx, false, "out of host memory"); }

@@ -29,6 +29,8 @@ struct ReadPlan {
     int64_t n_out = 0;        // slots in the output arrays (== n_reads unless segmented: + padding)
     int64_t n_groups_with_reads = 0;  // cells that own at least one read
     int segmented = 0;        // cell-major, tile-padded layout (enables the per-cell 3-pass sort)
+    bool sizes_fresh = false; // the build just computed sizes / offsets for `sizes_seed`: the first step reuses them
+    uint64_t sizes_seed = 0;
 };
 
 // allele convention of the generator: ref = cell_id & 3, alt = one of the other three
