@@ -324,7 +324,7 @@ typedef struct pmrd_read_sim_params {
     double hop_rate;            /* contamination.py:230-254 */
     double collision_rate;      /* contamination.py:256-278 */
     int32_t shuffle;            /* 0: family-major order; 1: tile-shuffled */
-    int32_t chunk_log2;         /* pipeline plans: cells are streamed in chunks of <= 2^chunk_log2 reads (0 = 28) */
+    int32_t chunk_log2;         /* pipeline plans: cells are streamed in chunks of <= 2^chunk_log2 reads (0 = 30) */
 } pmrd_read_sim_params;
 
 /* Counts reads: h_read_offsets[C+1] CSR of reads per cell (family-major layout). */

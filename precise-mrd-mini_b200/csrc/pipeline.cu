@@ -94,7 +94,7 @@ error_rate_kernel(uint64_t seed, uint64_t stream_id, const int64_t* __restrict__
 // ---------------------------------------------------------------- plan -------------------
 // A plan owns every buffer of one grid of cells, so that run() only enqueues kernels: no
 // allocation, no host sync, no host<->device copy inside the step.  The grid is cut into
-// CHUNKS of consecutive cells (<= 2^chunk_log2 reads each, default 2^28) that stream through
+// CHUNKS of consecutive cells (<= 2^chunk_log2 reads each, default 2^30: 17 GB of record buffers) that stream through
 // ONE set of read / family buffers sized for the largest chunk -- 180 GB of HBM is plenty, but
 // a chunk must stay below 2^31 reads (32-bit positions in the sort) and small chunks keep
 // the working set of a radix pass closer to L2.  Per-cell counts land in grid-wide arrays;
@@ -159,7 +159,7 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
         if (v == 8 || v == 16 || v == 24) P->sort_bits = v;
     }
     // cut into chunks by expected reads (mean size with 25% head room; exact counts follow)
-    const double budget = (double)(1ll << (sp->chunk_log2 ? sp->chunk_log2 : 28));
+    const double budget = (double)(1ll << (sp->chunk_log2 ? sp->chunk_log2 : 30));
     const double per_family = (sp->mean_family_size + 1.0) * 1.25;
     int64_t c0 = 0;
     int32_t st = PMRD_OK;
