@@ -336,6 +336,7 @@ struct VoteS {
     }
 };
 #define CC_ITEMS (CC_TILE / CC_THREADS)
+#define CC_SKEW(i) ((i) + ((i) >> 5))
 
 // Input: packed 8-byte records  rec = payload:32 | umi:32  in cell-major, tile-padded order,
 // each cell sorted on the low `run_mask` bits of the UMI.  `run_mask` selects the UMI bits the
@@ -349,7 +350,9 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
                       pmrd_umi_params P, uint32_t run_mask, int64_t cell0, const uint8_t* __restrict__ alt_allele,
                       unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot,
                       unsigned long long* __restrict__ o_var) {
-    __shared__ __align__(16) uint32_t s_umi[CC_TILE];   // split halves: the vote walks only the payloads (32-bit, half the
+    // (s_umi is skewed by one word per 32: the head pass reads 16 CONSECUTIVE words per thread, which
+    // unskewed is a 16-way bank conflict on every load -- it was 60 % of the kernel's shared-memory wavefronts)
+    __shared__ __align__(16) uint32_t s_umi[CC_TILE + CC_TILE / 32];   // split halves: the vote walks only the payloads (32-bit, half the
     __shared__ uint32_t s_pl[CC_TILE];    // shared-memory traffic and bank conflicts of walking 64-bit records)
     __shared__ uint16_t s_head[CC_TILE];
     __shared__ uint32_t sw[33];
@@ -376,7 +379,7 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     for (int j = 0; j < CC_ITEMS; ++j) {
         const int i = j * CC_THREADS + threadIdx.x;
         const uint64_t v = rec[base + i];
-        s_umi[i] = (uint32_t)v;
+        s_umi[CC_SKEW(i)] = (uint32_t)v;
         s_pl[i] = (uint32_t)(v >> 32);
     }
     __syncthreads();
@@ -389,7 +392,7 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     for (int j = 0; j < CC_ITEMS; ++j) {
         const int i = i0 + j;
         bool head;
-        if (i > 0) head = ((s_umi[i] ^ s_umi[i - 1]) & run_mask) != 0u;
+        if (i > 0) head = ((s_umi[CC_SKEW(i)] ^ s_umi[CC_SKEW(i - 1)]) & run_mask) != 0u;
         else head = base == cell_lo || ((((uint32_t)rec[base - 1]) ^ s_umi[0]) & run_mask) != 0u;
         if (head) { flags |= 1u << j; ++cnt; }
     }
@@ -399,7 +402,7 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     for (int j = 0; j < CC_ITEMS; ++j)
         if (flags & (1u << j)) {
             // FULL: bit 15 marks a run of padding reads (s_umi is recycled below)
-            const uint32_t pad = (FULL && (s_umi[i0 + j] >> 24) == 0xffu) ? 0x8000u : 0u;
+            const uint32_t pad = (FULL && (s_umi[CC_SKEW(i0 + j)] >> 24) == 0xffu) ? 0x8000u : 0u;
             s_head[r++] = (uint16_t)((uint32_t)(i0 + j) | pad);
         }
     __syncthreads();
@@ -443,11 +446,11 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         // the tile's last run may continue into the next tile(s) of the same cell
         int64_t g_hi = base + CC_TILE;
         if (h + 1 == n_heads) {
-            const uint32_t rk = (FULL ? (uint32_t)rec[base + lo] : s_umi[lo]) & run_mask;
+            const uint32_t rk = (FULL ? (uint32_t)rec[base + lo] : s_umi[CC_SKEW(lo)]) & run_mask;
             while (g_hi < cell_hi && ((((uint32_t)rec[g_hi]) & run_mask) == rk)) ++g_hi;
         }
         const int len = n_in + (int)(g_hi - (base + CC_TILE));
-        auto umi_at = [&](int i) -> uint32_t { return i < n_in ? s_umi[lo + i] : (uint32_t)rec[base + CC_TILE + (i - n_in)]; };
+        auto umi_at = [&](int i) -> uint32_t { return i < n_in ? s_umi[CC_SKEW(lo + i)] : (uint32_t)rec[base + CC_TILE + (i - n_in)]; };
         auto pl_at = [&](int i) -> uint32_t { return i < n_in ? s_pl[lo + i] : (uint32_t)(rec[base + CC_TILE + (i - n_in)] >> 32); };
         if (FULL) {
             // the sort ordered every UMI bit: a run IS a family
