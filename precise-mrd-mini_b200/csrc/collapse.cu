@@ -516,11 +516,11 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
 int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d_rec_tmp, int64_t n_out,
                                      const pmrd_umi_params* params, const int64_t* d_cell_tile_start, const int32_t* d_tile_cell,
                                      int64_t n_cells, int sort_bits, int umi_bits, int64_t cell0, const uint8_t* d_alt_allele,
-                                     int64_t* d_o_fam, int64_t* d_o_tot, int64_t* d_o_var) {
+                                     int64_t* d_o_fam, int64_t* d_o_tot, int64_t* d_o_var, uint32_t* d_hist0) {
     if (n_out <= 0) return PMRD_OK;
     PMRD_ARG(ctx, n_out % CC_TILE == 0, "segmented collapse: input must be whole tiles");
     int in_b = 0;
-    PMRD_TRY(radix_sort_pairs_segmented(ctx, d_rec, nullptr, d_rec_tmp, nullptr, n_out, d_cell_tile_start, n_cells, sort_bits, &in_b));
+    PMRD_TRY(radix_sort_pairs_segmented(ctx, d_rec, nullptr, d_rec_tmp, nullptr, n_out, d_cell_tile_start, n_cells, sort_bits, &in_b, d_hist0));
     const uint64_t* sr = in_b ? d_rec_tmp : d_rec;
     const uint32_t run_mask = sort_bits >= 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
     const int grid = (int)(n_out / CC_TILE);

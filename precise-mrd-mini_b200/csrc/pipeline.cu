@@ -23,7 +23,7 @@ int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d
                                      const pmrd_umi_params* params, const int64_t* d_cell_tile_start, const int32_t* d_tile_cell,
                                      int64_t n_cells,
                                      int sort_bits, int umi_bits, int64_t cell0, const uint8_t* d_alt_allele, int64_t* d_o_fam,
-                                     int64_t* d_o_tot, int64_t* d_o_var);
+                                     int64_t* d_o_tot, int64_t* d_o_var, uint32_t* d_hist0);
 
 // scatter the group table into per-cell arrays (cells without reads keep zeros)
 __global__ void __launch_bounds__(256)
@@ -117,6 +117,8 @@ struct pmrd_plan {
     int sort_bits = 24;   // UMI bits ordered by the radix sort; the consensus kernel resolves the rest (16: 2 passes, 24: 3)
     uint64_t stream_id = 0;
     DevBuf keys, keys_tmp, pl, pl_tmp;
+    DevBuf tile_hist;     // [max tiles][256]: first-pass digit histogram the generator counts as a by-product (cell-major path)
+    bool gen_hist = true;
     DevBuf fk, fs, fa, fc, fq, fn, ff, fam_start;
     DevBuf gg, gf, gc, ga, gt, grp_start, counts, totals;
     DevBuf alt, neg, negc, mean_rate;
@@ -203,6 +205,9 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.alloc(ctx->stream, bytes); };
     A(P->keys, n * 8); A(P->keys_tmp, n * 8);
+    if (const char* gh = getenv("PMRD_GEN_HIST")) P->gen_hist = atoi(gh) != 0;   // 0: the sort counts its first digit itself
+    if (sp->hop_rate > 0.0) P->gen_hist = false;
+    if (P->gen_hist) A(P->tile_hist, (n / READS_SEG_TILE + 1) * 256 * sizeof(uint32_t));
     if (sp->hop_rate > 0.0) { A(P->pl, n * 4); A(P->pl_tmp, n * 4); }
     if (sp->hop_rate > 0.0) {   // only the general (non cell-major) path materialises the family / group tables
         A(P->fk, f * 8); A(P->fs, f * 4); A(P->fa, f * 4); A(P->fc, f * 4); A(P->fq, f * 4); A(P->fn, f * 4); A(P->ff, f * 4);
@@ -252,7 +257,8 @@ static int32_t chunk_simulate(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
     if (!(ch->reads.sizes_fresh && ch->reads.sizes_seed == ctx->seed)) PMRD_TRY(reads_plan_sizes(ctx, &ch->reads));
     ch->reads.sizes_fresh = false;
     // cell-major chunks are generated as packed 8-byte records (payload:32 | umi:32)
-    return reads_plan_generate(ctx, &ch->reads, P->keys.as<uint64_t>(), ch->reads.segmented ? nullptr : P->pl.as<uint32_t>());
+    return reads_plan_generate(ctx, &ch->reads, P->keys.as<uint64_t>(), ch->reads.segmented ? nullptr : P->pl.as<uint32_t>(),
+                               P->gen_hist ? P->tile_hist.as<uint32_t>() : nullptr);
 }
 
 static int32_t chunk_collapse(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
@@ -263,7 +269,8 @@ static int32_t chunk_collapse(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
                                             (const int64_t*)ch->reads.cell_tile_start.as<int64_t>(),
                                             (const int32_t*)ch->reads.tile_cell.as<int32_t>(), ch->n_cells, P->sort_bits, 24,
                                             ch->cell0, (const uint8_t*)P->alt.as<uint8_t>(), P->o_fam.as<int64_t>(),
-                                            P->o_tot.as<int64_t>(), P->o_var.as<int64_t>());
+                                            P->o_tot.as<int64_t>(), P->o_var.as<int64_t>(),
+                                            P->gen_hist ? P->tile_hist.as<uint32_t>() : nullptr);
     }
     pmrd_family_table fam{P->fk.as<uint64_t>(), P->fs.as<uint32_t>(), P->fa.as<uint32_t>(), P->fc.as<uint32_t>(),
                           P->fq.as<uint32_t>(), P->fn.as<uint32_t>(), P->ff.as<uint32_t>()};

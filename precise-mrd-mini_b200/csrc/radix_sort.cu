@@ -92,10 +92,8 @@ RadixPlan radix_make_plan(uint64_t varying) {
 // ---------------------------------------------------------------- upsweep ---------------
 // hist[tile][256] (tile-major: one coalesced 1 KB row per tile)
 __global__ void __launch_bounds__(RS_THREADS)
-rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ hist, int shift, uint32_t mask,
-                  uint16_t* __restrict__ tile_excl /* optional: exclusive scan of the tile's own histogram */) {
+rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ hist, int shift, uint32_t mask) {
     __shared__ uint32_t s_hist[RS_WARPS][RS_MAX_BINS];
-    __shared__ uint32_t sw[33];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -127,11 +125,6 @@ rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __rest
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) c += s_hist[w][threadIdx.x];
         hist[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] = c;
-    }
-    if (tile_excl) {   // (uniform) where each digit's run starts inside the tile: the staged downsweep needs it
-        uint32_t tot;
-        const uint32_t e = block_exclusive_scan<uint32_t>(c, sw, tot);
-        if (threadIdx.x < RS_MAX_BINS) tile_excl[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] = (uint16_t)e;
     }
 }
 
@@ -352,11 +345,11 @@ struct RsStage {
     uint32_t cnt[RS_WARPS][RS_MAX_BINS];
     uint64_t rec[RS_TILE];
     uint32_t delta[RS_MAX_BINS];
+    uint32_t sw[33];
 };
 __global__ void __launch_bounds__(RS_THREADS, RS_DIRECT_MIN_BLOCKS)
 rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
-                           const uint32_t* __restrict__ hist_scanned, const uint16_t* __restrict__ tile_excl, int shift,
-                           uint32_t mask) {
+                           const uint32_t* __restrict__ hist_scanned, int shift, uint32_t mask) {
     extern __shared__ __align__(16) unsigned char rs_stage_raw[];
     RsStage& S = *reinterpret_cast<RsStage*>(rs_stage_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -382,15 +375,24 @@ rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
         else rank2[i >> 1] = r;
     }
     __syncthreads();
-    if (threadIdx.x < RS_MAX_BINS) {
-        const int64_t row = (int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x;
-        uint32_t run = tile_excl[row];                           // start of the digit's run inside the tile
-        S.delta[threadIdx.x] = hist_scanned[row] - run;          // tile position -> global position
+    {
+        // where each digit's run starts inside the tile: exclusive scan of the tile's own digit counts
+        // (the sum of the warp counters -- no histogram of the tile has to be read for it)
+        uint32_t tot = 0;
+        if (threadIdx.x < RS_MAX_BINS) {
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
-            const uint32_t c = S.cnt[w][threadIdx.x];
-            S.cnt[w][threadIdx.x] = run;
-            run += c;
+            for (int w = 0; w < RS_WARPS; ++w) tot += S.cnt[w][threadIdx.x];
+        }
+        uint32_t all;
+        uint32_t run = block_exclusive_scan<uint32_t>(tot, S.sw, all);
+        if (threadIdx.x < RS_MAX_BINS) {
+            S.delta[threadIdx.x] = hist_scanned[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] - run;   // tile position -> global position
+#pragma unroll
+            for (int w = 0; w < RS_WARPS; ++w) {
+                const uint32_t c = S.cnt[w][threadIdx.x];
+                S.cnt[w][threadIdx.x] = run;
+                run += c;
+            }
         }
     }
     __syncthreads();
@@ -457,16 +459,21 @@ static int32_t rs_set_attrs(pmrd_ctx* ctx) {
 // Per-cell sort of the low `key_bits` key bits; n must be a whole number of tiles and
 // d_cell_tile_start[n_cells] == n / RS_TILE.  The bits above key_bits must be constant
 // inside a cell (they are: the cell index).
+// d_hist0 (optional): a [n / RS_TILE][256] buffer that already holds the per-tile histogram of the FIRST
+// digit (the producer of the records counted it as a by-product): the first counting pass is skipped and
+// the buffer serves as the histogram scratch of the later passes.
 int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
-                                   int64_t n, const int64_t* d_cell_tile_start, int64_t n_cells, int key_bits, int* in_b) {
+                                   int64_t n, const int64_t* d_cell_tile_start, int64_t n_cells, int key_bits, int* in_b,
+                                   uint32_t* d_hist0) {
     *in_b = 0;
     if (n <= 0 || n_cells <= 0) return PMRD_OK;
     PMRD_ARG(ctx, n % RS_TILE == 0 && n < (1ll << 32) - RS_TILE, "segmented sort: n must be a multiple of the tile size and < 2^32");
     PMRD_ARG(ctx, key_bits >= 1 && key_bits <= 32, "segmented sort: key_bits");
     PMRD_TRY(rs_set_attrs(ctx));
     const int n_tiles = (int)(n / RS_TILE);
-    DevBuf hist;
-    PMRD_CUDA(ctx, hist.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
+    DevBuf hist_own;
+    if (!d_hist0) PMRD_CUDA(ctx, hist_own.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
+    uint32_t* const hist = d_hist0 ? d_hist0 : hist_own.as<uint32_t>();
     uint64_t* kin = keys_a; uint32_t* vin = vals_a; uint64_t* kout = keys_b; uint32_t* vout = vals_b;
     const int n_passes = (key_bits + 7) / 8;
     static int direct = -1, staged = 1;
@@ -476,26 +483,22 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         e = getenv("PMRD_RS_STAGED");
         if (e) staged = atoi(e);
     }
-    DevBuf texcl;
-    if (!vals_a && direct && staged) PMRD_CUDA(ctx, texcl.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint16_t)));
     for (int p = 0; p < n_passes; ++p) {
         const int shift = p * 8;
         const int w = key_bits - shift < 8 ? key_bits - shift : 8;
         const uint32_t mask = (1u << w) - 1u;
         // bit p of `staged`: pass p goes through the shared-memory staged scatter (default: the first pass only)
         const bool stage = !vals_a && direct && ((staged >> p) & 1);
-        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask,
-                    stage ? texcl.as<uint16_t>() : (uint16_t*)nullptr);
-        PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256, 0, hist.as<uint32_t>(), d_cell_tile_start, (int)n_cells);
+        if (!(p == 0 && d_hist0)) PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist, shift, mask);
+        PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256, 0, hist, d_cell_tile_start, (int)n_cells);
         if (vals_a) {
-            PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
+            PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);
         } else if (stage) {
-            PMRD_LAUNCH(ctx, rs_downsweep_staged_kernel, n_tiles, RS_THREADS, sizeof(RsStage), kin, kout, hist.as<uint32_t>(),
-                        (const uint16_t*)texcl.as<uint16_t>(), shift, mask);
+            PMRD_LAUNCH(ctx, rs_downsweep_staged_kernel, n_tiles, RS_THREADS, sizeof(RsStage), kin, kout, hist, shift, mask);
         } else if (direct) {   // packed 8-byte records, stored straight to their final place (L2 merges the sectors)
-            PMRD_LAUNCH(ctx, rs_downsweep_direct_kernel, n_tiles, RS_THREADS, 0, kin, kout, hist.as<uint32_t>(), shift, mask);
+            PMRD_LAUNCH(ctx, rs_downsweep_direct_kernel, n_tiles, RS_THREADS, 0, kin, kout, hist, shift, mask);
         } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits
-            PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist.as<uint32_t>(), n, shift, mask);
+            PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);
         }
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;
@@ -531,7 +534,7 @@ int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint
     for (int p = 0; p < plan.n_passes; ++p) {
         const int shift = plan.shift[p];
         const uint32_t mask = (1u << plan.bits[p]) - 1u;
-        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask, (uint16_t*)nullptr);
+        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask);
         PMRD_LAUNCH(ctx, rs_colsum_kernel, n_chunks, 256, 0, hist.as<uint32_t>(), n_tiles, chunk, colsum.as<uint32_t>());
         PMRD_LAUNCH(ctx, rs_colbase_kernel, 1, 256, 0, colsum.as<uint32_t>(), n_chunks);
         PMRD_LAUNCH(ctx, rs_colapply_kernel, n_chunks, 256, 0, hist.as<uint32_t>(), n_tiles, chunk, colsum.as<uint32_t>());

@@ -31,4 +31,5 @@ RadixPlan radix_make_plan(uint64_t varying);
 int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                          int64_t n, uint64_t varying, int* in_b);
 int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
-                                   int64_t n, const int64_t* d_cell_tile_start, int64_t n_cells, int key_bits, int* in_b);
+                                   int64_t n, const int64_t* d_cell_tile_start, int64_t n_cells, int key_bits, int* in_b,
+                                   uint32_t* d_hist0 = nullptr);

@@ -141,19 +141,22 @@ __device__ __forceinline__ float shuffle_inv(uint32_t n) {
     const uint32_t n_full = n / SHUF_WINDOW;
     return (n_full > 1u && n_full <= 65536u && n_full % SHUF_MUL != 0u) ? 1.0f / (float)n_full : 0.0f;
 }
+// destination of complete window w (< n_full) under the window permutation
+__device__ __forceinline__ uint32_t shuffle_window(uint32_t w, uint32_t n_full, float inv_full) {
+    if (inv_full == 0.0f) return w;
+    const uint32_t y = w * SHUF_MUL + 13u;
+    int32_t r = (int32_t)(y - (uint32_t)((float)y * inv_full) * n_full);
+    r += r < 0 ? (int32_t)n_full : 0;
+    r -= r >= (int32_t)n_full ? (int32_t)n_full : 0;
+    return (uint32_t)r;
+}
 __device__ __forceinline__ uint32_t shuffle_slot(uint32_t x, uint32_t n, float inv_full, int shuffle) {
     if (!shuffle) return x;
     const uint32_t n_full = n / SHUF_WINDOW;
     uint32_t w = x / SHUF_WINDOW, l = x % SHUF_WINDOW;
     if (w >= n_full) return x;
     l = (l * 2654435761u + 0x9e37u * w) & (SHUF_WINDOW - 1);  // odd multiplier: bijection mod 4096
-    if (inv_full != 0.0f) {
-        const uint32_t y = w * SHUF_MUL + 13u;
-        int32_t r = (int32_t)(y - (uint32_t)((float)y * inv_full) * n_full);
-        r += r < 0 ? (int32_t)n_full : 0;
-        r -= r >= (int32_t)n_full ? (int32_t)n_full : 0;
-        w = (uint32_t)r;
-    }
+    w = shuffle_window(w, n_full, inv_full);
     return w * SHUF_WINDOW + l;
 }
 
@@ -190,7 +193,8 @@ __global__ void __launch_bounds__(256)
 reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                  int64_t n_fam, pmrd_read_sim_params sp, const uint64_t* __restrict__ read_offset /*[n_fam]*/,
                  const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_word, const int32_t* __restrict__ blk_cell,
-                 int64_t n_reads, int segmented, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+                 int64_t n_reads, int segmented, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload,
+                 uint32_t* __restrict__ tile_hist /* [n_tiles][256], zeroed, or NULL */) {
     __shared__ FamSlot s_slot[8][32];
     __shared__ uint32_t s_qthr[32];
     __shared__ __align__(16) uint8_t s_qlut[1 << QUAL_LUT_BITS];
@@ -227,6 +231,24 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
             S.out_start = 0;
         }
         S.inv_full = shuffle_inv(S.cell_n);
+        if (tile_hist) {
+            // By-product for the collapse stage: the first radix pass needs, per 4096-slot tile of the
+            // output, the histogram of the low UMI byte.  A window of the family-major read order lands
+            // in ONE tile and a family's reads share their UMI, so the whole histogram costs one
+            // reduction per (family, window) -- 0.2 per read -- instead of a pass over the 8 B/read.
+            const uint32_t n_full = S.cell_n / SHUF_WINDOW;
+            uint32_t x = S.cell_off, rem = size;
+            uint32_t* const row0 = tile_hist + (S.out_start / SHUF_WINDOW) * 256 + (fw & 0xffu);
+            while (rem) {
+                const uint32_t w = x / SHUF_WINDOW;
+                const uint32_t room = SHUF_WINDOW - x % SHUF_WINDOW;
+                const uint32_t take = rem < room ? rem : room;
+                const uint32_t dw = (sp.shuffle && w < n_full) ? shuffle_window(w, n_full, S.inv_full) : w;
+                atomicAdd(row0 + (size_t)dw * 256, take);
+                x += take;
+                rem -= take;
+            }
+        }
     }
     const int64_t r0 = __shfl_sync(0xffffffffu, off, 0);
     // sorted ascending over the lanes; lanes past the last family never own a read
@@ -298,11 +320,15 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
 // reads that sort to the end of the cell and are ignored downstream
 __global__ void __launch_bounds__(256)
 reads_pad_kernel(const ReadCell* __restrict__ cells, int n_cells, const int64_t* __restrict__ cell_tile_start,
-                 uint64_t* __restrict__ keys, uint32_t* __restrict__ payload) {
+                 uint64_t* __restrict__ keys, uint32_t* __restrict__ payload, uint32_t* __restrict__ tile_hist) {
+    __shared__ uint32_t s_h[256];
     const int ci = blockIdx.x;
     if (ci >= n_cells) return;
     const ReadCell c = cells[ci];
     const int64_t lo = c.out_start + c.n_reads, hi = cell_tile_start[ci + 1] * READS_SEG_TILE;
+    if (lo >= hi) return;
+    s_h[threadIdx.x] = 0u;
+    __syncthreads();
     for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const uint32_t pad_umi = 0xff000000u | (((uint32_t)i * 40503u) & 0xffffffu);
         if (payload) {
@@ -311,7 +337,12 @@ reads_pad_kernel(const ReadCell* __restrict__ cells, int n_cells, const int64_t*
         } else {
             keys[i] = pad_umi;
         }
+        if (tile_hist) atomicAdd(&s_h[pad_umi & 0xffu], 1u);
     }
+    if (!tile_hist) return;
+    __syncthreads();
+    // the padding lies in the cell's last tile (hi - lo < READS_SEG_TILE)
+    if (s_h[threadIdx.x]) atomicAdd(&tile_hist[(cell_tile_start[ci + 1] - 1) * 256 + threadIdx.x], s_h[threadIdx.x]);
 }
 
 // ---------------------------------------------------------------- host side --------------
@@ -471,16 +502,20 @@ int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
 }
 
 // generate the reads (device only, no sync); capacity must be >= plan->n_out
-int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload) {
+// d_tile_hist (optional, segmented packed layout only): [n_out / 4096][256] histogram of the low UMI byte per
+// output tile, produced as a by-product -- the collapse stage then skips its first counting pass
+int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload, uint32_t* d_tile_hist) {
     if (plan->n_fam <= 0) return PMRD_OK;
+    if (!plan->segmented) d_tile_hist = nullptr;
+    if (d_tile_hist) PMRD_CUDA(ctx, cudaMemsetAsync(d_tile_hist, 0, (size_t)(plan->n_out / READS_SEG_TILE) * 256 * sizeof(uint32_t), ctx->stream));
     PMRD_LAUNCH(ctx, reads_gen_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
                 (const uint64_t*)plan->read_offset.as<uint64_t>(), (const uint32_t*)plan->fam_size.as<uint32_t>(),
                 (const uint32_t*)plan->fam_word.as<uint32_t>(), (const int32_t*)plan->blk_cell.as<int32_t>(), plan->n_reads,
-                plan->segmented, d_keys, d_payload);
+                plan->segmented, d_keys, d_payload, d_tile_hist);
     if (plan->segmented && plan->n_out > plan->n_reads)
         PMRD_LAUNCH(ctx, reads_pad_kernel, (int)plan->n_cells, 256, 0, plan->cells.as<ReadCell>(), (int)plan->n_cells,
-                    (const int64_t*)plan->cell_tile_start.as<int64_t>(), d_keys, d_payload);
+                    (const int64_t*)plan->cell_tile_start.as<int64_t>(), d_keys, d_payload, d_tile_hist);
     return PMRD_OK;
 }
 

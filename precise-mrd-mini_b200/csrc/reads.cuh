@@ -43,6 +43,6 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
                          int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, int segmented, ReadPlan* plan,
                          int64_t* h_read_offsets);
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan);
-int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload);
+int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload, uint32_t* d_tile_hist = nullptr);
 int32_t reads_plan_cell_counts(pmrd_ctx* ctx, ReadPlan* plan, int64_t* d_out);
 int32_t reads_upload_tables(pmrd_ctx* ctx);

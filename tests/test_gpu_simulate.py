@@ -320,6 +320,32 @@ def test_chunked_plan_equals_single_chunk(ctx, native):
     assert prof["rs_downsweep_kernel<true>"][0] >= plan.n_chunks and prof["reads_gen_kernel"][1] > 0
 
 
+def test_generator_histogram_replaces_the_first_counting_pass(ctx, native, monkeypatch):
+    """The generator counts the first radix digit per output tile as a by-product (one reduction per
+    family and window); the sort must then give the very same tables with one upsweep fewer per chunk."""
+    rng = np.random.default_rng(21)
+    c = 120
+    cid = np.arange(c) * 3 + 1
+    af = np.tile([0.0, 1e-4, 0.01, 0.05], c // 4)
+    nf = rng.integers(1, 12000, c)           # 1 .. 15 tiles per cell: tail-only cells, permuted windows, padding
+    nf[7] = 0
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PMRD_GEN_HIST", flag)
+        plan = native.Plan(ctx, cid, af, nf, _sp(native, family_model=1, collision_rate=1e-3), _umi(native))
+        plan.run()
+        ctx.profile_enable(True)
+        plan.run()
+        prof = ctx.profile_report()
+        ctx.profile_enable(False)
+        out[flag] = (plan.results(), prof["rs_upsweep_kernel"][0], plan.n_chunks)
+        plan.close()
+    a, b = out["0"][0], out["1"][0]
+    for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+        assert (a[k_] == b[k_]).all(), k_
+    assert out["0"][1] - out["1"][1] == out["1"][2] >= 1      # one counting pass per chunk gone (BH sorts too)
+
+
 # ------------------------------------------------------------------------------ K11 LoD fit
 def test_fit_lod_matches_reference_golden(ctx, golden):
     g = golden("lod_fit.npz")
