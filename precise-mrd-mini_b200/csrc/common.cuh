@@ -121,6 +121,21 @@ struct Philox {
     }
 };
 
+// Philox2x32-10 (same paper): 64-bit counter, 32-bit key, one multiply per round.  Used for the
+// per-read draws, whose key is a per-family word drawn from the Philox4x32 family block -- half the
+// multiplies of a 4x32 block for the 64 random bits a read needs.
+__host__ __device__ static inline uint2 philox2x32(uint32_t key, uint32_t c0, uint32_t c1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi, lo;
+        Philox::mulhilo(0xD256D193u, c0, hi, lo);
+        c0 = hi ^ key ^ c1;
+        c1 = lo;
+        key += 0x9E3779B9u;
+    }
+    return make_uint2(c0, c1);
+}
+
 // stream ids: the 4th counter word's top byte names the stage so that streams never overlap
 #define PMRD_STREAM_CELLS 1u     /* simulate_reads per-cell draws            */
 #define PMRD_STREAM_GD_FAMILY 2u /* G-D collapse_umis per-family draws       */

@@ -37,6 +37,7 @@ __device__ __forceinline__ int find_cell(const int64_t* __restrict__ fam_offsets
 struct FamDraw {
     int size;
     uint32_t umi;
+    uint32_t key;      // key of the family's per-read Philox2x32 stream
     bool has_variant;
 };
 
@@ -66,6 +67,7 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
     }
     if (d.size > sp.max_family_size) d.size = sp.max_family_size;
     d.umi = b.z & 0xffffffu;
+    d.key = b.y ^ (b.z >> 24);
     // io.py:97: has_variant = u53(b.w, b2.x) < af.  The top 32 bits settle it unless b.w sits on the
     // cell's threshold word (probability 2^-32), so the second Philox block is drawn only then, or
     // when a contamination knob needs its other words (io.py:100-101).
@@ -89,7 +91,8 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
 __global__ void __launch_bounds__(256)
 reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                   int64_t n_fam, pmrd_read_sim_params sp, const float* __restrict__ size_cdf /* [128] or NULL */,
-                  const int32_t* __restrict__ blk_cell, uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word) {
+                  const int32_t* __restrict__ blk_cell, uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word,
+                  uint32_t* __restrict__ fam_key) {
     __shared__ float s_cdf[128];
     const int64_t f = (int64_t)blockIdx.x * READS_FAM_BLOCK + threadIdx.x;
     if (size_cdf && threadIdx.x < 128) s_cdf[threadIdx.x] = size_cdf[threadIdx.x];
@@ -101,6 +104,7 @@ reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64
     const FamDraw d = draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp, size_cdf ? s_cdf : nullptr);
     fam_size[f] = (uint32_t)d.size;
     fam_word[f] = d.umi | ((d.has_variant ? 1u : 0u) << 24);   // the generator re-reads this instead of re-drawing
+    fam_key[f] = d.key;
 }
 
 #define SHUF_WINDOW 4096u
@@ -150,16 +154,6 @@ __device__ __forceinline__ uint32_t shuffle_window(uint32_t w, uint32_t n_full, 
     r -= r >= (int32_t)n_full ? (int32_t)n_full : 0;
     return (uint32_t)r;
 }
-__device__ __forceinline__ uint32_t shuffle_slot(uint32_t x, uint32_t n, float inv_full, int shuffle) {
-    if (!shuffle) return x;
-    const uint32_t n_full = n / SHUF_WINDOW;
-    uint32_t w = x / SHUF_WINDOW, l = x % SHUF_WINDOW;
-    if (w >= n_full) return x;
-    l = (l * 2654435761u + 0x9e37u * w) & (SHUF_WINDOW - 1);  // odd multiplier: bijection mod 4096
-    w = shuffle_window(w, n_full, inv_full);
-    return w * SHUF_WINDOW + l;
-}
-
 // per-cell read counts from the family-major read offsets
 __global__ void __launch_bounds__(256)
 cell_read_count_kernel(const uint64_t* __restrict__ read_offset, const int64_t* __restrict__ fam_offsets, int64_t n_cells,
@@ -176,25 +170,40 @@ cell_read_count_kernel(const uint64_t* __restrict__ read_offset, const int64_t* 
 // family (warp_base + l) and parks its attributes in shared memory; the warp then walks the
 // contiguous range of reads those families own, one read per lane per step, so lanes stay
 // busy whatever the family sizes are (a per-family loop leaves ~45 % of the lanes idle).
-struct FamSlot {
+//
+// Where a read goes: read x of its cell (family-major numbering) belongs to window x / 4096, and a
+// window lands as a whole in one output tile.  A family touches at most two windows unless it is longer
+// than a window, so the lane that parks the family also works out the two destination tiles once
+// (tile_a, tile_b; bit 31 = "this window is not scrambled") and a read only picks one of them.
+#define SLOT_IDENT 0x80000000u
+struct __align__(16) FamSlot {
     uint32_t local_off;   // first read of the family, relative to the warp's first read
     uint32_t cell_off;    // first read of the family, relative to its cell (or to the chunk)
-    uint32_t cell_n;      // reads in that cell (or chunk): range of the shuffle
-    uint32_t fam;         // family index inside the cell (Philox counter word)
-    uint32_t c2, c3;      // Philox counter words of the cell
+    uint32_t tile_a;      // destination tile of window cell_off / 4096
+    uint32_t tile_b;      // ... and of the next window
+    uint32_t key;         // Philox2x32 key of the family's read stream
+    uint32_t ctr_hi;      // low 16 bits of the cell id << 16 (counter word 0 = ctr_hi | read index)
+    uint32_t fam;         // family index inside the cell (counter word 1)
     uint32_t word;        // umi[23:0] | has_variant[24] | ref[27:26] | alt[29:28]
     uint32_t group;
-    int64_t out_start;    // output position of the cell's (chunk's) first read
     int32_t ci;
-    float inv_full;       // shuffle_inv(cell_n)
+    uint32_t cell_n;      // reads in that cell (or chunk): range of the shuffle (slow path, hopping)
+    uint32_t tile0;       // first output tile of the cell
 };
+
+// destination tile (| SLOT_IDENT) of source window w of a cell with n reads whose output starts at tile0
+__device__ __forceinline__ uint32_t window_tile(uint32_t w, uint32_t n, float inv_full, int shuffle, uint32_t tile0) {
+    const uint32_t n_full = n / SHUF_WINDOW;
+    if (!shuffle || w >= n_full) return (tile0 + w) | SLOT_IDENT;
+    return tile0 + shuffle_window(w, n_full, inv_full);
+}
 
 __global__ void __launch_bounds__(256)
 reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                  int64_t n_fam, pmrd_read_sim_params sp, const uint64_t* __restrict__ read_offset /*[n_fam]*/,
-                 const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_word, const int32_t* __restrict__ blk_cell,
-                 int64_t n_reads, int segmented, uint64_t* __restrict__ keys, uint32_t* __restrict__ payload,
-                 uint32_t* __restrict__ tile_hist /* [n_tiles][256], zeroed, or NULL */) {
+                 const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_word, const uint32_t* __restrict__ fam_key,
+                 const int32_t* __restrict__ blk_cell, int64_t n_reads, int segmented, uint64_t* __restrict__ keys,
+                 uint32_t* __restrict__ payload, uint32_t* __restrict__ tile_hist /* [n_tiles][256], zeroed, or NULL */) {
     __shared__ FamSlot s_slot[8][32];
     __shared__ uint32_t s_qthr[32];
     __shared__ __align__(16) uint8_t s_qlut[1 << QUAL_LUT_BITS];
@@ -203,48 +212,48 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
     reinterpret_cast<uint4*>(s_qlut)[threadIdx.x] = reinterpret_cast<const uint4*>(c_qual_lut)[threadIdx.x];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t f = (int64_t)blockIdx.x * READS_FAM_BLOCK + threadIdx.x;
-    const Philox ph(seed);
     const bool valid = f < n_fam;
     int64_t off = 0;
     uint32_t size = 0;
     if (valid) {
         const int ci = find_cell_in(fam_offsets, blk_cell[blockIdx.x], blk_cell[blockIdx.x + 1] + 1, f);
         const ReadCell c = cells[ci];
-        const uint32_t fam = (uint32_t)(f - c.fam_offset);
         off = (int64_t)read_offset[f];
         size = fam_size[f];
         const uint32_t fw = fam_word[f];
         FamSlot& S = s_slot[warp][lane];
-        S.fam = fam;
-        S.c2 = (uint32_t)c.cell_id;
-        S.c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((c.cell_id >> 32) & 0xffffffu);
+        S.fam = (uint32_t)(f - c.fam_offset);
+        S.key = fam_key[f];
+        S.ctr_hi = (uint32_t)c.cell_id << 16;
         S.word = fw | (c.ref_allele << 26) | (c.alt_allele << 28);
         S.group = c.group;
         S.ci = ci;
         if (segmented) {
             S.cell_off = (uint32_t)(off - c.read_start);
             S.cell_n = c.n_reads;
-            S.out_start = c.out_start;
+            S.tile0 = (uint32_t)(c.out_start / SHUF_WINDOW);
         } else {
             S.cell_off = (uint32_t)off;
             S.cell_n = (uint32_t)n_reads;
-            S.out_start = 0;
+            S.tile0 = 0u;
         }
-        S.inv_full = shuffle_inv(S.cell_n);
+        const float inv_full = shuffle_inv(S.cell_n);
+        const uint32_t w0 = S.cell_off / SHUF_WINDOW;
+        S.tile_a = window_tile(w0, S.cell_n, inv_full, sp.shuffle, S.tile0);
+        S.tile_b = window_tile(w0 + 1u, S.cell_n, inv_full, sp.shuffle, S.tile0);
         if (tile_hist) {
             // By-product for the collapse stage: the first radix pass needs, per 4096-slot tile of the
             // output, the histogram of the low UMI byte.  A window of the family-major read order lands
             // in ONE tile and a family's reads share their UMI, so the whole histogram costs one
             // reduction per (family, window) -- 0.2 per read -- instead of a pass over the 8 B/read.
-            const uint32_t n_full = S.cell_n / SHUF_WINDOW;
             uint32_t x = S.cell_off, rem = size;
-            uint32_t* const row0 = tile_hist + (S.out_start / SHUF_WINDOW) * 256 + (fw & 0xffu);
+            uint32_t* const col = tile_hist + (fw & 0xffu);
             while (rem) {
                 const uint32_t w = x / SHUF_WINDOW;
                 const uint32_t room = SHUF_WINDOW - x % SHUF_WINDOW;
                 const uint32_t take = rem < room ? rem : room;
-                const uint32_t dw = (sp.shuffle && w < n_full) ? shuffle_window(w, n_full, S.inv_full) : w;
-                atomicAdd(row0 + (size_t)dw * 256, take);
+                const uint32_t t = w == w0 ? S.tile_a : (w == w0 + 1u ? S.tile_b : window_tile(w, S.cell_n, inv_full, sp.shuffle, S.tile0));
+                atomicAdd(col + (size_t)(t & ~SLOT_IDENT) * 256, take);
                 x += take;
                 rem -= take;
             }
@@ -261,6 +270,7 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
     for (int o = 16; o > 0; o >>= 1) total = max(total, __shfl_xor_sync(0xffffffffu, total, o));
     __syncthreads();
     const uint32_t le = lanemask_lt() | (1u << lane);
+    const bool hopping = sp.hop_rate > 0.0 && n_cells > 1;
     for (uint32_t k0 = 0; k0 < total; k0 += 32) {
         const uint32_t k = k0 + lane;
         // owner of read k = (number of families whose first read is <= k) - 1.  Lane s still holds
@@ -272,13 +282,16 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         const uint32_t heads = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
         if (k >= total) continue;
         const uint32_t lo = before + __popc(heads & le) - 1u;
-        const FamSlot S = s_slot[warp][lo];
-        const uint32_t j = k - S.local_off;
-        const uint32_t umi = S.word & 0xffffffu, ref = (S.word >> 26) & 3u, alt = (S.word >> 28) & 3u;
-        const bool has_variant = (S.word >> 24) & 1u;
-        // one Philox block feeds TWO reads: 64 random bits per read
-        const uint4 r4 = ph(j >> 1, S.fam, S.c2, S.c3);
-        const uint32_t ra = (j & 1u) ? r4.z : r4.x, rb = (j & 1u) ? r4.w : r4.y;
+        const FamSlot& S = s_slot[warp][lo];
+        const uint4 sa = *reinterpret_cast<const uint4*>(&S.local_off);   // local_off, cell_off, tile_a, tile_b
+        const uint4 sb = *reinterpret_cast<const uint4*>(&S.key);         // key, ctr_hi, fam, word
+        const uint32_t j = k - sa.x;
+        const uint32_t word = sb.w;
+        const uint32_t umi = word & 0xffffffu, ref = (word >> 26) & 3u, alt = (word >> 28) & 3u;
+        const bool has_variant = (word >> 24) & 1u;
+        // 64 random bits per read: Philox2x32-10 keyed by the family, counter = (cell | read, family)
+        const uint2 r2 = philox2x32(sb.x, sb.y | j, sb.z);
+        const uint32_t ra = r2.x, rb = r2.y;
         // io.py:105-108 (16-bit uniform: thresholds 0.9 / 0.95 are hit to 7e-6)
         const uint32_t ua = rb & 0xffffu;
         uint32_t allele;
@@ -294,20 +307,31 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         const uint32_t strand = ra & 1u;
         const uint32_t rpos = 10u + (((rb >> 16) * 140u) >> 16);     // io.py:119 randint(10, 150)
         uint32_t pl = allele | ((uint32_t)q << 2) | (strand << 8) | (rpos << 9) | ((allele == alt ? 1u : 0u) << 31);
-        uint64_t key = ((uint64_t)S.group << 32) | umi;
-        if (sp.hop_rate > 0.0 && n_cells > 1) {
+        uint32_t group = 0;
+        if (payload) group = S.group;
+        if (hopping) {
             // index hopping: the read is assigned to another sample's index (contamination.py:230-254)
-            const uint4 h = ph(0x80000000u | j, S.fam, S.c2, S.c3);  // (a block of its own: hopping is rare)
+            const Philox ph(seed);
+            const uint32_t c2 = (uint32_t)cells[S.ci].cell_id;
+            const uint32_t c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((cells[S.ci].cell_id >> 32) & 0xffffffu);
+            const uint4 h = ph(0x80000000u | j, sb.z, c2, c3);  // (a block of its own: hopping is rare)
             if (u24(h.x) < (float)sp.hop_rate) {
                 const uint32_t other = (uint32_t)S.ci + 1u + h.y % (uint32_t)(n_cells - 1);
                 const ReadCell oc = cells[other % (uint32_t)n_cells];
-                key = ((uint64_t)oc.group << 32) | umi;
+                group = oc.group;
                 pl = (pl & 0x7fffffffu) | ((allele == oc.alt_allele ? 1u : 0u) << 31);
             }
         }
-        const int64_t dst = S.out_start + (int64_t)shuffle_slot(S.cell_off + j, S.cell_n, S.inv_full, sp.shuffle);
+        // slot: window x / 4096 goes to one tile; inside a scrambled window the slot is an odd-multiplier affine map
+        const uint32_t x = sa.y + j;
+        const uint32_t w = x / SHUF_WINDOW, dw = w - sa.y / SHUF_WINDOW;
+        uint32_t t = dw == 0u ? sa.z : sa.w;
+        if (dw > 1u) t = window_tile(w, S.cell_n, shuffle_inv(S.cell_n), sp.shuffle, S.tile0);   // a family longer than a window
+        uint32_t l = x % SHUF_WINDOW;
+        if (!(t & SLOT_IDENT)) l = (l * 2654435761u + 0x9e37u * w) & (SHUF_WINDOW - 1);
+        const int64_t dst = (int64_t)(t & ~SLOT_IDENT) * SHUF_WINDOW + l;
         if (payload) {
-            keys[dst] = key;
+            keys[dst] = ((uint64_t)group << 32) | umi;
             payload[dst] = pl;
         } else {
             // packed 8-byte record (cell-major layout: the cell is implied by the position)
@@ -392,6 +416,7 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
     if (e == cudaSuccess) e = plan->fam_offsets.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
     if (e == cudaSuccess) e = plan->fam_size.alloc(ctx->stream, 4 * (size_t)(nf + 1));
     if (e == cudaSuccess) e = plan->fam_word.alloc(ctx->stream, 4 * (size_t)(nf + 1));
+    if (e == cudaSuccess) e = plan->fam_key.alloc(ctx->stream, 4 * (size_t)(nf + 1));
     if (e == cudaSuccess) e = plan->read_offset.alloc(ctx->stream, 8 * (size_t)(nf + 1));
     if (e == cudaSuccess) e = plan->total.alloc(ctx->stream, 8);
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
@@ -496,7 +521,8 @@ int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
     PMRD_LAUNCH(ctx, reads_size_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
                 plan->has_size_cdf ? (const float*)plan->size_cdf.as<float>() : (const float*)nullptr,
-                (const int32_t*)plan->blk_cell.as<int32_t>(), plan->fam_size.as<uint32_t>(), plan->fam_word.as<uint32_t>());
+                (const int32_t*)plan->blk_cell.as<int32_t>(), plan->fam_size.as<uint32_t>(), plan->fam_word.as<uint32_t>(),
+                plan->fam_key.as<uint32_t>());
     return exclusive_scan<uint32_t, uint64_t>(ctx, plan->fam_size.as<uint32_t>(), plan->read_offset.as<uint64_t>(), plan->n_fam,
                                               plan->total.as<uint64_t>());
 }
@@ -511,7 +537,8 @@ int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uin
     PMRD_LAUNCH(ctx, reads_gen_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
                 (const uint64_t*)plan->read_offset.as<uint64_t>(), (const uint32_t*)plan->fam_size.as<uint32_t>(),
-                (const uint32_t*)plan->fam_word.as<uint32_t>(), (const int32_t*)plan->blk_cell.as<int32_t>(), plan->n_reads,
+                (const uint32_t*)plan->fam_word.as<uint32_t>(), (const uint32_t*)plan->fam_key.as<uint32_t>(),
+                (const int32_t*)plan->blk_cell.as<int32_t>(), plan->n_reads,
                 plan->segmented, d_keys, d_payload, d_tile_hist);
     if (plan->segmented && plan->n_out > plan->n_reads)
         PMRD_LAUNCH(ctx, reads_pad_kernel, (int)plan->n_cells, 256, 0, plan->cells.as<ReadCell>(), (int)plan->n_cells,
