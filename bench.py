@@ -161,34 +161,59 @@ def cpu_baseline(cfg, cell_id, af, depth, budget_s=12.0):
 
 
 # ------------------------------------------------------------------------------- LoD grid
-def lod_grid_wall(cfg):
+def lod_grid_wall(cfg, world=1, barrier=None):
     """Second half of BASELINE.json's metric: wall time of the eval-lod grid (C3 of SURVEY.md §8d:
     LoB blanks + 15 log-spaced AF in [1e-4, 1e-2] x depths {1k,5k,10k,50k,100k} x 25 replicates, 200-resample
     logistic bootstrap per depth) from LODAnalyzer entry to the finished tables, host wall clock."""
+    import contextlib
     import copy
+    import io
     import tempfile
 
     from precise_mrd.eval import LODAnalyzer
 
     out = {}
     depths = [1000, 5000, 10000, 50000, 100000]
-    for engine, reps in (("grid", 25), ("stages", 2)):
+    # world > 1: every rank enters; LODAnalyzer shards the cells over the ranks (LPT on the family count) and
+    # all-gathers the per-cell counts once per grid (precise_mrd.distributed); wall = barrier to barrier
+    engines = (("grid", 25), ("stages", 2)) if world == 1 else (("grid", 25),)
+    from precise_mrd import _native as nv
+
+    def analysis(engine, reps):
         c = copy.deepcopy(cfg)
         c.seed = 7
-        t0 = time.perf_counter()
         an = LODAnalyzer(c, np.random.default_rng(7), engine=engine)
-        import contextlib
-        import io
-
         with contextlib.redirect_stdout(io.StringIO()):
             an.estimate_lob(n_blank_runs=max(10, reps // 2))
             res = an.estimate_lod(depth_values=depths if engine == "grid" else depths[:3], n_replicates=reps)
             with tempfile.TemporaryDirectory() as td:
                 an.generate_reports(td)
+        return res
+
+    for engine, reps in engines:
+        if engine == "grid":
+            analysis(engine, reps)                   # warm-up: allocator pool, module load
+        if barrier:
+            barrier()
+        t0 = time.perf_counter()
+        res = analysis(engine, reps)
+        if barrier:
+            barrier()
         wall = time.perf_counter() - t0
         n_dep = len(res["depth_results"])
-        out[engine] = {"wall_s": wall, "cells": 15 * n_dep * reps, "depths": n_dep, "replicates": reps,
+        out[engine] = {"wall_s": wall, "n_gpus": world, "cells": 15 * n_dep * reps, "depths": n_dep, "replicates": reps,
                        "lod_af": {str(d): r["lod_af"] for d, r in res["depth_results"].items()}}
+        if engine == "grid":
+            # device-only time of the same analysis (per-kernel CUDA events on this rank), so that the host part is visible
+            dctx = nv.default_context(7)
+            dctx.profile_enable(True)
+            analysis(engine, reps)
+            prof = dctx.profile_report()
+            dctx.profile_enable(False)
+            out[engine]["device_ms"] = round(sum(v[1] for v in prof.values()), 3)
+            out[engine]["device_launches"] = int(sum(v[0] for v in prof.values()))
+            top = sorted(prof.items(), key=lambda kv: -kv[1][1])[:4]
+            out[engine]["device_top_ms"] = {k: round(v[1], 3) for k, v in top}
     out["note"] = ("grid = read-level fused device plan over the whole C3 grid (1875 cells + blanks); stages = the reference's own "
                    "per-cell simulate->collapse->fit_error_model->call_mrd loop with every stage on the GPU (parity engine; 90 cells "
                    "timed here, the reference's default 1125-cell grid scales linearly; the reference itself needs 3-7 s per cell)")
@@ -196,7 +221,7 @@ def lod_grid_wall(cfg):
 
 
 # ------------------------------------------------------------------------------- reference arm
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit):
     if rank != 0:
         return 0
     cfg, label, cell_id, af, depth = workload(args.workload, 0, 1)
@@ -223,7 +248,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -242,8 +267,16 @@ def main() -> int:
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries ONE JSON line: anything a library prints on fd 1 meanwhile (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, rank, world, emit)
 
     import torch
     import torch.distributed as dist
@@ -322,6 +355,10 @@ def main() -> int:
     value = total_reads * args.steps / (ms_max * 1e-3)
     e2e_value = total_reads * args.steps / (e2e_ms_max * 1e-3)
 
+    lod = None
+    if not args.no_lod:
+        lod = lod_grid_wall(cfg, world, barrier if world > 1 else None)      # every rank takes part when world > 1
+
     if rank == 0:
         peak, peak_src = peak_hbm()
         # Per-kernel device time comes from CUDA events recorded inside the timed region.  The radix scatter
@@ -333,9 +370,11 @@ def main() -> int:
         slots = pinfo["n_slots"]                                       # record slots per step (reads + tile padding)
         passes = pinfo["sort_passes"]
         n_staged = sum(v[0] for k, v in prof.items() if k.startswith("rs_downsweep_staged_kernel")) / max(args.steps * n_chunks, 1)
+        # the generator counts the first digit as a by-product (PMRD_GEN_HIST, default on): one counting pass fewer
+        up_passes = passes - (0 if os.environ.get("PMRD_GEN_HIST", "1") == "0" else 1)
         groups = {
             "rs_downsweep": (["rs_downsweep_direct_kernel", "rs_downsweep_staged_kernel", "rs_downsweep_kernel<false>"], 2.0 * rec * passes),
-            "rs_upsweep_kernel": (["rs_upsweep_kernel"], 8.0 * passes),
+            "rs_upsweep_kernel": (["rs_upsweep_kernel"], 8.0 * up_passes),
             "reads_gen_kernel": (["reads_gen_kernel"], float(rec)),
             "cell_consensus_kernel": (["cell_consensus_kernel<true>", "cell_consensus_kernel<false>"], float(rec)),
         }
@@ -360,7 +399,7 @@ def main() -> int:
                 if top["launches"] else None,
                 "bytes_per_record": top["algorithmic_bytes_per_record"] / (passes if top["kernel"].startswith("rs_") else 1),
                 "records_per_launch": slots / max(n_chunks, 1), "staged_passes_per_chunk": n_staged,
-                "note": "reads_gen_kernel is INT32-issue bound (Philox4x32-10 per read; ncu issue slots 75 % busy), "
+                "note": "reads_gen_kernel is INT32-issue bound (one Philox2x32-10 block per read), "
                         "its HBM fraction is listed for completeness only",
                 "all_hot_kernels": table}
         reads_per_launch = slots / max(n_chunks, 1)
@@ -392,14 +431,14 @@ def main() -> int:
             "result_check": {"significant_cells": int(res["significant"].sum()), "mean_error_rate": res["mean_error_rate"],
                              "families_formed": int(res["totals"][1])},
         }
-        if world == 1 and not args.no_lod:
-            line["lod_grid"] = lod_grid_wall(cfg)
+        if lod is not None:
+            line["lod_grid"] = lod
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(cfg, cell_id, af, depth)
             except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": f"failed: {exc}"}
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -365,6 +365,17 @@ int32_t pmrd_pipeline_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const doubl
                             double neg_af_max, int32_t test_type, int32_t alternative, double alpha,
                             pmrd_pipeline_result* h_out, double* h_mean_error_rate);
 
+/* The call stage of the pipeline on its own, over per-cell counts: error rate from the negative
+ * controls (mean over 64 contexts of (sum n_variants / sum n_total) * U(0.5,2), error_model.py:153-156,
+ * call.py:178), tail p per cell (call.py:182-197), BH over the batch (call.py:200-212).  This is what
+ * every rank runs after the one all-gather of per-cell counts of a grid sharded over several GPUs
+ * (SURVEY.md 8e): the same kernels as pmrd_pipeline_cells, so the table equals the single-GPU one bit
+ * for bit.  stream_id = the grid's first cell id (keys the 64 context modifiers). */
+int32_t pmrd_call_counts(pmrd_ctx* ctx, const int64_t* h_n_total, const int64_t* h_n_variants,
+                         const uint8_t* h_is_negative, int64_t n_cells, uint64_t stream_id,
+                         int32_t test_type, int32_t alternative, double alpha, double* h_p_value,
+                         double* h_p_adjusted, uint8_t* h_significant, double* h_mean_error_rate);
+
 /* The same pipeline as a prepared plan: create() uploads the cell table, sizes and
  * allocates every buffer once; run() only enqueues kernels on the context's stream (no
  * allocation, no host<->device copy, no sync -- safe to time with events or capture in a
@@ -401,6 +412,12 @@ int32_t pmrd_plan_run_call(pmrd_ctx* ctx, pmrd_plan* plan);                    /
  * out[0]=lod, out[1]=ci_lo (P2.5), out[2]=ci_hi (P97.5); NaN where the reference is NaN. */
 int32_t pmrd_fit_lod(pmrd_ctx* ctx, const double* h_af, const double* h_hit, int32_t n, double target,
                      int32_t n_boot, uint64_t stream_id, double* h_out3);
+/* The same for n_series detection curves over the same af grid in ONE launch (the per-depth loop of
+ * LODAnalyzer.estimate_lod, eval/lod.py:147-160): h_hits [n_series][n], one stream id per curve,
+ * h_out3 [n_series][3].  A fit is a latency-bound sequential iteration, so the curves of an analysis are
+ * fitted side by side; results equal n_series separate pmrd_fit_lod calls bit for bit. */
+int32_t pmrd_fit_lod_batch(pmrd_ctx* ctx, const double* h_af, const double* h_hits, int32_t n, int32_t n_series,
+                           double target, int32_t n_boot, const uint64_t* h_stream_ids, double* h_out3);
 
 #ifdef __cplusplus
 }

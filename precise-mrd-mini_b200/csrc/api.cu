@@ -53,8 +53,11 @@ int32_t k2_gd_families(pmrd_ctx* ctx, const int32_t* d_tile_cell, const int32_t*
                        uint64_t* d_tile_base, const pmrd_gd_family_table* d_out);
 int32_t k10_error_model(pmrd_ctx* ctx, int64_t n_neg, int64_t n_var, int32_t n_boot, uint64_t stream_id, double* d_rate64,
                         double* d_lo64, double* d_hi64);
-int32_t k11_fit_lod(pmrd_ctx* ctx, const double* d_af, const double* d_hit, int32_t n, double target, int32_t n_boot,
-                    uint64_t stream_id, double* d_out3);
+int32_t k11_fit_lod_batch(pmrd_ctx* ctx, const double* d_af, const double* d_hits, int32_t n, int32_t n_series, double target,
+                          int32_t n_boot, const uint64_t* d_stream_ids, double* d_out3);
+int32_t call_counts_dev(pmrd_ctx* ctx, const int64_t* d_tot, const int64_t* d_var, const uint8_t* d_neg, int64_t n_cells,
+                        uint64_t stream_id, int32_t test_type, int32_t alternative, double alpha, double* d_mean_rate,
+                        int64_t* d_negc, double* d_p, double* d_q, uint8_t* d_sig);
 struct pmrd_plan;
 int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
                     int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, double neg_af_max,
@@ -815,19 +818,52 @@ int32_t pmrd_pipeline_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const doubl
     return st;
 }
 
-// ---------------------------------------------------------------- K11 -------------------
-int32_t pmrd_fit_lod(pmrd_ctx* ctx, const double* h_af, const double* h_hit, int32_t n, double target, int32_t n_boot,
-                     uint64_t stream_id, double* h_out3) {
+// call stage over per-cell counts gathered from several GPUs: the plan's own kernels
+int32_t pmrd_call_counts(pmrd_ctx* ctx, const int64_t* h_n_total, const int64_t* h_n_variants, const uint8_t* h_is_negative,
+                         int64_t n_cells, uint64_t stream_id, int32_t test_type, int32_t alternative, double alpha,
+                         double* h_p_value, double* h_p_adjusted, uint8_t* h_significant, double* h_mean_error_rate) {
     ENTER(ctx);
-    PMRD_ARG(ctx, h_af && h_hit && h_out3 && n >= 1, "arguments");
-    DevBuf af, hit, out;
-    PMRD_TRY(up(ctx, af, h_af, (size_t)n * 8));
-    PMRD_TRY(up(ctx, hit, h_hit, (size_t)n * 8));
-    PMRD_CUDA(ctx, out.alloc(ctx->stream, 24));
-    PMRD_TRY(k11_fit_lod(ctx, af.as<double>(), hit.as<double>(), n, target, n_boot, stream_id, out.as<double>()));
-    PMRD_TRY(down(ctx, h_out3, out.p, 24));
+    PMRD_ARG(ctx, n_cells > 0 && h_n_total && h_n_variants && h_is_negative, "arguments");
+    PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || test_type == PMRD_TEST_BINOMIAL, "Unknown test type");
+    const size_t c = (size_t)n_cells;
+    DevBuf tot, var, neg, mean, negc, p, q, sig;
+    PMRD_TRY(up(ctx, tot, h_n_total, c * 8));
+    PMRD_TRY(up(ctx, var, h_n_variants, c * 8));
+    PMRD_TRY(up(ctx, neg, h_is_negative, c));
+    PMRD_CUDA(ctx, mean.alloc(ctx->stream, 8));
+    PMRD_CUDA(ctx, negc.alloc(ctx->stream, 16));
+    PMRD_CUDA(ctx, p.alloc(ctx->stream, c * 8));
+    PMRD_CUDA(ctx, q.alloc(ctx->stream, c * 8));
+    PMRD_CUDA(ctx, sig.alloc(ctx->stream, c));
+    PMRD_TRY(call_counts_dev(ctx, tot.as<int64_t>(), var.as<int64_t>(), neg.as<uint8_t>(), n_cells, stream_id, test_type, alternative,
+                             alpha, mean.as<double>(), negc.as<int64_t>(), p.as<double>(), q.as<double>(), sig.as<uint8_t>()));
+    PMRD_TRY(down(ctx, h_p_value, p.p, c * 8));
+    PMRD_TRY(down(ctx, h_p_adjusted, q.p, c * 8));
+    PMRD_TRY(down(ctx, h_significant, sig.p, c));
+    PMRD_TRY(down(ctx, h_mean_error_rate, mean.p, 8));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- K11 -------------------
+int32_t pmrd_fit_lod_batch(pmrd_ctx* ctx, const double* h_af, const double* h_hits, int32_t n, int32_t n_series, double target,
+                           int32_t n_boot, const uint64_t* h_stream_ids, double* h_out3) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, h_af && h_hits && h_stream_ids && h_out3 && n >= 1 && n_series >= 1, "arguments");
+    DevBuf af, hit, ids, out;
+    PMRD_TRY(up(ctx, af, h_af, (size_t)n * 8));
+    PMRD_TRY(up(ctx, hit, h_hits, (size_t)n * (size_t)n_series * 8));
+    PMRD_TRY(up(ctx, ids, h_stream_ids, (size_t)n_series * 8));
+    PMRD_CUDA(ctx, out.alloc(ctx->stream, (size_t)n_series * 24));
+    PMRD_TRY(k11_fit_lod_batch(ctx, af.as<double>(), hit.as<double>(), n, n_series, target, n_boot, ids.as<uint64_t>(), out.as<double>()));
+    PMRD_TRY(down(ctx, h_out3, out.p, (size_t)n_series * 24));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
+int32_t pmrd_fit_lod(pmrd_ctx* ctx, const double* h_af, const double* h_hit, int32_t n, double target, int32_t n_boot,
+                     uint64_t stream_id, double* h_out3) {
+    return pmrd_fit_lod_batch(ctx, h_af, h_hit, n, 1, target, n_boot, &stream_id, h_out3);
 }
 
 }  // extern "C"

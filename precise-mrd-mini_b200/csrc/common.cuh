@@ -53,14 +53,15 @@ extern char g_pmrd_create_err[512];
     } while (0)
 
 // launch + count + check
-#define PMRD_LAUNCH(ctx, kernel, grid, block, smem, ...)                                      \
+#define PMRD_LAUNCH_NAMED(ctx, name, kernel, grid, block, smem, ...)                          \
     do {                                                                                      \
-        if ((ctx)->prof_on) pmrd_prof_begin(ctx, #kernel);                                    \
+        if ((ctx)->prof_on) pmrd_prof_begin(ctx, name);                                       \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                      \
         if ((ctx)->prof_on) pmrd_prof_end(ctx);                                               \
         (ctx)->launches++;                                                                    \
         PMRD_CUDA(ctx, cudaGetLastError());                                                   \
     } while (0)
+#define PMRD_LAUNCH(ctx, kernel, grid, block, smem, ...) PMRD_LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
 
 // stream-ordered scratch buffer; freed on scope exit (cudaFreeAsync on the same stream)
 struct DevBuf {

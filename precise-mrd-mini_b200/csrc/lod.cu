@@ -61,6 +61,9 @@ __host__ __device__ static double lm_enorm(int n, const double* x) {
 
 // residuals: logistic(x; a, b) - y     (lod.py:360-361 through curve_fit's wrapper)
 __host__ __device__ static void lm_fcn(const LmProblem& P, const double* p, double* f) {
+    // (the residuals are independent: unrolled so that the fp64 exp / divide chains of several points overlap --
+    // a refit is ONE thread, bound by dependent-instruction latency)
+#pragma unroll 5
     for (int i = 0; i < P.m; ++i) f[i] = 1.0 / (1.0 + exp(-(p[0] * P.x[i] + p[1]))) - P.y[i];
 }
 
@@ -410,12 +413,16 @@ __host__ __device__ static double lod_fit_one(const LmProblem& P, const double* 
     return lod_interp_fallback(P, af, target);
 }
 
-// thread 0 of the grid: point estimate; threads 1..n_boot: resampled pairs (lod.py:389-399)
+// thread 0 of a series: point estimate; threads 1..n_boot: resampled pairs (lod.py:389-399).
+// blockIdx.y = series (one detection curve per depth): all curves of an analysis are fitted by ONE launch
+// -- a fit is a latency-bound sequential LM iteration, so five launches cost five times the slowest refit.
 __global__ void __launch_bounds__(64)
-lod_fit_kernel(uint64_t seed, uint64_t stream_id, const double* __restrict__ af, const double* __restrict__ hit, int m,
-               double target, int n_boot, double* __restrict__ fits /*[1+n_boot]*/) {
+lod_fit_kernel(uint64_t seed, const uint64_t* __restrict__ stream_ids, const double* __restrict__ af,
+               const double* __restrict__ hits /*[S][m]*/, int m, double target, int n_boot, double* __restrict__ fits /*[S][1+n_boot]*/) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_boot) return;
+    const uint64_t stream_id = stream_ids[blockIdx.y];
+    const double* __restrict__ hit = hits + (size_t)blockIdx.y * m;
     LmProblem P;
     double afs[LOD_MAX_M];
     P.m = m;
@@ -431,7 +438,7 @@ lod_fit_kernel(uint64_t seed, uint64_t stream_id, const double* __restrict__ af,
         P.x[i] = log10(af[src]);
         P.y[i] = hit[src];
     }
-    fits[t] = lod_fit_one(P, afs, target);
+    fits[(size_t)blockIdx.y * (n_boot + 1) + t] = lod_fit_one(P, afs, target);
 }
 
 // numpy.percentile(method='linear') incl. its lerp form; NaN in -> NaN out
@@ -444,9 +451,11 @@ __host__ __device__ static double np_percentile_sorted(const double* s, int n, d
     return t >= 0.5 ? b - d * (1.0 - t) : a + d * t;
 }
 
-__global__ void __launch_bounds__(256) lod_ci_kernel(const double* __restrict__ fits, int n_boot, double* __restrict__ out3) {
+__global__ void __launch_bounds__(256) lod_ci_kernel(const double* __restrict__ fits_all, int n_boot, double* __restrict__ out3_all) {
     extern __shared__ double s_v[];
     __shared__ int s_nan;
+    const double* __restrict__ fits = fits_all + (size_t)blockIdx.x * (n_boot + 1);   // one block per series
+    double* __restrict__ out3 = out3_all + (size_t)blockIdx.x * 3;
     if (threadIdx.x == 0) s_nan = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < n_boot; i += blockDim.x) {
@@ -474,15 +483,16 @@ __global__ void __launch_bounds__(256) lod_ci_kernel(const double* __restrict__ 
     }
 }
 
-int32_t k11_fit_lod(pmrd_ctx* ctx, const double* d_af, const double* d_hit, int32_t n, double target, int32_t n_boot,
-                    uint64_t stream_id, double* d_out3) {
+int32_t k11_fit_lod_batch(pmrd_ctx* ctx, const double* d_af, const double* d_hits, int32_t n, int32_t n_series, double target,
+                          int32_t n_boot, const uint64_t* d_stream_ids, double* d_out3 /*[S][3]*/) {
     PMRD_ARG(ctx, n >= 1 && n <= LOD_MAX_M, "1 <= n <= 64 curve points");
+    PMRD_ARG(ctx, n_series >= 1 && n_series <= 65535, "1 <= n_series <= 65535");
     PMRD_ARG(ctx, n_boot >= 0 && n_boot <= 4096, "0 <= n_boot <= 4096");
     PMRD_ARG(ctx, target > 0.0 && target < 1.0, "0 < target < 1");
     DevBuf fits;
-    PMRD_CUDA(ctx, fits.alloc(ctx->stream, (size_t)(n_boot + 1) * 8));
-    PMRD_LAUNCH(ctx, lod_fit_kernel, pmrd_blocks(n_boot + 1, 64), 64, 0, ctx->seed, stream_id, d_af, d_hit, (int)n, target,
-                (int)n_boot, fits.as<double>());
-    PMRD_LAUNCH(ctx, lod_ci_kernel, 1, 256, (size_t)(n_boot > 0 ? n_boot : 1) * 8, (const double*)fits.as<double>(), (int)n_boot, d_out3);
+    PMRD_CUDA(ctx, fits.alloc(ctx->stream, (size_t)n_series * (size_t)(n_boot + 1) * 8));
+    PMRD_LAUNCH(ctx, lod_fit_kernel, dim3(pmrd_blocks(n_boot + 1, 64), n_series), 64, 0, ctx->seed, d_stream_ids, d_af, d_hits, (int)n,
+                target, (int)n_boot, fits.as<double>());
+    PMRD_LAUNCH(ctx, lod_ci_kernel, n_series, 256, (size_t)(n_boot > 0 ? n_boot : 1) * 8, (const double*)fits.as<double>(), (int)n_boot, d_out3);
     return PMRD_OK;
 }

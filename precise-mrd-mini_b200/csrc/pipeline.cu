@@ -305,16 +305,22 @@ static int32_t plan_reset_outputs(pmrd_ctx* ctx, pmrd_plan* P) {
     return PMRD_OK;
 }
 
-// call stage over ALL cells: error rate from the negative controls, tail p per cell, BH (K8, K9)
-int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
-    const int64_t n_cells = P->n_cells;
-    PMRD_LAUNCH(ctx, error_rate_kernel, 1, 256, 0, ctx->seed, P->stream_id, (const int64_t*)P->o_tot.as<int64_t>(),
-                (const int64_t*)P->o_var.as<int64_t>(), (const uint8_t*)P->neg.as<uint8_t>(), n_cells, P->mean_rate.as<double>(),
-                P->negc.as<int64_t>());
-    PMRD_TRY(k8_pvalues(ctx, P->o_var.as<int64_t>(), P->o_tot.as<int64_t>(), P->mean_rate.as<double>(), 0, n_cells, P->test_type,
-                        P->alternative, P->o_p.as<double>()));
-    PMRD_TRY(k9_bh(ctx, P->o_p.as<double>(), n_cells, P->alpha, P->o_sig.as<uint8_t>(), P->o_q.as<double>()));
+// call stage over ALL cells: error rate from the negative controls, tail p per cell, BH (K8, K9).
+// Device arrays in, device arrays out; shared by the plan and by pmrd_call_counts (the multi-GPU finish:
+// every rank runs it over the all-gathered counts, so the table is the single-GPU one bit for bit).
+int32_t call_counts_dev(pmrd_ctx* ctx, const int64_t* d_tot, const int64_t* d_var, const uint8_t* d_neg, int64_t n_cells,
+                        uint64_t stream_id, int32_t test_type, int32_t alternative, double alpha, double* d_mean_rate,
+                        int64_t* d_negc, double* d_p, double* d_q, uint8_t* d_sig) {
+    PMRD_LAUNCH(ctx, error_rate_kernel, 1, 256, 0, ctx->seed, stream_id, d_tot, d_var, d_neg, n_cells, d_mean_rate, d_negc);
+    PMRD_TRY(k8_pvalues(ctx, d_var, d_tot, d_mean_rate, 0, n_cells, test_type, alternative, d_p));
+    PMRD_TRY(k9_bh(ctx, d_p, n_cells, alpha, d_sig, d_q));
     return PMRD_OK;
+}
+
+int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
+    return call_counts_dev(ctx, P->o_tot.as<int64_t>(), P->o_var.as<int64_t>(), P->neg.as<uint8_t>(), P->n_cells, P->stream_id,
+                           P->test_type, P->alternative, P->alpha, P->mean_rate.as<double>(), P->negc.as<int64_t>(),
+                           P->o_p.as<double>(), P->o_q.as<double>(), P->o_sig.as<uint8_t>());
 }
 
 // Stage entry points for per-stage timing.  With more than one chunk the read buffers are

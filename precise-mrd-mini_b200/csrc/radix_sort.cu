@@ -288,21 +288,24 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
 // in L2 before they are evicted (DRAM write traffic stays at 8 B / record -- checked with ncu),
 // and the shared-memory reorder (a bank-conflicted 64-bit scatter + a gather + a barrier) is gone.
 // (whole tiles only: the cell-major layout pads every cell to a multiple of RS_TILE)
-__global__ void __launch_bounds__(RS_THREADS, RS_DIRECT_MIN_BLOCKS)
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                            const uint32_t* __restrict__ hist_scanned, int shift, uint32_t mask) {
-    __shared__ uint32_t s_cnt[RS_WARPS][RS_MAX_BINS];
+    static_assert(THREADS * ITEMS == RS_TILE, "one 4096-record tile per block");
+    constexpr int WARPS = THREADS / 32;
+    __shared__ uint32_t s_cnt[WARPS][RS_MAX_BINS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = lanemask_lt();
-    for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&s_cnt[0][0])[i] = 0;
-    const uint64_t* __restrict__ src = keys_in + (int64_t)blockIdx.x * RS_TILE + warp * (RS_TILE / RS_WARPS) + lane;
-    uint64_t key[RS_ITEMS];
+    for (int i = threadIdx.x; i < WARPS * RS_MAX_BINS; i += THREADS) (&s_cnt[0][0])[i] = 0;
+    const uint64_t* __restrict__ src = keys_in + (int64_t)blockIdx.x * RS_TILE + warp * (RS_TILE / WARPS) + lane;
+    uint64_t key[ITEMS];
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) key[i] = src[i * 32];
+    for (int i = 0; i < ITEMS; ++i) key[i] = src[i * 32];
     __syncthreads();
-    uint32_t rank2[RS_ITEMS / 2];   // two 16-bit ranks per register
+    uint32_t rank2[ITEMS / 2];   // two 16-bit ranks per register
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
         const uint32_t m = rs_peer_mask(d, 0xffffffffu);
         const uint32_t before = __popc(m & lt);
@@ -319,7 +322,7 @@ rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
     if (threadIdx.x < RS_MAX_BINS) {
         uint32_t run = hist_scanned[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x];
 #pragma unroll
-        for (int w = 0; w < RS_WARPS; ++w) {
+        for (int w = 0; w < WARPS; ++w) {
             const uint32_t c = s_cnt[w][threadIdx.x];
             s_cnt[w][threadIdx.x] = run;
             run += c;
@@ -327,7 +330,7 @@ rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
         const uint32_t r = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
         keys_out[s_cnt[warp][d] + r] = key[i];
@@ -496,7 +499,12 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         } else if (stage) {
             PMRD_LAUNCH(ctx, rs_downsweep_staged_kernel, n_tiles, RS_THREADS, sizeof(RsStage), kin, kout, hist, shift, mask);
         } else if (direct) {   // packed 8-byte records, stored straight to their final place (L2 merges the sectors)
-            PMRD_LAUNCH(ctx, rs_downsweep_direct_kernel, n_tiles, RS_THREADS, 0, kin, kout, hist, shift, mask);
+            static int wide = -1;
+            if (wide < 0) { const char* e = getenv("PMRD_RS_WIDE"); wide = e ? atoi(e) : 2; }   // 2: 256 threads x 16 records, 4 blocks / SM (measured best, by 3 %)
+            if (wide == 1) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<1024, 4, 2>), n_tiles, 1024, 0, kin, kout, hist, shift, mask);
+            else if (wide == 2) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<256, 16, 4>), n_tiles, 256, 0, kin, kout, hist, shift, mask);
+            else if (wide == 3) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<256, 16, 3>), n_tiles, 256, 0, kin, kout, hist, shift, mask);
+            else PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>), n_tiles, RS_THREADS, 0, kin, kout, hist, shift, mask);
         } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);
         }

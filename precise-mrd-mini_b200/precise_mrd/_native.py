@@ -355,6 +355,19 @@ class Context:
         finally:
             plan.close()
 
+    def call_counts(self, n_total, n_variants, is_negative, stream_id: int, test_type: int = TEST_POISSON,
+                    alternative: int = ALT_TWO_SIDED, alpha: float = 0.05) -> Dict[str, np.ndarray]:
+        """The pipeline's call stage over per-cell counts (``pmrd_call_counts``): what every rank runs
+        after the all-gather of a grid sharded over several GPUs."""
+        tot, var = _arr(n_total, np.int64), _arr(n_variants, np.int64)
+        neg = np.ascontiguousarray(np.asarray(is_negative).astype(np.uint8))
+        c = tot.shape[0]
+        p, q, sig, rate = np.zeros(c), np.zeros(c), np.zeros(c, np.uint8), np.zeros(1)
+        self._check(self.lib.pmrd_call_counts(self.h, _ptr(tot), _ptr(var), _ptr(neg), C.c_int64(c), C.c_uint64(stream_id),
+                                              C.c_int32(test_type), C.c_int32(alternative), C.c_double(alpha), _ptr(p), _ptr(q),
+                                              _ptr(sig), _ptr(rate)))
+        return {"p_value": p, "p_adjusted": q, "significant": sig.astype(bool), "mean_error_rate": float(rate[0])}
+
     # -- K14 -----------------------------------------------------------------------------
     def fisher_exact(self, tables) -> Tuple[np.ndarray, np.ndarray]:
         """(odds_ratio[m], p[m]) of m 2x2 tables given as [m, 4] = c00 c01 c10 c11 (two-sided)."""
@@ -413,12 +426,24 @@ class Context:
 
     # -- K11 -----------------------------------------------------------------------------
     def fit_lod(self, af, hit, target: float = 0.95, n_boot: int = 200, stream_id: int = 0):
+        """(lod, ci_lo, ci_hi) of one detection curve (``pmrd_fit_lod``)."""
+        return self.fit_lod_batch(af, np.asarray(hit, dtype=np.float64)[None, :], target, n_boot, [stream_id])[0]
+
+    def fit_lod_batch(self, af, hits, target: float = 0.95, n_boot: int = 200, stream_ids=None):
+        """[(lod, ci_lo, ci_hi)] of ``hits.shape[0]`` detection curves over the same AF grid, fitted by one
+        launch (``pmrd_fit_lod_batch``); equal to separate ``fit_lod`` calls bit for bit."""
         af = _arr(af, np.float64)
-        hit = _arr(hit, np.float64)
-        out = np.zeros(3)
-        self._check(self.lib.pmrd_fit_lod(self.h, _ptr(af), _ptr(hit), C.c_int32(af.shape[0]), C.c_double(target),
-                                          C.c_int32(n_boot), C.c_uint64(stream_id), _ptr(out)))
-        return float(out[0]), float(out[1]), float(out[2])
+        hits = np.ascontiguousarray(np.asarray(hits, dtype=np.float64))
+        if hits.ndim != 2 or hits.shape[1] != af.shape[0]:
+            raise ValueError("hits must be [n_series, len(af)]")
+        s = hits.shape[0]
+        ids = np.zeros(s, np.uint64) if stream_ids is None else np.ascontiguousarray(np.asarray(stream_ids, dtype=np.uint64))
+        if ids.shape[0] != s:
+            raise ValueError("one stream id per series")
+        out = np.zeros((s, 3))
+        self._check(self.lib.pmrd_fit_lod_batch(self.h, _ptr(af), _ptr(hits), C.c_int32(af.shape[0]), C.c_int32(s), C.c_double(target),
+                                                C.c_int32(n_boot), _ptr(ids), _ptr(out)))
+        return [(float(r[0]), float(r[1]), float(r[2])) for r in out]
 
 
 class Plan:

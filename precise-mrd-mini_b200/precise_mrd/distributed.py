@@ -58,14 +58,25 @@ def all_gather_rows(local_index: np.ndarray, local_rows: np.ndarray, n_total: in
     return out
 
 
+def world_size() -> int:
+    """Ranks of the initialised default process group (1 when torch.distributed is not in use)."""
+    try:
+        import torch.distributed as dist
+    except Exception:          # pragma: no cover
+        return 1
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def run_cells_sharded(config, cell_id, allele_fraction, n_families, neg_af_max: float = 1e-4, alternative: int = 0,
-                      sim=None, compute=None) -> Dict[str, np.ndarray]:
+                      sim=None, compute=None, ctx=None, finish: bool = True) -> Dict[str, np.ndarray]:
     """``precise_mrd.grid.run_cells`` over all ranks of the current process group: each rank runs
     its shard of cells through the fused device plan, the per-cell counts are all-gathered, and
-    every rank finishes the call stage (error rate, p-values, BH) over the whole grid.
+    every rank finishes the call stage (error rate, p-values, BH) over the whole grid with the
+    plan's own kernels (``pmrd_call_counts``) -- the table equals the single-GPU one bit for bit.
 
     ``compute(cell_id, af, n_families) -> {"n_total", "n_variants", "n_families", "n_reads"}`` is
-    injectable so that the sharding / gathering logic can be tested on CPU ranks (gloo)."""
+    injectable so that the sharding / gathering logic can be tested on CPU ranks (gloo); with an
+    injected ``compute`` (or ``finish=False``) only the gathered counts are returned."""
     import torch.distributed as dist
 
     from . import _native as nv
@@ -76,29 +87,30 @@ def run_cells_sharded(config, cell_id, allele_fraction, n_families, neg_af_max: 
     cell_id = np.asarray(cell_id, dtype=np.int64)
     af = np.asarray(allele_fraction, dtype=np.float64)
     nf = np.asarray(n_families, dtype=np.int64)
+    st = section(config, "stats")
+    if st["test_type"] not in nv.TEST_TYPES:
+        raise ValueError(f"Unknown test type: {st['test_type']}")      # call.py:187
     mine = shard_cells(nf, rank, world)
-    if compute is None:
+    on_device = compute is None
+    if on_device:
         from . import grid
 
-        def compute(c, a, f):          # counts only: alpha / test type do not matter here
-            return grid.run_cells(config, c, a, f, sim=sim, neg_af_max=neg_af_max, alternative=alternative)
+        ctx = ctx or nv.default_context(int(config.seed))
+
+        def compute(c, a, f):          # counts only: the rank's own p-values are discarded
+            return grid.run_cells(config, c, a, f, ctx=ctx, sim=sim, neg_af_max=neg_af_max, alternative=alternative)
 
     loc = compute(cell_id[mine], af[mine], nf[mine]) if len(mine) else {k: np.zeros(0, np.int64) for k in ("n_total", "n_variants", "n_families", "n_reads")}
     rows = np.stack([loc["n_total"], loc["n_variants"], loc["n_families"], loc["n_reads"]], axis=1) if len(mine) else np.zeros((0, 4), np.int64)
     table = all_gather_rows(mine, rows, len(cell_id))
     out = {"n_total": table[:, 0], "n_variants": table[:, 1], "n_families": table[:, 2], "n_reads": table[:, 3]}
     # call stage over the full grid, identically on every rank (call.py:178-229)
-    st = section(config, "stats")
     neg = af <= neg_af_max
     if not neg.any():
         neg = af == af.min()
     out["negative_control"] = neg
-    out["finish"] = lambda ctx, mean_rate: _finish(ctx, out, mean_rate, nv.TEST_TYPES[st["test_type"]], alternative, float(st["alpha"]))
-    return out
-
-
-def _finish(ctx, out, mean_rate: float, test_type: int, alternative: int, alpha: float):
-    p = ctx.pvalues(out["n_variants"], out["n_total"], mean_rate, test_type, alternative)
-    rej, q = ctx.bh(p, alpha)
-    out.update({"p_value": p, "p_adjusted": q, "significant": rej, "variant_call": rej, "mean_error_rate": mean_rate})
+    if on_device and finish:
+        out.update(ctx.call_counts(out["n_total"], out["n_variants"], neg, int(cell_id[0]), nv.TEST_TYPES[st["test_type"]],
+                                   alternative, float(st["alpha"])))
+        out["variant_call"] = out["significant"]
     return out

@@ -90,6 +90,12 @@ class LODAnalyzer:
         # one-sided (greater) test: a read-level "detection" is an EXCESS of alt families over the
         # blank-derived background (G-B stats.py:135-157); the two-sided G-D test also fires when a
         # cell sits significantly BELOW the U(0.5,2)-inflated expectation
+        from .. import distributed
+
+        if distributed.world_size() > 1:
+            # one process per GPU: cells sharded by family count, ONE all-gather of the per-cell counts, then
+            # the call stage over the whole grid on every rank -- same table as on one GPU
+            return distributed.run_cells_sharded(self.config, cell_id, af, depth, neg_af_max=0.0, alternative=nv.ALT_GREATER, ctx=ctx)
         return grid.run_cells(self.config, cell_id, af, depth, ctx=ctx, neg_af_max=0.0, alternative=nv.ALT_GREATER)
 
     # ------------------------------------------------------------------ LoB
@@ -140,8 +146,13 @@ class LODAnalyzer:
             for depth in depth_values:
                 hits[depth] = [float(detected[(dp == depth) & (af == a)].mean()) for a in af_values]
         lod_results = {}
+        # all depth curves are fitted (and bootstrapped) by ONE device launch; the salts are drawn in depth order,
+        # exactly as a per-depth loop of _fit_with_ci would draw them
+        ids = [(int(self.rng.integers(0, 2**31 - 1)) << 8) | (di & 0xFF) for di in range(len(depth_values))]
+        fits = nv.default_context(int(self.config.seed)).fit_lod_batch(
+            list(af_values), [hits[d] for d in depth_values], target_detection_rate, 200, ids)
         for di, depth in enumerate(depth_values):
-            lod_af, lo, hi = self._fit_with_ci(list(af_values), hits[depth], target_detection_rate, 200, stream_id=di)
+            lod_af, lo, hi = fits[di]
             lod_results[depth] = {
                 "lod_af": float(lod_af), "lod_ci_lower": float(lo), "lod_ci_upper": float(hi),
                 "af_values": [float(x) for x in af_values], "hit_rates": [float(h) for h in hits[depth]],

@@ -363,3 +363,8 @@ def test_fit_lod_matches_reference_golden(ctx, golden):
     assert np.isnan(float(g["zeros_lod"]))
     # determinism
     assert ctx.fit_lod(af, g["mid_hit"], 0.95, 50, 9) == ctx.fit_lod(af, g["mid_hit"], 0.95, 50, 9)
+    # all curves of an analysis in one launch == one launch per curve
+    names = [k[:-4] for k in g.files if k.endswith("_hit")]
+    batch = ctx.fit_lod_batch(af, [g[f"{n}_hit"] for n in names], 0.95, 60, list(range(3, 3 + len(names))))
+    for i, n in enumerate(names):
+        assert str(batch[i]) == str(ctx.fit_lod(af, g[f"{n}_hit"], 0.95, 60, 3 + i)), n
