@@ -13,6 +13,7 @@
 // The 1 + n_boot fits (point estimate + Philox-resampled pairs) run in parallel.
 #include "kernels.cuh"
 #include "rng.cuh"
+#include <stdlib.h>
 
 #define LOD_MAX_M 64
 #define LM_N 2
@@ -61,6 +62,9 @@ __host__ __device__ static double lm_enorm(int n, const double* x) {
 
 // residuals: logistic(x; a, b) - y     (lod.py:360-361 through curve_fit's wrapper)
 __host__ __device__ static void lm_fcn(const LmProblem& P, const double* p, double* f) {
+#if defined(LM_COUNT_FEV) && !defined(__CUDA_ARCH__)
+    ++g_fev;   // host development harness only
+#endif
     // (the residuals are independent: unrolled so that the fp64 exp / divide chains of several points overlap --
     // a refit is ONE thread, bound by dependent-instruction latency)
 #pragma unroll 5
@@ -120,6 +124,9 @@ __host__ __device__ static void lm_qrfac(int m, double* a, int* ipvt, double* rd
 // r: n x n, r[j*ldr + i] column-major with ldr = m (the top of fjac)
 __host__ __device__ static void lm_qrsolv(double* r, int ldr, const int* ipvt, const double* diag, const double* qtb, double* x,
                                  double* sdiag, double* wa) {
+#if defined(LM_COUNT_QRSOLV) && !defined(__CUDA_ARCH__)
+    ++g_qrsolv;   // host development harness only
+#endif
     for (int j = 0; j < LM_N; ++j) {
         for (int i = j; i < LM_N; ++i) r[j * ldr + i] = r[i * ldr + j];
         x[j] = r[j * ldr + j];
@@ -378,6 +385,255 @@ __host__ __device__ static int lm_lmdif(const LmProblem& P, double* x, int maxfe
     return info;
 }
 
+// ---------------------------------------------------------------- one fit per WARP ------------------
+// A refit is a strictly sequential iteration and the kernel lasts as long as its slowest refit -- the resamples
+// whose parameters run away until maxfev = 2000 (about 5 % of them; the others stop after ~30 evaluations).  One
+// thread per fit spends that time in ~150 dependent fp64 exp / divide chains per iteration (measured: 48 ms for
+// the five depth curves of the eval-lod grid, 75 % of its wall time).  Here a fit owns a warp and lane i owns
+// curve point i: residuals, Jacobian columns and Householder updates are one operation per lane, and every sum
+// over the points is taken by ALL lanes in the index order of the loops above (operands broadcast by shuffle),
+// so the arithmetic -- and with it every convergence / fallback decision -- is that of lm_lmdif.  The 2 x 2
+// triangular solves (lmpar, qrsolv) run redundantly on every lane, on a 2 x 2 copy of the top of the Jacobian.
+#ifdef __CUDACC__
+#define LMW_FULL 0xffffffffu
+__device__ __forceinline__ double lmw_get(double v, int lane) { return __shfl_sync(LMW_FULL, v, lane); }
+
+// enorm over points [start, start + n) of a lane-distributed vector
+__device__ static double lmw_enorm(double v, int start, int n) {
+    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+    double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
+    const double agiant = rgiant / (double)n;
+    for (int i = start; i < start + n; ++i) {
+        const double xabs = fabs(lmw_get(v, i));
+        if (xabs > rdwarf && xabs < agiant) {
+            s2 += xabs * xabs;
+        } else if (xabs <= rdwarf) {
+            if (xabs > x3max) {
+                const double t = x3max / xabs;
+                s3 = 1.0 + s3 * (t * t);
+                x3max = xabs;
+            } else if (xabs != 0.0) {
+                const double t = xabs / x3max;
+                s3 += t * t;
+            }
+        } else {
+            if (xabs > x1max) {
+                const double t = x1max / xabs;
+                s1 = 1.0 + s1 * (t * t);
+                x1max = xabs;
+            } else {
+                const double t = xabs / x1max;
+                s1 += t * t;
+            }
+        }
+    }
+    if (s1 != 0.0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0.0) {
+        if (s2 >= x3max) return sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    }
+    return x3max * sqrt(s3);
+}
+
+// sum_{i = start}^{m-1} a[i] * b[i], in index order
+__device__ __forceinline__ double lmw_dot(double a, double b, int start, int m) {
+    double sum = 0.0;
+    for (int i = start; i < m; ++i) sum += lmw_get(a, i) * lmw_get(b, i);
+    return sum;
+}
+
+__device__ __forceinline__ double lmw_fcn(double px, double py, const double* p) {
+    return 1.0 / (1.0 + exp(-(p[0] * px + p[1]))) - py;
+}
+
+// Householder QR with column pivoting of the m x 2 Jacobian held as two lane-distributed columns
+__device__ static void lmw_qrfac(int m, int lane, double& c0, double& c1, int* ipvt, double* rdiag, double* acnorm, double* wa) {
+    const double epsmch = 2.220446049250313e-16;
+    acnorm[0] = lmw_enorm(c0, 0, m);
+    acnorm[1] = lmw_enorm(c1, 0, m);
+    rdiag[0] = wa[0] = acnorm[0];
+    rdiag[1] = wa[1] = acnorm[1];
+    ipvt[0] = 0;
+    ipvt[1] = 1;
+    if (rdiag[1] > rdiag[0]) {          // n = 2: the only possible exchange
+        const double t = c0; c0 = c1; c1 = t;
+        rdiag[1] = rdiag[0];
+        wa[1] = wa[0];
+        ipvt[0] = 1;
+        ipvt[1] = 0;
+    }
+    double ajnorm = lmw_enorm(c0, 0, m);
+    if (ajnorm != 0.0) {
+        if (lmw_get(c0, 0) < 0.0) ajnorm = -ajnorm;
+        if (lane < m) c0 /= ajnorm;
+        if (lane == 0) c0 += 1.0;
+        const double sum = lmw_dot(c0, c1, 0, m);
+        const double temp = sum / lmw_get(c0, 0);
+        if (lane < m) c1 -= temp * c0;
+        if (rdiag[1] != 0.0) {
+            double t = lmw_get(c1, 0) / rdiag[1];
+            rdiag[1] *= sqrt(fmax(0.0, 1.0 - t * t));
+            t = rdiag[1] / wa[1];
+            if (0.05 * (t * t) <= epsmch) {
+                rdiag[1] = lmw_enorm(c1, 1, m - 1);
+                wa[1] = rdiag[1];
+            }
+        }
+    }
+    rdiag[0] = -ajnorm;
+    ajnorm = lmw_enorm(c1, 1, m - 1);
+    if (ajnorm != 0.0) {
+        if (lmw_get(c1, 1) < 0.0) ajnorm = -ajnorm;
+        if (lane >= 1 && lane < m) c1 /= ajnorm;
+        if (lane == 1) c1 += 1.0;
+    }
+    rdiag[1] = -ajnorm;
+}
+
+// lm_lmdif with the curve distributed over the lanes (px, py: this lane's point); m <= 32
+__device__ static int lmw_lmdif(int m, int lane, double px, double py, double* x, int maxfev) {
+    const double epsmch = 2.220446049250313e-16;
+    const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
+    double fvec, wa4v, c0, c1;                       // this lane's row of fvec, wa4 and the two Jacobian columns
+    double r[LM_N * LM_N];                           // top 2 x 2 of the factored Jacobian (column-major, ldr = 2)
+    double diag[LM_N], qtf[LM_N], wa1[LM_N], wa2[LM_N], wa3[LM_N], wa4[LM_N];
+    int ipvt[LM_N];
+    int info = 0, nfev = 0;
+    fvec = lmw_fcn(px, py, x);
+    nfev = 1;
+    double fnorm = lmw_enorm(fvec, 0, m);
+    double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
+    int iter = 1;
+    for (;;) {
+        {
+            const double eps = sqrt(epsmch);
+            for (int j = 0; j < LM_N; ++j) {
+                const double temp = x[j];
+                double h = eps * fabs(temp);
+                if (h == 0.0) h = eps;
+                x[j] = temp + h;
+                wa4v = lmw_fcn(px, py, x);
+                x[j] = temp;
+                const double d = (wa4v - fvec) / h;
+                if (j == 0) c0 = d; else c1 = d;
+            }
+            nfev += LM_N;
+        }
+        lmw_qrfac(m, lane, c0, c1, ipvt, wa1, wa2, wa3);
+        if (iter == 1) {
+            for (int j = 0; j < LM_N; ++j) {
+                diag[j] = wa2[j];
+                if (wa2[j] == 0.0) diag[j] = 1.0;
+            }
+            for (int j = 0; j < LM_N; ++j) wa3[j] = diag[j] * x[j];
+            xnorm = lm_enorm(LM_N, wa3);
+            delta = factor * xnorm;
+            if (delta == 0.0) delta = factor;
+        }
+        wa4v = fvec;
+        {   // j = 0
+            const double ajj = lmw_get(c0, 0);
+            if (ajj != 0.0) {
+                const double sum = lmw_dot(c0, wa4v, 0, m);
+                const double temp = -sum / ajj;
+                if (lane < m) wa4v += c0 * temp;
+            }
+            if (lane == 0) c0 = wa1[0];
+            qtf[0] = lmw_get(wa4v, 0);
+        }
+        {   // j = 1
+            const double ajj = lmw_get(c1, 1);
+            if (ajj != 0.0) {
+                const double sum = lmw_dot(c1, wa4v, 1, m);
+                const double temp = -sum / ajj;
+                if (lane >= 1 && lane < m) wa4v += c1 * temp;
+            }
+            if (lane == 1) c1 = wa1[1];
+            qtf[1] = lmw_get(wa4v, 1);
+        }
+        r[0] = lmw_get(c0, 0); r[1] = lmw_get(c0, 1);          // r[j * 2 + i] = column j, row i
+        r[2] = lmw_get(c1, 0); r[3] = lmw_get(c1, 1);
+        gnorm = 0.0;
+        if (fnorm != 0.0) {
+            for (int j = 0; j < LM_N; ++j) {
+                const int l = ipvt[j];
+                if (wa2[l] != 0.0) {
+                    double sum = 0.0;
+                    for (int i = 0; i <= j; ++i) sum += r[j * LM_N + i] * (qtf[i] / fnorm);
+                    gnorm = fmax(gnorm, fabs(sum / wa2[l]));
+                }
+            }
+        }
+        if (gnorm <= gtol) info = 4;
+        if (info != 0) break;
+        for (int j = 0; j < LM_N; ++j) diag[j] = fmax(diag[j], wa2[j]);
+        double ratio;
+        do {
+            // (lmpar / qrsolv only write the strict lower triangle of r, which nothing below reads)
+            lm_lmpar(r, LM_N, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wa4);
+            for (int j = 0; j < LM_N; ++j) {
+                wa1[j] = -wa1[j];
+                wa2[j] = x[j] + wa1[j];
+                wa3[j] = diag[j] * wa1[j];
+            }
+            const double pnorm = lm_enorm(LM_N, wa3);
+            if (iter == 1) delta = fmin(delta, pnorm);
+            wa4v = lmw_fcn(px, py, wa2);
+            ++nfev;
+            const double fnorm1 = lmw_enorm(wa4v, 0, m);
+            double actred = -1.0;
+            if (0.1 * fnorm1 < fnorm) {
+                const double t = fnorm1 / fnorm;
+                actred = 1.0 - t * t;
+            }
+            for (int j = 0; j < LM_N; ++j) {
+                wa3[j] = 0.0;
+                const double temp = wa1[ipvt[j]];
+                for (int i = 0; i <= j; ++i) wa3[i] += r[j * LM_N + i] * temp;
+            }
+            const double temp1 = lm_enorm(LM_N, wa3) / fnorm;
+            const double temp2 = (sqrt(par) * pnorm) / fnorm;
+            const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
+            const double dirder = -(temp1 * temp1 + temp2 * temp2);
+            ratio = 0.0;
+            if (prered != 0.0) ratio = actred / prered;
+            if (ratio <= 0.25) {
+                double temp;
+                if (actred >= 0.0) temp = 0.5;
+                else temp = 0.5 * dirder / (dirder + 0.5 * actred);
+                if (0.1 * fnorm1 >= fnorm || temp < 0.1) temp = 0.1;
+                delta = temp * fmin(delta, pnorm / 0.1);
+                par /= temp;
+            } else if (par == 0.0 || ratio >= 0.75) {
+                delta = pnorm / 0.5;
+                par *= 0.5;
+            }
+            if (ratio >= 1e-4) {
+                for (int j = 0; j < LM_N; ++j) {
+                    x[j] = wa2[j];
+                    wa2[j] = diag[j] * x[j];
+                }
+                fvec = wa4v;
+                xnorm = lm_enorm(LM_N, wa2);
+                fnorm = fnorm1;
+                ++iter;
+            }
+            if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0) info = 1;
+            if (delta <= xtol * xnorm) info = 2;
+            if (fabs(actred) <= ftol && prered <= ftol && 0.5 * ratio <= 1.0 && info == 2) info = 3;
+            if (info != 0) break;
+            if (nfev >= maxfev) info = 5;
+            if (fabs(actred) <= epsmch && prered <= epsmch && 0.5 * ratio <= 1.0) info = 6;
+            if (delta <= epsmch * xnorm) info = 7;
+            if (gnorm <= epsmch) info = 8;
+            if (info != 0) break;
+        } while (ratio < 1e-4);
+        if (info != 0) break;
+    }
+    return info;
+}
+#endif  // __CUDACC__
+
 // scipy.interpolate.interp1d(hit, af, bounds_error=False, fill_value='extrapolate')(target)
 __host__ __device__ static double lod_interp_fallback(const LmProblem& P, const double* af, double target) {
     const int m = P.m;
@@ -413,9 +669,17 @@ __host__ __device__ static double lod_fit_one(const LmProblem& P, const double* 
     return lod_interp_fallback(P, af, target);
 }
 
+// point i of resample t of a series (t = 0: the curve itself): lod.py:389-399 on a Philox stream
+__device__ __forceinline__ int lod_source(const Philox& ph, uint64_t stream_id, int t, int i, int m) {
+    if (t == 0) return i;
+    const uint4 r = ph((uint32_t)i, (uint32_t)t, (uint32_t)stream_id, (PMRD_STREAM_LODBOOT << 24) | (uint32_t)((stream_id >> 32) & 0xffffffu));
+    const int src = (int)(u53(r.x, r.y) * (double)m);
+    return src >= m ? m - 1 : src;
+}
+
 // thread 0 of a series: point estimate; threads 1..n_boot: resampled pairs (lod.py:389-399).
-// blockIdx.y = series (one detection curve per depth): all curves of an analysis are fitted by ONE launch
-// -- a fit is a latency-bound sequential LM iteration, so five launches cost five times the slowest refit.
+// blockIdx.y = series (one detection curve per depth): all curves of an analysis are fitted by ONE launch.
+// One THREAD per fit: the general form (any m <= LOD_MAX_M); curves of <= 32 points take the warp kernel below.
 __global__ void __launch_bounds__(64)
 lod_fit_kernel(uint64_t seed, const uint64_t* __restrict__ stream_ids, const double* __restrict__ af,
                const double* __restrict__ hits /*[S][m]*/, int m, double target, int n_boot, double* __restrict__ fits /*[S][1+n_boot]*/) {
@@ -428,17 +692,52 @@ lod_fit_kernel(uint64_t seed, const uint64_t* __restrict__ stream_ids, const dou
     P.m = m;
     const Philox ph(seed);
     for (int i = 0; i < m; ++i) {
-        int src = i;
-        if (t > 0) {
-            const uint4 r = ph((uint32_t)i, (uint32_t)t, (uint32_t)stream_id, (PMRD_STREAM_LODBOOT << 24) | (uint32_t)((stream_id >> 32) & 0xffffffu));
-            src = (int)(u53(r.x, r.y) * (double)m);
-            if (src >= m) src = m - 1;
-        }
+        const int src = lod_source(ph, stream_id, t, i, m);
         afs[i] = af[src];
         P.x[i] = log10(af[src]);
         P.y[i] = hit[src];
     }
     fits[(size_t)blockIdx.y * (n_boot + 1) + t] = lod_fit_one(P, afs, target);
+}
+
+// One WARP per fit, lane i = curve point i (m <= 32): see lmw_lmdif.
+#define LODW_FITS_PER_BLOCK 4
+__global__ void __launch_bounds__(32 * LODW_FITS_PER_BLOCK)
+lod_fit_warp_kernel(uint64_t seed, const uint64_t* __restrict__ stream_ids, const double* __restrict__ af,
+                    const double* __restrict__ hits /*[S][m]*/, int m, double target, int n_boot, double* __restrict__ fits /*[S][1+n_boot]*/) {
+    const int t = blockIdx.x * LODW_FITS_PER_BLOCK + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t > n_boot) return;                          // (whole warps leave together)
+    const uint64_t stream_id = stream_ids[blockIdx.y];
+    const double* __restrict__ hit = hits + (size_t)blockIdx.y * m;
+    const Philox ph(seed);
+    double a = 1.0, px = 0.0, py = 0.0;
+    if (lane < m) {
+        const int src = lod_source(ph, stream_id, t, lane, m);
+        a = af[src];
+        px = log10(a);
+        py = hit[src];
+    }
+    const bool finite_in = __all_sync(0xffffffffu, lane >= m || (isfinite(px) && isfinite(py)));
+    double p[2] = {1.0, 1.0};
+    const int info = finite_in ? lmw_lmdif(m, lane, px, py, p, 2000) : 0;
+    double lod;
+    if (info >= 1 && info <= 4) {
+        const double logit_target = log(target / (1.0 - target));          // lod.py:365-371
+        lod = pow(10.0, (logit_target - p[1]) / p[0]);
+    } else {
+        // interpolation fallback on the gathered curve (every lane runs it: the shuffles need the whole warp)
+        LmProblem P;
+        double afs[32];
+        P.m = m;
+        for (int i = 0; i < m; ++i) {
+            P.x[i] = __shfl_sync(0xffffffffu, px, i);
+            P.y[i] = __shfl_sync(0xffffffffu, py, i);
+            afs[i] = __shfl_sync(0xffffffffu, a, i);
+        }
+        lod = lod_interp_fallback(P, afs, target);
+    }
+    if (lane == 0) fits[(size_t)blockIdx.y * (n_boot + 1) + t] = lod;
 }
 
 // numpy.percentile(method='linear') incl. its lerp form; NaN in -> NaN out
@@ -491,8 +790,15 @@ int32_t k11_fit_lod_batch(pmrd_ctx* ctx, const double* d_af, const double* d_hit
     PMRD_ARG(ctx, target > 0.0 && target < 1.0, "0 < target < 1");
     DevBuf fits;
     PMRD_CUDA(ctx, fits.alloc(ctx->stream, (size_t)n_series * (size_t)(n_boot + 1) * 8));
-    PMRD_LAUNCH(ctx, lod_fit_kernel, dim3(pmrd_blocks(n_boot + 1, 64), n_series), 64, 0, ctx->seed, d_stream_ids, d_af, d_hits, (int)n,
-                target, (int)n_boot, fits.as<double>());
+    const char* e = getenv("PMRD_LOD_WARP");               // 0: one thread per fit (the general kernel) whatever n is
+    const int warp_fit = e ? atoi(e) : 1;
+    if (warp_fit && n <= 32) {
+        PMRD_LAUNCH(ctx, lod_fit_warp_kernel, dim3(pmrd_blocks(n_boot + 1, LODW_FITS_PER_BLOCK), n_series), 32 * LODW_FITS_PER_BLOCK, 0,
+                    ctx->seed, d_stream_ids, d_af, d_hits, (int)n, target, (int)n_boot, fits.as<double>());
+    } else {
+        PMRD_LAUNCH(ctx, lod_fit_kernel, dim3(pmrd_blocks(n_boot + 1, 64), n_series), 64, 0, ctx->seed, d_stream_ids, d_af, d_hits, (int)n,
+                    target, (int)n_boot, fits.as<double>());
+    }
     PMRD_LAUNCH(ctx, lod_ci_kernel, n_series, 256, (size_t)(n_boot > 0 ? n_boot : 1) * 8, (const double*)fits.as<double>(), (int)n_boot, d_out3);
     return PMRD_OK;
 }

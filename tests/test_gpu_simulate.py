@@ -347,7 +347,7 @@ def test_generator_histogram_replaces_the_first_counting_pass(ctx, native, monke
 
 
 # ------------------------------------------------------------------------------ K11 LoD fit
-def test_fit_lod_matches_reference_golden(ctx, golden):
+def test_fit_lod_matches_reference_golden(ctx, golden, monkeypatch):
     g = golden("lod_fit.npz")
     af = g["af"]
     for name in ("mid", "steep", "shallow"):
@@ -363,6 +363,21 @@ def test_fit_lod_matches_reference_golden(ctx, golden):
     assert np.isnan(float(g["zeros_lod"]))
     # determinism
     assert ctx.fit_lod(af, g["mid_hit"], 0.95, 50, 9) == ctx.fit_lod(af, g["mid_hit"], 0.95, 50, 9)
+    # one warp per fit (lane = curve point) takes the decisions of one thread per fit: the same NaN pattern and the
+    # same optimum to within lmdif's own stopping tolerance (ftol = xtol = 1.5e-8; the two kernels may contract
+    # different products into FMAs, so the iterates differ in the last bits)
+    rng = np.random.default_rng(5)
+    curves = np.clip(np.sort(rng.random((12, len(af))), axis=1) ** rng.uniform(0.5, 6.0, (12, 1)), 0, 1)
+    curves[3] = 0.0
+    curves[4, :-2] = 0.0
+    ids = list(range(40, 52))
+    monkeypatch.setenv("PMRD_LOD_WARP", "0")
+    ref = ctx.fit_lod_batch(af, curves, 0.95, 200, ids)
+    monkeypatch.setenv("PMRD_LOD_WARP", "1")
+    got = ctx.fit_lod_batch(af, curves, 0.95, 200, ids)
+    for r, g_ in zip(ref, got):
+        for a_, b_ in zip(r, g_):
+            assert (np.isnan(a_) and np.isnan(b_)) or abs(a_ - b_) <= 1e-6 * abs(a_), (r, g_)
     # all curves of an analysis in one launch == one launch per curve
     names = [k[:-4] for k in g.files if k.endswith("_hit")]
     batch = ctx.fit_lod_batch(af, [g[f"{n}_hit"] for n in names], 0.95, 60, list(range(3, 3 + len(names))))
