@@ -405,6 +405,25 @@ int32_t pmrd_plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* plan, int64_t chunk); /
 int32_t pmrd_plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* plan, int64_t chunk); /* sort + families + cell counts */
 int32_t pmrd_plan_run_call(pmrd_ctx* ctx, pmrd_plan* plan);                    /* error rate + p + BH, all cells */
 
+/* ---------------------------------------------------------------- K15: feature table */
+/* FeatureEngineer.extract_features (src/precise_mrd/advanced_stats.py:33-83): the matrix the ML /
+ * Bayesian callers train on, from the columns of the collapsed-family table.  h_out [n][6] row-major =
+ * family_size, quality_score, consensus_agreement, allele_fraction, family_size / (quality_score + 1),
+ * consensus_agreement * allele_fraction -- single IEEE operations, bit-equal to the pandas expressions. */
+int32_t pmrd_feature_table(pmrd_ctx* ctx, const int64_t* h_family_size, const double* h_quality_score,
+                           const double* h_consensus_agreement, const double* h_allele_fraction, int64_t n,
+                           double* h_out);
+
+/* ---------------------------------------------------------------- K16: QC reductions */
+/* QCAnalyzer.analyze_family_size_distribution / analyze_consensus_efficiency (src/precise_mrd/qc.py:
+ * 54-97, 185-215) over a family table: h_hist[min(size, n_bins-1)] = number of families of that size (the
+ * last bin collects every larger one), h_counts2[0] = families whose flags meet flag_mask (e.g.
+ * PMRD_FAM_HAS_CONSENSUS; h_flags may be NULL), h_counts2[1] = largest size.  Every statistic of the
+ * report (count, mean, std, percentiles, skewness, kurtosis, Counter, below / above threshold) is exact
+ * integer arithmetic on this histogram (precise_mrd/qc.py). */
+int32_t pmrd_qc_family_stats(pmrd_ctx* ctx, const uint32_t* h_family_size, const uint32_t* h_flags, uint32_t flag_mask,
+                             int64_t n, int32_t n_bins, uint64_t* h_hist, uint64_t* h_counts2);
+
 /* ---------------------------------------------------------------- K11: LoD fit ------ */
 /* LODAnalyzer._fit_detection_curve + _bootstrap_lod_ci (src/precise_mrd/eval/lod.py:
  * 351-408): 2-parameter logistic on log10(af) by Levenberg-Marquardt from (1,1), solved

@@ -22,7 +22,7 @@ Layouts produced:
                                    missing ``performance`` symbols and the two missing
                                    ``advanced_stats`` symbols
   oracle/_ref/ga/mrd/              G-A read-level package (precise-mrd-mini/src/mrd)
-  oracle/_ref/gb/precise_mrd_gb/   G-B read-level modules io/umi/context/errors/stats/filters (validation stubbed)
+  oracle/_ref/gb/precise_mrd_gb/   G-B read-level modules io/umi/context/errors/stats/filters/qc + advanced_stats/config (validation stubbed)
   oracle/_ref/stubs/               matplotlib / seaborn stand-ins (PNG writers only); statsmodels.multipletests
                                    stand-in backed by oracle/port.py
 """
@@ -96,7 +96,7 @@ def build_ga() -> None:
 def build_gb() -> None:
     src = REF / "src" / "precise_mrd"
     pkg = OUT / "gb" / "precise_mrd_gb"
-    for name in ("io", "umi", "context", "errors", "stats", "filters"):
+    for name in ("io", "umi", "context", "errors", "stats", "filters", "qc", "advanced_stats", "config"):
         _link(src / f"{name}.py", pkg / f"{name}.py")
     _write(pkg / "__init__.py", "")
     # umi.py:16 imports a validate_umi_output that exists nowhere in the tree

@@ -17,6 +17,7 @@ parity tests can run where the reference cannot travel.
   gb_reads.npz                            G-B SyntheticReadGenerator reads -> UMIProcessor(max_edit_distance=0)
   gb_stats.json                           G-B StatisticalTester (one-sided tests, CIs, BH/Bonferroni/Holm),
                                           ContextAnalyzer and ErrorModel on seeded inputs
+  gb_qc.json                              G-B QCAnalyzer report + FeatureEngineer.extract_features on seeded tables
   gb_filters.json                         G-B QualityFilter (Fisher strand bias, end-repair, depth, quality) on a seeded table
   fastq_mixed.fastq / fastq_mixed.json    a synthetic FASTQ with every header convention and parser edge
                                           case + the reference's read list / family table / validation for it
@@ -397,6 +398,75 @@ def golden_filters() -> None:
     print("  wrote gb_filters.json", m, "variants;", int(out_df.all_filters_passed.sum()), "pass;", rep["failure_reasons"])
 
 
+# ------------------------------------------------------------------------------- QC report + feature table
+def golden_qc() -> None:
+    """QCAnalyzer (src/precise_mrd/qc.py) and FeatureEngineer.extract_features (advanced_stats.py:33-83) of
+    the reference on seeded tables -> tests/golden/gb_qc.json."""
+    import json
+
+    sys.path.insert(0, str(HERE / "_ref" / "stubs"))
+    sys.path.insert(0, str(HERE / "_ref" / "gb"))
+    from precise_mrd_gb.advanced_stats import FeatureEngineer
+    from precise_mrd_gb.qc import QCAnalyzer, QCThresholds
+
+    rng = np.random.default_rng(77)
+    n_sites, fams, cons = 14, [], []
+    for s in range(n_sites):
+        key = f"chr{1 + s % 5}:{1000 + 37 * s}:{'ACGT'[s % 4]}"
+        ref = "ACGT"[s % 4]
+        nf = int(rng.integers(40, 900)) if s != 3 else 25
+        sizes = np.clip(rng.poisson(rng.choice([1.5, 5.0, 9.0]), nf), 1, None)
+        sizes[rng.random(nf) < 0.01] = int(rng.integers(101, 1500))
+        counts = {}
+        for f in range(nf):
+            has = rng.random() < (0.93 if s != 5 else 0.6)
+            al = ref if rng.random() > 0.02 else "ACGT"[(s + 1 + int(rng.integers(0, 3))) % 4]
+            fams.append({"site_key": key, "family_size": int(sizes[f]), "consensus_allele": (al if has else None)})
+            if has and sizes[f] >= 3:
+                counts[al] = counts.get(al, 0) + 1
+        for al, c in counts.items():
+            cons.append({"site_key": key, "allele": al, "ref": ref, "consensus_count": int(c)})
+    consensus = pd.DataFrame(cons)
+    qa = QCAnalyzer(QCThresholds())
+
+    def clean(o):
+        if isinstance(o, dict):
+            return {str(k): clean(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return [clean(v) for v in o]
+        if isinstance(o, (np.integer,)):
+            return int(o)
+        if isinstance(o, (np.floating,)):
+            return float(o)
+        if isinstance(o, np.bool_):
+            return bool(o)
+        return o
+
+    keys = sorted({f["site_key"] for f in fams})
+    out = {"site_keys": keys,
+           "families": {"site": [keys.index(f["site_key"]) for f in fams], "size": [f["family_size"] for f in fams],
+                        "allele": "".join(f["consensus_allele"] or "-" for f in fams)},
+           "consensus": cons,
+           "family_size": clean(qa.analyze_family_size_distribution([f["family_size"] for f in fams])),
+           "family_size_const": clean(qa.analyze_family_size_distribution([4, 4, 4])),
+           "depth": clean(qa.calculate_depth_metrics(consensus)),
+           "contamination": clean(qa.estimate_contamination_metrics(consensus)),
+           "efficiency": clean(qa.analyze_consensus_efficiency(fams)),
+           "report": clean(qa.generate_comprehensive_qc_report(consensus, fams, {"seed": 77}))}
+    # feature table of the collapsed-family frame (G-D columns)
+    m = 400
+    df = pd.DataFrame({"family_size": rng.integers(1, 40, m), "quality_score": rng.normal(28, 4, m).clip(10, 40),
+                       "consensus_agreement": rng.uniform(0.6, 1.0, m), "allele_fraction": rng.choice([0.0, 1e-4, 1e-3, 0.01, 0.05], m)})
+    X, names = FeatureEngineer(None).extract_features(df)
+    out["features"] = {"frame": {c: [float(v) if c != "family_size" else int(v) for v in df[c]] for c in df.columns},
+                       "names": list(names), "matrix_hex": [[float(v).hex() for v in row] for row in X.to_numpy()]}
+    X2, names2 = FeatureEngineer(None).extract_features(df[["family_size", "allele_fraction"]])
+    out["features_partial"] = {"names": list(names2), "shape": list(X2.shape)}
+    with open(OUT / "gb_qc.json", "w") as f:
+        json.dump(out, f)
+    print("  wrote gb_qc.json", len(fams), "families,", len(cons), "consensus rows; valid:", out["report"]["clinical_validation"]["sample_valid"])
+
+
 # ------------------------------------------------------------------------------- FASTQ ingest
 def golden_fastq() -> None:
     """A seeded synthetic FASTQ exercising every header convention and parser edge case
@@ -541,7 +611,7 @@ def main() -> int:
     only = set(sys.argv[1:])
     steps = {
         "call": lambda: (golden_call("gd_v1", "det_a", "call_smoke_v1.npz"), golden_call("gd_v2", "smoke", "call_smoke_v2.npz")),
-        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbstats": golden_gb_stats, "filters": golden_filters, "fastq": golden_fastq,
+        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbstats": golden_gb_stats, "filters": golden_filters, "qc": golden_qc, "fastq": golden_fastq,
         "lod": golden_lod_fit,
         "dist": golden_gd_dist,
     }

@@ -58,6 +58,10 @@ int32_t k11_fit_lod_batch(pmrd_ctx* ctx, const double* d_af, const double* d_hit
 int32_t call_counts_dev(pmrd_ctx* ctx, const int64_t* d_tot, const int64_t* d_var, const uint8_t* d_neg, int64_t n_cells,
                         uint64_t stream_id, int32_t test_type, int32_t alternative, double alpha, double* d_mean_rate,
                         int64_t* d_negc, double* d_p, double* d_q, uint8_t* d_sig);
+int32_t k15_gd_features(pmrd_ctx* ctx, const int64_t* d_size, const double* d_q, const double* d_agr, const double* d_af, int64_t n,
+                        double* d_out);
+int32_t k16_qc_family(pmrd_ctx* ctx, const uint32_t* d_size, const uint32_t* d_flags, uint32_t flag_mask, int64_t n, int n_bins,
+                      unsigned long long* d_hist, unsigned long long* d_counts);
 struct pmrd_plan;
 int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
                     int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, double neg_af_max,
@@ -841,6 +845,42 @@ int32_t pmrd_call_counts(pmrd_ctx* ctx, const int64_t* h_n_total, const int64_t*
     PMRD_TRY(down(ctx, h_p_adjusted, q.p, c * 8));
     PMRD_TRY(down(ctx, h_significant, sig.p, c));
     PMRD_TRY(down(ctx, h_mean_error_rate, mean.p, 8));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- K15 / K16 -------------
+int32_t pmrd_feature_table(pmrd_ctx* ctx, const int64_t* h_family_size, const double* h_quality_score,
+                           const double* h_consensus_agreement, const double* h_allele_fraction, int64_t n, double* h_out) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n >= 0, "n");
+    if (n == 0) return PMRD_OK;
+    PMRD_ARG(ctx, h_family_size && h_quality_score && h_consensus_agreement && h_allele_fraction && h_out, "null buffer");
+    DevBuf sz, q, a, f, out;
+    PMRD_TRY(up(ctx, sz, h_family_size, (size_t)n * 8));
+    PMRD_TRY(up(ctx, q, h_quality_score, (size_t)n * 8));
+    PMRD_TRY(up(ctx, a, h_consensus_agreement, (size_t)n * 8));
+    PMRD_TRY(up(ctx, f, h_allele_fraction, (size_t)n * 8));
+    PMRD_CUDA(ctx, out.alloc(ctx->stream, (size_t)n * 48));
+    PMRD_TRY(k15_gd_features(ctx, sz.as<int64_t>(), q.as<double>(), a.as<double>(), f.as<double>(), n, out.as<double>()));
+    PMRD_TRY(down(ctx, h_out, out.p, (size_t)n * 48));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
+int32_t pmrd_qc_family_stats(pmrd_ctx* ctx, const uint32_t* h_family_size, const uint32_t* h_flags, uint32_t flag_mask, int64_t n,
+                             int32_t n_bins, uint64_t* h_hist, uint64_t* h_counts2) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n >= 0 && h_hist && h_counts2 && (n == 0 || h_family_size), "arguments");
+    DevBuf sz, fl, hist, cnt;
+    PMRD_TRY(up(ctx, sz, h_family_size, (size_t)n * 4));
+    if (h_flags) PMRD_TRY(up(ctx, fl, h_flags, (size_t)n * 4));
+    PMRD_CUDA(ctx, hist.alloc(ctx->stream, (size_t)(n_bins > 0 ? n_bins : 1) * 8));
+    PMRD_CUDA(ctx, cnt.alloc(ctx->stream, 16));
+    PMRD_TRY(k16_qc_family(ctx, sz.as<uint32_t>(), h_flags ? fl.as<uint32_t>() : nullptr, flag_mask, n, n_bins,
+                           hist.as<unsigned long long>(), cnt.as<unsigned long long>()));
+    PMRD_TRY(down(ctx, h_hist, hist.p, (size_t)n_bins * 8));
+    PMRD_TRY(down(ctx, h_counts2, cnt.p, 16));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PMRD_OK;
 }

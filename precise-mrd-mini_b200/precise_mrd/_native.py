@@ -368,6 +368,28 @@ class Context:
                                               _ptr(sig), _ptr(rate)))
         return {"p_value": p, "p_adjusted": q, "significant": sig.astype(bool), "mean_error_rate": float(rate[0])}
 
+    # -- K15 / K16 -----------------------------------------------------------------------
+    def feature_table(self, family_size, quality_score, consensus_agreement, allele_fraction) -> np.ndarray:
+        """[n, 6] feature matrix of FeatureEngineer.extract_features (``pmrd_feature_table``)."""
+        sz = _arr(family_size, np.int64)
+        q, a, f = _arr(quality_score, np.float64), _arr(consensus_agreement, np.float64), _arr(allele_fraction, np.float64)
+        n = sz.shape[0]
+        if not (q.shape[0] == a.shape[0] == f.shape[0] == n):
+            raise ValueError("feature columns must have one length")
+        out = np.zeros((n, 6))
+        self._check(self.lib.pmrd_feature_table(self.h, _ptr(sz), _ptr(q), _ptr(a), _ptr(f), C.c_int64(n), _ptr(out)))
+        return out
+
+    def qc_family_stats(self, family_size, flags=None, flag_mask: int = FAM_HAS_CONSENSUS, n_bins: int = 4096):
+        """(hist[n_bins] of family sizes (last bin = larger), families meeting flag_mask, largest size)
+        (``pmrd_qc_family_stats``)."""
+        sz = np.ascontiguousarray(family_size, dtype=np.uint32)
+        fl = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint32)
+        hist, cnt = np.zeros(n_bins, np.uint64), np.zeros(2, np.uint64)
+        self._check(self.lib.pmrd_qc_family_stats(self.h, _ptr(sz), _ptr(fl), C.c_uint32(flag_mask), C.c_int64(sz.shape[0]),
+                                                  C.c_int32(n_bins), _ptr(hist), _ptr(cnt)))
+        return hist.astype(np.int64), int(cnt[0]), int(cnt[1])
+
     # -- K14 -----------------------------------------------------------------------------
     def fisher_exact(self, tables) -> Tuple[np.ndarray, np.ndarray]:
         """(odds_ratio[m], p[m]) of m 2x2 tables given as [m, 4] = c00 c01 c10 c11 (two-sided)."""

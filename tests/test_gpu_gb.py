@@ -384,3 +384,113 @@ def test_quality_filters_match_reference(ctx):
     assert set(res) == {"depth", "quality"} and qf.summarize_filters(res)["all_filters_passed"]
     assert QualityFilter(end_repair_filter=False).test_end_repair_artifact("G", "T", [1, 2, 3]).passed
     assert qf.filter_variant_dataframe(pd.DataFrame()).empty and qf.generate_filter_report(pd.DataFrame()) == {"total_variants": 0}
+
+
+# ------------------------------------------------------------------------------ QC report + feature table (K15, K16)
+def _qc_golden():
+    import json
+
+    with open(ROOT / "tests" / "golden" / "gb_qc.json") as f:
+        g = json.load(f)
+    fam = g["families"]
+    families = [{"site_key": g["site_keys"][s], "family_size": z, "consensus_allele": (None if a == "-" else a)}
+                for s, z, a in zip(fam["site"], fam["size"], fam["allele"])]
+    return g, families, pd.DataFrame(g["consensus"])
+
+
+def _same(got, want, path=""):
+    """recursive equality: ints / strings / bools exact, floats to 1e-12 relative (NaN == NaN)"""
+    if isinstance(want, dict):
+        assert set(map(str, got.keys())) == set(want.keys()), path
+        for k, v in want.items():
+            _same({str(kk): vv for kk, vv in got.items()}[k], v, f"{path}/{k}")
+    elif isinstance(want, list):
+        assert len(got) == len(want), path
+        for i, (a, b) in enumerate(zip(got, want)):
+            _same(a, b, f"{path}[{i}]")
+    elif isinstance(want, float):
+        assert (np.isnan(want) and np.isnan(got)) or abs(float(got) - want) <= 1e-12 * max(1.0, abs(want)), (path, got, want)
+    else:
+        assert got == want or (isinstance(want, int) and int(got) == want), (path, got, want)
+
+
+def test_qc_analyzer_matches_reference_report(ctx):
+    from precise_mrd.qc import QCAnalyzer, QCThresholds
+
+    g, families, consensus = _qc_golden()
+    qa = QCAnalyzer(QCThresholds())
+    _same(qa.analyze_family_size_distribution([f["family_size"] for f in families]), g["family_size"], "family_size")
+    _same(qa.analyze_family_size_distribution([4, 4, 4]), g["family_size_const"], "family_size_const")
+    _same(qa.calculate_depth_metrics(consensus), g["depth"], "depth")
+    _same(qa.estimate_contamination_metrics(consensus), g["contamination"], "contamination")
+    _same(qa.analyze_consensus_efficiency(families), g["efficiency"], "efficiency")
+    rep = qa.generate_comprehensive_qc_report(consensus, families, {"seed": 77})
+    _same(json_roundtrip(rep), g["report"], "report")
+    assert qa.analyze_family_size_distribution([]) == {"error": "No family sizes provided"}
+    assert qa.analyze_consensus_efficiency([]) == {"error": "No families data provided"}
+    # sizes beyond the device histogram are counted exactly
+    big = qa.analyze_family_size_distribution([5, 70000, 5, 4095, 4094])
+    assert big["max"] == 70000 and big["size_distribution"] == {5: 2, 70000: 1, 4095: 1, 4094: 1} and big["median"] == 4094.0
+
+
+def json_roundtrip(o):
+    import json
+
+    def conv(x):
+        if isinstance(x, dict):
+            return {str(k): conv(v) for k, v in x.items()}
+        if isinstance(x, (list, tuple)):
+            return [conv(v) for v in x]
+        if isinstance(x, np.integer):
+            return int(x)
+        if isinstance(x, np.floating):
+            return float(x)
+        if isinstance(x, np.bool_):
+            return bool(x)
+        return x
+
+    return json.loads(json.dumps(conv(o)))
+
+
+def test_qc_report_from_device_collapse_tables(ctx, native):
+    """report_from_tables (device family / group tables) == the list-of-dicts report on the same collapse."""
+    from precise_mrd.qc import QCAnalyzer
+
+    rng = np.random.default_rng(12)
+    n, n_sites = 60000, 12
+    keys = (rng.integers(0, n_sites, n, dtype=np.uint64) << np.uint64(32)) | rng.integers(0, 1500, n, dtype=np.uint64)
+    q = rng.choice([12, 25, 30, 37], n).astype(np.uint32)
+    pl = (rng.choice([0, 0, 0, 0, 0, 0, 0, 1, 2], n).astype(np.uint32)) | (q << np.uint32(2))
+    P = native.UmiParams(min_family_size=3, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6,
+                         mode=native.MODE_WEIGHTED, cluster=native.CLUSTER_EXACT, max_distance=0, umi_len=12)
+    fam, grp = ctx.collapse_reads(keys, pl, P)
+    qa = QCAnalyzer()
+    rep = qa.report_from_tables(fam, grp)
+    group = (fam["key"] >> np.uint64(32)).astype(np.int64)
+    has = (fam["flags"] & native.FAM_HAS_CONSENSUS) != 0
+    families = [{"site_key": f"site{g}", "family_size": int(s), "consensus_allele": ("ACGT"[int(c)] if h else None)}
+                for g, s, c, h in zip(group, fam["size"], fam["consensus"], has)]
+    rows = [{"site_key": f"site{int(g)}", "allele": "ACGT"[a], "ref": "A", "consensus_count": int(c)}
+            for g, cc in zip(grp["group"], grp["consensus_count"]) for a, c in enumerate(cc) if c > 0]
+    want = qa.generate_comprehensive_qc_report(pd.DataFrame(rows), families)
+    _same(json_roundtrip(rep), json_roundtrip(want), "report")
+    assert rep["overall_metrics"]["total_families"] == len(fam["size"]) and rep["site_qc_summary"]["total_sites_analyzed"] == 10
+
+
+def test_feature_table_bit_equal_to_reference(ctx):
+    from precise_mrd.advanced_stats import FeatureEngineer
+
+    g, _, _ = _qc_golden()
+    fr = g["features"]["frame"]
+    df = pd.DataFrame({"family_size": np.array(fr["family_size"], dtype=np.int64), "quality_score": fr["quality_score"],
+                       "consensus_agreement": fr["consensus_agreement"], "allele_fraction": fr["allele_fraction"]})
+    X, names = FeatureEngineer(None).extract_features(df)
+    assert names == g["features"]["names"] and list(X.columns) == names
+    want = np.array([[float.fromhex(v) for v in row] for row in g["features"]["matrix_hex"]])
+    assert X.to_numpy().tobytes() == want.tobytes()                      # bit-exact
+    X2, names2 = FeatureEngineer(None).extract_features(df[["family_size", "allele_fraction"]])
+    assert names2 == g["features_partial"]["names"] and list(X2.shape) == g["features_partial"]["shape"]
+    Xs, sel = FeatureEngineer(None).select_features(X, (df["allele_fraction"] > 0.001).to_numpy().astype(int), method="f_classif", k=3)
+    assert len(sel) == 3 and Xs.shape == (len(df), 3)
+    with pytest.raises(ValueError):
+        FeatureEngineer(None).select_features(X, np.zeros(len(df)), method="nope")
