@@ -323,7 +323,10 @@ typedef struct pmrd_read_sim_params {
     double contamination_rate;  /* io.py:100-101 */
     double hop_rate;            /* contamination.py:230-254 */
     double collision_rate;      /* contamination.py:256-278 */
-    int32_t shuffle;            /* 0: family-major order; 1: tile-shuffled */
+    int32_t shuffle;            /* 0: family-major order; 1: tile-shuffled; 2 (pmrd_simulate_reads*): the
+                                 * cell-major order of the fused plan -- cell after cell, each cell window-
+                                 * shuffled inside its own region -- so that order-sensitive results (weighted
+                                 * sums, first-seen tie-breaks) can be checked against the plan read for read */
     int32_t chunk_log2;         /* pipeline plans: cells are streamed in chunks of <= 2^chunk_log2 reads (0 = 30) */
 } pmrd_read_sim_params;
 

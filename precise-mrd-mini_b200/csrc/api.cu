@@ -727,13 +727,15 @@ int32_t pmrd_simulate_reads_dev(pmrd_ctx* ctx, const int64_t* h_cell_id, const d
     *n_reads = 0;
     if (n_cells <= 0) return PMRD_OK;
     ReadPlan plan;
-    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, 0, &plan, nullptr));
+    const int cell_major = sp && sp->shuffle == 2 && sp->hop_rate == 0.0;   // the plan's own order (see pmrd.h)
+    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, cell_major, &plan, nullptr));
     *n_reads = plan.n_reads;
     if (plan.n_reads > capacity) {
         snprintf(ctx->err, sizeof(ctx->err), "read capacity %lld < %lld reads", (long long)capacity, (long long)plan.n_reads);
         return PMRD_ERR_CAPACITY;
     }
-    PMRD_TRY(reads_plan_generate(ctx, &plan, d_keys, d_payload));
+    if (cell_major) PMRD_TRY(reads_plan_generate_cell_major(ctx, &plan, d_keys, d_payload));
+    else PMRD_TRY(reads_plan_generate(ctx, &plan, d_keys, d_payload));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the plan's scratch dies with this scope
     return PMRD_OK;
 }
@@ -746,7 +748,8 @@ int32_t pmrd_simulate_reads(pmrd_ctx* ctx, const int64_t* h_cell_id, const doubl
     *n_reads = 0;
     if (n_cells <= 0) return PMRD_OK;
     ReadPlan plan;
-    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, 0, &plan, nullptr));
+    const int cell_major = sp && sp->shuffle == 2 && sp->hop_rate == 0.0;   // the plan's own order (see pmrd.h)
+    PMRD_TRY(reads_plan_build(ctx, h_cell_id, h_af, h_n_families, n_cells, group_base, sp, cell_major, &plan, nullptr));
     *n_reads = plan.n_reads;
     if (plan.n_reads > capacity) {
         snprintf(ctx->err, sizeof(ctx->err), "read capacity %lld < %lld reads", (long long)capacity, (long long)plan.n_reads);
@@ -756,7 +759,8 @@ int32_t pmrd_simulate_reads(pmrd_ctx* ctx, const int64_t* h_cell_id, const doubl
     DevBuf k, p;
     PMRD_CUDA(ctx, k.alloc(ctx->stream, (size_t)plan.n_reads * 8));
     PMRD_CUDA(ctx, p.alloc(ctx->stream, (size_t)plan.n_reads * 4));
-    PMRD_TRY(reads_plan_generate(ctx, &plan, k.as<uint64_t>(), p.as<uint32_t>()));
+    if (cell_major) PMRD_TRY(reads_plan_generate_cell_major(ctx, &plan, k.as<uint64_t>(), p.as<uint32_t>()));
+    else PMRD_TRY(reads_plan_generate(ctx, &plan, k.as<uint64_t>(), p.as<uint32_t>()));
     PMRD_TRY(down(ctx, h_keys, k.p, (size_t)plan.n_reads * 8));
     PMRD_TRY(down(ctx, h_payload, p.p, (size_t)plan.n_reads * 4));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -335,6 +335,34 @@ struct VoteS {
         return (__ddiv_rn(bw, total) < cthr) ? -1 : best;
     }
 };
+// consensus_threshold > 0.5: the winning allele must hold a strict majority of the weight, so two alleles tied for
+// the best weight can never pass (each holds at most half) and the reference's tie-break -- the allele seen first
+// wins -- cannot change the outcome.  The walk then only accumulates: no seen mask, no first-seen order.
+struct VoteM {
+    double* acc;
+    double total = 0.0;
+    __device__ __forceinline__ explicit VoteM(double* column) : acc(column) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) acc[a * CC_THREADS] = 0.0;
+    }
+    __device__ __forceinline__ void add(uint32_t pl, const double* wt) {
+        const double w = wt[(pl >> 2) & 63u];
+        total = __dadd_rn(total, w);
+        double* p = acc + (pl & 3u) * CC_THREADS;
+        *p = __dadd_rn(*p, w);
+    }
+    __device__ __forceinline__ int result(double cthr) const {
+        if (total == 0.0) return -1;                 // every read was below the quality threshold
+        int best = 0;
+        double bw = acc[0];
+#pragma unroll
+        for (int a = 1; a < 4; ++a) {
+            const double wa = acc[a * CC_THREADS];
+            if (wa > bw) { bw = wa; best = a; }
+        }
+        return (__ddiv_rn(bw, total) < cthr) ? -1 : best;
+    }
+};
 #define CC_ITEMS (CC_TILE / CC_THREADS)
 #define CC_SKEW(i) ((i) + ((i) >> 5))
 
@@ -455,14 +483,20 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         if (FULL) {
             // the sort ordered every UMI bit: a run IS a family
             if (hv & 0x8000u) continue;                          // padding of the tile-aligned cell
-            VoteS v(s_sum);
-            for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], s_wt);
-            for (int c = n_in; c < len; ++c) v.add(pl_at(c), s_wt);
-            ++n_fam;
-            if (len >= P.min_family_size) {
-                const int best = v.result(P.consensus_threshold);
-                if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt; }
+            int best = -1;
+            if (P.consensus_threshold > 0.5) {                   // (uniform) strict majority: accumulate only
+                VoteM v(s_sum);
+                for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], s_wt);
+                for (int c = n_in; c < len; ++c) v.add(pl_at(c), s_wt);
+                if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
+            } else {
+                VoteS v(s_sum);
+                for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], s_wt);
+                for (int c = n_in; c < len; ++c) v.add(pl_at(c), s_wt);
+                if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
             }
+            ++n_fam;
+            if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt; }
             continue;
         }
         // peel families: read a opens a family iff no earlier read of the run carries its UMI.

@@ -546,6 +546,33 @@ int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uin
     return PMRD_OK;
 }
 
+// cell-major packed records (as the plan generates them) -> compact (key, payload) arrays in the SAME order:
+// cell after cell, each cell's reads in slot order, padding dropped.  One block per cell.
+__global__ void __launch_bounds__(256)
+reads_unpack_kernel(const ReadCell* __restrict__ cells, int n_cells, const uint64_t* __restrict__ rec, uint64_t* __restrict__ keys,
+                    uint32_t* __restrict__ payload) {
+    const int ci = blockIdx.x;
+    if (ci >= n_cells) return;
+    const ReadCell c = cells[ci];
+    for (uint32_t i = threadIdx.x; i < c.n_reads; i += blockDim.x) {
+        const uint64_t r = rec[c.out_start + i];
+        keys[c.read_start + i] = ((uint64_t)c.group << 32) | (uint32_t)r;
+        payload[c.read_start + i] = (uint32_t)(r >> 32);
+    }
+}
+
+// generate in the plan's cell-major layout and hand the reads back compacted, in that order (tests / inspection)
+int32_t reads_plan_generate_cell_major(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload) {
+    if (plan->n_fam <= 0 || plan->n_reads <= 0) return PMRD_OK;
+    PMRD_ARG(ctx, plan->segmented, "cell-major generation needs a segmented plan (hop_rate == 0)");
+    DevBuf rec;
+    PMRD_CUDA(ctx, rec.alloc(ctx->stream, (size_t)plan->n_out * 8));
+    PMRD_TRY(reads_plan_generate(ctx, plan, rec.as<uint64_t>(), nullptr, nullptr));
+    PMRD_LAUNCH(ctx, reads_unpack_kernel, (int)plan->n_cells, 256, 0, plan->cells.as<ReadCell>(), (int)plan->n_cells,
+                (const uint64_t*)rec.as<uint64_t>(), d_keys, d_payload);
+    return PMRD_OK;
+}
+
 // per-cell read counts into d_out[n_cells] (not part of the timed step)
 int32_t reads_plan_cell_counts(pmrd_ctx* ctx, ReadPlan* plan, int64_t* d_out) {
     if (plan->n_cells <= 0) return PMRD_OK;

@@ -44,5 +44,6 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
                          int64_t* h_read_offsets);
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan);
 int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload, uint32_t* d_tile_hist = nullptr);
+int32_t reads_plan_generate_cell_major(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload);
 int32_t reads_plan_cell_counts(pmrd_ctx* ctx, ReadPlan* plan, int64_t* d_out);
 int32_t reads_upload_tables(pmrd_ctx* ctx);

@@ -281,6 +281,30 @@ def test_pipeline_equals_oracle_on_the_same_reads(ctx, native, test_type):
     assert (res3["n_total"] == res["n_total"][sub]).all() and (res3["n_variants"] == res["n_variants"][sub]).all()
 
 
+@pytest.mark.parametrize("cthr,qthr", [(0.4, 20), (0.5, 30), (0.51, 20), (0.9, 0)])
+def test_plan_consensus_thresholds_either_side_of_one_half(ctx, native, cthr, qthr):
+    """The fused consensus kernel walks with a lighter vote when consensus_threshold > 0.5 (a tie for the best weight
+    can never pass, so the first-seen tie-break is moot) and with the full one otherwise: both against the oracle."""
+    rng = np.random.default_rng(17)
+    c = 40
+    cid = np.arange(c) * 5 + 2
+    af = np.tile([0.0, 0.3, 0.5, 0.05], c // 4)          # high AF: many mixed families, ties and near-threshold votes
+    nf = rng.integers(200, 2500, c)
+    sp, up = _sp(native, mean_family_size=2.5, family_model=1), _umi(native, consensus_threshold=cthr, quality_threshold=qthr, min_family_size=2)
+    res = ctx.pipeline_cells(cid, af, nf, sp, up)
+    # shuffle=2: the reads in the plan's own (cell-major) order -- the first-seen tie-break depends on it
+    keys, pl = ctx.simulate_reads(cid, af, nf, _sp(native, mean_family_size=2.5, family_model=1, shuffle=2))
+    k1, p1 = ctx.simulate_reads(cid, af, nf, sp)
+    assert (np.sort(keys) == np.sort(k1)).all() and np.sort(pl).tobytes() == np.sort(p1).tobytes()   # the same reads, reordered
+    fam, grp = port.collapse_exact(keys, pl, 0, 2, 1000, qthr, cthr)
+    alt = ((cid & 3) + 1 + ((cid >> 2) % 3)) & 3
+    n_total, n_var = np.zeros(c, np.int64), np.zeros(c, np.int64)
+    n_total[grp["group"]] = grp["consensus_count"].sum(1)
+    n_var[grp["group"]] = grp["consensus_count"][np.arange(len(grp["group"])), alt[grp["group"]]]
+    assert (res["n_total"] == n_total).all() and (res["n_variants"] == n_var).all()
+    assert n_total.sum() > 0 and (n_total < res["n_families"]).any()          # some families did fail the vote
+
+
 def test_plan_stage_entry_points_compose(ctx, native):
     cid = np.arange(32)
     af = np.tile([0.0, 0.02], 16)
