@@ -27,6 +27,16 @@ __device__ __forceinline__ uint32_t rs_peer_mask(uint32_t d, uint32_t m) {
     return m;
 }
 
+// zero `words` (a multiple of 4 * THREADS) 32-bit shared-memory counters with 16-byte stores, fully unrolled
+// (the scalar loop was 9 % of the direct downsweep's instructions)
+template <int THREADS, int WORDS>
+__device__ __forceinline__ void rs_zero_smem(uint32_t* p) {
+    static_assert(WORDS % (4 * THREADS) == 0, "whole 16-byte stores per thread");
+    uint4* q = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < WORDS / (4 * THREADS); ++i) q[i * THREADS + threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // ---------------------------------------------------------------- varying bits ----------
 __global__ void __launch_bounds__(256) rs_varying_kernel(const uint64_t* __restrict__ keys, int64_t n,
                                                          unsigned long long* __restrict__ or_and /*[2]*/) {
@@ -93,9 +103,9 @@ RadixPlan radix_make_plan(uint64_t varying) {
 // hist[tile][256] (tile-major: one coalesced 1 KB row per tile)
 __global__ void __launch_bounds__(RS_THREADS)
 rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ hist, int shift, uint32_t mask) {
-    __shared__ uint32_t s_hist[RS_WARPS][RS_MAX_BINS];
+    __shared__ __align__(16) uint32_t s_hist[RS_WARPS][RS_MAX_BINS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
+    rs_zero_smem<RS_THREADS, RS_WARPS * RS_MAX_BINS>(&s_hist[0][0]);
     __syncthreads();
     const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
     const int64_t rem = n - tile_base;
@@ -196,7 +206,7 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
     RsSmem& S = *reinterpret_cast<RsSmem*>(rs_smem_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = lanemask_lt();
-    for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&S.warp_cnt[0][0])[i] = 0;
+    rs_zero_smem<RS_THREADS, RS_WARPS * RS_MAX_BINS>(&S.warp_cnt[0][0]);
     const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
     const int64_t rem = n - tile_base;
     const int tile_n = rem < RS_TILE ? (int)rem : RS_TILE;
@@ -294,10 +304,10 @@ rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
                            const uint32_t* __restrict__ hist_scanned, int shift, uint32_t mask) {
     static_assert(THREADS * ITEMS == RS_TILE, "one 4096-record tile per block");
     constexpr int WARPS = THREADS / 32;
-    __shared__ uint32_t s_cnt[WARPS][RS_MAX_BINS];
+    __shared__ __align__(16) uint32_t s_cnt[WARPS][RS_MAX_BINS];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = lanemask_lt();
-    for (int i = threadIdx.x; i < WARPS * RS_MAX_BINS; i += THREADS) (&s_cnt[0][0])[i] = 0;
+    rs_zero_smem<THREADS, WARPS * RS_MAX_BINS>(&s_cnt[0][0]);
     const uint64_t* __restrict__ src = keys_in + (int64_t)blockIdx.x * RS_TILE + warp * (RS_TILE / WARPS) + lane;
     uint64_t key[ITEMS];
 #pragma unroll
@@ -344,28 +354,32 @@ rs_downsweep_direct_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
 // first pass over generator output a direct warp store touches 30.5 distinct 32-byte sectors
 // (the kernel is bound by that L1->L2 sector rate), here ~10; on later passes the first pass has
 // already clustered each family's reads and the direct kernel is the faster one.
+template <int WARPS>
 struct RsStage {
-    uint32_t cnt[RS_WARPS][RS_MAX_BINS];
+    uint32_t cnt[WARPS][RS_MAX_BINS];
     uint64_t rec[RS_TILE];
     uint32_t delta[RS_MAX_BINS];
     uint32_t sw[33];
 };
-__global__ void __launch_bounds__(RS_THREADS, RS_DIRECT_MIN_BLOCKS)
+template <int THREADS, int ITEMS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS)
 rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
                            const uint32_t* __restrict__ hist_scanned, int shift, uint32_t mask) {
+    static_assert(THREADS * ITEMS == RS_TILE && THREADS >= RS_MAX_BINS, "one 4096-record tile per block");
+    constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char rs_stage_raw[];
-    RsStage& S = *reinterpret_cast<RsStage*>(rs_stage_raw);
+    RsStage<WARPS>& S = *reinterpret_cast<RsStage<WARPS>*>(rs_stage_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = lanemask_lt();
-    for (int i = threadIdx.x; i < RS_WARPS * RS_MAX_BINS; i += RS_THREADS) (&S.cnt[0][0])[i] = 0;
-    const uint64_t* __restrict__ src = keys_in + (int64_t)blockIdx.x * RS_TILE + warp * (RS_TILE / RS_WARPS) + lane;
-    uint64_t key[RS_ITEMS];
+    rs_zero_smem<THREADS, WARPS * RS_MAX_BINS>(&S.cnt[0][0]);
+    const uint64_t* __restrict__ src = keys_in + (int64_t)blockIdx.x * RS_TILE + warp * (RS_TILE / WARPS) + lane;
+    uint64_t key[ITEMS];
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) key[i] = src[i * 32];
+    for (int i = 0; i < ITEMS; ++i) key[i] = src[i * 32];
     __syncthreads();
-    uint32_t rank2[RS_ITEMS / 2];
+    uint32_t rank2[ITEMS / 2];
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
         const uint32_t m = rs_peer_mask(d, 0xffffffffu);
         const uint32_t before = __popc(m & lt);
@@ -384,14 +398,14 @@ rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
         uint32_t tot = 0;
         if (threadIdx.x < RS_MAX_BINS) {
 #pragma unroll
-            for (int w = 0; w < RS_WARPS; ++w) tot += S.cnt[w][threadIdx.x];
+            for (int w = 0; w < WARPS; ++w) tot += S.cnt[w][threadIdx.x];
         }
         uint32_t all;
         uint32_t run = block_exclusive_scan<uint32_t>(tot, S.sw, all);
         if (threadIdx.x < RS_MAX_BINS) {
             S.delta[threadIdx.x] = hist_scanned[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] - run;   // tile position -> global position
 #pragma unroll
-            for (int w = 0; w < RS_WARPS; ++w) {
+            for (int w = 0; w < WARPS; ++w) {
                 const uint32_t c = S.cnt[w][threadIdx.x];
                 S.cnt[w][threadIdx.x] = run;
                 run += c;
@@ -400,7 +414,7 @@ rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
+    for (int i = 0; i < ITEMS; ++i) {
         const uint32_t d = (uint32_t)(key[i] >> shift) & mask;
         const uint32_t r = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
         S.rec[S.cnt[warp][d] + r] = key[i];
@@ -408,8 +422,8 @@ rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
     __syncthreads();
     uint64_t* __restrict__ dst = keys_out;
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) {
-        const uint32_t j = i * RS_THREADS + threadIdx.x;
+    for (int i = 0; i < ITEMS; ++i) {
+        const uint32_t j = i * THREADS + threadIdx.x;
         const uint64_t k = S.rec[j];
         dst[j + S.delta[(uint32_t)(k >> shift) & mask]] = k;
     }
@@ -453,7 +467,8 @@ static int32_t rs_set_attrs(pmrd_ctx* ctx) {
     if (!attr_set) {
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<RS_WARPS>)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<256, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<8>)));
         attr_set = true;
     }
     return PMRD_OK;
@@ -497,13 +512,14 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);
         } else if (stage) {
-            PMRD_LAUNCH(ctx, rs_downsweep_staged_kernel, n_tiles, RS_THREADS, sizeof(RsStage), kin, kout, hist, shift, mask);
+            static int swide = -1;
+            if (swide < 0) { const char* e = getenv("PMRD_RS_SWIDE"); swide = e ? atoi(e) : 1; }   // 1: 256 threads x 16 records, 4 blocks / SM (8.1 vs 9.2 ms per step)
+            if (swide) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_staged_kernel", (rs_downsweep_staged_kernel<256, 16, 4>), n_tiles, 256, sizeof(RsStage<8>), kin, kout, hist, shift, mask);
+            else PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_staged_kernel", (rs_downsweep_staged_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>), n_tiles, RS_THREADS, sizeof(RsStage<RS_WARPS>), kin, kout, hist, shift, mask);
         } else if (direct) {   // packed 8-byte records, stored straight to their final place (L2 merges the sectors)
             static int wide = -1;
             if (wide < 0) { const char* e = getenv("PMRD_RS_WIDE"); wide = e ? atoi(e) : 2; }   // 2: 256 threads x 16 records, 4 blocks / SM (measured best, by 3 %)
-            if (wide == 1) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<1024, 4, 2>), n_tiles, 1024, 0, kin, kout, hist, shift, mask);
-            else if (wide == 2) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<256, 16, 4>), n_tiles, 256, 0, kin, kout, hist, shift, mask);
-            else if (wide == 3) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<256, 16, 3>), n_tiles, 256, 0, kin, kout, hist, shift, mask);
+            if (wide == 2) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<256, 16, 4>), n_tiles, 256, 0, kin, kout, hist, shift, mask);
             else PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>), n_tiles, RS_THREADS, 0, kin, kout, hist, shift, mask);
         } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);
