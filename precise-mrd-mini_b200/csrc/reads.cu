@@ -43,7 +43,7 @@ struct FamDraw {
 
 // s_cdf: Poisson cdf table in shared memory (128 floats, padded with 2.0f) or nullptr
 __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell& c, uint32_t fam, const pmrd_read_sim_params& sp,
-                                               const float* s_cdf) {
+                                               const float* s_cdf, const uint8_t* s_lut = nullptr) {
     const uint32_t c2 = (uint32_t)c.cell_id, c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((c.cell_id >> 32) & 0xffffffu);
     const uint4 b = ph(0xffffffffu, fam, c2, c3);
     FamDraw d;
@@ -52,8 +52,15 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
         // built on the host (the sizes only steer a simulation): size = #{k : F[k] < u}
         const float uf = u24(b.x);
         int k = 0;
+        if (s_lut) {
+            // 4096-bucket inverse of the table: the count for the bucket's smallest uniform, then a walk that almost
+            // never takes a step (a bucket holds a cdf step with probability ~10 / 4096)
+            k = s_lut[b.x >> 20];
+            while (s_cdf[k] < uf) ++k;
+        } else {
 #pragma unroll
-        for (int step = 64; step > 0; step >>= 1) k += (s_cdf[k + step - 1] < uf) ? step : 0;
+            for (int step = 64; step > 0; step >>= 1) k += (s_cdf[k + step - 1] < uf) ? step : 0;
+        }
         d.size = k < 1 ? 1 : k;
     } else {
         const double u = u53(b.x, b.y);
@@ -91,17 +98,21 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
 __global__ void __launch_bounds__(256)
 reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                   int64_t n_fam, pmrd_read_sim_params sp, const float* __restrict__ size_cdf /* [128] or NULL */,
-                  const int32_t* __restrict__ blk_cell, uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word,
-                  uint32_t* __restrict__ fam_key) {
+                  const uint8_t* __restrict__ size_lut /* [4096] or NULL */, const int32_t* __restrict__ blk_cell,
+                  uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word, uint32_t* __restrict__ fam_key) {
     __shared__ float s_cdf[128];
+    __shared__ __align__(16) uint8_t s_lut[4096];
+    static_assert(READS_FAM_BLOCK * 16 == 4096, "one 16-byte LUT slice per thread");
     const int64_t f = (int64_t)blockIdx.x * READS_FAM_BLOCK + threadIdx.x;
     if (size_cdf && threadIdx.x < 128) s_cdf[threadIdx.x] = size_cdf[threadIdx.x];
+    if (size_cdf && size_lut) reinterpret_cast<uint4*>(s_lut)[threadIdx.x] = reinterpret_cast<const uint4*>(size_lut)[threadIdx.x];
     __syncthreads();
     if (f >= n_fam) return;
     const Philox ph(seed);
     const int ci = find_cell_in(fam_offsets, blk_cell[blockIdx.x], blk_cell[blockIdx.x + 1] + 1, f);
     const ReadCell c = cells[ci];
-    const FamDraw d = draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp, size_cdf ? s_cdf : nullptr);
+    const FamDraw d = draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp, size_cdf ? s_cdf : nullptr,
+                                  (size_cdf && size_lut) ? s_lut : nullptr);
     fam_size[f] = (uint32_t)d.size;
     fam_word[f] = d.umi | ((d.has_variant ? 1u : 0u) << 24);   // the generator re-reads this instead of re-drawing
     fam_key[f] = d.key;
@@ -449,6 +460,16 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         }
         if (e == cudaSuccess) e = plan->size_cdf.alloc(ctx->stream, sizeof(h_cdf));
         if (e == cudaSuccess) e = cudaMemcpyAsync(plan->size_cdf.p, h_cdf, sizeof(h_cdf), cudaMemcpyHostToDevice, ctx->stream);
+        // inverse table: lut[b] = #{k : F[k] < u} for the smallest uniform of bucket b (u24 of the words b << 20 ..)
+        static uint8_t h_lut[4096];
+        for (uint32_t b = 0; b < 4096u; ++b) {
+            const float u = u24(b << 20);
+            int k = 0;
+            while (k < 127 && h_cdf[k] < u) ++k;
+            h_lut[b] = (uint8_t)k;
+        }
+        if (e == cudaSuccess) e = plan->size_lut.alloc(ctx->stream, sizeof(h_lut));
+        if (e == cudaSuccess) e = cudaMemcpyAsync(plan->size_lut.p, h_lut, sizeof(h_lut), cudaMemcpyHostToDevice, ctx->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     free(h_blk);
@@ -521,6 +542,7 @@ int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
     PMRD_LAUNCH(ctx, reads_size_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
                 plan->has_size_cdf ? (const float*)plan->size_cdf.as<float>() : (const float*)nullptr,
+                plan->has_size_cdf ? (const uint8_t*)plan->size_lut.as<uint8_t>() : (const uint8_t*)nullptr,
                 (const int32_t*)plan->blk_cell.as<int32_t>(), plan->fam_size.as<uint32_t>(), plan->fam_word.as<uint32_t>(),
                 plan->fam_key.as<uint32_t>());
     return exclusive_scan<uint32_t, uint64_t>(ctx, plan->fam_size.as<uint32_t>(), plan->read_offset.as<uint64_t>(), plan->n_fam,

@@ -20,7 +20,7 @@ struct ReadCell {
 #define READS_IS_PAD_UMI(u) (((u) >> 24) == 0xffu)
 
 struct ReadPlan {
-    DevBuf cells, fam_offsets, fam_size, fam_word, fam_key, read_offset, total, cell_tile_start, size_cdf, blk_cell, tile_cell;
+    DevBuf cells, fam_offsets, fam_size, fam_word, fam_key, read_offset, total, cell_tile_start, size_cdf, size_lut, blk_cell, tile_cell;
     bool has_size_cdf = false;  // Poisson sizes with mean <= 16: inverted against an fp32 cdf table
     pmrd_read_sim_params sp;
     int64_t n_cells = 0;
