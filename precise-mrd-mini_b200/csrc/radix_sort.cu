@@ -433,31 +433,50 @@ rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
 // Cell-major input (each cell = whole tiles [t0, t1)): every cell is an independent sort, so
 // the scan restarts at each cell -- one block per cell, thread d owns digit d.
 //   base(d, t) = t0 * RS_TILE + sum_{d' < d} sum_{t' in cell} H[t'][d'] + sum_{t0 <= t' < t} H[t'][d]
-__global__ void __launch_bounds__(256)
+#define RS_SCAN_PARTS 4   /* a cell's tiles are cut into this many contiguous ranges, walked side by side */
+__global__ void __launch_bounds__(256 * RS_SCAN_PARTS)
 rs_cellscan_kernel(uint32_t* __restrict__ hist, const int64_t* __restrict__ cell_tile_start, int n_cells) {
     __shared__ uint32_t sw[33];
+    __shared__ uint32_t s_part[RS_SCAN_PARTS][256];
     const int c = blockIdx.x;
     if (c >= n_cells) return;
+    const uint32_t d = threadIdx.x & 255u, part = threadIdx.x >> 8;
     const int64_t t0 = cell_tile_start[c], t1 = cell_tile_start[c + 1];
+    const int64_t per = (t1 - t0 + RS_SCAN_PARTS - 1) / RS_SCAN_PARTS;
+    const int64_t p0 = min(t0 + (int64_t)part * per, t1), p1 = min(p0 + per, t1);
+    // the serial walk over a cell's (up to ~60) tiles is pure load latency: four ranges in flight cut it fourfold
     uint32_t acc = 0;
 #pragma unroll 4
-    for (int64_t t = t0; t < t1; ++t) acc += hist[t * 256 + threadIdx.x];
+    for (int64_t t = p0; t < p1; ++t) acc += hist[t * 256 + d];
+    s_part[part][d] = acc;
+    __syncthreads();
+    uint32_t tot_d = 0, before = 0;
+#pragma unroll
+    for (int p = 0; p < RS_SCAN_PARTS; ++p) {
+        const uint32_t v = s_part[p][d];
+        before += p < (int)part ? v : 0u;
+        tot_d += v;
+    }
     uint32_t tot;
-    uint32_t run = (uint32_t)(t0 * RS_TILE) + block_exclusive_scan<uint32_t>(acc, sw, tot);
-    int64_t t = t0;
-    for (; t + 4 <= t1; t += 4) {
+    // exclusive scan over the digits of the cell's totals (the first 256 threads carry them, the others add zero)
+    const uint32_t ex = block_exclusive_scan<uint32_t>(part == 0 ? tot_d : 0u, sw, tot);
+    if (part == 0) s_part[0][d] = ex;
+    __syncthreads();
+    uint32_t run = (uint32_t)(t0 * RS_TILE) + s_part[0][d] + before;
+    int64_t t = p0;
+    for (; t + 4 <= p1; t += 4) {
         uint32_t v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = hist[(t + j) * 256 + threadIdx.x];
+        for (int j = 0; j < 4; ++j) v[j] = hist[(t + j) * 256 + d];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            hist[(t + j) * 256 + threadIdx.x] = run;
+            hist[(t + j) * 256 + d] = run;
             run += v[j];
         }
     }
-    for (; t < t1; ++t) {
-        const uint32_t v = hist[t * 256 + threadIdx.x];
-        hist[t * 256 + threadIdx.x] = run;
+    for (; t < p1; ++t) {
+        const uint32_t v = hist[t * 256 + d];
+        hist[t * 256 + d] = run;
         run += v;
     }
 }
@@ -508,7 +527,7 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         // bit p of `staged`: pass p goes through the shared-memory staged scatter (default: the first pass only)
         const bool stage = !vals_a && direct && ((staged >> p) & 1);
         if (!(p == 0 && d_hist0)) PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist, shift, mask);
-        PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256, 0, hist, d_cell_tile_start, (int)n_cells);
+        PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256 * RS_SCAN_PARTS, 0, hist, d_cell_tile_start, (int)n_cells);
         if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);
         } else if (stage) {
