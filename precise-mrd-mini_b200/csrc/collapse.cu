@@ -414,7 +414,7 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     const int cell = s_cell;
     const int64_t cell_lo = cell_tile_start[cell] * CC_TILE, cell_hi = cell_tile_start[cell + 1] * CC_TILE;
     // heads, blocked so that the compacted list follows memory order
-    uint32_t flags = 0, cnt = 0;
+    uint32_t flags = 0;
     const int i0 = threadIdx.x * CC_ITEMS;
 #pragma unroll
     for (int j = 0; j < CC_ITEMS; ++j) {
@@ -422,17 +422,18 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         bool head;
         if (i > 0) head = ((s_umi[CC_SKEW(i)] ^ s_umi[CC_SKEW(i - 1)]) & run_mask) != 0u;
         else head = base == cell_lo || ((((uint32_t)rec[base - 1]) ^ s_umi[0]) & run_mask) != 0u;
-        if (head) { flags |= 1u << j; ++cnt; }
+        flags |= (head ? 1u : 0u) << j;
     }
     uint32_t n_heads;
-    uint32_t r = block_exclusive_scan<uint32_t>(cnt, sw, n_heads);
-#pragma unroll
-    for (int j = 0; j < CC_ITEMS; ++j)
-        if (flags & (1u << j)) {
-            // FULL: bit 15 marks a run of padding reads (s_umi is recycled below)
-            const uint32_t pad = (FULL && (s_umi[CC_SKEW(i0 + j)] >> 24) == 0xffu) ? 0x8000u : 0u;
-            s_head[r++] = (uint16_t)((uint32_t)(i0 + j) | pad);
-        }
+    uint32_t r = block_exclusive_scan<uint32_t>((uint32_t)__popc(flags), sw, n_heads);
+    // compaction: walk the set bits only (a thread owns ~3 heads of its 16 records)
+    while (flags) {
+        const int j = __ffs((int)flags) - 1;
+        flags &= flags - 1u;
+        // FULL: bit 15 marks a run of padding reads (s_umi is recycled below)
+        const uint32_t pad = (FULL && (s_umi[CC_SKEW(i0 + j)] >> 24) == 0xffu) ? 0x8000u : 0u;
+        s_head[r++] = (uint16_t)((uint32_t)(i0 + j) | pad);
+    }
     __syncthreads();
     // FULL: the UMI halves are not needed past this point; their 16 KB now hold the votes' allele sums
     double* const s_sum = reinterpret_cast<double*>(s_umi) + threadIdx.x;          // 8 KB: [4 alleles][CC_THREADS]
