@@ -152,7 +152,7 @@ int32_t reads_upload_tables(pmrd_ctx* ctx) {
 // fp32 when the window permutation applies (n_full <= 2^16, so 97 w + 13 < 2^24 is exact in fp32
 // and the quotient estimate is off by at most one), else 0.
 #define SHUF_MUL 97u
-__device__ __forceinline__ float shuffle_inv(uint32_t n) {
+__host__ __device__ __forceinline__ float shuffle_inv(uint32_t n) {
     const uint32_t n_full = n / SHUF_WINDOW;
     return (n_full > 1u && n_full <= 65536u && n_full % SHUF_MUL != 0u) ? 1.0f / (float)n_full : 0.0f;
 }
@@ -239,16 +239,18 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         S.word = fw | (c.ref_allele << 26) | (c.alt_allele << 28);
         S.group = c.group;
         S.ci = ci;
+        float inv_full;
         if (segmented) {
             S.cell_off = (uint32_t)(off - c.read_start);
             S.cell_n = c.n_reads;
-            S.tile0 = (uint32_t)(c.out_start / SHUF_WINDOW);
+            S.tile0 = c.tile0;
+            inv_full = c.inv_full;                   // (per cell: worked out on the host with the plan)
         } else {
             S.cell_off = (uint32_t)off;
             S.cell_n = (uint32_t)n_reads;
             S.tile0 = 0u;
+            inv_full = shuffle_inv(S.cell_n);
         }
-        const float inv_full = shuffle_inv(S.cell_n);
         const uint32_t w0 = S.cell_off / SHUF_WINDOW;
         S.tile_a = window_tile(w0, S.cell_n, inv_full, sp.shuffle, S.tile0);
         S.tile_b = window_tile(w0 + 1u, S.cell_n, inv_full, sp.shuffle, S.tile0);
@@ -406,6 +408,8 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         hc[i].read_start = 0;
         hc[i].out_start = 0;
         hc[i].n_reads = 0;
+        hc[i].inv_full = 0.0f;
+        hc[i].tile0 = 0;
         {
             // words w of the has_variant uniform that settle u53(w, .) < af on their own:
             // w < af_lt: true whatever the low word; w >= af_ge: false whatever the low word
@@ -510,6 +514,8 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
             plan->n_groups_with_reads += h_cnt[i] > 0;
             h_tile[i] = tile;
             hc[i].out_start = plan->segmented ? tile * READS_SEG_TILE : rs;
+            hc[i].tile0 = (uint32_t)tile;
+            hc[i].inv_full = shuffle_inv((uint32_t)h_cnt[i]);
             if (h_read_offsets) h_read_offsets[i] = rs;
             rs += h_cnt[i];
             tile += (h_cnt[i] + READS_SEG_TILE - 1) / READS_SEG_TILE;

@@ -12,6 +12,8 @@ struct ReadCell {
     uint32_t group;
     uint32_t ref_allele, alt_allele;
     int64_t af_lt, af_ge;  // has_variant threshold words (see draw_family)
+    float inv_full;        // segmented layout: 1 / (complete 4096-read windows) when the window permutation applies, else 0
+    uint32_t tile0;        // segmented layout: out_start / 4096
 };
 
 #define READS_SEG_TILE 4096 /* == RS_TILE: cells are padded to whole sort tiles when segmented */
