@@ -116,6 +116,7 @@ struct pmrd_plan {
     int64_t max_reads = 0, max_fcap = 0, max_cells = 0;
     int sort_bits = 24;   // UMI bits ordered by the radix sort; the consensus kernel resolves the rest (16: 2 passes, 24: 3)
     uint64_t stream_id = 0;
+    uint64_t seed = 0;    // the context seed the layout was sized for (read counts are a function of it)
     DevBuf keys, keys_tmp, pl, pl_tmp;
     DevBuf tile_hist;     // [max tiles][256]: first-pass digit histogram the generator counts as a by-product (cell-major path)
     bool gen_hist = true;
@@ -156,6 +157,7 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     P->up = *up; P->neg_af_max = neg_af_max; P->alpha = alpha; P->test_type = test_type; P->alternative = alternative;
     P->n_cells = n_cells;
     P->stream_id = (uint64_t)h_cell_id[0];
+    P->seed = ctx->seed;
     if (const char* sb = getenv("PMRD_SORT_BITS")) {   // tuning knob: 16 (2 radix passes) or 24 (3 passes)
         const int v = atoi(sb);
         if (v == 8 || v == 16 || v == 24) P->sort_bits = v;
@@ -326,7 +328,11 @@ int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
 // Stage entry points for per-stage timing.  With more than one chunk the read buffers are
 // reused, so simulate / collapse of different chunks cannot be separated: these run the
 // stage for chunk `which` only (bench.py times chunk 0), plan_run() is the real step.
+// the cell layout (reads per cell, tiles, buffer sizes) is a function of the seed the plan was built with
+#define PLAN_SEED_GUARD(ctx, P) PMRD_ARG(ctx, (ctx)->seed == (P)->seed, "the plan was built for another seed: create a new plan after pmrd_set_seed")
+
 int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P, int64_t which) {
+    PLAN_SEED_GUARD(ctx, P);
     PMRD_ARG(ctx, which >= 0 && which < (int64_t)P->chunks.size(), "chunk index");
     return chunk_simulate(ctx, P, P->chunks[(size_t)which]);
 }
@@ -339,6 +345,7 @@ int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P, int64_t which) {
 }
 
 int32_t plan_run(pmrd_ctx* ctx, pmrd_plan* P) {
+    PLAN_SEED_GUARD(ctx, P);
     PMRD_TRY(plan_reset_outputs(ctx, P));
     for (PlanChunk* ch : P->chunks) {
         PMRD_TRY(chunk_simulate(ctx, P, ch));

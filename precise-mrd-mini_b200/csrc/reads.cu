@@ -137,9 +137,13 @@ int32_t reads_upload_tables(pmrd_ctx* ctx) {
         h[k] = k < 30 ? (uint32_t)llround(cdf * 16777216.0) : 0xffffffffu;
     }
     for (uint32_t b = 0; b < (1u << QUAL_LUT_BITS); ++b) {
-        int cnt = 0;
-        for (int k = 0; k < 30; ++k) cnt += h[k] <= (b << (24 - QUAL_LUT_BITS));
-        lut[b] = (uint8_t)cnt;
+        int cnt = 0, cnt_end = 0;
+        for (int k = 0; k < 30; ++k) {
+            cnt += h[k] <= (b << (24 - QUAL_LUT_BITS));
+            cnt_end += h[k] <= (((b + 1u) << (24 - QUAL_LUT_BITS)) - 1u);
+        }
+        // bit 7: a threshold lies inside the bucket, the count has to be finished by a walk (30 of 4096 buckets)
+        lut[b] = (uint8_t)(cnt | (cnt_end != cnt ? 0x80 : 0));
     }
     PMRD_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qual_thr, h, sizeof(h), 0, cudaMemcpyHostToDevice, ctx->stream));
     PMRD_CUDA(ctx, cudaMemcpyToSymbolAsync(c_qual_lut, lut, sizeof(lut), 0, cudaMemcpyHostToDevice, ctx->stream));
@@ -315,7 +319,10 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
         // (4096-bucket table, then a walk that almost never takes a step; T[30] = T[31] = 2^32 - 1 stops it)
         const uint32_t uq = ra >> 8;
         uint32_t qi = s_qlut[uq >> (24 - QUAL_LUT_BITS)];
-        while (uq >= s_qthr[qi]) ++qi;
+        if (qi & 0x80u) {                                    // (rare) the bucket holds a cdf step
+            qi &= 0x7fu;
+            while (uq >= s_qthr[qi]) ++qi;
+        }
         const int q = 10 + (int)qi;
         const uint32_t strand = ra & 1u;
         const uint32_t rpos = 10u + (((rb >> 16) * 140u) >> 16);     // io.py:119 randint(10, 150)

@@ -305,6 +305,36 @@ def test_plan_consensus_thresholds_either_side_of_one_half(ctx, native, cthr, qt
     assert n_total.sum() > 0 and (n_total < res["n_families"]).any()          # some families did fail the vote
 
 
+def test_families_longer_than_a_shuffle_window(ctx, native, monkeypatch):
+    """Families of thousands of reads span three and more 4096-read windows: the generator's per-window destination
+    tiles (two precomputed, the rest worked out per read) and its by-product histogram must still describe the very
+    layout the sort and the consensus walk."""
+    rng = np.random.default_rng(4)
+    c = 24
+    cid = np.arange(c) + 90
+    af = np.tile([0.0, 0.2, 0.01], c // 3)
+    nf = rng.integers(3, 40, c)
+    sp = _sp(native, family_model=0, mean_family_size=3000.0, max_family_size=30000)
+    up = _umi(native, max_family_size=100000)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PMRD_GEN_HIST", flag)
+        out[flag] = ctx.pipeline_cells(cid, af, nf, sp, up)
+    for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value"):
+        assert (out["0"][k_] == out["1"][k_]).all(), k_
+    res = out["1"]
+    keys, pl = ctx.simulate_reads(cid, af, nf, _sp(native, family_model=0, mean_family_size=3000.0, max_family_size=30000, shuffle=2))
+    assert len(keys) == res["n_reads"].sum()
+    sizes = np.unique(keys, return_counts=True)[1]
+    assert sizes.max() > 3 * 4096                                  # the case is really exercised
+    fam, grp = port.collapse_exact(keys, pl, 0, 3, 100000, 20, 0.6)
+    alt = ((cid & 3) + 1 + ((cid >> 2) % 3)) & 3
+    n_total, n_var = np.zeros(c, np.int64), np.zeros(c, np.int64)
+    n_total[grp["group"]] = grp["consensus_count"].sum(1)
+    n_var[grp["group"]] = grp["consensus_count"][np.arange(len(grp["group"])), alt[grp["group"]]]
+    assert (res["n_total"] == n_total).all() and (res["n_variants"] == n_var).all()
+
+
 def test_plan_stage_entry_points_compose(ctx, native):
     cid = np.arange(32)
     af = np.tile([0.0, 0.02], 16)
@@ -319,6 +349,16 @@ def test_plan_stage_entry_points_compose(ctx, native):
     for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
         assert (a[k_] == b[k_]).all(), k_
     assert a["totals"][0] == plan.n_reads and a["totals"][2] == 32
+    # a plan is sized for the seed it was built with (read counts depend on it): running it under another seed is refused
+    plan = native.Plan(ctx, cid, af, nf, _sp(native), _umi(native))
+    seed = ctx.seed
+    ctx.set_seed(seed + 1)
+    with pytest.raises(native.NativeError, match="another seed"):
+        plan.run()
+    ctx.set_seed(seed)
+    plan.run()
+    assert (plan.results()["n_total"] == b["n_total"]).all()
+    plan.close()
 
 
 def test_chunked_plan_equals_single_chunk(ctx, native):
