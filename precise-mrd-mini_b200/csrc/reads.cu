@@ -172,9 +172,10 @@ __device__ __forceinline__ uint32_t shuffle_window(uint32_t w, uint32_t n_full, 
 // per-cell read counts from the family-major read offsets
 __global__ void __launch_bounds__(256)
 cell_read_count_kernel(const uint64_t* __restrict__ read_offset, const int64_t* __restrict__ fam_offsets, int64_t n_cells,
-                       int64_t n_fam, int64_t n_reads, int64_t* __restrict__ out) {
+                       int64_t n_fam, const uint64_t* __restrict__ total /* reads of the batch (device) */, int64_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cells) return;
+    const int64_t n_reads = (int64_t)total[0];
     const int64_t f0 = fam_offsets[i], f1 = fam_offsets[i + 1];
     const int64_t r0 = f0 < n_fam ? (int64_t)read_offset[f0] : n_reads;
     const int64_t r1 = f1 < n_fam ? (int64_t)read_offset[f1] : n_reads;
@@ -482,7 +483,8 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         if (e == cudaSuccess) e = plan->size_lut.alloc(ctx->stream, sizeof(h_lut));
         if (e == cudaSuccess) e = cudaMemcpyAsync(plan->size_lut.p, h_lut, sizeof(h_lut), cudaMemcpyHostToDevice, ctx->stream);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    // (no host sync here: copies from pageable memory are staged before cudaMemcpyAsync returns, and everything
+    // below is ordered on the stream)
     free(h_blk);
     if (e != cudaSuccess) {
         free(hc); free(ho);
@@ -497,19 +499,20 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
     if (!h_cnt || !h_tile) { free(hc); free(ho); free(h_cnt); free(h_tile); PMRD_ARG(ctx, false, "out of host memory"); }
     if (st == PMRD_OK) {
         // exact read count per cell (a pure function of the Philox key), gathered on the device
+        // (ONE host sync per build: the total and the per-cell counts come back together)
         uint64_t tot = 0;
         DevBuf cnt;
         e = cnt.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
-        if (e == cudaSuccess && nf > 0) e = cudaMemcpyAsync(&tot, plan->total.p, 8, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        plan->n_reads = (int64_t)tot;
+        if (e == cudaSuccess && nf == 0) e = cudaMemsetAsync(plan->total.p, 0, 8, ctx->stream);
         if (e == cudaSuccess && n_cells > 0) {
             cell_read_count_kernel<<<pmrd_blocks(n_cells, 256), 256, 0, ctx->stream>>>(
-                plan->read_offset.as<uint64_t>(), plan->fam_offsets.as<int64_t>(), n_cells, nf, plan->n_reads, cnt.as<int64_t>());
+                plan->read_offset.as<uint64_t>(), plan->fam_offsets.as<int64_t>(), n_cells, nf, plan->total.as<uint64_t>(), cnt.as<int64_t>());
             ctx->launches++;
             e = cudaMemcpyAsync(h_cnt, cnt.p, 8 * (size_t)n_cells, cudaMemcpyDeviceToHost, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&tot, plan->total.p, 8, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        plan->n_reads = (int64_t)tot;
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "read plan: %s", cudaGetErrorString(e)); st = PMRD_ERR_CUDA; }
     }
     if (st == PMRD_OK) {
@@ -541,7 +544,6 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
             if (e == cudaSuccess) e = plan->tile_cell.alloc(ctx->stream, 4 * (size_t)(tile + 1));
             if (e == cudaSuccess) e = cudaMemcpyAsync(plan->tile_cell.p, h_tc, 4 * (size_t)tile, cudaMemcpyHostToDevice, ctx->stream);
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         free(h_tc);
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "read plan: %s", cudaGetErrorString(e)); st = PMRD_ERR_CUDA; }
     }
@@ -612,6 +614,6 @@ int32_t reads_plan_generate_cell_major(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* 
 int32_t reads_plan_cell_counts(pmrd_ctx* ctx, ReadPlan* plan, int64_t* d_out) {
     if (plan->n_cells <= 0) return PMRD_OK;
     PMRD_LAUNCH(ctx, cell_read_count_kernel, pmrd_blocks(plan->n_cells, 256), 256, 0, (const uint64_t*)plan->read_offset.as<uint64_t>(),
-                (const int64_t*)plan->fam_offsets.as<int64_t>(), plan->n_cells, plan->n_fam, plan->n_reads, d_out);
+                (const int64_t*)plan->fam_offsets.as<int64_t>(), plan->n_cells, plan->n_fam, (const uint64_t*)plan->total.as<uint64_t>(), d_out);
     return PMRD_OK;
 }
