@@ -54,6 +54,17 @@ def workload(name: str, rank: int, world: int):
     elif name == "smoke":
         cfg = load_config(cfg_dir / "smoke.yaml")
         label = "configs/smoke.yaml C1 grid: 3 AF x 2 depths x 10 replicates = 60 cells per GPU"
+    elif name == "panel":
+        # BASELINE.json configs[4]: 8 samples x 1e5 loci x 250 families per locus, Poisson(5) family
+        # sizes, AF strata {0, 1e-4, 1e-3, 1e-2} by locus mod 4; one sample per GPU (the sample axis shards).  A cell is
+        # a (sample, locus) pair: ~1250 reads, less than one 4096-record tile -- a secondary line, not the default.
+        cfg = load_config(cfg_dir / "default.yaml")
+        n_loci = int(os.environ.get("PMRD_PANEL_LOCI", 100000))
+        locus = np.arange(n_loci, dtype=np.int64)
+        cell_id = (np.int64(rank) << 20) + locus
+        af = np.array([0.0, 1e-4, 1e-3, 1e-2])[locus % 4]
+        depth = np.full(n_loci, 250, dtype=np.int64)
+        return cfg, f"C5 panel: 1 sample x {n_loci} loci x 250 families per GPU (AF strata by locus mod 4)", cell_id, af, depth
     else:
         raise SystemExit(f"unknown workload {name}")
     sim = cfg.simulation
@@ -306,7 +317,8 @@ def main() -> int:
         torch.cuda.synchronize()
 
     # ---- device-resident arm: the plan owns all buffers; run() only enqueues kernels ----------
-    plan = nv.Plan(ctx, cell_id, af, depth, sim, up, neg_af_max=1e-4, test_type=tt, alpha=float(cfg.stats.alpha))
+    neg_af_max = 0.0 if args.workload == "panel" else 1e-4
+    plan = nv.Plan(ctx, cell_id, af, depth, sim, up, neg_af_max=neg_af_max, test_type=tt, alpha=float(cfg.stats.alpha))
     n_reads = plan.n_reads
     for _ in range(max(args.warmup, 3)):
         plan.run()
@@ -333,11 +345,11 @@ def main() -> int:
     # ---- end-to-end arm: public API, host buffers in, host table out, every step ------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     h_cid, h_af, h_depth = pin(cell_id), pin(af), pin(depth)
-    out = grid.run_cells(cfg, h_cid, h_af, h_depth, ctx=ctx, sim=sim)      # warm the allocator pool
+    out = grid.run_cells(cfg, h_cid, h_af, h_depth, ctx=ctx, sim=sim, neg_af_max=neg_af_max)      # warm the allocator pool
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = grid.run_cells(cfg, h_cid, h_af, h_depth, ctx=ctx, sim=sim)
+        out = grid.run_cells(cfg, h_cid, h_af, h_depth, ctx=ctx, sim=sim, neg_af_max=neg_af_max)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d = int(h_cid.nbytes + h_af.nbytes + h_depth.nbytes)

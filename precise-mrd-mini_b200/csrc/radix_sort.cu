@@ -461,7 +461,8 @@ rs_downsweep_staged_kernel(const uint64_t* __restrict__ keys_in, uint64_t* __res
 // Cell-major input (each cell = whole tiles [t0, t1)): every cell is an independent sort, so
 // the scan restarts at each cell -- one block per cell, thread d owns digit d.
 //   base(d, t) = t0 * RS_TILE + sum_{d' < d} sum_{t' in cell} H[t'][d'] + sum_{t0 <= t' < t} H[t'][d]
-#define RS_SCAN_PARTS 4   /* a cell's tiles are cut into this many contiguous ranges, walked side by side */
+// a cell's tiles are cut into RS_SCAN_PARTS contiguous ranges, walked side by side (1: cells of a few tiles only)
+template <int RS_SCAN_PARTS>
 __global__ void __launch_bounds__(256 * RS_SCAN_PARTS)
 rs_cellscan_kernel(uint32_t* __restrict__ hist, const int64_t* __restrict__ cell_tile_start, int n_cells) {
     __shared__ uint32_t sw[33];
@@ -559,7 +560,8 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
             if (shift + 8 <= 32) PMRD_LAUNCH_NAMED(ctx, "rs_upsweep_kernel", (rs_upsweep_tiles_kernel<256>), n_tiles, 256, 0, kin, hist, shift, mask);
             else PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist, shift, mask);
         }
-        PMRD_LAUNCH(ctx, rs_cellscan_kernel, (int)n_cells, 256 * RS_SCAN_PARTS, 0, hist, d_cell_tile_start, (int)n_cells);
+        if ((int64_t)n_tiles >= 8 * n_cells) PMRD_LAUNCH_NAMED(ctx, "rs_cellscan_kernel", rs_cellscan_kernel<4>, (int)n_cells, 1024, 0, hist, d_cell_tile_start, (int)n_cells);
+        else PMRD_LAUNCH_NAMED(ctx, "rs_cellscan_kernel", rs_cellscan_kernel<1>, (int)n_cells, 256, 0, hist, d_cell_tile_start, (int)n_cells);
         if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);
         } else if (stage) {
