@@ -547,6 +547,136 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     }
 }
 
+// ---------------------------------------------------------------- small cells: one block, no HBM round trip ----
+// Cells of at most SC_THREADS * ITEMS reads (the C5 panel: ~1250 reads per (sample, locus) cell) are not worth a
+// tile-padded trip through the global radix passes.  Their records sit back to back (compact layout, no padding);
+// one block loads a cell, sorts it by the 24 UMI bits with three ranked passes that never leave shared memory,
+// finds the family heads and votes them -- the 8 bytes per read are read once and nothing but the three per-cell
+// counts is written.  Ranking and vote are those of the tile kernels (ballot peer masks, stable; VoteM / VoteS).
+#define SC_THREADS 256
+#include "reads.cuh"
+template <int ITEMS>
+__global__ void __launch_bounds__(SC_THREADS)
+small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__ cells, int n_cells, pmrd_umi_params P, int64_t cell0,
+                  const uint8_t* __restrict__ alt_allele, unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot,
+                  unsigned long long* __restrict__ o_var) {
+    constexpr int CAP = SC_THREADS * ITEMS, WARPS = SC_THREADS / 32, PER_WARP = CAP / WARPS;
+    __shared__ __align__(16) uint64_t s_rec[CAP];
+    __shared__ __align__(16) unsigned char s_raw[4 * SC_THREADS * sizeof(double)];   // ranking counters, then the votes' allele sums
+    static_assert(sizeof(s_raw) >= WARPS * 256 * sizeof(uint32_t), "counters fit the shared scratch");
+    uint32_t (*s_cnt)[256] = reinterpret_cast<uint32_t (*)[256]>(s_raw);
+    double* const s_sum = reinterpret_cast<double*>(s_raw);
+    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t sw[33];
+    __shared__ double s_wt[64];
+    __shared__ unsigned long long s_acc[3];
+    const int cell = blockIdx.x;
+    if (cell >= n_cells) return;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = lanemask_lt();
+    const int n = (int)cells[cell].n_reads;
+    const uint64_t* __restrict__ src = rec + cells[cell].out_start;
+    if (threadIdx.x < 3) s_acc[threadIdx.x] = 0ull;
+    if (threadIdx.x < 64) s_wt[threadIdx.x] = (int)threadIdx.x >= P.quality_threshold ? c_wtab[threadIdx.x] : 0.0;
+    // warp-striped: item i of lane l = warp * PER_WARP + i * 32 + l (memory order = item-major, lane-minor: stable)
+    uint64_t key[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int loc = (int)warp * PER_WARP + i * 32 + (int)lane;
+        key[i] = loc < n ? src[loc] : 0xffffffffull;        // filler: UMI word 0xFFFFFFFF sorts last and is no 12-mer
+    }
+#pragma unroll 1
+    for (int shift = 0; shift < 24; shift += 8) {
+        for (int i = threadIdx.x; i < WARPS * 256; i += SC_THREADS) (&s_cnt[0][0])[i] = 0u;
+        __syncthreads();
+        uint32_t rank2[ITEMS / 2 > 0 ? (ITEMS + 1) / 2 : 1];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = ((uint32_t)key[i] >> shift) & 0xffu;
+            const uint32_t m = rs_peer_mask(d, 0xffffffffu);
+            const uint32_t before = __popc(m & lt);
+            const int leader = __ffs((int)m) - 1;
+            uint32_t old = 0;
+            if (before == 0) old = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(m));
+            old = __shfl_sync(0xffffffffu, old, leader);
+            const uint32_t r = old + before;
+            if (i & 1) rank2[i >> 1] |= r << 16;
+            else rank2[i >> 1] = r;
+        }
+        __syncthreads();
+        {   // per digit: exclusive prefix over the warps, then over the digits
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = s_cnt[w][threadIdx.x];
+                s_cnt[w][threadIdx.x] = run;
+                run += c;
+            }
+            uint32_t tot;
+            s_base[threadIdx.x] = block_exclusive_scan<uint32_t>(run, sw, tot);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = ((uint32_t)key[i] >> shift) & 0xffu;
+            const uint32_t r = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
+            s_rec[s_base[d] + s_cnt[warp][d] + r] = key[i];
+        }
+        __syncthreads();
+        if (shift < 16) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) key[i] = s_rec[warp * PER_WARP + i * 32 + lane];
+        }
+    }
+    // sorted: real reads occupy [0, n).  One thread per family head, in head order.
+    const uint32_t alt = alt_allele[cell0 + cell];
+    uint32_t n_fam = 0, n_tot = 0, n_var = 0;
+    for (int i = threadIdx.x; i < n; i += SC_THREADS) {
+        const uint32_t umi = (uint32_t)s_rec[i];
+        if (i > 0 && (uint32_t)s_rec[i - 1] == umi) continue;           // not a head
+        int len = 1;
+        while (i + len < n && (uint32_t)s_rec[i + len] == umi) ++len;
+        int best = -1;
+        if (P.consensus_threshold > 0.5) {
+            VoteM v(s_sum + threadIdx.x);
+            for (int c = 0; c < len; ++c) v.add((uint32_t)(s_rec[i + c] >> 32), s_wt);
+            if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
+        } else {
+            VoteS v(s_sum + threadIdx.x);
+            for (int c = 0; c < len; ++c) v.add((uint32_t)(s_rec[i + c] >> 32), s_wt);
+            if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
+        }
+        ++n_fam;
+        if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt; }
+    }
+    n_fam = warp_sum(n_fam); n_tot = warp_sum(n_tot); n_var = warp_sum(n_var);
+    if (lane == 0) {
+        atomicAdd(&s_acc[0], (unsigned long long)n_fam);
+        atomicAdd(&s_acc[1], (unsigned long long)n_tot);
+        atomicAdd(&s_acc[2], (unsigned long long)n_var);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        o_fam[cell0 + cell] = s_acc[0];
+        o_tot[cell0 + cell] = s_acc[1];
+        o_var[cell0 + cell] = s_acc[2];
+    }
+}
+
+// cells of a compact chunk (every cell <= max_cell_reads <= 4096 reads), records back to back at cells[c].out_start
+int32_t k5_collapse_counts_small(pmrd_ctx* ctx, const uint64_t* d_rec, const ReadCell* d_cells, int64_t n_cells, int64_t max_cell_reads,
+                                 const pmrd_umi_params* params, int64_t cell0, const uint8_t* d_alt_allele, int64_t* d_o_fam,
+                                 int64_t* d_o_tot, int64_t* d_o_var) {
+    if (n_cells <= 0) return PMRD_OK;
+    PMRD_ARG(ctx, max_cell_reads <= 4096, "small-cell collapse: a cell holds more than 4096 reads");
+    unsigned long long *f = (unsigned long long*)d_o_fam, *t = (unsigned long long*)d_o_tot, *v = (unsigned long long*)d_o_var;
+    if (max_cell_reads <= 512) PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<2>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, *params, cell0, d_alt_allele, f, t, v);
+    else if (max_cell_reads <= 1024) PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<4>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, *params, cell0, d_alt_allele, f, t, v);
+    else if (max_cell_reads <= 2048) PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<8>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, *params, cell0, d_alt_allele, f, t, v);
+    else PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<16>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, *params, cell0, d_alt_allele, f, t, v);
+    return PMRD_OK;
+}
+
 // segmented sort of packed records + fused consensus/count; outputs accumulate into the per-cell arrays
 int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d_rec_tmp, int64_t n_out,
                                      const pmrd_umi_params* params, const int64_t* d_cell_tile_start, const int32_t* d_tile_cell,

@@ -19,6 +19,10 @@ int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pa
                                  int64_t capacity_g, uint32_t* d_fam_start, uint32_t* d_grp_start, uint32_t* d_counts,
                                  const int64_t* d_cell_tile_start, int64_t n_seg_cells, int seg_key_bits);
 
+int32_t k5_collapse_counts_small(pmrd_ctx* ctx, const uint64_t* d_rec, const ReadCell* d_cells, int64_t n_cells, int64_t max_cell_reads,
+                                 const pmrd_umi_params* params, int64_t cell0, const uint8_t* d_alt_allele, int64_t* d_o_fam,
+                                 int64_t* d_o_tot, int64_t* d_o_var);
+
 int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d_rec_tmp, int64_t n_out,
                                      const pmrd_umi_params* params, const int64_t* d_cell_tile_start, const int32_t* d_tile_cell,
                                      int64_t n_cells,
@@ -264,6 +268,10 @@ static int32_t chunk_simulate(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
 }
 
 static int32_t chunk_collapse(pmrd_ctx* ctx, pmrd_plan* P, PlanChunk* ch) {
+    if (ch->reads.segmented == 2)      // compact chunk: every cell sorted and voted inside one block
+        return k5_collapse_counts_small(ctx, P->keys.as<uint64_t>(), ch->reads.cells.as<ReadCell>(), ch->n_cells, ch->reads.max_cell_reads,
+                                        &P->up, ch->cell0, (const uint8_t*)P->alt.as<uint8_t>(), P->o_fam.as<int64_t>(),
+                                        P->o_tot.as<int64_t>(), P->o_var.as<int64_t>());
     if (ch->reads.segmented) {
         // cell-major input: per-cell 3-pass sort, then ONE kernel from sorted reads to per-cell counts
         // (packed 8-byte records: P->keys / P->keys_tmp are the ping-pong pair, no payload arrays)

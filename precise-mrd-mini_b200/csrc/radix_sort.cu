@@ -7,26 +7,6 @@
 #define RS_DIRECT_MIN_BLOCKS 3
 #endif
 
-// Peer mask of a warp-wide digit: the lanes holding the same 8-bit digit as the caller.
-// Eight ballots, each written so that ONE predicate feeds both the vote and the select -- ptxas then
-// moves all eight digit bits into predicates with a single R2P and spends three instructions per bit
-// (VOTE, SEL, LOP3).  The C++ form `m &= bit ? bal : ~bal` costs six per bit, and MATCH.ANY on the
-// whole digit saturates the ADU pipe (ncu: 88 %).  Measured on B200, direct downsweep, 2.13e9 records x 3
-// passes: C++ ballots + MATCH on the top 3 bits 34.5 ms; this form 28.3 ms (MATCH on the top 1-2 bits: same;
-// 3 bits 29.1; 4 bits 31.1).
-__device__ __forceinline__ uint32_t rs_peer_mask(uint32_t d, uint32_t m) {
-#pragma unroll
-    for (int b = 0; b < 8; ++b) {
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, bal, x;\n\t"
-                     "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
-                     "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
-                     "selp.b32 x, 0, 0xffffffff, p;\n\t"
-                     "lop3.b32 %0, %0, bal, x, 0x60;\n\t}"      // m & (bal ^ x)
-                     : "+r"(m) : "r"(d), "r"(1u << b));
-    }
-    return m;
-}
-
 // zero `words` (a multiple of 4 * THREADS) 32-bit shared-memory counters with 16-byte stores, fully unrolled
 // (the scalar loop was 9 % of the direct downsweep's instructions)
 template <int THREADS, int WORDS>

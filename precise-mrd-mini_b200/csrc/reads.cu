@@ -17,6 +17,7 @@
 #include "rng.cuh"
 #include "scan.cuh"
 #include "reads.cuh"
+#include <stdlib.h>
 
 __device__ __forceinline__ int find_cell_in(const int64_t* __restrict__ fam_offsets, int lo, int hi, int64_t f) {
     while (hi - lo > 1) {  // fam_offsets[lo] <= f < fam_offsets[hi]
@@ -257,8 +258,16 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
             inv_full = shuffle_inv(S.cell_n);
         }
         const uint32_t w0 = S.cell_off / SHUF_WINDOW;
-        S.tile_a = window_tile(w0, S.cell_n, inv_full, sp.shuffle, S.tile0);
-        S.tile_b = window_tile(w0 + 1u, S.cell_n, inv_full, sp.shuffle, S.tile0);
+        if (segmented == 2) {
+            // compact layout (cells of <= 4096 reads, back to back, no padding): the cell's reads are scrambled by an
+            // odd-multiplier affine map inside its largest power-of-two prefix, the rest stays in place
+            S.tile0 = (uint32_t)c.out_start;
+            S.tile_a = (sp.shuffle && c.n_reads > 1u) ? 1u << (31 - __clz((int)c.n_reads)) : 0u;
+            S.tile_b = 0u;
+        } else {
+            S.tile_a = window_tile(w0, S.cell_n, inv_full, sp.shuffle, S.tile0);
+            S.tile_b = window_tile(w0 + 1u, S.cell_n, inv_full, sp.shuffle, S.tile0);
+        }
         if (tile_hist) {
             // By-product for the collapse stage: the first radix pass needs, per 4096-slot tile of the
             // output, the histogram of the low UMI byte.  A window of the family-major read order lands
@@ -344,13 +353,19 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
             }
         }
         // slot: window x / 4096 goes to one tile; inside a scrambled window the slot is an odd-multiplier affine map
-        const uint32_t x = sa.y + j;
-        const uint32_t w = x / SHUF_WINDOW, dw = w - sa.y / SHUF_WINDOW;
-        uint32_t t = dw == 0u ? sa.z : sa.w;
-        if (dw > 1u) t = window_tile(w, S.cell_n, shuffle_inv(S.cell_n), sp.shuffle, S.tile0);   // a family longer than a window
-        uint32_t l = x % SHUF_WINDOW;
-        if (!(t & SLOT_IDENT)) l = (l * 2654435761u + 0x9e37u * w) & (SHUF_WINDOW - 1);
-        const int64_t dst = (int64_t)(t & ~SLOT_IDENT) * SHUF_WINDOW + l;
+        uint32_t x = sa.y + j;
+        int64_t dst;
+        if (segmented == 2) {
+            if (x < sa.z) x = (x * 2654435761u + 0x9e37u) & (sa.z - 1u);      // sa.z: power-of-two prefix of the cell
+            dst = (int64_t)S.tile0 + x;                                        // S.tile0: the cell's first slot
+        } else {
+            const uint32_t w = x / SHUF_WINDOW, dw = w - sa.y / SHUF_WINDOW;
+            uint32_t t = dw == 0u ? sa.z : sa.w;
+            if (dw > 1u) t = window_tile(w, S.cell_n, shuffle_inv(S.cell_n), sp.shuffle, S.tile0);   // a family longer than a window
+            uint32_t l = x % SHUF_WINDOW;
+            if (!(t & SLOT_IDENT)) l = (l * 2654435761u + 0x9e37u * w) & (SHUF_WINDOW - 1);
+            dst = (int64_t)(t & ~SLOT_IDENT) * SHUF_WINDOW + l;
+        }
         if (payload) {
             keys[dst] = ((uint64_t)group << 32) | umi;
             payload[dst] = pl;
@@ -515,6 +530,14 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         plan->n_reads = (int64_t)tot;
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "read plan: %s", cudaGetErrorString(e)); st = PMRD_ERR_CUDA; }
     }
+    if (st == PMRD_OK && plan->segmented) {
+        // every cell far below a tile: the compact layout (no padding) and the one-block-per-cell collapse
+        int64_t mx = 0;
+        for (int64_t i = 0; i < n_cells; ++i) mx = h_cnt[i] > mx ? h_cnt[i] : mx;
+        plan->max_cell_reads = mx;
+        const char* sc = getenv("PMRD_SMALL_CELLS");
+        if ((!sc || atoi(sc) != 0) && mx <= READS_SEG_TILE && plan->n_reads < (1ll << 32)) plan->segmented = 2;
+    }
     if (st == PMRD_OK) {
         int64_t rs = 0, tile = 0;
         for (int64_t i = 0; i < n_cells; ++i) {
@@ -523,16 +546,16 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
             hc[i].n_reads = (uint32_t)h_cnt[i];
             plan->n_groups_with_reads += h_cnt[i] > 0;
             h_tile[i] = tile;
-            hc[i].out_start = plan->segmented ? tile * READS_SEG_TILE : rs;
+            hc[i].out_start = plan->segmented == 1 ? tile * READS_SEG_TILE : rs;
             hc[i].tile0 = (uint32_t)tile;
             hc[i].inv_full = shuffle_inv((uint32_t)h_cnt[i]);
             if (h_read_offsets) h_read_offsets[i] = rs;
             rs += h_cnt[i];
-            tile += (h_cnt[i] + READS_SEG_TILE - 1) / READS_SEG_TILE;
+            if (plan->segmented == 1) tile += (h_cnt[i] + READS_SEG_TILE - 1) / READS_SEG_TILE;
         }
         h_tile[n_cells] = tile;
         if (h_read_offsets) h_read_offsets[n_cells] = rs;
-        plan->n_out = plan->segmented ? tile * READS_SEG_TILE : plan->n_reads;
+        plan->n_out = plan->segmented == 1 ? tile * READS_SEG_TILE : plan->n_reads;
         e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cell_tile_start.p, h_tile, 8 * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, ctx->stream);
         // cell of every tile (the consensus kernel would otherwise binary-search it, one thread per block)
@@ -569,7 +592,7 @@ int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
 // output tile, produced as a by-product -- the collapse stage then skips its first counting pass
 int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload, uint32_t* d_tile_hist) {
     if (plan->n_fam <= 0) return PMRD_OK;
-    if (!plan->segmented) d_tile_hist = nullptr;
+    if (plan->segmented != 1) d_tile_hist = nullptr;
     if (d_tile_hist) PMRD_CUDA(ctx, cudaMemsetAsync(d_tile_hist, 0, (size_t)(plan->n_out / READS_SEG_TILE) * 256 * sizeof(uint32_t), ctx->stream));
     PMRD_LAUNCH(ctx, reads_gen_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
                 plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
@@ -577,7 +600,7 @@ int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uin
                 (const uint32_t*)plan->fam_word.as<uint32_t>(), (const uint32_t*)plan->fam_key.as<uint32_t>(),
                 (const int32_t*)plan->blk_cell.as<int32_t>(), plan->n_reads,
                 plan->segmented, d_keys, d_payload, d_tile_hist);
-    if (plan->segmented && plan->n_out > plan->n_reads)
+    if (plan->segmented == 1 && plan->n_out > plan->n_reads)
         PMRD_LAUNCH(ctx, reads_pad_kernel, (int)plan->n_cells, 256, 0, plan->cells.as<ReadCell>(), (int)plan->n_cells,
                     (const int64_t*)plan->cell_tile_start.as<int64_t>(), d_keys, d_payload, d_tile_hist);
     return PMRD_OK;

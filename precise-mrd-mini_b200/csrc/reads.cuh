@@ -30,7 +30,9 @@ struct ReadPlan {
     int64_t n_reads = 0;      // reads generated
     int64_t n_out = 0;        // slots in the output arrays (== n_reads unless segmented: + padding)
     int64_t n_groups_with_reads = 0;  // cells that own at least one read
-    int segmented = 0;        // cell-major, tile-padded layout (enables the per-cell 3-pass sort)
+    int segmented = 0;        // 1: cell-major, tile-padded layout (per-cell 3-pass sort); 2: cell-major COMPACT layout (every
+                              // cell <= 4096 reads, no padding: one block sorts and votes a cell in shared memory)
+    int64_t max_cell_reads = 0;
     bool sizes_fresh = false; // the build just computed sizes / offsets for `sizes_seed`: the first step reuses them
     uint64_t sizes_seed = 0;
 };

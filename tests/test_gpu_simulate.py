@@ -335,6 +335,57 @@ def test_families_longer_than_a_shuffle_window(ctx, native, monkeypatch):
     assert (res["n_total"] == n_total).all() and (res["n_variants"] == n_var).all()
 
 
+@pytest.mark.parametrize("cthr", [0.6, 0.4])
+def test_small_cells_are_sorted_and_voted_inside_one_block(ctx, native, monkeypatch, cthr):
+    """Grids whose cells all hold <= 4096 reads (the C5 panel: ~1250 reads per locus) take the compact layout: no tile
+    padding, one block sorts and votes a cell in shared memory.  Same tables as the tile-padded path, and equal to the
+    oracle on the plan's own read order (first-seen tie-breaks included)."""
+    rng = np.random.default_rng(31)
+    c = 700
+    cid = (np.int64(3) << 20) + np.arange(c)
+    af = np.array([0.0, 1e-4, 0.3, 0.01])[np.arange(c) % 4]
+    nf = rng.integers(0, 700, c)                     # 0 .. ~3500 reads: 2, 4, 8 and 16 records per thread
+    nf[:5] = [0, 1, 2, 250, 699]
+    sp = _sp(native, family_model=1, mean_family_size=5.0, collision_rate=2e-3)
+    up = _umi(native, consensus_threshold=cthr, min_family_size=2)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PMRD_SMALL_CELLS", flag)
+        plan = native.Plan(ctx, cid, af, nf, sp, up)
+        ctx.profile_enable(True)
+        plan.run()
+        prof = ctx.profile_report()
+        ctx.profile_enable(False)
+        out[flag] = (plan.results(), prof)
+        plan.close()
+    assert "small_cell_kernel" in out["1"][1] and "small_cell_kernel" not in out["0"][1]
+    assert "rs_downsweep_direct_kernel" not in out["1"][1]
+    a, b = out["1"][0], out["0"][0]
+    for k_ in ("n_reads", "n_families"):
+        assert (a[k_] == b[k_]).all(), k_
+    # (the two layouts order a cell's reads differently, so only order-free columns must agree between them ...)
+    if cthr > 0.5:
+        for k_ in ("n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+            assert (a[k_] == b[k_]).all(), k_
+    # ... and each must equal the oracle run on ITS OWN read order
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PMRD_SMALL_CELLS", flag)
+        keys, pl = ctx.simulate_reads(cid, af, nf, _sp(native, family_model=1, mean_family_size=5.0, collision_rate=2e-3, shuffle=2))
+        fam, grp = port.collapse_exact(keys, pl, 0, 2, 1000, 20, cthr)
+        alt = ((cid & 3) + 1 + ((cid >> 2) % 3)) & 3
+        n_total, n_var, n_fam = np.zeros(c, np.int64), np.zeros(c, np.int64), np.zeros(c, np.int64)
+        n_total[grp["group"]] = grp["consensus_count"].sum(1)
+        n_var[grp["group"]] = grp["consensus_count"][np.arange(len(grp["group"])), alt[grp["group"]]]
+        np.add.at(n_fam, (fam["key"] >> np.uint64(32)).astype(np.int64), 1)
+        r = out[flag][0]
+        assert (r["n_total"] == n_total).all() and (r["n_variants"] == n_var).all() and (r["n_families"] == n_fam).all(), flag
+    # the compact layout does scramble a cell (inside its power-of-two prefix)
+    monkeypatch.setenv("PMRD_SMALL_CELLS", "1")
+    keys, _ = ctx.simulate_reads(cid[3:4], af[3:4], nf[3:4], _sp(native, family_model=1, shuffle=2))
+    runs = 1 + int((np.diff(keys.astype(np.int64)) != 0).sum())
+    assert runs > 3 * 250                                   # 250 families would form 250 runs if left family by family
+
+
 def test_plan_stage_entry_points_compose(ctx, native):
     cid = np.arange(32)
     af = np.tile([0.0, 0.02], 16)
