@@ -628,12 +628,17 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
             for (int i = 0; i < ITEMS; ++i) key[i] = s_rec[warp * PER_WARP + i * 32 + lane];
         }
     }
-    // sorted: real reads occupy [0, n).  One thread per family head, in head order.
+    // sorted: real reads occupy [0, n).  The family heads are compacted into a list first (a warp's 32 consecutive
+    // records hold ~6 heads: voting in place would leave 26 lanes idle), then one thread votes one family.
+    constexpr bool LIST = ITEMS <= 12;                       // (the list must fit the 48 KB of static shared memory)
+    __shared__ uint16_t s_list[LIST ? CAP : 1];
+    __shared__ uint32_t s_nheads;
+    if (threadIdx.x == 0) s_nheads = 0u;
+    __syncthreads();
     const uint32_t alt = alt_allele[cell0 + cell];
     uint32_t n_fam = 0, n_tot = 0, n_var = 0;
-    for (int i = threadIdx.x; i < n; i += SC_THREADS) {
+    auto vote_family = [&](int i) {
         const uint32_t umi = (uint32_t)s_rec[i];
-        if (i > 0 && (uint32_t)s_rec[i - 1] == umi) continue;           // not a head
         int len = 1;
         while (i + len < n && (uint32_t)s_rec[i + len] == umi) ++len;
         int best = -1;
@@ -648,6 +653,23 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
         }
         ++n_fam;
         if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt; }
+    };
+    if (LIST) {
+        for (int i0 = 0; i0 < n; i0 += SC_THREADS) {
+            const int i = i0 + (int)threadIdx.x;
+            const bool head = i < n && (i == 0 || (uint32_t)s_rec[i - 1] != (uint32_t)s_rec[i]);
+            const uint32_t hm = __ballot_sync(0xffffffffu, head);
+            uint32_t pos = 0;
+            if (lane == 0 && hm) pos = atomicAdd(&s_nheads, (uint32_t)__popc(hm));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (head) s_list[pos + __popc(hm & lt)] = (uint16_t)i;
+        }
+        __syncthreads();
+        const int n_heads = (int)s_nheads;
+        for (int h = threadIdx.x; h < n_heads; h += SC_THREADS) vote_family((int)s_list[h]);
+    } else {
+        for (int i = threadIdx.x; i < n; i += SC_THREADS)
+            if (i == 0 || (uint32_t)s_rec[i - 1] != (uint32_t)s_rec[i]) vote_family(i);
     }
     n_fam = warp_sum(n_fam); n_tot = warp_sum(n_tot); n_var = warp_sum(n_var);
     if (lane == 0) {
@@ -670,10 +692,15 @@ int32_t k5_collapse_counts_small(pmrd_ctx* ctx, const uint64_t* d_rec, const Rea
     if (n_cells <= 0) return PMRD_OK;
     PMRD_ARG(ctx, max_cell_reads <= 4096, "small-cell collapse: a cell holds more than 4096 reads");
     unsigned long long *f = (unsigned long long*)d_o_fam, *t = (unsigned long long*)d_o_tot, *v = (unsigned long long*)d_o_var;
-    if (max_cell_reads <= 512) PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<2>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, *params, cell0, d_alt_allele, f, t, v);
-    else if (max_cell_reads <= 1024) PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<4>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, *params, cell0, d_alt_allele, f, t, v);
-    else if (max_cell_reads <= 2048) PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<8>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, *params, cell0, d_alt_allele, f, t, v);
-    else PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<16>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, *params, cell0, d_alt_allele, f, t, v);
+    // records per thread: the smallest that holds the largest cell (a slot beyond the cell's reads still costs a rank)
+#define SC_CASE(I) \
+    if (max_cell_reads <= (int64_t)SC_THREADS * (I)) {                                                                          \
+        PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<I>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, \
+                          *params, cell0, d_alt_allele, f, t, v);                                                                \
+        return PMRD_OK;                                                                                                          \
+    }
+    SC_CASE(1) SC_CASE(2) SC_CASE(3) SC_CASE(4) SC_CASE(5) SC_CASE(6) SC_CASE(7) SC_CASE(8) SC_CASE(10) SC_CASE(12) SC_CASE(14) SC_CASE(16)
+#undef SC_CASE
     return PMRD_OK;
 }
 
