@@ -379,6 +379,15 @@ def test_small_cells_are_sorted_and_voted_inside_one_block(ctx, native, monkeypa
         np.add.at(n_fam, (fam["key"] >> np.uint64(32)).astype(np.int64), 1)
         r = out[flag][0]
         assert (r["n_total"] == n_total).all() and (r["n_variants"] == n_var).all() and (r["n_families"] == n_fam).all(), flag
+    # streamed through many compact chunks: nothing changes
+    monkeypatch.setenv("PMRD_SMALL_CELLS", "1")
+    plan = native.Plan(ctx, cid, af, nf, _sp(native, family_model=1, mean_family_size=5.0, collision_rate=2e-3, chunk_log2=16), up)
+    assert plan.n_chunks > 5
+    plan.run()
+    many = plan.results()
+    plan.close()
+    for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+        assert (many[k_] == a[k_]).all(), k_
     # the compact layout does scramble a cell (inside its power-of-two prefix)
     monkeypatch.setenv("PMRD_SMALL_CELLS", "1")
     keys, _ = ctx.simulate_reads(cid[3:4], af[3:4], nf[3:4], _sp(native, family_model=1, shuffle=2))
