@@ -17,14 +17,16 @@ def set_global_seed(seed: int, deterministic_ops: bool = True) -> np.random.Gene
     os.environ["PYTHONHASHSEED"] = str(seed)      # no effect after start-up; kept for parity
     random.seed(seed)
     rng = np.random.default_rng(seed)
-    try:
-        import torch
-
-        torch.manual_seed(seed)
-        if torch.cuda.is_available():
-            torch.cuda.manual_seed_all(seed)
-    except Exception:
-        pass
+    # the reference also seeds torch "when present" (seed.py:40-47).  Nothing on this path draws from torch, so it is
+    # seeded only if the caller has imported it -- importing it here would cost every CLI process ~2.5 s
+    if "torch" in sys.modules:
+        try:
+            torch = sys.modules["torch"]
+            torch.manual_seed(seed)
+            if torch.cuda.is_available():
+                torch.cuda.manual_seed_all(seed)
+        except Exception:
+            pass
     return rng
 
 
@@ -49,13 +51,20 @@ def env_fingerprint() -> dict[str, Any]:
         fp["scipy_version"] = scipy.__version__
     except ImportError:
         pass
+    # same keys as the reference's fingerprint, filled without importing torch (2.5 s): the version from the
+    # package metadata, the device from the native library this path actually runs on
     try:
-        import torch
+        from importlib import metadata
 
-        fp["torch_version"] = torch.__version__
-        fp["cuda_available"] = bool(torch.cuda.is_available())
-    except ImportError:
+        fp["torch_version"] = metadata.version("torch")
+    except Exception:
         fp["torch_version"] = None
+    try:
+        from .. import _native as nv
+
+        nv.default_context()
+        fp["cuda_available"] = True
+    except Exception:
         fp["cuda_available"] = False
     fp["cpu_count"] = os.cpu_count() or 1
     fp["machine"] = platform.machine()

@@ -60,6 +60,10 @@ def all_gather_rows(local_index: np.ndarray, local_rows: np.ndarray, n_total: in
 
 def world_size() -> int:
     """Ranks of the initialised default process group (1 when torch.distributed is not in use)."""
+    import sys
+
+    if "torch" not in sys.modules:      # nobody imported torch, so no process group exists: do not pay its import
+        return 1
     try:
         import torch.distributed as dist
     except Exception:          # pragma: no cover
