@@ -395,6 +395,38 @@ def test_small_cells_are_sorted_and_voted_inside_one_block(ctx, native, monkeypa
     assert runs > 3 * 250                                   # 250 families would form 250 runs if left family by family
 
 
+@pytest.mark.parametrize("nf", [[4096, 4095, 1, 2048, 4096, 0, 3], [4097, 8191, 8192, 8193, 12288, 16384, 4096, 1, 0, 20480]])
+def test_cells_exactly_at_tile_boundaries(ctx, native, monkeypatch, nf):
+    """max_family_size = 1 makes every family one read, so a cell of n families holds exactly n reads: cells that fill
+    whole 4096-record tiles (no padding, empty tail window), one read more, one less; the first list takes the compact
+    layout (every cell <= 4096 reads), the second the tile-padded one."""
+    nf = np.array(nf, dtype=np.int64)
+    c = len(nf)
+    cid = np.arange(c) + 500
+    af = np.tile([0.0, 0.5], c)[:c]
+    sp = _sp(native, family_model=1, max_family_size=1)
+    up = _umi(native, min_family_size=1)
+    out = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("PMRD_GEN_HIST", flag)
+        out[flag] = ctx.pipeline_cells(cid, af, nf, sp, up)
+    monkeypatch.setenv("PMRD_GEN_HIST", "1")
+    res = out["1"]
+    for k_ in ("n_reads", "n_families", "n_total", "n_variants"):
+        assert (out["0"][k_] == res[k_]).all(), k_
+    assert (res["n_reads"] == nf).all()
+    keys, pl = ctx.simulate_reads(cid, af, nf, _sp(native, family_model=1, max_family_size=1, shuffle=2))
+    assert len(keys) == nf.sum()
+    fam, grp = port.collapse_exact(keys, pl, 0, 1, 1000, 20, 0.6)
+    alt = ((cid & 3) + 1 + ((cid >> 2) % 3)) & 3
+    n_total, n_var, n_fam = np.zeros(c, np.int64), np.zeros(c, np.int64), np.zeros(c, np.int64)
+    n_total[grp["group"]] = grp["consensus_count"].sum(1)
+    n_var[grp["group"]] = grp["consensus_count"][np.arange(len(grp["group"])), alt[grp["group"]]]
+    np.add.at(n_fam, (fam["key"] >> np.uint64(32)).astype(np.int64), 1)
+    assert (res["n_total"] == n_total).all() and (res["n_variants"] == n_var).all() and (res["n_families"] == n_fam).all()
+    assert (res["n_families"] <= nf).all() and res["n_families"].sum() > 0.99 * nf.sum()      # (UMI collisions merge a few)
+
+
 def test_plan_stage_entry_points_compose(ctx, native):
     cid = np.arange(32)
     af = np.tile([0.0, 0.02], 16)
