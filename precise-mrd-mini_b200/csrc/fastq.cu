@@ -24,14 +24,26 @@
 __device__ __forceinline__ bool fq_space(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 0x1c && c <= 0x1f); }
 __device__ __forceinline__ bool fq_upper(uint8_t c) { return c >= 'A' && c <= 'Z'; }
 
+// A thread owns one 64-byte chunk (the device buffer is 256-byte aligned, chunks are 64-aligned): four 16-byte loads,
+// newlines found four bytes at a time with the SIMD byte compare (the byte loop was 64 loads per thread).
+#define FQ_NL4 0x0a0a0a0au
 __global__ void __launch_bounds__(256)
 fq_count_kernel(const uint8_t* __restrict__ buf, int64_t n, uint32_t* __restrict__ counts) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t lo = c * FQ_CHUNK;
     if (lo >= n) return;
-    const int64_t hi = lo + FQ_CHUNK < n ? lo + FQ_CHUNK : n;
     uint32_t k = 0;
-    for (int64_t i = lo; i < hi; ++i) k += buf[i] == '\n';
+    if (lo + FQ_CHUNK <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(buf + lo);
+#pragma unroll
+        for (int j = 0; j < FQ_CHUNK / 16; ++j) {
+            const uint4 v = p[j];
+            k += __popc(__vcmpeq4(v.x, FQ_NL4) & 0x01010101u) + __popc(__vcmpeq4(v.y, FQ_NL4) & 0x01010101u) +
+                 __popc(__vcmpeq4(v.z, FQ_NL4) & 0x01010101u) + __popc(__vcmpeq4(v.w, FQ_NL4) & 0x01010101u);
+        }
+    } else {
+        for (int64_t i = lo; i < n; ++i) k += buf[i] == '\n';
+    }
     counts[c] = k;
 }
 
@@ -40,10 +52,27 @@ fq_fill_kernel(const uint8_t* __restrict__ buf, int64_t n, const uint32_t* __res
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t lo = c * FQ_CHUNK;
     if (lo >= n) return;
-    const int64_t hi = lo + FQ_CHUNK < n ? lo + FQ_CHUNK : n;
     uint32_t k = offs[c];
-    for (int64_t i = lo; i < hi; ++i)
-        if (buf[i] == '\n') line_end[k++] = i;
+    if (lo + FQ_CHUNK <= n) {
+        const uint4* p = reinterpret_cast<const uint4*>(buf + lo);
+#pragma unroll
+        for (int j = 0; j < FQ_CHUNK / 16; ++j) {
+            const uint4 v = p[j];
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t m = __vcmpeq4(w[q], FQ_NL4) & 0x01010101u;     // bit 8b set <=> byte b is a newline
+                while (m) {
+                    const int b = (__ffs((int)m) - 1) >> 3;
+                    m &= m - 1u;
+                    line_end[k++] = lo + j * 16 + q * 4 + b;
+                }
+            }
+        }
+    } else {
+        for (int64_t i = lo; i < n; ++i)
+            if (buf[i] == '\n') line_end[k++] = i;
+    }
 }
 
 struct FqLine { int64_t lo, hi; };   // stripped [lo, hi)
