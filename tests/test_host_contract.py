@@ -2,6 +2,7 @@
 validation, manifest format, CLI wiring, packing helpers.  Modelled on the reference's
 tests/test_determinism_hashes.py, tests/test_artifact_contract.py and tests/test_rng_api.py."""
 import ast
+import os
 import json
 from pathlib import Path
 
@@ -130,3 +131,46 @@ def test_metrics_oracle_matches_sklearn_and_calibration_bins():
     assert a == b and a["lower"] <= a["mean"] <= a["upper"]                    # test_lob_lod_bootstrap.py:148-168
     cal = calibration_analysis(np.array([0, 1, 1]), np.array([0.05, 0.95, 1.0]))
     assert cal[-1]["bin"] == 9 and cal[-1]["count"] == 2                       # last bin closed
+
+
+def test_bench_workloads_and_sharding_keys():
+    """bench.py's workloads: the C2 grid shards the replicate axis with GLOBAL cell ids (so a cell's Philox stream does not
+    depend on the rank), the C5 panel gives each rank one sample of 1e5 loci with the AF strata by locus mod 4."""
+    import importlib
+    import sys as _sys
+
+    root = str(Path(__file__).resolve().parent.parent)
+    if root not in _sys.path:
+        _sys.path.insert(0, root)
+    bench = importlib.import_module("bench")
+    os.environ["PMRD_BENCH_REPS"] = "3"
+    try:
+        ids = []
+        for rank in range(2):
+            cfg, label, cid, af, depth = bench.workload("default", rank, 2)
+            assert len(cid) == 5 * 4 * 3 and "C2" in label
+            ids.append(cid)
+        assert len(np.intersect1d(ids[0], ids[1])) == 0                      # ranks own disjoint global cells
+        _, _, one, _, _ = bench.workload("default", 0, 1)
+        assert len(one) == 60
+    finally:
+        os.environ.pop("PMRD_BENCH_REPS", None)
+    os.environ["PMRD_PANEL_LOCI"] = "1000"
+    try:
+        cfg, label, cid, af, depth = bench.workload("panel", 3, 8)
+        assert len(cid) == 1000 and (depth == 250).all() and (cid >> 20 == 3).all()
+        assert (af == np.array([0.0, 1e-4, 1e-3, 1e-2])[np.arange(1000) % 4]).all()
+    finally:
+        os.environ.pop("PMRD_PANEL_LOCI", None)
+
+
+def test_world_size_does_not_import_torch():
+    """A CLI process must not pay torch's import (2.5 s) to learn that it is alone."""
+    import subprocess
+    import sys as _sys
+
+    pkg = str(Path(__file__).resolve().parent.parent / "precise-mrd-mini_b200")
+    code = ("import sys; sys.path.insert(0, %r); from precise_mrd import distributed as d; from precise_mrd.determinism_utils import "
+            "set_global_seed; set_global_seed(7); assert d.world_size() == 1; assert 'torch' not in sys.modules; print('ok')" % pkg)
+    out = subprocess.run([_sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-500:]
