@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "reads.cuh"
 
 __constant__ double c_wtab[64];  // 10^(q/10), q = 0..63
 
@@ -554,7 +555,6 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
 // finds the family heads and votes them -- the 8 bytes per read are read once and nothing but the three per-cell
 // counts is written.  Ranking and vote are those of the tile kernels (ballot peer masks, stable; VoteM / VoteS).
 #define SC_THREADS 256
-#include "reads.cuh"
 template <int ITEMS>
 __global__ void __launch_bounds__(SC_THREADS)
 small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__ cells, int n_cells, pmrd_umi_params P, int64_t cell0,

@@ -491,13 +491,12 @@ rs_cellscan_kernel(uint32_t* __restrict__ hist, const int64_t* __restrict__ cell
 }
 
 static int32_t rs_set_attrs(pmrd_ctx* ctx) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    // (function attributes belong to the device of the current context: set on every call, it costs microseconds)
+    {
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<RS_WARPS>)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<256, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<8>)));
-        attr_set = true;
     }
     return PMRD_OK;
 }

@@ -130,7 +130,7 @@ __device__ __align__(16) uint8_t c_qual_lut[1 << QUAL_LUT_BITS];   // global, no
 
 int32_t reads_upload_tables(pmrd_ctx* ctx) {
     uint32_t h[32];
-    static uint8_t lut[1 << QUAL_LUT_BITS];
+    uint8_t lut[1 << QUAL_LUT_BITS];          // (on the stack: contexts of different threads may build at once)
     for (int k = 0; k < 32; ++k) {
         // int() truncates toward zero and 30 + 5 z > 0 here, so q <= 10 + k  <=>  30 + 5 z < 11 + k
         const double zc = ((double)(11 + k) - 30.0) / 5.0;
@@ -488,7 +488,7 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
         if (e == cudaSuccess) e = plan->size_cdf.alloc(ctx->stream, sizeof(h_cdf));
         if (e == cudaSuccess) e = cudaMemcpyAsync(plan->size_cdf.p, h_cdf, sizeof(h_cdf), cudaMemcpyHostToDevice, ctx->stream);
         // inverse table: lut[b] = #{k : F[k] < u} for the smallest uniform of bucket b (u24 of the words b << 20 ..)
-        static uint8_t h_lut[4096];
+        uint8_t h_lut[4096];
         for (uint32_t b = 0; b < 4096u; ++b) {
             const float u = u24(b << 20);
             int k = 0;
