@@ -429,7 +429,7 @@ def main() -> int:
             "dtype": "u64 keys / u32 payload / f64 tests", "data": "synthetic",
             "config": {"workload": label, "cells_per_gpu": int(len(cell_id)), "reads_per_gpu_per_step": int(n_reads),
                        "families_per_gpu_per_step": int(depth.sum()), "chunks": n_chunks, "record_bytes": pinfo["record_bytes"],
-                       "radix_passes": pinfo["sort_passes"], "family_sizes": "clip(Poisson(5),1,1000)",
+                       "radix_passes": pinfo["sort_passes"], "counting_passes": up_passes, "family_sizes": "clip(Poisson(5),1,1000)",
                        "umi": "12-mer (24 bit)", "input_order": "window-shuffled (Philox-keyed affine permutation)",
                        "l2": f"inputs larger than L2 ({min(chunk_reads) * pinfo['record_bytes'] / 1e9:.1f} GB of records in the smallest chunk vs 126 MB)", "parallelism": f"replicate axis sharded over {world} GPU(s)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
