@@ -134,6 +134,8 @@ int32_t pmrd_sort_pairs_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_vals, i
 
 #define PMRD_CLUSTER_EXACT 0    /* exact UMI match   umi.py:111-115, lib.rs:7-22                  */
 #define PMRD_CLUSTER_FIRSTFIT 1 /* first-fit Hamming <= d to the representative  mrd/umi.py:29-40 */
+#define PMRD_CLUSTER_GREEDY 2   /* greedy Hamming <= d around seeds taken in (-count, umi) order:
+                                   umi_clustering.py:59-101, the defined-order form of umi.py:117-144 */
 
 typedef struct pmrd_umi_params {
     int32_t min_family_size;     /* families below are dropped (after consensus, on raw size: umi.py:181-203) */
@@ -142,7 +144,7 @@ typedef struct pmrd_umi_params {
     double consensus_threshold;  /* w_best / w_total must be >= this              umi.py:172 */
     int32_t mode;                /* PMRD_MODE_*                                               */
     int32_t cluster;             /* PMRD_CLUSTER_*                                            */
-    int32_t max_distance;        /* Hamming radius for FIRSTFIT                               */
+    int32_t max_distance;        /* Hamming radius for FIRSTFIT / GREEDY                      */
     int32_t umi_len;             /* bases in the UMI (<=16)                                   */
 } pmrd_umi_params;
 
@@ -153,7 +155,8 @@ typedef struct pmrd_umi_params {
 
 typedef struct pmrd_family_table {
     uint64_t* key;       /* [F] group:32 | representative umi:32; sorted ascending (EXACT) or
-                            group-sorted then cluster-creation order (FIRSTFIT)           */
+                            group-sorted then cluster-creation order (FIRSTFIT: the UMI that opened
+                            the cluster; GREEDY: seed order, the UMI of the cluster's first read) */
     uint32_t* size;      /* [F] reads in the family                                       */
     uint32_t* n_alt;     /* [F] reads with is_alt set                                     */
     uint32_t* consensus; /* [F] WEIGHTED: allele code; MAJORITY: 20-bit consensus sequence */

@@ -15,6 +15,8 @@ parity tests can run where the reference cannot travel.
   ga_reads.npz                            G-A reads -> mrd.umi.collapse_reads (== tmp/families.parquet)
   gc_reads.npz                            G-C reads -> committed collapsed_umis / mrd_calls tables
   gb_reads.npz                            G-B SyntheticReadGenerator reads -> UMIProcessor(max_edit_distance=0)
+  gb_greedy.npz                           the same reads with barcode errors -> UMIProcessor(max_edit_distance=1, 2) with the
+                                          reference's deterministic greedy clusters (umi_clustering.py:59-101)
   gb_stats.json                           G-B StatisticalTester (one-sided tests, CIs, BH/Bonferroni/Holm),
                                           ContextAnalyzer and ErrorModel on seeded inputs
   gb_qc.json                              G-B QCAnalyzer report + FeatureEngineer.extract_features on seeded tables
@@ -262,6 +264,81 @@ def golden_gb() -> None:
         params=np.array([3, 1000, 20], np.int64), consensus_threshold=np.float64(0.6),
     )
     print("  wrote gb_reads.npz", len(reads), "reads", len(fams), "families", len(kept), "kept")
+
+
+# ------------------------------------------------------------------------------- G-B greedy clustering
+def golden_gb_greedy() -> None:
+    """UMIProcessor with max_edit_distance = 1 (configs/default.yaml:16), the Hamming clusters taken from the
+    reference's DETERMINISTIC greedy form: src/precise_mrd/umi_clustering.py:59-101 (cluster_umis_greedy -- unique
+    UMIs ordered by (-count, umi); the first unused UMI seeds a cluster and absorbs every unused UMI within the
+    distance).  umi.py:117-144 runs the same loop over list(set(...)) -- hash-order dependent -- so its iteration
+    order is DEFINED here as that sorted order.  Everything else is the reference's own code:
+    cluster reads in input order (umi.py:137-140), UMIFamily.umi = first read's UMI (umi.py:225), call_consensus,
+    filter_family_size."""
+    import importlib.util
+
+    sys.path.insert(0, str(HERE / "_ref" / "gb"))
+    from precise_mrd_gb.io import SyntheticReadGenerator
+    from precise_mrd_gb.umi import UMIProcessor
+
+    spec = importlib.util.spec_from_file_location("ref_umi_clustering", REF / "src" / "precise_mrd" / "umi_clustering.py")
+    uc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(uc)
+
+    gen = SyntheticReadGenerator(seed=23)
+    sites = gen.generate_target_sites(16)
+    reads = []
+    afs = [0.0, 0.05, 0.3, 0.6]
+    for i, s in enumerate(sites):
+        reads += gen.generate_reads_for_site(s, n_umi_families=150 if i % 4 else 600, allele_fraction=afs[i % 4],
+                                             mean_family_size=4.0)
+    rng = np.random.default_rng(9)
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    # sequencing errors in the barcode: one substituted base in 12 % of the reads, two in 2 % (so that clusters of
+    # several UMIs, chains a-b-c the greedy rule cuts, and equal-count ties all occur)
+    for r in reads:
+        u = rng.random()
+        n_sub = 2 if u < 0.02 else (1 if u < 0.14 else 0)
+        for _ in range(n_sub):
+            pos = int(rng.integers(0, len(r.umi)))
+            r.umi = r.umi[:pos] + "ACGT"[(BASE[r.umi[pos]] + 1 + int(rng.integers(0, 3))) % 4] + r.umi[pos + 1:]
+    for r in reads[::9]:
+        r.quality = max(10, r.quality - 12)
+    out = {}
+    skeys = None
+    for d in (1, 2):
+        proc = UMIProcessor(min_family_size=3, max_family_size=1000, max_edit_distance=d, quality_threshold=20,
+                            consensus_threshold=0.6)
+        clusterer = uc.OptimizedUMICluster(max_edit_distance=d)
+        site_groups = proc.group_umis_by_site(reads)
+        skeys = list(site_groups.keys())
+        fams = []
+        for site_key, site_reads in site_groups.items():
+            for cluster_umis in clusterer.cluster_umis_greedy([r.umi for r in site_reads]):
+                members = set(cluster_umis)
+                umi_reads = [r for r in site_reads if r.umi in members]          # umi.py:137-140
+                ca, cq = proc.call_consensus(umi_reads)
+                fams.append((site_key, umi_reads[0].umi, len(umi_reads), ca, cq, len(cluster_umis)))
+        sid = {k: i for i, k in enumerate(skeys)}
+        out[f"want_fam_key_d{d}"] = (np.array([sid[f[0]] for f in fams], np.uint64) << np.uint64(32)) | \
+            np.array([pack_seq(f[1]) for f in fams], np.uint64)
+        out[f"want_fam_size_d{d}"] = np.array([f[2] for f in fams], np.uint32)
+        out[f"want_fam_allele_d{d}"] = np.array([-1 if f[3] is None else BASE[f[3]] for f in fams], np.int32)
+        out[f"want_fam_quality_d{d}"] = np.array([np.nan if f[4] is None else f[4] for f in fams], np.float64)
+        out[f"want_cluster_umis_d{d}"] = np.array([f[5] for f in fams], np.int32)
+        print(f"    d={d}: {len(fams)} clusters, {sum(f[5] > 1 for f in fams)} of several UMIs, "
+              f"{sum(f[2] >= 3 for f in fams)} kept")
+    sid = {k: i for i, k in enumerate(skeys)}
+    site_alt = {f"{s.chrom}:{s.pos}:{s.ref}": s.alt for s in sites}
+    g = np.array([sid[f"{r.chrom}:{r.pos}:{r.ref}"] for r in reads], np.uint64)
+    keys = (g << np.uint64(32)) | np.array([pack_seq(r.umi) for r in reads], np.uint64)
+    payload = np.array([
+        BASE[r.alt] | (r.quality << 2) | ((1 if r.strand == "+" else 0) << 8) | (r.read_position << 9) |
+        ((1 if r.alt == site_alt[f"{r.chrom}:{r.pos}:{r.ref}"] else 0) << 31) for r in reads], np.uint64).astype(np.uint32)
+    np.savez_compressed(OUT / "gb_greedy.npz", keys=keys, payload=payload, params=np.array([3, 1000, 20], np.int64),
+                        consensus_threshold=np.float64(0.6), **out)
+    print("  wrote gb_greedy.npz", len(reads), "reads")
 
 
 # ------------------------------------------------------------------------------- G-B stats / context / errors
@@ -611,7 +688,7 @@ def main() -> int:
     only = set(sys.argv[1:])
     steps = {
         "call": lambda: (golden_call("gd_v1", "det_a", "call_smoke_v1.npz"), golden_call("gd_v2", "smoke", "call_smoke_v2.npz")),
-        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbstats": golden_gb_stats, "filters": golden_filters, "qc": golden_qc, "fastq": golden_fastq,
+        "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbgreedy": golden_gb_greedy, "gbstats": golden_gb_stats, "filters": golden_filters, "qc": golden_qc, "fastq": golden_fastq,
         "lod": golden_lod_fit,
         "dist": golden_gd_dist,
     }

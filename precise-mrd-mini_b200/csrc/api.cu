@@ -57,7 +57,7 @@ int32_t k11_fit_lod_batch(pmrd_ctx* ctx, const double* d_af, const double* d_hit
                           int32_t n_boot, const uint64_t* d_stream_ids, double* d_out3);
 int32_t call_counts_dev(pmrd_ctx* ctx, const int64_t* d_tot, const int64_t* d_var, const uint8_t* d_neg, int64_t n_cells,
                         uint64_t stream_id, int32_t test_type, int32_t alternative, double alpha, double* d_mean_rate,
-                        int64_t* d_negc, double* d_p, double* d_q, uint8_t* d_sig);
+                        int64_t* d_negc, double* d_p, double* d_q, uint8_t* d_sig, void* d_bh_workspace);
 int32_t k15_gd_features(pmrd_ctx* ctx, const int64_t* d_size, const double* d_q, const double* d_agr, const double* d_af, int64_t n,
                         double* d_out);
 int32_t k16_qc_family(pmrd_ctx* ctx, const uint32_t* d_size, const uint32_t* d_flags, uint32_t flag_mask, int64_t n, int n_bins,
@@ -844,7 +844,7 @@ int32_t pmrd_call_counts(pmrd_ctx* ctx, const int64_t* h_n_total, const int64_t*
     PMRD_CUDA(ctx, q.alloc(ctx->stream, c * 8));
     PMRD_CUDA(ctx, sig.alloc(ctx->stream, c));
     PMRD_TRY(call_counts_dev(ctx, tot.as<int64_t>(), var.as<int64_t>(), neg.as<uint8_t>(), n_cells, stream_id, test_type, alternative,
-                             alpha, mean.as<double>(), negc.as<int64_t>(), p.as<double>(), q.as<double>(), sig.as<uint8_t>()));
+                             alpha, mean.as<double>(), negc.as<int64_t>(), p.as<double>(), q.as<double>(), sig.as<uint8_t>(), nullptr));
     PMRD_TRY(down(ctx, h_p_value, p.p, c * 8));
     PMRD_TRY(down(ctx, h_p_adjusted, q.p, c * 8));
     PMRD_TRY(down(ctx, h_significant, sig.p, c));

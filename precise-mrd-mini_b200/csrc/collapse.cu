@@ -833,6 +833,70 @@ int32_t k6_hamming(pmrd_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, int6
     return PMRD_OK;
 }
 
+// ---------------------------------------------------------------- K6 greedy --------------
+// Deterministic greedy Hamming clustering (src/precise_mrd/umi_clustering.py:59-101 cluster_umis_greedy, the
+// defined-order form of the loop at src/precise_mrd/umi.py:117-144): per group the UNIQUE UMIs are ordered by
+// (-count, umi); the first unused one seeds a cluster and absorbs every unused UMI within max_distance of the
+// seed (no chaining through absorbed UMIs).  Clusters are numbered in seed order.
+#define GREEDY_NONE 0xffffffffu
+// unique-UMI table of the (group, umi)-sorted reads: sort key group:32 | (2^32 - 1 - count), value = unique index.
+// The uniques are already in (group, umi) order, so a STABLE sort on this key yields (group, -count, umi).
+__global__ void __launch_bounds__(256)
+greedy_uniq_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ useg, int64_t n_uniq, uint64_t* __restrict__ ukey,
+                   uint32_t* __restrict__ uidx) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_uniq) return;
+    const uint32_t count = useg[u + 1] - useg[u];
+    ukey[u] = (sk[useg[u]] & 0xffffffff00000000ull) | (uint64_t)(0xffffffffu - count);
+    uidx[u] = (uint32_t)u;
+}
+// UMIs in seed order (coalesced for the clustering loop) + cluster ids cleared
+__global__ void __launch_bounds__(256)
+greedy_gather_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ useg, const uint32_t* __restrict__ ord, int64_t n_uniq,
+                     uint32_t* __restrict__ sumi, uint32_t* __restrict__ scl) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_uniq) return;
+    sumi[i] = (uint32_t)sk[useg[ord[i]]];
+    scl[i] = GREEDY_NONE;
+}
+// one block per group: seeds in order (sequential by nature), absorption spread over the threads
+__global__ void __launch_bounds__(256)
+greedy_cluster_kernel(const uint32_t* __restrict__ sumi, uint32_t* __restrict__ scl, const uint32_t* __restrict__ gstart, int64_t n_groups,
+                      int max_distance) {
+    const int64_t g = blockIdx.x;
+    if (g >= n_groups) return;
+    const uint32_t lo = gstart[g], hi = gstart[g + 1];
+    uint32_t n_clusters = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+        // every entry before i is used (it was a seed or was absorbed), so only [i, hi) can still join
+        if (((volatile uint32_t*)scl)[i] != GREEDY_NONE) continue;          // uniform: written before the last barrier
+        const uint32_t seed = sumi[i];
+        for (uint32_t j = i + threadIdx.x; j < hi; j += blockDim.x)
+            if (scl[j] == GREEDY_NONE && umi_hamming(seed, sumi[j]) <= max_distance) scl[j] = n_clusters;
+        ++n_clusters;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256)
+greedy_scatter_kernel(const uint32_t* __restrict__ ord, const uint32_t* __restrict__ scl, int64_t n_uniq, uint32_t* __restrict__ ucluster) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_uniq) ucluster[ord[i]] = scl[i];
+}
+// every read, back at its ORIGINAL position, gets the key group:32 | cluster:32 -- a stable sort of those keys then
+// lists each cluster's reads in input order (umi.py:137-140)
+__global__ void __launch_bounds__(256)
+greedy_assign_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict__ si, int64_t n, const uint32_t* __restrict__ useg,
+                     int64_t n_uniq, const uint32_t* __restrict__ ucluster, uint64_t* __restrict__ keys_out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int64_t lo = 0, hi = n_uniq;                   // useg[lo] <= r < useg[hi]
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)useg[mid] <= r) lo = mid; else hi = mid;
+    }
+    keys_out[si[r]] = (sk[r] & 0xffffffff00000000ull) | ucluster[lo];
+}
+
 // ---------------------------------------------------------------- driver ----------------
 template <bool GATHER>
 static int32_t launch_family(pmrd_ctx* ctx, int mode, const uint64_t* keys, const uint32_t* pl_or_idx,
@@ -893,7 +957,7 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
     PMRD_ARG(ctx, params != nullptr, "params");
     const pmrd_umi_params P = *params;
     PMRD_ARG(ctx, P.mode >= 0 && P.mode <= 2, "mode");
-    PMRD_ARG(ctx, P.cluster == PMRD_CLUSTER_EXACT || P.cluster == PMRD_CLUSTER_FIRSTFIT, "cluster");
+    PMRD_ARG(ctx, P.cluster == PMRD_CLUSTER_EXACT || P.cluster == PMRD_CLUSTER_FIRSTFIT || P.cluster == PMRD_CLUSTER_GREEDY, "cluster");
     PMRD_ARG(ctx, ((uintptr_t)d_keys & 15) == 0 && ((uintptr_t)d_keys_tmp & 15) == 0, "key buffers must be 16-byte aligned");
     *n_families = 0;
     if (n_groups) *n_groups = 0;
@@ -917,8 +981,8 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
         PMRD_TRY(read_count(ctx, counts.as<uint32_t>(), &nf));
         if (want_groups) PMRD_TRY(read_count(ctx, counts.as<uint32_t>() + 1, &ng));
     } else {
-        // FIRSTFIT: (1) stable sort read indices by group, (2) sequential first-fit per group,
-        // (3) stable sort by (group, cluster), (4) consensus with gather through the index.
+        // FIRSTFIT / GREEDY: reads get a new key group:32 | cluster:32, a stable sort by that key lists every
+        // cluster's reads in input order, and the consensus kernel gathers the payloads through the index.
         DevBuf gk, idx, idx_tmp, reps, grp_start0, cnt0;
         PMRD_CUDA(ctx, gk.alloc(ctx->stream, (size_t)n_reads * 8));
         PMRD_CUDA(ctx, idx.alloc(ctx->stream, (size_t)n_reads * 4));
@@ -927,29 +991,85 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
         PMRD_CUDA(ctx, grp_start0.alloc(ctx->stream, (size_t)(n_reads + 1) * 4));
         PMRD_CUDA(ctx, cnt0.alloc(ctx->stream, 4));
         const int g256 = pmrd_blocks(n_reads, 256);
-        PMRD_LAUNCH(ctx, iota_kernel, g256, 256, 0, idx.as<uint32_t>(), n_reads);
-        PMRD_LAUNCH(ctx, groupkey_kernel, g256, 256, 0, (const uint64_t*)d_keys, gk.as<uint64_t>(), n_reads);
         uint64_t varying = 0;
-        PMRD_TRY(radix_varying_bits(ctx, gk.as<uint64_t>(), n_reads, &varying));
-        int in_b = 0;
-        PMRD_TRY(radix_sort_pairs(ctx, gk.as<uint64_t>(), idx.as<uint32_t>(), d_keys_tmp, idx_tmp.as<uint32_t>(), n_reads, varying, &in_b));
-        uint64_t* sk = in_b ? d_keys_tmp : gk.as<uint64_t>();
-        uint32_t* si = in_b ? idx_tmp.as<uint32_t>() : idx.as<uint32_t>();
-        uint64_t* ok = in_b ? gk.as<uint64_t>() : d_keys_tmp;
-        uint32_t* oi = in_b ? idx.as<uint32_t>() : idx_tmp.as<uint32_t>();
-        int64_t ng0 = 0;
-        PMRD_TRY(find_segments_dev(ctx, sk, n_reads, nullptr, 32, n_reads, grp_start0.as<uint32_t>(), cnt0.as<uint32_t>()));
-        PMRD_TRY(read_count(ctx, cnt0.as<uint32_t>(), &ng0));
-        // new keys (group | cluster) are written into `ok`, at the same positions as sk/si
-        PMRD_LAUNCH(ctx, firstfit_kernel, pmrd_blocks(ng0 * 32, 128), 128, 0, (const uint64_t*)sk, (const uint32_t*)si,
-                    (const uint64_t*)d_keys, (const uint32_t*)grp_start0.as<uint32_t>(), ng0, P.max_distance,
-                    reps.as<uint32_t>(), ok);
-        // sort (ok, si) by cluster bits; group bits are already in order and constant-digit passes are skipped
-        PMRD_TRY(radix_varying_bits(ctx, ok, n_reads, &varying));
-        int in_b2 = 0;
-        PMRD_TRY(radix_sort_pairs(ctx, ok, si, sk, oi, n_reads, varying, &in_b2));
-        const uint64_t* fk = in_b2 ? sk : ok;
-        const uint32_t* fi = in_b2 ? oi : si;
+        const uint64_t* fk = nullptr;      // sorted (group | cluster) keys ...
+        const uint32_t* fi = nullptr;      // ... and the original index of every read, cluster by cluster in input order
+        if (P.cluster == PMRD_CLUSTER_FIRSTFIT) {
+            // (1) stable sort read indices by group, (2) sequential first-fit per group, (3) stable sort by (group, cluster)
+            PMRD_LAUNCH(ctx, iota_kernel, g256, 256, 0, idx.as<uint32_t>(), n_reads);
+            PMRD_LAUNCH(ctx, groupkey_kernel, g256, 256, 0, (const uint64_t*)d_keys, gk.as<uint64_t>(), n_reads);
+            PMRD_TRY(radix_varying_bits(ctx, gk.as<uint64_t>(), n_reads, &varying));
+            int in_b = 0;
+            PMRD_TRY(radix_sort_pairs(ctx, gk.as<uint64_t>(), idx.as<uint32_t>(), d_keys_tmp, idx_tmp.as<uint32_t>(), n_reads, varying, &in_b));
+            uint64_t* sk = in_b ? d_keys_tmp : gk.as<uint64_t>();
+            uint32_t* si = in_b ? idx_tmp.as<uint32_t>() : idx.as<uint32_t>();
+            uint64_t* ok = in_b ? gk.as<uint64_t>() : d_keys_tmp;
+            uint32_t* oi = in_b ? idx.as<uint32_t>() : idx_tmp.as<uint32_t>();
+            int64_t ng0 = 0;
+            PMRD_TRY(find_segments_dev(ctx, sk, n_reads, nullptr, 32, n_reads, grp_start0.as<uint32_t>(), cnt0.as<uint32_t>()));
+            PMRD_TRY(read_count(ctx, cnt0.as<uint32_t>(), &ng0));
+            // new keys (group | cluster) are written into `ok`, at the same positions as sk/si
+            PMRD_LAUNCH(ctx, firstfit_kernel, pmrd_blocks(ng0 * 32, 128), 128, 0, (const uint64_t*)sk, (const uint32_t*)si,
+                        (const uint64_t*)d_keys, (const uint32_t*)grp_start0.as<uint32_t>(), ng0, P.max_distance,
+                        reps.as<uint32_t>(), ok);
+            // sort (ok, si) by cluster bits; group bits are already in order and constant-digit passes are skipped
+            PMRD_TRY(radix_varying_bits(ctx, ok, n_reads, &varying));
+            int in_b2 = 0;
+            PMRD_TRY(radix_sort_pairs(ctx, ok, si, sk, oi, n_reads, varying, &in_b2));
+            fk = in_b2 ? sk : ok;
+            fi = in_b2 ? oi : si;
+        } else {
+            // GREEDY (umi_clustering.py:59-101).  (1) stable sort read indices by the FULL key: exact-UMI runs;
+            // (2) unique UMIs per group ordered by (-count, umi); (3) sequential seeding per group; (4) every read
+            // gets group | cluster at its original position; (5) stable sort by that key.
+            PMRD_LAUNCH(ctx, iota_kernel, g256, 256, 0, idx.as<uint32_t>(), n_reads);
+            PMRD_CUDA(ctx, cudaMemcpyAsync(gk.p, d_keys, (size_t)n_reads * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            PMRD_TRY(radix_varying_bits(ctx, gk.as<uint64_t>(), n_reads, &varying));
+            int in_b = 0;
+            PMRD_TRY(radix_sort_pairs(ctx, gk.as<uint64_t>(), idx.as<uint32_t>(), d_keys_tmp, idx_tmp.as<uint32_t>(), n_reads, varying, &in_b));
+            uint64_t* sk = in_b ? d_keys_tmp : gk.as<uint64_t>();
+            uint32_t* si = in_b ? idx_tmp.as<uint32_t>() : idx.as<uint32_t>();
+            uint64_t* ok = in_b ? gk.as<uint64_t>() : d_keys_tmp;
+            uint32_t* oi = in_b ? idx.as<uint32_t>() : idx_tmp.as<uint32_t>();
+            uint32_t* useg = grp_start0.as<uint32_t>();
+            int64_t nu = 0;
+            PMRD_TRY(find_segments_dev(ctx, sk, n_reads, nullptr, 0, n_reads, useg, cnt0.as<uint32_t>()));
+            PMRD_TRY(read_count(ctx, cnt0.as<uint32_t>(), &nu));
+            DevBuf uk, uk_tmp, ui, ui_tmp, gst, gcnt, sumi, scl;
+            PMRD_CUDA(ctx, uk.alloc(ctx->stream, (size_t)nu * 8));
+            PMRD_CUDA(ctx, uk_tmp.alloc(ctx->stream, (size_t)nu * 8));
+            PMRD_CUDA(ctx, ui.alloc(ctx->stream, (size_t)nu * 4));
+            PMRD_CUDA(ctx, ui_tmp.alloc(ctx->stream, (size_t)nu * 4));
+            PMRD_CUDA(ctx, gst.alloc(ctx->stream, (size_t)(nu + 1) * 4));
+            PMRD_CUDA(ctx, gcnt.alloc(ctx->stream, 4));
+            PMRD_CUDA(ctx, sumi.alloc(ctx->stream, (size_t)nu * 4));
+            PMRD_CUDA(ctx, scl.alloc(ctx->stream, (size_t)nu * 4));
+            const int u256 = pmrd_blocks(nu, 256);
+            PMRD_LAUNCH(ctx, greedy_uniq_kernel, u256, 256, 0, (const uint64_t*)sk, (const uint32_t*)useg, nu, uk.as<uint64_t>(), ui.as<uint32_t>());
+            uint64_t uvar = 0;
+            PMRD_TRY(radix_varying_bits(ctx, uk.as<uint64_t>(), nu, &uvar));
+            int in_u = 0;
+            PMRD_TRY(radix_sort_pairs(ctx, uk.as<uint64_t>(), ui.as<uint32_t>(), uk_tmp.as<uint64_t>(), ui_tmp.as<uint32_t>(), nu, uvar, &in_u));
+            const uint64_t* suk = in_u ? uk_tmp.as<uint64_t>() : uk.as<uint64_t>();
+            const uint32_t* ord = in_u ? ui_tmp.as<uint32_t>() : ui.as<uint32_t>();
+            int64_t ng0 = 0;
+            PMRD_TRY(find_segments_dev(ctx, suk, nu, nullptr, 32, nu, gst.as<uint32_t>(), gcnt.as<uint32_t>()));
+            PMRD_TRY(read_count(ctx, gcnt.as<uint32_t>(), &ng0));
+            PMRD_LAUNCH(ctx, greedy_gather_kernel, u256, 256, 0, (const uint64_t*)sk, (const uint32_t*)useg, ord, nu, sumi.as<uint32_t>(), scl.as<uint32_t>());
+            PMRD_LAUNCH(ctx, greedy_cluster_kernel, (int)ng0, 256, 0, (const uint32_t*)sumi.as<uint32_t>(), scl.as<uint32_t>(),
+                        (const uint32_t*)gst.as<uint32_t>(), ng0, P.max_distance);
+            uint32_t* ucluster = reps.as<uint32_t>();          // [nu] <= [n_reads]
+            PMRD_LAUNCH(ctx, greedy_scatter_kernel, u256, 256, 0, ord, (const uint32_t*)scl.as<uint32_t>(), nu, ucluster);
+            PMRD_LAUNCH(ctx, greedy_assign_kernel, g256, 256, 0, (const uint64_t*)sk, (const uint32_t*)si, n_reads, (const uint32_t*)useg, nu,
+                        (const uint32_t*)ucluster, ok);
+            PMRD_LAUNCH(ctx, iota_kernel, g256, 256, 0, oi, n_reads);
+            PMRD_TRY(radix_varying_bits(ctx, ok, n_reads, &varying));
+            int in_b2 = 0;
+            PMRD_TRY(radix_sort_pairs(ctx, ok, oi, sk, si, n_reads, varying, &in_b2));
+            fk = in_b2 ? sk : ok;
+            fi = in_b2 ? si : oi;
+            PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // the unique-UMI scratch is released at scope exit
+        }
         PMRD_TRY(find_segments_dev(ctx, fk, n_reads, nullptr, 0, fcap, fam_start.as<uint32_t>(), counts.as<uint32_t>()));
         PMRD_TRY(read_count(ctx, counts.as<uint32_t>(), &nf));
         FamOut out{d_fam->key, d_fam->size, d_fam->n_alt, d_fam->consensus, d_fam->qsum, d_fam->n_best, d_fam->flags};
@@ -962,7 +1082,8 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
                 if (grid < 1) grid = 1;
                 PMRD_LAUNCH(ctx, group_kernel, grid, 128, 0, (const uint64_t*)d_fam->key, (const uint32_t*)d_fam->size,
                             (const uint32_t*)d_fam->n_alt, (const uint32_t*)d_fam->consensus, (const uint32_t*)d_fam->flags,
-                            (const uint32_t*)grp_start.as<uint32_t>(), (const uint32_t*)(counts.as<uint32_t>() + 1), gcap, 0, *d_grp);
+                            (const uint32_t*)grp_start.as<uint32_t>(), (const uint32_t*)(counts.as<uint32_t>() + 1), gcap,
+                            P.mode == PMRD_MODE_WEIGHTED ? 1 : 0, *d_grp);
             }
         }
         PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -128,6 +128,7 @@ struct pmrd_plan {
     DevBuf gg, gf, gc, ga, gt, grp_start, counts, totals;
     DevBuf alt, neg, negc, mean_rate;
     DevBuf o_reads, o_fam, o_tot, o_var, o_p, o_q, o_sig;
+    DevBuf bh_ws;         // BH workspace (sort buffers + scratch): the call stage of a step allocates nothing
     ~pmrd_plan() {
         for (PlanChunk* c : chunks) delete c;
     }
@@ -222,6 +223,7 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     }
     A(P->counts, 8); A(P->totals, 16); A(P->alt, c); A(P->neg, c); A(P->negc, 16); A(P->mean_rate, 8);
     A(P->o_reads, c * 8); A(P->o_fam, c * 8); A(P->o_tot, c * 8); A(P->o_var, c * 8); A(P->o_p, c * 8); A(P->o_q, c * 8); A(P->o_sig, c);
+    A(P->bh_ws, bh_workspace_bytes((int64_t)c));
     uint8_t* h_alt = (uint8_t*)malloc(c * 2);
     if (e == cudaSuccess && h_alt) {
         uint8_t* h_neg = h_alt + c;
@@ -320,17 +322,17 @@ static int32_t plan_reset_outputs(pmrd_ctx* ctx, pmrd_plan* P) {
 // every rank runs it over the all-gathered counts, so the table is the single-GPU one bit for bit).
 int32_t call_counts_dev(pmrd_ctx* ctx, const int64_t* d_tot, const int64_t* d_var, const uint8_t* d_neg, int64_t n_cells,
                         uint64_t stream_id, int32_t test_type, int32_t alternative, double alpha, double* d_mean_rate,
-                        int64_t* d_negc, double* d_p, double* d_q, uint8_t* d_sig) {
+                        int64_t* d_negc, double* d_p, double* d_q, uint8_t* d_sig, void* d_bh_workspace) {
     PMRD_LAUNCH(ctx, error_rate_kernel, 1, 256, 0, ctx->seed, stream_id, d_tot, d_var, d_neg, n_cells, d_mean_rate, d_negc);
     PMRD_TRY(k8_pvalues(ctx, d_var, d_tot, d_mean_rate, 0, n_cells, test_type, alternative, d_p));
-    PMRD_TRY(k9_bh(ctx, d_p, n_cells, alpha, d_sig, d_q));
+    PMRD_TRY(k9_bh(ctx, d_p, n_cells, alpha, d_sig, d_q, d_bh_workspace));
     return PMRD_OK;
 }
 
 int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
     return call_counts_dev(ctx, P->o_tot.as<int64_t>(), P->o_var.as<int64_t>(), P->neg.as<uint8_t>(), P->n_cells, P->stream_id,
                            P->test_type, P->alternative, P->alpha, P->mean_rate.as<double>(), P->negc.as<int64_t>(),
-                           P->o_p.as<double>(), P->o_q.as<double>(), P->o_sig.as<uint8_t>());
+                           P->o_p.as<double>(), P->o_q.as<double>(), P->o_sig.as<uint8_t>(), P->bh_ws.p);
 }
 
 // Stage entry points for per-stage timing.  With more than one chunk the read buffers are

@@ -179,28 +179,44 @@ bh_apply_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ 
     }
 }
 
-int32_t k9_bh(pmrd_ctx* ctx, const double* d_p, int64_t m, double alpha, uint8_t* d_rejected, double* d_q) {
+// Workspace of one BH run over up to m tests.  A plan owns one, so that its step allocates nothing, copies nothing
+// between host and device and never synchronises (the pmrd_plan contract; it also keeps the step graph-capturable).
+size_t bh_workspace_bytes(int64_t m) {
+    if (m < 1) m = 1;
+    const size_t a = ((size_t)m * 8 + 255) & ~(size_t)255, b = ((size_t)m * 4 + 255) & ~(size_t)255;
+    const size_t tiles = (size_t)((m + BH_TILE - 1) / BH_TILE);
+    return 2 * a + 2 * b + ((tiles * 8 + 255) & ~(size_t)255) + 256 + radix_scratch_bytes(m);
+}
+
+int32_t k9_bh(pmrd_ctx* ctx, const double* d_p, int64_t m, double alpha, uint8_t* d_rejected, double* d_q, void* d_workspace) {
     if (m <= 0) return PMRD_OK;
     PMRD_ARG(ctx, m < (1ll << 31), "BH: m must be < 2^31");
-    DevBuf ka, kb, va, vb, tmin, kstar;
-    PMRD_CUDA(ctx, ka.alloc(ctx->stream, (size_t)m * 8));
-    PMRD_CUDA(ctx, kb.alloc(ctx->stream, (size_t)m * 8));
-    PMRD_CUDA(ctx, va.alloc(ctx->stream, (size_t)m * 4));
-    PMRD_CUDA(ctx, vb.alloc(ctx->stream, (size_t)m * 4));
-    PMRD_LAUNCH(ctx, bh_pack_kernel, pmrd_blocks(m, 256), 256, 0, d_p, m, ka.as<uint64_t>(), va.as<uint32_t>());
-    uint64_t varying = 0;
-    PMRD_TRY(radix_varying_bits(ctx, ka.as<uint64_t>(), m, &varying));
-    int in_b = 0;
-    PMRD_TRY(radix_sort_pairs(ctx, ka.as<uint64_t>(), va.as<uint32_t>(), kb.as<uint64_t>(), vb.as<uint32_t>(), m, varying, &in_b));
-    const uint64_t* keys = in_b ? kb.as<uint64_t>() : ka.as<uint64_t>();
-    const uint32_t* idx = in_b ? vb.as<uint32_t>() : va.as<uint32_t>();
+    const size_t a = ((size_t)m * 8 + 255) & ~(size_t)255, b = ((size_t)m * 4 + 255) & ~(size_t)255;
     const int n_tiles = (int)((m + BH_TILE - 1) / BH_TILE);
-    PMRD_CUDA(ctx, tmin.alloc(ctx->stream, (size_t)n_tiles * 8));
-    PMRD_CUDA(ctx, kstar.alloc(ctx->stream, 8));
-    PMRD_CUDA(ctx, cudaMemsetAsync(kstar.p, 0, 8, ctx->stream));
-    PMRD_LAUNCH(ctx, bh_tile_kernel, n_tiles, BH_THREADS, 0, keys, m, alpha, tmin.as<double>(), kstar.as<unsigned long long>());
-    PMRD_LAUNCH(ctx, bh_suffix_kernel, 1, 256, 0, tmin.as<double>(), n_tiles);
-    PMRD_LAUNCH(ctx, bh_apply_kernel, n_tiles, BH_THREADS, 0, keys, idx, m, (const double*)tmin.as<double>(),
-                (const unsigned long long*)kstar.as<unsigned long long>(), d_rejected, d_q);
+    DevBuf own;
+    if (!d_workspace) PMRD_CUDA(ctx, own.alloc(ctx->stream, bh_workspace_bytes(m)));
+    unsigned char* w = d_workspace ? (unsigned char*)d_workspace : own.as<unsigned char>();
+    uint64_t* ka = (uint64_t*)w; w += a;
+    uint64_t* kb = (uint64_t*)w; w += a;
+    uint32_t* va = (uint32_t*)w; w += b;
+    uint32_t* vb = (uint32_t*)w; w += b;
+    double* tmin = (double*)w; w += ((size_t)n_tiles * 8 + 255) & ~(size_t)255;
+    unsigned long long* kstar = (unsigned long long*)w; w += 256;
+    uint32_t* rs_scratch = (uint32_t*)w;
+    PMRD_LAUNCH(ctx, bh_pack_kernel, pmrd_blocks(m, 256), 256, 0, d_p, m, ka, va);
+    // Digit windows: with a caller-owned workspace (plans) the mask is FIXED -- p lies in [0, 1], so its bit pattern
+    // is at most 0x3FF0...0 and bits 0..61 may vary: no reduction, no device -> host copy, no sync.  Otherwise the
+    // varying bits are measured first (one sync; fewer passes for the host-buffer entry points).
+    uint64_t varying = (1ull << 62) - 1ull;
+    if (!d_workspace) PMRD_TRY(radix_varying_bits(ctx, ka, m, &varying));
+    int in_b = 0;
+    PMRD_TRY(radix_sort_pairs(ctx, ka, va, kb, vb, m, varying, &in_b, rs_scratch));
+    const uint64_t* keys = in_b ? kb : ka;
+    const uint32_t* idx = in_b ? vb : va;
+    PMRD_CUDA(ctx, cudaMemsetAsync(kstar, 0, 8, ctx->stream));
+    PMRD_LAUNCH(ctx, bh_tile_kernel, n_tiles, BH_THREADS, 0, keys, m, alpha, tmin, kstar);
+    PMRD_LAUNCH(ctx, bh_suffix_kernel, 1, 256, 0, tmin, n_tiles);
+    PMRD_LAUNCH(ctx, bh_apply_kernel, n_tiles, BH_THREADS, 0, keys, idx, m, (const double*)tmin, (const unsigned long long*)kstar,
+                d_rejected, d_q);
     return PMRD_OK;
 }

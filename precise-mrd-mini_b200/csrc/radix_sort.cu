@@ -564,8 +564,16 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
 }
 
 // ---------------------------------------------------------------- driver ----------------
+size_t radix_scratch_bytes(int64_t n) {
+    const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    int64_t chunk = 1;
+    while (chunk * chunk < n_tiles) ++chunk;
+    const int64_t n_chunks = chunk > 0 ? (n_tiles + chunk - 1) / chunk : 0;
+    return (size_t)(n_tiles + n_chunks + 2) * RS_MAX_BINS * sizeof(uint32_t);
+}
+
 int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
-                         int64_t n, uint64_t varying, int* in_b) {
+                         int64_t n, uint64_t varying, int* in_b, uint32_t* d_scratch) {
     *in_b = 0;
     if (n <= 1) return PMRD_OK;
     PMRD_ARG(ctx, n < (1ll << 32) - RS_TILE, "radix_sort_pairs: n must be < 2^32 (chunk the input)");
@@ -577,9 +585,14 @@ int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint
     while ((int64_t)chunk * chunk < n_tiles) ++chunk;
     const int n_chunks = (n_tiles + chunk - 1) / chunk;
 
-    DevBuf hist, colsum;
-    PMRD_CUDA(ctx, hist.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
-    PMRD_CUDA(ctx, colsum.alloc(ctx->stream, (size_t)n_chunks * 256 * sizeof(uint32_t)));
+    // caller-owned scratch (radix_scratch_bytes(n)): nothing is allocated here (plans: allocation-free steps)
+    DevBuf hist_own, colsum_own;
+    if (!d_scratch) {
+        PMRD_CUDA(ctx, hist_own.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
+        PMRD_CUDA(ctx, colsum_own.alloc(ctx->stream, (size_t)n_chunks * 256 * sizeof(uint32_t)));
+    }
+    uint32_t* const hist = d_scratch ? d_scratch : hist_own.as<uint32_t>();
+    uint32_t* const colsum = d_scratch ? d_scratch + (size_t)n_tiles * RS_MAX_BINS : colsum_own.as<uint32_t>();
 
     PMRD_TRY(rs_set_attrs(ctx));
 
@@ -590,16 +603,16 @@ int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint
     for (int p = 0; p < plan.n_passes; ++p) {
         const int shift = plan.shift[p];
         const uint32_t mask = (1u << plan.bits[p]) - 1u;
-        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist.as<uint32_t>(), shift, mask);
-        PMRD_LAUNCH(ctx, rs_colsum_kernel, n_chunks, 256, 0, hist.as<uint32_t>(), n_tiles, chunk, colsum.as<uint32_t>());
-        PMRD_LAUNCH(ctx, rs_colbase_kernel, 1, 256, 0, colsum.as<uint32_t>(), n_chunks);
-        PMRD_LAUNCH(ctx, rs_colapply_kernel, n_chunks, 256, 0, hist.as<uint32_t>(), n_tiles, chunk, colsum.as<uint32_t>());
+        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist, shift, mask);
+        PMRD_LAUNCH(ctx, rs_colsum_kernel, n_chunks, 256, 0, hist, n_tiles, chunk, colsum);
+        PMRD_LAUNCH(ctx, rs_colbase_kernel, 1, 256, 0, colsum, n_chunks);
+        PMRD_LAUNCH(ctx, rs_colapply_kernel, n_chunks, 256, 0, hist, n_tiles, chunk, colsum);
         if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout,
-                        hist.as<uint32_t>(), n, shift, mask);
+                        hist, n, shift, mask);
         } else {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout,
-                        hist.as<uint32_t>(), n, shift, mask);
+                        hist, n, shift, mask);
         }
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;

@@ -51,8 +51,10 @@ RadixPlan radix_make_plan(uint64_t varying);
 // Sorts; on return *in_b tells whether the result lives in (keys_b, vals_b).  vals may be
 // NULL (keys only).  `varying` = mask of key bits that differ across the input (pass ~0ull
 // to sort on every bit).
+// d_scratch (optional): radix_scratch_bytes(n) bytes owned by the caller -- the sort then allocates nothing.
 int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
-                         int64_t n, uint64_t varying, int* in_b);
+                         int64_t n, uint64_t varying, int* in_b, uint32_t* d_scratch = nullptr);
+size_t radix_scratch_bytes(int64_t n);
 int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                                    int64_t n, const int64_t* d_cell_tile_start, int64_t n_cells, int key_bits, int* in_b,
                                    uint32_t* d_hist0 = nullptr);

@@ -21,7 +21,7 @@ ERR_CUDA, ERR_ARG, ERR_CAPACITY, ERR_NO_DEVICE = -1, -2, -3, -4
 TEST_POISSON, TEST_BINOMIAL = 0, 1
 ALT_TWO_SIDED, ALT_GREATER, ALT_LESS = 0, 1, 2
 MODE_WEIGHTED, MODE_MAJORITY, MODE_COUNT = 0, 1, 2
-CLUSTER_EXACT, CLUSTER_FIRSTFIT = 0, 1
+CLUSTER_EXACT, CLUSTER_FIRSTFIT, CLUSTER_GREEDY = 0, 1, 2
 FAM_HAS_CONSENSUS, FAM_KEPT, FAM_OVERSIZE = 1, 2, 4
 
 TEST_TYPES = {"poisson": TEST_POISSON, "binomial": TEST_BINOMIAL}

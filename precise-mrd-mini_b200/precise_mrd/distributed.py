@@ -94,6 +94,13 @@ def run_cells_sharded(config, cell_id, allele_fraction, n_families, neg_af_max: 
     st = section(config, "stats")
     if st["test_type"] not in nv.TEST_TYPES:
         raise ValueError(f"Unknown test type: {st['test_type']}")      # call.py:187
+    if len(cell_id) == 0:                                              # empty grid: an empty table on every rank
+        out = {k: np.zeros(0, np.int64) for k in ("n_total", "n_variants", "n_families", "n_reads")}
+        out["negative_control"] = np.zeros(0, bool)
+        if compute is None and finish:
+            out.update({"p_value": np.zeros(0), "p_adjusted": np.zeros(0), "significant": np.zeros(0, bool),
+                        "variant_call": np.zeros(0, bool), "mean_error_rate": 0.0})
+        return out
     mine = shard_cells(nf, rank, world)
     on_device = compute is None
     if on_device:

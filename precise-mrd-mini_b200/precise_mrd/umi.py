@@ -51,13 +51,18 @@ class UMIFamily:
 
 
 class UMIProcessor:
-    """``src/precise_mrd/umi.py:50-285`` with ``max_edit_distance == 0`` semantics.
+    """``src/precise_mrd/umi.py:50-285``.
 
-    (Greedy Hamming clustering in the reference iterates ``list(set(...))`` of strings and is
-    therefore hash-order dependent -- SURVEY.md §0.3-3 -- so only exact-UMI grouping has a
-    defined result to be bit-exact with.)"""
+    ``max_edit_distance == 0``: exact-UMI families (``umi.py:111-115``).  ``max_edit_distance > 0`` (the
+    reference's default, ``configs/default.yaml:16``): greedy Hamming clustering.  The reference loop
+    (``umi.py:117-144``) iterates ``list(set(...))`` of strings, so its result depends on the process's
+    hash seed; the iteration order is DEFINED here as that of the reference's own
+    deterministic form, ``umi_clustering.py:59-101`` (``cluster_umis_greedy``): unique UMIs by
+    ``(-count, umi)``, the first unused one seeds a cluster and absorbs every unused UMI within the
+    distance.  Families come back in the reference's order: sites by first appearance, then UMIs by
+    first appearance (exact) / clusters in seed order (greedy)."""
 
-    def __init__(self, min_family_size: int = 3, max_family_size: int = 1000, max_edit_distance: int = 0,
+    def __init__(self, min_family_size: int = 3, max_family_size: int = 1000, max_edit_distance: int = 1,
                  quality_threshold: int = 20, consensus_threshold: float = 0.6):
         if min_family_size < 1:
             raise ValueError("min_family_size must be at least 1")
@@ -69,8 +74,6 @@ class UMIProcessor:
             raise ValueError("quality_threshold must be between 0 and 60")
         if not 0.0 < consensus_threshold <= 1.0:
             raise ValueError("consensus_threshold must be between 0.0 and 1.0")
-        if max_edit_distance != 0:
-            raise NotImplementedError("only exact UMI matching is reproducible in the reference (SURVEY.md §0.3-3)")
         self.min_family_size, self.max_family_size = min_family_size, max_family_size
         self.max_edit_distance, self.quality_threshold = max_edit_distance, quality_threshold
         self.consensus_threshold = consensus_threshold
@@ -102,23 +105,42 @@ class UMIProcessor:
         payload = allele | (q << np.uint32(2)) | (strand << np.uint32(8)) | (rp << np.uint32(9))
         return key, payload.astype(np.uint32), list(sites), umi_len
 
+    def collapse_packed(self, key: np.ndarray, payload: np.ndarray, umi_len: int = 12):
+        """Device collapse of packed reads with this processor's thresholds; returns the family and group tables
+        with the families in the reference's order (see the class docstring) and a ``first_read`` column."""
+        greedy = self.max_edit_distance > 0
+        params = nv.UmiParams(min_family_size=self.min_family_size, max_family_size=self.max_family_size,
+                              quality_threshold=self.quality_threshold, consensus_threshold=self.consensus_threshold,
+                              mode=nv.MODE_WEIGHTED, cluster=nv.CLUSTER_GREEDY if greedy else nv.CLUSTER_EXACT,
+                              max_distance=self.max_edit_distance, umi_len=umi_len)
+        fam, grp = nv.default_context().collapse_reads(key, payload, params)
+        if not greedy and len(fam["key"]):
+            # exact families arrive sorted by (site, packed UMI); the reference lists a site's UMIs in insertion
+            # order (umi.py:111-115, dict order): reorder by each family's first read
+            uniq, first = np.unique(key, return_index=True)
+            assert len(uniq) == len(fam["key"])
+            order = np.lexsort((first, fam["key"] >> np.uint64(32)))
+            fam = {k: v[order] for k, v in fam.items()}
+            fam["first_read"] = first[order]
+        return fam, grp
+
     def process_reads(self, reads) -> List[UMIFamily]:
         """``umi.py:205-239``: group by site, group by UMI, call consensus, filter family size."""
         if reads is None or len(reads) == 0:
             return []
         key, payload, sites, umi_len = self.pack_reads(reads)
-        params = nv.UmiParams(min_family_size=self.min_family_size, max_family_size=self.max_family_size,
-                              quality_threshold=self.quality_threshold, consensus_threshold=self.consensus_threshold,
-                              mode=nv.MODE_WEIGHTED, cluster=nv.CLUSTER_EXACT, max_distance=0, umi_len=umi_len)
-        fam, self._groups = nv.default_context().collapse_reads(key, payload, params)
+        fam, self._groups = self.collapse_packed(key, payload, umi_len)
         self._sites = sites
         out = []
         kept = (fam["flags"] & nv.FAM_KEPT) != 0
         for i in np.flatnonzero(kept):
             has = bool(fam["flags"][i] & nv.FAM_HAS_CONSENSUS)
+            # filter_family_size (umi.py:190-199) caps an oversize family at max_family_size reads (which reads it
+            # keeps is drawn from the global NumPy RNG there -- SURVEY.md App. A #10; the consensus was called before)
             out.append(UMIFamily(
                 umi=unpack_bases(int(fam["key"][i]) & 0xFFFFFFFF, umi_len), site_key=sites[int(fam["key"][i]) >> 32],
-                family_size=int(fam["size"][i]), consensus_allele=BASES[int(fam["consensus"][i])] if has else None,
+                family_size=min(int(fam["size"][i]), self.max_family_size),
+                consensus_allele=BASES[int(fam["consensus"][i])] if has else None,
                 consensus_quality=(float(fam["qsum"][i]) / float(fam["n_best"][i])) if has else None,
                 n_alt_reads=int(fam["n_alt"][i])))
         return out

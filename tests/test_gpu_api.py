@@ -46,8 +46,11 @@ def test_call_mrd_dataframe_api_on_reference_fixture(ctx, golden, smoke_cfg, nam
                                    "fold_change", "p_value", "mean_quality", "mean_consensus", "test_type", "config_hash",
                                    "p_adjusted", "significant", "alpha", "fdr_method", "variant_call"]
     assert calls["n_variants"].dtype == np.int64 and calls["significant"].dtype == bool
-    for col in ("n_variants", "n_total", "significant", "sample_id", "allele_fraction"):
-        assert (calls[col].values == g[f"want_{col}"] if col.startswith(("n_", "sig")) else True).all() if col in ("n_variants", "n_total", "significant") else True
+    for col in ("n_variants", "n_total", "significant"):                           # bit-exact columns
+        assert (calls[col].values == g[f"want_{col}"]).all(), col
+    # one row per sample in first-appearance order, carrying the sample's own allele fraction (call.py:161-170)
+    assert (calls["sample_id"].values == g["sample_id"]).all()
+    assert (calls["allele_fraction"].values == g["allele_fraction"]).all()
     for col in ("variant_fraction", "expected_variants", "fold_change", "p_value", "p_adjusted", "mean_quality", "mean_consensus"):
         assert _rel(calls[col].values, g[f"want_{col}"]).max() < 1e-12, col
     assert (calls["variant_call"] == calls["significant"]).all()
@@ -172,7 +175,35 @@ def test_read_level_dataframe_apis_vs_reference_golden(ctx, golden):
         k = (int(f.site_key.split(":")[0][3:]) << 32) | int(sum("ACGT".index(b) << (2 * (11 - i)) for i, b in enumerate(f.umi)))
         if f.consensus_quality is not None:
             assert f.consensus_quality == want_q[k]
+    # families come back in the reference's order: sites by first appearance, UMIs by insertion order (umi.py:97-115)
+    def fkey(f):
+        return (int(f.site_key.split(":")[0][3:]) << 32) | int(sum("ACGT".index(b) << (2 * (11 - i)) for i, b in enumerate(f.umi)))
+    assert [fkey(f) for f in fams] == [int(k) for k in g["want_fam_key"][g["want_fam_size"] >= 3]]
+    assert [f.family_size for f in fams] == [int(v) for v in g["want_fam_size"][g["want_fam_size"] >= 3]]
+    # filter_family_size caps an oversize family at max_family_size reads (umi.py:190-199)
+    capped = UMIProcessor(min_family_size=3, max_family_size=6, max_edit_distance=0).process_reads(reads)
+    assert len(capped) == len(fams) and max(f.family_size for f in capped) == 6 < max(f.family_size for f in fams)
     assert proc.edit_distance("ACGTACGTACGT", "ACGTACGTACGA") == 1 and proc.edit_distance("ACG", "ACGT") == 4
+
+    # the reference's DEFAULT: max_edit_distance = 1 (configs/default.yaml:16) -- greedy Hamming clusters, listed as
+    # umi_clustering.py:59-101 seeds them; reference-generated vectors (oracle/make_golden.py gbgreedy)
+    g = golden("gb_greedy.npz")
+    keys, pl = g["keys"], g["payload"]
+    site = (keys >> np.uint64(32)).astype(np.int64)
+    reads = pd.DataFrame({"chrom": "chr" + pd.Series(site).astype(str), "pos": 1000 + site, "ref": "A",
+                          "alt": ["ACGT"[int(p) & 3] for p in pl], "umi": [unpack_bases(int(k) & 0xFFFFFF, 12) for k in keys],
+                          "quality": ((pl >> 2) & 63).astype(int), "strand": np.where((pl >> 8) & 1, "+", "-"),
+                          "read_position": ((pl >> 9) & 255).astype(int)})
+    default = UMIProcessor()
+    assert default.max_edit_distance == 1
+    fams = default.process_reads(reads)
+    keep = g["want_fam_size_d1"] >= 3
+    assert [fkey(f) for f in fams] == [int(k) for k in g["want_fam_key_d1"][keep]]
+    assert [f.family_size for f in fams] == [int(v) for v in g["want_fam_size_d1"][keep]]
+    want_allele = g["want_fam_allele_d1"][keep]
+    assert [(-1 if f.consensus_allele is None else "ACGT".index(f.consensus_allele)) for f in fams] == [int(a) for a in want_allele]
+    wq = g["want_fam_quality_d1"][keep]
+    assert all(f.consensus_quality == q for f, q in zip(fams, wq) if f.consensus_allele is not None)
     with pytest.raises(ValueError):
         UMIProcessor(min_family_size=0)
 

@@ -65,6 +65,43 @@ def test_c2_conservation_and_shape(c2):
     assert res["significant"][af <= 1e-4].mean() < 0.6 < res["significant"][af >= 0.01].mean() and 0.0 < res["mean_error_rate"] < 0.1
 
 
+def test_c2_strided_cells_equal_the_oracle(ctx, native, c2):
+    """Oracle comparison AT C2 CELL SIZES: a strided sample of the real grid's cells (every depth 5k / 10k / 20k / 50k,
+    every AF, 48 cells; the 50 000-family cells span 61 tiles, so their families straddle many tile boundaries and the
+    four-range cell scan runs).  The plan's own reads of each cell (``simulate_reads(shuffle=2)`` = the cell-major
+    order the sort sees, first-seen tie-breaks included) go through the C restatement of the reference
+    (``oracle/pmrd_oracle.c``: umi.py:97-203), and the three per-cell counts of the full 20 000-cell run must be
+    bit-equal to it."""
+    from oracle import cport
+
+    af, depth, cid, res, cfg = c2["af"], c2["depth"], c2["cell_id"], c2["res"], c2["cfg"]
+    # cells are AF-major, then depth, then 1000 replicates: stride 419 (coprime to 1000) walks every (AF, depth) stratum
+    sel = np.arange(7, len(depth), 419)[:48]
+    strata = {(a, d) for a, d in zip(af[sel], depth[sel])}
+    assert len(strata) >= 18 and (depth[sel] == 50000).sum() >= 8
+    sp2 = c2["grid"].read_sim_params(cfg, mean_family_size=5.0, family_model=1)
+    sp2.shuffle = 2
+    u = cfg.umi
+    checked = 0
+    for lo in range(0, len(sel), 8):                       # 8 cells (~1e6 reads) per round trip
+        s = sel[lo:lo + 8]
+        keys, pl = ctx.simulate_reads(cid[s], af[s], depth[s], sp2)
+        assert len(keys) == res["n_reads"][s].sum()
+        fam = cport.collapse_weighted(keys, pl, int(u.min_family_size), int(u.max_family_size), int(u.quality_threshold),
+                                      float(u.consensus_threshold))
+        g = (fam["key"] >> np.uint64(32)).astype(np.int64)              # group = position of the cell in the sub-batch
+        alt = ((cid[s] & 3) + 1 + ((cid[s] >> 2) % 3)) & 3
+        ok = (fam["flags"] & 3) == 3                                    # has consensus and kept (>= min_family_size)
+        n_fam = np.bincount(g, minlength=len(s))
+        n_tot = np.bincount(g[ok], minlength=len(s))
+        n_var = np.bincount(g[ok & (fam["consensus"] == alt[g])], minlength=len(s))
+        assert (res["n_families"][s] == n_fam).all(), (lo, res["n_families"][s], n_fam)
+        assert (res["n_total"][s] == n_tot).all(), (lo, res["n_total"][s], n_tot)
+        assert (res["n_variants"][s] == n_var).all(), (lo, res["n_variants"][s], n_var)
+        checked += len(keys)
+    assert checked > 5_000_000
+
+
 def test_c2_idempotent_and_chunking_invariant(ctx, native, c2):
     """Same plan twice -> identical table; a 4x finer chunking -> identical table."""
     plan, res = c2["plan"], c2["res"]

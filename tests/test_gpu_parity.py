@@ -267,6 +267,44 @@ def test_collapse_gb_weighted_vs_reference(ctx, golden, native):
     _assert_tables_equal(fam, grp, wfam, wgrp)
 
 
+@pytest.mark.parametrize("d", [1, 2])
+def test_collapse_gb_greedy_clusters_vs_reference(ctx, golden, native, d):
+    """K6 greedy (max_edit_distance > 0, the reference's default): the device clusters equal the reference's
+    cluster_umis_greedy (umi_clustering.py:59-101) cluster for cluster and in its order; consensus per cluster
+    over the reads in input order (umi.py:137-140) bit-exact; also equal to the port on every column."""
+    from test_oracle_golden import check_greedy_tables_against_reference
+
+    g = golden("gb_greedy.npz")
+    mn, mx, qthr = [int(v) for v in g["params"]]
+    P = _params(native, min_family_size=mn, max_family_size=mx, quality_threshold=qthr, consensus_threshold=float(g["consensus_threshold"]),
+                mode=native.MODE_WEIGHTED, cluster=native.CLUSTER_GREEDY, max_distance=d, umi_len=12)
+    fam, grp = ctx.collapse_reads(g["keys"], g["payload"], P)
+    check_greedy_tables_against_reference(fam, g, d, native.FAM_HAS_CONSENSUS)
+    wfam, wgrp = port.collapse_greedy(g["keys"], g["payload"], 0, mn, mx, d, qthr, float(g["consensus_threshold"]))
+    _assert_tables_equal(fam, grp, wfam, wgrp)
+
+
+@pytest.mark.parametrize("n,n_groups,umi_space", [(1, 1, 4), (7, 2, 3), (5000, 3, 1 << 9), (40_000, 50, 1 << 12), (30_000, 1, 1 << 13)])
+def test_collapse_greedy_vs_oracle_random(ctx, native, n, n_groups, umi_space):
+    """Random reads, dense barcode neighbourhoods (equal-count ties, chains the greedy rule cuts, one group with
+    thousands of unique UMIs): every mode, distances 0-2, against the port."""
+    rng = np.random.default_rng(n + n_groups)
+    groups = rng.integers(0, n_groups, n, dtype=np.uint64) * np.uint64(17)
+    umis = np.where(rng.random(n) < 0.5, rng.zipf(1.6, n).astype(np.uint64) % np.uint64(umi_space),     # skewed counts ...
+                    rng.integers(0, umi_space, n, dtype=np.uint64))                                  # ... + many singletons
+    keys = (groups << np.uint64(32)) | umis
+    payload = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    q = rng.choice([5, 10, 20, 20, 30, 30, 30, 37, 40], n).astype(np.uint32)
+    wpay = (payload & np.uint32(0xFFFFFF03)) | (q << np.uint32(2))
+    for mode, d in ((0, 1), (0, 2), (1, 1), (2, 0)):
+        pl = wpay if mode == 0 else payload
+        P = _params(native, min_family_size=2, max_family_size=50, quality_threshold=20, consensus_threshold=0.6, mode=mode,
+                    cluster=native.CLUSTER_GREEDY, max_distance=d, umi_len=7)
+        fam, grp = ctx.collapse_reads(keys, pl, P)
+        wfam, wgrp = port.collapse_greedy(keys, pl, mode, 2, 50, d, 20, 0.6)
+        _assert_tables_equal(fam, grp, wfam, wgrp)
+
+
 @pytest.mark.parametrize("n", [0, 1, 5, 4097, 60_000])
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_collapse_exact_vs_oracle_random(ctx, native, n, mode):

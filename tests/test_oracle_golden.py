@@ -99,6 +99,33 @@ def test_gb_weighted_consensus_matches_reference(golden):
     assert (grp["consensus_count"] == g["want_consensus_count"][grp["group"]]).all()
 
 
+def check_greedy_tables_against_reference(fam, g, d, has_flag):
+    """Family table of a greedy-clustered collapse (group-major, seed order) vs the reference-generated vectors."""
+    assert len(fam["key"]) == len(g[f"want_fam_key_d{d}"])
+    assert (fam["key"] == g[f"want_fam_key_d{d}"]).all()           # same clusters, same order, same first-read UMI
+    assert (fam["size"] == g[f"want_fam_size_d{d}"]).all()
+    has = (fam["flags"] & has_flag) != 0
+    want_allele = g[f"want_fam_allele_d{d}"]
+    assert (has == (want_allele >= 0)).all()
+    assert (fam["consensus"][has] == want_allele[has]).all()
+    assert (fam["qsum"][has] / fam["n_best"][has] == g[f"want_fam_quality_d{d}"][has]).all()
+
+
+@pytest.mark.parametrize("d", [1, 2])
+def test_gb_greedy_clustering_matches_reference(golden, d):
+    """max_edit_distance > 0 (configs/default.yaml:16): the port's greedy Hamming clustering equals the reference's
+    cluster_umis_greedy (umi_clustering.py:59-101) cluster for cluster, in its order, consensus included."""
+    g = golden("gb_greedy.npz")
+    mn, mx, qthr = [int(v) for v in g["params"]]
+    fam, grp = port.collapse_greedy(g["keys"], g["payload"], 0, mn, mx, d, qthr, float(g["consensus_threshold"]))
+    check_greedy_tables_against_reference(fam, g, d, port.FAM_HAS_CONSENSUS)
+    assert (g[f"want_cluster_umis_d{d}"] > 1).sum() > 1000         # the fixture does merge barcodes
+    # distance 0 degenerates to exact matching
+    f0, g0 = port.collapse_greedy(g["keys"], g["payload"], 0, mn, mx, 0, qthr, float(g["consensus_threshold"]))
+    e0, ge0 = port.collapse_exact(g["keys"], g["payload"], 0, mn, mx, qthr, float(g["consensus_threshold"]))
+    assert sorted(f0["key"].tolist()) == e0["key"].tolist() and (g0["consensus_count"] == ge0["consensus_count"]).all()
+
+
 def test_c_oracle_collapse_matches_reference_and_port(golden):
     """oracle/pmrd_oracle.c (the cpu_baseline port) reproduces the reference-generated G-B fixture."""
     from oracle import cport
