@@ -325,17 +325,22 @@ def main() -> int:
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launch_count
-    ctx.profile_enable(True)
     with ClockSampler(local_rank) as clocks:
         ev0.record(stream)
         for _ in range(args.steps):
             plan.run()
         ev1.record(stream)
         barrier()
-    prof = ctx.profile_report()
-    ctx.profile_enable(False)
     launches = ctx.launch_count - launches0
     ms = ev0.elapsed_time(ev1)
+    # per-kernel breakdown: a SEPARATE pass of the same K steps with per-launch CUDA events (pmrd_profile_enable) --
+    # the event pairs cost device time, so they stay out of the region `value` is timed over
+    ctx.profile_enable(True)
+    for _ in range(args.steps):
+        plan.run()
+    barrier()
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
     res = plan.results()
     chunk_reads = [plan.chunk_reads(i) for i in range(plan.n_chunks)]
     n_chunks = plan.n_chunks

@@ -23,6 +23,7 @@ parity tests can run where the reference cannot travel.
   gb_filters.json                         G-B QualityFilter (Fisher strand bias, end-repair, depth, quality) on a seeded table
   fastq_mixed.fastq / fastq_mixed.json    a synthetic FASTQ with every header convention and parser edge
                                           case + the reference's read list / family table / validation for it
+  contam_ref.json                         ContaminationSimulator.simulate_contamination_effects (reduced sweep) of the reference
   lod_fit.npz                             LODAnalyzer._fit_detection_curve/_bootstrap_lod_ci on given vectors
   gd_dist.npz                             distribution samples from the reference simulate/collapse (KS targets)
 """
@@ -615,6 +616,52 @@ def golden_fastq() -> None:
     print("  wrote fastq_mixed.fastq / .json:", len(reads), "reads,", len(out["table_all"]["umi"]), "families, format", out["format"])
 
 
+# ------------------------------------------------------------------------------- contamination (C4)
+def golden_contam() -> None:
+    """The reference's own ContaminationSimulator (src/precise_mrd/sim/contamination.py:33-311, G-D v1 snapshot) on a
+    reduced sweep: 2 rates per kind x AF {0.001, 0.01} x depth 1000 x 2 replicates.  call_mrd is wrapped to add the
+    `variant_call` column the reference never produces -- without it every eval-* command dies on
+    a KeyError.  Output: tests/golden/contam_ref.json (the result dict, keys stringified)."""
+    import json
+
+    _import_ref("gd_v1")
+    import precise_mrd.call as ref_call
+    import precise_mrd.sim.contamination as ref_contam
+    from precise_mrd.config import load_config
+
+    real = ref_call.call_mrd
+
+    def call_with_variant_call(*a, **k):
+        df = real(*a, **k)
+        if len(df) and "variant_call" not in df:
+            df["variant_call"] = df["significant"]
+        return df
+
+    ref_contam.call_mrd = call_with_variant_call
+    cfg = load_config(REF / "configs" / "smoke.yaml")
+    args = dict(hop_rates=[0.0, 0.01], barcode_collision_rates=[0.0, 0.001], cross_sample_proportions=[0.0, 0.1],
+                af_test_values=[0.001, 0.01], depth_values=[1000], n_replicates=2)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sim = ref_contam.ContaminationSimulator(cfg, np.random.default_rng(cfg.seed))
+        res = sim.simulate_contamination_effects(**args)
+
+    def clean(o):
+        if isinstance(o, dict):
+            return {str(k): clean(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return [clean(v) for v in o]
+        if isinstance(o, (np.floating, np.integer)):
+            return o.item()
+        return o
+
+    with open(OUT / "contam_ref.json", "w") as f:
+        json.dump({"args": args, "seed": int(cfg.seed), "results": clean(res)}, f, indent=1)
+    flat = [v["mean_sensitivity"] for kind in ("index_hopping", "barcode_collisions", "cross_sample_contamination")
+            for r in res[kind].values() for a in r.values() for v in a.values()]
+    print("  wrote contam_ref.json; mean sensitivities:", sorted(set(flat)))
+
+
 # ------------------------------------------------------------------------------- LoD fit
 def golden_lod_fit() -> None:
     _import_ref("gd_v1")
@@ -689,7 +736,7 @@ def main() -> int:
     steps = {
         "call": lambda: (golden_call("gd_v1", "det_a", "call_smoke_v1.npz"), golden_call("gd_v2", "smoke", "call_smoke_v2.npz")),
         "stats": golden_stats, "ga": golden_ga, "gc": golden_gc, "gb": golden_gb, "gbgreedy": golden_gb_greedy, "gbstats": golden_gb_stats, "filters": golden_filters, "qc": golden_qc, "fastq": golden_fastq,
-        "lod": golden_lod_fit,
+        "lod": golden_lod_fit, "contam": golden_contam,
         "dist": golden_gd_dist,
     }
     for name, fn in steps.items():

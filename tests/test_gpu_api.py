@@ -208,6 +208,35 @@ def test_read_level_dataframe_apis_vs_reference_golden(ctx, golden):
         UMIProcessor(min_family_size=0)
 
 
+def test_contamination_stages_engine_equals_the_reference_run(ctx, smoke_cfg):
+    """C4 parity: the stages engine against the reference's OWN ContaminationSimulator run (oracle/make_golden.py
+    contam -> tests/golden/contam_ref.json; src/precise_mrd/sim/contamination.py:85-228 with `variant_call` added).
+    On the reference grid (AF <= 0.01) no variant is ever generated, so every sensitivity and
+    false-positive rate of the reference is exactly 0 -- and must be here: same keys, same numbers."""
+    import json
+    from pathlib import Path
+
+    from precise_mrd.sim import ContaminationSimulator
+
+    ref = json.loads((Path(__file__).parent / "golden" / "contam_ref.json").read_text())
+    assert ref["seed"] == smoke_cfg.seed
+    got = ContaminationSimulator(smoke_cfg, np.random.default_rng(smoke_cfg.seed), engine="stages").simulate_contamination_effects(**ref["args"])
+    n = 0
+    for kind in ("index_hopping", "barcode_collisions", "cross_sample_contamination"):
+        assert [str(r) for r in got[kind]] == list(ref["results"][kind])
+        for rate, by_af in got[kind].items():
+            for af, by_depth in by_af.items():
+                for depth, cell in by_depth.items():
+                    want = ref["results"][kind][str(rate)][str(af)][str(depth)]
+                    assert set(cell) == set(want), (kind, rate, af, depth)
+                    for k, v in want.items():
+                        assert cell[k] == v, (kind, rate, af, depth, k, cell[k], v)
+                    n += 1
+    assert n == 12
+    m, want_m = got["sensitivity_matrix"]["index_hopping"], ref["results"]["sensitivity_matrix"]["index_hopping"]
+    assert m["matrix"] == want_m["matrix"] and m["condition_labels"] == want_m["condition_labels"]
+
+
 def test_lod_analyzer_both_engines(ctx, smoke_cfg, tmp_path):
     from precise_mrd.eval import LODAnalyzer
     from precise_mrd.validation import validate_json

@@ -281,6 +281,38 @@ def test_pipeline_equals_oracle_on_the_same_reads(ctx, native, test_type):
     assert (res3["n_total"] == res["n_total"][sub]).all() and (res3["n_variants"] == res["n_variants"][sub]).all()
 
 
+@pytest.mark.parametrize("hop,coll", [(0.01, 0.0), (0.05, 0.02)])
+def test_pipeline_with_index_hopping_equals_oracle(ctx, native, hop, coll):
+    """C4 (eval-contamination) read-level knobs through the plan: with hop_rate > 0 reads leave their cell, so the
+    plan takes the general path (12-byte records, full-key sort, family + group tables).  Same gate as the
+    cell-major path: the plan's per-cell counts equal the oracle's collapse of the very reads it generated."""
+    rng = np.random.default_rng(8)
+    c = 60
+    cid = np.arange(c) * 3 + 1000
+    af = np.tile([0.0, 0.0, 0.01, 0.05, 0.2, 0.001], c // 6)
+    nf = rng.integers(100, 4000, c)
+    sp, up = _sp(native, hop_rate=hop, collision_rate=coll), _umi(native)
+    res = ctx.pipeline_cells(cid, af, nf, sp, up, neg_af_max=1e-4, test_type=native.TEST_POISSON, alpha=0.05)
+    keys, pl = ctx.simulate_reads(cid, af, nf, sp)
+    assert res["n_reads"].sum() == len(keys)
+    k0, _ = ctx.simulate_reads(cid, af, nf, _sp(native, collision_rate=coll))
+    moved = ((keys >> np.uint64(32)) != (k0 >> np.uint64(32))).mean()
+    assert abs(moved - hop) < 5 * np.sqrt(hop / len(keys)) + 1e-4              # reads did hop, at the requested rate
+    fam, grp = port.collapse_exact(keys, pl, 0, 3, 1000, 20, 0.6)
+    alt = ((cid & 3) + 1 + ((cid >> 2) % 3)) & 3
+    n_total, n_var, n_fam = np.zeros(c, np.int64), np.zeros(c, np.int64), np.zeros(c, np.int64)
+    n_total[grp["group"]] = grp["consensus_count"].sum(1)
+    n_var[grp["group"]] = grp["consensus_count"][np.arange(len(grp["group"])), alt[grp["group"]]]
+    np.add.at(n_fam, (fam["key"] >> np.uint64(32)).astype(np.int64), 1)
+    assert (res["n_total"] == n_total).all() and (res["n_variants"] == n_var).all() and (res["n_families"] == n_fam).all()
+    # hopped reads open small foreign families in the receiving cell: more families, (almost) none of them kept
+    base = ctx.pipeline_cells(cid, af, nf, _sp(native, collision_rate=coll), up)
+    assert res["n_families"].sum() > base["n_families"].sum() and res["n_total"].sum() <= base["n_total"].sum()
+    want_p = np.array([port.poisson_test(int(k), int(n) * res["mean_error_rate"]) for k, n in zip(n_var, n_total)])
+    ok = want_p >= 1e-50
+    assert np.max(np.abs(res["p_value"][ok] - want_p[ok]) / want_p[ok]) < 1e-12
+
+
 @pytest.mark.parametrize("cthr,qthr", [(0.4, 20), (0.5, 30), (0.51, 20), (0.9, 0)])
 def test_plan_consensus_thresholds_either_side_of_one_half(ctx, native, cthr, qthr):
     """The fused consensus kernel walks with a lighter vote when consensus_threshold > 0.5 (a tie for the best weight
