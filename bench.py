@@ -38,6 +38,7 @@ for _p in (str(ROOT / "precise-mrd-mini_b200"), str(ROOT)):
 
 METRIC = "umi_reads_per_sec_simulate_collapse_call"
 UNIT = "reads/s"
+DTYPE = "u64 packed records (payload:32 | umi:32) through the sort, f64 consensus weights and tail tests"
 B_READ_PIPELINE = 54.4  # algorithmic bytes per read of the whole path (48 + 32/f, f = 5)
 HBM_FALLBACK_GBS = 6650.0
 
@@ -72,6 +73,16 @@ def workload(name: str, rank: int, world: int):
     cell_id, af, depth, rep = grid_cells(sim.allele_fractions, sim.umi_depths, reps, rep_offset=rank * reps,
                                          rep_stride=world * reps)
     return cfg, label, cell_id, af, depth
+
+
+def workload_config(name, label, cell_id, depth, world):
+    """The workload-defining facts both arms can state without running anything (the reference arm prints the same dict)."""
+    fused = name == "fused"
+    return {"workload": label, "cells_per_gpu": int(len(cell_id)), "families_per_gpu_per_step": int(depth.sum()),
+            "family_sizes": "clip(Poisson(5),1,1000)", "umi": "12-mer (24 bit)",
+            "input_order": "family-major (no reads exist to be ordered)" if fused else "window-shuffled (Philox-keyed affine permutation)",
+            "l2": "no read buffers; per-cell state lives in shared memory" if fused else "inputs larger than L2 (GBs of records per chunk vs 126 MB)",
+            "parallelism": f"replicate axis sharded over {world} GPU(s)"}
 
 
 def peak_hbm():
@@ -235,7 +246,10 @@ def lod_grid_wall(cfg, world=1, barrier=None):
 def run_reference(args, rank, world, emit):
     if rank != 0:
         return 0
-    cfg, label, cell_id, af, depth = workload(args.workload, 0, 1)
+    fused = args.workload == "fused"
+    cfg, label, cell_id, af, depth = workload("default" if fused else args.workload, 0, 1)
+    if fused:
+        label = label.replace("C2 grid", "C2 grid, FUSED engine (reads voted where they are drawn, never written)")
     threads = host_threads()
     n = int(os.environ.get("PMRD_REF_CELLS", 256))
     cid, a, d = cpu_sample_cells(cell_id, af, depth, n)
@@ -251,13 +265,14 @@ def run_reference(args, rank, world, emit):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u64 keys / u32 payload / f64 tests", "data": "synthetic",
-        "config": {"workload": label, "sample": f"{len(cid)} cells per step (every {max(1, len(cell_id) // n)}th cell of the grid)"},
+        "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(args.workload, label, cell_id, depth, args.gpus),
+        "sample": f"{len(cid)} cells per step (every {max(1, len(cell_id) // n)}th cell of the grid: every AF x depth stratum); value is a rate",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{len(cid)} cells, {reads // args.steps} reads per step; oracle/pmrd_oracle.c (C + OpenMP "
                                    "restatement of io.py / umi.py / call.py; the Python reference cannot travel to the GPU box)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "reference_class": "cpu-port",
     }
     emit(line)
     return 0
@@ -302,11 +317,19 @@ def main() -> int:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    cfg, label, cell_id, af, depth = workload(args.workload, rank, world)
+    fused = args.workload == "fused"
+    cfg, label, cell_id, af, depth = workload("default" if fused else args.workload, rank, world)
+    if fused:
+        label = label.replace("C2 grid", "C2 grid, FUSED engine (reads voted where they are drawn, never written)")
     ctx = nv.Context(device=local_rank, seed=int(cfg.seed))
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch's events and the library's launches: the CUDA events that time the
+    # step are recorded on the very stream the kernels run on (the default stream's handle is 0, which pmrd_set_stream
+    # reads as "keep the context's own stream")
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    sim = grid.read_sim_params(cfg, mean_family_size=5.0, family_model=1, chunk_log2=args.chunk_log2)
+    assert stream.cuda_stream != 0
+    sim = grid.read_sim_params(cfg, mean_family_size=5.0, family_model=1, chunk_log2=args.chunk_log2, fused=fused)
     up = grid.umi_params(cfg)
     tt = nv.TEST_TYPES[cfg.stats.test_type]
 
@@ -316,23 +339,27 @@ def main() -> int:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed_steps(plan, steps):
+        """K steps bracketed by CUDA events on the launching stream, barrier + synchronize on both sides."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            plan.run()
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
+
     # ---- device-resident arm: the plan owns all buffers; run() only enqueues kernels ----------
     neg_af_max = 0.0 if args.workload == "panel" else 1e-4
     plan = nv.Plan(ctx, cell_id, af, depth, sim, up, neg_af_max=neg_af_max, test_type=tt, alpha=float(cfg.stats.alpha))
     n_reads = plan.n_reads
     for _ in range(max(args.warmup, 3)):
         plan.run()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = ctx.launch_count
     with ClockSampler(local_rank) as clocks:
-        ev0.record(stream)
-        for _ in range(args.steps):
-            plan.run()
-        ev1.record(stream)
-        barrier()
+        ms = timed_steps(plan, args.steps)
     launches = ctx.launch_count - launches0
-    ms = ev0.elapsed_time(ev1)
     # per-kernel breakdown: a SEPARATE pass of the same K steps with per-launch CUDA events (pmrd_profile_enable) --
     # the event pairs cost device time, so they stay out of the region `value` is timed over
     ctx.profile_enable(True)
@@ -361,6 +388,52 @@ def main() -> int:
     d2h = int(sum(v.nbytes for k, v in out.items() if isinstance(v, np.ndarray) and k != "variant_call"))
     assert (out["n_total"] == res["n_total"]).all() and (out["p_adjusted"] == res["p_adjusted"]).all()
 
+    # ---- strong scaling (N > 1): the FIXED single-GPU grid split over the ranks ---------------------------------
+    # `value` above is weak scaling (every rank runs a whole grid).  north_star also asks how one fixed grid scales:
+    # the N = 1 workload's cells (same global cell ids) are dealt to the ranks in blocks of replicates, every rank
+    # runs its share, time = max over ranks.  No data-path collective (per-cell counts are what a rank keeps).
+    strong = None
+    if world > 1 and args.workload in ("default", "fused"):
+        _, _, s_cid, s_af, s_depth = workload("default", 0, 1)
+        mine = np.arange(len(s_cid))[rank::world]                      # every (AF, depth) stratum on every rank
+        splan = nv.Plan(ctx, s_cid[mine], s_af[mine], s_depth[mine], sim, up, neg_af_max=neg_af_max, test_type=tt, alpha=float(cfg.stats.alpha))
+        for _ in range(3):
+            splan.run()
+        s_ms = timed_steps(splan, args.steps)
+        s_reads = splan.n_reads
+        splan.close()
+        ts = torch.tensor([s_ms], dtype=torch.float64, device="cuda")
+        rs = torch.tensor([float(s_reads)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rs, op=dist.ReduceOp.SUM)
+        strong = {"scaling": "strong", "workload": f"the fixed N=1 grid ({len(s_cid)} cells, {int(rs.item())} reads) split over {world} GPUs, cell i -> rank i mod N",
+                  "ms_per_step": float(ts.item()) / args.steps, "value": float(rs.item()) * args.steps / (float(ts.item()) * 1e-3), "unit": UNIT,
+                  "note": "per-rank share incl. its own call stage; compare ms_per_step with the N=1 line's"}
+
+    # ---- sharded == single (N > 1): driver-visible proof that the multi-GPU table is the single-GPU one ----------
+    sharded_equals_single = None
+    if world > 1:
+        from precise_mrd import distributed
+        from precise_mrd.eval import LODAnalyzer
+
+        an = LODAnalyzer(cfg, np.random.default_rng(7), engine="grid")
+        g_cid, g_af, g_dp = an._grid_cells(2, np.logspace(-4, -2, 15), [1000, 5000, 10000, 50000, 100000], 25, 25)
+        sh = distributed.run_cells_sharded(cfg, g_cid, g_af, g_dp, neg_af_max=0.0, alternative=nv.ALT_GREATER, ctx=ctx)
+        ok = True
+        if rank == 0:
+            one = grid.run_cells(cfg, g_cid, g_af, g_dp, ctx=ctx, neg_af_max=0.0, alternative=nv.ALT_GREATER)
+            for k in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+                ok = ok and bool((np.asarray(sh[k]) == np.asarray(one[k])).all())
+            ok = ok and sh["mean_error_rate"] == one["mean_error_rate"]
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sharded_equals_single = {"equal": bool(flag.item()), "cells": int(len(g_cid)),
+                                 "what": "C3 eval-lod grid (1875 cells + blanks): run_cells_sharded over all ranks (LPT shards, one NCCL "
+                                         "all-gather of per-cell counts, call stage on every rank) vs grid.run_cells on rank 0 alone; "
+                                         "counts, p, q, significant, error rate compared bit for bit"}
+        if not flag.item():
+            raise SystemExit("bench.py: the sharded table differs from the single-GPU one")
+
     # ---- reduce over ranks: max time, sum of reads ---------------------------------------------
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     r = torch.tensor([float(n_reads)], dtype=torch.float64, device="cuda")
@@ -378,76 +451,115 @@ def main() -> int:
 
     if rank == 0:
         peak, peak_src = peak_hbm()
-        # Per-kernel device time comes from CUDA events recorded inside the timed region.  The radix scatter
-        # pass exists in two variants -- staged through shared memory for the first pass (scattered generator
-        # output), direct for the later passes -- which are ONE logical kernel: the dominant one.  Its
-        # achieved bandwidth = algorithmic bytes of all its launches in a step / their summed device time.
         total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
-        rec = pinfo["record_bytes"]
-        slots = pinfo["n_slots"]                                       # record slots per step (reads + tile padding)
-        passes = pinfo["sort_passes"]
-        n_staged = sum(v[0] for k, v in prof.items() if k.startswith("rs_downsweep_staged_kernel")) / max(args.steps * n_chunks, 1)
-        # the generator counts the first digit as a by-product (PMRD_GEN_HIST, default on): one counting pass fewer
-        up_passes = passes - (0 if os.environ.get("PMRD_GEN_HIST", "1") == "0" else 1)
-        groups = {
-            "rs_downsweep": (["rs_downsweep_direct_kernel", "rs_downsweep_staged_kernel", "rs_downsweep_kernel<false>"], 2.0 * rec * passes),
-            "rs_upsweep_kernel": (["rs_upsweep_kernel"], 8.0 * up_passes),
-            "reads_gen_kernel": (["reads_gen_kernel"], float(rec)),
-            "cell_consensus_kernel": (["cell_consensus_kernel<true>", "cell_consensus_kernel<false>"], float(rec)),
-        }
-        table = []
-        for gname, (members, bytes_per_slot) in groups.items():
-            g_ms = sum(prof[m][1] for m in members if m in prof)
-            g_n = sum(prof[m][0] for m in members if m in prof)
-            if g_n == 0:
-                continue
-            ach = bytes_per_slot * slots * args.steps / (g_ms * 1e-3) / 1e9
-            table.append({"kernel": gname, "variants": [m for m in members if m in prof], "launches": g_n, "ms_per_step": g_ms / args.steps,
-                          "share_of_step": g_ms / total_prof_ms, "algorithmic_bytes_per_record": bytes_per_slot, "achieved": ach,
-                          "frac": ach / peak})
-        table.sort(key=lambda r: -r["ms_per_step"])
-        top = table[0] if table else {"kernel": "none", "variants": [], "launches": 0, "ms_per_step": 0.0, "share_of_step": 0.0,
-                                      "algorithmic_bytes_per_record": 0.0, "achieved": None, "frac": None}
-        kname = top["variants"][0] if top["variants"] else "none"
-        roof = {"bound": "hbm", "kernel": top["kernel"], "variants": top["variants"], "launches": top["launches"],
-                "avg_launch_ms": top["ms_per_step"] * args.steps / max(top["launches"], 1), "share_of_step": top["share_of_step"],
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None, "achieved": top["achieved"], "frac": top["frac"],
-                "algorithmic_bytes_per_launch": (top["algorithmic_bytes_per_record"] * slots * args.steps / max(top["launches"], 1))
-                if top["launches"] else None,
-                "bytes_per_record": top["algorithmic_bytes_per_record"] / (passes if top["kernel"].startswith("rs_") else 1),
-                "records_per_launch": slots / max(n_chunks, 1), "staged_passes_per_chunk": n_staged,
-                "note": "reads_gen_kernel is INT32-issue bound (one Philox2x32-10 block per read), "
-                        "its HBM fraction is listed for completeness only",
-                "all_hot_kernels": table}
-        reads_per_launch = slots / max(n_chunks, 1)
-        tj = ROOT / "profiles" / "traffic.json"
-        if tj.exists():
-            try:
-                per_read = json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_read")   # per launch of one variant
-                if per_read:
-                    roof["traffic"] = per_read * reads_per_launch
-            except Exception:
-                pass
+        kernels_ms = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]}
+        config = workload_config(args.workload, label, cell_id, depth, world)
+        layout = {"reads_per_gpu_per_step": int(n_reads), "chunks": n_chunks}
+        if fused:
+            # No read is written: the bounding resource is the INT32 issue rate of Philox, so the
+            # roofline is issue-slot utilisation.  Warp instructions per read come from the ncu capture of the same
+            # kernel (profiles/fused_inst.json: smsp__inst_executed.sum / reads); peak = SMs x 4 schedulers x SM clock.
+            inst = None
+            fj = ROOT / "profiles" / "fused_inst.json"
+            if fj.exists():
+                try:
+                    inst = float(json.loads(fj.read_text())["warp_inst_per_read"])
+                except Exception:
+                    inst = None
+            cs = clocks.summary()
+            sm_clock = (cs["sm_mhz"] or 1965.0) * 1e6
+            k_ms = sum(v[1] for k, v in prof.items() if k.startswith("fused_cell_kernel")) / args.steps
+            issue_peak = 148 * 4 * sm_clock / 1e9                                    # G warp-instructions / s
+            ach = inst * n_reads / (k_ms * 1e-3) / 1e9 if (inst and k_ms) else None
+            roof = {"bound": "issue", "kernel": "fused_cell_kernel", "launches": int(sum(v[0] for k, v in prof.items() if k.startswith("fused_cell_kernel"))),
+                    "avg_launch_ms": k_ms / max(n_chunks, 1), "share_of_step": k_ms * args.steps / total_prof_ms,
+                    "achieved": ach, "peak": issue_peak, "peak_source": "148 SMs x 4 warp schedulers x SM clock under load",
+                    "unit": "Gwarp-inst/s", "frac": (ach / issue_peak) if ach else None,
+                    "warp_inst_per_read": inst, "traffic": 12.0 * pinfo["n_slots"] / max(n_chunks, 1),
+                    "note": "traffic = the candidate-duplicate list (12 B per candidate), the only per-read-scale HBM data; "
+                            "HBM fraction is not this kernel's roofline"}
+            layout.update({"candidate_duplicates_per_step": pinfo["n_slots"]})
+            pipeline = {"algorithmic_bytes_per_read": 6.4, "achieved": value / world * 6.4 / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": value / world * 6.4 / 1e9 / peak, "note": "SURVEY.md §8d: family record only, 32 B / f"}
+        else:
+            # Per-kernel device time comes from CUDA events recorded in the profiled pass.  The radix scatter
+            # pass exists in two variants -- staged through shared memory for the first pass (scattered generator
+            # output), direct for the later passes -- which are ONE logical kernel: the dominant one.  Its
+            # achieved bandwidth = algorithmic bytes of all its launches in a step / their summed device time.
+            rec = pinfo["record_bytes"]
+            slots = pinfo["n_slots"]                                       # record slots per step (reads + tile padding)
+            passes = pinfo["sort_passes"]
+            n_staged = sum(v[0] for k, v in prof.items() if k.startswith("rs_downsweep_staged_kernel")) / max(args.steps * n_chunks, 1)
+            # the generator counts the first digit as a by-product (PMRD_GEN_HIST, default on): one counting pass fewer
+            up_passes = passes - (0 if os.environ.get("PMRD_GEN_HIST", "1") == "0" else 1)
+            groups = {
+                "rs_downsweep": (["rs_downsweep_direct_kernel", "rs_downsweep_staged_kernel", "rs_downsweep_kernel<false>"], 2.0 * rec * passes),
+                "rs_upsweep_kernel": (["rs_upsweep_kernel"], 8.0 * up_passes),
+                "reads_gen_kernel": (["reads_gen_kernel"], float(rec)),
+                "cell_consensus_kernel": (["cell_consensus_kernel<true>", "cell_consensus_kernel<false>"], float(rec)),
+                "small_cell_kernel": (["small_cell_kernel"], float(rec)),
+            }
+            table = []
+            for gname, (members, bytes_per_slot) in groups.items():
+                g_ms = sum(prof[m][1] for m in members if m in prof)
+                g_n = sum(prof[m][0] for m in members if m in prof)
+                if g_n == 0:
+                    continue
+                ach = bytes_per_slot * slots * args.steps / (g_ms * 1e-3) / 1e9
+                table.append({"kernel": gname, "variants": [m for m in members if m in prof], "launches": g_n, "ms_per_step": g_ms / args.steps,
+                              "share_of_step": g_ms / total_prof_ms, "algorithmic_bytes_per_record": bytes_per_slot, "achieved": ach,
+                              "frac": ach / peak})
+            table.sort(key=lambda r: -r["ms_per_step"])
+            top = table[0] if table else {"kernel": "none", "variants": [], "launches": 0, "ms_per_step": 0.0, "share_of_step": 0.0,
+                                          "algorithmic_bytes_per_record": 0.0, "achieved": None, "frac": None}
+            kname = top["variants"][0] if top["variants"] else "none"
+            roof = {"bound": "hbm", "kernel": top["kernel"], "variants": top["variants"], "launches": top["launches"],
+                    "avg_launch_ms": top["ms_per_step"] * args.steps / max(top["launches"], 1), "share_of_step": top["share_of_step"],
+                    "peak": peak, "peak_source": peak_src, "unit": "GB/s", "traffic": None, "achieved": top["achieved"], "frac": top["frac"],
+                    "algorithmic_bytes_per_launch": (top["algorithmic_bytes_per_record"] * slots * args.steps / max(top["launches"], 1))
+                    if top["launches"] else None,
+                    "bytes_per_record": top["algorithmic_bytes_per_record"] / (passes if top["kernel"].startswith("rs_") else 1),
+                    "records_per_launch": slots / max(n_chunks, 1), "staged_passes_per_chunk": n_staged,
+                    "note": "reads_gen_kernel is INT32-issue bound (one Philox2x32-10 block per read), "
+                            "its HBM fraction is listed for completeness only",
+                    "all_hot_kernels": table}
+            reads_per_launch = slots / max(n_chunks, 1)
+            tj = ROOT / "profiles" / "traffic.json"
+            if tj.exists():
+                try:
+                    per_read = json.loads(tj.read_text()).get(kname, {}).get("dram_bytes_per_read")   # per launch of one variant
+                    if per_read:
+                        roof["traffic"] = per_read * reads_per_launch
+                except Exception:
+                    pass
+            layout.update({"record_bytes": pinfo["record_bytes"], "radix_passes": pinfo["sort_passes"], "counting_passes": up_passes,
+                           "smallest_chunk_gb": round(min(chunk_reads) * pinfo["record_bytes"] / 1e9, 2)})
+            pipeline = {"algorithmic_bytes_per_read": B_READ_PIPELINE, "achieved": value / world * B_READ_PIPELINE / 1e9,
+                        "peak": peak, "unit": "GB/s", "frac": value / world * B_READ_PIPELINE / 1e9 / peak}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64 keys / u32 payload / f64 tests", "data": "synthetic",
-            "config": {"workload": label, "cells_per_gpu": int(len(cell_id)), "reads_per_gpu_per_step": int(n_reads),
-                       "families_per_gpu_per_step": int(depth.sum()), "chunks": n_chunks, "record_bytes": pinfo["record_bytes"],
-                       "radix_passes": pinfo["sort_passes"], "counting_passes": up_passes, "family_sizes": "clip(Poisson(5),1,1000)",
-                       "umi": "12-mer (24 bit)", "input_order": "window-shuffled (Philox-keyed affine permutation)",
-                       "l2": f"inputs larger than L2 ({min(chunk_reads) * pinfo['record_bytes'] / 1e9:.1f} GB of records in the smallest chunk vs 126 MB)", "parallelism": f"replicate axis sharded over {world} GPU(s)"},
+            "dtype": DTYPE, "data": "synthetic", "config": config, "layout": layout,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "precise_mrd.grid.run_cells (plan create + H2D + run + D2H per step)"},
+                    "api": "precise_mrd.grid.run_cells: per step plan create (host cell tables + H2D + the sizing pass over the "
+                           "families -- the first run() after a build reuses that pass's family sizes instead of redrawing them, "
+                           "which saves reads_size_kernel once per e2e step) + run + D2H of the per-cell table"},
             "gpu_launches": int(launches),
             "roofline": roof,
-            "pipeline_roofline": {"algorithmic_bytes_per_read": B_READ_PIPELINE, "achieved": value / world * B_READ_PIPELINE / 1e9,
-                                  "peak": peak, "unit": "GB/s", "frac": value / world * B_READ_PIPELINE / 1e9 / peak},
-            "kernels_ms_per_step": {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:12]},
+            "pipeline_roofline": pipeline,
+            "kernels_ms_per_step": kernels_ms,
             "clocks": clocks.summary(),
             "result_check": {"significant_cells": int(res["significant"].sum()), "mean_error_rate": res["mean_error_rate"],
                              "families_formed": int(res["totals"][1])},
+            "reference_class": "cpu-port",
+            "tolerances": "counts / consensus / BH decisions bit-exact; p, q <= 1e-12 relative (p >= 1e-50, binomial n <= 2e4), "
+                          "2e-11 / 1e-11 in the deeper tails where SciPy itself is the inexact party (mpmath evidence in tests/test_gpu_parity.py)",
         }
+        if strong is not None:
+            line["strong_scaling"] = strong
+        if sharded_equals_single is not None:
+            line["sharded_equals_single"] = sharded_equals_single["equal"]
+            line["sharded_check"] = sharded_equals_single
         if lod is not None:
             line["lod_grid"] = lod
         if world == 1 and not args.no_cpu_baseline:

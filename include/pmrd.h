@@ -331,7 +331,15 @@ typedef struct pmrd_read_sim_params {
                                  * shuffled inside its own region -- so that order-sensitive results (weighted
                                  * sums, first-seen tie-breaks) can be checked against the plan read for read */
     int32_t chunk_log2;         /* pipeline plans: cells are streamed in chunks of <= 2^chunk_log2 reads (0 = 30) */
+    int32_t engine;             /* pipeline plans: PMRD_ENGINE_MATERIALISED (0) reads are written, sorted and voted
+                                 * (the headline path: the sort does real work on window-shuffled input);
+                                 * PMRD_ENGINE_FUSED (1) reads are voted where they are drawn and never written
+                                 * (eval/lod.py:125-150, sim/contamination.py:85-228 grids; results = the materialised
+                                 * path on family-major read order; hop_rate must be 0) */
+    int32_t reserved0;
 } pmrd_read_sim_params;
+#define PMRD_ENGINE_MATERIALISED 0
+#define PMRD_ENGINE_FUSED 1
 
 /* Counts reads: h_read_offsets[C+1] CSR of reads per cell (family-major layout). */
 int32_t pmrd_simulate_reads_count(pmrd_ctx* ctx, const int64_t* h_cell_id, const int64_t* h_n_families,

@@ -47,6 +47,7 @@ void pmrd_prof_end(pmrd_ctx* ctx) {
 }
 
 int32_t collapse_upload_weights(pmrd_ctx* ctx, const double* h_w64);
+int32_t fused_upload_tables(pmrd_ctx* ctx, const double* h_w64);
 int32_t k6_hamming(pmrd_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, int64_t n, int32_t* d_d);
 int32_t k2_gd_families(pmrd_ctx* ctx, const int32_t* d_tile_cell, const int32_t* d_tile_fam0, int64_t n_tiles,
                        const void* d_cells, const int64_t* d_n_families, const pmrd_umi_params* P, int variant,
@@ -137,6 +138,7 @@ int32_t pmrd_create(int32_t device, uint64_t seed, pmrd_ctx** out) {
     for (int q = 0; q < 64; ++q) w[q] = pow(10.0, (double)q / 10.0);
     int32_t s = collapse_upload_weights(ctx, w);
     if (s == PMRD_OK) s = reads_upload_tables(ctx);
+    if (s == PMRD_OK) s = fused_upload_tables(ctx, w);
     if (s == PMRD_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) s = PMRD_ERR_CUDA;
     if (s != PMRD_OK) {
         snprintf(g_pmrd_create_err, sizeof(g_pmrd_create_err), "pmrd_create: %s", ctx->err);

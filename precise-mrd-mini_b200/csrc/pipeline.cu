@@ -12,6 +12,7 @@
 #include <stdlib.h>
 
 #include "reads.cuh"
+#include "fused.cuh"
 
 int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp,
                                  uint32_t* d_payload_tmp, int64_t n_reads, uint64_t varying, const pmrd_umi_params* params,
@@ -113,6 +114,9 @@ struct PlanChunk {
 
 struct pmrd_plan {
     std::vector<PlanChunk*> chunks;
+    std::vector<FusedChunk*> fchunks;   // PMRD_ENGINE_FUSED: reads are never written (fused.cu)
+    DevBuf fscratch;                    // candidate-duplicate list + its sort buffers, sized for the largest chunk
+    bool fused = false;
     pmrd_umi_params up;
     double neg_af_max, alpha;
     int32_t test_type, alternative;
@@ -131,6 +135,7 @@ struct pmrd_plan {
     DevBuf bh_ws;         // BH workspace (sort buffers + scratch): the call stage of a step allocates nothing
     ~pmrd_plan() {
         for (PlanChunk* c : chunks) delete c;
+        for (FusedChunk* c : fchunks) delete c;
     }
 };
 
@@ -161,6 +166,11 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     PMRD_ARG(ctx, P != nullptr, "out of host memory");
     P->up = *up; P->neg_af_max = neg_af_max; P->alpha = alpha; P->test_type = test_type; P->alternative = alternative;
     P->n_cells = n_cells;
+    P->fused = sp->engine == PMRD_ENGINE_FUSED;
+    if (P->fused && sp->hop_rate > 0.0) {
+        delete P;
+        PMRD_ARG(ctx, false, "the fused engine keeps a read inside its cell: hop_rate > 0 needs PMRD_ENGINE_MATERIALISED");
+    }
     P->stream_id = (uint64_t)h_cell_id[0];
     P->seed = ctx->seed;
     if (const char* sb = getenv("PMRD_SORT_BITS")) {   // tuning knob: 16 (2 radix passes) or 24 (3 passes)
@@ -180,6 +190,18 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
             if (c1 > c0 && acc + add > budget) break;
             acc += add;
             ++c1;
+        }
+        if (P->fused) {
+            FusedChunk* fc = new (std::nothrow) FusedChunk();
+            if (!fc) { st = PMRD_ERR_ARG; snprintf(ctx->err, sizeof(ctx->err), "out of host memory"); break; }
+            P->fchunks.push_back(fc);
+            st = fused_chunk_build(ctx, h_cell_id + c0, h_af ? h_af + c0 : nullptr, h_n_families + c0, c1 - c0, c0, sp, up, fc);
+            if (st != PMRD_OK) break;
+            P->n_reads += fc->n_reads;
+            P->n_fam += fc->n_fam;
+            if (fc->n_cand > P->max_fcap) P->max_fcap = fc->n_cand;
+            c0 = c1;
+            continue;
         }
         PlanChunk* ch = new (std::nothrow) PlanChunk();
         if (!ch) { st = PMRD_ERR_ARG; snprintf(ctx->err, sizeof(ctx->err), "out of host memory"); break; }
@@ -211,9 +233,10 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     const size_t f = (size_t)(P->max_fcap > 0 ? P->max_fcap : 1), g = (size_t)P->max_cells, c = (size_t)n_cells;
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.alloc(ctx->stream, bytes); };
-    A(P->keys, n * 8); A(P->keys_tmp, n * 8);
+    if (P->fused) A(P->fscratch, fused_scratch_bytes(P->max_fcap));
+    else { A(P->keys, n * 8); A(P->keys_tmp, n * 8); }
     if (const char* gh = getenv("PMRD_GEN_HIST")) P->gen_hist = atoi(gh) != 0;   // 0: the sort counts its first digit itself
-    if (sp->hop_rate > 0.0) P->gen_hist = false;
+    if (sp->hop_rate > 0.0 || P->fused) P->gen_hist = false;
     if (P->gen_hist) A(P->tile_hist, (n / READS_SEG_TILE + 1) * 256 * sizeof(uint32_t));
     if (sp->hop_rate > 0.0) { A(P->pl, n * 4); A(P->pl_tmp, n * 4); }
     if (sp->hop_rate > 0.0) {   // only the general (non cell-major) path materialises the family / group tables
@@ -343,6 +366,7 @@ int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
 
 int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P, int64_t which) {
     PLAN_SEED_GUARD(ctx, P);
+    PMRD_ARG(ctx, !P->fused, "the fused engine has no separate simulate / collapse stages");
     PMRD_ARG(ctx, which >= 0 && which < (int64_t)P->chunks.size(), "chunk index");
     return chunk_simulate(ctx, P, P->chunks[(size_t)which]);
 }
@@ -356,6 +380,13 @@ int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P, int64_t which) {
 
 int32_t plan_run(pmrd_ctx* ctx, pmrd_plan* P) {
     PLAN_SEED_GUARD(ctx, P);
+    if (P->fused) {
+        // every cell's counts are WRITTEN by its block (no reset needed); the replay of the candidate duplicates adds to them
+        for (FusedChunk* fc : P->fchunks)
+            PMRD_TRY(fused_chunk_run(ctx, fc, &P->up, P->fscratch.p, (const uint8_t*)P->alt.as<uint8_t>(), P->o_reads.as<int64_t>(),
+                                     P->o_fam.as<int64_t>(), P->o_tot.as<int64_t>(), P->o_var.as<int64_t>()));
+        return plan_run_call(ctx, P);
+    }
     PMRD_TRY(plan_reset_outputs(ctx, P));
     for (PlanChunk* ch : P->chunks) {
         PMRD_TRY(chunk_simulate(ctx, P, ch));
@@ -375,6 +406,7 @@ __global__ void __launch_bounds__(256) sum_i64_kernel(const int64_t* __restrict_
 int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h, double* h_mean_rate, int64_t* h_totals /*[3]: reads, families, groups*/) {
     const size_t c = (size_t)P->n_cells;
     for (PlanChunk* ch : P->chunks) PMRD_TRY(reads_plan_cell_counts(ctx, &ch->reads, P->o_reads.as<int64_t>() + ch->cell0));
+    // (fused engine: the cell kernel writes the per-cell read counts itself)
     auto D = [&](void* dst, const DevBuf& b, size_t bytes) -> cudaError_t {
         return dst ? cudaMemcpyAsync(dst, b.p, bytes, cudaMemcpyDeviceToHost, ctx->stream) : cudaSuccess;
     };
@@ -397,6 +429,7 @@ int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h,
         int64_t groups = (int64_t)tot[1];
         for (PlanChunk* ch : P->chunks)
             if (ch->reads.segmented) groups += ch->reads.n_groups_with_reads;
+        for (FusedChunk* fc : P->fchunks) groups += fc->n_cells_with_reads;
         h_totals[2] = groups;
     }
     return PMRD_OK;
@@ -405,13 +438,20 @@ int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h,
 void plan_destroy(pmrd_plan* P) { delete P; }
 int64_t plan_n_reads(const pmrd_plan* P) { return P ? P->n_reads : 0; }
 int64_t plan_n_families(const pmrd_plan* P) { return P ? P->n_fam : 0; }
-int64_t plan_n_chunks(const pmrd_plan* P) { return P ? (int64_t)P->chunks.size() : 0; }
+int64_t plan_n_chunks(const pmrd_plan* P) { return P ? (int64_t)(P->fused ? P->fchunks.size() : P->chunks.size()) : 0; }
 int64_t plan_chunk_reads(const pmrd_plan* P, int64_t which) {
+    if (P && P->fused) return (which >= 0 && which < (int64_t)P->fchunks.size()) ? P->fchunks[(size_t)which]->n_reads : 0;
     return (P && which >= 0 && which < (int64_t)P->chunks.size()) ? P->chunks[(size_t)which]->reads.n_reads : 0;
 }
 
 int32_t plan_info(const pmrd_plan* P, int64_t* o) {
     if (!P || !o) return PMRD_ERR_ARG;
+    if (P->fused) {   // no records, no radix passes; [1] = candidate duplicates replayed per step, [5] = 12 B per candidate
+        int64_t cand = 0;
+        for (const FusedChunk* fc : P->fchunks) cand += fc->n_cand;
+        o[0] = P->n_reads; o[1] = cand; o[2] = P->n_fam; o[3] = (int64_t)P->fchunks.size(); o[4] = 0; o[5] = 12; o[6] = P->max_fcap; o[7] = 2;
+        return PMRD_OK;
+    }
     int64_t n_out = 0, max_out = 0, seg = 1, passes = 0;
     for (const PlanChunk* ch : P->chunks) {
         n_out += ch->reads.n_out;

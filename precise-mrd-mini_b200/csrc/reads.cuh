@@ -1,6 +1,7 @@
 // reads.cuh -- host-visible pieces of the read-level generator (reads.cu).
 #pragma once
 #include "common.cuh"
+#include <math.h>
 
 struct ReadCell {
     uint64_t cell_id;
@@ -41,6 +42,49 @@ struct ReadPlan {
 static inline uint32_t pmrd_cell_ref_allele(uint64_t cell_id) { return (uint32_t)(cell_id & 3u); }
 static inline uint32_t pmrd_cell_alt_allele(uint64_t cell_id) {
     return (pmrd_cell_ref_allele(cell_id) + 1u + (uint32_t)((cell_id >> 2) % 3u)) & 3u;
+}
+
+// uniform in (0,1) from 53 bits (common.cuh u53) decides has_variant: words w of the first 32 bits that settle
+// u53(w, .) < af on their own -- w < af_lt: true whatever the low word; w >= af_ge: false whatever the low word
+static inline void reads_init_cell(ReadCell* c, uint64_t cell_id, double af, int64_t fam_offset, uint32_t group) {
+    c->cell_id = cell_id;
+    c->af = af;
+    c->fam_offset = fam_offset;
+    c->group = group;
+    c->ref_allele = (uint32_t)(cell_id & 3u);
+    c->alt_allele = (c->ref_allele + 1u + (uint32_t)((cell_id >> 2) % 3u)) & 3u;
+    c->read_start = 0;
+    c->out_start = 0;
+    c->n_reads = 0;
+    c->inv_full = 0.0f;
+    c->tile0 = 0;
+    const double a = af;
+    int64_t g = a <= 0.0 ? 0 : (a >= 1.0 ? (1ll << 32) : (int64_t)(a * 4294967296.0));
+    while (g > 0 && !(u53((uint32_t)(g - 1), 0xffffffffu) < a)) --g;
+    while (g < (1ll << 32) && u53((uint32_t)g, 0xffffffffu) < a) ++g;
+    c->af_lt = g;
+    while (g < (1ll << 32) && u53((uint32_t)g, 0u) < a) ++g;
+    c->af_ge = g;
+}
+
+// Poisson family sizes with mean <= 16 are inverted against an fp32 cdf table: F[k] = P(X <= k), k < 96, by the pmf
+// recurrence, padded so the search stops; lut[b] = #{k : F[k] < u} for the smallest uniform of bucket b (u24 of the
+// words b << 20 ..).  Returns whether the tables apply.
+static inline bool reads_build_size_tables(const pmrd_read_sim_params* sp, float h_cdf[128], uint8_t h_lut[4096]) {
+    if (!(sp->family_model == 1 && sp->mean_family_size <= 16.0)) return false;
+    const float lam = (float)sp->mean_family_size;
+    float p = expf(-lam), F = p;
+    for (int k = 0; k < 128; ++k) {
+        if (k > 0 && k < 96) { p *= lam / (float)k; F += p; }
+        h_cdf[k] = k < 96 ? F : 2.0f;
+    }
+    for (uint32_t b = 0; b < 4096u; ++b) {
+        const float u = u24(b << 20);
+        int k = 0;
+        while (k < 127 && h_cdf[k] < u) ++k;
+        h_lut[b] = (uint8_t)k;
+    }
+    return true;
 }
 
 int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,

@@ -22,6 +22,7 @@ TEST_POISSON, TEST_BINOMIAL = 0, 1
 ALT_TWO_SIDED, ALT_GREATER, ALT_LESS = 0, 1, 2
 MODE_WEIGHTED, MODE_MAJORITY, MODE_COUNT = 0, 1, 2
 CLUSTER_EXACT, CLUSTER_FIRSTFIT, CLUSTER_GREEDY = 0, 1, 2
+ENGINE_MATERIALISED, ENGINE_FUSED = 0, 1
 FAM_HAS_CONSENSUS, FAM_KEPT, FAM_OVERSIZE = 1, 2, 4
 
 TEST_TYPES = {"poisson": TEST_POISSON, "binomial": TEST_BINOMIAL}
@@ -63,6 +64,8 @@ class ReadSimParams(C.Structure):
         ("collision_rate", C.c_double),
         ("shuffle", C.c_int32),
         ("chunk_log2", C.c_int32),
+        ("engine", C.c_int32),          # ENGINE_MATERIALISED / ENGINE_FUSED (pipeline plans)
+        ("reserved0", C.c_int32),
     ]
 
 

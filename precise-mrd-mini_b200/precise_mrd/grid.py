@@ -42,11 +42,12 @@ def umi_params(config, mode: int = nv.MODE_WEIGHTED, cluster: int = nv.CLUSTER_E
 
 def read_sim_params(config=None, mean_family_size: float = 5.0, family_model: int = 1, hop_rate: float = 0.0,
                     collision_rate: float = 0.0, contamination_rate: float = 0.0, shuffle: bool = True,
-                    chunk_log2: int = 0) -> nv.ReadSimParams:
+                    chunk_log2: int = 0, fused: bool = False) -> nv.ReadSimParams:
     max_fs = int(section(config, "umi")["max_family_size"]) if config is not None else 1000
     return nv.ReadSimParams(mean_family_size=mean_family_size, family_model=family_model, max_family_size=max_fs,
                             contamination_rate=contamination_rate, hop_rate=hop_rate, collision_rate=collision_rate,
-                            shuffle=1 if shuffle else 0, chunk_log2=chunk_log2)
+                            shuffle=1 if shuffle else 0, chunk_log2=chunk_log2,
+                            engine=nv.ENGINE_FUSED if fused else nv.ENGINE_MATERIALISED)
 
 
 def run_cells(config, cell_id, allele_fraction, n_families, ctx: Optional[nv.Context] = None,

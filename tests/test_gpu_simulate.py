@@ -281,6 +281,71 @@ def test_pipeline_equals_oracle_on_the_same_reads(ctx, native, test_type):
     assert (res3["n_total"] == res["n_total"][sub]).all() and (res3["n_variants"] == res["n_variants"][sub]).all()
 
 
+# ------------------------------------------------------------------------------ fused engine (no reads written)
+def _counts_from_oracle(keys, pl, cid, min_fs, qthr, cthr):
+    c = len(cid)
+    fam, grp = port.collapse_exact(keys, pl, 0, min_fs, 1000, qthr, cthr)
+    alt = ((cid & 3) + 1 + ((cid >> 2) % 3)) & 3
+    n_total, n_var, n_fam = np.zeros(c, np.int64), np.zeros(c, np.int64), np.zeros(c, np.int64)
+    n_total[grp["group"]] = grp["consensus_count"].sum(1)
+    n_var[grp["group"]] = grp["consensus_count"][np.arange(len(grp["group"])), alt[grp["group"]]]
+    np.add.at(n_fam, (fam["key"] >> np.uint64(32)).astype(np.int64), 1)
+    return n_fam, n_total, n_var
+
+
+@pytest.mark.parametrize("cthr,qthr,coll,model", [(0.6, 20, 0.0, 1), (0.4, 20, 0.0, 1), (0.6, 30, 0.05, 1), (0.5, 20, 0.01, 0)])
+def test_fused_engine_equals_oracle_on_family_major_reads(ctx, native, cthr, qthr, coll, model):
+    """PMRD_ENGINE_FUSED (reads voted where they are drawn, never written; duplicate UMIs found by two hash bitmaps
+    and replayed from the Philox counters): per-cell counts bit-equal to the oracle's collapse of the reads the
+    materialising generator writes in family-major order (shuffle = 0).  Cells of 0 / 1 / a few / thousands / 70 000
+    molecules: the 128-, 256- and 1024-thread blocks, natural 24-bit UMI coincidences (n^2 / 2^25 pairs) and forced
+    ones (collision_rate)."""
+    rng = np.random.default_rng(int(cthr * 100) + qthr)
+    big = np.array([0, 1, 2, 33, 700, 5000, 70000, 31, 4096, 4097, 20000, 512])
+    for nf in (big, rng.integers(1, 400, 150), rng.integers(500, 4000, 24)):
+        c = len(nf)
+        cid = np.arange(c, dtype=np.int64) * 11 + 5 + (np.int64(9) << 33)
+        af = np.tile([0.0, 0.3, 0.5, 0.05, 0.01, 1e-4], c // 6 + 1)[:c]
+        kw = dict(mean_family_size=4.0 if model else 3.0, family_model=model, collision_rate=coll)
+        up = _umi(native, consensus_threshold=cthr, quality_threshold=qthr, min_family_size=2)
+        res = ctx.pipeline_cells(cid, af, nf, _sp(native, engine=native.ENGINE_FUSED, **kw), up)
+        keys, pl = ctx.simulate_reads(cid, af, nf, _sp(native, shuffle=0, **kw))
+        assert res["n_reads"].sum() == len(keys) == res["totals"][0]
+        assert (res["n_reads"] == np.bincount((keys >> np.uint64(32)).astype(np.int64), minlength=c)).all()
+        n_fam, n_total, n_var = _counts_from_oracle(keys, pl, cid, 2, qthr, cthr)
+        assert (res["n_families"] == n_fam).all(), np.flatnonzero(res["n_families"] != n_fam)
+        assert (res["n_total"] == n_total).all(), np.flatnonzero(res["n_total"] != n_total)
+        assert (res["n_variants"] == n_var).all(), np.flatnonzero(res["n_variants"] != n_var)
+        if nf.max() >= 20000 or coll > 0:
+            assert n_fam.sum() < nf.sum()                              # molecules did share UMIs: the replay ran
+        # the call stage is the materialised plan's: same counts -> same table
+        rej, adj = port.benjamini_hochberg(res["p_value"], 0.05)
+        assert (res["significant"] == rej).all() and (res["p_adjusted"] == adj).all()
+        # deterministic, and a cell's row does not depend on the batch
+        again = ctx.pipeline_cells(cid[::-1].copy(), af[::-1].copy(), nf[::-1].copy(), _sp(native, engine=native.ENGINE_FUSED, **kw), up)
+        for k_ in ("n_reads", "n_families", "n_total", "n_variants"):
+            assert (again[k_][::-1] == res[k_]).all(), k_
+
+
+def test_fused_engine_agrees_with_the_materialised_plan_and_refuses_hopping(ctx, native):
+    """Same molecules, same reads: the fused engine and the sort-based plan see each family's reads in different
+    orders (family-major vs window-shuffled), which can only matter through fp64 rounding at the consensus threshold or
+    a first-seen tie (threshold <= 0.5).  At the default thresholds the two tables are equal."""
+    rng = np.random.default_rng(12)
+    c = 64
+    cid = np.arange(c, dtype=np.int64) + 300
+    af = np.tile([0.0, 1e-4, 1e-3, 1e-2, 0.05, 0.2, 0.0, 0.0], c // 8)
+    nf = rng.integers(100, 12000, c)
+    up = _umi(native)
+    a = ctx.pipeline_cells(cid, af, nf, _sp(native, family_model=1, engine=native.ENGINE_FUSED), up)
+    b = ctx.pipeline_cells(cid, af, nf, _sp(native, family_model=1), up)
+    for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+        assert (a[k_] == b[k_]).all(), k_
+    assert a["mean_error_rate"] == b["mean_error_rate"]
+    with pytest.raises(native.NativeError):
+        ctx.pipeline_cells(cid, af, nf, _sp(native, engine=native.ENGINE_FUSED, hop_rate=0.01), up)
+
+
 @pytest.mark.parametrize("hop,coll", [(0.01, 0.0), (0.05, 0.02)])
 def test_pipeline_with_index_hopping_equals_oracle(ctx, native, hop, coll):
     """C4 (eval-contamination) read-level knobs through the plan: with hop_rate > 0 reads leave their cell, so the
