@@ -242,9 +242,214 @@ def lod_grid_wall(cfg, world=1, barrier=None):
     return out
 
 
+# ------------------------------------------------------------------------------- external reads
+EXT_B_READ = 42.4   # SURVEY.md §8d without the simulate stage: sort 24 + consensus 15.2 + call 3.2 B / read
+
+
+def external_reads(seed: int, n: int, n_loci: int):
+    """BASELINE.json configs[4] as EXTERNAL input (one sample): n reads over n_loci loci in random
+    order -- every read picks one of n / 5 molecules uniformly (family sizes ~ Poisson(5)), molecule m sits at locus
+    m mod n_loci and carries a hashed 24-bit UMI; qualities uniform on 10..40, 3 % alt reads.  NumPy, so that the
+    reference arm builds the very same arrays without a GPU."""
+    rng = np.random.default_rng(seed)
+    fam = rng.integers(0, max(1, n // 5), n)
+    umi = (fam.astype(np.uint64) * np.uint64(2654435761)) & np.uint64(0xFFFFFF)
+    keys = ((fam % n_loci).astype(np.uint64) << np.uint64(32)) | umi
+    q = rng.integers(10, 41, n).astype(np.uint32)
+    alt = (rng.random(n) < 0.03).astype(np.uint32)
+    payload = alt | (q << np.uint32(2)) | (alt << np.uint32(31))
+    return keys, payload
+
+
+def external_config(n, n_loci, world):
+    return {"workload": f"C5 panel as EXTERNAL reads: {n} reads per GPU over {n_loci} loci in random order (one sample per GPU) "
+                        "-> pmrd_collapse_reads (UMIProcessor.process_reads + get_consensus_counts)",
+            "reads_per_gpu": int(n), "loci": int(n_loci), "family_sizes": "~Poisson(5) (uniform molecule choice)", "umi": "12-mer (24 bit)",
+            "input_order": "random (i.i.d. molecule choice per read)", "l2": "inputs larger than L2 (12 B x reads vs 126 MB)",
+            "parallelism": f"sample axis sharded over {world} GPU(s)"}
+
+
+def external_cpu(keys, payload, n_loci, cfg, threads):
+    from oracle import cport
+
+    t0 = time.perf_counter()
+    r = cport.collapse_groups(keys, payload, n_loci, cfg.umi.min_family_size, cfg.umi.max_family_size, cfg.umi.quality_threshold,
+                              cfg.umi.consensus_threshold, n_threads=threads)
+    return r, time.perf_counter() - t0
+
+
+def run_external(args, rank, world, local_rank, emit):
+    """--workload external: the general collapse path on reads that arrive from outside, in arbitrary order."""
+    import torch
+    import torch.distributed as dist
+
+    from precise_mrd import _native as nv
+    from precise_mrd.config import load_config
+
+    cfg = load_config(ROOT / "precise-mrd-mini_b200" / "precise_mrd" / "assets" / "configs" / "default.yaml")
+    n = int(os.environ.get("PMRD_EXT_READS", 125_000_000))
+    n_loci = int(os.environ.get("PMRD_EXT_LOCI", 100_000))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = nv.Context(device=local_rank, seed=int(cfg.seed))
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    P = nv.UmiParams(min_family_size=cfg.umi.min_family_size, max_family_size=cfg.umi.max_family_size,
+                     quality_threshold=cfg.umi.quality_threshold, consensus_threshold=cfg.umi.consensus_threshold,
+                     mode=nv.MODE_WEIGHTED, cluster=nv.CLUSTER_EXACT, max_distance=0, umi_len=12)
+    keys, payload = external_reads(int(cfg.seed) + rank, n, n_loci)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm: pmrd_collapse_reads_dev on buffers already in HBM ---------------------------
+    dev = torch.device("cuda", local_rank)
+    k0 = torch.from_numpy(keys.view(np.int64)).to(dev)
+    p0 = torch.from_numpy(payload.view(np.int32)).to(dev)
+    dk, dp, dkt, dpt = torch.empty_like(k0), torch.empty_like(p0), torch.empty_like(k0), torch.empty_like(p0)
+    fcap = n
+    fam_t = {"key": torch.empty(fcap, dtype=torch.int64, device=dev)}
+    for name in ("size", "n_alt", "consensus", "qsum", "n_best", "flags"):
+        fam_t[name] = torch.empty(fcap, dtype=torch.int32, device=dev)
+    gcap = n_loci + 16
+    grp_t = {"group": torch.empty(gcap, dtype=torch.int32, device=dev), "family_count": torch.empty(gcap, dtype=torch.int32, device=dev),
+             "consensus_count": torch.empty(gcap * 4, dtype=torch.int32, device=dev), "alt_count": torch.empty(gcap, dtype=torch.int64, device=dev),
+             "total_count": torch.empty(gcap, dtype=torch.int64, device=dev)}
+    fam_p = {k: v.data_ptr() for k, v in fam_t.items()}
+    grp_p = {k: v.data_ptr() for k, v in grp_t.items()}
+
+    def step_dev():
+        dk.copy_(k0); dp.copy_(p0)                                   # restore the inputs (the call clobbers them): untimed
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        nf, ng = ctx.collapse_reads_dev(dk.data_ptr(), dp.data_ptr(), dkt.data_ptr(), dpt.data_ptr(), n, P, fam_p, fcap, grp_p, gcap)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), nf, ng
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    barrier()
+    launches0 = ctx.launch_count
+    ms = 0.0
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.steps):
+            dt, nf, ng = step_dev()
+            ms += dt
+        barrier()
+    launches = ctx.launch_count - launches0
+    ctx.profile_enable(True)
+    for _ in range(args.steps):
+        step_dev()
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+    d_fc = grp_t["family_count"][:ng].cpu().numpy().astype(np.uint32)
+    d_cc = grp_t["consensus_count"][:ng * 4].cpu().numpy().astype(np.uint32).reshape(ng, 4)
+
+    # ---- end-to-end arm: host (pageable NumPy) arrays in, the per-locus table out, every step --------------
+    ctx.collapse_reads(keys, payload, P, want_families=False)        # warm the allocator pool and the pinned ring
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fam_h, grp_h = ctx.collapse_reads(keys, payload, P, want_families=False)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = int(keys.nbytes + payload.nbytes)
+    d2h = int(sum(v.nbytes for v in grp_h.values()))
+    assert (grp_h["family_count"] == d_fc).all() and (grp_h["consensus_count"] == d_cc).all()
+    # with the family table as well (7 columns, 32 B per family)
+    t1 = time.perf_counter()
+    fam_h, _ = ctx.collapse_reads(keys, payload, P, want_families=True)
+    torch.cuda.synchronize()
+    e2e_fam_s = time.perf_counter() - t1
+    assert len(fam_h["key"]) == nf
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = [float(x) for x in t.tolist()]
+    value = float(n) * world * args.steps / (ms_max * 1e-3)
+    e2e_value = float(n) * world * args.steps / (e2e_ms_max * 1e-3)
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        total_prof_ms = sum(v[1] for v in prof.values()) or 1.0
+        kms = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:10]}
+        top_name, top = max(prof.items(), key=lambda kv: kv[1][1])
+        # bytes one launch of each kernel moves per read (its share of the data path)
+        per_launch = {"rs_downsweep_kernel<true>": 24.0, "rs_upsweep_kernel": 8.0, "group_rows_kernel": 12.0 + 32.0 / 5.0, "grp_count_kernel": 8.0,
+                      "family_kernel": 12.0 + 32.0 / 5.0, "group_rows_compact_kernel": 64.0 / 5.0}
+        b = next((v for k, v in per_launch.items() if top_name.startswith(k.split("<")[0])), None)
+        avg_ms = top[1] / max(top[0], 1)
+        ach = b * n / (avg_ms * 1e-3) / 1e9 if b else None
+        roof = {"bound": "hbm", "kernel": top_name, "launches": int(top[0]), "avg_launch_ms": avg_ms, "share_of_step": top[1] / total_prof_ms,
+                "algorithmic_bytes_per_launch": b * n if b else None, "bytes_per_record": b, "achieved": ach, "peak": peak,
+                "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": None,
+                "note": "partition pass over the group bits: R 12 + W 12 B per read and launch"}
+        line = {
+            "metric": METRIC.replace("simulate_collapse_call", "collapse_external"), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 key (group:32 | umi:32) + u32 payload, f64 consensus weights", "data": "synthetic",
+            "config": external_config(n, n_loci, world),
+            "layout": {"families": int(nf), "loci_with_reads": int(ng), "path": "group-major (count -> partition by group -> one block sorts and votes a locus)"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "Context.collapse_reads(keys, payload, want_families=False): pageable NumPy arrays through the pinned staging "
+                           "ring (csrc/staging.cu), per-locus table back",
+                    "with_family_table": {"value": float(n) / e2e_fam_s, "d2h_bytes": int(sum(v.nbytes for v in fam_h.values()))}},
+            "gpu_launches": int(launches), "roofline": roof,
+            "pipeline_roofline": {"algorithmic_bytes_per_read": EXT_B_READ, "achieved": value / world * EXT_B_READ / 1e9, "peak": peak, "unit": "GB/s",
+                                  "frac": value / world * EXT_B_READ / 1e9 / peak},
+            "kernels_ms_per_step": kms, "clocks": clocks.summary(), "reference_class": "cpu-port",
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = host_threads()
+            r, dt = external_cpu(keys, payload, n_loci, cfg, threads)
+            assert (r["family_count"][:ng] == d_fc).all() and (r["consensus_count"][:ng] == d_cc).all(), "device table != oracle table"
+            line["cpu_baseline"] = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"all {n} reads once in {dt:.2f} s; oracle/pmrd_oracle.c oracle_collapse_groups (bucket by locus, hash "
+                                              "the UMIs, weighted vote: umi.py:205-266), OpenMP over loci; its table equals the device's"}
+            line["result_check"] = {"families": int(nf), "equals_oracle": True}
+        emit(line)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 # ------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank, world, emit):
     if rank != 0:
+        return 0
+    if args.workload == "external":
+        from precise_mrd.config import load_config
+
+        cfg = load_config(ROOT / "precise-mrd-mini_b200" / "precise_mrd" / "assets" / "configs" / "default.yaml")
+        n_full = int(os.environ.get("PMRD_EXT_READS", 125_000_000))
+        n_loci = int(os.environ.get("PMRD_EXT_LOCI", 100_000))
+        n = int(os.environ.get("PMRD_REF_READS", min(n_full, 25_000_000)))         # bounded sample: a fifth of the reads, all loci
+        keys, payload = external_reads(int(cfg.seed), n, n_loci)
+        threads = host_threads()
+        for _ in range(args.warmup):
+            external_cpu(keys, payload, n_loci, cfg, threads)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            external_cpu(keys, payload, n_loci, cfg, threads)
+        dt = time.perf_counter() - t0
+        value = n * args.steps / dt
+        emit({"impl": "reference", "metric": METRIC.replace("simulate_collapse_call", "collapse_external"), "value": value, "unit": UNIT,
+              "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "u64 key (group:32 | umi:32) + u32 payload, f64 consensus weights",
+              "data": "synthetic", "config": external_config(n_full, n_loci, args.gpus),
+              "sample": f"{n} of {n_full} reads per step over all {n_loci} loci; value is a rate",
+              "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": f"{n} reads per step; oracle/pmrd_oracle.c oracle_collapse_groups (umi.py:205-266), OpenMP over loci"},
+              "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+              "reference_class": "cpu-port"})
         return 0
     fused = args.workload == "fused"
     cfg, label, cell_id, af, depth = workload("default" if fused else args.workload, 0, 1)
@@ -312,6 +517,8 @@ def main() -> int:
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    if args.workload == "external":
+        return run_external(args, rank, world, local_rank, emit)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

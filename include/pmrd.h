@@ -181,7 +181,10 @@ typedef struct pmrd_group_table {
  * capacity_f / capacity_g: entries available in the output tables; *n_families /
  * *n_groups receive the counts (PMRD_ERR_CAPACITY if too small; n <= n_reads always
  * suffices).  The family table lists ALL families (flags tell kept/consensus), so that
- * the host can apply either generation's filtering order. */
+ * the host can apply either generation's filtering order.  h_fam->key == NULL: the family rows are
+ * not downloaded (only *n_families and the group table leave the device).  Large pageable host buffers
+ * move through a ring of pinned staging buffers filled by a few host threads (csrc/staging.cu), so the
+ * call runs at the PCIe / host-memcpy rate instead of the driver's single-threaded pageable path. */
 int32_t pmrd_collapse_reads(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_t* h_payload,
                             int64_t n_reads, const pmrd_umi_params* params,
                             pmrd_family_table* h_fam, int64_t capacity_f, int64_t* n_families,

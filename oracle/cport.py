@@ -21,6 +21,7 @@ def load():
         _lib = C.CDLL(str(LIB))
         _lib.oracle_collapse_weighted.restype = C.c_int64
         _lib.oracle_pipeline_cells.restype = C.c_int64
+        _lib.oracle_collapse_groups.restype = C.c_int64
         _lib.oracle_poisson_two_sided.restype = C.c_double
         _lib.oracle_poisson_two_sided.argtypes = [C.c_int64, C.c_double]
         _lib.oracle_max_threads.restype = C.c_int
@@ -42,6 +43,18 @@ def collapse_weighted(keys, payload, min_fs, max_fs, qthr, cthr):
     nf = lib.oracle_collapse_weighted(_p(keys), _p(payload), C.c_int64(n), C.c_int(min_fs), C.c_int(max_fs), C.c_int(qthr),
                                       C.c_double(cthr), *[_p(out[k]) for k in ("key", "size", "n_alt", "consensus", "qsum", "n_best", "flags")])
     return {k: v[:nf] for k, v in out.items()}
+
+
+def collapse_groups(keys, payload, n_ids, min_fs, max_fs, qthr, cthr, n_threads=0):
+    """Group table of external panel reads (dense group ids < n_ids): kept families, consensus counts per allele,
+    families formed -- umi.py:205-266 per group, OpenMP over groups."""
+    lib = load()
+    keys = np.ascontiguousarray(keys, np.uint64)
+    payload = np.ascontiguousarray(payload, np.uint32)
+    fc, cc, ff = np.zeros(n_ids, np.uint32), np.zeros((n_ids, 4), np.uint32), np.zeros(n_ids, np.uint32)
+    total = lib.oracle_collapse_groups(_p(keys), _p(payload), C.c_int64(len(keys)), C.c_int64(n_ids), C.c_int(min_fs), C.c_int(max_fs),
+                                       C.c_int(qthr), C.c_double(cthr), _p(fc), _p(cc), _p(ff), C.c_int(n_threads))
+    return {"family_count": fc, "consensus_count": cc, "families_formed": ff, "total_families": int(total)}
 
 
 def pipeline_cells(cell_id, af, n_families, seed, mean_family_size=5.0, family_model=1, max_family_size=1000, min_fs=3,

@@ -197,6 +197,65 @@ int64_t oracle_collapse_weighted(const uint64_t* keys, const uint32_t* payload, 
     return total_f;
 }
 
+/* External reads of a panel (dense group ids < n_ids, any order): the group table of UMIProcessor.process_reads +
+ * get_consensus_counts (umi.py:205-266).  Reads are bucketed by group in input order (a counting sort of the read
+ * indices), then every group goes through collapse_group, groups spread over the OpenMP team.  This is the CPU
+ * baseline of bench.py --workload external and a checker of the device group table at sizes the whole-array
+ * entry point above (O(groups x reads)) cannot reach. */
+int64_t oracle_collapse_groups(const uint64_t* keys, const uint32_t* payload, int64_t n, int64_t n_ids, int min_fs, int max_fs,
+                               int qthr, double cthr, uint32_t* family_count /*[n_ids]: kept*/, uint32_t* consensus_count /*[n_ids*4]*/,
+                               uint32_t* families_formed /*[n_ids]*/, int n_threads) {
+    double wtab[64];
+    for (int q = 0; q < 64; ++q) wtab[q] = pow(10.0, (double)q / 10.0);
+    int64_t* start = (int64_t*)calloc((size_t)(n_ids + 1), 8);
+    for (int64_t i = 0; i < n; ++i) start[(keys[i] >> 32) + 1]++;
+    for (int64_t g = 0; g < n_ids; ++g) start[g + 1] += start[g];
+    int64_t* cur = (int64_t*)malloc(8 * (size_t)(n_ids + 1));
+    memcpy(cur, start, 8 * (size_t)(n_ids + 1));
+    uint32_t* u = (uint32_t*)malloc(4 * (size_t)(n + 1));
+    uint32_t* p = (uint32_t*)malloc(4 * (size_t)(n + 1));
+    for (int64_t i = 0; i < n; ++i) {              /* stable: input order inside a group */
+        const int64_t d = cur[keys[i] >> 32]++;
+        u[d] = (uint32_t)keys[i];
+        p[d] = payload[i];
+    }
+    int64_t total = 0;
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+#pragma omp parallel reduction(+ : total)
+    {
+        int64_t cap = 0;
+        fam_rec* rec = NULL;
+        int32_t* work = NULL;
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t g = 0; g < n_ids; ++g) {
+            const int64_t m = start[g + 1] - start[g];
+            family_count[g] = 0; families_formed[g] = 0;
+            consensus_count[4 * g] = consensus_count[4 * g + 1] = consensus_count[4 * g + 2] = consensus_count[4 * g + 3] = 0;
+            if (m == 0) continue;
+            const int64_t ts = pow2_at_least(2 * m);
+            if (m > cap) {
+                cap = 2 * m;
+                free(rec); free(work);
+                rec = (fam_rec*)malloc(sizeof(fam_rec) * (size_t)(cap + 1));
+                work = (int32_t*)malloc(sizeof(int32_t) * (size_t)(2 * cap + pow2_at_least(2 * cap)));
+            }
+            const int64_t nf = collapse_group(u + start[g], p + start[g], m, min_fs, max_fs, qthr, cthr, wtab, rec, work, ts);
+            families_formed[g] = (uint32_t)nf;
+            total += nf;
+            for (int64_t f = 0; f < nf; ++f) {
+                if (!(rec[f].flags & FAM_KEPT)) continue;         /* umi.py:186 */
+                family_count[g]++;
+                if (rec[f].flags & FAM_HAS_CONSENSUS) consensus_count[4 * g + (rec[f].consensus & 3u)]++;   /* umi.py:246-251 */
+            }
+        }
+        free(rec); free(work);
+    }
+    free(start); free(cur); free(u); free(p);
+    return total;
+}
+
 /* ------------------------------------------------------------------ statistics ---------- */
 /* Regularised incomplete gamma by series / continued fraction (the textbook pair the
  * reference reaches through scipy.special.pdtr / pdtrc). */

@@ -118,6 +118,7 @@ int32_t pmrd_create(int32_t device, uint64_t seed, pmrd_ctx** out) {
     ctx->launches = 0;
     ctx->prof_on = 0;
     ctx->prof = nullptr;
+    ctx->stager = nullptr;
     ctx->err[0] = 0;
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
@@ -154,6 +155,7 @@ void pmrd_destroy(pmrd_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    pmrd_stager_destroy(ctx);
     cudaStreamDestroy(ctx->own_stream);
     if (ctx->prof) {
         PmrdProf* p = (PmrdProf*)ctx->prof;
@@ -240,12 +242,10 @@ int64_t pmrd_profile_report(pmrd_ctx* ctx, char* buf, int64_t cap) {
 
 static int32_t up(pmrd_ctx* ctx, DevBuf& b, const void* h, size_t bytes) {
     PMRD_CUDA(ctx, b.alloc(ctx->stream, bytes));
-    if (bytes) PMRD_CUDA(ctx, cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return PMRD_OK;
+    return pmrd_stage_up(ctx, b.p, h, bytes);     // (large pageable buffers go through the pinned ring: staging.cu)
 }
 static int32_t down(pmrd_ctx* ctx, void* h, const void* d, size_t bytes) {
-    if (bytes && h) PMRD_CUDA(ctx, cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    return PMRD_OK;
+    return pmrd_stage_down(ctx, h, d, bytes);
 }
 
 extern "C" {
@@ -428,10 +428,13 @@ int32_t pmrd_collapse_reads(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_
                          &dfam, n_reads, &nf, want_groups ? &dgrp : nullptr, n_reads, want_groups ? &ng : nullptr));
     *n_families = nf;
     if (n_groups) *n_groups = ng;
-    if (nf > capacity_f || (want_groups && ng > capacity_g)) {
+    const bool want_fam = h_fam->key != nullptr;          // NULL columns: the family rows stay on the device
+    if ((want_fam && nf > capacity_f) || (want_groups && ng > capacity_g)) {
         snprintf(ctx->err, sizeof(ctx->err), "output capacity too small: %lld families, %lld groups", (long long)nf, (long long)ng);
         return PMRD_ERR_CAPACITY;
     }
+    if (want_fam) PMRD_ARG(ctx, h_fam->size && h_fam->n_alt && h_fam->consensus && h_fam->qsum && h_fam->n_best && h_fam->flags, "family table columns");
+    if (!want_fam) nf = 0;                                 // (nothing to download; *n_families already holds the count)
     PMRD_TRY(down(ctx, h_fam->key, dfam.key, (size_t)nf * 8));
     PMRD_TRY(down(ctx, h_fam->size, dfam.size, (size_t)nf * 4));
     PMRD_TRY(down(ctx, h_fam->n_alt, dfam.n_alt, (size_t)nf * 4));

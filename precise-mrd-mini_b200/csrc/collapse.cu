@@ -127,27 +127,17 @@ struct FamOut {
     uint32_t *size, *n_alt, *consensus, *qsum, *n_best, *flags;
 };
 
-template <int MODE, bool GATHER>
-__global__ void __launch_bounds__(128)
-family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload_or_idx,
-              const uint64_t* __restrict__ keys_orig, const uint32_t* __restrict__ payload_orig,
-              const uint32_t* __restrict__ fam_start, const uint32_t* __restrict__ d_nfam, int64_t fam_cap,
-              pmrd_umi_params P, uint32_t sentinel_umi, FamOut out) {
-    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= (int64_t)*d_nfam || f >= fam_cap) return;
-    const uint32_t lo = fam_start[f], hi = fam_start[f + 1];
-    const uint32_t size = hi - lo;
-    uint64_t key = keys[lo];
-    if (GATHER) key = (key & 0xffffffff00000000ull) | (keys_orig[payload_or_idx[lo]] & 0xffffffffull);
-
-    uint32_t n_alt = 0, consensus = 0, qsum_best = 0, n_best = 0, flags = 0;
-
+// One family's row from its reads in input order; pl_at(i) = payload of read i of the family.
+template <int MODE, typename PlAt>
+__device__ __forceinline__ void family_row(uint32_t size, PlAt pl_at, const pmrd_umi_params& P, uint32_t& n_alt, uint32_t& consensus,
+                                           uint32_t& qsum_best, uint32_t& n_best, uint32_t& flags) {
+    n_alt = 0; consensus = 0; qsum_best = 0; n_best = 0; flags = 0;
     if (MODE == PMRD_MODE_WEIGHTED) {
         double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, total = 0.0;
         uint32_t qs0 = 0, qs1 = 0, qs2 = 0, qs3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
         uint32_t order = 0, seen = 0, n_seen = 0;  // order: 2 bits per allele = rank of first appearance
-        for (uint32_t r = lo; r < hi; ++r) {
-            const uint32_t pl = GATHER ? payload_orig[payload_or_idx[r]] : payload_or_idx[r];
+        for (uint32_t r = 0; r < size; ++r) {
+            const uint32_t pl = pl_at(r);
             n_alt += pl >> 31;
             const uint32_t a = pl & 3u, q = (pl >> 2) & 63u;
             if ((int)q >= P.quality_threshold) {
@@ -198,8 +188,8 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
         uint32_t ord[10];
 #pragma unroll
         for (int c = 0; c < 10; ++c) { cnt[c] = 0; ord[c] = 0; }
-        for (uint32_t r = lo; r < hi; ++r) {
-            const uint32_t pl = GATHER ? payload_orig[payload_or_idx[r]] : payload_or_idx[r];
+        for (uint32_t r = 0; r < size; ++r) {
+            const uint32_t pl = pl_at(r);
             n_alt += pl >> 31;
 #pragma unroll
             for (int c = 0; c < 10; ++c) {
@@ -232,14 +222,28 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
         consensus = seq;
         flags |= PMRD_FAM_HAS_CONSENSUS;
     } else {
-        for (uint32_t r = lo; r < hi; ++r) {
-            const uint32_t pl = GATHER ? payload_orig[payload_or_idx[r]] : payload_or_idx[r];
-            n_alt += pl >> 31;
-        }
+        for (uint32_t r = 0; r < size; ++r) n_alt += pl_at(r) >> 31;
         flags |= PMRD_FAM_HAS_CONSENSUS;
     }
     if ((int64_t)size >= (int64_t)P.min_family_size) flags |= PMRD_FAM_KEPT;
     if ((int64_t)size > (int64_t)P.max_family_size) flags |= PMRD_FAM_OVERSIZE;
+}
+
+template <int MODE, bool GATHER>
+__global__ void __launch_bounds__(128)
+family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload_or_idx,
+              const uint64_t* __restrict__ keys_orig, const uint32_t* __restrict__ payload_orig,
+              const uint32_t* __restrict__ fam_start, const uint32_t* __restrict__ d_nfam, int64_t fam_cap,
+              pmrd_umi_params P, uint32_t sentinel_umi, FamOut out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= (int64_t)*d_nfam || f >= fam_cap) return;
+    const uint32_t lo = fam_start[f], hi = fam_start[f + 1];
+    const uint32_t size = hi - lo;
+    uint64_t key = keys[lo];
+    if (GATHER) key = (key & 0xffffffff00000000ull) | (keys_orig[payload_or_idx[lo]] & 0xffffffffull);
+    uint32_t n_alt, consensus, qsum_best, n_best, flags;
+    family_row<MODE>(size, [&](uint32_t r) -> uint32_t { return GATHER ? payload_orig[payload_or_idx[lo + r]] : payload_or_idx[lo + r]; },
+                     P, n_alt, consensus, qsum_best, n_best, flags);
     if (sentinel_umi != 0u && (((uint32_t)key) >> 24) == 0xffu) flags = 0;  // padding of a tile-aligned cell
     out.key[f] = key;
     out.size[f] = size;
@@ -897,6 +901,191 @@ greedy_assign_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict
     keys_out[si[r]] = (sk[r] & 0xffffffff00000000ull) | ucluster[lo];
 }
 
+// ---------------------------------------------------------------- external reads: group-major fast path ----
+// pmrd_collapse_reads on reads in ARBITRARY order (UMIProcessor.process_reads src/precise_mrd/umi.py:205-285,
+// group_umis_fast rust_ext/src/lib.rs:7-109, mrd/umi.py:57-115 EXACT clustering) when the group ids are dense
+// (< 2^22) and no group holds more than 4096 reads -- a panel of loci, the shape of BASELINE.json configs[4].
+// The full-key sort (6 passes of 12 + 12 B for a 17-bit group and a 24-bit UMI) becomes
+//   count      reads per group id (one pass over the keys, L2 atomics)             -> eligibility + group starts
+//   partition  stable LSD radix passes over the GROUP bits only (2-3 passes)        -> reads group-major, input order kept
+//   group_rows one block per group: loads the group, sorts it on the UMI bits inside shared memory (ranked passes of the
+//              tile kernels, stable), finds the family heads and votes every family -> family rows, written where
+//              the group's reads start (a group has at most as many families as reads)
+//   compact    scan of the per-group family counts, rows moved to their final place -> the family table, sorted by key
+// The consensus arithmetic is family_row(), the one family_kernel runs.
+__global__ void __launch_bounds__(256)
+grp_count_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ cnt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[(uint32_t)(keys[i] >> 32)], 1u);
+}
+__global__ void __launch_bounds__(256)
+grp_max_kernel(const uint32_t* __restrict__ cnt, int64_t n_ids, uint32_t* __restrict__ out /*[2]: max size, groups with reads*/) {
+    uint32_t mx = 0, ne = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ids; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = cnt[i];
+        mx = max(mx, c);
+        ne += c > 0;
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    ne = warp_sum(ne);
+    if ((threadIdx.x & 31) == 0) { atomicMax(&out[0], mx); atomicAdd(&out[1], ne); }
+}
+
+#define GR_THREADS 256
+template <int ITEMS, int MODE>
+__global__ void __launch_bounds__(GR_THREADS)
+group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload, const uint32_t* __restrict__ grp_start,
+                  const uint32_t* __restrict__ grp_cnt, int n_rounds, pmrd_umi_params P, FamOut tmp, uint32_t* __restrict__ fam_cnt) {
+    constexpr int CAP = GR_THREADS * ITEMS, WARPS = GR_THREADS / 32, PER_WARP = CAP / WARPS;
+    extern __shared__ __align__(16) unsigned char gr_raw[];
+    uint64_t* const s_rec = reinterpret_cast<uint64_t*>(gr_raw);                 // payload:32 | umi:32
+    uint32_t (*s_cnt)[256] = reinterpret_cast<uint32_t (*)[256]>(s_rec + CAP);
+    uint32_t* const s_base = &s_cnt[0][0] + WARPS * 256;
+    uint32_t* const sw = s_base + 256;                                           // [33]
+    uint16_t* const s_list = reinterpret_cast<uint16_t*>(sw + 36);                // [CAP]
+    __shared__ uint32_t s_nheads;
+    const uint32_t g = blockIdx.x;
+    const int n = (int)grp_cnt[g];
+    if (n == 0) { if (threadIdx.x == 0) fam_cnt[g] = 0u; return; }
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = lanemask_lt();
+    const uint32_t lo = grp_start[g];
+    uint64_t key[ITEMS];
+#pragma unroll
+    for (int i = 0; i < ITEMS; ++i) {
+        const int loc = (int)warp * PER_WARP + i * 32 + (int)lane;
+        // filler: UMI word 0xFFFFFFFF sorts last; a REAL UMI of that value sits before the fillers and stays there (stable)
+        key[i] = loc < n ? (((uint64_t)payload[lo + loc] << 32) | (uint32_t)keys[lo + loc]) : 0xffffffffull;
+    }
+    if (threadIdx.x == 0) s_nheads = 0u;
+#pragma unroll 1
+    for (int rd = 0; rd < n_rounds; ++rd) {
+        const int shift = rd * 8;
+        for (int i = threadIdx.x; i < WARPS * 256; i += GR_THREADS) (&s_cnt[0][0])[i] = 0u;
+        __syncthreads();
+        uint32_t rank2[(ITEMS + 1) / 2];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = ((uint32_t)key[i] >> shift) & 0xffu;
+            const uint32_t m = rs_peer_mask(d, 0xffffffffu);
+            const uint32_t before = __popc(m & lt);
+            const int leader = __ffs((int)m) - 1;
+            uint32_t old = 0;
+            if (before == 0) old = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(m));
+            old = __shfl_sync(0xffffffffu, old, leader);
+            const uint32_t r = old + before;
+            if (i & 1) rank2[i >> 1] |= r << 16;
+            else rank2[i >> 1] = r;
+        }
+        __syncthreads();
+        {
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = s_cnt[w][threadIdx.x];
+                s_cnt[w][threadIdx.x] = run;
+                run += c;
+            }
+            uint32_t tot;
+            s_base[threadIdx.x] = block_exclusive_scan<uint32_t>(run, sw, tot);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const uint32_t d = ((uint32_t)key[i] >> shift) & 0xffu;
+            const uint32_t r = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
+            s_rec[s_base[d] + s_cnt[warp][d] + r] = key[i];
+        }
+        __syncthreads();
+        if (rd + 1 < n_rounds) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) key[i] = s_rec[warp * PER_WARP + i * 32 + lane];
+        }
+    }
+    if (n_rounds == 0) {                          // one UMI in the whole input: nothing to order
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) s_rec[warp * PER_WARP + i * 32 + lane] = key[i];
+        __syncthreads();
+    }
+    // family heads, compacted in order
+    for (int i0 = 0; i0 < n; i0 += GR_THREADS) {
+        const int i = i0 + (int)threadIdx.x;
+        const bool head = i < n && (i == 0 || (uint32_t)s_rec[i - 1] != (uint32_t)s_rec[i]);
+        const uint32_t hm = __ballot_sync(0xffffffffu, head);
+        uint32_t wcount = __popc(hm), excl;
+        // (ordered across the warps of this sweep: prefix over the warps through shared memory)
+        if (lane == 0) sw[warp] = wcount;
+        __syncthreads();
+        excl = 0;
+        for (uint32_t w = 0; w < warp; ++w) excl += sw[w];
+        uint32_t all = 0;
+        for (uint32_t w = 0; w < (uint32_t)WARPS; ++w) all += sw[w];
+        const uint32_t base = s_nheads;
+        if (head) s_list[base + excl + __popc(hm & lt)] = (uint16_t)i;
+        __syncthreads();
+        if (threadIdx.x == 0) s_nheads = base + all;
+        __syncthreads();
+    }
+    const int n_heads = (int)s_nheads;
+    const uint64_t ghi = keys[lo] & 0xffffffff00000000ull;
+    for (int h = threadIdx.x; h < n_heads; h += GR_THREADS) {
+        const int i = (int)s_list[h];
+        const int end = h + 1 < n_heads ? (int)s_list[h + 1] : n;
+        uint32_t n_alt, consensus, qsum_best, n_best, flags;
+        family_row<MODE>((uint32_t)(end - i), [&](uint32_t r) -> uint32_t { return (uint32_t)(s_rec[i + r] >> 32); }, P, n_alt, consensus,
+                         qsum_best, n_best, flags);
+        const size_t o = (size_t)lo + h;
+        tmp.key[o] = ghi | (uint32_t)s_rec[i];
+        tmp.size[o] = (uint32_t)(end - i);
+        tmp.n_alt[o] = n_alt;
+        tmp.consensus[o] = consensus;
+        tmp.qsum[o] = qsum_best;
+        tmp.n_best[o] = n_best;
+        tmp.flags[o] = flags;
+    }
+    if (threadIdx.x == 0) fam_cnt[g] = (uint32_t)n_heads;
+}
+
+// rows of group g: tmp[grp_start[g] .. + fam_cnt[g])  ->  out[fam_base[g] ..)
+__global__ void __launch_bounds__(128)
+group_rows_compact_kernel(const uint32_t* __restrict__ grp_start, const uint32_t* __restrict__ fam_cnt, const uint32_t* __restrict__ fam_base,
+                          int64_t fam_cap, FamOut tmp, FamOut out) {
+    const uint32_t g = blockIdx.x;
+    const uint32_t n = fam_cnt[g], src = grp_start[g], dst = fam_base[g];
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+        if ((int64_t)(dst + k) >= fam_cap) break;
+        out.key[dst + k] = tmp.key[src + k];
+        out.size[dst + k] = tmp.size[src + k];
+        out.n_alt[dst + k] = tmp.n_alt[src + k];
+        out.consensus[dst + k] = tmp.consensus[src + k];
+        out.qsum[dst + k] = tmp.qsum[src + k];
+        out.n_best[dst + k] = tmp.n_best[src + k];
+        out.flags[dst + k] = tmp.flags[src + k];
+    }
+}
+
+static size_t group_rows_smem(int items) {
+    const size_t cap = (size_t)GR_THREADS * items;
+    return cap * 8 + (GR_THREADS / 32) * 256 * 4 + 256 * 4 + 36 * 4 + cap * 2 + 16;
+}
+
+template <int MODE>
+static int32_t launch_group_rows(pmrd_ctx* ctx, int64_t max_group, int64_t n_ids, const uint64_t* keys, const uint32_t* payload,
+                                 const uint32_t* grp_start, const uint32_t* grp_cnt, int n_rounds, const pmrd_umi_params& P, FamOut tmp,
+                                 uint32_t* fam_cnt) {
+#define GR_CASE(I)                                                                                                                  \
+    if (max_group <= (int64_t)GR_THREADS * (I)) {                                                                                   \
+        const size_t smem = group_rows_smem(I);                                                                                     \
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(group_rows_kernel<I, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
+        PMRD_LAUNCH_NAMED(ctx, "group_rows_kernel", (group_rows_kernel<I, MODE>), (int)n_ids, GR_THREADS, smem, keys, payload, grp_start, \
+                          grp_cnt, n_rounds, P, tmp, fam_cnt);                                                                       \
+        return PMRD_OK;                                                                                                             \
+    }
+    GR_CASE(1) GR_CASE(2) GR_CASE(4) GR_CASE(6) GR_CASE(8) GR_CASE(12) GR_CASE(16)
+#undef GR_CASE
+    return PMRD_ERR_ARG;
+}
+
 // ---------------------------------------------------------------- driver ----------------
 template <bool GATHER>
 static int32_t launch_family(pmrd_ctx* ctx, int mode, const uint64_t* keys, const uint32_t* pl_or_idx,
@@ -951,6 +1140,82 @@ int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pa
     return PMRD_OK;
 }
 
+// EXACT clustering, external reads: the group-major fast path (see above).  *done = false: not eligible (sparse or
+// huge group ids, a group of more than 4096 reads): nothing was changed, the caller runs the full-key sort.
+#define GR_MAX_IDS (1ll << 22)
+#define GR_MAX_GROUP 4096
+static int32_t k5_collapse_groups_fast(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp, uint32_t* d_payload_tmp,
+                                       int64_t n_reads, const pmrd_umi_params& P, const pmrd_family_table* d_fam, int64_t fcap,
+                                       const pmrd_group_table* d_grp, int64_t gcap, uint32_t* d_grp_start, uint32_t* d_counts,
+                                       bool* done, int64_t* nf_out, int64_t* ng_out) {
+    *done = false;
+    static_assert(GR_MAX_GROUP == GR_THREADS * 16, "the largest group_rows_kernel instance holds GR_MAX_GROUP reads");
+    const char* env = getenv("PMRD_GROUP_FAST");
+    if (env && atoi(env) == 0) return PMRD_OK;
+    uint64_t varying = 0, all_or = 0;
+    PMRD_TRY(radix_varying_bits(ctx, d_keys, n_reads, &varying, &all_or));
+    const int64_t n_ids = (int64_t)(all_or >> 32) + 1;
+    if (n_ids > GR_MAX_IDS || n_ids > n_reads + 1024) return PMRD_OK;
+    DevBuf cnt, start, mx, fcnt;
+    PMRD_CUDA(ctx, cnt.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
+    PMRD_CUDA(ctx, start.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
+    PMRD_CUDA(ctx, mx.alloc(ctx->stream, 8));
+    PMRD_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, (size_t)(n_ids + 1) * 4, ctx->stream));
+    PMRD_CUDA(ctx, cudaMemsetAsync(mx.p, 0, 8, ctx->stream));
+    int grid = (int)((n_reads + 255) / 256);
+    if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
+    PMRD_LAUNCH(ctx, grp_count_kernel, grid, 256, 0, (const uint64_t*)d_keys, n_reads, cnt.as<uint32_t>());
+    int g2 = (int)((n_ids + 255) / 256);
+    if (g2 > ctx->sm_count * 8) g2 = ctx->sm_count * 8;
+    PMRD_LAUNCH(ctx, grp_max_kernel, g2, 256, 0, (const uint32_t*)cnt.as<uint32_t>(), n_ids, mx.as<uint32_t>());
+    uint32_t h_mx[2] = {0, 0};
+    PMRD_CUDA(ctx, cudaMemcpyAsync(h_mx, mx.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_mx[0] > GR_MAX_GROUP) return PMRD_OK;
+    *done = true;
+    // group starts (over the id space) and the stable partition by group
+    PMRD_TRY((exclusive_scan<uint32_t, uint32_t>(ctx, cnt.as<uint32_t>(), start.as<uint32_t>(), n_ids, (uint32_t*)nullptr)));
+    int in_b = 0;
+    PMRD_TRY(radix_sort_pairs(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, varying & 0xffffffff00000000ull, &in_b));
+    const uint64_t* sk = in_b ? d_keys_tmp : d_keys;
+    const uint32_t* sp = in_b ? d_payload_tmp : d_payload;
+    int ubits = 0;
+    while (ubits < 32 && (varying & 0xffffffffull) >> ubits) ++ubits;
+    const int n_rounds = (ubits + 7) / 8;
+    DevBuf tk, ts, ta, tc, tq, tn, tf;
+    const size_t n = (size_t)n_reads;
+    PMRD_CUDA(ctx, tk.alloc(ctx->stream, n * 8)); PMRD_CUDA(ctx, ts.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, ta.alloc(ctx->stream, n * 4));
+    PMRD_CUDA(ctx, tc.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, tq.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, tn.alloc(ctx->stream, n * 4));
+    PMRD_CUDA(ctx, tf.alloc(ctx->stream, n * 4));
+    PMRD_CUDA(ctx, fcnt.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
+    FamOut tmp{tk.as<uint64_t>(), ts.as<uint32_t>(), ta.as<uint32_t>(), tc.as<uint32_t>(), tq.as<uint32_t>(), tn.as<uint32_t>(), tf.as<uint32_t>()};
+    if (P.mode == PMRD_MODE_WEIGHTED)
+        PMRD_TRY(launch_group_rows<PMRD_MODE_WEIGHTED>(ctx, h_mx[0], n_ids, sk, sp, start.as<uint32_t>(), cnt.as<uint32_t>(), n_rounds, P, tmp, fcnt.as<uint32_t>()));
+    else if (P.mode == PMRD_MODE_MAJORITY)
+        PMRD_TRY(launch_group_rows<PMRD_MODE_MAJORITY>(ctx, h_mx[0], n_ids, sk, sp, start.as<uint32_t>(), cnt.as<uint32_t>(), n_rounds, P, tmp, fcnt.as<uint32_t>()));
+    else
+        PMRD_TRY(launch_group_rows<PMRD_MODE_COUNT>(ctx, h_mx[0], n_ids, sk, sp, start.as<uint32_t>(), cnt.as<uint32_t>(), n_rounds, P, tmp, fcnt.as<uint32_t>()));
+    // family counts -> row offsets; the total is the family count of the call
+    DevBuf fbase;
+    PMRD_CUDA(ctx, fbase.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
+    PMRD_TRY((exclusive_scan<uint32_t, uint32_t>(ctx, fcnt.as<uint32_t>(), fbase.as<uint32_t>(), n_ids, d_counts)));
+    FamOut out{d_fam->key, d_fam->size, d_fam->n_alt, d_fam->consensus, d_fam->qsum, d_fam->n_best, d_fam->flags};
+    PMRD_LAUNCH(ctx, group_rows_compact_kernel, (int)n_ids, 128, 0, (const uint32_t*)start.as<uint32_t>(), (const uint32_t*)fcnt.as<uint32_t>(),
+                (const uint32_t*)fbase.as<uint32_t>(), fcap, tmp, out);
+    PMRD_TRY(read_count(ctx, d_counts, nf_out));
+    *ng_out = 0;
+    if (d_grp && *nf_out <= fcap) {
+        PMRD_TRY(find_segments_dev(ctx, d_fam->key, *nf_out, nullptr, 32, gcap, d_grp_start, d_counts + 1));
+        int ggrid = (int)(gcap < (int64_t)ctx->sm_count * 32 ? gcap : (int64_t)ctx->sm_count * 32);
+        if (ggrid < 1) ggrid = 1;
+        PMRD_LAUNCH(ctx, group_kernel, ggrid, 128, 0, (const uint64_t*)d_fam->key, (const uint32_t*)d_fam->size,
+                    (const uint32_t*)d_fam->n_alt, (const uint32_t*)d_fam->consensus, (const uint32_t*)d_fam->flags,
+                    (const uint32_t*)d_grp_start, (const uint32_t*)(d_counts + 1), gcap, P.mode == PMRD_MODE_WEIGHTED ? 1 : 0, *d_grp);
+        PMRD_TRY(read_count(ctx, d_counts + 1, ng_out));
+    }
+    return PMRD_OK;
+}
+
 int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp, uint32_t* d_payload_tmp,
                     int64_t n_reads, const pmrd_umi_params* params, const pmrd_family_table* d_fam, int64_t capacity_f,
                     int64_t* n_families, const pmrd_group_table* d_grp, int64_t capacity_g, int64_t* n_groups) {
@@ -974,7 +1239,13 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
     PMRD_CUDA(ctx, cudaMemsetAsync(counts.p, 0, 8, ctx->stream));
     int64_t nf = 0, ng = 0;
 
-    if (P.cluster == PMRD_CLUSTER_EXACT) {
+    bool fast_done = false;
+    if (P.cluster == PMRD_CLUSTER_EXACT)
+        PMRD_TRY(k5_collapse_groups_fast(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, P, d_fam, fcap, want_groups ? d_grp : nullptr,
+                                         gcap, grp_start.as<uint32_t>(), counts.as<uint32_t>(), &fast_done, &nf, &ng));
+    if (fast_done) {
+        // (family table and group table are in place; the counts were read back)
+    } else if (P.cluster == PMRD_CLUSTER_EXACT) {
         PMRD_TRY(k5_collapse_exact_nosync(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, 0, params, d_fam, fcap,
                                           want_groups ? d_grp : nullptr, gcap, fam_start.as<uint32_t>(), grp_start.as<uint32_t>(),
                                           counts.as<uint32_t>(), nullptr, 0, 0));

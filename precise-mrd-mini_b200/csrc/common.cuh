@@ -19,9 +19,13 @@ struct pmrd_ctx {
     int64_t launches;
     int prof_on;   // per-kernel CUDA-event timing (pmrd_profile_enable)
     void* prof;    // opaque: api.cu
+    void* stager;  // opaque: staging.cu (pinned ring + copy threads, created on the first large pageable copy)
     char err[512];
 };
 
+int32_t pmrd_stage_up(pmrd_ctx* ctx, void* d, const void* h, size_t bytes);
+int32_t pmrd_stage_down(pmrd_ctx* ctx, void* h, const void* d, size_t bytes);
+void pmrd_stager_destroy(pmrd_ctx* ctx);
 void pmrd_prof_begin(pmrd_ctx* ctx, const char* kernel_name);
 void pmrd_prof_end(pmrd_ctx* ctx);
 

@@ -42,9 +42,11 @@ __global__ void __launch_bounds__(256) rs_varying_kernel(const uint64_t* __restr
     }
 }
 
-int32_t radix_varying_bits(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, uint64_t* h_varying) {
+int32_t radix_varying_bits(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, uint64_t* h_varying, uint64_t* h_or) {
     *h_varying = 0;
-    if (n <= 1) return PMRD_OK;
+    if (h_or) *h_or = 0;
+    if (n <= 0) return PMRD_OK;
+    if (n == 1 && !h_or) return PMRD_OK;
     DevBuf buf;
     PMRD_CUDA(ctx, buf.alloc(ctx->stream, 16));
     unsigned long long init[2] = {0ull, ~0ull};
@@ -57,6 +59,7 @@ int32_t radix_varying_bits(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, uin
     PMRD_CUDA(ctx, cudaMemcpyAsync(res, buf.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *h_varying = res[0] ^ res[1];
+    if (h_or) *h_or = res[0];
     return PMRD_OK;
 }
 

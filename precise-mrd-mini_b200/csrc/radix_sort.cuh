@@ -46,7 +46,8 @@ struct RadixPlan {
     int bits[8];
 };
 
-int32_t radix_varying_bits(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, uint64_t* h_varying);
+// h_or (optional): the OR of all keys (an upper bound of every key field)
+int32_t radix_varying_bits(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, uint64_t* h_varying, uint64_t* h_or = nullptr);
 RadixPlan radix_make_plan(uint64_t varying);
 // Sorts; on return *in_b tells whether the result lives in (keys_b, vals_b).  vals may be
 // NULL (keys only).  `varying` = mask of key bits that differ across the input (pass ~0ull

@@ -246,32 +246,52 @@ class Context:
         return ko, vo
 
     # -- collapse ------------------------------------------------------------------------
-    def collapse_reads(self, keys, payload, params: UmiParams, want_groups: bool = True):
+    def collapse_reads(self, keys, payload, params: UmiParams, want_groups: bool = True, want_families: bool = True):
+        """``pmrd_collapse_reads``: host arrays in, family table and / or group table out (views of the
+        call's output buffers, no extra copy).  ``want_families=False`` leaves the family rows on the
+        device -- only the per-group table (``umi.py:241-266``) crosses PCIe."""
         keys = _arr(keys, np.uint64)
         payload = _arr(payload, np.uint32)
         n = keys.shape[0]
         if payload.shape[0] != n:
             raise ValueError("keys and payload must have the same length")
         cap = max(n, 1)
-        fam = {"key": np.zeros(cap, np.uint64)}
-        for name in ("size", "n_alt", "consensus", "qsum", "n_best", "flags"):
-            fam[name] = np.zeros(cap, np.uint32)
-        ft = FamilyTable(*[fam[nm].ctypes.data for nm, _ in FamilyTable._fields_])
+        fam = {}
+        if want_families:
+            fam = {"key": np.zeros(cap, np.uint64)}
+            for name in ("size", "n_alt", "consensus", "qsum", "n_best", "flags"):
+                fam[name] = np.zeros(cap, np.uint32)
+            ft = FamilyTable(*[fam[nm].ctypes.data for nm, _ in FamilyTable._fields_])
+        else:
+            ft = FamilyTable(*[None for _ in FamilyTable._fields_])
         grp = {"group": np.zeros(cap, np.uint32), "family_count": np.zeros(cap, np.uint32),
                "consensus_count": np.zeros(cap * 4, np.uint32), "alt_count": np.zeros(cap, np.uint64),
-               "total_count": np.zeros(cap, np.uint64)}
-        gt = GroupTable(*[grp[nm].ctypes.data for nm, _ in GroupTable._fields_])
+               "total_count": np.zeros(cap, np.uint64)} if want_groups else {}
+        gt = GroupTable(*[grp[nm].ctypes.data for nm, _ in GroupTable._fields_]) if want_groups else None
         nf, ng = C.c_int64(0), C.c_int64(0)
         self._check(self.lib.pmrd_collapse_reads(
             self.h, _ptr(keys), _ptr(payload), C.c_int64(n), C.byref(params), C.byref(ft), C.c_int64(cap), C.byref(nf),
             C.byref(gt) if want_groups else None, C.c_int64(cap), C.byref(ng) if want_groups else None))
         F, G = nf.value, ng.value
-        fam = {k: v[:F].copy() for k, v in fam.items()}
+        fam = {k: v[:F] for k, v in fam.items()} if want_families else {"n_families": F}
         if want_groups:
-            grp = {k: (v[:G * 4].reshape(G, 4).copy() if k == "consensus_count" else v[:G].copy()) for k, v in grp.items()}
+            grp = {k: (v[:G * 4].reshape(G, 4) if k == "consensus_count" else v[:G]) for k, v in grp.items()}
         else:
             grp = None
         return fam, grp
+
+    def collapse_reads_dev(self, d_keys: int, d_payload: int, d_keys_tmp: int, d_payload_tmp: int, n: int, params: UmiParams,
+                           d_fam: Dict[str, int], capacity_f: int, d_grp: Optional[Dict[str, int]] = None, capacity_g: int = 0):
+        """``pmrd_collapse_reads_dev``: every buffer is a DEVICE pointer (an int: ``tensor.data_ptr()``); the key /
+        payload buffers are clobbered.  Returns ``(n_families, n_groups)``."""
+        ft = FamilyTable(*[d_fam[nm] for nm, _ in FamilyTable._fields_])
+        gt = GroupTable(*[d_grp[nm] for nm, _ in GroupTable._fields_]) if d_grp else None
+        nf, ng = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.pmrd_collapse_reads_dev(
+            self.h, C.c_void_p(d_keys), C.c_void_p(d_payload), C.c_void_p(d_keys_tmp), C.c_void_p(d_payload_tmp), C.c_int64(n),
+            C.byref(params), C.byref(ft), C.c_int64(capacity_f), C.byref(nf), C.byref(gt) if d_grp else None, C.c_int64(capacity_g),
+            C.byref(ng) if d_grp else None))
+        return nf.value, ng.value
 
     def umi_hamming(self, a, b, umi_len: int) -> np.ndarray:
         a = _arr(a, np.uint32)

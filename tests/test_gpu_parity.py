@@ -267,6 +267,52 @@ def test_collapse_gb_weighted_vs_reference(ctx, golden, native):
     _assert_tables_equal(fam, grp, wfam, wgrp)
 
 
+def _panel_reads(rng, n, n_groups, umis_per_group, umi_bits=24):
+    """External reads of a panel: dense group ids, a pool of UMIs per group, arbitrary order."""
+    g = rng.integers(0, n_groups, n, dtype=np.uint64)
+    pool = rng.integers(0, 1 << umi_bits, (n_groups, umis_per_group), dtype=np.uint64)
+    umi = pool[g.astype(np.int64), rng.integers(0, umis_per_group, n)]
+    payload = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    q = rng.choice([5, 10, 20, 20, 30, 30, 30, 37, 40], n).astype(np.uint32)
+    return (g << np.uint64(32)) | umi, (payload & np.uint32(0xFFFFFF03)) | (q << np.uint32(2))
+
+
+def test_collapse_external_reads_group_major_path(ctx, native, monkeypatch):
+    """pmrd_collapse_reads on a panel of loci in arbitrary order (dense group ids, no group above 4096 reads) takes the
+    group-major path: stable partition by group, then one block sorts and votes a group in shared memory.  Tables
+    against the C restatement of the reference (umi.py:97-203), and -- at a size the oracle cannot reach in seconds --
+    against the full-key-sort path (PMRD_GROUP_FAST=0), for every consensus mode."""
+    from oracle import cport
+
+    rng = np.random.default_rng(77)
+    keys, pl = _panel_reads(rng, 300_000, 600, 120)
+    P = _params(native, min_family_size=3, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6, mode=native.MODE_WEIGHTED)
+    fam, grp = ctx.collapse_reads(keys, pl, P)
+    want = cport.collapse_weighted(keys, pl, 3, 1000, 20, 0.6)
+    for k in want:
+        assert (fam[k] == want[k]).all(), k
+    assert len(grp["group"]) == 600 and (grp["family_count"] == np.bincount((want["key"][(want["flags"] & 2) != 0] >> np.uint64(32)).astype(np.int64), minlength=600)).all()
+    # 16-mer UMIs (32 bits, four ranked rounds), a UMI of all T (= the filler word), groups of one read, empty ids
+    keys2, pl2 = _panel_reads(rng, 40_000, 3000, 4, umi_bits=32)
+    keys2[:50] |= np.uint64(0xFFFFFFFF)
+    keys2 = np.where((keys2 >> np.uint64(32)) % np.uint64(7) == 3, keys2 + (np.uint64(1) << np.uint64(32)), keys2)   # leave some ids empty
+    for mode in (0, 1, 2):
+        P2 = _params(native, min_family_size=2, max_family_size=9, quality_threshold=20, consensus_threshold=0.4, mode=mode, umi_len=16)
+        fam, grp = ctx.collapse_reads(keys2, pl2, P2)
+        wfam, wgrp = port.collapse_exact(keys2, pl2, mode, 2, 9, 20, 0.4)
+        _assert_tables_equal(fam, grp, wfam, wgrp)
+    # 3e6 reads over 20 000 loci: both paths, every mode
+    keys3, pl3 = _panel_reads(rng, 3_000_000, 20_000, 40)
+    for mode in (0, 1, 2):
+        P3 = _params(native, min_family_size=3, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6, mode=mode)
+        monkeypatch.setenv("PMRD_GROUP_FAST", "1")
+        fa, ga = ctx.collapse_reads(keys3, pl3, P3)
+        monkeypatch.setenv("PMRD_GROUP_FAST", "0")
+        fb, gb = ctx.collapse_reads(keys3, pl3, P3)
+        _assert_tables_equal(fa, ga, fb, gb)
+        assert len(fa["key"]) > 700_000 and (np.diff(fa["key"].astype(np.int64)) > 0).all()       # sorted by (group, UMI), no duplicates
+
+
 @pytest.mark.parametrize("d", [1, 2])
 def test_collapse_gb_greedy_clusters_vs_reference(ctx, golden, native, d):
     """K6 greedy (max_edit_distance > 0, the reference's default): the device clusters equal the reference's
