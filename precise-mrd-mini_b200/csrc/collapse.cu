@@ -19,6 +19,7 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "reads.cuh"
+#include "vote.cuh"
 
 __constant__ double c_wtab[64];  // 10^(q/10), q = 0..63
 
@@ -128,9 +129,11 @@ struct FamOut {
 };
 
 // One family's row from its reads in input order; pl_at(i) = payload of read i of the family.
+// wt: the 64-entry weight table 10^(q/10) in SHARED memory (the lanes of a warp look up different q, which a
+// __constant__ table would serialise).
 template <int MODE, typename PlAt>
-__device__ __forceinline__ void family_row(uint32_t size, PlAt pl_at, const pmrd_umi_params& P, uint32_t& n_alt, uint32_t& consensus,
-                                           uint32_t& qsum_best, uint32_t& n_best, uint32_t& flags) {
+__device__ __forceinline__ void family_row(uint32_t size, PlAt pl_at, const pmrd_umi_params& P, const double* wt, uint32_t& n_alt,
+                                           uint32_t& consensus, uint32_t& qsum_best, uint32_t& n_best, uint32_t& flags) {
     n_alt = 0; consensus = 0; qsum_best = 0; n_best = 0; flags = 0;
     if (MODE == PMRD_MODE_WEIGHTED) {
         double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, total = 0.0;
@@ -141,7 +144,7 @@ __device__ __forceinline__ void family_row(uint32_t size, PlAt pl_at, const pmrd
             n_alt += pl >> 31;
             const uint32_t a = pl & 3u, q = (pl >> 2) & 63u;
             if ((int)q >= P.quality_threshold) {
-                const double w = c_wtab[q];
+                const double w = wt[q];
                 // same sequential IEEE additions as umi.py:161-164
                 w0 = __dadd_rn(w0, a == 0 ? w : 0.0);
                 w1 = __dadd_rn(w1, a == 1 ? w : 0.0);
@@ -235,6 +238,9 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
               const uint64_t* __restrict__ keys_orig, const uint32_t* __restrict__ payload_orig,
               const uint32_t* __restrict__ fam_start, const uint32_t* __restrict__ d_nfam, int64_t fam_cap,
               pmrd_umi_params P, uint32_t sentinel_umi, FamOut out) {
+    __shared__ double s_wt[64];
+    if (threadIdx.x < 64) s_wt[threadIdx.x] = c_wtab[threadIdx.x];
+    __syncthreads();
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= (int64_t)*d_nfam || f >= fam_cap) return;
     const uint32_t lo = fam_start[f], hi = fam_start[f + 1];
@@ -243,7 +249,7 @@ family_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ pa
     if (GATHER) key = (key & 0xffffffff00000000ull) | (keys_orig[payload_or_idx[lo]] & 0xffffffffull);
     uint32_t n_alt, consensus, qsum_best, n_best, flags;
     family_row<MODE>(size, [&](uint32_t r) -> uint32_t { return GATHER ? payload_orig[payload_or_idx[lo + r]] : payload_or_idx[lo + r]; },
-                     P, n_alt, consensus, qsum_best, n_best, flags);
+                     P, s_wt, n_alt, consensus, qsum_best, n_best, flags);
     if (sentinel_umi != 0u && (((uint32_t)key) >> 24) == 0xffu) flags = 0;  // padding of a tile-aligned cell
     out.key[f] = key;
     out.size[f] = size;
@@ -440,8 +446,7 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         s_head[r++] = (uint16_t)((uint32_t)(i0 + j) | pad);
     }
     __syncthreads();
-    // FULL: the UMI halves are not needed past this point; their 16 KB now hold the votes' allele sums
-    double* const s_sum = reinterpret_cast<double*>(s_umi) + threadIdx.x;          // 8 KB: [4 alleles][CC_THREADS]
+    // FULL: the UMI halves are not needed past this point; part of their 16 KB now holds the bucketed head order
     uint16_t* const s_order = reinterpret_cast<uint16_t*>(s_umi + 2 * CC_THREADS * 4);   // the other 8 KB: [CC_TILE]
     if (FULL) {
         // One thread votes one family, and a warp is as slow as its longest family (sizes are Poisson:
@@ -489,20 +494,22 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
         if (FULL) {
             // the sort ordered every UMI bit: a run IS a family
             if (hv & 0x8000u) continue;                          // padding of the tile-aligned cell
+            // generated reads carry the cell's ref or alt allele only: two sums in registers (vote.cuh); result 1 = the
+            // tested (alt) allele, 0 = the other one, -1 = no consensus
             int best = -1;
             if (P.consensus_threshold > 0.5) {                   // (uniform) strict majority: accumulate only
-                VoteM v(s_sum);
-                for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], s_wt);
-                for (int c = n_in; c < len; ++c) v.add(pl_at(c), s_wt);
+                FoldVote2<true> v;
+                for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], alt, s_wt);
+                for (int c = n_in; c < len; ++c) v.add(pl_at(c), alt, s_wt);
                 if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
             } else {
-                VoteS v(s_sum);
-                for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], s_wt);
-                for (int c = n_in; c < len; ++c) v.add(pl_at(c), s_wt);
+                FoldVote2<false> v;
+                for (int c = 0; c < n_in; ++c) v.add(s_pl[lo + c], alt, s_wt);
+                for (int c = n_in; c < len; ++c) v.add(pl_at(c), alt, s_wt);
                 if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
             }
             ++n_fam;
-            if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt; }
+            if (best >= 0) { ++n_tot; n_var += best == 1; }
             continue;
         }
         // peel families: read a opens a family iff no earlier read of the run carries its UMI.
@@ -569,7 +576,6 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
     __shared__ __align__(16) unsigned char s_raw[4 * SC_THREADS * sizeof(double)];   // ranking counters, then the votes' allele sums
     static_assert(sizeof(s_raw) >= WARPS * 256 * sizeof(uint32_t), "counters fit the shared scratch");
     uint32_t (*s_cnt)[256] = reinterpret_cast<uint32_t (*)[256]>(s_raw);
-    double* const s_sum = reinterpret_cast<double*>(s_raw);
     __shared__ uint32_t s_base[256];
     __shared__ uint32_t sw[33];
     __shared__ double s_wt[64];
@@ -647,16 +653,16 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
         while (i + len < n && (uint32_t)s_rec[i + len] == umi) ++len;
         int best = -1;
         if (P.consensus_threshold > 0.5) {
-            VoteM v(s_sum + threadIdx.x);
-            for (int c = 0; c < len; ++c) v.add((uint32_t)(s_rec[i + c] >> 32), s_wt);
+            FoldVote2<true> v;
+            for (int c = 0; c < len; ++c) v.add((uint32_t)(s_rec[i + c] >> 32), alt, s_wt);
             if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
         } else {
-            VoteS v(s_sum + threadIdx.x);
-            for (int c = 0; c < len; ++c) v.add((uint32_t)(s_rec[i + c] >> 32), s_wt);
+            FoldVote2<false> v;
+            for (int c = 0; c < len; ++c) v.add((uint32_t)(s_rec[i + c] >> 32), alt, s_wt);
             if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
         }
         ++n_fam;
-        if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt; }
+        if (best >= 0) { ++n_tot; n_var += best == 1; }
     };
     if (LIST) {
         for (int i0 = 0; i0 < n; i0 += SC_THREADS) {
@@ -944,9 +950,11 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
     uint32_t* const sw = s_base + 256;                                           // [33]
     uint16_t* const s_list = reinterpret_cast<uint16_t*>(sw + 36);                // [CAP]
     __shared__ uint32_t s_nheads;
+    __shared__ double s_wt[64];
     const uint32_t g = blockIdx.x;
     const int n = (int)grp_cnt[g];
     if (n == 0) { if (threadIdx.x == 0) fam_cnt[g] = 0u; return; }
+    if (threadIdx.x < 64) s_wt[threadIdx.x] = c_wtab[threadIdx.x];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = lanemask_lt();
     const uint32_t lo = grp_start[g];
@@ -1032,8 +1040,8 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
         const int i = (int)s_list[h];
         const int end = h + 1 < n_heads ? (int)s_list[h + 1] : n;
         uint32_t n_alt, consensus, qsum_best, n_best, flags;
-        family_row<MODE>((uint32_t)(end - i), [&](uint32_t r) -> uint32_t { return (uint32_t)(s_rec[i + r] >> 32); }, P, n_alt, consensus,
-                         qsum_best, n_best, flags);
+        family_row<MODE>((uint32_t)(end - i), [&](uint32_t r) -> uint32_t { return (uint32_t)(s_rec[i + r] >> 32); }, P, s_wt, n_alt,
+                         consensus, qsum_best, n_best, flags);
         const size_t o = (size_t)lo + h;
         tmp.key[o] = ghi | (uint32_t)s_rec[i];
         tmp.size[o] = (uint32_t)(end - i);

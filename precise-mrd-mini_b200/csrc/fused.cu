@@ -25,6 +25,7 @@
 #include "reads_dev.cuh"
 #include "radix_sort.cuh"
 #include "fused.cuh"
+#include "vote.cuh"
 #include <new>
 #include <stdlib.h>
 
@@ -83,32 +84,6 @@ struct FoldVote {
     }
 };
 
-// The generator only ever emits a cell's ref or alt allele (io.py:105-108), so the cell kernel's fold needs two sums,
-// both in registers: no shared-memory accumulator columns, no address arithmetic.  Same additions, same order.
-template <bool MAJ>
-struct FoldVote2 {
-    double total = 0.0, wref = 0.0, walt = 0.0;
-    uint32_t first = 0;            // !MAJ: 1 = ref voted first, 2 = alt voted first (the dict-order tie-break of umi.py:166)
-    __device__ __forceinline__ void add(uint32_t byte, uint32_t alt, const double* wt) {
-        const double w = wt[(byte >> 2) & 63u];              // 0.0 below the quality threshold: adds nothing
-        const bool is_alt = (byte & 3u) == alt;
-        total = __dadd_rn(total, w);
-        if (is_alt) walt = __dadd_rn(walt, w);
-        else wref = __dadd_rn(wref, w);
-        if (!MAJ) first = (first == 0u && __double2hiint(w) != 0) ? (is_alt ? 2u : 1u) : first;
-    }
-    // 1 = consensus is the alt allele, 0 = the ref allele, -1 = none (umi.py:166-174)
-    __device__ __forceinline__ int result(double cthr) const {
-        if (total == 0.0) return -1;                         // no read passed the quality threshold
-        bool alt_wins;
-        if (MAJ) alt_wins = walt > wref;                     // (a tie cannot pass a threshold above one half)
-        else alt_wins = walt > wref || (walt == wref && first == 2u);
-        const double bw = alt_wins ? walt : wref;
-        if (bw != total && __ddiv_rn(bw, total) < cthr) return -1;      // bw == total: the fraction is exactly 1 >= cthr
-        return alt_wins ? 1 : 0;
-    }
-};
-
 // ---------------------------------------------------------------- the cell kernel --------
 #define FUSED_STASH 256     /* reads stashed per warp between two folds */
 struct __align__(16) FusedSlot {
@@ -133,13 +108,14 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
                   unsigned long long* __restrict__ o_cand) {
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char fz_raw[];
-    // layout: [4 bitmaps][weights][slots][stash][tables]
+    // layout: [4 bitmaps][allele sums 4 x THREADS doubles][weights][slots][stash][tables]
     const uint32_t words = (1u << filt_log2) / 32u;
     uint32_t* const s_seen1 = reinterpret_cast<uint32_t*>(fz_raw);
     uint32_t* const s_dup1 = s_seen1 + words;
     uint32_t* const s_seen2 = s_dup1 + words;
     uint32_t* const s_dup2 = s_seen2 + words;
-    double* const s_wt = reinterpret_cast<double*>(s_dup2 + words);
+    double* const s_sum = reinterpret_cast<double*>(s_dup2 + words);
+    double* const s_wt = s_sum + 4 * THREADS;
     FusedSlot* const s_slot = reinterpret_cast<FusedSlot*>(s_wt + 64);
     uint8_t* const s_stash = reinterpret_cast<uint8_t*>(s_slot + THREADS);
     uint8_t* const s_qlut = s_stash + WARPS * FUSED_STASH;
@@ -231,7 +207,9 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
             S.word = d.umi | ((d.has_variant ? 1u : 0u) << 24) | (c.ref_allele << 26) | (c.alt_allele << 28);
         }
         __syncwarp();
-        FoldVote2<MAJ> v;
+        // (measured on the C2 grid: shared-memory columns 17.1 ms, two register sums with predicated DADDs 18.3 ms, one DADD
+        // on a selected sum 18.5 ms -- here the fold runs on the few lanes that own a family and the FP64 pipe is the scarce one)
+        FoldVote<THREADS, MAJ> v(s_sum + threadIdx.x);
         const uint32_t le = lt | (1u << lane);
         for (uint32_t w0 = 0; w0 < total; w0 += FUSED_STASH) {
             const uint32_t w1 = min(total, w0 + FUSED_STASH);
@@ -251,16 +229,15 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
             // every voting lane folds the reads of ITS molecule that lie in this window, in read order (umi.py:161-164)
             if (votes) {
                 const uint32_t a = max(loc, w0), b = min(loc + size, w1);
-                for (uint32_t k = a; k < b; ++k) v.add(stash[k - w0], c.alt_allele, s_wt);
+                for (uint32_t k = a; k < b; ++k) v.add(stash[k - w0], s_wt);
             }
             __syncwarp();
         }
         if (votes) {
             ++n_famc;
             if ((int)size >= P.min_family_size) {
-                // (a consensus on the cell's ref / alt allele: it is a variant family iff that allele is the tested one)
                 const int best = v.result(P.consensus_threshold);
-                if (best >= 0) { ++n_tot; n_var += (best ? c.alt_allele : c.ref_allele) == alt ? 1u : 0u; }
+                if (best >= 0) { ++n_tot; n_var += (uint32_t)best == alt ? 1u : 0u; }
             }
         }
     }
@@ -289,7 +266,7 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
 }
 
 static size_t fused_smem_bytes(int threads, int filt_log2) {
-    return (size_t)4 * ((1u << filt_log2) / 8u) + 64 * 8 + (size_t)threads * sizeof(FusedSlot) +
+    return (size_t)4 * ((1u << filt_log2) / 8u) + (size_t)4 * threads * 8 + 64 * 8 + (size_t)threads * sizeof(FusedSlot) +
            (size_t)(threads / 32) * FUSED_STASH + (1 << QUAL_LUT_BITS) + 4096 + 128 * 4 + 32 * 4 + 5 * 8 + 64;
 }
 
