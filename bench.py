@@ -242,6 +242,44 @@ def lod_grid_wall(cfg, world=1, barrier=None):
     return out
 
 
+def contamination_grid_wall(cfg):
+    """C4 (BASELINE.json configs[3]): the eval-contamination stress sweep -- hop {0,.001,.002,.005,.01} x AF {.001,.005,.01} x
+    depth {1k,5k} x 20 reps + collisions (4 rates) + cross-sample (4 proportions) = 1 560 cells + their blanks -- through
+    ContaminationSimulator(engine="grid"): ONE device plan with per-cell knobs.  Wall time and device time."""
+    import contextlib
+    import copy
+    import io
+
+    from precise_mrd import _native as nv
+    from precise_mrd.sim import ContaminationSimulator
+
+    c = copy.deepcopy(cfg)
+    c.seed = 7
+
+    def once():
+        sim = ContaminationSimulator(c, np.random.default_rng(7), engine="grid")
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim.simulate_contamination_effects()
+        return sim
+
+    once()                                   # warm-up
+    t0 = time.perf_counter()
+    sim = once()
+    wall = time.perf_counter() - t0
+    dctx = nv.default_context(7)
+    dctx.profile_enable(True)
+    l0 = dctx.launch_count
+    once()
+    launches = dctx.launch_count - l0
+    prof = dctx.profile_report()
+    dctx.profile_enable(False)
+    t = sim.grid_table
+    return {"wall_s": wall, "device_ms": round(sum(v[1] for v in prof.values()), 3), "device_launches": int(launches),
+            "cells": int(len(t["p_value"])), "call_groups": int(len(t["group_error_rate"])), "reads": int(t["n_reads"].sum()),
+            "device_top_ms": {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:4]},
+            "note": "one plan: hopping conditions take the general path (12-byte records, full-key sort), the others the cell-major path"}
+
+
 # ------------------------------------------------------------------------------- external reads
 EXT_B_READ = 42.4   # SURVEY.md §8d without the simulate stage: sort 24 + consensus 15.2 + call 3.2 B / read
 
@@ -769,6 +807,11 @@ def main() -> int:
             line["sharded_check"] = sharded_equals_single
         if lod is not None:
             line["lod_grid"] = lod
+        if world == 1 and not args.no_lod:
+            try:
+                line["contamination_grid"] = contamination_grid_wall(cfg)
+            except Exception as exc:
+                line["contamination_grid"] = {"failed": str(exc)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(cfg, cell_id, af, depth)

@@ -399,10 +399,41 @@ int32_t pmrd_call_counts(pmrd_ctx* ctx, const int64_t* h_n_total, const int64_t*
  * CUDA graph); results() copies the per-cell table back and synchronises.
  * h_totals3 = {reads generated, families formed, groups (cells) with reads}. */
 typedef struct pmrd_plan pmrd_plan;
+
+/* Optional per-cell knobs of a plan: the contamination stress sweep of sim/contamination.py:85-228 (index hopping x
+ * barcode collisions x cross-sample contamination, each over rates x AF x depth x replicates) as ONE plan instead of one
+ * pipeline per (rate, AF, depth).  Every pointer may be NULL (the plan-wide pmrd_read_sim_params value applies).
+ *   hop_rate / hop_pool_start / hop_pool_size   a read is re-keyed, w.p. hop_rate[c], to another cell of its hop pool =
+ *        cells [hop_pool_start[c], + hop_pool_size[c]) of this call (the samples that share a flow-cell lane:
+ *        contamination.py:230-254).  Cells with hop_rate > 0 take the general path (full-key sort); pools must be
+ *        contiguous and are never split over chunks.
+ *   collision_rate      a molecule takes the previous molecule's UMI w.p. collision_rate[c] (contamination.py:256-278)
+ *   cross_proportion / cross_af   int(n_families[c] * cross_proportion[c]) EXTRA molecules are mixed into the cell from a
+ *        contaminating sample of allele fraction cross_af[c] (contamination.py:280-311: n_contam = int(n * proportion),
+ *        contam_af = min(0.1, 10 af)); they carry their own UMIs and reads and are collapsed with the cell's own
+ *   call_group_start[G + 1]   cells [s[g], s[g+1]) are CALLED together: error rate from the group's own negative
+ *        controls, BH inside the group -- what one call_mrd of the reference sees (call.py:146-229).  NULL: one group.
+ *        Groups hold at most 4096 cells when G > 1. */
+typedef struct pmrd_cell_knobs {
+    const double* hop_rate;
+    const int64_t* hop_pool_start;
+    const int64_t* hop_pool_size;
+    const double* collision_rate;
+    const double* cross_proportion;
+    const double* cross_af;
+    const int64_t* call_group_start;
+    int64_t n_call_groups;
+} pmrd_cell_knobs;
+int32_t pmrd_plan_create_ex(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
+                            const int64_t* h_n_families, int64_t n_cells, const pmrd_read_sim_params* sp,
+                            const pmrd_umi_params* up, double neg_af_max, int32_t test_type,
+                            int32_t alternative, double alpha, const pmrd_cell_knobs* knobs, pmrd_plan** out);
 int32_t pmrd_plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
                          const int64_t* h_n_families, int64_t n_cells, const pmrd_read_sim_params* sp,
                          const pmrd_umi_params* up, double neg_af_max, int32_t test_type,
                          int32_t alternative, double alpha, pmrd_plan** out);
+/* mean error rate of every call group of the last run (h_rates[capacity >= G]); synchronises */
+int32_t pmrd_plan_group_rates(pmrd_ctx* ctx, pmrd_plan* plan, double* h_rates, int64_t capacity);
 int32_t pmrd_plan_run(pmrd_ctx* ctx, pmrd_plan* plan);
 int32_t pmrd_plan_results(pmrd_ctx* ctx, pmrd_plan* plan, pmrd_pipeline_result* h_out,
                           double* h_mean_error_rate, int64_t* h_totals3);

@@ -66,7 +66,8 @@ int32_t k16_qc_family(pmrd_ctx* ctx, const uint32_t* d_size, const uint32_t* d_f
 struct pmrd_plan;
 int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
                     int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, double neg_af_max,
-                    int32_t test_type, int32_t alternative, double alpha, pmrd_plan** out);
+                    int32_t test_type, int32_t alternative, double alpha, const pmrd_cell_knobs* knobs, pmrd_plan** out);
+int32_t plan_group_rates(pmrd_ctx* ctx, pmrd_plan* P, double* h_rates, int64_t cap);
 int32_t plan_run(pmrd_ctx* ctx, pmrd_plan* P);
 int32_t plan_run_simulate(pmrd_ctx* ctx, pmrd_plan* P, int64_t which);
 int32_t plan_run_collapse(pmrd_ctx* ctx, pmrd_plan* P, int64_t which);
@@ -777,7 +778,18 @@ int32_t pmrd_plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
                          int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up_, double neg_af_max,
                          int32_t test_type, int32_t alternative, double alpha, pmrd_plan** out) {
     ENTER(ctx);
-    return plan_create(ctx, h_cell_id, h_af, h_n_families, n_cells, sp, up_, neg_af_max, test_type, alternative, alpha, out);
+    return plan_create(ctx, h_cell_id, h_af, h_n_families, n_cells, sp, up_, neg_af_max, test_type, alternative, alpha, nullptr, out);
+}
+int32_t pmrd_plan_create_ex(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+                            int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up_, double neg_af_max,
+                            int32_t test_type, int32_t alternative, double alpha, const pmrd_cell_knobs* knobs, pmrd_plan** out) {
+    ENTER(ctx);
+    return plan_create(ctx, h_cell_id, h_af, h_n_families, n_cells, sp, up_, neg_af_max, test_type, alternative, alpha, knobs, out);
+}
+int32_t pmrd_plan_group_rates(pmrd_ctx* ctx, pmrd_plan* plan, double* h_rates, int64_t capacity) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, plan != nullptr && h_rates != nullptr, "plan / buffer");
+    return plan_group_rates(ctx, plan, h_rates, capacity);
 }
 int32_t pmrd_plan_run(pmrd_ctx* ctx, pmrd_plan* plan) {
     ENTER(ctx);
@@ -823,7 +835,7 @@ int32_t pmrd_pipeline_cells(pmrd_ctx* ctx, const int64_t* h_cell_id, const doubl
     ENTER(ctx);
     PMRD_ARG(ctx, h_out != nullptr, "out");
     pmrd_plan* plan = nullptr;
-    PMRD_TRY(plan_create(ctx, h_cell_id, h_af, h_n_families, n_cells, sp, up_, neg_af_max, test_type, alternative, alpha, &plan));
+    PMRD_TRY(plan_create(ctx, h_cell_id, h_af, h_n_families, n_cells, sp, up_, neg_af_max, test_type, alternative, alpha, nullptr, &plan));
     int32_t st = plan_run(ctx, plan);
     if (st == PMRD_OK) st = plan_results(ctx, plan, h_out, h_mean_error_rate, nullptr);
     cudaStreamSynchronize(ctx->stream);

@@ -361,7 +361,7 @@ static int32_t fused_dispatch(pmrd_ctx* ctx, FusedChunk* ch, const pmrd_umi_para
 
 // cells + tables of one chunk on the device; counts its candidates (one sync) so that the step's list is sized exactly
 int32_t fused_chunk_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families, int64_t n_cells,
-                          int64_t cell0, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, FusedChunk* ch) {
+                          int64_t cell0, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, FusedChunk* ch, const CellExtra* h_extra) {
     ch->sp = *sp;
     ch->n_cells = n_cells;
     ch->cell0 = cell0;
@@ -370,6 +370,8 @@ int32_t fused_chunk_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double*
     int64_t nf = 0, max_f = 0;
     for (int64_t i = 0; i < n_cells; ++i) {
         reads_init_cell(&hc[i], (uint64_t)h_cell_id[i], h_af ? h_af[i] : 0.0, nf, (uint32_t)i);
+        reads_apply_extra(&hc[i], sp, h_extra ? h_extra + i : nullptr, cell0, n_cells);
+        if (hc[i].hop_rate > 0.0f) { free(hc); PMRD_ARG(ctx, false, "the fused engine keeps a read inside its cell: hop_rate > 0 needs the materialised engine"); }
         const int64_t f = h_n_families[i] > 0 ? h_n_families[i] : 0;
         nf += f;
         if (f > max_f) max_f = f;

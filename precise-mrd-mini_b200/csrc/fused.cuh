@@ -17,7 +17,8 @@ struct FusedChunk {
 
 int32_t fused_upload_tables(pmrd_ctx* ctx, const double* h_w64);
 int32_t fused_chunk_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families, int64_t n_cells,
-                          int64_t cell0, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, FusedChunk* ch);
+                          int64_t cell0, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, FusedChunk* ch,
+                          const CellExtra* h_extra = nullptr /* [n_cells], already sliced to the chunk */);
 size_t fused_scratch_bytes(int64_t n_cand);
 int32_t fused_chunk_run(pmrd_ctx* ctx, FusedChunk* ch, const pmrd_umi_params* up, void* d_scratch, const uint8_t* d_alt,
                         int64_t* o_reads, int64_t* o_fam, int64_t* o_tot, int64_t* o_var);

@@ -4,7 +4,9 @@
 
 // pvalues.cu
 int32_t k8_pvalues(pmrd_ctx* ctx, const int64_t* d_k, const int64_t* d_n, const double* d_rate, int64_t rate_stride,
-                   int64_t m, int32_t test_type, int32_t alternative, double* d_p);
+                   int64_t m, int32_t test_type, int32_t alternative, double* d_p, const int32_t* d_rate_index = nullptr);
+int32_t k9_bh_groups(pmrd_ctx* ctx, const double* d_p, const int64_t* d_group_start, int64_t n_groups, double alpha, uint8_t* d_rejected,
+                     double* d_q);
 int32_t k9_bh(pmrd_ctx* ctx, const double* d_p, int64_t m, double alpha, uint8_t* d_rejected, double* d_q, void* d_workspace = nullptr);
 size_t bh_workspace_bytes(int64_t m);
 

@@ -60,15 +60,21 @@ cell_family_count_kernel(const uint64_t* __restrict__ fam_key, const uint32_t* _
     }
 }
 
-// single block: rate = sum(n_var)/sum(n_tot) over negative cells; mean of 64 context rates
+// one block per CALL GROUP (cells [gs[g], gs[g+1]); gs == NULL: one group of all cells):
+// rate = sum(n_var)/sum(n_tot) over the group's negative cells; mean of 64 context rates
 __global__ void __launch_bounds__(256)
-error_rate_kernel(uint64_t seed, uint64_t stream_id, const int64_t* __restrict__ n_total, const int64_t* __restrict__ n_variants,
-                  const uint8_t* __restrict__ is_negative, int64_t n_cells, double* __restrict__ mean_rate /*[1]*/,
-                  int64_t* __restrict__ neg_counts /*[2]*/) {
+error_rate_kernel(uint64_t seed, uint64_t stream_id, const uint64_t* __restrict__ group_stream /* [G] or NULL */,
+                  const int64_t* __restrict__ gs /* [G+1] or NULL */, const int64_t* __restrict__ n_total,
+                  const int64_t* __restrict__ n_variants, const uint8_t* __restrict__ is_negative, int64_t n_cells,
+                  double* __restrict__ mean_rate /*[G]*/, int64_t* __restrict__ neg_counts /*[2G]*/, int32_t* __restrict__ cell_group /*[C] or NULL*/) {
     __shared__ unsigned long long s_n[8], s_v[8];
     __shared__ double s_mod[64];
+    const int g = blockIdx.x;
+    const int64_t lo = gs ? gs[g] : 0, hi = gs ? gs[g + 1] : n_cells;
+    if (group_stream) stream_id = group_stream[g];
     unsigned long long n = 0, v = 0;
-    for (int64_t i = threadIdx.x; i < n_cells; i += blockDim.x) {
+    for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        if (cell_group) cell_group[i] = g;
         if (is_negative[i]) {
             n += (unsigned long long)n_total[i];
             v += (unsigned long long)n_variants[i];
@@ -90,9 +96,9 @@ error_rate_kernel(uint64_t seed, uint64_t stream_id, const int64_t* __restrict__
         // error_rate.mean() over the 64 contexts (call.py:178), summed in context order
         double acc = 0.0;
         for (int c = 0; c < 64; ++c) acc += vr * s_mod[c];
-        mean_rate[0] = acc / 64.0;
-        neg_counts[0] = (int64_t)nn;
-        neg_counts[1] = (int64_t)vv;
+        mean_rate[g] = acc / 64.0;
+        neg_counts[2 * g] = (int64_t)nn;
+        neg_counts[2 * g + 1] = (int64_t)vv;
     }
 }
 
@@ -133,6 +139,11 @@ struct pmrd_plan {
     DevBuf alt, neg, negc, mean_rate;
     DevBuf o_reads, o_fam, o_tot, o_var, o_p, o_q, o_sig;
     DevBuf bh_ws;         // BH workspace (sort buffers + scratch): the call stage of a step allocates nothing
+    // call groups (pmrd_cell_knobs.call_group_start): error rate, tail tests and BH per group of cells
+    int64_t n_groups = 1;
+    DevBuf gs, gstream, cell_group;   // [G+1] cell ranges, [G] stream ids (a group's first cell id), [C] group of every cell
+    // general-path (hopping) chunks size these separately from the cell-major ones
+    int64_t max_reads_gen = 0, max_fcap_gen = 0, max_cells_gen = 0;
     ~pmrd_plan() {
         for (PlanChunk* c : chunks) delete c;
         for (FusedChunk* c : fchunks) delete c;
@@ -152,13 +163,47 @@ __global__ void add_counts_kernel(const uint32_t* __restrict__ counts, unsigned 
     totals[1] += counts[1];
 }
 
-int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
+int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families_in,
                     int64_t n_cells, const pmrd_read_sim_params* sp, const pmrd_umi_params* up, double neg_af_max,
-                    int32_t test_type, int32_t alternative, double alpha, pmrd_plan** out) {
+                    int32_t test_type, int32_t alternative, double alpha, const pmrd_cell_knobs* knobs, pmrd_plan** out) {
     PMRD_ARG(ctx, out != nullptr, "out");
     *out = nullptr;
     PMRD_ARG(ctx, n_cells > 0 && n_cells < (1ll << 30), "n_cells");
-    PMRD_ARG(ctx, h_cell_id && h_n_families && sp, "null cell arrays / params");
+    PMRD_ARG(ctx, h_cell_id && h_n_families_in && sp, "null cell arrays / params");
+    // per-cell knobs -> host-side CellExtra rows + effective family counts (own + cross-sample contaminants)
+    std::vector<CellExtra> extra;
+    std::vector<int64_t> nf_eff;
+    const int64_t* h_n_families = h_n_families_in;
+    if (knobs && (knobs->hop_rate || knobs->collision_rate || knobs->cross_proportion)) {
+        PMRD_ARG(ctx, !knobs->cross_proportion || knobs->cross_af, "cross_proportion needs cross_af");
+        PMRD_ARG(ctx, !knobs->hop_rate || (knobs->hop_pool_start && knobs->hop_pool_size), "hop_rate needs hop_pool_start / hop_pool_size");
+        extra.resize((size_t)n_cells);
+        nf_eff.resize((size_t)n_cells);
+        for (int64_t i = 0; i < n_cells; ++i) {
+            CellExtra& x = extra[(size_t)i];
+            x.hop_rate = knobs->hop_rate ? (float)knobs->hop_rate[i] : (float)sp->hop_rate;
+            x.collision_rate = knobs->collision_rate ? (float)knobs->collision_rate[i] : (float)sp->collision_rate;
+            x.pool_start = 0; x.pool_n = 0;
+            if (knobs->hop_rate && knobs->hop_rate[i] > 0.0) {
+                const int64_t ps = knobs->hop_pool_start[i], pn = knobs->hop_pool_size[i];
+                PMRD_ARG(ctx, ps >= 0 && pn >= 1 && ps <= i && i < ps + pn && ps + pn <= n_cells, "hop pool must be a cell range containing the cell");
+                x.pool_start = (uint32_t)ps; x.pool_n = (uint32_t)pn;
+            }
+            const int64_t own = h_n_families_in[i] > 0 ? h_n_families_in[i] : 0;
+            x.n_own = -1; x.af2 = 0.0;
+            int64_t add = 0;
+            if (knobs->cross_proportion && knobs->cross_proportion[i] > 0.0) {
+                add = (int64_t)((double)own * knobs->cross_proportion[i]);          // contamination.py:288
+                x.n_own = own; x.af2 = knobs->cross_af[i];
+            }
+            nf_eff[(size_t)i] = own + add;
+        }
+        h_n_families = nf_eff.data();
+    }
+    const CellExtra* h_extra = extra.empty() ? nullptr : extra.data();
+    auto cell_hops = [&](int64_t i) { return h_extra ? h_extra[i].hop_rate > 0.0f : sp->hop_rate > 0.0; };
+    // a chunk may end before cell i unless that would split a hop pool or mix hopping and non-hopping cells is avoided
+    auto pool_open_at = [&](int64_t i) { return h_extra && i > 0 && h_extra[i].pool_n > 0 && (int64_t)h_extra[i].pool_start < i; };
     PMRD_ARG(ctx, up && up->mode == PMRD_MODE_WEIGHTED && up->cluster == PMRD_CLUSTER_EXACT, "pipeline needs WEIGHTED/EXACT umi params");
     PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || test_type == PMRD_TEST_BINOMIAL, "Unknown test type");
     PMRD_ARG(ctx, sp->chunk_log2 == 0 || (sp->chunk_log2 >= 16 && sp->chunk_log2 <= 30), "chunk_log2 must be 0 or in [16, 30]");
@@ -167,9 +212,13 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     P->up = *up; P->neg_af_max = neg_af_max; P->alpha = alpha; P->test_type = test_type; P->alternative = alternative;
     P->n_cells = n_cells;
     P->fused = sp->engine == PMRD_ENGINE_FUSED;
-    if (P->fused && sp->hop_rate > 0.0) {
-        delete P;
-        PMRD_ARG(ctx, false, "the fused engine keeps a read inside its cell: hop_rate > 0 needs PMRD_ENGINE_MATERIALISED");
+    {
+        bool any_hop = false;
+        for (int64_t i = 0; i < n_cells; ++i) any_hop |= cell_hops(i);
+        if (P->fused && any_hop) {
+            delete P;
+            PMRD_ARG(ctx, false, "the fused engine keeps a read inside its cell: hop_rate > 0 needs PMRD_ENGINE_MATERIALISED");
+        }
     }
     P->stream_id = (uint64_t)h_cell_id[0];
     P->seed = ctx->seed;
@@ -187,7 +236,9 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
         int64_t c1 = c0;
         while (c1 < n_cells) {
             const double add = (double)(h_n_families[c1] > 0 ? h_n_families[c1] : 0) * per_family;
-            if (c1 > c0 && acc + add > budget) break;
+            // a chunk is either all hopping cells (general path) or none (cell-major path), and never splits a hop pool
+            if (c1 > c0 && cell_hops(c1) != cell_hops(c0)) break;
+            if (c1 > c0 && acc + add > budget && !pool_open_at(c1)) break;
             acc += add;
             ++c1;
         }
@@ -195,7 +246,8 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
             FusedChunk* fc = new (std::nothrow) FusedChunk();
             if (!fc) { st = PMRD_ERR_ARG; snprintf(ctx->err, sizeof(ctx->err), "out of host memory"); break; }
             P->fchunks.push_back(fc);
-            st = fused_chunk_build(ctx, h_cell_id + c0, h_af ? h_af + c0 : nullptr, h_n_families + c0, c1 - c0, c0, sp, up, fc);
+            st = fused_chunk_build(ctx, h_cell_id + c0, h_af ? h_af + c0 : nullptr, h_n_families + c0, c1 - c0, c0, sp, up, fc,
+                                   h_extra ? h_extra + c0 : nullptr);
             if (st != PMRD_OK) break;
             P->n_reads += fc->n_reads;
             P->n_fam += fc->n_fam;
@@ -209,7 +261,7 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
         ch->cell0 = c0;
         ch->n_cells = c1 - c0;
         st = reads_plan_build(ctx, h_cell_id + c0, h_af ? h_af + c0 : nullptr, h_n_families + c0, c1 - c0, 0, sp, /*segmented=*/1,
-                              &ch->reads, nullptr);
+                              &ch->reads, nullptr, h_extra ? h_extra + c0 : nullptr, c0);
         if (st != PMRD_OK) break;
         if (ch->reads.n_out >= (1ll << 31) - 8192) {
             snprintf(ctx->err, sizeof(ctx->err), "a chunk of %lld cells holds %lld reads (>= 2^31): lower chunk_log2 or split the cell",
@@ -218,8 +270,13 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
             break;
         }
         // UMI merging can only lower the family count; hopped reads can open new (cell, UMI) families
-        ch->fcap = sp->hop_rate > 0.0 ? ch->reads.n_reads : ch->reads.n_fam + ch->n_cells /* padding sentinels */;
+        ch->fcap = !ch->reads.segmented ? ch->reads.n_reads : ch->reads.n_fam + ch->n_cells /* padding sentinels */;
         if (ch->fcap < 1) ch->fcap = 1;
+        if (!ch->reads.segmented) {
+            if (ch->reads.n_out > P->max_reads_gen) P->max_reads_gen = ch->reads.n_out;
+            if (ch->fcap > P->max_fcap_gen) P->max_fcap_gen = ch->fcap;
+            if (ch->n_cells > P->max_cells_gen) P->max_cells_gen = ch->n_cells;
+        }
         ch->varying = varying_mask_for(ch->n_cells);
         P->n_reads += ch->reads.n_reads;
         P->n_fam += ch->reads.n_fam;
@@ -230,38 +287,64 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     }
     if (st != PMRD_OK) { delete P; return st; }
     const size_t n = (size_t)(P->max_reads > 0 ? P->max_reads : 1);
-    const size_t f = (size_t)(P->max_fcap > 0 ? P->max_fcap : 1), g = (size_t)P->max_cells, c = (size_t)n_cells;
+    const size_t c = (size_t)n_cells;
     cudaError_t e = cudaSuccess;
     auto A = [&](DevBuf& b, size_t bytes) { if (e == cudaSuccess) e = b.alloc(ctx->stream, bytes); };
     if (P->fused) A(P->fscratch, fused_scratch_bytes(P->max_fcap));
     else { A(P->keys, n * 8); A(P->keys_tmp, n * 8); }
     if (const char* gh = getenv("PMRD_GEN_HIST")) P->gen_hist = atoi(gh) != 0;   // 0: the sort counts its first digit itself
-    if (sp->hop_rate > 0.0 || P->fused) P->gen_hist = false;
+    if (P->fused) P->gen_hist = false;
     if (P->gen_hist) A(P->tile_hist, (n / READS_SEG_TILE + 1) * 256 * sizeof(uint32_t));
-    if (sp->hop_rate > 0.0) { A(P->pl, n * 4); A(P->pl_tmp, n * 4); }
-    if (sp->hop_rate > 0.0) {   // only the general (non cell-major) path materialises the family / group tables
+    if (P->max_reads_gen > 0) {   // only the general (non cell-major) path carries payload arrays and the family / group tables
+        const size_t ng = (size_t)P->max_reads_gen;
+        A(P->pl, ng * 4); A(P->pl_tmp, ng * 4);
+    }
+    const size_t f = (size_t)(P->max_fcap_gen > 0 ? P->max_fcap_gen : 1), g = (size_t)(P->max_cells_gen > 0 ? P->max_cells_gen : 1);
+    if (P->max_reads_gen > 0) {
         A(P->fk, f * 8); A(P->fs, f * 4); A(P->fa, f * 4); A(P->fc, f * 4); A(P->fq, f * 4); A(P->fn, f * 4); A(P->ff, f * 4);
         A(P->fam_start, (f + 1) * 4);
         A(P->gg, g * 4); A(P->gf, g * 4); A(P->gc, g * 16); A(P->ga, g * 8); A(P->gt, g * 8); A(P->grp_start, (g + 1) * 4);
     }
-    A(P->counts, 8); A(P->totals, 16); A(P->alt, c); A(P->neg, c); A(P->negc, 16); A(P->mean_rate, 8);
+    // call groups
+    std::vector<int64_t> h_gs;
+    if (knobs && knobs->call_group_start && knobs->n_call_groups > 0) {
+        P->n_groups = knobs->n_call_groups;
+        h_gs.assign(knobs->call_group_start, knobs->call_group_start + P->n_groups + 1);
+        bool ok = h_gs.front() == 0 && h_gs.back() == n_cells;
+        for (int64_t gi = 0; gi < P->n_groups && ok; ++gi)
+            ok = h_gs[(size_t)gi + 1] > h_gs[(size_t)gi] && (P->n_groups == 1 || h_gs[(size_t)gi + 1] - h_gs[(size_t)gi] <= 4096);
+        if (!ok) { delete P; PMRD_ARG(ctx, false, "call_group_start must partition the cells into non-empty ranges of <= 4096 cells"); }
+    } else {
+        h_gs = {0, n_cells};
+    }
+    const size_t G = (size_t)P->n_groups;
+    A(P->counts, 8); A(P->totals, 16); A(P->alt, c); A(P->neg, c); A(P->negc, 16 * G); A(P->mean_rate, 8 * G);
+    A(P->gs, 8 * (G + 1)); A(P->gstream, 8 * G); A(P->cell_group, 4 * c);
     A(P->o_reads, c * 8); A(P->o_fam, c * 8); A(P->o_tot, c * 8); A(P->o_var, c * 8); A(P->o_p, c * 8); A(P->o_q, c * 8); A(P->o_sig, c);
     A(P->bh_ws, bh_workspace_bytes((int64_t)c));
     uint8_t* h_alt = (uint8_t*)malloc(c * 2);
     if (e == cudaSuccess && h_alt) {
         uint8_t* h_neg = h_alt + c;
-        bool any_neg = false;
-        double min_af = INFINITY;
-        for (int64_t i = 0; i < n_cells; ++i) {
-            h_alt[i] = (uint8_t)pmrd_cell_alt_allele((uint64_t)h_cell_id[i]);
-            const double a = h_af ? h_af[i] : 0.0;
-            h_neg[i] = a <= neg_af_max;
-            any_neg |= h_neg[i] != 0;
-            if (a < min_af) min_af = a;
+        std::vector<uint64_t> h_gstream(G);
+        for (size_t gi = 0; gi < G; ++gi) {            // negative controls per call group (error_model.py:144-149)
+            const int64_t lo = h_gs[gi], hi = h_gs[gi + 1];
+            h_gstream[gi] = (uint64_t)h_cell_id[lo];
+            bool any_neg = false;
+            double min_af = INFINITY;
+            for (int64_t i = lo; i < hi; ++i) {
+                h_alt[i] = (uint8_t)pmrd_cell_alt_allele((uint64_t)h_cell_id[i]);
+                const double a = h_af ? h_af[i] : 0.0;
+                h_neg[i] = a <= neg_af_max;
+                any_neg |= h_neg[i] != 0;
+                if (a < min_af) min_af = a;
+            }
+            if (!any_neg)  // fallback: the lowest-AF samples
+                for (int64_t i = lo; i < hi; ++i) h_neg[i] = (h_af ? h_af[i] : 0.0) == min_af;
         }
-        if (!any_neg)  // error_model.py:146-149 fallback: the lowest-AF samples
-            for (int64_t i = 0; i < n_cells; ++i) h_neg[i] = (h_af ? h_af[i] : 0.0) == min_af;
         e = cudaMemcpyAsync(P->alt.p, h_alt, c, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(P->gs.p, h_gs.data(), 8 * (G + 1), cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(P->gstream.p, h_gstream.data(), 8 * G, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      // (h_gstream leaves scope)
         if (e == cudaSuccess) e = cudaMemcpyAsync(P->neg.p, h_neg, c, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(P->totals.p, 0, 16, ctx->stream);
         if (e == cudaSuccess) e = cudaMemsetAsync(P->o_tot.p, 0, c * 8, ctx->stream);
@@ -346,16 +429,25 @@ static int32_t plan_reset_outputs(pmrd_ctx* ctx, pmrd_plan* P) {
 int32_t call_counts_dev(pmrd_ctx* ctx, const int64_t* d_tot, const int64_t* d_var, const uint8_t* d_neg, int64_t n_cells,
                         uint64_t stream_id, int32_t test_type, int32_t alternative, double alpha, double* d_mean_rate,
                         int64_t* d_negc, double* d_p, double* d_q, uint8_t* d_sig, void* d_bh_workspace) {
-    PMRD_LAUNCH(ctx, error_rate_kernel, 1, 256, 0, ctx->seed, stream_id, d_tot, d_var, d_neg, n_cells, d_mean_rate, d_negc);
+    PMRD_LAUNCH(ctx, error_rate_kernel, 1, 256, 0, ctx->seed, stream_id, (const uint64_t*)nullptr, (const int64_t*)nullptr, d_tot, d_var, d_neg,
+                n_cells, d_mean_rate, d_negc, (int32_t*)nullptr);
     PMRD_TRY(k8_pvalues(ctx, d_var, d_tot, d_mean_rate, 0, n_cells, test_type, alternative, d_p));
     PMRD_TRY(k9_bh(ctx, d_p, n_cells, alpha, d_sig, d_q, d_bh_workspace));
     return PMRD_OK;
 }
 
 int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
-    return call_counts_dev(ctx, P->o_tot.as<int64_t>(), P->o_var.as<int64_t>(), P->neg.as<uint8_t>(), P->n_cells, P->stream_id,
-                           P->test_type, P->alternative, P->alpha, P->mean_rate.as<double>(), P->negc.as<int64_t>(),
-                           P->o_p.as<double>(), P->o_q.as<double>(), P->o_sig.as<uint8_t>(), P->bh_ws.p);
+    if (P->n_groups <= 1)
+        return call_counts_dev(ctx, P->o_tot.as<int64_t>(), P->o_var.as<int64_t>(), P->neg.as<uint8_t>(), P->n_cells, P->stream_id,
+                               P->test_type, P->alternative, P->alpha, P->mean_rate.as<double>(), P->negc.as<int64_t>(),
+                               P->o_p.as<double>(), P->o_q.as<double>(), P->o_sig.as<uint8_t>(), P->bh_ws.p);
+    // several call groups: each is what ONE call_mrd of the reference sees -- its own error rate, its own BH
+    PMRD_LAUNCH(ctx, error_rate_kernel, (int)P->n_groups, 256, 0, ctx->seed, (uint64_t)0, (const uint64_t*)P->gstream.as<uint64_t>(),
+                (const int64_t*)P->gs.as<int64_t>(), (const int64_t*)P->o_tot.as<int64_t>(), (const int64_t*)P->o_var.as<int64_t>(),
+                (const uint8_t*)P->neg.as<uint8_t>(), P->n_cells, P->mean_rate.as<double>(), P->negc.as<int64_t>(), P->cell_group.as<int32_t>());
+    PMRD_TRY(k8_pvalues(ctx, P->o_var.as<int64_t>(), P->o_tot.as<int64_t>(), P->mean_rate.as<double>(), 0, P->n_cells, P->test_type,
+                        P->alternative, P->o_p.as<double>(), (const int32_t*)P->cell_group.as<int32_t>()));
+    return k9_bh_groups(ctx, P->o_p.as<double>(), (const int64_t*)P->gs.as<int64_t>(), P->n_groups, P->alpha, P->o_sig.as<uint8_t>(), P->o_q.as<double>());
 }
 
 // Stage entry points for per-stage timing.  With more than one chunk the read buffers are
@@ -432,6 +524,14 @@ int32_t plan_results(pmrd_ctx* ctx, pmrd_plan* P, const pmrd_pipeline_result* h,
         for (FusedChunk* fc : P->fchunks) groups += fc->n_cells_with_reads;
         h_totals[2] = groups;
     }
+    return PMRD_OK;
+}
+
+// mean error rate of every call group (after a run); synchronises
+int32_t plan_group_rates(pmrd_ctx* ctx, pmrd_plan* P, double* h_rates, int64_t cap) {
+    PMRD_ARG(ctx, cap >= P->n_groups, "capacity < number of call groups");
+    PMRD_CUDA(ctx, cudaMemcpyAsync(h_rates, P->mean_rate.p, 8 * (size_t)P->n_groups, cudaMemcpyDeviceToHost, ctx->stream));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PMRD_OK;
 }
 

@@ -9,11 +9,12 @@
 // ---------------------------------------------------------------- K8 --------------------
 __global__ void __launch_bounds__(128)
 pvalues_kernel(const int64_t* __restrict__ k, const int64_t* __restrict__ n, const double* __restrict__ rate,
-               int64_t rate_stride, int64_t m, int test_type, int alternative, double* __restrict__ p) {
+               int64_t rate_stride, const int32_t* __restrict__ rate_index /* or NULL: rate[i * rate_stride] */, int64_t m,
+               int test_type, int alternative, double* __restrict__ p) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const int64_t ki = k[i];
-    const double r = rate[i * rate_stride];
+    const double r = rate_index ? rate[rate_index[i]] : rate[i * rate_stride];
     double out;
     if (test_type == PMRD_TEST_POISSON) {
         // call.py:179 expected = n_total * mean_error_rate: one IEEE multiply, no contraction
@@ -29,13 +30,13 @@ pvalues_kernel(const int64_t* __restrict__ k, const int64_t* __restrict__ n, con
 }
 
 int32_t k8_pvalues(pmrd_ctx* ctx, const int64_t* d_k, const int64_t* d_n, const double* d_rate, int64_t rate_stride,
-                   int64_t m, int32_t test_type, int32_t alternative, double* d_p) {
+                   int64_t m, int32_t test_type, int32_t alternative, double* d_p, const int32_t* d_rate_index) {
     PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || test_type == PMRD_TEST_BINOMIAL, "Unknown test type");
     PMRD_ARG(ctx, alternative == PMRD_ALT_TWO_SIDED || alternative == PMRD_ALT_GREATER || alternative == PMRD_ALT_LESS,
              "unknown alternative");
     PMRD_ARG(ctx, test_type == PMRD_TEST_POISSON || d_n != nullptr, "binomial test needs n");
     if (m <= 0) return PMRD_OK;
-    PMRD_LAUNCH(ctx, pvalues_kernel, pmrd_blocks(m, 128), 128, 0, d_k, d_n, d_rate, rate_stride, m, test_type, alternative, d_p);
+    PMRD_LAUNCH(ctx, pvalues_kernel, pmrd_blocks(m, 128), 128, 0, d_k, d_n, d_rate, rate_stride, d_rate_index, m, test_type, alternative, d_p);
     return PMRD_OK;
 }
 
@@ -218,5 +219,63 @@ int32_t k9_bh(pmrd_ctx* ctx, const double* d_p, int64_t m, double alpha, uint8_t
     PMRD_LAUNCH(ctx, bh_suffix_kernel, 1, 256, 0, tmin, n_tiles);
     PMRD_LAUNCH(ctx, bh_apply_kernel, n_tiles, BH_THREADS, 0, keys, idx, m, (const double*)tmin, (const unsigned long long*)kstar,
                 d_rejected, d_q);
+    return PMRD_OK;
+}
+
+// ---------------------------------------------------------------- K9 per call group --------
+// Benjamini-Hochberg inside every call group (cells [gs[g], gs[g+1]), at most BHG_MAX of them): one block per group.
+// Ranks by counting (ties by index: tied p-values get the same adjusted value and never straddle the rejection
+// cut, Appendix B of SURVEY.md), then exactly the arithmetic of the global path -- p * m / rank in that order, reverse
+// running minimum, clip -- so a group's q-values are bit-equal to pmrd_bh run on that group alone.
+#define BHG_MAX 4096
+__global__ void __launch_bounds__(256)
+bh_group_kernel(const double* __restrict__ p, const int64_t* __restrict__ gs, double alpha, uint8_t* __restrict__ rejected, double* __restrict__ q) {
+    __shared__ double s_p[BHG_MAX];        // sorted p, then raw adjusted values
+    __shared__ uint16_t s_src[BHG_MAX];    // sorted position -> cell of the group
+    __shared__ unsigned int s_kstar;
+    const int64_t lo = gs[blockIdx.x];
+    const int m = (int)(gs[blockIdx.x + 1] - lo);
+    if (m <= 0) return;
+    if (threadIdx.x == 0) s_kstar = 0u;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        double v = p[lo + i];
+        if (v == 0.0) v = 0.0;                                   // -0.0 folded onto +0.0, as bh_pack_kernel does
+        int rank = 0;
+        for (int j = 0; j < m; ++j) {
+            const double w = p[lo + j];
+            rank += (w < v) || (w == v && j < i);
+        }
+        s_p[rank] = v;
+        s_src[rank] = (uint16_t)i;
+    }
+    __syncthreads();
+    const double md = (double)m;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double v = s_p[i];
+        const double thr = __dmul_rn(__ddiv_rn((double)(i + 1), md), alpha);      // call.py:55
+        if (v <= thr) atomicMax(&s_kstar, (unsigned int)(i + 1));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s_p[i] = __ddiv_rn(__dmul_rn(s_p[i], md), (double)(i + 1));   // call.py:59-61
+    __syncthreads();
+    if (threadIdx.x == 0) {                                       // reverse running minimum (call.py:64-70): m <= 4096
+        double run = INFINITY;
+        for (int i = m - 1; i >= 0; --i) {
+            run = fmin(run, s_p[i]);
+            s_p[i] = run;
+        }
+    }
+    __syncthreads();
+    const unsigned int ks = s_kstar;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int64_t dst = lo + s_src[i];
+        q[dst] = fmin(fmax(s_p[i], 0.0), 1.0);
+        rejected[dst] = (unsigned int)(i + 1) <= ks ? 1 : 0;
+    }
+}
+
+int32_t k9_bh_groups(pmrd_ctx* ctx, const double* d_p, const int64_t* d_gs, int64_t n_groups, double alpha, uint8_t* d_rejected, double* d_q) {
+    if (n_groups <= 0) return PMRD_OK;
+    PMRD_LAUNCH(ctx, bh_group_kernel, (int)n_groups, 256, 0, d_p, d_gs, alpha, d_rejected, d_q);
     return PMRD_OK;
 }

@@ -221,9 +221,10 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
             const uint32_t c2 = (uint32_t)cells[S.ci].cell_id;
             const uint32_t c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((cells[S.ci].cell_id >> 32) & 0xffffffu);
             const uint4 h = ph(0x80000000u | j, sb.z, c2, c3);  // (a block of its own: hopping is rare)
-            if (u24(h.x) < (float)sp.hop_rate) {
-                const uint32_t other = (uint32_t)S.ci + 1u + h.y % (uint32_t)(n_cells - 1);
-                const ReadCell oc = cells[other % (uint32_t)n_cells];
+            const ReadCell& hc = cells[S.ci];                   // per-cell rate, hop pool = cells [pool_start, pool_start + pool_n)
+            if (hc.pool_n > 1u && u24(h.x) < hc.hop_rate) {
+                const uint32_t other = hc.pool_start + ((uint32_t)S.ci - hc.pool_start + 1u + h.y % (hc.pool_n - 1u)) % hc.pool_n;
+                const ReadCell oc = cells[other];
                 group = oc.group;
                 pl = (pl & 0x7fffffffu) | ((allele == oc.alt_allele ? 1u : 0u) << 31);
             }
@@ -287,18 +288,30 @@ reads_pad_kernel(const ReadCell* __restrict__ cells, int n_cells, const int64_t*
 // Philox key, so it can be known before the timed step allocates anything).
 int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
                          int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, int segmented, ReadPlan* plan,
-                         int64_t* h_read_offsets /* optional [C+1] */) {
+                         int64_t* h_read_offsets /* optional [C+1] */, const CellExtra* h_extra /* optional [C] */, int64_t first_cell) {
     PMRD_ARG(ctx, sp != nullptr && sp->mean_family_size > 0.0 && sp->max_family_size >= 1, "read sim params");
     PMRD_ARG(ctx, n_cells >= 0 && n_cells < (1ll << 31), "n_cells");
     plan->sp = *sp;
     plan->n_cells = n_cells;
-    plan->segmented = (segmented && sp->hop_rate == 0.0) ? 1 : 0;   // hopped reads leave their cell's region
+    bool any_hop = sp->hop_rate > 0.0;
+    if (h_extra) {
+        any_hop = false;
+        for (int64_t i = 0; i < n_cells; ++i) {
+            any_hop |= h_extra[i].hop_rate > 0.0f;
+            if (h_extra[i].pool_n > 0)
+                PMRD_ARG(ctx, (int64_t)h_extra[i].pool_start >= first_cell && (int64_t)h_extra[i].pool_start + h_extra[i].pool_n <= first_cell + n_cells,
+                         "a hop pool must lie inside one chunk of cells");
+        }
+    }
+    plan->sp.hop_rate = any_hop ? (sp->hop_rate > 0.0 ? sp->hop_rate : 1.0) : 0.0;   // (the kernel's switch; the rates are per cell)
+    plan->segmented = (segmented && !any_hop) ? 1 : 0;   // hopped reads leave their cell's region
     ReadCell* hc = (ReadCell*)malloc(sizeof(ReadCell) * (size_t)(n_cells + 1));
     int64_t* ho = (int64_t*)malloc(8 * (size_t)(n_cells + 1));
     if (!hc || !ho) { free(hc); free(ho); PMRD_ARG(ctx, false, "out of host memory"); }
     int64_t nf = 0;
     for (int64_t i = 0; i < n_cells; ++i) {
-reads_init_cell(&hc[i], (uint64_t)h_cell_id[i], h_af ? h_af[i] : 0.0, nf, group_base + (uint32_t)i);
+        reads_init_cell(&hc[i], (uint64_t)h_cell_id[i], h_af ? h_af[i] : 0.0, nf, group_base + (uint32_t)i);
+        reads_apply_extra(&hc[i], sp, h_extra ? h_extra + i : nullptr, first_cell, n_cells);
         ho[i] = nf;
         nf += h_n_families[i] > 0 ? h_n_families[i] : 0;
     }

@@ -15,6 +15,21 @@ struct ReadCell {
     int64_t af_lt, af_ge;  // has_variant threshold words (see draw_family)
     float inv_full;        // segmented layout: 1 / (complete 4096-read windows) when the window permutation applies, else 0
     uint32_t tile0;        // segmented layout: out_start / 4096
+    // per-cell contamination knobs (sim/contamination.py:230-311 at read level; defaults: the plan-wide pmrd_read_sim_params)
+    float hop_rate;        // each read is re-keyed to another cell of the cell's hop pool w.p. hop_rate
+    float collision_rate;  // a molecule takes the previous molecule's UMI w.p. collision_rate
+    uint32_t pool_start, pool_n;   // hop pool: cells [pool_start, pool_start + pool_n) of the batch
+    uint32_t n_own;        // molecules [0, n_own) are the sample's own; [n_own, ...) come from a contaminating sample ...
+    double af2;            // ... with this allele fraction (cross-sample contamination, contamination.py:280-311)
+    int64_t af2_lt, af2_ge;
+};
+
+// host-side per-cell overrides handed to the plan builders (NULL: every cell takes the plan-wide parameters)
+struct CellExtra {
+    float hop_rate, collision_rate;
+    uint32_t pool_start, pool_n;   // relative to the first cell of the call
+    int64_t n_own;                 // own molecules (the rest of the cell's families are cross-sample contaminants); < 0: all
+    double af2;
 };
 
 #define READS_SEG_TILE 4096 /* == RS_TILE: cells are padded to whole sort tiles when segmented */
@@ -46,6 +61,14 @@ static inline uint32_t pmrd_cell_alt_allele(uint64_t cell_id) {
 
 // uniform in (0,1) from 53 bits (common.cuh u53) decides has_variant: words w of the first 32 bits that settle
 // u53(w, .) < af on their own -- w < af_lt: true whatever the low word; w >= af_ge: false whatever the low word
+static inline void reads_af_thresholds(double a, int64_t* lt, int64_t* ge) {
+    int64_t g = a <= 0.0 ? 0 : (a >= 1.0 ? (1ll << 32) : (int64_t)(a * 4294967296.0));
+    while (g > 0 && !(u53((uint32_t)(g - 1), 0xffffffffu) < a)) --g;
+    while (g < (1ll << 32) && u53((uint32_t)g, 0xffffffffu) < a) ++g;
+    *lt = g;
+    while (g < (1ll << 32) && u53((uint32_t)g, 0u) < a) ++g;
+    *ge = g;
+}
 static inline void reads_init_cell(ReadCell* c, uint64_t cell_id, double af, int64_t fam_offset, uint32_t group) {
     c->cell_id = cell_id;
     c->af = af;
@@ -58,13 +81,33 @@ static inline void reads_init_cell(ReadCell* c, uint64_t cell_id, double af, int
     c->n_reads = 0;
     c->inv_full = 0.0f;
     c->tile0 = 0;
-    const double a = af;
-    int64_t g = a <= 0.0 ? 0 : (a >= 1.0 ? (1ll << 32) : (int64_t)(a * 4294967296.0));
-    while (g > 0 && !(u53((uint32_t)(g - 1), 0xffffffffu) < a)) --g;
-    while (g < (1ll << 32) && u53((uint32_t)g, 0xffffffffu) < a) ++g;
-    c->af_lt = g;
-    while (g < (1ll << 32) && u53((uint32_t)g, 0u) < a) ++g;
-    c->af_ge = g;
+    reads_af_thresholds(af, &c->af_lt, &c->af_ge);
+    c->hop_rate = 0.0f;
+    c->collision_rate = 0.0f;
+    c->pool_start = 0;
+    c->pool_n = 0;
+    c->n_own = 0xffffffffu;
+    c->af2 = af;
+    c->af2_lt = c->af_lt;
+    c->af2_ge = c->af_ge;
+}
+
+// plan-wide knobs, then the per-cell overrides (`first` = index of the chunk's first cell in the call, `n_chunk` its
+// cell count: hop pools are re-based to the chunk and must lie inside it)
+static inline void reads_apply_extra(ReadCell* c, const pmrd_read_sim_params* sp, const CellExtra* x, int64_t first, int64_t n_chunk) {
+    c->hop_rate = (float)sp->hop_rate;
+    c->collision_rate = (float)sp->collision_rate;
+    c->pool_start = 0;
+    c->pool_n = (uint32_t)n_chunk;
+    if (!x) return;
+    c->hop_rate = x->hop_rate;
+    c->collision_rate = x->collision_rate;
+    if (x->pool_n > 0) { c->pool_start = (uint32_t)((int64_t)x->pool_start - first); c->pool_n = x->pool_n; }
+    if (x->n_own >= 0) {
+        c->n_own = (uint32_t)x->n_own;
+        c->af2 = x->af2;
+        reads_af_thresholds(x->af2, &c->af2_lt, &c->af2_ge);
+    }
 }
 
 // Poisson family sizes with mean <= 16 are inverted against an fp32 cdf table: F[k] = P(X <= k), k < 96, by the pmf
@@ -89,7 +132,7 @@ static inline bool reads_build_size_tables(const pmrd_read_sim_params* sp, float
 
 int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af, const int64_t* h_n_families,
                          int64_t n_cells, uint32_t group_base, const pmrd_read_sim_params* sp, int segmented, ReadPlan* plan,
-                         int64_t* h_read_offsets);
+                         int64_t* h_read_offsets, const CellExtra* h_extra = nullptr, int64_t first_cell = 0);
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan);
 int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload, uint32_t* d_tile_hist = nullptr);
 int32_t reads_plan_generate_cell_major(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uint32_t* d_payload);

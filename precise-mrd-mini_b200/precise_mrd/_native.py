@@ -69,6 +69,13 @@ class ReadSimParams(C.Structure):
     ]
 
 
+class CellKnobs(C.Structure):
+    """``pmrd_cell_knobs``: optional per-cell contamination knobs + call groups of a plan."""
+    _fields_ = [("hop_rate", C.c_void_p), ("hop_pool_start", C.c_void_p), ("hop_pool_size", C.c_void_p),
+                ("collision_rate", C.c_void_p), ("cross_proportion", C.c_void_p), ("cross_af", C.c_void_p),
+                ("call_group_start", C.c_void_p), ("n_call_groups", C.c_int64)]
+
+
 class CallTable(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "n_variants", "n_total", "variant_fraction", "expected_variants", "fold_change",
@@ -370,8 +377,8 @@ class Context:
 
     # -- fused pipeline ------------------------------------------------------------------
     def pipeline_cells(self, cell_id, af, n_families, sp: ReadSimParams, up: UmiParams, neg_af_max: float = 1e-4,
-                       test_type: int = TEST_POISSON, alternative: int = ALT_TWO_SIDED, alpha: float = 0.05):
-        plan = Plan(self, cell_id, af, n_families, sp, up, neg_af_max, test_type, alternative, alpha)
+                       test_type: int = TEST_POISSON, alternative: int = ALT_TWO_SIDED, alpha: float = 0.05, knobs=None):
+        plan = Plan(self, cell_id, af, n_families, sp, up, neg_af_max, test_type, alternative, alpha, knobs=knobs)
         try:
             plan.run()
             return plan.results()
@@ -495,7 +502,10 @@ class Plan:
     """Prepared simulate -> collapse -> call pipeline over a batch of cells (``pmrd_plan``)."""
 
     def __init__(self, ctx: Context, cell_id, af, n_families, sp: ReadSimParams, up: UmiParams, neg_af_max: float = 1e-4,
-                 test_type: int = TEST_POISSON, alternative: int = ALT_TWO_SIDED, alpha: float = 0.05):
+                 test_type: int = TEST_POISSON, alternative: int = ALT_TWO_SIDED, alpha: float = 0.05,
+                 knobs: Optional[Dict[str, np.ndarray]] = None):
+        """``knobs`` (optional, ``pmrd_cell_knobs``): per-cell arrays ``hop_rate`` (+ ``hop_pool_start`` / ``hop_pool_size``),
+        ``collision_rate``, ``cross_proportion`` (+ ``cross_af``) and ``call_group_start`` (G + 1 cell offsets)."""
         self.ctx = ctx
         self.cell_id = _arr(cell_id, np.int64)
         self.af = _arr(af, np.float64)
@@ -508,9 +518,28 @@ class Plan:
         ctx.lib.pmrd_plan_n_families.argtypes = [C.c_void_p]
         ctx.lib.pmrd_plan_destroy.restype = None
         ctx.lib.pmrd_plan_destroy.argtypes = [C.c_void_p]
-        ctx._check(ctx.lib.pmrd_plan_create(ctx.h, _ptr(self.cell_id), _ptr(self.af), _ptr(self.nf), C.c_int64(self.n_cells),
-                                            C.byref(sp), C.byref(up), C.c_double(neg_af_max), C.c_int32(test_type),
-                                            C.c_int32(alternative), C.c_double(alpha), C.byref(h)))
+        self.n_groups = 1
+        if knobs:
+            typ = {"hop_rate": np.float64, "hop_pool_start": np.int64, "hop_pool_size": np.int64, "collision_rate": np.float64,
+                   "cross_proportion": np.float64, "cross_af": np.float64, "call_group_start": np.int64}
+            unknown = set(knobs) - set(typ)
+            if unknown:
+                raise ValueError(f"unknown plan knobs: {sorted(unknown)}")
+            self._knobs = {k: _arr(v, typ[k]) for k, v in knobs.items() if v is not None}
+            for k, v in self._knobs.items():
+                if k != "call_group_start" and v.shape[0] != self.n_cells:
+                    raise ValueError(f"knob {k} must hold one value per cell")
+            kn = CellKnobs(*[self._knobs[k].ctypes.data if k in self._knobs else None for k in typ], 0)
+            if "call_group_start" in self._knobs:
+                self.n_groups = int(self._knobs["call_group_start"].shape[0] - 1)
+                kn.n_call_groups = self.n_groups
+            ctx._check(ctx.lib.pmrd_plan_create_ex(ctx.h, _ptr(self.cell_id), _ptr(self.af), _ptr(self.nf), C.c_int64(self.n_cells),
+                                                   C.byref(sp), C.byref(up), C.c_double(neg_af_max), C.c_int32(test_type),
+                                                   C.c_int32(alternative), C.c_double(alpha), C.byref(kn), C.byref(h)))
+        else:
+            ctx._check(ctx.lib.pmrd_plan_create(ctx.h, _ptr(self.cell_id), _ptr(self.af), _ptr(self.nf), C.c_int64(self.n_cells),
+                                                C.byref(sp), C.byref(up), C.c_double(neg_af_max), C.c_int32(test_type),
+                                                C.c_int32(alternative), C.c_double(alpha), C.byref(h)))
         self.h = h
         self.n_reads = int(ctx.lib.pmrd_plan_n_reads(h))
         self.n_families = int(ctx.lib.pmrd_plan_n_families(h))
@@ -556,6 +585,10 @@ class Plan:
         out["significant"] = out["significant"].astype(bool)
         out["mean_error_rate"] = float(rate[0])
         out["totals"] = totals
+        if self.n_groups > 1:
+            rates = np.zeros(self.n_groups)
+            self.ctx._check(self.ctx.lib.pmrd_plan_group_rates(self.ctx.h, self.h, _ptr(rates), C.c_int64(self.n_groups)))
+            out["group_error_rate"] = rates
         return out
 
     def close(self) -> None:

@@ -52,15 +52,16 @@ def read_sim_params(config=None, mean_family_size: float = 5.0, family_model: in
 
 def run_cells(config, cell_id, allele_fraction, n_families, ctx: Optional[nv.Context] = None,
               sim: Optional[nv.ReadSimParams] = None, neg_af_max: float = 1e-4,
-              alternative: int = nv.ALT_TWO_SIDED) -> Dict[str, np.ndarray]:
+              alternative: int = nv.ALT_TWO_SIDED, knobs: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
     """One pass of the hot path over a batch of cells given as HOST arrays; returns the
-    per-cell call table as HOST arrays (the C ABI stages both directions)."""
+    per-cell call table as HOST arrays (the C ABI stages both directions).  ``knobs``: per-cell
+    contamination knobs and call groups (``pmrd_cell_knobs``)."""
     st = section(config, "stats")
     if st["test_type"] not in nv.TEST_TYPES:
         raise ValueError(f"Unknown test type: {st['test_type']}")      # call.py:187
     ctx = ctx or nv.default_context(int(config.seed))
     sim = sim or read_sim_params(config)
     res = ctx.pipeline_cells(cell_id, allele_fraction, n_families, sim, umi_params(config), neg_af_max=neg_af_max,
-                             test_type=nv.TEST_TYPES[st["test_type"]], alternative=alternative, alpha=float(st["alpha"]))
+                             test_type=nv.TEST_TYPES[st["test_type"]], alternative=alternative, alpha=float(st["alpha"]), knobs=knobs)
     res["variant_call"] = res["significant"]                           # SURVEY.md §0.3-2
     return res

@@ -8,8 +8,13 @@
   in the reference.
 * ``engine="grid"``: the read-level meaning ``north_star`` gives these knobs -- index hopping
   re-keys a Binomial(n_reads, hop) subset of READS to another sample's index, barcode collisions
-  make a Binomial(n_families, rate) subset of FAMILIES share another molecule's UMI
-  (``csrc/reads.cu``) -- through the fused device plan."""
+  make a Binomial(n_families, rate) subset of FAMILIES share another molecule's UMI, cross-sample
+  contamination mixes ``int(n_families * proportion)`` molecules of a 10x-AF sample (their own UMIs
+  and reads) into the cell (``contamination.py:280-311``) -- and the WHOLE sweep (1 560 cells + their
+  blanks: every kind x rate x AF x depth x replicate) runs as ONE device plan with per-cell knobs
+  (``pmrd_plan_create_ex``): a (kind, rate, AF, depth) condition is a *call group* (own negative
+  controls, own error rate -- what one ``call_mrd`` of the reference sees) and, for hopping, a *hop
+  pool* (the samples that share a lane)."""
 from __future__ import annotations
 
 import json
@@ -42,6 +47,10 @@ class ContaminationSimulator:
                                        depth_values: List[int] = [1000, 5000], n_replicates: int = 20) -> Dict[str, Any]:
         print("Running contamination stress testing...")
         results: Dict[str, Any] = {}
+        self._grid_det = None
+        if self.engine == "grid":
+            self._grid_det = self._grid_sweep_all({"hop": hop_rates, "collision": barcode_collision_rates, "cross": cross_sample_proportions},
+                                                  af_test_values, depth_values, n_replicates)
         results["index_hopping"] = self._sweep("hop", hop_rates, af_test_values, depth_values, n_replicates, 1000)
         results["barcode_collisions"] = self._sweep("collision", barcode_collision_rates, af_test_values, depth_values, n_replicates, 2000)
         results["cross_sample_contamination"] = self._sweep("cross", cross_sample_proportions, af_test_values, depth_values, n_replicates, 3000)
@@ -87,21 +96,45 @@ class ContaminationSimulator:
         return int((calls_df["variant_call"] == True).sum())                            # noqa: E712
 
     def _grid_runs(self, kind: str, rate: float, af: float, depth: int, n_rep: int, index) -> List[int]:
+        return self._grid_det[(kind,) + tuple(index)]
+
+    def _grid_sweep_all(self, rates_by_kind, af_values, depth_values, n_rep: int):
+        """The whole stress sweep as ONE plan: returns {(kind, rate_i, af_i, depth_i): [detected per replicate]}."""
         from .. import grid
 
         ctx = nv.default_context(int(self.config.seed))
-        kid = {"hop": 1, "collision": 2, "cross": 3}[kind]
-        ri, ai, di = index       # cell ids from INDICES (sweep, rate_i, af_i, depth_i, rep), never from seeds
-        base = ((((kid * 64 + ri) * 64 + ai) * 64 + di) << 20) + (4 << 50)
         n_blank = max(n_rep, 10)
-        cid = base + np.arange(n_rep + n_blank, dtype=np.int64)
-        afs = np.concatenate([np.full(n_rep, af), np.zeros(n_blank)])
-        if kind == "cross":   # a proportion of the families comes from a 10x-AF sample (contamination.py:291-299)
-            afs[:n_rep] = (1 - rate) * af + rate * min(0.1, af * 10)
-        sim = grid.read_sim_params(self.config, hop_rate=rate if kind == "hop" else 0.0,
-                                   collision_rate=rate if kind == "collision" else 0.0)
-        res = grid.run_cells(self.config, cid, afs, np.full(n_rep + n_blank, depth, dtype=np.int64), ctx=ctx, sim=sim, neg_af_max=0.0, alternative=nv.ALT_GREATER)
-        return [int(v) for v in (res["p_value"][:n_rep] <= float(self.config.stats.alpha))]
+        m = n_rep + n_blank
+        cid, afs, nfam, hop, pool0, pooln, coll, crossp, crossaf, gstart, keys = [], [], [], [], [], [], [], [], [], [0], []
+        # hopping conditions first (those cells take the general path; a chunk never mixes the two kinds of cells)
+        for kind in ("hop", "collision", "cross"):
+            kid = {"hop": 1, "collision": 2, "cross": 3}[kind]
+            for ri, rate in enumerate(rates_by_kind[kind]):
+                for ai, af in enumerate(af_values):
+                    for di, depth in enumerate(depth_values):
+                        # cell ids from INDICES (sweep, rate_i, af_i, depth_i, rep), never from seeds
+                        base = ((((kid * 64 + ri) * 64 + ai) * 64 + di) << 20) + (4 << 50)
+                        start = gstart[-1]
+                        cid.append(base + np.arange(m, dtype=np.int64))
+                        afs.append(np.concatenate([np.full(n_rep, af), np.zeros(n_blank)]))
+                        nfam.append(np.full(m, depth, dtype=np.int64))
+                        hop.append(np.full(m, rate if kind == "hop" else 0.0))
+                        pool0.append(np.full(m, start, dtype=np.int64))
+                        pooln.append(np.full(m, m, dtype=np.int64))
+                        coll.append(np.full(m, rate if kind == "collision" else 0.0))
+                        # contamination.py:291-299: the contaminating sample carries min(0.1, 10 AF); blanks stay clean
+                        crossp.append(np.concatenate([np.full(n_rep, rate if kind == "cross" else 0.0), np.zeros(n_blank)]))
+                        crossaf.append(np.full(m, min(0.1, af * 10)))
+                        gstart.append(start + m)
+                        keys.append((kind, ri, ai, di))
+        knobs = {"hop_rate": np.concatenate(hop), "hop_pool_start": np.concatenate(pool0), "hop_pool_size": np.concatenate(pooln),
+                 "collision_rate": np.concatenate(coll), "cross_proportion": np.concatenate(crossp), "cross_af": np.concatenate(crossaf),
+                 "call_group_start": np.array(gstart, dtype=np.int64)}
+        res = grid.run_cells(self.config, np.concatenate(cid), np.concatenate(afs), np.concatenate(nfam), ctx=ctx,
+                             sim=grid.read_sim_params(self.config), neg_af_max=0.0, alternative=nv.ALT_GREATER, knobs=knobs)
+        self.grid_table = res
+        det = res["p_value"] <= float(self.config.stats.alpha)
+        return {k: [int(v) for v in det[gstart[g]: gstart[g] + n_rep]] for g, k in enumerate(keys)}
 
     # ------------------------------------------------------------------ reference perturbations (stages engine)
     def _simulate_with_index_hopping(self, config, rng, hop_rate: float) -> pd.DataFrame:

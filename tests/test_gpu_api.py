@@ -237,6 +237,31 @@ def test_contamination_stages_engine_equals_the_reference_run(ctx, smoke_cfg):
     assert m["matrix"] == want_m["matrix"] and m["condition_labels"] == want_m["condition_labels"]
 
 
+def test_contamination_grid_engine_is_one_plan(ctx, smoke_cfg):
+    """engine="grid": the whole stress sweep runs as ONE device plan (per-cell knobs, hop pools, call groups).
+    Detection falls with the hop rate's dilution only mildly, rises with AF and depth; the result dict has the
+    reference's shape; the launch count is that of one plan, not one per condition."""
+    from precise_mrd import _native as nv
+    from precise_mrd.sim import ContaminationSimulator
+
+    c = nv.default_context(int(smoke_cfg.seed))
+    sim = ContaminationSimulator(smoke_cfg, np.random.default_rng(smoke_cfg.seed), engine="grid")
+    l0 = c.launch_count
+    res = sim.simulate_contamination_effects(n_replicates=6)
+    launches = c.launch_count - l0
+    assert set(res) == {"index_hopping", "barcode_collisions", "cross_sample_contamination", "sensitivity_matrix"}
+    assert list(res["index_hopping"]) == [0.0, 0.001, 0.002, 0.005, 0.01] and list(res["cross_sample_contamination"]) == [0.0, 0.01, 0.05, 0.1]
+    n_groups = (5 + 4 + 4) * 3 * 2
+    assert len(sim.grid_table["group_error_rate"]) == n_groups and len(sim.grid_table["p_value"]) == n_groups * (6 + 10)
+    assert launches < 6 * n_groups, launches                     # one plan per condition used to cost ~40 launches each
+    hop = res["index_hopping"]
+    assert hop[0.0][0.01][5000]["mean_sensitivity"] >= hop[0.0][0.001][1000]["mean_sensitivity"]
+    # a 10x-AF contaminant raises the alt-family count: detection at AF 1e-3 / depth 5000 does not fall with the proportion
+    cross = res["cross_sample_contamination"]
+    assert cross[0.1][0.001][5000]["mean_sensitivity"] >= cross[0.0][0.001][5000]["mean_sensitivity"]
+    assert all("mean_fp_rate" in v for r in res["barcode_collisions"].values() for a in r.values() for v in a.values())
+
+
 def test_lod_analyzer_both_engines(ctx, smoke_cfg, tmp_path):
     from precise_mrd.eval import LODAnalyzer
     from precise_mrd.validation import validate_json

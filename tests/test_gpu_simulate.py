@@ -346,6 +346,86 @@ def test_fused_engine_agrees_with_the_materialised_plan_and_refuses_hopping(ctx,
         ctx.pipeline_cells(cid, af, nf, _sp(native, engine=native.ENGINE_FUSED, hop_rate=0.01), up)
 
 
+# ------------------------------------------------------------------------------ per-cell knobs: one plan for the C4 sweep
+def test_one_plan_with_per_cell_knobs_equals_one_plan_per_condition(ctx, native):
+    """pmrd_plan_create_ex: a contamination sweep (hop rates x collision rates, each condition = test cells + blanks) as
+    ONE plan with per-cell knobs, hop pools and call groups gives, condition by condition, exactly the table of a
+    separate plan with the plan-wide knob: counts, error rate, p-values, and BH inside the group (bit-equal q)."""
+    rng = np.random.default_rng(21)
+    conds = [("hop", 0.0), ("hop", 0.01), ("hop", 0.05), ("coll", 0.0), ("coll", 0.02), ("coll", 0.1)]
+    m = 14
+    up = _umi(native)
+    cid, af, nf, hop, p0, pn, coll, gs, singles = [], [], [], [], [], [], [], [0], []
+    for gi, (kind, rate) in enumerate(conds):
+        c = (np.int64(7) << 40) + gi * 1000 + np.arange(m, dtype=np.int64)
+        a = np.concatenate([np.full(8, 0.05), np.zeros(6)])
+        f = rng.integers(300, 2500, m)
+        start = gs[-1]
+        cid.append(c); af.append(a); nf.append(f)
+        hop.append(np.full(m, rate if kind == "hop" else 0.0)); p0.append(np.full(m, start)); pn.append(np.full(m, m))
+        coll.append(np.full(m, rate if kind == "coll" else 0.0))
+        gs.append(start + m)
+        sp = _sp(native, family_model=1, hop_rate=rate if kind == "hop" else 0.0, collision_rate=rate if kind == "coll" else 0.0)
+        singles.append(ctx.pipeline_cells(c, a, f, sp, up, neg_af_max=0.0, alternative=native.ALT_GREATER))
+    knobs = {"hop_rate": np.concatenate(hop), "hop_pool_start": np.concatenate(p0), "hop_pool_size": np.concatenate(pn),
+             "collision_rate": np.concatenate(coll), "call_group_start": np.array(gs)}
+    res = ctx.pipeline_cells(np.concatenate(cid), np.concatenate(af), np.concatenate(nf), _sp(native, family_model=1), up,
+                             neg_af_max=0.0, alternative=native.ALT_GREATER, knobs=knobs)
+    assert len(res["group_error_rate"]) == len(conds)
+    for gi, one in enumerate(singles):
+        sl = slice(gs[gi], gs[gi + 1])
+        for k in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+            assert (res[k][sl] == one[k]).all(), (conds[gi], k)
+        assert res["group_error_rate"][gi] == one["mean_error_rate"]
+        rej, adj = port.benjamini_hochberg(res["p_value"][sl], 0.05)
+        assert (res["significant"][sl] == rej).all() and (res["p_adjusted"][sl] == adj).all()
+    # hopping did move reads between the cells of a pool (more, smaller families), never across pools
+    assert res["n_families"][gs[2]:gs[3]].sum() > np.concatenate(nf)[gs[2]:gs[3]].sum()
+    assert res["n_reads"].sum() == sum(o["n_reads"].sum() for o in singles)
+    # a hop pool that a chunk boundary would split, or that does not contain its cell, is refused
+    bad = dict(knobs)
+    bad["hop_pool_start"] = np.concatenate(p0) + 1
+    with pytest.raises(native.NativeError):
+        ctx.pipeline_cells(np.concatenate(cid), np.concatenate(af), np.concatenate(nf), _sp(native, family_model=1), up, knobs=bad)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_cross_sample_contamination_mixes_molecules_of_a_second_sample(ctx, native, fused):
+    """Read-level cross-sample contamination (contamination.py:280-311): int(n * proportion) molecules of a sample with
+    its own allele fraction are added to the cell -- own UMIs, own reads, collapsed together with the cell's.  The mixed
+    cell must look like the union of a clean cell and a separate cell of the contaminating sample: read and family
+    counts add up, and the variant consensus count matches the sum within binomial noise (a chi-square on the 2 x 2
+    table variant / non-variant x mixed / union at alpha = 0.001)."""
+    n, prop, af2 = 20000, 0.25, 0.5
+    c = 40
+    cid = (np.int64(11) << 40) + np.arange(c, dtype=np.int64)
+    eng = dict(engine=native.ENGINE_FUSED) if fused else {}
+    sp = _sp(native, family_model=1, **eng)
+    up = _umi(native)
+    z = np.zeros(c)
+    mixed = ctx.pipeline_cells(cid, z, np.full(c, n), sp, up, knobs={"cross_proportion": np.full(c, prop), "cross_af": np.full(c, af2)})
+    clean = ctx.pipeline_cells(cid, z, np.full(c, n), sp, up)
+    same = ctx.pipeline_cells(cid, z, np.full(c, n), sp, up, knobs={"cross_proportion": z, "cross_af": np.full(c, af2)})
+    for k in ("n_reads", "n_families", "n_total", "n_variants"):
+        assert (same[k] == clean[k]).all(), k                                        # proportion 0: nothing is mixed in
+    donor = ctx.pipeline_cells(cid + 5000, np.full(c, af2), np.full(c, int(n * prop)), sp, up)
+    n_add = int(n * prop)
+    # molecules: exactly n + int(n * prop) drawn; reads and families follow (minus the few UMI coincidences)
+    assert (mixed["n_reads"] > clean["n_reads"]).all()
+    assert abs(mixed["n_reads"].sum() / clean["n_reads"].sum() - (1 + prop)) < 0.01
+    assert abs(mixed["n_families"].sum() - (clean["n_families"].sum() + donor["n_families"].sum())) < 0.002 * c * n
+    # the cell's own molecules are untouched: the clean cell's variant families are still there, the rest is the donor's share
+    a = np.array([[mixed["n_variants"].sum(), mixed["n_total"].sum() - mixed["n_variants"].sum()],
+                  [clean["n_variants"].sum() + donor["n_variants"].sum(),
+                   clean["n_total"].sum() + donor["n_total"].sum() - clean["n_variants"].sum() - donor["n_variants"].sum()]], float)
+    exp = a.sum(1, keepdims=True) * a.sum(0, keepdims=True) / a.sum()
+    chi2 = ((a - exp) ** 2 / exp).sum()
+    assert chi2 < 10.83, (chi2, a)                                                   # 1 dof, alpha = 0.001
+    frac = (mixed["n_variants"].sum() - clean["n_variants"].sum()) / max(1, donor["n_total"].sum())
+    assert 0.35 < frac < 0.55                                                        # ~ af2 x P(alt consensus | variant molecule)
+    assert n_add == 5000
+
+
 @pytest.mark.parametrize("hop,coll", [(0.01, 0.0), (0.05, 0.02)])
 def test_pipeline_with_index_hopping_equals_oracle(ctx, native, hop, coll):
     """C4 (eval-contamination) read-level knobs through the plan: with hop_rate > 0 reads leave their cell, so the
