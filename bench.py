@@ -663,17 +663,19 @@ def main() -> int:
 
         an = LODAnalyzer(cfg, np.random.default_rng(7), engine="grid")
         g_cid, g_af, g_dp = an._grid_cells(2, np.logspace(-4, -2, 15), [1000, 5000, 10000, 50000, 100000], 25, 25)
-        sh = distributed.run_cells_sharded(cfg, g_cid, g_af, g_dp, neg_af_max=0.0, alternative=nv.ALT_GREATER, ctx=ctx)
         ok = True
-        if rank == 0:
-            one = grid.run_cells(cfg, g_cid, g_af, g_dp, ctx=ctx, neg_af_max=0.0, alternative=nv.ALT_GREATER)
-            for k in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
-                ok = ok and bool((np.asarray(sh[k]) == np.asarray(one[k])).all())
-            ok = ok and sh["mean_error_rate"] == one["mean_error_rate"]
+        for eng_fused in (True, False):                      # the engine LODAnalyzer(engine="grid") uses, and the sort-based one
+            g_sim = grid.read_sim_params(cfg, fused=eng_fused)
+            sh = distributed.run_cells_sharded(cfg, g_cid, g_af, g_dp, neg_af_max=0.0, alternative=nv.ALT_GREATER, ctx=ctx, sim=g_sim)
+            if rank == 0:
+                one = grid.run_cells(cfg, g_cid, g_af, g_dp, ctx=ctx, sim=g_sim, neg_af_max=0.0, alternative=nv.ALT_GREATER)
+                for k in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+                    ok = ok and bool((np.asarray(sh[k]) == np.asarray(one[k])).all())
+                ok = ok and sh["mean_error_rate"] == one["mean_error_rate"]
         flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         sharded_equals_single = {"equal": bool(flag.item()), "cells": int(len(g_cid)),
-                                 "what": "C3 eval-lod grid (1875 cells + blanks): run_cells_sharded over all ranks (LPT shards, one NCCL "
+                                 "what": "C3 eval-lod grid (1875 cells + blanks), fused and materialised engines: run_cells_sharded over all ranks (LPT shards, one NCCL "
                                          "all-gather of per-cell counts, call stage on every rank) vs grid.run_cells on rank 0 alone; "
                                          "counts, p, q, significant, error rate compared bit for bit"}
         if not flag.item():

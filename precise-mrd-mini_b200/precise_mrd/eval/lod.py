@@ -9,8 +9,10 @@ Two engines behind the reference's class and method signatures:
   milliseconds instead of 3-7 s.  It reproduces the reference's behaviour including its
   degenerate outputs on its own grids (LoB 0, LoD NaN, LoQ None: SURVEY.md Appendix A #12).
 * ``engine="grid"`` (the read-level mode ``north_star`` describes): all cells of the grid go
-  through ONE fused device plan (``precise_mrd.grid``): Philox read generation, radix-sort
-  collapse, quality-weighted consensus, blank-derived error rate, tail test per cell.  Cell
+  through ONE device plan (``precise_mrd.grid``) on the fused engine: Philox read generation and
+  quality-weighted consensus in one kernel, no read ever written (duplicate UMIs are found by hash
+  bitmaps and replayed; results = the radix-sort collapse on family-major read order),
+  blank-derived error rate, tail test per cell.  Cell
   keys are built from the INDICES (analysis, depth_i, af_i, rep), which removes the reference's
   seed collisions across AF/replicate pairs and depths.
 
@@ -92,11 +94,13 @@ class LODAnalyzer:
         # cell sits significantly BELOW the U(0.5,2)-inflated expectation
         from .. import distributed
 
+        # the FUSED engine (csrc/fused.cu): a cell goes from Philox counters to its counts without a read ever being written
+        sim = grid.read_sim_params(self.config, fused=True)
         if distributed.world_size() > 1:
             # one process per GPU: cells sharded by family count, ONE all-gather of the per-cell counts, then
             # the call stage over the whole grid on every rank -- same table as on one GPU
-            return distributed.run_cells_sharded(self.config, cell_id, af, depth, neg_af_max=0.0, alternative=nv.ALT_GREATER, ctx=ctx)
-        return grid.run_cells(self.config, cell_id, af, depth, ctx=ctx, neg_af_max=0.0, alternative=nv.ALT_GREATER)
+            return distributed.run_cells_sharded(self.config, cell_id, af, depth, neg_af_max=0.0, alternative=nv.ALT_GREATER, ctx=ctx, sim=sim)
+        return grid.run_cells(self.config, cell_id, af, depth, ctx=ctx, sim=sim, neg_af_max=0.0, alternative=nv.ALT_GREATER)
 
     # ------------------------------------------------------------------ LoB
     def estimate_lob(self, n_blank_runs: int = 100) -> Dict[str, Any]:
