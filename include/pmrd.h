@@ -50,6 +50,8 @@ int32_t pmrd_set_stream(pmrd_ctx* ctx, void* cuda_stream);
 int32_t pmrd_sync(pmrd_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py: gpu_launches) */
 int64_t pmrd_launch_count(const pmrd_ctx* ctx);
+/* high-water mark (bytes) of the device's stream-ordered allocator pool: `precise-mrd performance` (cli.py:408-438, peak_memory_mb) */
+int64_t pmrd_peak_memory_bytes(pmrd_ctx* ctx);
 /* Per-kernel device timing: while enabled, every launch is bracketed by CUDA events on the
  * launching stream.  pmrd_profile_report synchronises and writes "<kernel> <launches>
  * <total_ms>\n" lines into buf (returns bytes written) and clears the records. */
@@ -196,6 +198,13 @@ int32_t pmrd_collapse_reads_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pay
                                 const pmrd_umi_params* params, pmrd_family_table* d_fam,
                                 int64_t capacity_f, int64_t* n_families, pmrd_group_table* d_grp,
                                 int64_t capacity_g, int64_t* n_groups);
+
+/* K4 on the plan's cell-major layout: cell c = whole 4096-record tiles [tile_start[c], tile_start[c+1]) of packed 8-byte records;
+ * every cell is sorted on its own, stable LSD over the low key_bits (<= 32) bits, the bits above are carried along -- the
+ * staged / direct scatter kernels the fused plan sorts its generated reads with (umi.py:97-115 grouping), exposed so that
+ * their ranking can be checked on arbitrary, adversarial digit distributions. */
+int32_t pmrd_sort_packed_cells(pmrd_ctx* ctx, const uint64_t* h_rec, int64_t n, const int64_t* h_cell_tile_start,
+                               int64_t n_cells, int32_t key_bits, uint64_t* h_out);
 
 /* umi_edit_distance (lib.rs:77-90, umi.py:90-95): Hamming on 2-bit packed UMIs of equal
  * length.  d[i] = hamming(a[i], b[i]). */

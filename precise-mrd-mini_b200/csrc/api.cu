@@ -189,6 +189,15 @@ int32_t pmrd_sync(pmrd_ctx* ctx) {
 
 int64_t pmrd_launch_count(const pmrd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
+int64_t pmrd_peak_memory_bytes(pmrd_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaMemPool_t pool;
+    uint64_t high = 0;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) != cudaSuccess) return 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &high) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (int64_t)high;
+}
+
 int32_t pmrd_profile_enable(pmrd_ctx* ctx, int32_t on) {
     if (!ctx) return PMRD_ERR_ARG;
     if (on && !ctx->prof) ctx->prof = new (std::nothrow) PmrdProf();
@@ -196,7 +205,7 @@ int32_t pmrd_profile_enable(pmrd_ctx* ctx, int32_t on) {
     return PMRD_OK;
 }
 
-// Synchronises, then writes one line per kernel: "<name> <launches> <total_ms>\n" and clears
+// Synchronises, then writes one line per kernel: "<name> <launches> <total_ms> <min_ms> <max_ms>\n" and clears
 // the records.  Returns the number of bytes written (truncated to cap-1).
 int64_t pmrd_profile_report(pmrd_ctx* ctx, char* buf, int64_t cap) {
     if (!ctx || !buf || cap <= 0) return 0;
@@ -204,18 +213,20 @@ int64_t pmrd_profile_report(pmrd_ctx* ctx, char* buf, int64_t cap) {
     PmrdProf* p = (PmrdProf*)ctx->prof;
     if (!p) return 0;
     cudaStreamSynchronize(ctx->stream);
-    std::map<std::string, std::pair<long long, double>> agg;
+    struct Agg { long long n = 0; double total = 0.0, mn = 1e300, mx = 0.0; };
+    std::map<std::string, Agg> agg;
     std::vector<std::string> order;
     for (ProfRec& r : p->recs) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
         std::string name(r.name);
-        const size_t lt = name.find('<');
         if (name.size() && name[0] == '(') name = name.substr(1, name.size() - 2);
-        (void)lt;
         if (!agg.count(name)) order.push_back(name);
-        agg[name].first += 1;
-        agg[name].second += ms;
+        Agg& a = agg[name];
+        a.n += 1;
+        a.total += ms;
+        if (ms < a.mn) a.mn = ms;
+        if (ms > a.mx) a.mx = ms;
         p->pool.push_back(r.a);
         p->pool.push_back(r.b);
     }
@@ -223,8 +234,9 @@ int64_t pmrd_profile_report(pmrd_ctx* ctx, char* buf, int64_t cap) {
     cudaGetLastError();
     int64_t off = 0;
     for (const std::string& n : order) {
-        char line[256];
-        const int w = snprintf(line, sizeof(line), "%s %lld %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        char line[320];
+        const Agg& a = agg[n];
+        const int w = snprintf(line, sizeof(line), "%s %lld %.6f %.6f %.6f\n", n.c_str(), a.n, a.total, a.mn, a.mx);
         if (off + w >= cap) break;
         memcpy(buf + off, line, (size_t)w);
         off += w;
@@ -384,6 +396,23 @@ int32_t pmrd_sort_pairs(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_t* h
 }
 
 // ---------------------------------------------------------------- collapse --------------
+int32_t pmrd_sort_packed_cells(pmrd_ctx* ctx, const uint64_t* h_rec, int64_t n, const int64_t* h_cell_tile_start, int64_t n_cells,
+                               int32_t key_bits, uint64_t* h_out) {
+    ENTER(ctx);
+    PMRD_ARG(ctx, n >= 0 && n_cells >= 0 && (n == 0 || (h_rec && h_out && h_cell_tile_start)), "null buffer");
+    if (n == 0 || n_cells == 0) return PMRD_OK;
+    PMRD_ARG(ctx, n % RS_TILE == 0 && h_cell_tile_start[0] == 0 && h_cell_tile_start[n_cells] * RS_TILE == n, "cells must be whole tiles covering [0, n)");
+    DevBuf a, b, ts;
+    PMRD_TRY(up(ctx, a, h_rec, (size_t)n * 8));
+    PMRD_CUDA(ctx, b.alloc(ctx->stream, (size_t)n * 8));
+    PMRD_TRY(up(ctx, ts, h_cell_tile_start, (size_t)(n_cells + 1) * 8));
+    int in_b = 0;
+    PMRD_TRY(radix_sort_pairs_segmented(ctx, a.as<uint64_t>(), nullptr, b.as<uint64_t>(), nullptr, n, ts.as<int64_t>(), n_cells, key_bits, &in_b));
+    PMRD_TRY(down(ctx, h_out, in_b ? b.p : a.p, (size_t)n * 8));
+    PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMRD_OK;
+}
+
 int32_t pmrd_collapse_reads_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp,
                                 uint32_t* d_payload_tmp, int64_t n_reads, const pmrd_umi_params* params,
                                 pmrd_family_table* d_fam, int64_t capacity_f, int64_t* n_families,

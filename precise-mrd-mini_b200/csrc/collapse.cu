@@ -559,6 +559,159 @@ cell_consensus_kernel(const uint64_t* __restrict__ rec, const int64_t* __restric
     }
 }
 
+// ---------------------------------------------------------------- fused consensus+count, bulk-copy form -------
+// The same tile -> per-cell counts step (FULL sort only) with the tile brought in by the copy engine: one elected thread
+// arms an mbarrier with the tile's 32 KB and issues ONE 1-D bulk async copy (cp.async.bulk.shared::cluster.global, SASS:
+// UBLKCP), every thread waits on the barrier's phase.  The 4096 LDG.64 + 8192 STS.32 of the load/split loop and their
+// address arithmetic leave the LSU -- the pipe ncu names as this kernel's limiter.  Records stay interleaved (umi | payload)
+// in shared memory; the head pass is warp-striped (a warp's 64-bit loads of 32 consecutive records are conflict-free,
+// neighbours compared through one shuffle) and leaves the one byte of every payload the vote needs (allele | quality)
+// in a dense array for the walk.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(CC_THREADS)
+cell_consensus_bulk_kernel(const uint64_t* __restrict__ rec, const int64_t* __restrict__ cell_tile_start, const int32_t* __restrict__ tile_cell,
+                           pmrd_umi_params P, int64_t cell0, const uint8_t* __restrict__ alt_allele, unsigned long long* __restrict__ o_fam,
+                           unsigned long long* __restrict__ o_tot, unsigned long long* __restrict__ o_var) {
+    constexpr int WARPS = CC_THREADS / 32, PER_WARP = CC_TILE / WARPS, ITERS = PER_WARP / 32;
+    __shared__ __align__(128) uint64_t s_rec[CC_TILE];
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ uint8_t s_plb[CC_TILE];
+    __shared__ uint16_t s_head[CC_TILE];
+    uint16_t* const s_order = reinterpret_cast<uint16_t*>(s_rec);    // (the records are not read any more once the heads are known)
+    __shared__ uint32_t s_wcount[WARPS];
+    __shared__ unsigned long long s_acc[3];
+    __shared__ double s_wt[64];
+    __shared__ uint32_t s_bkt[32];
+    const int64_t tile = blockIdx.x;
+    const int64_t base = tile * CC_TILE;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = lanemask_lt();
+    const uint32_t bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(CC_TILE * 8)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(s_rec)), "l"(rec + base), "r"((uint32_t)(CC_TILE * 8)), "r"(bar) : "memory");
+    }
+    // (overlaps the copy)
+    if (threadIdx.x < 3) s_acc[threadIdx.x] = 0ull;
+    if (threadIdx.x < 32) s_bkt[threadIdx.x] = 0u;
+    if (threadIdx.x < 64) s_wt[threadIdx.x] = (int)threadIdx.x >= P.quality_threshold ? c_wtab[threadIdx.x] : 0.0;
+    const int cell = tile_cell[tile];
+    const int64_t cell_lo = cell_tile_start[cell] * CC_TILE, cell_hi = cell_tile_start[cell + 1] * CC_TILE;
+    const uint32_t prev_tile_umi = base == cell_lo ? 0u : (uint32_t)rec[base - 1];
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+    // ---- heads, warp-striped: warp w owns records [w * 512, (w + 1) * 512)
+    uint32_t hm[ITERS], pm[ITERS];
+    uint32_t n_mine = 0;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int i = (int)warp * PER_WARP + it * 32 + (int)lane;
+        const uint64_t r = s_rec[i];
+        const uint32_t umi = (uint32_t)r;
+        s_plb[i] = (uint8_t)(r >> 32);                                  // allele[1:0] | quality << 2
+        uint32_t prev = __shfl_up_sync(0xffffffffu, umi, 1);
+        if (lane == 0) prev = i > 0 ? (uint32_t)s_rec[i - 1] : prev_tile_umi;
+        const bool head = (i == 0 && base == cell_lo) || umi != prev;
+        hm[it] = __ballot_sync(0xffffffffu, head);
+        pm[it] = __ballot_sync(0xffffffffu, (umi >> 24) == 0xffu);        // padding of the tile-aligned cell
+        n_mine += __popc(hm[it]);
+    }
+    if (lane == 0) s_wcount[warp] = n_mine;
+    __syncthreads();
+    uint32_t hbase = 0, n_heads = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+        const uint32_t c = s_wcount[w];
+        hbase += w < (int)warp ? c : 0u;
+        n_heads += c;
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        if ((hm[it] >> lane) & 1u) {
+            const int i = (int)warp * PER_WARP + it * 32 + (int)lane;
+            s_head[hbase + __popc(hm[it] & lt)] = (uint16_t)((uint32_t)i | (((pm[it] >> lane) & 1u) ? 0x8000u : 0u));
+        }
+        hbase += __popc(hm[it]);
+    }
+    const uint32_t last_umi = (uint32_t)s_rec[CC_TILE - 1];           // the UMI of the tile's last run (it may continue in the next tile)
+    __syncthreads();
+    // ---- heads bucketed by family length (longest first, padding runs last): the lanes of a warp walk equal lengths
+    auto bucket = [&](uint32_t h) -> uint32_t {
+        const uint32_t hv = s_head[h];
+        const uint32_t hi = (h + 1 < n_heads) ? (uint32_t)(s_head[h + 1] & 0xfffu) : (uint32_t)CC_TILE;
+        const uint32_t len = hi - (hv & 0xfffu);
+        return (hv & 0x8000u) ? 31u : 30u - (len < 30u ? len : 30u);
+    };
+    for (uint32_t h = threadIdx.x; h < n_heads; h += CC_THREADS) atomicAdd(&s_bkt[bucket(h)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t c = s_bkt[threadIdx.x];
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (threadIdx.x >= (uint32_t)o) incl += t;
+        }
+        s_bkt[threadIdx.x] = incl - c;
+    }
+    __syncthreads();
+    for (uint32_t h = threadIdx.x; h < n_heads; h += CC_THREADS) s_order[atomicAdd(&s_bkt[bucket(h)], 1u)] = (uint16_t)h;
+    __syncthreads();
+    const uint32_t alt = alt_allele[cell0 + cell];
+    uint32_t n_fam = 0, n_tot = 0, n_var = 0;
+    for (uint32_t hh = threadIdx.x; hh < n_heads; hh += CC_THREADS) {
+        const uint32_t h = (uint32_t)s_order[hh];
+        const uint32_t hv = s_head[h];
+        if (hv & 0x8000u) continue;                                      // padding
+        const int lo = (int)(hv & 0xfffu);
+        const int hi = (h + 1 < n_heads) ? (int)(s_head[h + 1] & 0xfffu) : CC_TILE;
+        const int n_in = hi - lo;
+        // the tile's last run may continue into the next tile(s) of the same cell
+        int64_t g_hi = base + CC_TILE;
+        if (h + 1 == n_heads) {
+            while (g_hi < cell_hi && (uint32_t)rec[g_hi] == last_umi) ++g_hi;
+        }
+        const int len = n_in + (int)(g_hi - (base + CC_TILE));
+        int best = -1;
+        if (P.consensus_threshold > 0.5) {
+            FoldVote2<true> v;
+            for (int c = 0; c < n_in; ++c) v.add(s_plb[lo + c], alt, s_wt);
+            for (int c = n_in; c < len; ++c) v.add((uint32_t)(rec[base + CC_TILE + (c - n_in)] >> 32), alt, s_wt);
+            if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
+        } else {
+            FoldVote2<false> v;
+            for (int c = 0; c < n_in; ++c) v.add(s_plb[lo + c], alt, s_wt);
+            for (int c = n_in; c < len; ++c) v.add((uint32_t)(rec[base + CC_TILE + (c - n_in)] >> 32), alt, s_wt);
+            if (len >= P.min_family_size) best = v.result(P.consensus_threshold);
+        }
+        ++n_fam;
+        if (best >= 0) { ++n_tot; n_var += best == 1; }
+    }
+    n_fam = warp_sum(n_fam); n_tot = warp_sum(n_tot); n_var = warp_sum(n_var);
+    if (lane == 0) {
+        atomicAdd(&s_acc[0], (unsigned long long)n_fam);
+        atomicAdd(&s_acc[1], (unsigned long long)n_tot);
+        atomicAdd(&s_acc[2], (unsigned long long)n_var);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_acc[0]) atomicAdd(&o_fam[cell0 + cell], s_acc[0]);
+        if (s_acc[1]) atomicAdd(&o_tot[cell0 + cell], s_acc[1]);
+        if (s_acc[2]) atomicAdd(&o_var[cell0 + cell], s_acc[2]);
+    }
+}
+
 // ---------------------------------------------------------------- small cells: one block, no HBM round trip ----
 // Cells of at most SC_THREADS * ITEMS reads (the C5 panel: ~1250 reads per (sample, locus) cell) are not worth a
 // tile-padded trip through the global radix passes.  Their records sit back to back (compact layout, no padding);
@@ -726,7 +879,11 @@ int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d
     const uint64_t* sr = in_b ? d_rec_tmp : d_rec;
     const uint32_t run_mask = sort_bits >= 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
     const int grid = (int)(n_out / CC_TILE);
-    if (sort_bits >= umi_bits) {
+    const char* cb = getenv("PMRD_CC_BULK");                 // 0: the LSU-loaded form of the consensus kernel
+    if (sort_bits >= umi_bits && d_tile_cell && (!cb || atoi(cb) != 0)) {
+        PMRD_LAUNCH_NAMED(ctx, "cell_consensus_kernel<true>", cell_consensus_bulk_kernel, grid, CC_THREADS, 0, sr, d_cell_tile_start, d_tile_cell, *params,
+                          cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot, (unsigned long long*)d_o_var);
+    } else if (sort_bits >= umi_bits) {
         PMRD_LAUNCH(ctx, cell_consensus_kernel<true>, grid, CC_THREADS, 0, sr, d_cell_tile_start, d_tile_cell, (int)n_cells, *params, 0xffffffffu,
                     cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot, (unsigned long long*)d_o_var);
     } else {

@@ -187,16 +187,23 @@ class Context:
     def profile_enable(self, on: bool = True) -> None:
         self._check(self.lib.pmrd_profile_enable(self.h, C.c_int32(1 if on else 0)))
 
-    def profile_report(self) -> Dict[str, Tuple[int, float]]:
-        """{kernel name: (launches, total device ms)} since the last report (synchronises)."""
+    def peak_memory_mb(self) -> float:
+        """High-water mark of the device's stream-ordered allocator pool, MB (``pmrd_peak_memory_bytes``)."""
+        self.lib.pmrd_peak_memory_bytes.restype = C.c_int64
+        self.lib.pmrd_peak_memory_bytes.argtypes = [C.c_void_p]
+        return float(self.lib.pmrd_peak_memory_bytes(self.h)) / 1e6
+
+    def profile_report(self, detail: bool = False):
+        """{kernel name: (launches, total device ms)} since the last report (synchronises);
+        ``detail=True``: ``(launches, total ms, min ms, max ms)``."""
         buf = C.create_string_buffer(1 << 16)
         self.lib.pmrd_profile_report.restype = C.c_int64
         self.lib.pmrd_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
         self.lib.pmrd_profile_report(self.h, buf, C.c_int64(len(buf)))
-        out: Dict[str, Tuple[int, float]] = {}
+        out = {}
         for line in buf.value.decode().splitlines():
-            name, cnt, ms = line.rsplit(" ", 2)
-            out[name] = (int(cnt), float(ms))
+            name, cnt, ms, mn, mx = line.rsplit(" ", 4)
+            out[name] = (int(cnt), float(ms), float(mn), float(mx)) if detail else (int(cnt), float(ms))
         return out
 
     # -- K8 ------------------------------------------------------------------------------
@@ -251,6 +258,15 @@ class Context:
         vo = None if vals is None else np.empty(n, np.uint32)
         self._check(self.lib.pmrd_sort_pairs(self.h, _ptr(keys), _ptr(v), C.c_int64(n), _ptr(ko), _ptr(vo)))
         return ko, vo
+
+    def sort_packed_cells(self, rec, cell_tile_start, key_bits: int = 24) -> np.ndarray:
+        """``pmrd_sort_packed_cells``: per-cell stable sort of packed 8-byte records on their low ``key_bits`` bits."""
+        rec = _arr(rec, np.uint64)
+        ts = _arr(cell_tile_start, np.int64)
+        out = np.empty_like(rec)
+        self._check(self.lib.pmrd_sort_packed_cells(self.h, _ptr(rec), C.c_int64(rec.shape[0]), _ptr(ts), C.c_int64(ts.shape[0] - 1),
+                                                    C.c_int32(key_bits), _ptr(out)))
+        return out
 
     # -- collapse ------------------------------------------------------------------------
     def collapse_reads(self, keys, payload, params: UmiParams, want_groups: bool = True, want_families: bool = True):

@@ -199,6 +199,49 @@ def eval_contamination_cmd(ctx: CLIContext) -> None:
     _echo("eval-contamination", ctx, contam=REPORTS_DIR / "contam_sensitivity.json", heatmap=REPORTS_DIR / "contam_heatmap.png")
 
 
+@main.command("performance")
+@click.option("--reset", is_flag=True, help="Reset performance monitoring data")
+@click.option("--out-dir", default=DATA_ROOT / "performance", show_default=True, type=click.Path(path_type=Path))
+@click.pass_obj
+def performance_cmd(ctx: CLIContext, reset: bool, out_dir: Path) -> None:
+    """Show performance monitoring statistics (``cli.py:408-438``).
+
+    The reference reports its in-process ``PerformanceMonitor`` (empty in a fresh CLI process).  Here the command
+    runs the smoke pipeline once with per-kernel CUDA-event timing and prints the same report shape --
+    ``timing_statistics`` maps every CUDA kernel to ``calls / total_time / avg_time / min_time / max_time`` (seconds),
+    ``peak_memory_mb`` is the device allocator's high-water mark."""
+    from . import _native as nv
+
+    if reset:
+        nv.default_context(ctx.seed).profile_report()
+        click.echo("Performance monitoring data reset.")
+        return
+    config = _load_pipeline_config(ctx.config_override, ctx.seed)
+    dctx = nv.default_context(int(config.seed))
+    dctx.profile_enable(True)
+    _run_smoke_pipeline(config, ctx.seed, out_dir)
+    prof = dctx.profile_report(detail=True)
+    dctx.profile_enable(False)
+    stats = {k: {"calls": n, "total_time": t * 1e-3, "avg_time": t * 1e-3 / max(n, 1), "min_time": mn * 1e-3, "max_time": mx * 1e-3}
+             for k, (n, t, mn, mx) in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    report = {"timing_statistics": stats, "peak_memory_mb": dctx.peak_memory_mb(), "total_functions_tracked": len(stats),
+              "device_time_s": sum(v["total_time"] for v in stats.values()), "kernel_launches": int(sum(v["calls"] for v in stats.values()))}
+    click.echo("Performance Report:")
+    click.echo("=" * 50)
+    if stats:
+        click.echo("\nTiming Statistics:")
+        for name, st in stats.items():
+            click.echo(f"  {name}:")
+            click.echo(f"    Calls: {st['calls']}")
+            click.echo(f"    Total: {st['total_time']:.6f}s")
+            click.echo(f"    Average: {st['avg_time']:.6f}s")
+            click.echo(f"    Min: {st['min_time']:.6f}s")
+            click.echo(f"    Max: {st['max_time']:.6f}s")
+    click.echo(f"\nPeak Memory Usage: {report['peak_memory_mb']:.1f} MB")
+    click.echo(f"Functions Tracked: {report['total_functions_tracked']}")
+    click.echo(json.dumps(report, indent=2, default=str))
+
+
 @main.command("eval-stratified")
 @click.pass_obj
 def eval_stratified_cmd(ctx: CLIContext) -> None:

@@ -345,3 +345,17 @@ def test_cli_smoke_and_determinism_subprocess(tmp_path):
     assert out.returncode == 0, out.stderr[-2000:]
     validate_artifacts(tmp_path / "reports")
     assert json.loads((tmp_path / "reports" / "lob.json").read_text())["n_blank_runs"] == 5
+    # `precise-mrd performance` (cli.py:408-438): the report shape of the reference's PerformanceMonitor, filled with the
+    # per-kernel CUDA-event times of one smoke run
+    out = subprocess.run([sys.executable, "-m", "precise_mrd.cli", "--seed", "7", "performance"], cwd=tmp_path, env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "Performance Report:" in out.stdout and "Timing Statistics:" in out.stdout
+    rep = json.loads(out.stdout[out.stdout.index("{"):])
+    assert set(rep) >= {"timing_statistics", "peak_memory_mb", "total_functions_tracked"}
+    ts = rep["timing_statistics"]
+    assert rep["total_functions_tracked"] == len(ts) >= 5 and rep["peak_memory_mb"] > 0
+    for name, st in ts.items():
+        assert set(st) == {"calls", "total_time", "avg_time", "min_time", "max_time"}
+        assert st["calls"] >= 1 and 0 <= st["min_time"] <= st["avg_time"] <= st["max_time"] <= st["total_time"] + 1e-12, name
+    assert any(k.startswith("gd_") for k in ts) and any(k.startswith("pvalues_kernel") for k in ts)

@@ -267,6 +267,50 @@ def test_collapse_gb_weighted_vs_reference(ctx, golden, native):
     _assert_tables_equal(fam, grp, wfam, wgrp)
 
 
+# ------------------------------------------------------------------------------ ranking kernels under stress
+@pytest.mark.parametrize("pattern", ["all_equal", "two_valued", "sorted", "reverse", "one_hot_digit", "random", "runs"])
+def test_ranking_kernels_on_adversarial_digit_distributions(ctx, pattern):
+    """The ballot / leader-atomic ranking of the scatter kernels (staged pass 1, direct passes 2-3, the counting and
+    cell-scan kernels) is where a race would hide, and the pool refuses compute-sanitizer's racecheck: every pattern
+    that maximises same-digit collisions inside a warp (all lanes one digit, two digits, long runs, already sorted,
+    reverse order) is sorted 40 times on the plan's cell-major layout -- cells of 1, 2, 7 and 61 tiles -- and must come
+    back, every time, as the stable per-cell sort of the input."""
+    rng = np.random.default_rng(len(pattern))
+    tiles = np.array([1, 2, 7, 61, 1, 3])
+    ts = np.concatenate([[0], np.cumsum(tiles)]).astype(np.int64)
+    n = int(ts[-1]) * 4096
+    if pattern == "all_equal":
+        umi = np.full(n, 0xABCDEF, np.uint64)
+    elif pattern == "two_valued":
+        umi = np.where(rng.random(n) < 0.5, np.uint64(0x010203), np.uint64(0xFFFEFD))
+    elif pattern == "sorted":
+        umi = (np.arange(n, dtype=np.uint64) // np.uint64(3)) & np.uint64(0xFFFFFF)
+    elif pattern == "reverse":
+        umi = ((np.uint64(n) - np.arange(n, dtype=np.uint64)) // np.uint64(5)) & np.uint64(0xFFFFFF)
+    elif pattern == "one_hot_digit":                      # one byte varies at a time, the other two constant
+        umi = (rng.integers(0, 256, n, dtype=np.uint64) << np.uint64(8)) | np.uint64(0x550033)
+    elif pattern == "runs":                               # runs of 32-200 equal keys: whole warps on one digit
+        lens = rng.integers(32, 200, n // 32)
+        umi = np.repeat(rng.integers(0, 1 << 24, len(lens), dtype=np.uint64), lens)[:n]
+    else:
+        umi = rng.integers(0, 1 << 24, n, dtype=np.uint64)
+    rec = (np.arange(n, dtype=np.uint64) << np.uint64(32)) | umi           # payload = input position: stability is visible
+    want = rec.copy()
+    for c in range(len(tiles)):
+        lo, hi = int(ts[c]) * 4096, int(ts[c + 1]) * 4096
+        want[lo:hi] = rec[lo:hi][np.argsort(umi[lo:hi], kind="stable")]
+    for _ in range(40):
+        got = ctx.sort_packed_cells(rec, ts, 24)
+        assert (got == want).all()
+    # the general (key + payload) scatter kernel and the in-block group sort on the same patterns
+    keys = ((np.arange(n, dtype=np.uint64) % np.uint64(37)) << np.uint64(32)) | umi
+    vals = np.arange(n, dtype=np.uint32)
+    for _ in range(10):
+        sk, sv = ctx.sort_pairs(keys, vals)
+        order = np.argsort(keys, kind="stable")
+        assert (sk == keys[order]).all() and (sv == vals[order]).all()
+
+
 def _panel_reads(rng, n, n_groups, umis_per_group, umi_bits=24):
     """External reads of a panel: dense group ids, a pool of UMIs per group, arbitrary order."""
     g = rng.integers(0, n_groups, n, dtype=np.uint64)
