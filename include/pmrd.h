@@ -348,7 +348,7 @@ typedef struct pmrd_read_sim_params {
                                  * PMRD_ENGINE_FUSED (1) reads are voted where they are drawn and never written
                                  * (eval/lod.py:125-150, sim/contamination.py:85-228 grids; results = the materialised
                                  * path on family-major read order; hop_rate must be 0) */
-    int32_t reserved0;
+    int32_t reserved0;          /* must be 0 (the library's own per-cell-knobs switch) */
 } pmrd_read_sim_params;
 #define PMRD_ENGINE_MATERIALISED 0
 #define PMRD_ENGINE_FUSED 1

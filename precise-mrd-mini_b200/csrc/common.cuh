@@ -66,6 +66,8 @@ extern char g_pmrd_create_err[512];
         PMRD_CUDA(ctx, cudaGetLastError());                                                   \
     } while (0)
 #define PMRD_LAUNCH(ctx, kernel, grid, block, smem, ...) PMRD_LAUNCH_NAMED(ctx, #kernel, kernel, grid, block, smem, __VA_ARGS__)
+// (arguments that are themselves macros holding a comma list are expanded first)
+#define PMRD_LAUNCH_NAMED_X(...) PMRD_LAUNCH_NAMED(__VA_ARGS__)
 
 // stream-ordered scratch buffer; freed on scope exit (cudaFreeAsync on the same stream)
 struct DevBuf {

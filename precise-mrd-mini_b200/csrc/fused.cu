@@ -98,14 +98,14 @@ __device__ __forceinline__ uint32_t fused_h2(uint32_t umi, int log2) { return (u
 
 // MODE 0: count the candidates of every cell (plan build: sizes the candidate list; nothing else is written)
 // MODE 1: the step
-template <int THREADS, bool MAJ, int MODE>
+template <int THREADS, bool MAJ, int MODE, bool KNOBS>
 __global__ void __launch_bounds__(THREADS)
 fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells, pmrd_read_sim_params sp, pmrd_umi_params P,
                   const float* __restrict__ size_cdf, const uint8_t* __restrict__ size_lut, int filt_log2,
                   uint64_t* __restrict__ cand_key, uint32_t* __restrict__ cand_fam, unsigned long long* __restrict__ cand_cursor,
                   int64_t cell0, const uint8_t* __restrict__ alt_allele, unsigned long long* __restrict__ o_reads,
                   unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot, unsigned long long* __restrict__ o_var,
-                  unsigned long long* __restrict__ o_cand) {
+                  unsigned long long* __restrict__ o_cand, const CellKnobDev* __restrict__ knobs /* [n_cells] or NULL */) {
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char fz_raw[];
     // layout: [4 bitmaps][allele sums 4 x THREADS doubles][weights][slots][stash][tables]
@@ -146,10 +146,11 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
     const Philox ph(seed);
     const float* const cdf = have_cdf ? s_cdf : nullptr;
     const uint8_t* const lut = have_cdf ? s_lut : nullptr;
+    const CellKnobDev* const kn = KNOBS ? knobs + cell : nullptr;
 
     // ---- pass 1: every molecule's UMI into the two filters --------------------------------
     for (uint32_t f = threadIdx.x; f < n_fam; f += THREADS) {
-        const FamDraw d = draw_family(ph, c, f, sp, cdf, lut);
+        const FamDraw d = draw_family<KNOBS>(ph, c, f, sp, cdf, lut, kn);
         const uint32_t a = fused_h1(d.umi, filt_log2), b = fused_h2(d.umi, filt_log2);
         const uint32_t ba = 1u << (a & 31u), bb = 1u << (b & 31u);
         if (atomicOr(&s_seen1[a >> 5], ba) & ba) atomicOr(&s_dup1[a >> 5], ba);
@@ -170,7 +171,7 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
         d.size = 0; d.umi = 0; d.key = 0; d.has_variant = false;
         bool cand = false;
         if (valid) {
-            d = draw_family(ph, c, f, sp, cdf, lut);
+            d = draw_family<KNOBS>(ph, c, f, sp, cdf, lut, kn);
             const uint32_t a = fused_h1(d.umi, filt_log2), b = fused_h2(d.umi, filt_log2);
             cand = ((s_dup1[a >> 5] >> (a & 31u)) & 1u) && ((s_dup2[b >> 5] >> (b & 31u)) & 1u);
             n_reads += (uint32_t)d.size;
@@ -273,12 +274,13 @@ static size_t fused_smem_bytes(int threads, int filt_log2) {
 // ---------------------------------------------------------------- replay -----------------
 // Sorted candidate list: a run of equal (cell, umi) keys is one family.  The thread at the head of a run re-draws
 // the reads of its molecules in family order and votes them as one family.
-template <bool MAJ>
+template <bool MAJ, bool KNOBS>
 __global__ void __launch_bounds__(128)
 fused_replay_kernel(uint64_t seed, const ReadCell* __restrict__ cells, pmrd_read_sim_params sp, pmrd_umi_params P,
                     const float* __restrict__ size_cdf, const uint8_t* __restrict__ size_lut, const uint64_t* __restrict__ key,
                     const uint32_t* __restrict__ fam, int64_t n, int64_t cell0, const uint8_t* __restrict__ alt_allele,
-                    unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot, unsigned long long* __restrict__ o_var) {
+                    unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot, unsigned long long* __restrict__ o_var,
+                    const CellKnobDev* __restrict__ knobs) {
     __shared__ double s_sum[4 * 128];
     __shared__ double s_wt[64];
     __shared__ float s_cdf[128];
@@ -315,7 +317,7 @@ fused_replay_kernel(uint64_t seed, const ReadCell* __restrict__ cells, pmrd_read
             if ((int64_t)fj > last && fj < f) f = fj;
         }
         last = (int64_t)f;
-        const FamDraw d = draw_family(ph, c, f, sp, have_cdf ? s_cdf : nullptr, have_cdf ? s_lut : nullptr);
+        const FamDraw d = draw_family<KNOBS>(ph, c, f, sp, have_cdf ? s_cdf : nullptr, have_cdf ? s_lut : nullptr, KNOBS ? knobs + cell : nullptr);
         const uint32_t word = d.umi | ((d.has_variant ? 1u : 0u) << 24) | (c.ref_allele << 26) | (c.alt_allele << 28);
         for (uint32_t r = 0; r < (uint32_t)d.size; ++r) v.add(draw_read_payload(d.key, ctr_hi | r, f, word, s_qlut, s_qthr) & 0xffu, s_wt);
         size_all += (uint32_t)d.size;
@@ -332,17 +334,17 @@ fused_replay_kernel(uint64_t seed, const ReadCell* __restrict__ cells, pmrd_read
 }
 
 // ---------------------------------------------------------------- host side --------------
-template <int THREADS, bool MAJ, int MODE>
+template <int THREADS, bool MAJ, int MODE, bool KNOBS>
 static int32_t fused_launch(pmrd_ctx* ctx, FusedChunk* ch, const pmrd_umi_params* up, uint64_t* ck, uint32_t* cf, unsigned long long* cursor,
                             const uint8_t* d_alt, int64_t* o_reads, int64_t* o_fam, int64_t* o_tot, int64_t* o_var, unsigned long long* o_cand) {
     const size_t smem = fused_smem_bytes(THREADS, ch->filt_log2);
-    PMRD_CUDA(ctx, cudaFuncSetAttribute(fused_cell_kernel<THREADS, MAJ, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PMRD_LAUNCH_NAMED(ctx, MODE ? "fused_cell_kernel" : "fused_count_kernel", (fused_cell_kernel<THREADS, MAJ, MODE>), (int)ch->n_cells, THREADS, smem,
+    PMRD_CUDA(ctx, cudaFuncSetAttribute(fused_cell_kernel<THREADS, MAJ, MODE, KNOBS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PMRD_LAUNCH_NAMED(ctx, MODE ? "fused_cell_kernel" : "fused_count_kernel", (fused_cell_kernel<THREADS, MAJ, MODE, KNOBS>), (int)ch->n_cells, THREADS, smem,
                       ctx->seed, (const ReadCell*)ch->cells.as<ReadCell>(), (int)ch->n_cells, ch->sp, *up,
                       ch->has_size_cdf ? (const float*)ch->size_cdf.as<float>() : (const float*)nullptr,
                       ch->has_size_cdf ? (const uint8_t*)ch->size_lut.as<uint8_t>() : (const uint8_t*)nullptr, ch->filt_log2, ck, cf, cursor,
                       ch->cell0, d_alt, (unsigned long long*)o_reads, (unsigned long long*)o_fam, (unsigned long long*)o_tot,
-                      (unsigned long long*)o_var, o_cand);
+                      (unsigned long long*)o_var, o_cand, ch->knobs.p ? (const CellKnobDev*)ch->knobs.as<CellKnobDev>() : (const CellKnobDev*)nullptr);
     return PMRD_OK;
 }
 
@@ -350,12 +352,15 @@ template <int MODE>
 static int32_t fused_dispatch(pmrd_ctx* ctx, FusedChunk* ch, const pmrd_umi_params* up, uint64_t* ck, uint32_t* cf, unsigned long long* cursor,
                               const uint8_t* d_alt, int64_t* o_reads, int64_t* o_fam, int64_t* o_tot, int64_t* o_var, unsigned long long* o_cand) {
     const bool maj = up->consensus_threshold > 0.5;
+    const bool kn = ch->knobs.p != nullptr;
+#define FUSED_ARGS ctx, ch, up, ck, cf, cursor, d_alt, o_reads, o_fam, o_tot, o_var, o_cand
 #define FUSED_GO(T)                                                                                                            \
-    return maj ? fused_launch<T, true, MODE>(ctx, ch, up, ck, cf, cursor, d_alt, o_reads, o_fam, o_tot, o_var, o_cand)          \
-               : fused_launch<T, false, MODE>(ctx, ch, up, ck, cf, cursor, d_alt, o_reads, o_fam, o_tot, o_var, o_cand)
+    if (kn) return maj ? fused_launch<T, true, MODE, true>(FUSED_ARGS) : fused_launch<T, false, MODE, true>(FUSED_ARGS);         \
+    return maj ? fused_launch<T, true, MODE, false>(FUSED_ARGS) : fused_launch<T, false, MODE, false>(FUSED_ARGS)
     if (ch->threads == 1024) { FUSED_GO(1024); }
     if (ch->threads == 256) { FUSED_GO(256); }
     FUSED_GO(128);
+#undef FUSED_ARGS
 #undef FUSED_GO
 }
 
@@ -370,8 +375,7 @@ int32_t fused_chunk_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double*
     int64_t nf = 0, max_f = 0;
     for (int64_t i = 0; i < n_cells; ++i) {
         reads_init_cell(&hc[i], (uint64_t)h_cell_id[i], h_af ? h_af[i] : 0.0, nf, (uint32_t)i);
-        reads_apply_extra(&hc[i], sp, h_extra ? h_extra + i : nullptr, cell0, n_cells);
-        if (hc[i].hop_rate > 0.0f) { free(hc); PMRD_ARG(ctx, false, "the fused engine keeps a read inside its cell: hop_rate > 0 needs the materialised engine"); }
+        if (h_extra && h_extra[i].hop_rate > 0.0f) { free(hc); PMRD_ARG(ctx, false, "the fused engine keeps a read inside its cell: hop_rate > 0 needs the materialised engine"); }
         const int64_t f = h_n_families[i] > 0 ? h_n_families[i] : 0;
         nf += f;
         if (f > max_f) max_f = f;
@@ -388,6 +392,14 @@ int32_t fused_chunk_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double*
     uint8_t h_lut[4096];
     ch->has_size_cdf = reads_build_size_tables(sp, h_cdf, h_lut);
     cudaError_t e = ch->cells.alloc(ctx->stream, sizeof(ReadCell) * (size_t)(n_cells + 1));
+    CellKnobDev* h_kn = nullptr;
+    if (h_extra && n_cells > 0) {
+        h_kn = (CellKnobDev*)malloc(sizeof(CellKnobDev) * (size_t)n_cells);
+        if (!h_kn) { free(hc); PMRD_ARG(ctx, false, "out of host memory"); }
+        for (int64_t i = 0; i < n_cells; ++i) reads_fill_knob(&h_kn[i], &hc[i], &h_extra[i], cell0, n_cells);
+        if (e == cudaSuccess) e = ch->knobs.alloc(ctx->stream, sizeof(CellKnobDev) * (size_t)n_cells);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(ch->knobs.p, h_kn, sizeof(CellKnobDev) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(ch->cells.p, hc, sizeof(ReadCell) * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess && ch->has_size_cdf) {
         e = ch->size_cdf.alloc(ctx->stream, sizeof(h_cdf));
@@ -400,6 +412,7 @@ int32_t fused_chunk_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double*
     if (e == cudaSuccess) e = reads.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);      // hc / tables were staged from the stack and the heap
     free(hc);
+    free(h_kn);
     if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "fused plan: %s", cudaGetErrorString(e)); return PMRD_ERR_CUDA; }
     ch->n_cand = 0;
     ch->n_reads = 0;
@@ -452,13 +465,14 @@ int32_t fused_chunk_run(pmrd_ctx* ctx, FusedChunk* ch, const pmrd_umi_params* up
     const uint32_t* sf = in_b ? vb : va;
     const float* cdf = ch->has_size_cdf ? (const float*)ch->size_cdf.as<float>() : (const float*)nullptr;
     const uint8_t* lut = ch->has_size_cdf ? (const uint8_t*)ch->size_lut.as<uint8_t>() : (const uint8_t*)nullptr;
-    if (up->consensus_threshold > 0.5)
-        PMRD_LAUNCH_NAMED(ctx, "fused_replay_kernel", fused_replay_kernel<true>, pmrd_blocks(ch->n_cand, 128), 128, 0, ctx->seed,
-                          (const ReadCell*)ch->cells.as<ReadCell>(), ch->sp, *up, cdf, lut, sk, sf, ch->n_cand, ch->cell0, d_alt,
-                          (unsigned long long*)o_fam, (unsigned long long*)o_tot, (unsigned long long*)o_var);
-    else
-        PMRD_LAUNCH_NAMED(ctx, "fused_replay_kernel", fused_replay_kernel<false>, pmrd_blocks(ch->n_cand, 128), 128, 0, ctx->seed,
-                          (const ReadCell*)ch->cells.as<ReadCell>(), ch->sp, *up, cdf, lut, sk, sf, ch->n_cand, ch->cell0, d_alt,
-                          (unsigned long long*)o_fam, (unsigned long long*)o_tot, (unsigned long long*)o_var);
+    const CellKnobDev* kn = (const CellKnobDev*)ch->knobs.as<CellKnobDev>();
+#define REPLAY_ARGS pmrd_blocks(ch->n_cand, 128), 128, 0, ctx->seed, (const ReadCell*)ch->cells.as<ReadCell>(), ch->sp, *up, cdf, lut, sk, sf, ch->n_cand, \
+                    ch->cell0, d_alt, (unsigned long long*)o_fam, (unsigned long long*)o_tot, (unsigned long long*)o_var, kn
+    const bool maj = up->consensus_threshold > 0.5;
+    if (kn && maj) PMRD_LAUNCH_NAMED_X(ctx, "fused_replay_kernel", (fused_replay_kernel<true, true>), REPLAY_ARGS);
+    else if (kn) PMRD_LAUNCH_NAMED_X(ctx, "fused_replay_kernel", (fused_replay_kernel<false, true>), REPLAY_ARGS);
+    else if (maj) PMRD_LAUNCH_NAMED_X(ctx, "fused_replay_kernel", (fused_replay_kernel<true, false>), REPLAY_ARGS);
+    else PMRD_LAUNCH_NAMED_X(ctx, "fused_replay_kernel", (fused_replay_kernel<false, false>), REPLAY_ARGS);
+#undef REPLAY_ARGS
     return PMRD_OK;
 }

@@ -4,6 +4,7 @@
 #include "reads.cuh"
 
 struct FusedChunk {
+    DevBuf knobs;                       // CellKnobDev[n_cells] or empty
     DevBuf cells, size_cdf, size_lut;   // ReadCell[n_cells + 1] (the closing entry carries the family total), size tables
     pmrd_read_sim_params sp;
     bool has_size_cdf = false;

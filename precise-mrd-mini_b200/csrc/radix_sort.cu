@@ -6,6 +6,12 @@
 #ifndef RS_DIRECT_MIN_BLOCKS
 #define RS_DIRECT_MIN_BLOCKS 3
 #endif
+#ifndef RS_WIDE_MIN_BLOCKS        /* blocks per SM the 256 x 16 scatter kernels are compiled for (register cap = 65536 / (256 x this)) */
+#define RS_WIDE_MIN_BLOCKS 4
+#endif
+#ifndef RS_SWIDE_MIN_BLOCKS
+#define RS_SWIDE_MIN_BLOCKS 4
+#endif
 
 // zero `words` (a multiple of 4 * THREADS) 32-bit shared-memory counters with 16-byte stores, fully unrolled
 // (the scalar loop was 9 % of the direct downsweep's instructions)
@@ -499,7 +505,7 @@ static int32_t rs_set_attrs(pmrd_ctx* ctx) {
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<RS_WARPS>)));
-        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<256, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<8>)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<256, 16, RS_SWIDE_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<8>)));
     }
     return PMRD_OK;
 }
@@ -549,12 +555,12 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         } else if (stage) {
             static int swide = -1;
             if (swide < 0) { const char* e = getenv("PMRD_RS_SWIDE"); swide = e ? atoi(e) : 1; }   // 1: 256 threads x 16 records, 4 blocks / SM (8.1 vs 9.2 ms per step)
-            if (swide) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_staged_kernel", (rs_downsweep_staged_kernel<256, 16, 4>), n_tiles, 256, sizeof(RsStage<8>), kin, kout, hist, shift, mask);
+            if (swide) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_staged_kernel", (rs_downsweep_staged_kernel<256, 16, RS_SWIDE_MIN_BLOCKS>), n_tiles, 256, sizeof(RsStage<8>), kin, kout, hist, shift, mask);
             else PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_staged_kernel", (rs_downsweep_staged_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>), n_tiles, RS_THREADS, sizeof(RsStage<RS_WARPS>), kin, kout, hist, shift, mask);
         } else if (direct) {   // packed 8-byte records, stored straight to their final place (L2 merges the sectors)
             static int wide = -1;
             if (wide < 0) { const char* e = getenv("PMRD_RS_WIDE"); wide = e ? atoi(e) : 2; }   // 2: 256 threads x 16 records, 4 blocks / SM (measured best, by 3 %)
-            if (wide == 2) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<256, 16, 4>), n_tiles, 256, 0, kin, kout, hist, shift, mask);
+            if (wide == 2) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<256, 16, RS_WIDE_MIN_BLOCKS>), n_tiles, 256, 0, kin, kout, hist, shift, mask);
             else PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>), n_tiles, RS_THREADS, 0, kin, kout, hist, shift, mask);
         } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);

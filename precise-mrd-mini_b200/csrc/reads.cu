@@ -20,11 +20,13 @@
 #include "reads_dev.cuh"
 #include <stdlib.h>
 
+template <bool KNOBS>
 __global__ void __launch_bounds__(256)
 reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                   int64_t n_fam, pmrd_read_sim_params sp, const float* __restrict__ size_cdf /* [128] or NULL */,
                   const uint8_t* __restrict__ size_lut /* [4096] or NULL */, const int32_t* __restrict__ blk_cell,
-                  uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word, uint32_t* __restrict__ fam_key) {
+                  uint32_t* __restrict__ fam_size, uint32_t* __restrict__ fam_word, uint32_t* __restrict__ fam_key,
+                  const CellKnobDev* __restrict__ knobs /* [n_cells] or NULL */) {
     __shared__ float s_cdf[128];
     __shared__ __align__(16) uint8_t s_lut[4096];
     static_assert(READS_FAM_BLOCK * 16 == 4096, "one 16-byte LUT slice per thread");
@@ -36,8 +38,8 @@ reads_size_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64
     const Philox ph(seed);
     const int ci = find_cell_in(fam_offsets, blk_cell[blockIdx.x], blk_cell[blockIdx.x + 1] + 1, f);
     const ReadCell c = cells[ci];
-    const FamDraw d = draw_family(ph, c, (uint32_t)(f - c.fam_offset), sp, size_cdf ? s_cdf : nullptr,
-                                  (size_cdf && size_lut) ? s_lut : nullptr);
+    const FamDraw d = draw_family<KNOBS>(ph, c, (uint32_t)(f - c.fam_offset), sp, size_cdf ? s_cdf : nullptr,
+                                         (size_cdf && size_lut) ? s_lut : nullptr, KNOBS ? knobs + ci : nullptr);
     fam_size[f] = (uint32_t)d.size;
     fam_word[f] = d.umi | ((d.has_variant ? 1u : 0u) << 24);   // the generator re-reads this instead of re-drawing
     fam_key[f] = d.key;
@@ -111,12 +113,14 @@ __device__ __forceinline__ uint32_t window_tile(uint32_t w, uint32_t n, float in
     return tile0 + shuffle_window(w, n_full, inv_full);
 }
 
+template <bool KNOBS>
 __global__ void __launch_bounds__(256)
 reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_t* __restrict__ fam_offsets, int n_cells,
                  int64_t n_fam, pmrd_read_sim_params sp, const uint64_t* __restrict__ read_offset /*[n_fam]*/,
                  const uint32_t* __restrict__ fam_size, const uint32_t* __restrict__ fam_word, const uint32_t* __restrict__ fam_key,
                  const int32_t* __restrict__ blk_cell, int64_t n_reads, int segmented, uint64_t* __restrict__ keys,
-                 uint32_t* __restrict__ payload, uint32_t* __restrict__ tile_hist /* [n_tiles][256], zeroed, or NULL */) {
+                 uint32_t* __restrict__ payload, uint32_t* __restrict__ tile_hist /* [n_tiles][256], zeroed, or NULL */,
+                 const CellKnobDev* __restrict__ knobs /* [n_cells] or NULL: hop rates and pools per cell */) {
     __shared__ FamSlot s_slot[8][32];
     __shared__ uint32_t s_qthr[32];
     __shared__ __align__(16) uint8_t s_qlut[1 << QUAL_LUT_BITS];
@@ -221,9 +225,11 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
             const uint32_t c2 = (uint32_t)cells[S.ci].cell_id;
             const uint32_t c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((cells[S.ci].cell_id >> 32) & 0xffffffu);
             const uint4 h = ph(0x80000000u | j, sb.z, c2, c3);  // (a block of its own: hopping is rare)
-            const ReadCell& hc = cells[S.ci];                   // per-cell rate, hop pool = cells [pool_start, pool_start + pool_n)
-            if (hc.pool_n > 1u && u24(h.x) < hc.hop_rate) {
-                const uint32_t other = hc.pool_start + ((uint32_t)S.ci - hc.pool_start + 1u + h.y % (hc.pool_n - 1u)) % hc.pool_n;
+            // per-cell rate and hop pool = cells [pool_start, pool_start + pool_n) when the plan carries knobs, else the whole batch
+            const float rate = KNOBS ? knobs[S.ci].hop_rate : (float)sp.hop_rate;
+            const uint32_t p0 = KNOBS ? knobs[S.ci].pool_start : 0u, pn = KNOBS ? knobs[S.ci].pool_n : (uint32_t)n_cells;
+            if (pn > 1u && u24(h.x) < rate) {
+                const uint32_t other = p0 + ((uint32_t)S.ci - p0 + 1u + h.y % (pn - 1u)) % pn;
                 const ReadCell oc = cells[other];
                 group = oc.group;
                 pl = (pl & 0x7fffffffu) | ((allele == oc.alt_allele ? 1u : 0u) << 31);
@@ -311,7 +317,6 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
     int64_t nf = 0;
     for (int64_t i = 0; i < n_cells; ++i) {
         reads_init_cell(&hc[i], (uint64_t)h_cell_id[i], h_af ? h_af[i] : 0.0, nf, group_base + (uint32_t)i);
-        reads_apply_extra(&hc[i], sp, h_extra ? h_extra + i : nullptr, first_cell, n_cells);
         ho[i] = nf;
         nf += h_n_families[i] > 0 ? h_n_families[i] : 0;
     }
@@ -328,6 +333,16 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->cells.p, hc, sizeof(ReadCell) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(plan->fam_offsets.p, ho, 8 * (size_t)(n_cells + 1), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = plan->cell_tile_start.alloc(ctx->stream, 8 * (size_t)(n_cells + 1));
+    CellKnobDev* h_kn = nullptr;
+    if (h_extra && n_cells > 0) {          // per-cell knobs ride in their own array (see reads.cuh)
+        h_kn = (CellKnobDev*)malloc(sizeof(CellKnobDev) * (size_t)n_cells);
+        if (!h_kn) { free(hc); free(ho); PMRD_ARG(ctx, false, "out of host memory"); }
+        for (int64_t i = 0; i < n_cells; ++i) reads_fill_knob(&h_kn[i], &hc[i], &h_extra[i], first_cell, n_cells);
+        if (e == cudaSuccess) e = plan->knobs.alloc(ctx->stream, sizeof(CellKnobDev) * (size_t)n_cells);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(plan->knobs.p, h_kn, sizeof(CellKnobDev) * (size_t)n_cells, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        free(h_kn);
+    }
     // cell of the first family of every READS_FAM_BLOCK-family block (+ a closing entry)
     const int64_t n_blk = (nf + READS_FAM_BLOCK - 1) / READS_FAM_BLOCK;
     int32_t* h_blk = (int32_t*)malloc(4 * (size_t)(n_blk + 1));
@@ -431,12 +446,14 @@ int32_t reads_plan_build(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* 
 // family sizes + read offsets (device only, no sync): part of every simulate step
 int32_t reads_plan_sizes(pmrd_ctx* ctx, ReadPlan* plan) {
     if (plan->n_fam <= 0) return PMRD_OK;
-    PMRD_LAUNCH(ctx, reads_size_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
-                plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
-                plan->has_size_cdf ? (const float*)plan->size_cdf.as<float>() : (const float*)nullptr,
-                plan->has_size_cdf ? (const uint8_t*)plan->size_lut.as<uint8_t>() : (const uint8_t*)nullptr,
-                (const int32_t*)plan->blk_cell.as<int32_t>(), plan->fam_size.as<uint32_t>(), plan->fam_word.as<uint32_t>(),
-                plan->fam_key.as<uint32_t>());
+#define SIZE_ARGS ctx->seed, plan->cells.as<ReadCell>(), plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,                       \
+                  plan->has_size_cdf ? (const float*)plan->size_cdf.as<float>() : (const float*)nullptr,                                                  \
+                  plan->has_size_cdf ? (const uint8_t*)plan->size_lut.as<uint8_t>() : (const uint8_t*)nullptr,                                            \
+                  (const int32_t*)plan->blk_cell.as<int32_t>(), plan->fam_size.as<uint32_t>(), plan->fam_word.as<uint32_t>(), plan->fam_key.as<uint32_t>(), \
+                  (const CellKnobDev*)plan->knobs.as<CellKnobDev>()
+    if (plan->knobs.p) PMRD_LAUNCH_NAMED_X(ctx, "reads_size_kernel", reads_size_kernel<true>, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, SIZE_ARGS);
+    else PMRD_LAUNCH_NAMED_X(ctx, "reads_size_kernel", reads_size_kernel<false>, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, SIZE_ARGS);
+#undef SIZE_ARGS
     return exclusive_scan<uint32_t, uint64_t>(ctx, plan->fam_size.as<uint32_t>(), plan->read_offset.as<uint64_t>(), plan->n_fam,
                                               plan->total.as<uint64_t>());
 }
@@ -448,12 +465,14 @@ int32_t reads_plan_generate(pmrd_ctx* ctx, ReadPlan* plan, uint64_t* d_keys, uin
     if (plan->n_fam <= 0) return PMRD_OK;
     if (plan->segmented != 1) d_tile_hist = nullptr;
     if (d_tile_hist) PMRD_CUDA(ctx, cudaMemsetAsync(d_tile_hist, 0, (size_t)(plan->n_out / READS_SEG_TILE) * 256 * sizeof(uint32_t), ctx->stream));
-    PMRD_LAUNCH(ctx, reads_gen_kernel, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, ctx->seed, plan->cells.as<ReadCell>(),
-                plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,
-                (const uint64_t*)plan->read_offset.as<uint64_t>(), (const uint32_t*)plan->fam_size.as<uint32_t>(),
-                (const uint32_t*)plan->fam_word.as<uint32_t>(), (const uint32_t*)plan->fam_key.as<uint32_t>(),
-                (const int32_t*)plan->blk_cell.as<int32_t>(), plan->n_reads,
-                plan->segmented, d_keys, d_payload, d_tile_hist);
+#define GEN_ARGS ctx->seed, plan->cells.as<ReadCell>(), plan->fam_offsets.as<int64_t>(), (int)plan->n_cells, plan->n_fam, plan->sp,                       \
+                 (const uint64_t*)plan->read_offset.as<uint64_t>(), (const uint32_t*)plan->fam_size.as<uint32_t>(),                                     \
+                 (const uint32_t*)plan->fam_word.as<uint32_t>(), (const uint32_t*)plan->fam_key.as<uint32_t>(),                                         \
+                 (const int32_t*)plan->blk_cell.as<int32_t>(), plan->n_reads, plan->segmented, d_keys, d_payload, d_tile_hist,                          \
+                 (const CellKnobDev*)plan->knobs.as<CellKnobDev>()
+    if (plan->knobs.p) PMRD_LAUNCH_NAMED_X(ctx, "reads_gen_kernel", reads_gen_kernel<true>, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, GEN_ARGS);
+    else PMRD_LAUNCH_NAMED_X(ctx, "reads_gen_kernel", reads_gen_kernel<false>, pmrd_blocks(plan->n_fam, READS_FAM_BLOCK), READS_FAM_BLOCK, 0, GEN_ARGS);
+#undef GEN_ARGS
     if (plan->segmented == 1 && plan->n_out > plan->n_reads)
         PMRD_LAUNCH(ctx, reads_pad_kernel, (int)plan->n_cells, 256, 0, plan->cells.as<ReadCell>(), (int)plan->n_cells,
                     (const int64_t*)plan->cell_tile_start.as<int64_t>(), d_keys, d_payload, d_tile_hist);

@@ -15,11 +15,17 @@ struct ReadCell {
     int64_t af_lt, af_ge;  // has_variant threshold words (see draw_family)
     float inv_full;        // segmented layout: 1 / (complete 4096-read windows) when the window permutation applies, else 0
     uint32_t tile0;        // segmented layout: out_start / 4096
-    // per-cell contamination knobs (sim/contamination.py:230-311 at read level; defaults: the plan-wide pmrd_read_sim_params)
+};
+
+// per-cell contamination knobs (sim/contamination.py:230-311 at read level), kept OUT of ReadCell: the hot kernels load a
+// ReadCell per block / family and must not carry fields only a contamination sweep reads.  One row per cell of a chunk,
+// present only when the plan was created with pmrd_cell_knobs.
+struct CellKnobDev {
     float hop_rate;        // each read is re-keyed to another cell of the cell's hop pool w.p. hop_rate
     float collision_rate;  // a molecule takes the previous molecule's UMI w.p. collision_rate
-    uint32_t pool_start, pool_n;   // hop pool: cells [pool_start, pool_start + pool_n) of the batch
+    uint32_t pool_start, pool_n;   // hop pool: cells [pool_start, pool_start + pool_n) of the chunk
     uint32_t n_own;        // molecules [0, n_own) are the sample's own; [n_own, ...) come from a contaminating sample ...
+    uint32_t pad0;
     double af2;            // ... with this allele fraction (cross-sample contamination, contamination.py:280-311)
     int64_t af2_lt, af2_ge;
 };
@@ -38,6 +44,7 @@ struct CellExtra {
 #define READS_IS_PAD_UMI(u) (((u) >> 24) == 0xffu)
 
 struct ReadPlan {
+    DevBuf knobs;   // CellKnobDev[n_cells] or empty (no per-cell knobs)
     DevBuf cells, fam_offsets, fam_size, fam_word, fam_key, read_offset, total, cell_tile_start, size_cdf, size_lut, blk_cell, tile_cell;
     bool has_size_cdf = false;  // Poisson sizes with mean <= 16: inverted against an fp32 cdf table
     pmrd_read_sim_params sp;
@@ -82,31 +89,25 @@ static inline void reads_init_cell(ReadCell* c, uint64_t cell_id, double af, int
     c->inv_full = 0.0f;
     c->tile0 = 0;
     reads_af_thresholds(af, &c->af_lt, &c->af_ge);
-    c->hop_rate = 0.0f;
-    c->collision_rate = 0.0f;
-    c->pool_start = 0;
-    c->pool_n = 0;
-    c->n_own = 0xffffffffu;
-    c->af2 = af;
-    c->af2_lt = c->af_lt;
-    c->af2_ge = c->af_ge;
 }
 
-// plan-wide knobs, then the per-cell overrides (`first` = index of the chunk's first cell in the call, `n_chunk` its
-// cell count: hop pools are re-based to the chunk and must lie inside it)
-static inline void reads_apply_extra(ReadCell* c, const pmrd_read_sim_params* sp, const CellExtra* x, int64_t first, int64_t n_chunk) {
-    c->hop_rate = (float)sp->hop_rate;
-    c->collision_rate = (float)sp->collision_rate;
-    c->pool_start = 0;
-    c->pool_n = (uint32_t)n_chunk;
-    if (!x) return;
-    c->hop_rate = x->hop_rate;
-    c->collision_rate = x->collision_rate;
-    if (x->pool_n > 0) { c->pool_start = (uint32_t)((int64_t)x->pool_start - first); c->pool_n = x->pool_n; }
+// device row of a cell's knobs (`first` = index of the chunk's first cell in the call, `n_chunk` its cell count: hop pools
+// are re-based to the chunk and must lie inside it)
+static inline void reads_fill_knob(CellKnobDev* k, const ReadCell* c, const CellExtra* x, int64_t first, int64_t n_chunk) {
+    k->hop_rate = x->hop_rate;
+    k->collision_rate = x->collision_rate;
+    k->pool_start = 0;
+    k->pool_n = (uint32_t)n_chunk;
+    if (x->pool_n > 0) { k->pool_start = (uint32_t)((int64_t)x->pool_start - first); k->pool_n = x->pool_n; }
+    k->n_own = 0xffffffffu;
+    k->pad0 = 0;
+    k->af2 = c->af;
+    k->af2_lt = c->af_lt;
+    k->af2_ge = c->af_ge;
     if (x->n_own >= 0) {
-        c->n_own = (uint32_t)x->n_own;
-        c->af2 = x->af2;
-        reads_af_thresholds(x->af2, &c->af2_lt, &c->af2_ge);
+        k->n_own = (uint32_t)x->n_own;
+        k->af2 = x->af2;
+        reads_af_thresholds(x->af2, &k->af2_lt, &k->af2_ge);
     }
 }
 

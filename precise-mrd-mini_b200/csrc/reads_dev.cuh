@@ -31,8 +31,11 @@ struct FamDraw {
 };
 
 // s_cdf: Poisson cdf table in shared memory (128 floats, padded with 2.0f) or nullptr
+// KNOBS / kn: the cell's row of per-cell knobs; KNOBS = false (plan-wide knobs only) is the hot configuration and compiles
+// to exactly the code it had before per-cell knobs existed
+template <bool KNOBS = false>
 __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell& c, uint32_t fam, const pmrd_read_sim_params& sp,
-                                               const float* s_cdf, const uint8_t* s_lut = nullptr) {
+                                               const float* s_cdf, const uint8_t* s_lut = nullptr, const CellKnobDev* kn = nullptr) {
     const uint32_t c2 = (uint32_t)c.cell_id, c3 = (PMRD_STREAM_READS << 24) | (uint32_t)((c.cell_id >> 32) & 0xffffffu);
     const uint4 b = ph(0xffffffffu, fam, c2, c3);
     FamDraw d;
@@ -67,20 +70,39 @@ __device__ __forceinline__ FamDraw draw_family(const Philox& ph, const ReadCell&
     // io.py:97: has_variant = u53(b.w, b2.x) < af.  The top 32 bits settle it unless b.w sits on the
     // cell's threshold word (probability 2^-32), so the second Philox block is drawn only then, or
     // when a contamination knob needs its other words (io.py:100-101).
-    const bool extras = sp.contamination_rate > 0.0 || c.collision_rate > 0.0f;
-    // molecules [n_own, ...) of the cell come from a contaminating sample with its own allele fraction
-    const bool own = fam < c.n_own;
-    const int64_t lt = own ? c.af_lt : c.af2_lt, ge = own ? c.af_ge : c.af2_ge;
+    if (!KNOBS) {
+        // plan-wide knobs only
+        const bool extras = sp.contamination_rate > 0.0 || sp.collision_rate > 0.0;
+        const int64_t hw = (int64_t)b.w;
+        if (!extras && (hw < c.af_lt || hw >= c.af_ge)) {
+            d.has_variant = hw < c.af_lt;
+            return d;
+        }
+        const uint4 b2 = ph(0xfffffffeu, fam, c2, c3);
+        d.has_variant = u53(b.w, b2.x) < c.af;
+        if (sp.contamination_rate > 0.0 && u53(b2.y, b2.z) < sp.contamination_rate) d.has_variant = !d.has_variant;
+        if (sp.collision_rate > 0.0 && fam > 0 && u24(b2.w) < (float)sp.collision_rate) {
+            // barcode collision: share the previous molecule's UMI (two molecules, one barcode)
+            const uint4 pb = ph(0xffffffffu, fam - 1, c2, c3);
+            d.umi = pb.z & 0xffffffu;
+        }
+        return d;
+    }
+    // per-cell knobs (pmrd_cell_knobs): the same draws, the cell's own collision rate, and molecules [n_own, ...) drawn
+    // against the contaminating sample's allele fraction
+    const CellKnobDev k = *kn;
+    const bool extras = sp.contamination_rate > 0.0 || k.collision_rate > 0.0f;
+    const bool own = fam < k.n_own;
+    const int64_t lt = own ? c.af_lt : k.af2_lt, ge = own ? c.af_ge : k.af2_ge;
     const int64_t hw = (int64_t)b.w;
     if (!extras && (hw < lt || hw >= ge)) {
         d.has_variant = hw < lt;
         return d;
     }
     const uint4 b2 = ph(0xfffffffeu, fam, c2, c3);
-    d.has_variant = u53(b.w, b2.x) < (own ? c.af : c.af2);
+    d.has_variant = u53(b.w, b2.x) < (own ? c.af : k.af2);
     if (sp.contamination_rate > 0.0 && u53(b2.y, b2.z) < sp.contamination_rate) d.has_variant = !d.has_variant;
-    if (c.collision_rate > 0.0f && fam > 0 && u24(b2.w) < c.collision_rate) {
-        // barcode collision: share the previous molecule's UMI (two molecules, one barcode)
+    if (k.collision_rate > 0.0f && fam > 0 && u24(b2.w) < k.collision_rate) {
         const uint4 pb = ph(0xffffffffu, fam - 1, c2, c3);
         d.umi = pb.z & 0xffffffu;
     }
