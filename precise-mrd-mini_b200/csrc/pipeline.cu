@@ -437,11 +437,13 @@ int32_t call_counts_dev(pmrd_ctx* ctx, const int64_t* d_tot, const int64_t* d_va
 }
 
 int32_t plan_run_call(pmrd_ctx* ctx, pmrd_plan* P) {
-    if (P->n_groups <= 1)
+    if (P->n_groups <= 1 && P->n_cells > 4096)
         return call_counts_dev(ctx, P->o_tot.as<int64_t>(), P->o_var.as<int64_t>(), P->neg.as<uint8_t>(), P->n_cells, P->stream_id,
                                P->test_type, P->alternative, P->alpha, P->mean_rate.as<double>(), P->negc.as<int64_t>(),
                                P->o_p.as<double>(), P->o_q.as<double>(), P->o_sig.as<uint8_t>(), P->bh_ws.p);
-    // several call groups: each is what ONE call_mrd of the reference sees -- its own error rate, its own BH
+    // several call groups: each is what ONE call_mrd of the reference sees -- its own error rate, its own BH.
+    // (A single group of <= 4096 cells takes this path too: BH by one block that ranks by counting -- 3 launches for
+    // the whole call stage instead of the 45 of a radix sort over 62 key bits; bit-equal to it.)
     PMRD_LAUNCH(ctx, error_rate_kernel, (int)P->n_groups, 256, 0, ctx->seed, (uint64_t)0, (const uint64_t*)P->gstream.as<uint64_t>(),
                 (const int64_t*)P->gs.as<int64_t>(), (const int64_t*)P->o_tot.as<int64_t>(), (const int64_t*)P->o_var.as<int64_t>(),
                 (const uint8_t*)P->neg.as<uint8_t>(), P->n_cells, P->mean_rate.as<double>(), P->negc.as<int64_t>(), P->cell_group.as<int32_t>());

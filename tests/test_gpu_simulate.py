@@ -646,11 +646,13 @@ def test_chunked_plan_equals_single_chunk(ctx, native):
     plan.run()
     prof = ctx.profile_report()
     ctx.profile_enable(False)
+    n_chunks = plan.n_chunks
     plan.close()
     for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
         assert (one[k_] == many[k_]).all(), k_
     assert one["mean_error_rate"] == many["mean_error_rate"] and (one["totals"] == many["totals"]).all()
-    assert prof["rs_downsweep_kernel<true>"][0] >= plan.n_chunks and prof["reads_gen_kernel"][1] > 0
+    assert prof["reads_gen_kernel"][0] == n_chunks and prof["reads_gen_kernel"][1] > 0
+    assert prof["bh_group_kernel"][0] == 1 and prof["pvalues_kernel"][0] == 1       # one call stage over all chunks (<= 4096 cells: BH in one block)
 
 
 def test_generator_histogram_replaces_the_first_counting_pass(ctx, native, monkeypatch):
