@@ -137,7 +137,6 @@ __device__ __forceinline__ void family_row(uint32_t size, PlAt pl_at, const pmrd
     n_alt = 0; consensus = 0; qsum_best = 0; n_best = 0; flags = 0;
     if (MODE == PMRD_MODE_WEIGHTED) {
         double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0, total = 0.0;
-        uint32_t qs0 = 0, qs1 = 0, qs2 = 0, qs3 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
         uint32_t order = 0, seen = 0, n_seen = 0;  // order: 2 bits per allele = rank of first appearance
         for (uint32_t r = 0; r < size; ++r) {
             const uint32_t pl = pl_at(r);
@@ -151,8 +150,6 @@ __device__ __forceinline__ void family_row(uint32_t size, PlAt pl_at, const pmrd
                 w2 = __dadd_rn(w2, a == 2 ? w : 0.0);
                 w3 = __dadd_rn(w3, a == 3 ? w : 0.0);
                 total = __dadd_rn(total, w);
-                qs0 += a == 0 ? q : 0; qs1 += a == 1 ? q : 0; qs2 += a == 2 ? q : 0; qs3 += a == 3 ? q : 0;
-                c0 += a == 0; c1 += a == 1; c2 += a == 2; c3 += a == 3;
                 if (!((seen >> a) & 1u)) {
                     seen |= 1u << a;
                     order |= n_seen << (2 * a);
@@ -180,9 +177,13 @@ __device__ __forceinline__ void family_row(uint32_t size, PlAt pl_at, const pmrd
             if (total != 0.0 && !(frac < P.consensus_threshold)) {
                 flags |= PMRD_FAM_HAS_CONSENSUS;
                 consensus = (uint32_t)best;
-                const uint32_t qs[4] = {qs0, qs1, qs2, qs3}, cs[4] = {c0, c1, c2, c3};
-                qsum_best = qs[best];
-                n_best = cs[best];
+                // consensus_quality = mean quality of the winner's qualifying reads (umi.py:177): a second, integer-only walk
+                // over the family instead of eight conditional counters in the first one
+                for (uint32_t r = 0; r < size; ++r) {
+                    const uint32_t pl = pl_at(r);
+                    const uint32_t q = (pl >> 2) & 63u;
+                    if ((pl & 3u) == (uint32_t)best && (int)q >= P.quality_threshold) { qsum_best += q; ++n_best; }
+                }
             }
         }
     } else if (MODE == PMRD_MODE_MAJORITY) {
@@ -1172,25 +1173,33 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
         for (int i = 0; i < ITEMS; ++i) s_rec[warp * PER_WARP + i * 32 + lane] = key[i];
         __syncthreads();
     }
-    // family heads, compacted in order
-    for (int i0 = 0; i0 < n; i0 += GR_THREADS) {
-        const int i = i0 + (int)threadIdx.x;
+    // family heads, compacted in order: warp w owns the sorted records [w * PER_WARP, (w + 1) * PER_WARP); the head masks
+    // of its ITEMS 32-record steps stay in registers while the eight warp totals are prefixed
+    uint32_t hm[ITEMS];
+    uint32_t n_mine = 0;
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int i = (int)warp * PER_WARP + it * 32 + (int)lane;
         const bool head = i < n && (i == 0 || (uint32_t)s_rec[i - 1] != (uint32_t)s_rec[i]);
-        const uint32_t hm = __ballot_sync(0xffffffffu, head);
-        uint32_t wcount = __popc(hm), excl;
-        // (ordered across the warps of this sweep: prefix over the warps through shared memory)
-        if (lane == 0) sw[warp] = wcount;
-        __syncthreads();
-        excl = 0;
-        for (uint32_t w = 0; w < warp; ++w) excl += sw[w];
-        uint32_t all = 0;
-        for (uint32_t w = 0; w < (uint32_t)WARPS; ++w) all += sw[w];
-        const uint32_t base = s_nheads;
-        if (head) s_list[base + excl + __popc(hm & lt)] = (uint16_t)i;
-        __syncthreads();
-        if (threadIdx.x == 0) s_nheads = base + all;
-        __syncthreads();
+        hm[it] = __ballot_sync(0xffffffffu, head);
+        n_mine += __popc(hm[it]);
     }
+    if (lane == 0) sw[warp] = n_mine;
+    __syncthreads();
+    uint32_t hbase = 0, n_all = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+        const uint32_t c = sw[w];
+        hbase += w < (int)warp ? c : 0u;
+        n_all += c;
+    }
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        if ((hm[it] >> lane) & 1u) s_list[hbase + __popc(hm[it] & lt)] = (uint16_t)((int)warp * PER_WARP + it * 32 + (int)lane);
+        hbase += __popc(hm[it]);
+    }
+    if (threadIdx.x == 0) s_nheads = n_all;
+    __syncthreads();
     const int n_heads = (int)s_nheads;
     const uint64_t ghi = keys[lo] & 0xffffffff00000000ull;
     for (int h = threadIdx.x; h < n_heads; h += GR_THREADS) {
