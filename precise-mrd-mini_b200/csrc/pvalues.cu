@@ -228,10 +228,13 @@ int32_t k9_bh(pmrd_ctx* ctx, const double* d_p, int64_t m, double alpha, uint8_t
 // cut, Appendix B of SURVEY.md), then exactly the arithmetic of the global path -- p * m / rank in that order, reverse
 // running minimum, clip -- so a group's q-values are bit-equal to pmrd_bh run on that group alone.
 #define BHG_MAX 4096
-__global__ void __launch_bounds__(256)
+#define BHG_THREADS 1024
+__global__ void __launch_bounds__(BHG_THREADS)
 bh_group_kernel(const double* __restrict__ p, const int64_t* __restrict__ gs, double alpha, uint8_t* __restrict__ rejected, double* __restrict__ q) {
-    __shared__ double s_p[BHG_MAX];        // sorted p, then raw adjusted values
-    __shared__ uint16_t s_src[BHG_MAX];    // sorted position -> cell of the group
+    extern __shared__ __align__(16) unsigned char bhg_raw[];
+    double* const s_in = reinterpret_cast<double*>(bhg_raw);           // [BHG_MAX] the group's p-values (every thread scans all of them)
+    double* const s_p = s_in + BHG_MAX;                                // [BHG_MAX] sorted p, then raw adjusted values
+    uint16_t* const s_src = reinterpret_cast<uint16_t*>(s_p + BHG_MAX); // [BHG_MAX] sorted position -> cell of the group
     __shared__ unsigned int s_kstar;
     const int64_t lo = gs[blockIdx.x];
     const int m = (int)(gs[blockIdx.x + 1] - lo);
@@ -240,9 +243,15 @@ bh_group_kernel(const double* __restrict__ p, const int64_t* __restrict__ gs, do
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         double v = p[lo + i];
         if (v == 0.0) v = 0.0;                                   // -0.0 folded onto +0.0, as bh_pack_kernel does
+        s_in[i] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double v = s_in[i];
         int rank = 0;
+#pragma unroll 4
         for (int j = 0; j < m; ++j) {
-            const double w = p[lo + j];
+            const double w = s_in[j];                            // (same address for the whole warp: a broadcast)
             rank += (w < v) || (w == v && j < i);
         }
         s_p[rank] = v;
@@ -258,9 +267,20 @@ bh_group_kernel(const double* __restrict__ p, const int64_t* __restrict__ gs, do
     __syncthreads();
     for (int i = threadIdx.x; i < m; i += blockDim.x) s_p[i] = __ddiv_rn(__dmul_rn(s_p[i], md), (double)(i + 1));   // call.py:59-61
     __syncthreads();
-    if (threadIdx.x == 0) {                                       // reverse running minimum (call.py:64-70): m <= 4096
-        double run = INFINITY;
-        for (int i = m - 1; i >= 0; --i) {
+    // reverse running minimum (call.py:64-70): warp 0, each lane a contiguous slice, then the carries from the slices after it
+    if (threadIdx.x < 32) {
+        const int per = (m + 31) / 32;
+        const int a = (int)threadIdx.x * per, b = min(a + per, m);
+        double mn = INFINITY;
+        for (int i = b - 1; i >= a; --i) mn = fmin(mn, s_p[i]);
+        double carry = INFINITY;                                  // min over the slices after mine
+#pragma unroll
+        for (int l = 31; l >= 0; --l) {
+            const double other = __shfl_sync(0xffffffffu, mn, l);
+            if (l > (int)threadIdx.x) carry = fmin(carry, other);
+        }
+        double run = carry;
+        for (int i = b - 1; i >= a; --i) {
             run = fmin(run, s_p[i]);
             s_p[i] = run;
         }
@@ -276,6 +296,8 @@ bh_group_kernel(const double* __restrict__ p, const int64_t* __restrict__ gs, do
 
 int32_t k9_bh_groups(pmrd_ctx* ctx, const double* d_p, const int64_t* d_gs, int64_t n_groups, double alpha, uint8_t* d_rejected, double* d_q) {
     if (n_groups <= 0) return PMRD_OK;
-    PMRD_LAUNCH(ctx, bh_group_kernel, (int)n_groups, 256, 0, d_p, d_gs, alpha, d_rejected, d_q);
+    const size_t smem = (size_t)BHG_MAX * (8 + 8 + 2);
+    PMRD_CUDA(ctx, cudaFuncSetAttribute(bh_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PMRD_LAUNCH(ctx, bh_group_kernel, (int)n_groups, BHG_THREADS, smem, d_p, d_gs, alpha, d_rejected, d_q);
     return PMRD_OK;
 }
