@@ -362,11 +362,12 @@ def run_external(args, rank, world, local_rank, emit):
     fam_p = {k: v.data_ptr() for k, v in fam_t.items()}
     grp_p = {k: v.data_ptr() for k, v in grp_t.items()}
 
-    def step_dev():
+    def step_dev(with_rows=False):
+        """The per-locus table (UMIProcessor.process_reads + get_consensus_counts); with_rows: the family table as well."""
         dk.copy_(k0); dp.copy_(p0)                                   # restore the inputs (the call clobbers them): untimed
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        nf, ng = ctx.collapse_reads_dev(dk.data_ptr(), dp.data_ptr(), dkt.data_ptr(), dpt.data_ptr(), n, P, fam_p, fcap, grp_p, gcap)
+        nf, ng = ctx.collapse_reads_dev(dk.data_ptr(), dp.data_ptr(), dkt.data_ptr(), dpt.data_ptr(), n, P, fam_p if with_rows else None, fcap, grp_p, gcap)
         e1.record(stream)
         torch.cuda.synchronize()
         return e0.elapsed_time(e1), nf, ng
@@ -389,6 +390,8 @@ def run_external(args, rank, world, local_rank, emit):
     ctx.profile_enable(False)
     d_fc = grp_t["family_count"][:ng].cpu().numpy().astype(np.uint32)
     d_cc = grp_t["consensus_count"][:ng * 4].cpu().numpy().astype(np.uint32).reshape(ng, 4)
+    rows_ms = min(step_dev(True)[0] for _ in range(3))               # the same call with the family table materialised as well
+    assert (grp_t["family_count"][:ng].cpu().numpy().astype(np.uint32) == d_fc).all()
 
     # ---- end-to-end arm: host (pageable NumPy) arrays in, the per-locus table out, every step --------------
     ctx.collapse_reads(keys, payload, P, want_families=False)        # warm the allocator pool and the pinned ring
@@ -420,7 +423,7 @@ def run_external(args, rank, world, local_rank, emit):
         kms = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])[:10]}
         top_name, top = max(prof.items(), key=lambda kv: kv[1][1])
         # bytes one launch of each kernel moves per read (its share of the data path)
-        per_launch = {"rs_downsweep_kernel<true>": 24.0, "rs_upsweep_kernel": 8.0, "group_rows_kernel": 12.0 + 32.0 / 5.0, "grp_count_kernel": 8.0,
+        per_launch = {"rs_downsweep_kernel<true>": 24.0, "rs_upsweep_kernel": 8.0, "group_rows_kernel": 12.0, "grp_bounds_kernel": 8.0,
                       "family_kernel": 12.0 + 32.0 / 5.0, "group_rows_compact_kernel": 64.0 / 5.0}
         b = next((v for k, v in per_launch.items() if top_name.startswith(k.split("<")[0])), None)
         avg_ms = top[1] / max(top[0], 1)
@@ -434,7 +437,8 @@ def run_external(args, rank, world, local_rank, emit):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 key (group:32 | umi:32) + u32 payload, f64 consensus weights", "data": "synthetic",
             "config": external_config(n, n_loci, world),
-            "layout": {"families": int(nf), "loci_with_reads": int(ng), "path": "group-major (count -> partition by group -> one block sorts and votes a locus)"},
+            "layout": {"families": int(nf), "loci_with_reads": int(ng), "path": "group-major (stable partition by locus -> one block sorts and votes a locus -> its row of the per-locus table)",
+                       "with_family_table_ms_per_step": rows_ms, "with_family_table_value": float(n) * world / (rows_ms * 1e-3)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "Context.collapse_reads(keys, payload, want_families=False): pageable NumPy arrays through the pinned staging "
                            "ring (csrc/staging.cu), per-locus table back",

@@ -439,12 +439,18 @@ int32_t pmrd_collapse_reads(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_
     PMRD_TRY(up(ctx, pa, h_payload, n * 4));
     PMRD_CUDA(ctx, kb.alloc(ctx->stream, n * 8));
     PMRD_CUDA(ctx, pb.alloc(ctx->stream, n * 4));
-    PMRD_CUDA(ctx, fk.alloc(ctx->stream, n * 8));
-    PMRD_CUDA(ctx, fs.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, fa.alloc(ctx->stream, n * 4));
-    PMRD_CUDA(ctx, fc.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, fq.alloc(ctx->stream, n * 4));
-    PMRD_CUDA(ctx, fn.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, ff.alloc(ctx->stream, n * 4));
-    pmrd_family_table dfam{fk.as<uint64_t>(), fs.as<uint32_t>(), fa.as<uint32_t>(), fc.as<uint32_t>(),
-                           fq.as<uint32_t>(), fn.as<uint32_t>(), ff.as<uint32_t>()};
+    const bool want_fam = h_fam->key != nullptr;          // NULL columns: only the group table is wanted (no family row is even computed
+                                                           // when the group-major path applies)
+    PMRD_ARG(ctx, want_fam || (h_grp && n_groups), "neither a family table nor a group table was asked for");
+    pmrd_family_table dfam{};
+    if (want_fam) {
+        PMRD_CUDA(ctx, fk.alloc(ctx->stream, n * 8));
+        PMRD_CUDA(ctx, fs.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, fa.alloc(ctx->stream, n * 4));
+        PMRD_CUDA(ctx, fc.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, fq.alloc(ctx->stream, n * 4));
+        PMRD_CUDA(ctx, fn.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, ff.alloc(ctx->stream, n * 4));
+        dfam = pmrd_family_table{fk.as<uint64_t>(), fs.as<uint32_t>(), fa.as<uint32_t>(), fc.as<uint32_t>(),
+                                 fq.as<uint32_t>(), fn.as<uint32_t>(), ff.as<uint32_t>()};
+    }
     pmrd_group_table dgrp{};
     const bool want_groups = h_grp && n_groups;
     if (want_groups) {
@@ -458,7 +464,6 @@ int32_t pmrd_collapse_reads(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_
                          &dfam, n_reads, &nf, want_groups ? &dgrp : nullptr, n_reads, want_groups ? &ng : nullptr));
     *n_families = nf;
     if (n_groups) *n_groups = ng;
-    const bool want_fam = h_fam->key != nullptr;          // NULL columns: the family rows stay on the device
     if ((want_fam && nf > capacity_f) || (want_groups && ng > capacity_g)) {
         snprintf(ctx->err, sizeof(ctx->err), "output capacity too small: %lld families, %lld groups", (long long)nf, (long long)ng);
         return PMRD_ERR_CAPACITY;

@@ -1077,16 +1077,27 @@ greedy_assign_kernel(const uint64_t* __restrict__ sk, const uint32_t* __restrict
 //              the group's reads start (a group has at most as many families as reads)
 //   compact    scan of the per-group family counts, rows moved to their final place -> the family table, sorted by key
 // The consensus arithmetic is family_row(), the one family_kernel runs.
+// group boundaries of the group-sorted keys: start[g] = first read of group g, cnt[g] = its read count (both zeroed
+// beforehand: ids without reads keep 0).  One coalesced pass over the keys -- the per-read L2 atomics of a histogram over
+// 1e5 ids cost four times as much (0.81 vs 0.2 ms per 1.25e8 reads).
 __global__ void __launch_bounds__(256)
-grp_count_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ cnt) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&cnt[(uint32_t)(keys[i] >> 32)], 1u);
+grp_bounds_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ start, uint32_t* __restrict__ cnt) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = (uint32_t)(keys[i] >> 32);
+        if (i == 0 || (uint32_t)(keys[i - 1] >> 32) != g) start[g] = (uint32_t)i;
+        if (i == n - 1 || (uint32_t)(keys[i + 1] >> 32) != g) cnt[g] = (uint32_t)(i + 1);      // end for now; grp_max_kernel turns it into a count
+    }
 }
+// end -> count, largest group, non-empty flag per id (scanned into the group-table row of every id)
 __global__ void __launch_bounds__(256)
-grp_max_kernel(const uint32_t* __restrict__ cnt, int64_t n_ids, uint32_t* __restrict__ out /*[2]: max size, groups with reads*/) {
+grp_max_kernel(const uint32_t* __restrict__ start, uint32_t* __restrict__ cnt, int64_t n_ids, uint32_t* __restrict__ nonempty,
+               uint32_t* __restrict__ out /*[2]: max size, groups with reads*/) {
     uint32_t mx = 0, ne = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_ids; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t c = cnt[i];
+        const uint32_t e = cnt[i];
+        const uint32_t c = e ? e - start[i] : 0u;
+        cnt[i] = c;
+        nonempty[i] = c > 0 ? 1u : 0u;
         mx = max(mx, c);
         ne += c > 0;
     }
@@ -1096,10 +1107,14 @@ grp_max_kernel(const uint32_t* __restrict__ cnt, int64_t n_ids, uint32_t* __rest
 }
 
 #define GR_THREADS 256
-template <int ITEMS, int MODE>
+// ROWS = true: family rows (tmp, then compacted) for a caller that wants the family table.  ROWS = false: the group's row
+// of the GROUP table is reduced right here (umi.py:241-266, mrd/umi.py:86-99) -- no family row is ever written.
+template <int ITEMS, int MODE, bool ROWS>
 __global__ void __launch_bounds__(GR_THREADS)
 group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload, const uint32_t* __restrict__ grp_start,
-                  const uint32_t* __restrict__ grp_cnt, int n_rounds, pmrd_umi_params P, FamOut tmp, uint32_t* __restrict__ fam_cnt) {
+                  const uint32_t* __restrict__ grp_cnt, int n_rounds, pmrd_umi_params P, FamOut tmp, uint32_t* __restrict__ fam_cnt,
+                  const uint32_t* __restrict__ grp_row /* ROWS = false: row of every id in the group table */, pmrd_group_table G,
+                  unsigned long long* __restrict__ n_fam_total) {
     constexpr int CAP = GR_THREADS * ITEMS, WARPS = GR_THREADS / 32, PER_WARP = CAP / WARPS;
     extern __shared__ __align__(16) unsigned char gr_raw[];
     uint64_t* const s_rec = reinterpret_cast<uint64_t*>(gr_raw);                 // payload:32 | umi:32
@@ -1111,7 +1126,7 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
     __shared__ double s_wt[64];
     const uint32_t g = blockIdx.x;
     const int n = (int)grp_cnt[g];
-    if (n == 0) { if (threadIdx.x == 0) fam_cnt[g] = 0u; return; }
+    if (n == 0) { if (ROWS && threadIdx.x == 0) fam_cnt[g] = 0u; return; }
     if (threadIdx.x < 64) s_wt[threadIdx.x] = c_wtab[threadIdx.x];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = lanemask_lt();
@@ -1202,22 +1217,56 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
     __syncthreads();
     const int n_heads = (int)s_nheads;
     const uint64_t ghi = keys[lo] & 0xffffffff00000000ull;
+    uint32_t a_fc = 0, a_alt = 0, a_tot = 0, a_c0 = 0, a_c1 = 0, a_c2 = 0, a_c3 = 0;      // ROWS = false: this thread's share of the group row
     for (int h = threadIdx.x; h < n_heads; h += GR_THREADS) {
         const int i = (int)s_list[h];
         const int end = h + 1 < n_heads ? (int)s_list[h + 1] : n;
         uint32_t n_alt, consensus, qsum_best, n_best, flags;
         family_row<MODE>((uint32_t)(end - i), [&](uint32_t r) -> uint32_t { return (uint32_t)(s_rec[i + r] >> 32); }, P, s_wt, n_alt,
                          consensus, qsum_best, n_best, flags);
-        const size_t o = (size_t)lo + h;
-        tmp.key[o] = ghi | (uint32_t)s_rec[i];
-        tmp.size[o] = (uint32_t)(end - i);
-        tmp.n_alt[o] = n_alt;
-        tmp.consensus[o] = consensus;
-        tmp.qsum[o] = qsum_best;
-        tmp.n_best[o] = n_best;
-        tmp.flags[o] = flags;
+        if (ROWS) {
+            const size_t o = (size_t)lo + h;
+            tmp.key[o] = ghi | (uint32_t)s_rec[i];
+            tmp.size[o] = (uint32_t)(end - i);
+            tmp.n_alt[o] = n_alt;
+            tmp.consensus[o] = consensus;
+            tmp.qsum[o] = qsum_best;
+            tmp.n_best[o] = n_best;
+            tmp.flags[o] = flags;
+        } else if (flags & PMRD_FAM_KEPT) {                      // exactly what group_kernel sums over the family table
+            ++a_fc;
+            a_alt += n_alt;
+            a_tot += (uint32_t)(end - i);
+            if (MODE == PMRD_MODE_WEIGHTED && (flags & PMRD_FAM_HAS_CONSENSUS)) {
+                const uint32_t a = consensus & 3u;
+                a_c0 += a == 0; a_c1 += a == 1; a_c2 += a == 2; a_c3 += a == 3;
+            }
+        }
     }
-    if (threadIdx.x == 0) fam_cnt[g] = (uint32_t)n_heads;
+    if (ROWS) {
+        if (threadIdx.x == 0) fam_cnt[g] = (uint32_t)n_heads;
+        return;
+    }
+    __shared__ uint32_t s_red[7];
+    if (threadIdx.x < 7) s_red[threadIdx.x] = 0u;
+    __syncthreads();
+    a_fc = warp_sum(a_fc); a_alt = warp_sum(a_alt); a_tot = warp_sum(a_tot);
+    a_c0 = warp_sum(a_c0); a_c1 = warp_sum(a_c1); a_c2 = warp_sum(a_c2); a_c3 = warp_sum(a_c3);
+    if (lane == 0) {
+        atomicAdd(&s_red[0], a_fc); atomicAdd(&s_red[1], a_alt); atomicAdd(&s_red[2], a_tot);
+        atomicAdd(&s_red[3], a_c0); atomicAdd(&s_red[4], a_c1); atomicAdd(&s_red[5], a_c2); atomicAdd(&s_red[6], a_c3);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t row = grp_row[g];
+        G.group[row] = g;
+        G.family_count[row] = s_red[0];
+        G.alt_count[row] = s_red[1];
+        G.total_count[row] = s_red[2];
+        G.consensus_count[row * 4 + 0] = s_red[3]; G.consensus_count[row * 4 + 1] = s_red[4];
+        G.consensus_count[row * 4 + 2] = s_red[5]; G.consensus_count[row * 4 + 3] = s_red[6];
+        atomicAdd(n_fam_total, (unsigned long long)n_heads);
+    }
 }
 
 // rows of group g: tmp[grp_start[g] .. + fam_cnt[g])  ->  out[fam_base[g] ..)
@@ -1243,21 +1292,32 @@ static size_t group_rows_smem(int items) {
     return cap * 8 + (GR_THREADS / 32) * 256 * 4 + 256 * 4 + 36 * 4 + cap * 2 + 16;
 }
 
-template <int MODE>
+template <int MODE, bool ROWS>
 static int32_t launch_group_rows(pmrd_ctx* ctx, int64_t max_group, int64_t n_ids, const uint64_t* keys, const uint32_t* payload,
                                  const uint32_t* grp_start, const uint32_t* grp_cnt, int n_rounds, const pmrd_umi_params& P, FamOut tmp,
-                                 uint32_t* fam_cnt) {
-#define GR_CASE(I)                                                                                                                  \
-    if (max_group <= (int64_t)GR_THREADS * (I)) {                                                                                   \
-        const size_t smem = group_rows_smem(I);                                                                                     \
-        PMRD_CUDA(ctx, cudaFuncSetAttribute(group_rows_kernel<I, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        PMRD_LAUNCH_NAMED(ctx, "group_rows_kernel", (group_rows_kernel<I, MODE>), (int)n_ids, GR_THREADS, smem, keys, payload, grp_start, \
-                          grp_cnt, n_rounds, P, tmp, fam_cnt);                                                                       \
-        return PMRD_OK;                                                                                                             \
+                                 uint32_t* fam_cnt, const uint32_t* grp_row, const pmrd_group_table& G, unsigned long long* n_fam_total) {
+#define GR_CASE(I)                                                                                                                      \
+    if (max_group <= (int64_t)GR_THREADS * (I)) {                                                                                       \
+        const size_t smem = group_rows_smem(I);                                                                                         \
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(group_rows_kernel<I, MODE, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+        PMRD_LAUNCH_NAMED(ctx, "group_rows_kernel", (group_rows_kernel<I, MODE, ROWS>), (int)n_ids, GR_THREADS, smem, keys, payload,     \
+                          grp_start, grp_cnt, n_rounds, P, tmp, fam_cnt, grp_row, G, n_fam_total);                                        \
+        return PMRD_OK;                                                                                                                 \
     }
     GR_CASE(1) GR_CASE(2) GR_CASE(4) GR_CASE(6) GR_CASE(8) GR_CASE(12) GR_CASE(16)
 #undef GR_CASE
     return PMRD_ERR_ARG;
+}
+
+template <bool ROWS>
+static int32_t launch_group_rows_mode(pmrd_ctx* ctx, int mode, int64_t max_group, int64_t n_ids, const uint64_t* keys, const uint32_t* payload,
+                                      const uint32_t* grp_start, const uint32_t* grp_cnt, int n_rounds, const pmrd_umi_params& P, FamOut tmp,
+                                      uint32_t* fam_cnt, const uint32_t* grp_row, const pmrd_group_table& G, unsigned long long* n_fam_total) {
+    if (mode == PMRD_MODE_WEIGHTED)
+        return launch_group_rows<PMRD_MODE_WEIGHTED, ROWS>(ctx, max_group, n_ids, keys, payload, grp_start, grp_cnt, n_rounds, P, tmp, fam_cnt, grp_row, G, n_fam_total);
+    if (mode == PMRD_MODE_MAJORITY)
+        return launch_group_rows<PMRD_MODE_MAJORITY, ROWS>(ctx, max_group, n_ids, keys, payload, grp_start, grp_cnt, n_rounds, P, tmp, fam_cnt, grp_row, G, n_fam_total);
+    return launch_group_rows<PMRD_MODE_COUNT, ROWS>(ctx, max_group, n_ids, keys, payload, grp_start, grp_cnt, n_rounds, P, tmp, fam_cnt, grp_row, G, n_fam_total);
 }
 
 // ---------------------------------------------------------------- driver ----------------
@@ -1321,8 +1381,9 @@ int32_t k5_collapse_exact_nosync(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pa
 static int32_t k5_collapse_groups_fast(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp, uint32_t* d_payload_tmp,
                                        int64_t n_reads, const pmrd_umi_params& P, const pmrd_family_table* d_fam, int64_t fcap,
                                        const pmrd_group_table* d_grp, int64_t gcap, uint32_t* d_grp_start, uint32_t* d_counts,
-                                       bool* done, int64_t* nf_out, int64_t* ng_out) {
+                                       bool* done, bool* in_tmp, int64_t* nf_out, int64_t* ng_out) {
     *done = false;
+    *in_tmp = false;
     static_assert(GR_MAX_GROUP == GR_THREADS * 16, "the largest group_rows_kernel instance holds GR_MAX_GROUP reads");
     const char* env = getenv("PMRD_GROUP_FAST");
     if (env && atoi(env) == 0) return PMRD_OK;
@@ -1330,32 +1391,57 @@ static int32_t k5_collapse_groups_fast(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t
     PMRD_TRY(radix_varying_bits(ctx, d_keys, n_reads, &varying, &all_or));
     const int64_t n_ids = (int64_t)(all_or >> 32) + 1;
     if (n_ids > GR_MAX_IDS || n_ids > n_reads + 1024) return PMRD_OK;
-    DevBuf cnt, start, mx, fcnt;
+    // stable partition by group (LSD radix over the group bits only: reads keep their input order inside a group)
+    int in_b = 0;
+    const char* e9 = getenv("PMRD_PARTITION_BITS");            // 8: 8-bit digits only
+    PMRD_TRY(radix_sort_pairs(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, varying & 0xffffffff00000000ull, &in_b, nullptr,
+                              e9 && atoi(e9) == 8 ? 8 : 9));
+    *in_tmp = in_b != 0;                 // (whatever happens next, this is where the reads are now)
+    const uint64_t* sk = in_b ? d_keys_tmp : d_keys;
+    const uint32_t* sp = in_b ? d_payload_tmp : d_payload;
+    DevBuf cnt, start, mx, fcnt, nonempty, grow;
     PMRD_CUDA(ctx, cnt.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
     PMRD_CUDA(ctx, start.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
+    PMRD_CUDA(ctx, nonempty.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
+    PMRD_CUDA(ctx, grow.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
     PMRD_CUDA(ctx, mx.alloc(ctx->stream, 8));
     PMRD_CUDA(ctx, cudaMemsetAsync(cnt.p, 0, (size_t)(n_ids + 1) * 4, ctx->stream));
+    PMRD_CUDA(ctx, cudaMemsetAsync(start.p, 0, (size_t)(n_ids + 1) * 4, ctx->stream));
     PMRD_CUDA(ctx, cudaMemsetAsync(mx.p, 0, 8, ctx->stream));
     int grid = (int)((n_reads + 255) / 256);
     if (grid > ctx->sm_count * 16) grid = ctx->sm_count * 16;
-    PMRD_LAUNCH(ctx, grp_count_kernel, grid, 256, 0, (const uint64_t*)d_keys, n_reads, cnt.as<uint32_t>());
+    PMRD_LAUNCH(ctx, grp_bounds_kernel, grid, 256, 0, sk, n_reads, start.as<uint32_t>(), cnt.as<uint32_t>());
     int g2 = (int)((n_ids + 255) / 256);
     if (g2 > ctx->sm_count * 8) g2 = ctx->sm_count * 8;
-    PMRD_LAUNCH(ctx, grp_max_kernel, g2, 256, 0, (const uint32_t*)cnt.as<uint32_t>(), n_ids, mx.as<uint32_t>());
+    PMRD_LAUNCH(ctx, grp_max_kernel, g2, 256, 0, (const uint32_t*)start.as<uint32_t>(), cnt.as<uint32_t>(), n_ids, nonempty.as<uint32_t>(), mx.as<uint32_t>());
     uint32_t h_mx[2] = {0, 0};
     PMRD_CUDA(ctx, cudaMemcpyAsync(h_mx, mx.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // a group beyond one block's capacity: the caller goes on with the full-key sort, FROM the partitioned arrays (a stable
+    // sort of them gives what it gives of the original order: the partition kept the input order inside every group)
     if (h_mx[0] > GR_MAX_GROUP) return PMRD_OK;
     *done = true;
-    // group starts (over the id space) and the stable partition by group
-    PMRD_TRY((exclusive_scan<uint32_t, uint32_t>(ctx, cnt.as<uint32_t>(), start.as<uint32_t>(), n_ids, (uint32_t*)nullptr)));
-    int in_b = 0;
-    PMRD_TRY(radix_sort_pairs(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, varying & 0xffffffff00000000ull, &in_b));
-    const uint64_t* sk = in_b ? d_keys_tmp : d_keys;
-    const uint32_t* sp = in_b ? d_payload_tmp : d_payload;
     int ubits = 0;
     while (ubits < 32 && (varying & 0xffffffffull) >> ubits) ++ubits;
     const int n_rounds = (ubits + 7) / 8;
+    const bool rows = d_fam && d_fam->key;
+    if (!rows) {
+        // group table only: every block reduces its group's row; row of an id = number of non-empty ids before it
+        PMRD_ARG(ctx, d_grp != nullptr, "neither a family table nor a group table was asked for");
+        *ng_out = (int64_t)h_mx[1];
+        if (*ng_out > gcap) { *nf_out = 0; return PMRD_OK; }             // the caller reports the capacity error
+        PMRD_TRY((exclusive_scan<uint32_t, uint32_t>(ctx, nonempty.as<uint32_t>(), grow.as<uint32_t>(), n_ids, (uint32_t*)nullptr)));
+        DevBuf tot;
+        PMRD_CUDA(ctx, tot.alloc(ctx->stream, 8));
+        PMRD_CUDA(ctx, cudaMemsetAsync(tot.p, 0, 8, ctx->stream));
+        PMRD_TRY(launch_group_rows_mode<false>(ctx, P.mode, h_mx[0], n_ids, sk, sp, start.as<uint32_t>(), cnt.as<uint32_t>(), n_rounds, P, FamOut{},
+                                               nullptr, grow.as<uint32_t>(), *d_grp, tot.as<unsigned long long>()));
+        unsigned long long h_tot = 0;
+        PMRD_CUDA(ctx, cudaMemcpyAsync(&h_tot, tot.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PMRD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *nf_out = (int64_t)h_tot;
+        return PMRD_OK;
+    }
     DevBuf tk, ts, ta, tc, tq, tn, tf;
     const size_t n = (size_t)n_reads;
     PMRD_CUDA(ctx, tk.alloc(ctx->stream, n * 8)); PMRD_CUDA(ctx, ts.alloc(ctx->stream, n * 4)); PMRD_CUDA(ctx, ta.alloc(ctx->stream, n * 4));
@@ -1363,12 +1449,8 @@ static int32_t k5_collapse_groups_fast(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t
     PMRD_CUDA(ctx, tf.alloc(ctx->stream, n * 4));
     PMRD_CUDA(ctx, fcnt.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
     FamOut tmp{tk.as<uint64_t>(), ts.as<uint32_t>(), ta.as<uint32_t>(), tc.as<uint32_t>(), tq.as<uint32_t>(), tn.as<uint32_t>(), tf.as<uint32_t>()};
-    if (P.mode == PMRD_MODE_WEIGHTED)
-        PMRD_TRY(launch_group_rows<PMRD_MODE_WEIGHTED>(ctx, h_mx[0], n_ids, sk, sp, start.as<uint32_t>(), cnt.as<uint32_t>(), n_rounds, P, tmp, fcnt.as<uint32_t>()));
-    else if (P.mode == PMRD_MODE_MAJORITY)
-        PMRD_TRY(launch_group_rows<PMRD_MODE_MAJORITY>(ctx, h_mx[0], n_ids, sk, sp, start.as<uint32_t>(), cnt.as<uint32_t>(), n_rounds, P, tmp, fcnt.as<uint32_t>()));
-    else
-        PMRD_TRY(launch_group_rows<PMRD_MODE_COUNT>(ctx, h_mx[0], n_ids, sk, sp, start.as<uint32_t>(), cnt.as<uint32_t>(), n_rounds, P, tmp, fcnt.as<uint32_t>()));
+    PMRD_TRY(launch_group_rows_mode<true>(ctx, P.mode, h_mx[0], n_ids, sk, sp, start.as<uint32_t>(), cnt.as<uint32_t>(), n_rounds, P, tmp,
+                                          fcnt.as<uint32_t>(), nullptr, pmrd_group_table{}, nullptr));
     // family counts -> row offsets; the total is the family count of the call
     DevBuf fbase;
     PMRD_CUDA(ctx, fbase.alloc(ctx->stream, (size_t)(n_ids + 1) * 4));
@@ -1403,6 +1485,7 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
     if (n_reads <= 0) return PMRD_OK;
     PMRD_ARG(ctx, n_reads < (1ll << 31), "n_reads must be < 2^31 per call (chunk the input)");
     const bool want_groups = d_grp && n_groups;
+    if (!(d_fam && d_fam->key)) capacity_f = n_reads;            // no family table asked for: no capacity to respect
     const int64_t fcap = capacity_f < n_reads ? capacity_f : n_reads;
     const int64_t gcap = want_groups ? (capacity_g < n_reads ? capacity_g : n_reads) : 0;
 
@@ -1413,10 +1496,28 @@ int32_t k5_collapse(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64
     PMRD_CUDA(ctx, cudaMemsetAsync(counts.p, 0, 8, ctx->stream));
     int64_t nf = 0, ng = 0;
 
-    bool fast_done = false;
+    bool fast_done = false, in_tmp = false;
+    const bool want_rows = d_fam && d_fam->key;
     if (P.cluster == PMRD_CLUSTER_EXACT)
         PMRD_TRY(k5_collapse_groups_fast(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, P, d_fam, fcap, want_groups ? d_grp : nullptr,
-                                         gcap, grp_start.as<uint32_t>(), counts.as<uint32_t>(), &fast_done, &nf, &ng));
+                                         gcap, grp_start.as<uint32_t>(), counts.as<uint32_t>(), &fast_done, &in_tmp, &nf, &ng));
+    if (in_tmp) {      // the partition left the reads in the tmp buffers: they are the input of whatever follows
+        uint64_t* tk = d_keys; d_keys = d_keys_tmp; d_keys_tmp = tk;
+        uint32_t* tp = d_payload; d_payload = d_payload_tmp; d_payload_tmp = tp;
+    }
+    // the other paths build the group table FROM the family table: a caller that did not ask for the family rows gets
+    // them computed into scratch all the same
+    DevBuf xk, xs, xa, xc, xq, xn, xf;
+    pmrd_family_table scratch_fam;
+    if (!fast_done && !want_rows) {
+        const size_t fn = (size_t)fcap;
+        PMRD_CUDA(ctx, xk.alloc(ctx->stream, fn * 8)); PMRD_CUDA(ctx, xs.alloc(ctx->stream, fn * 4)); PMRD_CUDA(ctx, xa.alloc(ctx->stream, fn * 4));
+        PMRD_CUDA(ctx, xc.alloc(ctx->stream, fn * 4)); PMRD_CUDA(ctx, xq.alloc(ctx->stream, fn * 4)); PMRD_CUDA(ctx, xn.alloc(ctx->stream, fn * 4));
+        PMRD_CUDA(ctx, xf.alloc(ctx->stream, fn * 4));
+        scratch_fam = pmrd_family_table{xk.as<uint64_t>(), xs.as<uint32_t>(), xa.as<uint32_t>(), xc.as<uint32_t>(), xq.as<uint32_t>(),
+                                        xn.as<uint32_t>(), xf.as<uint32_t>()};
+        d_fam = &scratch_fam;
+    }
     if (fast_done) {
         // (family table and group table are in place; the counts were read back)
     } else if (P.cluster == PMRD_CLUSTER_EXACT) {

@@ -69,11 +69,29 @@ int32_t radix_varying_bits(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, uin
     return PMRD_OK;
 }
 
-RadixPlan radix_make_plan(uint64_t varying) {
+RadixPlan radix_make_plan(uint64_t varying, int max_digit_bits) {
     RadixPlan p;
     p.n_passes = 0;
-    // greedy: an (up to) 8-bit window starting at the lowest varying bit not yet covered;
-    // at most 8 windows cover 64 bits.
+    // greedy: an (up to) 8-bit window starting at the lowest varying bit not yet covered; at most 8 windows cover 64 bits.
+    // max_digit_bits = 9: if 9-bit windows save a pass, the varying span is cut into equal windows of at most 9 bits.
+    int lo = 0, hi = 63, nbits = 0;
+    while (lo < 64 && !((varying >> lo) & 1ull)) ++lo;
+    while (hi >= 0 && !((varying >> hi) & 1ull)) --hi;
+    for (int b = 0; b < 64; ++b) nbits += (int)((varying >> b) & 1ull);
+    if (max_digit_bits >= 9 && lo <= hi && nbits == hi - lo + 1) {            // one contiguous run of varying bits
+        const int span = hi - lo + 1, p8 = (span + 7) / 8, p9 = (span + 8) / 9;
+        if (p9 < p8) {
+            int b = lo;
+            for (int k = 0; k < p9; ++k) {
+                const int w = (span - (b - lo) + (p9 - k) - 1) / (p9 - k);    // balanced: 17 bits -> 9 + 8
+                p.shift[p.n_passes] = b;
+                p.bits[p.n_passes] = w;
+                ++p.n_passes;
+                b += w;
+            }
+            return p;
+        }
+    }
     int b = 0;
     while (b < 64) {
         if (!((varying >> b) & 1ull)) { ++b; continue; }
@@ -89,12 +107,15 @@ RadixPlan radix_make_plan(uint64_t varying) {
 }
 
 // ---------------------------------------------------------------- upsweep ---------------
-// hist[tile][256] (tile-major: one coalesced 1 KB row per tile)
+// hist[tile][BINS] (tile-major: one coalesced row per tile).  BINS = 256 (8-bit digits) or 512 (9-bit digits: a 17-bit
+// group index is partitioned in two passes instead of three)
+template <int BINS>
 __global__ void __launch_bounds__(RS_THREADS)
 rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __restrict__ hist, int shift, uint32_t mask) {
-    __shared__ __align__(16) uint32_t s_hist[RS_WARPS][RS_MAX_BINS];
+    extern __shared__ __align__(16) uint32_t s_hist_raw[];
+    uint32_t (*s_hist)[BINS] = reinterpret_cast<uint32_t (*)[BINS]>(s_hist_raw);          // [RS_WARPS][BINS]
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    rs_zero_smem<RS_THREADS, RS_WARPS * RS_MAX_BINS>(&s_hist[0][0]);
+    rs_zero_smem<RS_THREADS, RS_WARPS * BINS>(&s_hist[0][0]);
     __syncthreads();
     const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
     const int64_t rem = n - tile_base;
@@ -114,16 +135,16 @@ rs_upsweep_kernel(const uint64_t* __restrict__ keys, int64_t n, uint32_t* __rest
             d0 = (uint32_t)(keys[wbase + i * 64 + lane * 2] >> shift) & mask;
         }
         // one shared-memory atomic per key on a warp-private histogram: digits of a scrambled
-        // input are spread over the 256 bins, so same-address conflicts inside a warp are rare
+        // input are spread over the bins, so same-address conflicts inside a warp are rare
         if (d0 != 0xffffffffu) atomicAdd(&s_hist[warp][d0], 1u);
         if (d1 != 0xffffffffu) atomicAdd(&s_hist[warp][d1], 1u);
     }
     __syncthreads();
-    uint32_t c = 0;
-    if (threadIdx.x < RS_MAX_BINS) {
+    if (threadIdx.x < BINS) {
+        uint32_t c = 0;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) c += s_hist[w][threadIdx.x];
-        hist[(int64_t)blockIdx.x * RS_MAX_BINS + threadIdx.x] = c;
+        hist[(int64_t)blockIdx.x * BINS + threadIdx.x] = c;
     }
 }
 
@@ -157,73 +178,79 @@ rs_upsweep_tiles_kernel(const uint64_t* __restrict__ keys, uint32_t* __restrict_
 
 // ---------------------------------------------------------------- column scan -----------
 // H[tile][d]  ->  exclusive over (d major, tile minor) order, computed column-wise.
-__global__ void __launch_bounds__(256)
-rs_colsum_kernel(const uint32_t* __restrict__ hist, int n_tiles, int chunk, uint32_t* __restrict__ colsum /*[n_chunks][256]*/) {
+// (the three column kernels run with one thread per bin: blockDim.x = 256 or 512)
+__global__ void __launch_bounds__(512)
+rs_colsum_kernel(const uint32_t* __restrict__ hist, int n_tiles, int chunk, uint32_t* __restrict__ colsum /*[n_chunks][bins]*/) {
+    const int bins = blockDim.x;
     const int t0 = blockIdx.x * chunk;
     const int t1 = min(t0 + chunk, n_tiles);
     uint32_t acc = 0;
 #pragma unroll 8
-    for (int t = t0; t < t1; ++t) acc += hist[(int64_t)t * 256 + threadIdx.x];
-    colsum[(int64_t)blockIdx.x * 256 + threadIdx.x] = acc;
+    for (int t = t0; t < t1; ++t) acc += hist[(int64_t)t * bins + threadIdx.x];
+    colsum[(int64_t)blockIdx.x * bins + threadIdx.x] = acc;
 }
 
-__global__ void __launch_bounds__(256) rs_colbase_kernel(uint32_t* __restrict__ colsum, int n_chunks) {
+__global__ void __launch_bounds__(512) rs_colbase_kernel(uint32_t* __restrict__ colsum, int n_chunks) {
     __shared__ uint32_t sw[33];
+    const int bins = blockDim.x;
     uint32_t run = 0;
 #pragma unroll 8
     for (int c = 0; c < n_chunks; ++c) {
-        uint32_t v = colsum[(int64_t)c * 256 + threadIdx.x];
-        colsum[(int64_t)c * 256 + threadIdx.x] = run;
+        uint32_t v = colsum[(int64_t)c * bins + threadIdx.x];
+        colsum[(int64_t)c * bins + threadIdx.x] = run;
         run += v;
     }
     uint32_t tot;
     uint32_t base = block_exclusive_scan<uint32_t>(run, sw, tot);
-    for (int c = 0; c < n_chunks; ++c) colsum[(int64_t)c * 256 + threadIdx.x] += base;
+    for (int c = 0; c < n_chunks; ++c) colsum[(int64_t)c * bins + threadIdx.x] += base;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 rs_colapply_kernel(uint32_t* __restrict__ hist, int n_tiles, int chunk, const uint32_t* __restrict__ colsum) {
+    const int bins = blockDim.x;
     const int t0 = blockIdx.x * chunk;
     const int t1 = min(t0 + chunk, n_tiles);
-    uint32_t run = colsum[(int64_t)blockIdx.x * 256 + threadIdx.x];
+    uint32_t run = colsum[(int64_t)blockIdx.x * bins + threadIdx.x];
     int t = t0;
     for (; t + 8 <= t1; t += 8) {
         uint32_t v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = hist[(int64_t)(t + j) * 256 + threadIdx.x];
+        for (int j = 0; j < 8; ++j) v[j] = hist[(int64_t)(t + j) * bins + threadIdx.x];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            hist[(int64_t)(t + j) * 256 + threadIdx.x] = run;
+            hist[(int64_t)(t + j) * bins + threadIdx.x] = run;
             run += v[j];
         }
     }
     for (; t < t1; ++t) {
-        uint32_t v = hist[(int64_t)t * 256 + threadIdx.x];
-        hist[(int64_t)t * 256 + threadIdx.x] = run;
+        uint32_t v = hist[(int64_t)t * bins + threadIdx.x];
+        hist[(int64_t)t * bins + threadIdx.x] = run;
         run += v;
     }
 }
 
 // ---------------------------------------------------------------- downsweep -------------
-struct RsSmem {
+template <int BINS>
+struct RsSmemT {
     uint64_t keys[RS_TILE];
     uint32_t vals[RS_TILE];
-    uint32_t warp_cnt[RS_WARPS][RS_MAX_BINS];
-    uint32_t bin_base[RS_MAX_BINS];
-    uint32_t glob_delta[RS_MAX_BINS];
+    uint32_t warp_cnt[RS_WARPS][BINS];
+    uint32_t bin_base[BINS];
+    uint32_t glob_delta[BINS];
     uint32_t sw[33];
 };
+typedef RsSmemT<RS_MAX_BINS> RsSmem;
 
-template <bool HAS_VALS>
-__global__ void __launch_bounds__(RS_THREADS, 3)
+template <bool HAS_VALS, int BINS = RS_MAX_BINS>
+__global__ void __launch_bounds__(RS_THREADS, BINS == 256 ? 3 : 2)
 rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                     uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out,
                     const uint32_t* __restrict__ hist_scanned, int64_t n, int shift, uint32_t mask) {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
-    RsSmem& S = *reinterpret_cast<RsSmem*>(rs_smem_raw);
+    RsSmemT<BINS>& S = *reinterpret_cast<RsSmemT<BINS>*>(rs_smem_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t lt = lanemask_lt();
-    rs_zero_smem<RS_THREADS, RS_WARPS * RS_MAX_BINS>(&S.warp_cnt[0][0]);
+    rs_zero_smem<RS_THREADS, RS_WARPS * BINS>(&S.warp_cnt[0][0]);
     const int64_t tile_base = (int64_t)blockIdx.x * RS_TILE;
     const int64_t rem = n - tile_base;
     const int tile_n = rem < RS_TILE ? (int)rem : RS_TILE;
@@ -247,7 +274,7 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
         const uint32_t d = valid ? ((uint32_t)(key[i] >> shift) & mask) : 0xffffffffu;
         // peers = lanes holding the same digit (lanes past the end of the input form their own group)
         const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
-        const uint32_t m = rs_peer_mask(d, valid ? vmask : ~vmask);
+        const uint32_t m = rs_peer_mask<BINS == 256 ? 8 : 9>(d, valid ? vmask : ~vmask);
         const uint32_t before = __popc(m & lt);
         // the lowest lane of each digit group bumps the warp's counter once for the whole group and
         // hands the old value to its peers by shuffle: one shared atomic + one shuffle per item,
@@ -262,9 +289,9 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
 
     // per-bin: exclusive prefix over warps, then block scan over bins
     {
-        const uint32_t b = threadIdx.x;  // threads 0..255 own one bin each
+        const uint32_t b = threadIdx.x;  // threads 0..BINS-1 own one bin each (BINS <= RS_THREADS)
         uint32_t run = 0;
-        if (b < RS_MAX_BINS) {
+        if (b < BINS) {
 #pragma unroll
             for (int w = 0; w < RS_WARPS; ++w) {
                 uint32_t c = S.warp_cnt[w][b];
@@ -274,9 +301,9 @@ rs_downsweep_kernel(const uint64_t* __restrict__ keys_in, const uint32_t* __rest
         }
         uint32_t tot;
         uint32_t base = block_exclusive_scan<uint32_t>(run, S.sw, tot);
-        if (b < RS_MAX_BINS) {
+        if (b < BINS) {
             S.bin_base[b] = base;
-            S.glob_delta[b] = hist_scanned[(int64_t)blockIdx.x * RS_MAX_BINS + b] - base;
+            S.glob_delta[b] = hist_scanned[(int64_t)blockIdx.x * BINS + b] - base;
         }
     }
     __syncthreads();
@@ -504,6 +531,9 @@ static int32_t rs_set_attrs(pmrd_ctx* ctx) {
     {
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute((rs_downsweep_kernel<true, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmemT<512>)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute((rs_downsweep_kernel<false, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmemT<512>)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_upsweep_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RS_WARPS * 512 * sizeof(uint32_t))));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<RS_WARPS>)));
         PMRD_CUDA(ctx, cudaFuncSetAttribute(rs_downsweep_staged_kernel<256, 16, RS_SWIDE_MIN_BLOCKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsStage<8>)));
     }
@@ -546,7 +576,7 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         if (!(p == 0 && d_hist0)) {
             // whole tiles, digit in the low key word: the loads-first counting kernel (5.2 vs 6.6 ms per step)
             if (shift + 8 <= 32) PMRD_LAUNCH_NAMED(ctx, "rs_upsweep_kernel", (rs_upsweep_tiles_kernel<256>), n_tiles, 256, 0, kin, hist, shift, mask);
-            else PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist, shift, mask);
+            else PMRD_LAUNCH_NAMED(ctx, "rs_upsweep_kernel", rs_upsweep_kernel<256>, n_tiles, RS_THREADS, RS_WARPS * 256 * sizeof(uint32_t), kin, n, hist, shift, mask);
         }
         if ((int64_t)n_tiles >= 8 * n_cells) PMRD_LAUNCH_NAMED(ctx, "rs_cellscan_kernel", rs_cellscan_kernel<4>, (int)n_cells, 1024, 0, hist, d_cell_tile_start, (int)n_cells);
         else PMRD_LAUNCH_NAMED(ctx, "rs_cellscan_kernel", rs_cellscan_kernel<1>, (int)n_cells, 256, 0, hist, d_cell_tile_start, (int)n_cells);
@@ -578,15 +608,15 @@ size_t radix_scratch_bytes(int64_t n) {
     int64_t chunk = 1;
     while (chunk * chunk < n_tiles) ++chunk;
     const int64_t n_chunks = chunk > 0 ? (n_tiles + chunk - 1) / chunk : 0;
-    return (size_t)(n_tiles + n_chunks + 2) * RS_MAX_BINS * sizeof(uint32_t);
+    return (size_t)(n_tiles + n_chunks + 2) * 512 * sizeof(uint32_t);      // (sized for 9-bit digits)
 }
 
 int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
-                         int64_t n, uint64_t varying, int* in_b, uint32_t* d_scratch) {
+                         int64_t n, uint64_t varying, int* in_b, uint32_t* d_scratch, int max_digit_bits) {
     *in_b = 0;
     if (n <= 1) return PMRD_OK;
     PMRD_ARG(ctx, n < (1ll << 32) - RS_TILE, "radix_sort_pairs: n must be < 2^32 (chunk the input)");
-    RadixPlan plan = radix_make_plan(varying);
+    RadixPlan plan = radix_make_plan(varying, max_digit_bits);
     if (plan.n_passes == 0) return PMRD_OK;
 
     const int n_tiles = (int)((n + RS_TILE - 1) / RS_TILE);
@@ -597,11 +627,11 @@ int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint
     // caller-owned scratch (radix_scratch_bytes(n)): nothing is allocated here (plans: allocation-free steps)
     DevBuf hist_own, colsum_own;
     if (!d_scratch) {
-        PMRD_CUDA(ctx, hist_own.alloc(ctx->stream, (size_t)n_tiles * RS_MAX_BINS * sizeof(uint32_t)));
-        PMRD_CUDA(ctx, colsum_own.alloc(ctx->stream, (size_t)n_chunks * 256 * sizeof(uint32_t)));
+        PMRD_CUDA(ctx, hist_own.alloc(ctx->stream, (size_t)n_tiles * 512 * sizeof(uint32_t)));
+        PMRD_CUDA(ctx, colsum_own.alloc(ctx->stream, (size_t)n_chunks * 512 * sizeof(uint32_t)));
     }
     uint32_t* const hist = d_scratch ? d_scratch : hist_own.as<uint32_t>();
-    uint32_t* const colsum = d_scratch ? d_scratch + (size_t)n_tiles * RS_MAX_BINS : colsum_own.as<uint32_t>();
+    uint32_t* const colsum = d_scratch ? d_scratch + (size_t)n_tiles * 512 : colsum_own.as<uint32_t>();
 
     PMRD_TRY(rs_set_attrs(ctx));
 
@@ -612,13 +642,20 @@ int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint
     for (int p = 0; p < plan.n_passes; ++p) {
         const int shift = plan.shift[p];
         const uint32_t mask = (1u << plan.bits[p]) - 1u;
-        PMRD_LAUNCH(ctx, rs_upsweep_kernel, n_tiles, RS_THREADS, 0, kin, n, hist, shift, mask);
-        PMRD_LAUNCH(ctx, rs_colsum_kernel, n_chunks, 256, 0, hist, n_tiles, chunk, colsum);
-        PMRD_LAUNCH(ctx, rs_colbase_kernel, 1, 256, 0, colsum, n_chunks);
-        PMRD_LAUNCH(ctx, rs_colapply_kernel, n_chunks, 256, 0, hist, n_tiles, chunk, colsum);
-        if (vals_a) {
+        const bool wide = plan.bits[p] > 8;                      // a 9-bit digit: 512 bins
+        const int bins = wide ? 512 : 256;
+        if (wide) PMRD_LAUNCH_NAMED(ctx, "rs_upsweep_kernel", rs_upsweep_kernel<512>, n_tiles, RS_THREADS, RS_WARPS * 512 * sizeof(uint32_t), kin, n, hist, shift, mask);
+        else PMRD_LAUNCH_NAMED(ctx, "rs_upsweep_kernel", rs_upsweep_kernel<256>, n_tiles, RS_THREADS, RS_WARPS * 256 * sizeof(uint32_t), kin, n, hist, shift, mask);
+        PMRD_LAUNCH(ctx, rs_colsum_kernel, n_chunks, bins, 0, hist, n_tiles, chunk, colsum);
+        PMRD_LAUNCH(ctx, rs_colbase_kernel, 1, bins, 0, colsum, n_chunks);
+        PMRD_LAUNCH(ctx, rs_colapply_kernel, n_chunks, bins, 0, hist, n_tiles, chunk, colsum);
+        if (vals_a && wide) {
+            PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_kernel<true>", (rs_downsweep_kernel<true, 512>), n_tiles, RS_THREADS, sizeof(RsSmemT<512>), kin, vin, kout, vout, hist, n, shift, mask);
+        } else if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout,
                         hist, n, shift, mask);
+        } else if (wide) {
+            PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_kernel<false>", (rs_downsweep_kernel<false, 512>), n_tiles, RS_THREADS, sizeof(RsSmemT<512>), kin, vin, kout, vout, hist, n, shift, mask);
         } else {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<false>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout,
                         hist, n, shift, mask);

@@ -25,9 +25,10 @@
 // whole digit saturates the ADU pipe (ncu: 88 %).  Measured on B200, direct downsweep, 2.13e9 records x 3
 // passes: C++ ballots + MATCH on the top 3 bits 34.5 ms; this form 28.3 ms (MATCH on the top 1-2 bits: same;
 // 3 bits 29.1; 4 bits 31.1).
+template <int BITS = 8>
 __device__ __forceinline__ uint32_t rs_peer_mask(uint32_t d, uint32_t m) {
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
+    for (int b = 0; b < BITS; ++b) {
         asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t, bal, x;\n\t"
                      "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
                      "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
@@ -48,13 +49,14 @@ struct RadixPlan {
 
 // h_or (optional): the OR of all keys (an upper bound of every key field)
 int32_t radix_varying_bits(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, uint64_t* h_varying, uint64_t* h_or = nullptr);
-RadixPlan radix_make_plan(uint64_t varying);
+RadixPlan radix_make_plan(uint64_t varying, int max_digit_bits = 8);
 // Sorts; on return *in_b tells whether the result lives in (keys_b, vals_b).  vals may be
 // NULL (keys only).  `varying` = mask of key bits that differ across the input (pass ~0ull
 // to sort on every bit).
 // d_scratch (optional): radix_scratch_bytes(n) bytes owned by the caller -- the sort then allocates nothing.
+// max_digit_bits = 9: digit windows of up to 9 bits (512 bins; scratch is sized for them either way)
 int32_t radix_sort_pairs(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
-                         int64_t n, uint64_t varying, int* in_b, uint32_t* d_scratch = nullptr);
+                         int64_t n, uint64_t varying, int* in_b, uint32_t* d_scratch = nullptr, int max_digit_bits = 8);
 size_t radix_scratch_bytes(int64_t n);
 int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                                    int64_t n, const int64_t* d_cell_tile_start, int64_t n_cells, int key_bits, int* in_b,

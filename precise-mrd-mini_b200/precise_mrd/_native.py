@@ -304,10 +304,10 @@ class Context:
         return fam, grp
 
     def collapse_reads_dev(self, d_keys: int, d_payload: int, d_keys_tmp: int, d_payload_tmp: int, n: int, params: UmiParams,
-                           d_fam: Dict[str, int], capacity_f: int, d_grp: Optional[Dict[str, int]] = None, capacity_g: int = 0):
+                           d_fam: Optional[Dict[str, int]], capacity_f: int, d_grp: Optional[Dict[str, int]] = None, capacity_g: int = 0):
         """``pmrd_collapse_reads_dev``: every buffer is a DEVICE pointer (an int: ``tensor.data_ptr()``); the key /
         payload buffers are clobbered.  Returns ``(n_families, n_groups)``."""
-        ft = FamilyTable(*[d_fam[nm] for nm, _ in FamilyTable._fields_])
+        ft = FamilyTable(*[(d_fam[nm] if d_fam else None) for nm, _ in FamilyTable._fields_])     # d_fam = None: group table only
         gt = GroupTable(*[d_grp[nm] for nm, _ in GroupTable._fields_]) if d_grp else None
         nf, ng = C.c_int64(0), C.c_int64(0)
         self._check(self.lib.pmrd_collapse_reads_dev(

@@ -336,6 +336,23 @@ def test_collapse_external_reads_group_major_path(ctx, native, monkeypatch):
     for k in want:
         assert (fam[k] == want[k]).all(), k
     assert len(grp["group"]) == 600 and (grp["family_count"] == np.bincount((want["key"][(want["flags"] & 2) != 0] >> np.uint64(32)).astype(np.int64), minlength=600)).all()
+    # group table only (no family row is written): the same table, the family count still reported
+    info, grp_only = ctx.collapse_reads(keys, pl, P, want_families=False)
+    assert info["n_families"] == len(want["key"])
+    for k in grp:
+        assert (grp_only[k] == grp[k]).all(), k
+    og = cport.collapse_groups(keys, pl, 600, 3, 1000, 20, 0.6)
+    assert (grp_only["family_count"] == og["family_count"]).all() and (grp_only["consensus_count"] == og["consensus_count"]).all()
+    # ... and when the group-major path does not apply (a group of more than 4096 reads) the fallback gives it too
+    kbig = keys.copy()
+    kbig[:6000] = (np.uint64(5) << np.uint64(32)) | (kbig[:6000] & np.uint64(0xFFFFFFFF))
+    f_all, g_all = ctx.collapse_reads(kbig, pl, P)
+    info2, g_only2 = ctx.collapse_reads(kbig, pl, P, want_families=False)
+    wf, wg = port.collapse_exact(kbig, pl, 0, 3, 1000, 20, 0.6)
+    _assert_tables_equal(f_all, g_all, wf, wg)
+    assert info2["n_families"] == len(wf["key"])
+    for k in g_all:
+        assert (g_only2[k] == g_all[k]).all(), k
     # 16-mer UMIs (32 bits, four ranked rounds), a UMI of all T (= the filler word), groups of one read, empty ids
     keys2, pl2 = _panel_reads(rng, 40_000, 3000, 4, umi_bits=32)
     keys2[:50] |= np.uint64(0xFFFFFFFF)
@@ -345,6 +362,16 @@ def test_collapse_external_reads_group_major_path(ctx, native, monkeypatch):
         fam, grp = ctx.collapse_reads(keys2, pl2, P2)
         wfam, wgrp = port.collapse_exact(keys2, pl2, mode, 2, 9, 20, 0.4)
         _assert_tables_equal(fam, grp, wfam, wgrp)
+    # 1e5 loci (17 group bits): the partition takes two 9-bit digit passes (512 bins) instead of three 8-bit ones
+    keys4, pl4 = _panel_reads(rng, 600_000, 100_000, 3)
+    fa, ga = ctx.collapse_reads(keys4, pl4, P)
+    monkeypatch.setenv("PMRD_PARTITION_BITS", "8")
+    fb, gb = ctx.collapse_reads(keys4, pl4, P)
+    monkeypatch.delenv("PMRD_PARTITION_BITS")
+    _assert_tables_equal(fa, ga, fb, gb)
+    og4 = cport.collapse_groups(keys4, pl4, 100_000, 3, 1000, 20, 0.6)
+    assert (ga["family_count"] == og4["family_count"][ga["group"]]).all() and (ga["consensus_count"] == og4["consensus_count"][ga["group"]]).all()
+    assert len(fa["key"]) == og4["total_families"]
     # 3e6 reads over 20 000 loci: both paths, every mode
     keys3, pl3 = _panel_reads(rng, 3_000_000, 20_000, 40)
     for mode in (0, 1, 2):
