@@ -560,13 +560,15 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
     uint32_t* const hist = d_hist0 ? d_hist0 : hist_own.as<uint32_t>();
     uint64_t* kin = keys_a; uint32_t* vin = vals_a; uint64_t* kout = keys_b; uint32_t* vout = vals_b;
     const int n_passes = (key_bits + 7) / 8;
-    static int direct = -1, staged = 1;
-    if (direct < 0) {
-        const char* e = getenv("PMRD_RS_DIRECT");
-        direct = e ? atoi(e) : 1;
-        e = getenv("PMRD_RS_STAGED");
-        if (e) staged = atoi(e);
-    }
+    // development knobs, read on every call (no static state: contexts of different threads may sort at once)
+    const char* e_knob = getenv("PMRD_RS_DIRECT");
+    const int direct = e_knob ? atoi(e_knob) : 1;
+    e_knob = getenv("PMRD_RS_STAGED");
+    const int staged = e_knob ? atoi(e_knob) : 1;
+    e_knob = getenv("PMRD_RS_SWIDE");
+    const int swide = e_knob ? atoi(e_knob) : 1;      // 1: 256 threads x 16 records, 4 blocks / SM (8.1 vs 9.2 ms per step)
+    e_knob = getenv("PMRD_RS_WIDE");
+    const int wide = e_knob ? atoi(e_knob) : 2;       // 2: 256 threads x 16 records, 4 blocks / SM (measured best, by 3 %)
     for (int p = 0; p < n_passes; ++p) {
         const int shift = p * 8;
         const int w = key_bits - shift < 8 ? key_bits - shift : 8;
@@ -583,13 +585,9 @@ int32_t radix_sort_pairs_segmented(pmrd_ctx* ctx, uint64_t* keys_a, uint32_t* va
         if (vals_a) {
             PMRD_LAUNCH(ctx, rs_downsweep_kernel<true>, n_tiles, RS_THREADS, sizeof(RsSmem), kin, vin, kout, vout, hist, n, shift, mask);
         } else if (stage) {
-            static int swide = -1;
-            if (swide < 0) { const char* e = getenv("PMRD_RS_SWIDE"); swide = e ? atoi(e) : 1; }   // 1: 256 threads x 16 records, 4 blocks / SM (8.1 vs 9.2 ms per step)
             if (swide) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_staged_kernel", (rs_downsweep_staged_kernel<256, 16, RS_SWIDE_MIN_BLOCKS>), n_tiles, 256, sizeof(RsStage<8>), kin, kout, hist, shift, mask);
             else PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_staged_kernel", (rs_downsweep_staged_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>), n_tiles, RS_THREADS, sizeof(RsStage<RS_WARPS>), kin, kout, hist, shift, mask);
         } else if (direct) {   // packed 8-byte records, stored straight to their final place (L2 merges the sectors)
-            static int wide = -1;
-            if (wide < 0) { const char* e = getenv("PMRD_RS_WIDE"); wide = e ? atoi(e) : 2; }   // 2: 256 threads x 16 records, 4 blocks / SM (measured best, by 3 %)
             if (wide == 2) PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<256, 16, RS_WIDE_MIN_BLOCKS>), n_tiles, 256, 0, kin, kout, hist, shift, mask);
             else PMRD_LAUNCH_NAMED(ctx, "rs_downsweep_direct_kernel", (rs_downsweep_direct_kernel<RS_THREADS, RS_ITEMS, RS_DIRECT_MIN_BLOCKS>), n_tiles, RS_THREADS, 0, kin, kout, hist, shift, mask);
         } else {   // packed 8-byte records: the "key" carries its payload in the bits above key_bits

@@ -164,6 +164,48 @@ def test_bench_workloads_and_sharding_keys():
         os.environ.pop("PMRD_PANEL_LOCI", None)
 
 
+def test_bench_external_workload_and_reference_arms(tmp_path):
+    """bench.py --workload external: the NumPy read generator (both arms build the same arrays), the oracle's per-locus table
+    on them, the config dict shared by the two arms, and the two reference arms end to end (CPU only: `--impl reference`
+    never touches a GPU)."""
+    import importlib
+    import json
+    import subprocess
+    import sys as _sys
+
+    root = Path(__file__).resolve().parent.parent
+    if str(root) not in _sys.path:
+        _sys.path.insert(0, str(root))
+    bench = importlib.import_module("bench")
+    keys, pl = bench.external_reads(42, 50_000, 400)
+    k2, p2 = bench.external_reads(42, 50_000, 400)
+    assert (keys == k2).all() and (pl == p2).all() and keys.dtype == np.uint64 and pl.dtype == np.uint32
+    assert (keys >> np.uint64(32)).max() < 400 and ((keys & np.uint64(0xFFFFFFFF)) < (1 << 24)).all()
+    sizes = np.unique(keys, return_counts=True)[1]
+    assert 4.0 < sizes.mean() < 6.5                                               # ~Poisson(5) families (zero-size ones never appear)
+    q = (pl >> np.uint32(2)) & np.uint32(63)
+    assert q.min() >= 10 and q.max() <= 40 and ((pl >> np.uint32(31)) == (pl & np.uint32(1))).all()
+    from oracle import cport, port
+
+    r = cport.collapse_groups(keys, pl, 400, 3, 1000, 20, 0.6)
+    fam, grp = port.collapse_exact(keys, pl, 0, 3, 1000, 20, 0.6)
+    assert (r["family_count"] == grp["family_count"]).all() and (r["consensus_count"] == grp["consensus_count"]).all()
+    assert r["total_families"] == len(fam["key"])
+    a, b = bench.external_config(1000, 10, 2), bench.external_config(1000, 10, 2)
+    assert a == b and "EXTERNAL" in a["workload"]
+    cfgd = bench.workload_config("default", "x", np.arange(3), np.array([5, 5, 5]), 1)
+    assert cfgd == bench.workload_config("default", "x", np.arange(3), np.array([5, 5, 5]), 1) and cfgd["families_per_gpu_per_step"] == 15
+    env = dict(os.environ, PMRD_REF_READS="200000", PMRD_EXT_LOCI="2000", PMRD_REF_CELLS="8", PMRD_BENCH_REPS="2")
+    for extra in (["--workload", "external"], []):
+        out = subprocess.run([_sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"] + extra,
+                             capture_output=True, text=True, timeout=300, env=env, cwd=tmp_path)
+        assert out.returncode == 0, out.stderr[-1000:]
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["value"] > 0 and line["gpu_launches"] == 0
+        assert line["e2e"]["value"] == line["value"] and line["cpu_baseline"]["kind"] == "port"
+        assert set(line) >= {"metric", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "config", "dtype"}
+
+
 def test_world_size_does_not_import_torch():
     """A CLI process must not pay torch's import (2.5 s) to learn that it is alone."""
     import subprocess
