@@ -93,8 +93,17 @@ struct __align__(16) FusedSlot {
     uint32_t fam;      // family index inside the cell (counter word 1)
 };
 
-__device__ __forceinline__ uint32_t fused_h1(uint32_t umi, int log2) { return umi & ((1u << log2) - 1u); }
-__device__ __forceinline__ uint32_t fused_h2(uint32_t umi, int log2) { return (umi * 0x9E3779B1u) >> (32 - log2); }
+// FUSED_K hash functions into ONE pair of bitmaps ("seen", "seen twice") of 2^(filt_log2 + 1) slots: a Bloom filter.  A
+// molecule is a candidate duplicate when ALL its slots were hit twice; two molecules with the same UMI share all of them.
+// With 8+ slots per molecule and k = 4 the false-positive rate of the largest cells is ~1 % (two separate bitmaps with one
+// hash each, the first version: 3 %) for the same shared memory.
+#ifndef FUSED_K
+#define FUSED_K 4
+#endif
+__device__ __forceinline__ uint32_t fused_hash(uint32_t umi, int j, int log2) {
+    const uint32_t mul[6] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du};
+    return (umi * mul[j]) >> (32 - log2);          // (the UMI's 24 bits, spread by an odd multiplier: the top bits)
+}
 
 // MODE 0: count the candidates of every cell (plan build: sizes the candidate list; nothing else is written)
 // MODE 1: the step
@@ -109,12 +118,11 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
     constexpr int WARPS = THREADS / 32;
     extern __shared__ __align__(16) unsigned char fz_raw[];
     // layout: [4 bitmaps][allele sums 4 x THREADS doubles][weights][slots][stash][tables]
-    const uint32_t words = (1u << filt_log2) / 32u;
-    uint32_t* const s_seen1 = reinterpret_cast<uint32_t*>(fz_raw);
-    uint32_t* const s_dup1 = s_seen1 + words;
-    uint32_t* const s_seen2 = s_dup1 + words;
-    uint32_t* const s_dup2 = s_seen2 + words;
-    double* const s_sum = reinterpret_cast<double*>(s_dup2 + words);
+    const int slot_log2 = filt_log2 + 1;                              // slots of the seen / dup bitmaps
+    const uint32_t words = (1u << slot_log2) / 32u;
+    uint32_t* const s_seen = reinterpret_cast<uint32_t*>(fz_raw);
+    uint32_t* const s_dup = s_seen + words;
+    double* const s_sum = reinterpret_cast<double*>(s_dup + words);
     double* const s_wt = s_sum + 4 * THREADS;
     FusedSlot* const s_slot = reinterpret_cast<FusedSlot*>(s_wt + 64);
     uint8_t* const s_stash = reinterpret_cast<uint8_t*>(s_slot + THREADS);
@@ -132,7 +140,7 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
     const uint32_t n_fam = (uint32_t)(cells[cell + 1].fam_offset - c.fam_offset);
     const bool have_cdf = size_cdf != nullptr;
 
-    for (uint32_t i = threadIdx.x; i < 4u * words; i += THREADS) s_seen1[i] = 0u;
+    for (uint32_t i = threadIdx.x; i < 2u * words; i += THREADS) s_seen[i] = 0u;
     if (threadIdx.x < 64) s_wt[threadIdx.x] = (int)threadIdx.x >= P.quality_threshold ? c_wtab_f[threadIdx.x] : 0.0;
     if (threadIdx.x < 32) s_qthr[threadIdx.x] = c_qual_thr[threadIdx.x];
     if (threadIdx.x < 5) s_acc[threadIdx.x] = 0ull;
@@ -151,10 +159,12 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
     // ---- pass 1: every molecule's UMI into the two filters --------------------------------
     for (uint32_t f = threadIdx.x; f < n_fam; f += THREADS) {
         const FamDraw d = draw_family<KNOBS>(ph, c, f, sp, cdf, lut, kn);
-        const uint32_t a = fused_h1(d.umi, filt_log2), b = fused_h2(d.umi, filt_log2);
-        const uint32_t ba = 1u << (a & 31u), bb = 1u << (b & 31u);
-        if (atomicOr(&s_seen1[a >> 5], ba) & ba) atomicOr(&s_dup1[a >> 5], ba);
-        if (atomicOr(&s_seen2[b >> 5], bb) & bb) atomicOr(&s_dup2[b >> 5], bb);
+#pragma unroll
+        for (int j = 0; j < FUSED_K; ++j) {
+            const uint32_t a = fused_hash(d.umi, j, slot_log2);
+            const uint32_t ba = 1u << (a & 31u);
+            if (atomicOr(&s_seen[a >> 5], ba) & ba) atomicOr(&s_dup[a >> 5], ba);
+        }
     }
     __syncthreads();
 
@@ -172,8 +182,12 @@ fused_cell_kernel(uint64_t seed, const ReadCell* __restrict__ cells, int n_cells
         bool cand = false;
         if (valid) {
             d = draw_family<KNOBS>(ph, c, f, sp, cdf, lut, kn);
-            const uint32_t a = fused_h1(d.umi, filt_log2), b = fused_h2(d.umi, filt_log2);
-            cand = ((s_dup1[a >> 5] >> (a & 31u)) & 1u) && ((s_dup2[b >> 5] >> (b & 31u)) & 1u);
+            cand = true;
+#pragma unroll
+            for (int j = 0; j < FUSED_K; ++j) {
+                const uint32_t a = fused_hash(d.umi, j, slot_log2);
+                cand = cand && ((s_dup[a >> 5] >> (a & 31u)) & 1u);
+            }
             n_reads += (uint32_t)d.size;
             n_cand += cand ? 1u : 0u;
         }
