@@ -387,45 +387,147 @@ __host__ __device__ static int lm_lmdif(const LmProblem& P, double* x, int maxfe
 
 // ---------------------------------------------------------------- one fit per WARP ------------------
 // A refit is a strictly sequential iteration and the kernel lasts as long as its slowest refit -- the resamples
-// whose parameters run away until maxfev = 2000 (about 5 % of them; the others stop after ~30 evaluations).  One
-// thread per fit spends that time in ~150 dependent fp64 exp / divide chains per iteration (measured: 48 ms for
-// the five depth curves of the eval-lod grid, 75 % of its wall time).  Here a fit owns a warp and lane i owns
-// curve point i: residuals, Jacobian columns and Householder updates are one operation per lane, and every sum
-// over the points is taken by ALL lanes in the index order of the loops above (operands broadcast by shuffle),
-// so the arithmetic -- and with it every convergence / fallback decision -- is that of lm_lmdif.  The 2 x 2
-// triangular solves (lmpar, qrsolv) run redundantly on every lane, on a 2 x 2 copy of the top of the Jacobian.
+// whose parameters run away until maxfev = 2000 (about 5 % of them: all-zero or perfectly separated hit rates, 667
+// iterations of three evaluations; the others stop after ~30 evaluations).  One thread per fit spends that time in
+// ~150 dependent fp64 exp / divide chains per iteration (measured: 45 ms for five curves x 201 refits).  Here a fit
+// owns a warp and lane i owns curve point i: residuals, Jacobian columns and Householder updates are one operation
+// per lane, every sum over the points is taken by ALL lanes in the index order of the loops above, and the 2 x 2
+// algebra (lmpar, qrsolv) is written out in registers, redundantly on every lane.  The arithmetic -- and with it
+// every convergence / fallback decision -- is that of lm_lmdif: the two kernels return the same bits.
+// What a runaway iteration costs was found with ncu's source view (profiles/r02_ncu_source_lod_fit_warp_kernel.txt):
+// its residuals are ~1e-290, so (1) every norm goes through enorm's "small" branch, fifteen dependent divisions by
+// the running maximum, (2) those and a dozen more divisions per iteration take the SLOW path of the fp64 division
+// routine (operands at extreme exponents), (3) pivot-indexed work vectors lived in local memory.  25 -> 13.4 ms.
 #ifdef __CUDACC__
 #define LMW_FULL 0xffffffffu
 __device__ __forceinline__ double lmw_get(double v, int lane) { return __shfl_sync(LMW_FULL, v, lane); }
 
-// enorm over points [start, start + n) of a lane-distributed vector
-__device__ static double lmw_enorm(double v, int start, int n) {
-    const double rdwarf = 3.834e-20, rgiant = 1.304e19;
+// Sums over the curve points are taken by ALL lanes in index order.  The operands cross the warp through a 32-double
+// row of shared memory per vector (one store per lane, then broadcast reads in batches of 16 so that the loads are
+// in flight together and only the DFMA chain itself is sequential); start is 0 or 1, start + n <= 32.
+struct LmwRow {
+    double a[32];
+    double b[32];
+};
+
+#define LMW_LOAD16(dst, src, base)                                              \
+    _Pragma("unroll") for (int k_ = 0; k_ < 8; ++k_) {                          \
+        const double2 p_ = reinterpret_cast<const double2*>(src)[(base) / 2 + k_]; \
+        dst[2 * k_] = p_.x;                                                     \
+        dst[2 * k_ + 1] = p_.y;                                                 \
+    }
+
+// enorm over points [start, start + n) of a lane-distributed vector.
+// The usual case (every |x| in enorm's middle range) is the plain sum of squares in index order.  The refits that
+// run away to maxfev are the other case: their residuals shrink to ~1e-290, enorm's "small" branch divides every
+// component by the running maximum.  The running maximum is a prefix maximum: a shuffle scan gives every lane the
+// maximum of the components before it, every lane then divides ITS component (all divisions of a norm at once), and
+// only the accumulation s = 1 + s t^2 / s += t^2 stays sequential -- the same operations on the same operands as the
+// loop form.
+__device__ __noinline__ double lmw_enorm(double v, int start, int n, double agiant /* rgiant / n */, LmwRow* row) {
+    const double rdwarf = 3.834e-20;
     double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
-    const double agiant = rgiant / (double)n;
-    for (int i = start; i < start + n; ++i) {
-        const double xabs = fabs(lmw_get(v, i));
-        if (xabs > rdwarf && xabs < agiant) {
-            s2 += xabs * xabs;
-        } else if (xabs <= rdwarf) {
-            if (xabs > x3max) {
-                const double t = x3max / xabs;
-                s3 = 1.0 + s3 * (t * t);
-                x3max = xabs;
-            } else if (xabs != 0.0) {
-                const double t = xabs / x3max;
-                s3 += t * t;
+    const int lane = threadIdx.x & 31, end = start + n;
+    const bool in = lane >= start && lane < end;
+    const double xa = fabs(v);
+    const bool mid = xa > rdwarf && xa < agiant;
+    double x[16];
+    if (__all_sync(LMW_FULL, mid || !in)) {
+        row->a[lane] = xa;
+        __syncwarp();
+        LMW_LOAD16(x, row->a, 0)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i >= start && i < end) s2 = fma(x[i], x[i], s2);
+        if (end > 16) {
+            LMW_LOAD16(x, row->a, 16)
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (16 + i < end) s2 = fma(x[i], x[i], s2);
+        }
+        __syncwarp();
+        return s2 != 0.0 ? sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3))) : 0.0;
+    }
+    const bool sml = in && !mid && xa <= rdwarf;
+    const bool big = in && !mid && !sml;
+    const bool any_big = __any_sync(LMW_FULL, big);
+    // inclusive prefix maxima of the small and of the large components (NaN never becomes a maximum: `xabs > max`)
+    double m3 = sml ? xa : 0.0, m1 = (big && xa == xa) ? xa : 0.0;
+    for (int d = 1; d < end; d <<= 1) {
+        const double t3 = __shfl_up_sync(LMW_FULL, m3, d);
+        if (lane >= d) m3 = fmax(m3, t3);
+        if (any_big) {
+            const double t1 = __shfl_up_sync(LMW_FULL, m1, d);
+            if (lane >= d) m1 = fmax(m1, t1);
+        }
+    }
+    double e3 = __shfl_up_sync(LMW_FULL, m3, 1), e1 = __shfl_up_sync(LMW_FULL, m1, 1);   // maxima BEFORE this component
+    if (lane == 0) e3 = e1 = 0.0;
+    // this lane's operand of the accumulation and which accumulation it is
+    double t = xa;
+    int op = 0;                                   // 1: s2 += t t   2: s3 = 1 + s3 t t   3: s3 += t t   4, 5: the same on s1
+    if (in) {
+        if (mid) {
+            op = 1;
+        } else if (sml) {
+            if (xa > e3) {
+                t = e3 / xa;
+                op = 2;
+            } else if (xa != 0.0) {
+                t = xa / e3;
+                op = 3;
             }
         } else {
-            if (xabs > x1max) {
-                const double t = x1max / xabs;
-                s1 = 1.0 + s1 * (t * t);
-                x1max = xabs;
+            if (xa > e1) {
+                t = e1 / xa;
+                op = 4;
             } else {
-                const double t = xabs / x1max;
-                s1 += t * t;
+                t = xa / e1;
+                op = 5;
             }
         }
+    }
+    row->a[lane] = t;
+    const unsigned b1 = __ballot_sync(LMW_FULL, op == 1), b2 = __ballot_sync(LMW_FULL, op == 2), b3 = __ballot_sync(LMW_FULL, op == 3),
+                   b4 = __ballot_sync(LMW_FULL, op == 4), b5 = __ballot_sync(LMW_FULL, op == 5);
+    __syncwarp();
+    // (the products are written as the fused multiply-adds the loop form compiles to)
+    if ((b1 | b4 | b5) == 0u) {                   // small components only: every norm of a runaway refit
+#pragma unroll
+        for (int h = 0; h < 32; h += 16) {
+            if (h < end) {
+                LMW_LOAD16(x, row->a, h)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const unsigned bit = 1u << (h + i);
+                    const double ti = x[i];
+                    const double r2 = fma(s3, ti * ti, 1.0), r3 = fma(ti, ti, s3);
+                    s3 = (b2 & bit) ? r2 : (b3 & bit) ? r3 : s3;
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int h = 0; h < 32; h += 16) {
+            if (h < end) {
+                LMW_LOAD16(x, row->a, h)
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const unsigned bit = 1u << (h + i);
+                    const double ti = x[i];
+                    if (b1 & bit) s2 = fma(ti, ti, s2);
+                    if (b2 & bit) s3 = fma(s3, ti * ti, 1.0);
+                    if (b3 & bit) s3 = fma(ti, ti, s3);
+                    if (b4 & bit) s1 = fma(s1, ti * ti, 1.0);
+                    if (b5 & bit) s1 = fma(ti, ti, s1);
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (n > 0) {
+        x3max = lmw_get(m3, end - 1);
+        x1max = lmw_get(m1, end - 1);
     }
     if (s1 != 0.0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
     if (s2 != 0.0) {
@@ -436,162 +538,403 @@ __device__ static double lmw_enorm(double v, int start, int n) {
 }
 
 // sum_{i = start}^{m-1} a[i] * b[i], in index order
-__device__ __forceinline__ double lmw_dot(double a, double b, int start, int m) {
-    double sum = 0.0;
-    for (int i = start; i < m; ++i) sum += lmw_get(a, i) * lmw_get(b, i);
+__device__ __noinline__ double lmw_dot(double a, double b, int start, int m, LmwRow* row) {
+    const int lane = threadIdx.x & 31;
+    row->a[lane] = a;
+    row->b[lane] = b;
+    __syncwarp();
+    double sum = 0.0, x[16], y[16];
+    LMW_LOAD16(x, row->a, 0)
+    LMW_LOAD16(y, row->b, 0)
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (i >= start && i < m) sum = fma(x[i], y[i], sum);
+    if (m > 16) {
+        LMW_LOAD16(x, row->a, 16)
+        LMW_LOAD16(y, row->b, 16)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (16 + i < m) sum = fma(x[i], y[i], sum);
+    }
+    __syncwarp();
     return sum;
 }
 
-__device__ __forceinline__ double lmw_fcn(double px, double py, const double* p) {
-    return 1.0 / (1.0 + exp(-(p[0] * px + p[1]))) - py;
-}
-
-// Householder QR with column pivoting of the m x 2 Jacobian held as two lane-distributed columns
-__device__ static void lmw_qrfac(int m, int lane, double& c0, double& c1, int* ipvt, double* rdiag, double* acnorm, double* wa) {
-    const double epsmch = 2.220446049250313e-16;
-    acnorm[0] = lmw_enorm(c0, 0, m);
-    acnorm[1] = lmw_enorm(c1, 0, m);
-    rdiag[0] = wa[0] = acnorm[0];
-    rdiag[1] = wa[1] = acnorm[1];
-    ipvt[0] = 0;
-    ipvt[1] = 1;
-    if (rdiag[1] > rdiag[0]) {          // n = 2: the only possible exchange
-        const double t = c0; c0 = c1; c1 = t;
-        rdiag[1] = rdiag[0];
-        wa[1] = wa[0];
-        ipvt[0] = 1;
-        ipvt[1] = 0;
-    }
-    double ajnorm = lmw_enorm(c0, 0, m);
-    if (ajnorm != 0.0) {
-        if (lmw_get(c0, 0) < 0.0) ajnorm = -ajnorm;
-        if (lane < m) c0 /= ajnorm;
-        if (lane == 0) c0 += 1.0;
-        const double sum = lmw_dot(c0, c1, 0, m);
-        const double temp = sum / lmw_get(c0, 0);
-        if (lane < m) c1 -= temp * c0;
-        if (rdiag[1] != 0.0) {
-            double t = lmw_get(c1, 0) / rdiag[1];
-            rdiag[1] *= sqrt(fmax(0.0, 1.0 - t * t));
-            t = rdiag[1] / wa[1];
-            if (0.05 * (t * t) <= epsmch) {
-                rdiag[1] = lmw_enorm(c1, 1, m - 1);
-                wa[1] = rdiag[1];
-            }
+// ---- the 2 x 2 algebra in REGISTERS ------------------------------------------------------------------------
+// The general lm_lmpar / lm_qrsolv index their work vectors by the pivot order (x[ipvt[j]], diag[ipvt[j]]): ptxas
+// keeps every such array in LOCAL memory and each dependent step waits for an L1 round trip.  Below, n = 2 is written
+// out: the pivot order is one bit (`sw`: the columns were exchanged), every vector is two scalars, the loops are
+// unrolled by hand.  Every expression is the one of the loop form, in its order, so the fits are unchanged.
+__device__ __forceinline__ void lm2_enorm_step(double xabs, double agiant, double& s1, double& s2, double& s3, double& x1max, double& x3max) {
+    const double rdwarf = 3.834e-20;
+    if (xabs > rdwarf && xabs < agiant) {
+        s2 += xabs * xabs;
+    } else if (xabs <= rdwarf) {
+        if (xabs > x3max) {
+            const double t = x3max / xabs;
+            s3 = 1.0 + s3 * (t * t);
+            x3max = xabs;
+        } else if (xabs != 0.0) {
+            const double t = xabs / x3max;
+            s3 += t * t;
+        }
+    } else {
+        if (xabs > x1max) {
+            const double t = x1max / xabs;
+            s1 = 1.0 + s1 * (t * t);
+            x1max = xabs;
+        } else {
+            const double t = xabs / x1max;
+            s1 += t * t;
         }
     }
-    rdiag[0] = -ajnorm;
-    ajnorm = lmw_enorm(c1, 1, m - 1);
-    if (ajnorm != 0.0) {
-        if (lmw_get(c1, 1) < 0.0) ajnorm = -ajnorm;
-        if (lane >= 1 && lane < m) c1 /= ajnorm;
-        if (lane == 1) c1 += 1.0;
+}
+__device__ __noinline__ double lm2_enorm(double a, double b) {          // lm_enorm(2, {a, b})
+    const double rgiant = 1.304e19;
+    double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
+    const double agiant = rgiant / 2.0;
+    lm2_enorm_step(fabs(a), agiant, s1, s2, s3, x1max, x3max);
+    lm2_enorm_step(fabs(b), agiant, s1, s2, s3, x1max, x3max);
+    if (s1 != 0.0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0.0) {
+        if (s2 >= x3max) return sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
     }
-    rdiag[1] = -ajnorm;
+    return x3max * sqrt(s3);
+}
+__device__ __forceinline__ double lm2_sel(bool sw, double a0, double a1) { return sw ? a1 : a0; }   // a[ipvt[0]]
+__device__ __forceinline__ void lm2_givens(double rkk, double sd, double& cs, double& sn) {
+    if (fabs(rkk) < fabs(sd)) {
+        const double cotan = rkk / sd;
+        sn = 0.5 / sqrt(0.25 + 0.25 * (cotan * cotan));
+        cs = sn * cotan;
+    } else {
+        const double tn = sd / rkk;
+        cs = 0.5 / sqrt(0.25 + 0.25 * (tn * tn));
+        sn = cs * tn;
+    }
 }
 
-// lm_lmdif with the curve distributed over the lanes (px, py: this lane's point); m <= 32
-__device__ static int lmw_lmdif(int m, int lane, double px, double py, double* x, int maxfev) {
+// lm_qrsolv for n = 2.  (r00, r01, r11): the upper triangle, left untouched (the general form saves and restores
+// its diagonal); t10: the strict lower triangle it leaves behind, which lmpar's Newton step reads.
+__device__ __forceinline__ void lm2_qrsolv(double r00, double r01, double r11, bool sw, double dg0, double dg1, double qtb0, double qtb1,
+                                           double& x0, double& x1, double& sdiag0, double& sdiag1, double& t10) {
+    double d00 = r00, d11 = r11, wa0 = qtb0, wa1 = qtb1;
+    t10 = r01;
+    {   // j = 0
+        const double dl = lm2_sel(sw, dg0, dg1);
+        if (dl != 0.0) {
+            double sd0 = dl, sd1 = 0.0, qtbpj = 0.0, cs, sn;
+            lm2_givens(d00, sd0, cs, sn);                    // k = 0
+            d00 = cs * d00 + sn * sd0;
+            {
+                const double temp = cs * wa0 + sn * qtbpj;
+                qtbpj = -sn * wa0 + cs * qtbpj;
+                wa0 = temp;
+            }
+            {
+                const double t2 = cs * t10 + sn * sd1;
+                sd1 = -sn * t10 + cs * sd1;
+                t10 = t2;
+            }
+            if (sd1 != 0.0) {                                // k = 1
+                lm2_givens(d11, sd1, cs, sn);
+                d11 = cs * d11 + sn * sd1;
+                const double temp = cs * wa1 + sn * qtbpj;
+                qtbpj = -sn * wa1 + cs * qtbpj;
+                wa1 = temp;
+            }
+        }
+        sdiag0 = d00;
+    }
+    {   // j = 1
+        const double dl = lm2_sel(sw, dg1, dg0);
+        if (dl != 0.0) {
+            double sd1 = dl, qtbpj = 0.0, cs, sn;
+            lm2_givens(d11, sd1, cs, sn);
+            d11 = cs * d11 + sn * sd1;
+            const double temp = cs * wa1 + sn * qtbpj;
+            wa1 = temp;
+        }
+        sdiag1 = d11;
+    }
+    if (sdiag0 == 0.0) {
+        wa0 = 0.0;
+        wa1 = 0.0;
+    } else if (sdiag1 == 0.0) {
+        wa1 = 0.0;
+        double sum = 0.0;
+        wa0 = (wa0 - sum) / sdiag0;
+    } else {
+        {
+            double sum = 0.0;
+            wa1 = (wa1 - sum) / sdiag1;
+        }
+        double sum = 0.0;
+        sum += t10 * wa1;
+        wa0 = (wa0 - sum) / sdiag0;
+    }
+    x0 = sw ? wa1 : wa0;                                     // x[ipvt[j]] = wa[j]
+    x1 = sw ? wa0 : wa1;
+}
+
+// lm_lmpar for n = 2 (x0, x1: the step, indexed by parameter)
+__device__ __forceinline__ void lm2_lmpar(double r00, double r01, double r11, bool sw, double diag0, double diag1, double qtb0, double qtb1,
+                                          double delta, double& par, double& x0, double& x1) {
+    const double dwarf = 2.2250738585072014e-308;
+    int nsing = 2;
+    double w0 = qtb0, w1 = qtb1;
+    if (r00 == 0.0) {
+        nsing = 0;
+        w0 = 0.0;
+        w1 = 0.0;
+    } else if (r11 == 0.0) {
+        nsing = 1;
+        w1 = 0.0;
+    }
+    if (nsing == 2) {
+        w1 /= r11;
+        const double temp = w1;
+        w0 -= r01 * temp;
+        w0 /= r00;
+    } else if (nsing == 1) {
+        w0 /= r00;
+    }
+    x0 = sw ? w1 : w0;
+    x1 = sw ? w0 : w1;
+    int iter = 0;
+    double v0 = diag0 * x0, v1 = diag1 * x1;                 // wa2
+    double dxnorm = lm2_enorm(v0, v1);
+    double fp = dxnorm - delta;
+    if (fp <= 0.1 * delta) {
+        par = 0.0;
+        return;
+    }
+    double parl = 0.0;
+    if (nsing >= 2) {
+        w0 = lm2_sel(sw, diag0, diag1) * (lm2_sel(sw, v0, v1) / dxnorm);
+        w1 = lm2_sel(sw, diag1, diag0) * (lm2_sel(sw, v1, v0) / dxnorm);
+        {
+            double sum = 0.0;
+            w0 = (w0 - sum) / r00;
+        }
+        {
+            double sum = 0.0;
+            sum += r01 * w0;
+            w1 = (w1 - sum) / r11;
+        }
+        const double temp = lm2_enorm(w0, w1);
+        parl = ((fp / delta) / temp) / temp;
+    }
+    {
+        double sum = 0.0;
+        sum += r00 * qtb0;
+        w0 = sum / lm2_sel(sw, diag0, diag1);
+    }
+    {
+        double sum = 0.0;
+        sum += r01 * qtb0;
+        sum += r11 * qtb1;
+        w1 = sum / lm2_sel(sw, diag1, diag0);
+    }
+    const double gnorm = lm2_enorm(w0, w1);
+    double paru = gnorm / delta;
+    if (paru == 0.0) paru = dwarf / fmin(delta, 0.1);
+    par = fmax(par, parl);
+    par = fmin(par, paru);
+    if (par == 0.0) par = gnorm / dxnorm;
+    for (;;) {
+        ++iter;
+        if (par == 0.0) par = fmax(dwarf, 0.001 * paru);
+        double temp = sqrt(par);
+        w0 = temp * diag0;
+        w1 = temp * diag1;
+        double sdiag0, sdiag1, t10;
+        lm2_qrsolv(r00, r01, r11, sw, w0, w1, qtb0, qtb1, x0, x1, sdiag0, sdiag1, t10);
+        v0 = diag0 * x0;
+        v1 = diag1 * x1;
+        dxnorm = lm2_enorm(v0, v1);
+        temp = fp;
+        fp = dxnorm - delta;
+        if (fabs(fp) <= 0.1 * delta || (parl == 0.0 && fp <= temp && temp < 0.0) || iter == 10) break;
+        w0 = lm2_sel(sw, diag0, diag1) * (lm2_sel(sw, v0, v1) / dxnorm);
+        w1 = lm2_sel(sw, diag1, diag0) * (lm2_sel(sw, v1, v0) / dxnorm);
+        w0 /= sdiag0;
+        {
+            const double t = w0;
+            w1 -= t10 * t;
+        }
+        w1 /= sdiag1;
+        temp = lm2_enorm(w0, w1);
+        const double parc = ((fp / delta) / temp) / temp;
+        if (fp > 0.0) parl = fmax(parl, par);
+        if (fp < 0.0) paru = fmin(paru, par);
+        par = fmax(parl, par + parc);
+    }
+}
+
+__device__ __noinline__ double lmw_fcn2(double px, double py, double a, double b) {
+    return 1.0 / (1.0 + exp(-(a * px + b))) - py;
+}
+
+__device__ static int lmw_lmdif2(int m, int lane, double px, double py, double* xio, int maxfev, LmwRow* row) {
     const double epsmch = 2.220446049250313e-16;
     const double ftol = 1.49012e-8, xtol = 1.49012e-8, gtol = 0.0, factor = 100.0;
-    double fvec, wa4v, c0, c1;                       // this lane's row of fvec, wa4 and the two Jacobian columns
-    double r[LM_N * LM_N];                           // top 2 x 2 of the factored Jacobian (column-major, ldr = 2)
-    double diag[LM_N], qtf[LM_N], wa1[LM_N], wa2[LM_N], wa3[LM_N], wa4[LM_N];
-    int ipvt[LM_N];
+    double x0 = xio[0], x1 = xio[1];
+    double fvec, wa4v, c0, c1;
+    double diag0 = 0.0, diag1 = 0.0;
     int info = 0, nfev = 0;
-    fvec = lmw_fcn(px, py, x);
+    const double ag_m = 1.304e19 / (double)m, ag_m1 = 1.304e19 / (double)(m - 1);      // enorm's agiant for n = m, m - 1
+    fvec = lmw_fcn2(px, py, x0, x1);
     nfev = 1;
-    double fnorm = lmw_enorm(fvec, 0, m);
+    double fnorm = lmw_enorm(fvec, 0, m, ag_m, row);
     double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
     int iter = 1;
     for (;;) {
         {
             const double eps = sqrt(epsmch);
-            for (int j = 0; j < LM_N; ++j) {
-                const double temp = x[j];
+            {
+                const double temp = x0;
                 double h = eps * fabs(temp);
                 if (h == 0.0) h = eps;
-                x[j] = temp + h;
-                wa4v = lmw_fcn(px, py, x);
-                x[j] = temp;
-                const double d = (wa4v - fvec) / h;
-                if (j == 0) c0 = d; else c1 = d;
+                wa4v = lmw_fcn2(px, py, temp + h, x1);
+                c0 = (wa4v - fvec) / h;
+            }
+            {
+                const double temp = x1;
+                double h = eps * fabs(temp);
+                if (h == 0.0) h = eps;
+                wa4v = lmw_fcn2(px, py, x0, temp + h);
+                c1 = (wa4v - fvec) / h;
             }
             nfev += LM_N;
         }
-        lmw_qrfac(m, lane, c0, c1, ipvt, wa1, wa2, wa3);
-        if (iter == 1) {
-            for (int j = 0; j < LM_N; ++j) {
-                diag[j] = wa2[j];
-                if (wa2[j] == 0.0) diag[j] = 1.0;
+        // qrfac (lmw_qrfac with the pivot order as one bit)
+        double rdiag0, rdiag1, acnorm0, acnorm1, qw1;
+        bool sw = false;
+        {
+            acnorm0 = lmw_enorm(c0, 0, m, ag_m, row);
+            acnorm1 = lmw_enorm(c1, 0, m, ag_m, row);
+            rdiag0 = acnorm0;
+            rdiag1 = qw1 = acnorm1;
+            if (rdiag1 > rdiag0) {
+                const double t = c0; c0 = c1; c1 = t;
+                rdiag1 = rdiag0;
+                qw1 = acnorm0;
+                sw = true;
             }
-            for (int j = 0; j < LM_N; ++j) wa3[j] = diag[j] * x[j];
-            xnorm = lm_enorm(LM_N, wa3);
+            double ajnorm = sw ? acnorm1 : acnorm0;         // enorm of the pivot column: the norm already taken
+            if (ajnorm != 0.0) {
+                if (lmw_get(c0, 0) < 0.0) ajnorm = -ajnorm;
+                if (lane < m) c0 /= ajnorm;
+                if (lane == 0) c0 += 1.0;
+                const double sum = lmw_dot(c0, c1, 0, m, row);
+                const double temp = sum / lmw_get(c0, 0);
+                if (lane < m) c1 -= temp * c0;
+                if (rdiag1 != 0.0) {
+                    double t = lmw_get(c1, 0) / rdiag1;
+                    rdiag1 *= sqrt(fmax(0.0, 1.0 - t * t));
+                    t = rdiag1 / qw1;
+                    if (0.05 * (t * t) <= epsmch) {
+                        rdiag1 = lmw_enorm(c1, 1, m - 1, ag_m1, row);
+                        qw1 = rdiag1;
+                    }
+                }
+            }
+            rdiag0 = -ajnorm;
+            ajnorm = lmw_enorm(c1, 1, m - 1, ag_m1, row);
+            if (ajnorm != 0.0) {
+                if (lmw_get(c1, 1) < 0.0) ajnorm = -ajnorm;
+                if (lane >= 1 && lane < m) c1 /= ajnorm;
+                if (lane == 1) c1 += 1.0;
+            }
+            rdiag1 = -ajnorm;
+        }
+        if (iter == 1) {
+            diag0 = acnorm0;
+            if (acnorm0 == 0.0) diag0 = 1.0;
+            diag1 = acnorm1;
+            if (acnorm1 == 0.0) diag1 = 1.0;
+            xnorm = lm2_enorm(diag0 * x0, diag1 * x1);
             delta = factor * xnorm;
             if (delta == 0.0) delta = factor;
         }
         wa4v = fvec;
+        double qtf0, qtf1;
         {   // j = 0
             const double ajj = lmw_get(c0, 0);
             if (ajj != 0.0) {
-                const double sum = lmw_dot(c0, wa4v, 0, m);
+                const double sum = lmw_dot(c0, wa4v, 0, m, row);
                 const double temp = -sum / ajj;
                 if (lane < m) wa4v += c0 * temp;
             }
-            if (lane == 0) c0 = wa1[0];
-            qtf[0] = lmw_get(wa4v, 0);
+            if (lane == 0) c0 = rdiag0;
+            qtf0 = lmw_get(wa4v, 0);
         }
         {   // j = 1
             const double ajj = lmw_get(c1, 1);
             if (ajj != 0.0) {
-                const double sum = lmw_dot(c1, wa4v, 1, m);
+                const double sum = lmw_dot(c1, wa4v, 1, m, row);
                 const double temp = -sum / ajj;
                 if (lane >= 1 && lane < m) wa4v += c1 * temp;
             }
-            if (lane == 1) c1 = wa1[1];
-            qtf[1] = lmw_get(wa4v, 1);
+            if (lane == 1) c1 = rdiag1;
+            qtf1 = lmw_get(wa4v, 1);
         }
-        r[0] = lmw_get(c0, 0); r[1] = lmw_get(c0, 1);          // r[j * 2 + i] = column j, row i
-        r[2] = lmw_get(c1, 0); r[3] = lmw_get(c1, 1);
+        const double r00 = lmw_get(c0, 0), r01 = lmw_get(c1, 0), r11 = lmw_get(c1, 1);
         gnorm = 0.0;
         if (fnorm != 0.0) {
-            for (int j = 0; j < LM_N; ++j) {
-                const int l = ipvt[j];
-                if (wa2[l] != 0.0) {
+            {
+                const double acn = lm2_sel(sw, acnorm0, acnorm1);
+                if (acn != 0.0) {
                     double sum = 0.0;
-                    for (int i = 0; i <= j; ++i) sum += r[j * LM_N + i] * (qtf[i] / fnorm);
-                    gnorm = fmax(gnorm, fabs(sum / wa2[l]));
+                    sum += r00 * (qtf0 / fnorm);
+                    gnorm = fmax(gnorm, fabs(sum / acn));
+                }
+            }
+            {
+                const double acn = lm2_sel(sw, acnorm1, acnorm0);
+                if (acn != 0.0) {
+                    double sum = 0.0;
+                    sum += r01 * (qtf0 / fnorm);
+                    sum += r11 * (qtf1 / fnorm);
+                    gnorm = fmax(gnorm, fabs(sum / acn));
                 }
             }
         }
         if (gnorm <= gtol) info = 4;
         if (info != 0) break;
-        for (int j = 0; j < LM_N; ++j) diag[j] = fmax(diag[j], wa2[j]);
+        diag0 = fmax(diag0, acnorm0);
+        diag1 = fmax(diag1, acnorm1);
         double ratio;
         do {
-            // (lmpar / qrsolv only write the strict lower triangle of r, which nothing below reads)
-            lm_lmpar(r, LM_N, ipvt, diag, qtf, delta, &par, wa1, wa2, wa3, wa4);
-            for (int j = 0; j < LM_N; ++j) {
-                wa1[j] = -wa1[j];
-                wa2[j] = x[j] + wa1[j];
-                wa3[j] = diag[j] * wa1[j];
-            }
-            const double pnorm = lm_enorm(LM_N, wa3);
+            double p0, p1;
+            lm2_lmpar(r00, r01, r11, sw, diag0, diag1, qtf0, qtf1, delta, par, p0, p1);
+            p0 = -p0;
+            p1 = -p1;
+            const double n0 = x0 + p0, n1 = x1 + p1;           // wa2
+            const double pnorm = lm2_enorm(diag0 * p0, diag1 * p1);
             if (iter == 1) delta = fmin(delta, pnorm);
-            wa4v = lmw_fcn(px, py, wa2);
+            wa4v = lmw_fcn2(px, py, n0, n1);
             ++nfev;
-            const double fnorm1 = lmw_enorm(wa4v, 0, m);
+            const double fnorm1 = lmw_enorm(wa4v, 0, m, ag_m, row);
             double actred = -1.0;
             if (0.1 * fnorm1 < fnorm) {
                 const double t = fnorm1 / fnorm;
                 actred = 1.0 - t * t;
             }
-            for (int j = 0; j < LM_N; ++j) {
-                wa3[j] = 0.0;
-                const double temp = wa1[ipvt[j]];
-                for (int i = 0; i <= j; ++i) wa3[i] += r[j * LM_N + i] * temp;
+            double u0 = 0.0, u1;                                // wa3 = R * P^T p
+            {
+                const double temp = lm2_sel(sw, p0, p1);
+                u0 += r00 * temp;
             }
-            const double temp1 = lm_enorm(LM_N, wa3) / fnorm;
+            {
+                u1 = 0.0;
+                const double temp = lm2_sel(sw, p1, p0);
+                u0 += r01 * temp;
+                u1 += r11 * temp;
+            }
+            const double temp1 = lm2_enorm(u0, u1) / fnorm;
             const double temp2 = (sqrt(par) * pnorm) / fnorm;
             const double prered = temp1 * temp1 + temp2 * temp2 / 0.5;
             const double dirder = -(temp1 * temp1 + temp2 * temp2);
@@ -609,12 +952,10 @@ __device__ static int lmw_lmdif(int m, int lane, double px, double py, double* x
                 par *= 0.5;
             }
             if (ratio >= 1e-4) {
-                for (int j = 0; j < LM_N; ++j) {
-                    x[j] = wa2[j];
-                    wa2[j] = diag[j] * x[j];
-                }
+                x0 = n0;
+                x1 = n1;
                 fvec = wa4v;
-                xnorm = lm_enorm(LM_N, wa2);
+                xnorm = lm2_enorm(diag0 * x0, diag1 * x1);
                 fnorm = fnorm1;
                 ++iter;
             }
@@ -630,6 +971,8 @@ __device__ static int lmw_lmdif(int m, int lane, double px, double py, double* x
         } while (ratio < 1e-4);
         if (info != 0) break;
     }
+    xio[0] = x0;
+    xio[1] = x1;
     return info;
 }
 #endif  // __CUDACC__
@@ -656,11 +999,12 @@ __host__ __device__ static double lod_interp_fallback(const LmProblem& P, const 
     return ((target - xlo) / (xhi - xlo)) * yhi + ((xhi - target) / (xhi - xlo)) * ylo;
 }
 
+#define LOD_MAXFEV 2000
 __host__ __device__ static double lod_fit_one(const LmProblem& P, const double* af, double target) {
     double p[2] = {1.0, 1.0};
     bool finite_in = true;
     for (int i = 0; i < P.m; ++i) finite_in &= isfinite(P.x[i]) && isfinite(P.y[i]);
-    int info = finite_in ? lm_lmdif(P, p, 2000) : 0;
+    int info = finite_in ? lm_lmdif(P, p, LOD_MAXFEV) : 0;
     if (info >= 1 && info <= 4) {
         // lod.py:365-371
         const double logit_target = log(target / (1.0 - target));
@@ -720,7 +1064,8 @@ lod_fit_warp_kernel(uint64_t seed, const uint64_t* __restrict__ stream_ids, cons
     }
     const bool finite_in = __all_sync(0xffffffffu, lane >= m || (isfinite(px) && isfinite(py)));
     double p[2] = {1.0, 1.0};
-    const int info = finite_in ? lmw_lmdif(m, lane, px, py, p, 2000) : 0;
+    __shared__ __align__(16) LmwRow s_row[LODW_FITS_PER_BLOCK];
+    const int info = finite_in ? lmw_lmdif2(m, lane, px, py, p, LOD_MAXFEV, &s_row[threadIdx.x >> 5]) : 0;
     double lod;
     if (info >= 1 && info <= 4) {
         const double logit_target = log(target / (1.0 - target));          // lod.py:365-371

@@ -698,9 +698,9 @@ def test_fit_lod_matches_reference_golden(ctx, golden, monkeypatch):
     assert np.isnan(float(g["zeros_lod"]))
     # determinism
     assert ctx.fit_lod(af, g["mid_hit"], 0.95, 50, 9) == ctx.fit_lod(af, g["mid_hit"], 0.95, 50, 9)
-    # one warp per fit (lane = curve point) takes the decisions of one thread per fit: the same NaN pattern and the
-    # same optimum to within lmdif's own stopping tolerance (ftol = xtol = 1.5e-8; the two kernels may contract
-    # different products into FMAs, so the iterates differ in the last bits)
+    # one warp per fit (lane = curve point, 2 x 2 algebra in registers) takes the decisions of one thread per fit
+    # (the general loop form): the same NaN pattern and the same optimum to within lmdif's own stopping tolerance
+    # (ftol = xtol = 1.5e-8; measured: the same bits, but FMA contraction is the compiler's choice)
     rng = np.random.default_rng(5)
     curves = np.clip(np.sort(rng.random((12, len(af))), axis=1) ** rng.uniform(0.5, 6.0, (12, 1)), 0, 1)
     curves[3] = 0.0
@@ -718,3 +718,4 @@ def test_fit_lod_matches_reference_golden(ctx, golden, monkeypatch):
     batch = ctx.fit_lod_batch(af, [g[f"{n}_hit"] for n in names], 0.95, 60, list(range(3, 3 + len(names))))
     for i, n in enumerate(names):
         assert str(batch[i]) == str(ctx.fit_lod(af, g[f"{n}_hit"], 0.95, 60, 3 + i)), n
+
