@@ -747,7 +747,7 @@ def main() -> int:
                 "rs_downsweep": (["rs_downsweep_direct_kernel", "rs_downsweep_staged_kernel", "rs_downsweep_kernel<false>"], 2.0 * rec * passes),
                 "rs_upsweep_kernel": (["rs_upsweep_kernel"], 8.0 * up_passes),
                 "reads_gen_kernel": (["reads_gen_kernel"], float(rec)),
-                "cell_consensus_kernel": (["cell_consensus_kernel<true>", "cell_consensus_kernel<false>"], float(rec)),
+                "cell_consensus_kernel": (["cell_consensus_peel_kernel", "cell_consensus_kernel<true>", "cell_consensus_kernel<false>"], float(rec)),
                 "small_cell_kernel": (["small_cell_kernel"], float(rec)),
             }
             table = []

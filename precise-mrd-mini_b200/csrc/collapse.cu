@@ -713,6 +713,292 @@ cell_consensus_bulk_kernel(const uint64_t* __restrict__ rec, const int64_t* __re
     }
 }
 
+// ---------------------------------------------------------------- fused consensus+count after a 16-BIT sort ---------
+// Grouping, not sorting, is what the vote needs: after TWO radix passes a cell is ordered on the low 16 UMI bits and a
+// RUN (equal low bits) holds the reads of the one to three families that differ only in the unsorted high byte,
+// interleaved, each still in input order (the passes are stable).  The third pass over HBM (16 B per record + its
+// counting pass) is replaced by work inside this kernel's shared-memory tile:
+//   * the head pass also leaves the high byte of every record in a dense array and marks the runs in which it changes;
+//   * a PURE run (the majority: 2^16 possible values for at most 5e4 families per cell) is one family, voted as in
+//     cell_consensus_bulk_kernel;
+//   * a MIXED run is swept: the first sweep folds two families at once (the first read's and the first that differs),
+//     branch-free -- a read of another family adds +0.0 -- and notes the two smallest other high bytes present (ordered
+//     from the run's first byte, cyclically: families are counted, their order is free); those rare third and fourth
+//     families become (run, byte) items of a work list that the block sweeps afterwards, one item per thread.  Pure and
+//     mixed runs are bucketed apart (and by length), so the lanes of a warp do the same work;
+//   * the tile's last run may continue in the next tile(s): it is swept through global memory by its owner.
+// Padding records (UMI 0xffffffff) share their low bits with real UMIs: a change between padding and reads opens a run
+// too, so padding forms runs of its own (skipped) exactly as under the full sort.
+struct CpSmem {
+    uint64_t rec[CC_TILE];             // the tile; recycled as the bucketed run order (uint16) once the heads are known
+    uint16_t head[CC_TILE];
+    uint16_t hp[CC_TILE];              // high UMI byte << 8 | payload byte (allele[1:0] | quality << 2)
+    uint8_t mixed[CC_TILE];            // [h] != 0: run h holds more than one distinct UMI (plain stores of 1: no atomics)
+    double wt[64];
+    unsigned long long acc[3];
+    unsigned long long bar;
+    uint32_t bkt[64];
+    uint32_t wcount[CC_THREADS / 32];
+    uint32_t n_items;
+};
+
+template <bool MAJ>
+__device__ __forceinline__ void cp_finish(const FoldVote2<MAJ>& v, int size, const pmrd_umi_params& P, uint32_t& n_fam, uint32_t& n_tot, uint32_t& n_var) {
+    ++n_fam;
+    if (size >= P.min_family_size) {
+        const int best = v.result(P.consensus_threshold);
+        if (best >= 0) { ++n_tot; n_var += best == 1; }
+    }
+}
+// Sweeps of a mixed run are BRANCH-FREE: a read of another family adds +0.0 (FoldVote2::add_w), so the lanes of a warp,
+// whose runs interleave their families differently, stay converged.  The first sweep folds TWO families at once (the
+// first read's and the first one that differs: most mixed runs hold exactly two); what is left is taken one family per
+// sweep in increasing (hi - t0) mod 256.
+// one family per sweep, in increasing (hi - t0) mod 256 from `key` on (key1 was folded by the first sweep); once = only `key`
+template <bool MAJ, typename HpAt>
+__device__ __forceinline__ void cp_sweep_chain(int len, HpAt hp_at, uint32_t t0, uint32_t key, uint32_t key1, bool once, uint32_t alt,
+                                               const double* wt, const pmrd_umi_params& P, uint32_t& n_fam, uint32_t& n_tot, uint32_t& n_var) {
+    while (key != 256u) {
+        FoldVote2<MAJ> v;
+        int size = 0;
+        uint32_t nxt = 256u;
+        for (int c = 0; c < len; ++c) {
+            const uint32_t x = hp_at(c);
+            const uint32_t k = ((x >> 8) - t0) & 0xffu;
+            const bool m = k == key;
+            v.add_w(x, alt, m ? wt[(x >> 2) & 63u] : 0.0);
+            size += m;
+            nxt = (k > key && k != key1) ? min(nxt, k) : nxt;
+        }
+        cp_finish<MAJ>(v, size, P, n_fam, n_tot, n_var);
+        if (once) break;
+        key = nxt;
+    }
+}
+// first sweep: folds the first read's family and the first family that differs; n1 < n2: the two smallest other keys (256: none)
+template <bool MAJ, typename HpAt>
+__device__ __forceinline__ void cp_sweep_first(int len, HpAt hp_at, uint32_t alt, const double* wt, const pmrd_umi_params& P, uint32_t& key1,
+                                               uint32_t& n1, uint32_t& n2, uint32_t& n_fam, uint32_t& n_tot, uint32_t& n_var) {
+    const uint32_t t0 = hp_at(0) >> 8;
+    key1 = 256u;                                            // (256: the run is pure -- only the tile's last run can be)
+    for (int c = 1; c < len; ++c) {
+        const uint32_t k = ((hp_at(c) >> 8) - t0) & 0xffu;
+        if (k) { key1 = k; break; }
+    }
+    n1 = n2 = 256u;
+    FoldVote2<MAJ> a, b;
+    int sa = 0, sb = 0;
+    for (int c = 0; c < len; ++c) {
+        const uint32_t x = hp_at(c);
+        const uint32_t k = ((x >> 8) - t0) & 0xffu;
+        const double w = wt[(x >> 2) & 63u];
+        const bool ma = k == 0u, mb = k == key1;
+        a.add_w(x, alt, ma ? w : 0.0);
+        b.add_w(x, alt, mb ? w : 0.0);
+        sa += ma;
+        sb += mb;
+        const uint32_t kk = (ma || mb) ? 256u : k;          // a third family's key, else neutral
+        const uint32_t hi = max(n1, kk);
+        n1 = min(n1, kk);
+        n2 = hi == n1 ? n2 : min(n2, hi);                   // (hi == n1: kk repeats the smallest key, or both are 256)
+    }
+    cp_finish<MAJ>(a, sa, P, n_fam, n_tot, n_var);
+    if (key1 != 256u) cp_finish<MAJ>(b, sb, P, n_fam, n_tot, n_var);
+}
+
+template <bool MAJ>
+__global__ void __launch_bounds__(CC_THREADS)
+cell_consensus_peel_kernel(const uint64_t* __restrict__ rec, const int64_t* __restrict__ cell_tile_start, const int32_t* __restrict__ tile_cell,
+                           pmrd_umi_params P, int64_t cell0, const uint8_t* __restrict__ alt_allele, unsigned long long* __restrict__ o_fam,
+                           unsigned long long* __restrict__ o_tot, unsigned long long* __restrict__ o_var) {
+    constexpr int WARPS = CC_THREADS / 32, PER_WARP = CC_TILE / WARPS, ITERS = PER_WARP / 32;
+    extern __shared__ __align__(128) unsigned char cp_raw[];
+    CpSmem& S = *reinterpret_cast<CpSmem*>(cp_raw);
+    uint16_t* const s_order = reinterpret_cast<uint16_t*>(S.rec);                       // [CC_TILE]: 8 KB
+    uint32_t* const s_items = reinterpret_cast<uint32_t*>(S.rec) + CC_TILE / 2;         // behind it: (run, key) items, at most one per read
+    const int64_t tile = blockIdx.x;
+    const int64_t base = tile * CC_TILE;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = lanemask_lt();
+    const uint32_t bar = smem_u32(&S.bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(CC_TILE * 8)) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(S.rec)), "l"(rec + base), "r"((uint32_t)(CC_TILE * 8)), "r"(bar) : "memory");
+    }
+    // (overlaps the copy)
+    if (threadIdx.x < 3) S.acc[threadIdx.x] = 0ull;
+    if (threadIdx.x == 3) S.n_items = 0u;
+    if (threadIdx.x < 64) S.bkt[threadIdx.x] = 0u;
+    if (threadIdx.x < 64) S.wt[threadIdx.x] = (int)threadIdx.x >= P.quality_threshold ? c_wtab[threadIdx.x] : 0.0;
+    reinterpret_cast<uint4*>(S.mixed)[threadIdx.x] = make_uint4(0u, 0u, 0u, 0u);
+    static_assert(CC_TILE == 16 * CC_THREADS, "one 16-byte slice of the run flags per thread");
+    const int cell = tile_cell[tile];
+    const int64_t cell_lo = cell_tile_start[cell] * CC_TILE, cell_hi = cell_tile_start[cell + 1] * CC_TILE;
+    const uint32_t prev_tile_umi = base == cell_lo ? 0u : (uint32_t)rec[base - 1];
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(bar) : "memory");
+    }
+    // ---- heads of the 16-bit runs, warp-striped: warp w owns records [w * 512, (w + 1) * 512)
+    uint32_t hm[ITERS], pm[ITERS], im[ITERS];
+    uint32_t n_mine = 0;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const int i = (int)warp * PER_WARP + it * 32 + (int)lane;
+        const uint64_t r = S.rec[i];
+        const uint32_t umi = (uint32_t)r;
+        const bool pad = (umi >> 24) == 0xffu;
+        S.hp[i] = (uint16_t)(((umi >> 8) & 0xff00u) | ((uint32_t)(r >> 32) & 0xffu));
+        uint32_t prev = __shfl_up_sync(0xffffffffu, umi, 1);
+        if (lane == 0) prev = i > 0 ? (uint32_t)S.rec[i - 1] : prev_tile_umi;
+        const bool head = (i == 0 && base == cell_lo) || ((umi ^ prev) & 0xffffu) != 0u || pad != ((prev >> 24) == 0xffu);
+        hm[it] = __ballot_sync(0xffffffffu, head);
+        pm[it] = __ballot_sync(0xffffffffu, pad);
+        im[it] = __ballot_sync(0xffffffffu, !head && umi != prev);    // the run changes its high byte here
+        n_mine += __popc(hm[it]);
+    }
+    if (lane == 0) S.wcount[warp] = n_mine;
+    const uint32_t last_lo = (uint32_t)S.rec[CC_TILE - 1] & 0xffffu;    // low bits of the tile's last run (it may continue in the next tile)
+    __syncthreads();
+    uint32_t hbase = 0, n_heads = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) {
+        const uint32_t c = S.wcount[w];
+        hbase += w < (int)warp ? c : 0u;
+        n_heads += c;
+    }
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const uint32_t before = __popc(hm[it] & lt);
+        if ((hm[it] >> lane) & 1u) {
+            const int i = (int)warp * PER_WARP + it * 32 + (int)lane;
+            S.head[hbase + before] = (uint16_t)((uint32_t)i | (((pm[it] >> lane) & 1u) ? 0x8000u : 0u));
+        } else if ((im[it] >> lane) & 1u) {
+            const uint32_t run = hbase + before;                       // heads up to this record; its run is number run - 1
+            if (run > 0u) S.mixed[run - 1u] = 1;
+        }
+        hbase += __popc(hm[it]);
+    }
+    __syncthreads();
+    // ---- runs bucketed: mixed runs first (by length, longest first), then pure runs (the same), padding runs last
+    auto bucket = [&](uint32_t h) -> uint32_t {
+        const uint32_t hv = S.head[h];
+        const uint32_t hi = (h + 1 < n_heads) ? (uint32_t)(S.head[h + 1] & 0xfffu) : (uint32_t)CC_TILE;
+        const uint32_t len = hi - (hv & 0xfffu);
+        if (hv & 0x8000u) return 63u;
+        const bool mixed = h + 1 == n_heads || S.mixed[h] != 0;
+        return (mixed ? 0u : 31u) + 30u - (len < 30u ? len : 30u);
+    };
+    constexpr int BK_KEEP = 5;                                // a thread owns n_heads / 256 runs: their buckets (6 bits each) stay in a register
+    uint32_t bk = 0u;
+#pragma unroll
+    for (int j = 0; j < BK_KEEP; ++j) {
+        const uint32_t h = threadIdx.x + j * CC_THREADS;
+        if (h < n_heads) {
+            const uint32_t b = bucket(h);
+            bk |= b << (6 * j);
+            atomicAdd(&S.bkt[b], 1u);
+        }
+    }
+    for (uint32_t h = threadIdx.x + BK_KEEP * CC_THREADS; h < n_heads; h += CC_THREADS) atomicAdd(&S.bkt[bucket(h)], 1u);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const uint32_t c0 = S.bkt[threadIdx.x], c1 = S.bkt[32 + threadIdx.x];
+        uint32_t i0 = c0, i1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+            if (threadIdx.x >= (uint32_t)o) { i0 += t0; i1 += t1; }
+        }
+        const uint32_t tot0 = __shfl_sync(0xffffffffu, i0, 31);
+        S.bkt[threadIdx.x] = i0 - c0;
+        S.bkt[32 + threadIdx.x] = tot0 + i1 - c1;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < BK_KEEP; ++j) {
+        const uint32_t h = threadIdx.x + j * CC_THREADS;
+        if (h < n_heads) s_order[atomicAdd(&S.bkt[(bk >> (6 * j)) & 63u], 1u)] = (uint16_t)h;
+    }
+    for (uint32_t h = threadIdx.x + BK_KEEP * CC_THREADS; h < n_heads; h += CC_THREADS) s_order[atomicAdd(&S.bkt[bucket(h)], 1u)] = (uint16_t)h;
+    __syncthreads();
+    const uint32_t alt = alt_allele[cell0 + cell];
+    uint32_t n_fam = 0, n_tot = 0, n_var = 0;
+    for (uint32_t hh = threadIdx.x; hh < n_heads; hh += CC_THREADS) {
+        const uint32_t h = (uint32_t)s_order[hh];
+        const uint32_t hv = S.head[h];
+        if (hv & 0x8000u) continue;                                      // padding
+        const int lo = (int)(hv & 0xfffu);
+        const int hi = (h + 1 < n_heads) ? (int)(S.head[h + 1] & 0xfffu) : CC_TILE;
+        const int n_in = hi - lo;
+        if (h + 1 == n_heads) {
+            // the tile's last run: it may continue into the next tile(s) of the same cell
+            int64_t g_hi = base + CC_TILE;
+            for (; g_hi < cell_hi; ++g_hi) {
+                const uint32_t u = (uint32_t)rec[g_hi];
+                if ((u & 0xffffu) != last_lo || (u >> 24) == 0xffu) break;
+            }
+            const int len = n_in + (int)(g_hi - (base + CC_TILE));
+            const uint64_t* __restrict__ more = rec + base + CC_TILE - n_in;
+            auto hp_at = [&](int c) -> uint32_t {
+                if (c < n_in) return S.hp[lo + c];
+                const uint64_t r = more[c];
+                return (((uint32_t)r >> 8) & 0xff00u) | ((uint32_t)(r >> 32) & 0xffu);
+            };
+            uint32_t key1, n1, n2;
+            cp_sweep_first<MAJ>(len, hp_at, alt, S.wt, P, key1, n1, n2, n_fam, n_tot, n_var);
+            cp_sweep_chain<MAJ>(len, hp_at, hp_at(0) >> 8, n1, key1, false, alt, S.wt, P, n_fam, n_tot, n_var);
+        } else if (S.mixed[h] != 0) {
+            const uint16_t* const ph = S.hp + lo;
+            uint32_t key1, n1, n2;
+            cp_sweep_first<MAJ>(n_in, [&](int c) -> uint32_t { return ph[c]; }, alt, S.wt, P, key1, n1, n2, n_fam, n_tot, n_var);
+            // a third (fourth, ...) family: not swept here, where most lanes have none, but queued as (run, key) items
+            if (n1 != 256u) {
+                const uint32_t cnt = n2 != 256u ? 2u : 1u;
+                const uint32_t at = atomicAdd(&S.n_items, cnt);
+                s_items[at] = h | (n1 << 12) | (key1 << 20);
+                if (cnt == 2u) s_items[at + 1] = h | (n2 << 12) | (key1 << 20) | 0x10000000u;     // ... and whatever follows n2
+            }
+        } else {
+            FoldVote2<MAJ> v;
+            for (int c = 0; c < n_in; ++c) v.add(S.hp[lo + c], alt, S.wt);
+            int best = -1;
+            if (n_in >= P.min_family_size) best = v.result(P.consensus_threshold);
+            ++n_fam;
+            if (best >= 0) { ++n_tot; n_var += best == 1; }
+        }
+    }
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < S.n_items; w += CC_THREADS) {
+        const uint32_t it = s_items[w];
+        const uint32_t h = it & 0xfffu;
+        const int lo = (int)(S.head[h] & 0xfffu), n_in = (int)(S.head[h + 1] & 0xfffu) - lo;      // (never the tile's last run)
+        const uint16_t* const ph = S.hp + lo;
+        cp_sweep_chain<MAJ>(n_in, [&](int c) -> uint32_t { return ph[c]; }, (uint32_t)ph[0] >> 8, (it >> 12) & 0xffu, (it >> 20) & 0xffu,
+                            !(it & 0x10000000u), alt, S.wt, P, n_fam, n_tot, n_var);
+    }
+    n_fam = warp_sum(n_fam); n_tot = warp_sum(n_tot); n_var = warp_sum(n_var);
+    if (lane == 0) {
+        atomicAdd(&S.acc[0], (unsigned long long)n_fam);
+        atomicAdd(&S.acc[1], (unsigned long long)n_tot);
+        atomicAdd(&S.acc[2], (unsigned long long)n_var);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (S.acc[0]) atomicAdd(&o_fam[cell0 + cell], S.acc[0]);
+        if (S.acc[1]) atomicAdd(&o_tot[cell0 + cell], S.acc[1]);
+        if (S.acc[2]) atomicAdd(&o_var[cell0 + cell], S.acc[2]);
+    }
+}
+
 // ---------------------------------------------------------------- small cells: one block, no HBM round trip ----
 // Cells of at most SC_THREADS * ITEMS reads (the C5 panel: ~1250 reads per (sample, locus) cell) are not worth a
 // tile-padded trip through the global radix passes.  Their records sit back to back (compact layout, no padding);
@@ -881,7 +1167,19 @@ int32_t k5_collapse_counts_segmented(pmrd_ctx* ctx, uint64_t* d_rec, uint64_t* d
     const uint32_t run_mask = sort_bits >= 32 ? 0xffffffffu : ((1u << sort_bits) - 1u);
     const int grid = (int)(n_out / CC_TILE);
     const char* cb = getenv("PMRD_CC_BULK");                 // 0: the LSU-loaded form of the consensus kernel
-    if (sort_bits >= umi_bits && d_tile_cell && (!cb || atoi(cb) != 0)) {
+    if (sort_bits == 16 && umi_bits == 24 && d_tile_cell && (!cb || atoi(cb) != 0)) {
+        // two passes ordered the low 16 bits: the consensus kernel resolves the high byte inside its tile
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(cell_consensus_peel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CpSmem)));
+        PMRD_CUDA(ctx, cudaFuncSetAttribute(cell_consensus_peel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CpSmem)));
+        if (params->consensus_threshold > 0.5)
+            PMRD_LAUNCH_NAMED(ctx, "cell_consensus_peel_kernel", cell_consensus_peel_kernel<true>, grid, CC_THREADS, sizeof(CpSmem), sr, d_cell_tile_start,
+                              d_tile_cell, *params, cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot,
+                              (unsigned long long*)d_o_var);
+        else
+            PMRD_LAUNCH_NAMED(ctx, "cell_consensus_peel_kernel", cell_consensus_peel_kernel<false>, grid, CC_THREADS, sizeof(CpSmem), sr, d_cell_tile_start,
+                              d_tile_cell, *params, cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot,
+                              (unsigned long long*)d_o_var);
+    } else if (sort_bits >= umi_bits && d_tile_cell && (!cb || atoi(cb) != 0)) {
         PMRD_LAUNCH_NAMED(ctx, "cell_consensus_kernel<true>", cell_consensus_bulk_kernel, grid, CC_THREADS, 0, sr, d_cell_tile_start, d_tile_cell, *params,
                           cell0, d_alt_allele, (unsigned long long*)d_o_fam, (unsigned long long*)d_o_tot, (unsigned long long*)d_o_var);
     } else if (sort_bits >= umi_bits) {

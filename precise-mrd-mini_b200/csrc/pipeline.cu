@@ -128,7 +128,8 @@ struct pmrd_plan {
     int32_t test_type, alternative;
     int64_t n_cells = 0, n_reads = 0, n_fam = 0;
     int64_t max_reads = 0, max_fcap = 0, max_cells = 0;
-    int sort_bits = 24;   // UMI bits ordered by the radix sort; the consensus kernel resolves the rest (16: 2 passes, 24: 3)
+    int sort_bits = 16;   // UMI bits ordered by the radix sort; the consensus kernel resolves the rest inside its tile
+                          // (16: two passes + cell_consensus_peel_kernel, the default; 24: three passes + cell_consensus_bulk_kernel)
     uint64_t stream_id = 0;
     uint64_t seed = 0;    // the context seed the layout was sized for (read counts are a function of it)
     DevBuf keys, keys_tmp, pl, pl_tmp;
@@ -222,7 +223,7 @@ int32_t plan_create(pmrd_ctx* ctx, const int64_t* h_cell_id, const double* h_af,
     }
     P->stream_id = (uint64_t)h_cell_id[0];
     P->seed = ctx->seed;
-    if (const char* sb = getenv("PMRD_SORT_BITS")) {   // tuning knob: 16 (2 radix passes) or 24 (3 passes)
+    if (const char* sb = getenv("PMRD_SORT_BITS")) {   // 24: order every UMI bit (3 radix passes); 16: the default; 8: one pass (slow peel)
         const int v = atoi(sb);
         if (v == 8 || v == 16 || v == 24) P->sort_bits = v;
     }

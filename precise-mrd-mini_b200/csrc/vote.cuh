@@ -12,7 +12,11 @@ struct FoldVote2  {
     double total = 0.0, wref = 0.0, walt = 0.0;
     uint32_t first = 0;            // !MAJ: 1 = ref voted first, 2 = alt voted first (the dict-order tie-break of umi.py:166)
     __device__ __forceinline__ void add(uint32_t byte, uint32_t alt, const double* wt) {
-        const double w = wt[(byte >> 2) & 63u];              // 0.0 below the quality threshold: adds nothing
+        add_w(byte, alt, wt[(byte >> 2) & 63u]);             // 0.0 below the quality threshold: adds nothing
+    }
+    // the same with the weight handed in: +0.0 is the identity on these non-negative sums and sets no state, so a caller
+    // can pass 0.0 for a read that belongs to another family instead of branching around the call
+    __device__ __forceinline__ void add_w(uint32_t byte, uint32_t alt, double w) {
         const bool is_alt = (byte & 3u) == alt;
         total = __dadd_rn(total, w);
 #ifdef PMRD_FOLD2_SELECT

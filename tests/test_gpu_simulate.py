@@ -719,3 +719,41 @@ def test_fit_lod_matches_reference_golden(ctx, golden, monkeypatch):
     for i, n in enumerate(names):
         assert str(batch[i]) == str(ctx.fit_lod(af, g[f"{n}_hit"], 0.95, 60, 3 + i)), n
 
+
+
+def test_two_pass_sort_with_in_tile_peel_equals_the_full_sort(ctx, native, monkeypatch):
+    """Default plan: two radix passes order the low 16 UMI bits and cell_consensus_peel_kernel separates the families
+    that share a 16-bit run inside its tile.  PMRD_SORT_BITS=24 orders every bit (three passes) and votes whole runs;
+    PMRD_SORT_BITS=8 leaves 16 bits to the general peel.  All three must give the same table -- for cells big enough that a
+    third of the runs hold several families (50 000 families over 65 536 values), with duplicate UMIs (collision_rate),
+    runs that straddle tiles, padding, and under both vote forms (consensus_threshold above and below one half)."""
+    rng = np.random.default_rng(77)
+    nf = np.concatenate([[50000, 41000, 1, 0, 3, 4097], rng.integers(1, 30000, 34)])
+    c = len(nf)
+    cid = np.arange(c) * 7 + 2
+    af = np.tile([0.0, 0.02, 0.3, 0.001], c // 4)
+    for cthr, minfs in ((0.6, 3), (0.5, 1), (0.3, 2)):
+        out = {}
+        for bits in ("24", "16", "8"):
+            monkeypatch.setenv("PMRD_SORT_BITS", bits)
+            plan = native.Plan(ctx, cid, af, nf, _sp(native, family_model=1, collision_rate=2e-3), _umi(native, consensus_threshold=cthr, min_family_size=minfs))
+            plan.run()
+            ctx.profile_enable(True)
+            plan.run()
+            prof = ctx.profile_report()
+            ctx.profile_enable(False)
+            out[bits] = (plan.results(), prof)
+            plan.close()
+        assert "cell_consensus_peel_kernel" in out["16"][1] and "cell_consensus_peel_kernel" not in out["24"][1]
+        for bits in ("16", "8"):
+            for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+                assert (out["24"][0][k_] == out[bits][0][k_]).all(), (cthr, bits, k_)
+        assert out["24"][0]["n_variants"].sum() > 0
+    monkeypatch.delenv("PMRD_SORT_BITS")
+    plan = native.Plan(ctx, cid[:4], af[:4], nf[:4], _sp(native, family_model=1), _umi(native))
+    ctx.profile_enable(True)
+    plan.run()
+    prof = ctx.profile_report()
+    ctx.profile_enable(False)
+    plan.close()
+    assert "cell_consensus_peel_kernel" in prof                     # the default
