@@ -13,10 +13,11 @@ ROOT = Path(__file__).resolve().parent.parent
 BUILD = ROOT / "precise-mrd-mini_b200" / "build"
 HOT = {
     "radix_sort.o": ["rs_downsweep_direct_kernel", "rs_downsweep_staged_kernel", "rs_upsweep_tiles_kernel", "rs_cellscan_kernel", "rs_downsweep_kernel"],
-    "collapse.o": ["cell_consensus_bulk_kernel", "cell_consensus_kernel", "small_cell_kernel", "group_rows_kernel", "family_kernel"],
+    "collapse.o": ["cell_consensus_peel_kernel", "cell_consensus_bulk_kernel", "cell_consensus_kernel", "small_cell_kernel", "group_rows_kernel", "family_kernel"],
     "reads.o": ["reads_gen_kernel", "reads_size_kernel"],
     "fused.o": ["fused_cell_kernel", "fused_replay_kernel"],
     "pvalues.o": ["pvalues_kernel", "bh_group_kernel"],
+    "lod.o": ["lod_fit_warp_kernel"],
 }
 MARK = ["UBLKCP", "SYNCS", "VOTE", "R2P", "ATOMS", "ATOMG", "RED", "DADD", "DFMA", "DMUL", "IMAD.WIDE", "LOP3", "SHFL", "LDS", "STS", "LDG", "STG",
         "MATCH", "BAR", "POPC", "STL", "LDL"]
