@@ -192,7 +192,9 @@ int32_t pmrd_collapse_reads(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_
                             pmrd_family_table* h_fam, int64_t capacity_f, int64_t* n_families,
                             pmrd_group_table* h_grp, int64_t capacity_g, int64_t* n_groups);
 /* Device-resident variant: d_keys/d_payload are clobbered (used as sort ping-pong with
- * the *_tmp buffers).  n_families/n_groups are host pointers written after a sync. */
+ * the *_tmp buffers).  n_families/n_groups are host pointers written after a sync.
+ * d_keys and d_keys_tmp must be 16-byte aligned (any cudaMalloc'd array is; a view that starts
+ * at an odd element is refused with PMRD_ERR_ARG): the kernels read keys two at a time. */
 int32_t pmrd_collapse_reads_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload,
                                 uint64_t* d_keys_tmp, uint32_t* d_payload_tmp, int64_t n_reads,
                                 const pmrd_umi_params* params, pmrd_family_table* d_fam,

@@ -384,6 +384,39 @@ def test_collapse_external_reads_group_major_path(ctx, native, monkeypatch):
         assert len(fa["key"]) > 700_000 and (np.diff(fa["key"].astype(np.int64)) > 0).all()       # sorted by (group, UMI), no duplicates
 
 
+def test_collapse_reads_dev_on_device_arrays_odd_length_and_alignment_contract(ctx, native):
+    """pmrd_collapse_reads_dev on a caller's device arrays: an odd read count (the tail of the wide run-boundary loads) gives
+    the oracle's table; key arrays that are not 16-byte aligned (a view one element into an allocation) are refused loudly,
+    as include/pmrd.h states for pmrd_collapse_reads_dev, instead of being read with misaligned vector loads."""
+    torch = pytest.importorskip("torch")
+    from oracle import cport
+
+    rng = np.random.default_rng(5)
+    keys, pl = _panel_reads(rng, 200_001, 900, 60)
+    n = len(keys)
+    P = _params(native, min_family_size=3, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6, mode=native.MODE_WEIGHTED)
+    dev = torch.device("cuda", 0)
+    kbuf, ktmp = torch.zeros(n + 1, dtype=torch.int64, device=dev), torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    pbuf, ptmp = torch.zeros(n + 1, dtype=torch.int32, device=dev), torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    gcap = 900 + 16
+    grp_t = {"group": torch.zeros(gcap, dtype=torch.int32, device=dev), "family_count": torch.zeros(gcap, dtype=torch.int32, device=dev),
+             "consensus_count": torch.zeros(gcap * 4, dtype=torch.int32, device=dev), "alt_count": torch.zeros(gcap, dtype=torch.int64, device=dev),
+             "total_count": torch.zeros(gcap, dtype=torch.int64, device=dev)}
+    grp_p = {k: v.data_ptr() for k, v in grp_t.items()}
+    kbuf[:n].copy_(torch.from_numpy(keys.view(np.int64)))
+    pbuf[:n].copy_(torch.from_numpy(pl.view(np.int32)))
+    torch.cuda.synchronize()
+    nf, ng = ctx.collapse_reads_dev(kbuf.data_ptr(), pbuf.data_ptr(), ktmp.data_ptr(), ptmp.data_ptr(), n, P, None, 0, grp_p, gcap)
+    torch.cuda.synchronize()
+    og = cport.collapse_groups(keys, pl, 900, 3, 1000, 20, 0.6)
+    assert nf == og["total_families"] and ng == 900
+    assert (grp_t["family_count"][:ng].cpu().numpy().astype(np.uint32) == og["family_count"]).all()
+    assert (grp_t["consensus_count"][:ng * 4].cpu().numpy().astype(np.uint32).reshape(ng, 4) == og["consensus_count"]).all()
+    assert kbuf[1:].data_ptr() % 16 == 8
+    with pytest.raises(native.NativeError, match="16-byte aligned"):
+        ctx.collapse_reads_dev(kbuf[1:].data_ptr(), pbuf.data_ptr(), ktmp[1:].data_ptr(), ptmp.data_ptr(), n, P, None, 0, grp_p, gcap)
+
+
 @pytest.mark.parametrize("d", [1, 2])
 def test_collapse_gb_greedy_clusters_vs_reference(ctx, golden, native, d):
     """K6 greedy (max_edit_distance > 0, the reference's default): the device clusters equal the reference's
