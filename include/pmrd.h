@@ -201,6 +201,21 @@ int32_t pmrd_collapse_reads_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pay
                                 int64_t capacity_f, int64_t* n_families, pmrd_group_table* d_grp,
                                 int64_t capacity_g, int64_t* n_groups);
 
+/* External reads held by SEVERAL GPUs (one process per GPU): the exchange step of SURVEY.md section 8(e).
+ * The reference collapses one process's reads (umi.py:205-285, lib.rs:7-109); with the reads of a sample striped
+ * over 2^k ranks every group (locus) gets the owner rank  group mod 2^k.
+ *   pmrd_owner_partition_dev: STABLE partition of this rank's reads into one contiguous run per owner (owner 0 first);
+ *     h_counts[r] = reads bound for rank r; *in_tmp = 1 when the result sits in the *_tmp arrays.  The host then moves the
+ *     runs (torch.distributed all_to_all_single over NCCL: INTEGRATION.md section 5); the runs arrive in source-rank order,
+ *     so an owner sees the reads of a family in the order of the concatenated input and its table is the single-GPU one.
+ *   pmrd_owner_rekey_dev: after the exchange a rank holds only groups = rank (mod 2^k); group >>= k makes the ids dense
+ *     again for pmrd_collapse_reads_dev (global id = local << k | rank).
+ * 16-byte aligned key arrays, as for pmrd_collapse_reads_dev. */
+int32_t pmrd_owner_partition_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp,
+                                 uint32_t* d_payload_tmp, int64_t n_reads, int32_t log2_world, int64_t* h_counts,
+                                 int32_t* in_tmp);
+int32_t pmrd_owner_rekey_dev(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n_reads, int32_t log2_world);
+
 /* K4 on the plan's cell-major layout: cell c = whole 4096-record tiles [tile_start[c], tile_start[c+1]) of packed 8-byte records;
  * every cell is sorted on its own, stable LSD over the low key_bits (<= 32) bits, the bits above are carried along -- the
  * staged / direct scatter kernels the fused plan sorts its generated reads with (umi.py:97-115 grouping), exposed so that

@@ -423,6 +423,17 @@ int32_t pmrd_collapse_reads_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pay
                        d_grp, capacity_g, n_groups);
 }
 
+int32_t pmrd_owner_partition_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp, uint32_t* d_payload_tmp,
+                                 int64_t n_reads, int32_t log2_world, int64_t* h_counts, int32_t* in_tmp) {
+    ENTER(ctx);
+    return k18_owner_partition(ctx, d_keys, d_payload, d_keys_tmp, d_payload_tmp, n_reads, log2_world, h_counts, in_tmp);
+}
+
+int32_t pmrd_owner_rekey_dev(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n_reads, int32_t log2_world) {
+    ENTER(ctx);
+    return k18_owner_rekey(ctx, d_keys, n_reads, log2_world);
+}
+
 int32_t pmrd_collapse_reads(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_t* h_payload, int64_t n_reads,
                             const pmrd_umi_params* params, pmrd_family_table* h_fam, int64_t capacity_f,
                             int64_t* n_families, pmrd_group_table* h_grp, int64_t capacity_g, int64_t* n_groups) {

@@ -35,3 +35,8 @@ int32_t k12_bootstrap_metrics(pmrd_ctx* ctx, const uint8_t* d_y, const double* d
 // simulate.cu
 int32_t k1_simulate_cells(pmrd_ctx* ctx, const int64_t* d_cell_id, const double* d_af, const int64_t* d_depth,
                           const double* d_bg_mult, int64_t n_cells, int32_t max_family_size, const pmrd_cell_table* d_out);
+
+// exchange.cu (K18): external reads held by several GPUs -- stable cut into one run per owner rank, dense ids after the exchange
+int32_t k18_owner_partition(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp, uint32_t* d_payload_tmp,
+                            int64_t n, int32_t log2_world, int64_t* h_counts, int32_t* in_tmp);
+int32_t k18_owner_rekey(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n, int32_t log2_world);

@@ -316,6 +316,20 @@ class Context:
             C.byref(ng) if d_grp else None))
         return nf.value, ng.value
 
+    def owner_partition_dev(self, d_keys: int, d_payload: int, d_keys_tmp: int, d_payload_tmp: int, n: int, log2_world: int):
+        """``pmrd_owner_partition_dev``: stable cut of this rank's reads (DEVICE pointers) into one run per owner rank
+        (``group mod 2**log2_world``).  Returns ``(counts, in_tmp)``: reads bound for each rank, and whether the
+        partitioned reads sit in the ``*_tmp`` arrays."""
+        counts = (C.c_int64 * (1 << log2_world))()
+        in_tmp = C.c_int32(0)
+        self._check(self.lib.pmrd_owner_partition_dev(self.h, C.c_void_p(d_keys), C.c_void_p(d_payload), C.c_void_p(d_keys_tmp),
+                                                      C.c_void_p(d_payload_tmp), C.c_int64(n), C.c_int32(log2_world), counts, C.byref(in_tmp)))
+        return [int(c) for c in counts], bool(in_tmp.value)
+
+    def owner_rekey_dev(self, d_keys: int, n: int, log2_world: int) -> None:
+        """``pmrd_owner_rekey_dev``: ``group >>= log2_world`` on a DEVICE key array (dense ids after the exchange)."""
+        self._check(self.lib.pmrd_owner_rekey_dev(self.h, C.c_void_p(d_keys), C.c_int64(n), C.c_int32(log2_world)))
+
     def umi_hamming(self, a, b, umi_len: int) -> np.ndarray:
         a = _arr(a, np.uint32)
         b = _arr(b, np.uint32)

@@ -1,11 +1,17 @@
 """Multi-GPU plumbing: one process per GPU, cells sharded across ranks, one small all-gather.
 
-The path has no data-path exchange: (AF, depth, replicate) cells are independent and every
+The generated grids have no data-path exchange: (AF, depth, replicate) cells are independent and every
 Philox stream is keyed by the GLOBAL cell id, so a cell gives the same counts whichever rank runs
 it.  A rank simulates / collapses / counts its own cells; the only collective is
 an all-gather of the per-cell ``(n_total, n_variants, n_families, n_reads)`` rows (32 B per
 cell: 60 KB for the eval-lod grid), after which every rank holds the full table and runs the
-error model, the tail tests and BH redundantly -- exactly what ``call_mrd`` does on one process."""
+error model, the tail tests and BH redundantly -- exactly what ``call_mrd`` does on one process.
+
+EXTERNAL reads are the one case with a real exchange (third bullet): when the reads of a sample are
+striped over the ranks in arrival order, the families of a locus are spread over all of them.
+``collapse_reads_exchanged`` gives every locus an owner rank, cuts each rank's reads into one run per owner on the
+device (``pmrd_owner_partition_dev``), moves the runs with one all-to-all over NCCL and lets each owner collapse what
+it received with the single-GPU kernels."""
 from __future__ import annotations
 
 from typing import Dict, Optional, Sequence, Tuple
@@ -125,3 +131,123 @@ def run_cells_sharded(config, cell_id, allele_fraction, n_families, neg_af_max: 
                                    alternative, float(st["alpha"])))
         out["variant_call"] = out["significant"]
     return out
+
+
+class _DeviceExchangeOps:
+    """The exchange's device steps on torch CUDA tensors, through the C-ABI (``csrc/exchange.cu``, ``collapse.cu``)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+
+    @staticmethod
+    def _after_torch(t):
+        # torch (copies, NCCL) wrote these arrays on ITS stream; the library launches on the context's
+        import torch
+
+        torch.cuda.current_stream(t.device).synchronize()
+
+    def owner_partition(self, keys, payload, keys_tmp, payload_tmp, log2_world):
+        self._after_torch(keys)
+        return self.ctx.owner_partition_dev(keys.data_ptr(), payload.data_ptr(), keys_tmp.data_ptr(), payload_tmp.data_ptr(),
+                                            keys.numel(), log2_world)
+
+    def owner_rekey(self, keys, log2_world):
+        self._after_torch(keys)
+        self.ctx.owner_rekey_dev(keys.data_ptr(), keys.numel(), log2_world)
+
+    def collapse_groups(self, keys, payload, keys_tmp, payload_tmp, params, capacity_g):
+        """Per-group table of the reads in ``keys`` / ``payload`` (clobbered): ``(n_families, {column: ndarray})``."""
+        import torch
+
+        dev = keys.device
+        grp = {"group": torch.empty(capacity_g, dtype=torch.int32, device=dev), "family_count": torch.empty(capacity_g, dtype=torch.int32, device=dev),
+               "consensus_count": torch.empty(capacity_g * 4, dtype=torch.int32, device=dev),
+               "alt_count": torch.empty(capacity_g, dtype=torch.int64, device=dev), "total_count": torch.empty(capacity_g, dtype=torch.int64, device=dev)}
+        nf, ng = self.ctx.collapse_reads_dev(keys.data_ptr(), payload.data_ptr(), keys_tmp.data_ptr(), payload_tmp.data_ptr(), keys.numel(),
+                                             params, None, 0, {k: v.data_ptr() for k, v in grp.items()}, capacity_g)
+        torch.cuda.synchronize(dev)
+        out = {"group": grp["group"][:ng].cpu().numpy().astype(np.int64), "family_count": grp["family_count"][:ng].cpu().numpy().astype(np.uint32),
+               "consensus_count": grp["consensus_count"][:ng * 4].cpu().numpy().astype(np.uint32).reshape(ng, 4)}
+        return nf, out
+
+
+def exchange_splits(send_counts: Sequence[int], group=None, device=None) -> Tuple[list, list]:
+    """``(send, recv)`` split sizes of the all-to-all: ``recv[r]`` = what rank ``r`` cut off for this rank."""
+    import torch
+    import torch.distributed as dist
+
+    send = torch.tensor(list(send_counts), dtype=torch.int64, device=device)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    return [int(v) for v in send.tolist()], [int(v) for v in recv.tolist()]
+
+
+def collapse_reads_exchanged(ctx, keys, payload, params, n_ids: int, group=None, ops=None, gather: bool = True,
+                             timings: Optional[dict] = None) -> Dict[str, np.ndarray]:
+    """``Context.collapse_reads(..., want_families=False)`` for reads held by ALL ranks of the process group.
+
+    ``keys`` (int64: ``group << 32 | umi``) and ``payload`` (int32) are this rank's reads as torch tensors on its GPU,
+    in arrival order; group ids are dense, ``< n_ids``.  Owner of a group = ``group mod world`` (world a power of two).
+    Returns the per-group table (``group``, ``family_count``, ``consensus_count``) and ``n_families`` -- of ALL groups on
+    every rank when ``gather`` (one all-gather of 24 B per group), else of the rank's own groups -- equal, bit for bit,
+    to the single-GPU table of the ranks' reads concatenated in rank order.  Replaces umi.py:205-285 for that case.
+
+    ``ops`` injects the device steps (tests run the exchange logic on CPU ranks over gloo with a NumPy double); without
+    it the reads must be CUDA tensors and the steps are the library's kernels."""
+    import torch
+    import torch.distributed as dist
+
+    on = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if on else 0
+    world = dist.get_world_size(group) if on else 1
+    if world & (world - 1):
+        raise ValueError(f"collapse_reads_exchanged needs a power-of-two number of ranks, not {world}")
+    log2w = world.bit_length() - 1
+    if ops is None:
+        if not (keys.is_cuda and payload.is_cuda):
+            raise RuntimeError("collapse_reads_exchanged: reads must be CUDA tensors (the exchange and the collapse run on the GPU)")
+        ops = _DeviceExchangeOps(ctx)
+    n = int(keys.numel())
+    keys_tmp, payload_tmp = torch.empty_like(keys), torch.empty_like(payload)
+    ev = None
+    if timings is not None and keys.is_cuda:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+    counts, in_tmp = ops.owner_partition(keys, payload, keys_tmp, payload_tmp, log2w) if n else ([0] * world, False)
+    sk, sp = (keys_tmp, payload_tmp) if in_tmp else (keys, payload)
+    if ev:
+        ev[1].record()
+    if world > 1:
+        send, recv = exchange_splits(counts, group, keys.device)
+        n_recv = sum(recv)
+        rk, rp = torch.empty(n_recv, dtype=keys.dtype, device=keys.device), torch.empty(n_recv, dtype=payload.dtype, device=keys.device)
+        dist.all_to_all_single(rk, sk[:n], output_split_sizes=recv, input_split_sizes=send, group=group)
+        dist.all_to_all_single(rp, sp[:n], output_split_sizes=recv, input_split_sizes=send, group=group)
+    else:
+        rk, rp, n_recv = sk, sp, n
+    if ev:
+        ev[2].record()
+    n_local_ids = (int(n_ids) - rank + world - 1) // world if n_ids > rank else 0
+    if n_recv:
+        ops.owner_rekey(rk, log2w)
+        rkt, rpt = torch.empty_like(rk), torch.empty_like(rp)
+        nf, tab = ops.collapse_groups(rk, rp, rkt, rpt, params, n_local_ids + 16)
+    else:
+        nf, tab = 0, {"group": np.zeros(0, np.int64), "family_count": np.zeros(0, np.uint32), "consensus_count": np.zeros((0, 4), np.uint32)}
+    if ev:
+        ev[3].record()
+        torch.cuda.synchronize(keys.device)
+        timings.update({"partition_ms": ev[0].elapsed_time(ev[1]), "exchange_ms": ev[1].elapsed_time(ev[2]), "collapse_ms": ev[2].elapsed_time(ev[3]),
+                        "sent_reads": n - counts[rank] if n else 0, "received_reads": n_recv})
+    tab["group"] = tab["group"] * world + rank                                  # local id -> global id
+    if not gather or world == 1:
+        tab["n_families"] = int(nf)
+        return tab
+    rows = np.concatenate([tab["family_count"].astype(np.int64)[:, None], tab["consensus_count"].astype(np.int64),
+                           np.ones((len(tab["group"]), 1), np.int64)], axis=1)   # last column: the group is present
+    full = all_gather_rows(tab["group"], rows, int(n_ids), group)
+    present = full[:, 5] != 0
+    tot = torch.tensor([int(nf)], dtype=torch.int64, device=keys.device)
+    dist.all_reduce(tot, group=group)
+    return {"group": np.flatnonzero(present).astype(np.int64), "family_count": full[present, 0].astype(np.uint32),
+            "consensus_count": full[present, 1:5].astype(np.uint32), "n_families": int(tot.item())}

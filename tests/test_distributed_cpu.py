@@ -77,3 +77,101 @@ def test_sharded_grid_equals_single_rank_gloo():
         assert n_var == ((cid * 13) % 11).tolist() and n_reads == (depth * 5 + cid).tolist()
         assert neg == (af <= 1e-4).tolist()
     assert res[0][1] + res[1][1] == len(cid) and min(res[0][1], res[1][1]) > 0   # the work really was split
+
+
+# ---------------------------------------------------------------- the exchange of external reads
+class _NumpyExchangeOps:
+    """Test double of the exchange's device steps (csrc/exchange.cu, the group-major collapse) on CPU tensors: NumPy
+    for the cut and the re-keying, the C oracle for the per-group table."""
+
+    def owner_partition(self, keys, payload, keys_tmp, payload_tmp, log2_world):
+        k, p = keys.numpy().view(np.uint64), payload.numpy().view(np.uint32)
+        dest = ((k >> np.uint64(32)) & np.uint64((1 << log2_world) - 1)).astype(np.int64)
+        order = np.argsort(dest, kind="stable")
+        keys_tmp.numpy().view(np.uint64)[:] = k[order]
+        payload_tmp.numpy().view(np.uint32)[:] = p[order]
+        return np.bincount(dest, minlength=1 << log2_world).tolist(), True
+
+    def owner_rekey(self, keys, log2_world):
+        k = keys.numpy().view(np.uint64)
+        k[:] = (((k >> np.uint64(32)) >> np.uint64(log2_world)) << np.uint64(32)) | (k & np.uint64(0xFFFFFFFF))
+
+    def collapse_groups(self, keys, payload, keys_tmp, payload_tmp, params, capacity_g):
+        from oracle import cport
+
+        k, p = keys.numpy().view(np.uint64), payload.numpy().view(np.uint32)
+        og = cport.collapse_groups(k, p, capacity_g, *params)
+        ids = np.unique((k >> np.uint64(32)).astype(np.int64))
+        return og["total_families"], {"group": ids, "family_count": og["family_count"][ids], "consensus_count": og["consensus_count"][ids]}
+
+
+def _striped_reads(rank, n, n_ids):
+    rng = np.random.default_rng(100 + rank)
+    g = rng.integers(0, n_ids, n, dtype=np.uint64)
+    g[g % np.uint64(11) == 3] += np.uint64(1)                              # some ids stay empty
+    umi = rng.integers(0, 40, n, dtype=np.uint64) * np.uint64(2654435761) % np.uint64(1 << 24)
+    q = rng.choice([5, 10, 20, 30, 30, 37, 40], n).astype(np.uint32)
+    pl = (rng.integers(0, 4, n).astype(np.uint32)) | (q << np.uint32(2))
+    return (g << np.uint64(32)) | umi, pl
+
+
+def _exchange_worker(rank, world, port, q, n_ids):
+    sys.path.insert(0, str(ROOT / "precise-mrd-mini_b200"))
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+
+    from precise_mrd.distributed import collapse_reads_exchanged
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    keys, pl = _striped_reads(rank, 30_000 + 1000 * rank, n_ids)
+    tk, tp = torch.from_numpy(keys.view(np.int64).copy()), torch.from_numpy(pl.view(np.int32).copy())
+    full = collapse_reads_exchanged(None, tk, tp, (3, 1000, 20, 0.6), n_ids, ops=_NumpyExchangeOps())
+    tk, tp = torch.from_numpy(keys.view(np.int64).copy()), torch.from_numpy(pl.view(np.int32).copy())
+    own = collapse_reads_exchanged(None, tk, tp, (3, 1000, 20, 0.6), n_ids, ops=_NumpyExchangeOps(), gather=False)
+    q.put((rank, {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in full.items()},
+           {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in own.items()}))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_exchanged_collapse_equals_the_collapse_of_the_concatenated_reads_gloo(world):
+    """Reads of one sample striped over the ranks: owner cut -> all-to-all -> owner-side collapse must give the table of
+    the ranks' reads concatenated in rank order (the family vote adds in read order, so the ORDER the runs arrive in
+    matters), on every rank; with gather=False each rank holds exactly its own groups."""
+    import torch.multiprocessing as mp
+
+    sys.path.insert(0, str(ROOT))
+    from oracle import cport
+
+    n_ids, port = 1000, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q, n_ids)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    parts = [_striped_reads(r, 30_000 + 1000 * r, n_ids) for r in range(world)]
+    keys, pl = np.concatenate([a for a, _ in parts]), np.concatenate([b for _, b in parts])
+    og = cport.collapse_groups(keys, pl, n_ids + 1, 3, 1000, 20, 0.6)
+    ids = np.unique((keys >> np.uint64(32)).astype(np.int64))
+    for rank, full, own in res:
+        assert full["group"] == ids.tolist() and full["n_families"] == og["total_families"]
+        assert full["family_count"] == og["family_count"][ids].tolist()
+        assert full["consensus_count"] == og["consensus_count"][ids].tolist()
+        mine = ids[ids % world == rank]
+        assert own["group"] == mine.tolist() and own["family_count"] == og["family_count"][mine].tolist()
+    assert sum(o["n_families"] for _, _, o in res) == og["total_families"]
+
+
+def test_exchanged_collapse_refuses_three_ranks_and_cpu_reads_without_ops():
+    import torch
+
+    from precise_mrd.distributed import collapse_reads_exchanged
+
+    with pytest.raises(RuntimeError, match="CUDA tensors"):           # no CPU fallback: the product path is the GPU's
+        collapse_reads_exchanged(None, torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int32), None, 8)

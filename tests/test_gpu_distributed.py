@@ -83,3 +83,86 @@ def test_lod_grid_on_two_gpus_equals_one_gpu(native):
             assert (np.asarray(out[k]) == one[k]).all(), (rank, k)
         assert out["mean_error_rate"] == one["mean_error_rate"]
         assert str(lod) == str(want_lod)          # (NaN-safe: an all-zero hit vector fits to NaN on both)
+
+
+# ---------------------------------------------------------------- the exchange of external reads
+def _striped_reads(rank, n, n_ids):
+    rng = np.random.default_rng(100 + rank)
+    g = rng.integers(0, n_ids, n, dtype=np.uint64)
+    g[g % np.uint64(11) == 3] += np.uint64(1)                              # some ids stay empty
+    umi = rng.integers(0, 60, n, dtype=np.uint64) * np.uint64(2654435761) % np.uint64(1 << 24)
+    q = rng.choice([5, 10, 20, 30, 30, 37, 40], n).astype(np.uint32)
+    pl = (rng.integers(0, 4, n).astype(np.uint32)) | (q << np.uint32(2)) | (rng.integers(0, 1 << 20, n).astype(np.uint32) << np.uint32(8))
+    return (g << np.uint64(32)) | umi, pl
+
+
+def _exchange_worker(rank, world, port, q, n_ids, n_per_rank):
+    sys.path.insert(0, str(ROOT / "precise-mrd-mini_b200"))
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+
+    from precise_mrd import _native as nv
+    from precise_mrd.distributed import collapse_reads_exchanged
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    ctx = nv.Context(device=rank, seed=7)
+    P = nv.UmiParams(min_family_size=3, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6, mode=nv.MODE_WEIGHTED,
+                     cluster=nv.CLUSTER_EXACT, max_distance=0, umi_len=12)
+    keys, pl = _striped_reads(rank, n_per_rank + 1001 * rank, n_ids)
+    dev = torch.device("cuda", rank)
+    out = {}
+    for gather in (True, False):
+        tk, tp = torch.from_numpy(keys.view(np.int64)).to(dev), torch.from_numpy(pl.view(np.int32)).to(dev)
+        t = {}
+        tab = collapse_reads_exchanged(ctx, tk, tp, P, n_ids, gather=gather, timings=t)
+        out[gather] = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in tab.items()}
+        out[gather]["timings"] = t
+    launched = ctx.launch_count
+    q.put((rank, out[True], out[False], launched))
+    ctx.close() if hasattr(ctx, "close") else None
+    dist.destroy_process_group()
+
+
+def test_exchanged_collapse_on_gpus_equals_one_gpu(native, ctx):
+    """External reads of one sample striped over 2 (and, when the box has them, 4) GPUs: owner cut on the device
+    (pmrd_owner_partition_dev) -> all-to-all over NCCL -> pmrd_collapse_reads_dev at the owner.  Every rank's gathered
+    table must equal the single-GPU table of the reads concatenated in rank order, which in turn equals the C oracle's."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+
+    from oracle import cport
+
+    n_ids, n_per_rank = 5000, 400_000
+    for world in [w for w in (2, 4) if torch.cuda.device_count() >= w]:
+        port = _free_port()
+        mpc = mp.get_context("spawn")
+        q = mpc.Queue()
+        procs = [mpc.Process(target=_exchange_worker, args=(r, world, port, q, n_ids, n_per_rank)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = sorted((q.get(timeout=600) for _ in procs), key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+        parts = [_striped_reads(r, n_per_rank + 1001 * r, n_ids) for r in range(world)]
+        keys, pl = np.concatenate([a for a, _ in parts]), np.concatenate([b for _, b in parts])
+        P = native.UmiParams(min_family_size=3, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6, mode=native.MODE_WEIGHTED,
+                             cluster=native.CLUSTER_EXACT, max_distance=0, umi_len=12)
+        info, one = ctx.collapse_reads(keys, pl, P, want_families=False)
+        og = cport.collapse_groups(keys, pl, n_ids + 1, 3, 1000, 20, 0.6)
+        assert (one["family_count"] == og["family_count"][one["group"]]).all() and info["n_families"] == og["total_families"]
+        for rank, full, own, launched in res:
+            assert full["group"] == one["group"].tolist() and full["n_families"] == info["n_families"], (world, rank)
+            assert full["family_count"] == one["family_count"].tolist()
+            assert full["consensus_count"] == one["consensus_count"].tolist()
+            mine = one["group"] % world == rank
+            assert own["group"] == one["group"][mine].tolist() and own["family_count"] == one["family_count"][mine].tolist()
+            t = full["timings"]
+            assert t["received_reads"] > 0 and t["sent_reads"] > 0 and launched > 0       # reads really changed hands, our kernels ran
+        assert sum(o["n_families"] for _, _, o, _ in res) == info["n_families"]
