@@ -411,6 +411,12 @@ def run_external(args, rank, world, local_rank, emit):
     e2e_fam_s = time.perf_counter() - t1
     assert len(fam_h["key"]) == nf
 
+    # ---- N > 1: the SAME reads taken as stripes of ONE sample -> loci shared by all ranks -> the exchange of SURVEY.md §8e
+    # (owner cut on the device, all-to-all over NCCL, owner-side collapse; precise_mrd.distributed.collapse_reads_exchanged)
+    exchange = None
+    if world > 1:
+        exchange = exchange_leg(ctx, args, k0, p0, P, n, n_loci, rank, world, local_rank, barrier)
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -448,6 +454,8 @@ def run_external(args, rank, world, local_rank, emit):
                                   "frac": value / world * EXT_B_READ / 1e9 / peak},
             "kernels_ms_per_step": kms, "clocks": clocks.summary(), "reference_class": "cpu-port",
         }
+        if exchange is not None:
+            line["exchange"] = exchange
         if world == 1 and not args.no_cpu_baseline:
             threads = host_threads()
             r, dt = external_cpu(keys, payload, n_loci, cfg, threads)
@@ -461,6 +469,65 @@ def run_external(args, rank, world, local_rank, emit):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def exchange_leg(ctx, args, k0, p0, P, n, n_loci, rank, world, local_rank, barrier):
+    """Reads of one sample striped over the ranks (each rank's 1.25e8 reads cover ALL loci): every step cuts them by owner
+    rank, moves 1 - 1/N of them over NVLink and collapses at the owner.  Device time per step = max over ranks (CUDA events
+    around the whole call); first a small instance is checked against the single-GPU table of the concatenated reads."""
+    import torch
+    import torch.distributed as dist
+
+    from precise_mrd.distributed import collapse_reads_exchanged
+
+    dev = torch.device("cuda", local_rank)
+    # (1) equality on a small instance: rank 0 collapses the concatenation on its own
+    ns, ids = 200_000, 4096
+    ks, ps = external_reads(1000 + rank, ns, ids)
+    tk, tp = torch.from_numpy(ks.view(np.int64)).to(dev), torch.from_numpy(ps.view(np.int32)).to(dev)
+    allk = [torch.empty_like(tk) for _ in range(world)]
+    allp = [torch.empty_like(tp) for _ in range(world)]
+    dist.all_gather(allk, tk)
+    dist.all_gather(allp, tp)
+    got = collapse_reads_exchanged(ctx, tk.clone(), tp.clone(), P, ids)
+    ok = torch.ones(1, dtype=torch.int64, device=dev)
+    if rank == 0:
+        info, one = ctx.collapse_reads(torch.cat(allk).cpu().numpy().view(np.uint64), torch.cat(allp).cpu().numpy().view(np.uint32), P, want_families=False)
+        same = (got["n_families"] == info["n_families"] and (got["group"] == one["group"]).all() and (got["family_count"] == one["family_count"]).all()
+                and (got["consensus_count"] == one["consensus_count"]).all())
+        ok[0] = 1 if same else 0
+    dist.broadcast(ok, 0)
+    # (2) the full-size exchange, timed
+    parts = {"partition_ms": 0.0, "exchange_ms": 0.0, "collapse_ms": 0.0}
+    total_ms, fams, sent = 0.0, 0, 0
+    for it in range(max(args.warmup, 3) + args.steps):
+        dk, dp = k0.clone(), p0.clone()                              # the call clobbers its inputs: restored untimed
+        barrier()
+        tm = {}
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tab = collapse_reads_exchanged(ctx, dk, dp, P, n_loci, gather=False, timings=tm)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= max(args.warmup, 3):
+            total_ms += e0.elapsed_time(e1)
+            for k_ in parts:
+                parts[k_] += tm[k_]
+            fams, sent = tab["n_families"], tm["sent_reads"]
+        del dk, dp
+    t = torch.tensor([total_ms] + [parts[k_] for k_ in ("partition_ms", "exchange_ms", "collapse_ms")], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    f = torch.tensor([fams, sent], dtype=torch.int64, device=dev)
+    dist.all_reduce(f)
+    tot, pm, xm, cm = [float(x) / args.steps for x in t.tolist()]
+    return {"what": "the ranks' reads as stripes of ONE sample: owner cut (pmrd_owner_partition_dev) -> all_to_all_single over NCCL -> "
+                    "pmrd_owner_rekey_dev + pmrd_collapse_reads_dev at the owner; per-locus table of all N x 1.25e8 reads, rows held by their owners",
+            "value": float(n) * world / (tot * 1e-3), "unit": UNIT, "ms_per_step": tot, "scaling": "weak",
+            "max_over_ranks_ms": {"owner_partition": pm, "all_to_all": xm, "owner_collapse": cm},
+            "reads_sent_per_step": int(f[1].item()), "bytes_sent_per_step": int(f[1].item()) * 12,
+            "all_to_all_GBps_per_gpu": (int(f[1].item()) / world * 12 / 1e9) / (xm * 1e-3) if xm > 0 else None,
+            "families": int(f[0].item()), "exchanged_equals_single": bool(ok.item()),
+            "equality_instance": f"{ns} reads per rank over {ids} loci vs rank 0's single-GPU table of the concatenation"}
 
 
 # ------------------------------------------------------------------------------- reference arm

@@ -216,6 +216,28 @@ int32_t pmrd_owner_partition_dev(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_pa
                                  int32_t* in_tmp);
 int32_t pmrd_owner_rekey_dev(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n_reads, int32_t log2_world);
 
+/* The same exchange as ONE kernel over peer memory (up to 8 ranks of one NVSwitch node): instead of a partitioned copy that
+ * NCCL then moves, the cut stores every read straight into its owner's receive arrays over NVLink.
+ *   pmrd_peer_alloc / pmrd_peer_free: a receive array other processes can map (cudaMalloc + cudaIpcGetMemHandle); the
+ *     64-byte handle is what the ranks exchange.  pmrd_peer_open / pmrd_peer_close: map / unmap a peer's array.
+ *   pmrd_owner_tiles_dev: per 4096-read tile, where the tile's reads of each owner start inside this rank's run for that
+ *     owner: d_tile_off[owner * n_tiles + tile], n_tiles = ceil(n_reads / 4096); h_counts[r] = reads bound for rank r.
+ *   pmrd_owner_scatter_peer_dev: the cut itself; read i goes to
+ *       peer_keys[owner][ h_base[owner] + d_tile_off[owner][tile] + stable rank of i among the tile's reads of that owner ],
+ *     h_base[owner] = reads that LOWER ranks send to that owner (the host all-gathers the count matrix), so an owner holds
+ *     the runs in source-rank order, as all_to_all would deliver them.  peer_keys / peer_payload: HOST arrays of the 2^k
+ *     device pointers (this rank's own arrays included).  The caller orders the ranks around the call (every owner's
+ *     previous contents consumed before; every writer finished after). */
+int32_t pmrd_peer_alloc(pmrd_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* handle64);
+int32_t pmrd_peer_free(pmrd_ctx* ctx, void* d_ptr);
+int32_t pmrd_peer_open(pmrd_ctx* ctx, const uint8_t* handle64, void** d_ptr);
+int32_t pmrd_peer_close(pmrd_ctx* ctx, void* d_ptr);
+int32_t pmrd_owner_tiles_dev(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n_reads, int32_t log2_world, uint32_t* d_tile_off,
+                             int64_t* h_counts);
+int32_t pmrd_owner_scatter_peer_dev(pmrd_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_payload, int64_t n_reads,
+                                    int32_t log2_world, const uint32_t* d_tile_off, uint64_t* const* peer_keys,
+                                    uint32_t* const* peer_payload, const int64_t* h_base);
+
 /* K4 on the plan's cell-major layout: cell c = whole 4096-record tiles [tile_start[c], tile_start[c+1]) of packed 8-byte records;
  * every cell is sorted on its own, stable LSD over the low key_bits (<= 32) bits, the bits above are carried along -- the
  * staged / direct scatter kernels the fused plan sorts its generated reads with (umi.py:97-115 grouping), exposed so that

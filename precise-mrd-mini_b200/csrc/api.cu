@@ -434,6 +434,37 @@ int32_t pmrd_owner_rekey_dev(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n_reads, i
     return k18_owner_rekey(ctx, d_keys, n_reads, log2_world);
 }
 
+int32_t pmrd_owner_tiles_dev(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n_reads, int32_t log2_world, uint32_t* d_tile_off, int64_t* h_counts) {
+    ENTER(ctx);
+    return k18_owner_tiles(ctx, d_keys, n_reads, log2_world, d_tile_off, h_counts);
+}
+
+int32_t pmrd_owner_scatter_peer_dev(pmrd_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_payload, int64_t n_reads, int32_t log2_world,
+                                    const uint32_t* d_tile_off, uint64_t* const* peer_keys, uint32_t* const* peer_payload, const int64_t* h_base) {
+    ENTER(ctx);
+    return k18_owner_scatter_peer(ctx, d_keys, d_payload, n_reads, log2_world, d_tile_off, peer_keys, peer_payload, h_base);
+}
+
+int32_t pmrd_peer_alloc(pmrd_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* handle64) {
+    ENTER(ctx);
+    return k18_peer_alloc(ctx, bytes, d_ptr, handle64);
+}
+
+int32_t pmrd_peer_open(pmrd_ctx* ctx, const uint8_t* handle64, void** d_ptr) {
+    ENTER(ctx);
+    return k18_peer_open(ctx, handle64, d_ptr);
+}
+
+int32_t pmrd_peer_close(pmrd_ctx* ctx, void* d_ptr) {
+    ENTER(ctx);
+    return k18_peer_close(ctx, d_ptr);
+}
+
+int32_t pmrd_peer_free(pmrd_ctx* ctx, void* d_ptr) {
+    ENTER(ctx);
+    return k18_peer_free(ctx, d_ptr);
+}
+
 int32_t pmrd_collapse_reads(pmrd_ctx* ctx, const uint64_t* h_keys, const uint32_t* h_payload, int64_t n_reads,
                             const pmrd_umi_params* params, pmrd_family_table* h_fam, int64_t capacity_f,
                             int64_t* n_families, pmrd_group_table* h_grp, int64_t capacity_g, int64_t* n_groups) {

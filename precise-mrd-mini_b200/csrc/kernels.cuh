@@ -40,3 +40,10 @@ int32_t k1_simulate_cells(pmrd_ctx* ctx, const int64_t* d_cell_id, const double*
 int32_t k18_owner_partition(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t* d_payload, uint64_t* d_keys_tmp, uint32_t* d_payload_tmp,
                             int64_t n, int32_t log2_world, int64_t* h_counts, int32_t* in_tmp);
 int32_t k18_owner_rekey(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n, int32_t log2_world);
+int32_t k18_owner_tiles(pmrd_ctx* ctx, const uint64_t* d_keys, int64_t n, int32_t log2_world, uint32_t* d_tile_off, int64_t* h_counts);
+int32_t k18_owner_scatter_peer(pmrd_ctx* ctx, const uint64_t* d_keys, const uint32_t* d_payload, int64_t n, int32_t log2_world,
+                               const uint32_t* d_tile_off, uint64_t* const* peer_keys, uint32_t* const* peer_payload, const int64_t* h_base);
+int32_t k18_peer_alloc(pmrd_ctx* ctx, int64_t bytes, void** d_ptr, uint8_t* handle64);
+int32_t k18_peer_open(pmrd_ctx* ctx, const uint8_t* handle64, void** d_ptr);
+int32_t k18_peer_close(pmrd_ctx* ctx, void* d_ptr);
+int32_t k18_peer_free(pmrd_ctx* ctx, void* d_ptr);

@@ -330,6 +330,40 @@ class Context:
         """``pmrd_owner_rekey_dev``: ``group >>= log2_world`` on a DEVICE key array (dense ids after the exchange)."""
         self._check(self.lib.pmrd_owner_rekey_dev(self.h, C.c_void_p(d_keys), C.c_int64(n), C.c_int32(log2_world)))
 
+    # -- peer-memory exchange (csrc/exchange.cu) ---------------------------------------------
+    def peer_alloc(self, nbytes: int):
+        """``pmrd_peer_alloc``: a device array other processes on the node can map.  Returns ``(device pointer, 64-byte handle)``."""
+        ptr, handle = C.c_void_p(0), (C.c_uint8 * 64)()
+        self._check(self.lib.pmrd_peer_alloc(self.h, C.c_int64(nbytes), C.byref(ptr), handle))
+        return int(ptr.value), bytes(handle)
+
+    def peer_open(self, handle: bytes) -> int:
+        ptr = C.c_void_p(0)
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self.lib.pmrd_peer_open(self.h, buf, C.byref(ptr)))
+        return int(ptr.value)
+
+    def peer_close(self, ptr: int) -> None:
+        self._check(self.lib.pmrd_peer_close(self.h, C.c_void_p(ptr)))
+
+    def peer_free(self, ptr: int) -> None:
+        self._check(self.lib.pmrd_peer_free(self.h, C.c_void_p(ptr)))
+
+    def owner_tiles_dev(self, d_keys: int, n: int, log2_world: int, d_tile_off: int):
+        """``pmrd_owner_tiles_dev``: fills ``d_tile_off`` (uint32 ``[2**log2_world][ceil(n / 4096)]``), returns reads per owner."""
+        counts = (C.c_int64 * (1 << log2_world))()
+        self._check(self.lib.pmrd_owner_tiles_dev(self.h, C.c_void_p(d_keys), C.c_int64(n), C.c_int32(log2_world), C.c_void_p(d_tile_off), counts))
+        return [int(c) for c in counts]
+
+    def owner_scatter_peer_dev(self, d_keys: int, d_payload: int, n: int, log2_world: int, d_tile_off: int, peer_keys, peer_payload, base) -> None:
+        """``pmrd_owner_scatter_peer_dev``: the cut, stored straight into the owners' (peer) arrays."""
+        w = 1 << log2_world
+        pk = (C.c_void_p * w)(*[C.c_void_p(int(p)) for p in peer_keys])
+        pp = (C.c_void_p * w)(*[C.c_void_p(int(p)) for p in peer_payload])
+        hb = (C.c_int64 * w)(*[int(b) for b in base])
+        self._check(self.lib.pmrd_owner_scatter_peer_dev(self.h, C.c_void_p(d_keys), C.c_void_p(d_payload), C.c_int64(n), C.c_int32(log2_world),
+                                                         C.c_void_p(d_tile_off), pk, pp, hb))
+
     def umi_hamming(self, a, b, umi_len: int) -> np.ndarray:
         a = _arr(a, np.uint32)
         b = _arr(b, np.uint32)

@@ -171,6 +171,57 @@ class _DeviceExchangeOps:
         return nf, out
 
 
+class _RawArray:
+    """A device array known by pointer only (a peer-mapped receive array): what the device steps need of a tensor."""
+
+    def __init__(self, ptr: int, n: int, device):
+        self._ptr, self._n, self.device = int(ptr), int(n), device
+
+    def data_ptr(self) -> int:
+        return self._ptr
+
+    def numel(self) -> int:
+        return self._n
+
+
+class PeerExchange:
+    """Receive arrays of every rank, mapped into every rank: the set-up of the peer-memory exchange (one NVSwitch node,
+    at most 8 ranks, one process per GPU).  Each rank allocates ``capacity_reads`` x (8 + 4) bytes with
+    ``pmrd_peer_alloc``, the 64-byte IPC handles go round once (``all_gather_object``) and every rank maps the others'
+    arrays (``pmrd_peer_open``).  ``collapse_reads_exchanged(..., peer=this)`` then cuts AND moves the reads with one
+    kernel (``pmrd_owner_scatter_peer_dev``) instead of a partitioned copy + NCCL all-to-all."""
+
+    def __init__(self, ctx, capacity_reads: int, group=None):
+        import torch.distributed as dist
+
+        self.ctx, self.group, self.capacity = ctx, group, int(capacity_reads)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8 or self.world & (self.world - 1):
+            raise ValueError(f"PeerExchange serves 2, 4 or 8 ranks of one node, not {self.world}")
+        self.kptr, kh = ctx.peer_alloc(self.capacity * 8)
+        self.pptr, ph = ctx.peer_alloc(self.capacity * 4)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, (kh, ph), group=group)
+        self.peer_keys = [self.kptr if r == self.rank else ctx.peer_open(h[0]) for r, h in enumerate(handles)]
+        self.peer_payload = [self.pptr if r == self.rank else ctx.peer_open(h[1]) for r, h in enumerate(handles)]
+        dist.barrier(group)
+
+    def close(self) -> None:
+        import torch.distributed as dist
+
+        if self.ctx is None:
+            return
+        dist.barrier(self.group)                      # nobody still writes into (or reads from) a mapped array
+        for r in range(self.world):
+            if r != self.rank:
+                self.ctx.peer_close(self.peer_keys[r])
+                self.ctx.peer_close(self.peer_payload[r])
+        dist.barrier(self.group)                      # every mapping is gone before the memory is
+        self.ctx.peer_free(self.kptr)
+        self.ctx.peer_free(self.pptr)
+        self.ctx = None
+
+
 def exchange_splits(send_counts: Sequence[int], group=None, device=None) -> Tuple[list, list]:
     """``(send, recv)`` split sizes of the all-to-all: ``recv[r]`` = what rank ``r`` cut off for this rank."""
     import torch
@@ -183,7 +234,7 @@ def exchange_splits(send_counts: Sequence[int], group=None, device=None) -> Tupl
 
 
 def collapse_reads_exchanged(ctx, keys, payload, params, n_ids: int, group=None, ops=None, gather: bool = True,
-                             timings: Optional[dict] = None) -> Dict[str, np.ndarray]:
+                             timings: Optional[dict] = None, peer: Optional[PeerExchange] = None) -> Dict[str, np.ndarray]:
     """``Context.collapse_reads(..., want_families=False)`` for reads held by ALL ranks of the process group.
 
     ``keys`` (int64: ``group << 32 | umi``) and ``payload`` (int32) are this rank's reads as torch tensors on its GPU,
@@ -191,6 +242,9 @@ def collapse_reads_exchanged(ctx, keys, payload, params, n_ids: int, group=None,
     Returns the per-group table (``group``, ``family_count``, ``consensus_count``) and ``n_families`` -- of ALL groups on
     every rank when ``gather`` (one all-gather of 24 B per group), else of the rank's own groups -- equal, bit for bit,
     to the single-GPU table of the ranks' reads concatenated in rank order.  Replaces umi.py:205-285 for that case.
+
+    ``peer``: a ``PeerExchange`` of the group -- the cut then stores every read straight into its owner's receive array
+    over NVLink (one kernel instead of partitioned copy + NCCL all-to-all); same table.
 
     ``ops`` injects the device steps (tests run the exchange logic on CPU ranks over gloo with a NumPy double); without
     it the reads must be CUDA tensors and the steps are the library's kernels."""
@@ -208,16 +262,41 @@ def collapse_reads_exchanged(ctx, keys, payload, params, n_ids: int, group=None,
             raise RuntimeError("collapse_reads_exchanged: reads must be CUDA tensors (the exchange and the collapse run on the GPU)")
         ops = _DeviceExchangeOps(ctx)
     n = int(keys.numel())
-    keys_tmp, payload_tmp = torch.empty_like(keys), torch.empty_like(payload)
+    fused = peer is not None and world > 1
     ev = None
     if timings is not None and keys.is_cuda:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record()
-    counts, in_tmp = ops.owner_partition(keys, payload, keys_tmp, payload_tmp, log2w) if n else ([0] * world, False)
-    sk, sp = (keys_tmp, payload_tmp) if in_tmp else (keys, payload)
-    if ev:
-        ev[1].record()
-    if world > 1:
+    if fused:
+        # ---- cut + exchange as one kernel over peer memory
+        n_tiles = (n + 4095) // 4096
+        tile_off = torch.empty(max(1, world * n_tiles), dtype=torch.int32, device=keys.device)
+        ops._after_torch(keys)
+        counts = ctx.owner_tiles_dev(keys.data_ptr(), n, log2w, tile_off.data_ptr()) if n else [0] * world
+        mat = torch.empty(world * world, dtype=torch.int64, device=keys.device)
+        dist.all_gather_into_tensor(mat, torch.tensor(counts, dtype=torch.int64, device=keys.device), group=group)
+        mat = mat.view(world, world).cpu().numpy()                 # mat[r][o]: reads rank r sends to owner o
+        base = mat[:rank].sum(axis=0).tolist()
+        n_recv = int(mat[:, rank].sum())
+        if n_recv > peer.capacity:
+            raise RuntimeError(f"PeerExchange capacity {peer.capacity} reads < {n_recv} reads bound for rank {rank}")
+        if ev:
+            ev[1].record()
+        dist.barrier(group)                                        # every owner has consumed what its arrays held
+        if n:
+            ctx.owner_scatter_peer_dev(keys.data_ptr(), payload.data_ptr(), n, log2w, tile_off.data_ptr(), peer.peer_keys, peer.peer_payload, base)
+        torch.cuda.synchronize(keys.device)
+        dist.barrier(group)                                        # every writer has finished
+        rk, rp = _RawArray(peer.kptr, n_recv, keys.device), _RawArray(peer.pptr, n_recv, keys.device)
+    else:
+        keys_tmp, payload_tmp = torch.empty_like(keys), torch.empty_like(payload)
+        counts, in_tmp = ops.owner_partition(keys, payload, keys_tmp, payload_tmp, log2w) if n else ([0] * world, False)
+        sk, sp = (keys_tmp, payload_tmp) if in_tmp else (keys, payload)
+        if ev:
+            ev[1].record()
+    if fused:
+        pass                                                        # (the reads are already at their owners)
+    elif world > 1:
         send, recv = exchange_splits(counts, group, keys.device)
         n_recv = sum(recv)
         rk, rp = torch.empty(n_recv, dtype=keys.dtype, device=keys.device), torch.empty(n_recv, dtype=payload.dtype, device=keys.device)
@@ -230,7 +309,8 @@ def collapse_reads_exchanged(ctx, keys, payload, params, n_ids: int, group=None,
     n_local_ids = (int(n_ids) - rank + world - 1) // world if n_ids > rank else 0
     if n_recv:
         ops.owner_rekey(rk, log2w)
-        rkt, rpt = torch.empty_like(rk), torch.empty_like(rp)
+        rkt = torch.empty(n_recv, dtype=torch.int64, device=keys.device)
+        rpt = torch.empty(n_recv, dtype=torch.int32, device=keys.device)
         nf, tab = ops.collapse_groups(rk, rp, rkt, rpt, params, n_local_ids + 16)
     else:
         nf, tab = 0, {"group": np.zeros(0, np.int64), "family_count": np.zeros(0, np.uint32), "consensus_count": np.zeros((0, 4), np.uint32)}

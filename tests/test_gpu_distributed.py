@@ -114,14 +114,31 @@ def _exchange_worker(rank, world, port, q, n_ids, n_per_rank):
     keys, pl = _striped_reads(rank, n_per_rank + 1001 * rank, n_ids)
     dev = torch.device("cuda", rank)
     out = {}
+    from precise_mrd.distributed import PeerExchange
+
+    peer = PeerExchange(ctx, 2 * (n_per_rank + 1001 * world))          # receive arrays of all ranks, mapped everywhere
     for gather in (True, False):
         tk, tp = torch.from_numpy(keys.view(np.int64)).to(dev), torch.from_numpy(pl.view(np.int32)).to(dev)
         t = {}
         tab = collapse_reads_exchanged(ctx, tk, tp, P, n_ids, gather=gather, timings=t)
         out[gather] = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in tab.items()}
         out[gather]["timings"] = t
+    # the same through ONE cut-and-store kernel over peer memory instead of partitioned copy + NCCL all-to-all (twice: the
+    # receive arrays are reused)
+    for it in range(2):
+        tk, tp = torch.from_numpy(keys.view(np.int64)).to(dev), torch.from_numpy(pl.view(np.int32)).to(dev)
+        tab = collapse_reads_exchanged(ctx, tk, tp, P, n_ids, gather=True, peer=peer)
+        out[("peer", it)] = {k: (v.tolist() if hasattr(v, "tolist") else v) for k, v in tab.items()}
+    with pytest.raises(RuntimeError, match="capacity"):
+        small = PeerExchange(ctx, 1000)
+        try:
+            tk, tp = torch.from_numpy(keys.view(np.int64)).to(dev), torch.from_numpy(pl.view(np.int32)).to(dev)
+            collapse_reads_exchanged(ctx, tk, tp, P, n_ids, peer=small)
+        finally:
+            small.close()
+    peer.close()
     launched = ctx.launch_count
-    q.put((rank, out[True], out[False], launched))
+    q.put((rank, out[True], out[False], launched, out[("peer", 0)], out[("peer", 1)]))
     ctx.close() if hasattr(ctx, "close") else None
     dist.destroy_process_group()
 
@@ -157,7 +174,10 @@ def test_exchanged_collapse_on_gpus_equals_one_gpu(native, ctx):
         info, one = ctx.collapse_reads(keys, pl, P, want_families=False)
         og = cport.collapse_groups(keys, pl, n_ids + 1, 3, 1000, 20, 0.6)
         assert (one["family_count"] == og["family_count"][one["group"]]).all() and info["n_families"] == og["total_families"]
-        for rank, full, own, launched in res:
+        for rank, full, own, launched, peer0, peer1 in res:
+            for pv in (peer0, peer1):                                   # the peer-memory form gives the very same table
+                assert pv["group"] == full["group"] and pv["family_count"] == full["family_count"], (world, rank)
+                assert pv["consensus_count"] == full["consensus_count"] and pv["n_families"] == full["n_families"]
             assert full["group"] == one["group"].tolist() and full["n_families"] == info["n_families"], (world, rank)
             assert full["family_count"] == one["family_count"].tolist()
             assert full["consensus_count"] == one["consensus_count"].tolist()
@@ -165,4 +185,4 @@ def test_exchanged_collapse_on_gpus_equals_one_gpu(native, ctx):
             assert own["group"] == one["group"][mine].tolist() and own["family_count"] == one["family_count"][mine].tolist()
             t = full["timings"]
             assert t["received_reads"] > 0 and t["sent_reads"] > 0 and launched > 0       # reads really changed hands, our kernels ran
-        assert sum(o["n_families"] for _, _, o, _ in res) == info["n_families"]
+        assert sum(r_[2]["n_families"] for r_ in res) == info["n_families"]
