@@ -497,36 +497,56 @@ def exchange_leg(ctx, args, k0, p0, P, n, n_loci, rank, world, local_rank, barri
                 and (got["consensus_count"] == one["consensus_count"]).all())
         ok[0] = 1 if same else 0
     dist.broadcast(ok, 0)
-    # (2) the full-size exchange, timed
-    parts = {"partition_ms": 0.0, "exchange_ms": 0.0, "collapse_ms": 0.0}
-    total_ms, fams, sent = 0.0, 0, 0
-    for it in range(max(args.warmup, 3) + args.steps):
-        dk, dp = k0.clone(), p0.clone()                              # the call clobbers its inputs: restored untimed
-        barrier()
-        tm = {}
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        tab = collapse_reads_exchanged(ctx, dk, dp, P, n_loci, gather=False, timings=tm)
-        e1.record()
-        torch.cuda.synchronize()
-        if it >= max(args.warmup, 3):
-            total_ms += e0.elapsed_time(e1)
-            for k_ in parts:
-                parts[k_] += tm[k_]
-            fams, sent = tab["n_families"], tm["sent_reads"]
-        del dk, dp
-    t = torch.tensor([total_ms] + [parts[k_] for k_ in ("partition_ms", "exchange_ms", "collapse_ms")], dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    f = torch.tensor([fams, sent], dtype=torch.int64, device=dev)
-    dist.all_reduce(f)
-    tot, pm, xm, cm = [float(x) / args.steps for x in t.tolist()]
-    return {"what": "the ranks' reads as stripes of ONE sample: owner cut (pmrd_owner_partition_dev) -> all_to_all_single over NCCL -> "
-                    "pmrd_owner_rekey_dev + pmrd_collapse_reads_dev at the owner; per-locus table of all N x 1.25e8 reads, rows held by their owners",
-            "value": float(n) * world / (tot * 1e-3), "unit": UNIT, "ms_per_step": tot, "scaling": "weak",
-            "max_over_ranks_ms": {"owner_partition": pm, "all_to_all": xm, "owner_collapse": cm},
-            "reads_sent_per_step": int(f[1].item()), "bytes_sent_per_step": int(f[1].item()) * 12,
-            "all_to_all_GBps_per_gpu": (int(f[1].item()) / world * 12 / 1e9) / (xm * 1e-3) if xm > 0 else None,
-            "families": int(f[0].item()), "exchanged_equals_single": bool(ok.item()),
+    # (2) the full-size exchange, timed in both forms: partitioned copy + NCCL all-to-all, and ONE cut-and-store kernel over
+    # peer memory (the owners' receive arrays mapped into every rank)
+    from precise_mrd.distributed import PeerExchange
+
+    peer = PeerExchange(ctx, int(n * 1.05) + 4096)
+    got_p = collapse_reads_exchanged(ctx, tk.clone(), tp.clone(), P, ids, peer=peer)
+    okp = torch.ones(1, dtype=torch.int64, device=dev)
+    if not (got_p["n_families"] == got["n_families"] and (got_p["group"] == got["group"]).all() and (got_p["family_count"] == got["family_count"]).all()
+            and (got_p["consensus_count"] == got["consensus_count"]).all()):
+        okp[0] = 0
+    dist.all_reduce(okp, op=dist.ReduceOp.MIN)
+    forms = {}
+    for form, pe in (("nccl", None), ("peer", peer)):
+        parts = {"partition_ms": 0.0, "exchange_ms": 0.0, "collapse_ms": 0.0}
+        total_ms, fams, sent = 0.0, 0, 0
+        launches0 = ctx.launch_count
+        for it in range(max(args.warmup, 3) + args.steps):
+            dk, dp = k0.clone(), p0.clone()                          # the call clobbers its inputs: restored untimed
+            barrier()
+            if it == max(args.warmup, 3):
+                launches0 = ctx.launch_count
+            tm = {}
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            tab = collapse_reads_exchanged(ctx, dk, dp, P, n_loci, gather=False, timings=tm, peer=pe)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= max(args.warmup, 3):
+                total_ms += e0.elapsed_time(e1)
+                for k_ in parts:
+                    parts[k_] += tm[k_]
+                fams, sent = tab["n_families"], tm["sent_reads"]
+            del dk, dp
+        t = torch.tensor([total_ms] + [parts[k_] for k_ in ("partition_ms", "exchange_ms", "collapse_ms")], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        f = torch.tensor([fams, sent], dtype=torch.int64, device=dev)
+        dist.all_reduce(f)
+        tot, pm, xm, cm = [float(x) / args.steps for x in t.tolist()]
+        names = ("owner_partition", "all_to_all", "owner_collapse") if form == "nccl" else ("tile_offsets_and_counts", "cut_and_store_over_nvlink", "owner_collapse")
+        forms[form] = {"value": float(n) * world / (tot * 1e-3), "unit": UNIT, "ms_per_step": tot, "max_over_ranks_ms": dict(zip(names, (pm, xm, cm))),
+                       "reads_sent_per_step": int(f[1].item()), "bytes_sent_per_step": int(f[1].item()) * 12,
+                       "exchange_GBps_per_gpu": (int(f[1].item()) / world * 12 / 1e9) / (xm * 1e-3) if xm > 0 else None,
+                       "families": int(f[0].item()), "gpu_launches_per_step": (ctx.launch_count - launches0) // max(args.steps, 1)}
+    peer.close()
+    return {"what": "the ranks' reads as stripes of ONE sample -> every locus has an owner rank (locus mod N) -> per-locus table of all N x 1.25e8 "
+                    "reads, rows held by their owners.  nccl: pmrd_owner_partition_dev -> all_to_all_single -> pmrd_owner_rekey_dev + "
+                    "pmrd_collapse_reads_dev; peer: pmrd_owner_tiles_dev -> pmrd_owner_scatter_peer_dev (the cut stores into the owners' "
+                    "IPC-mapped receive arrays over NVLink: no staging copy, no all-to-all) -> the same owner-side collapse",
+            "scaling": "weak", "value": forms["peer"]["value"], "unit": UNIT, "ms_per_step": forms["peer"]["ms_per_step"], "forms": forms,
+            "exchanged_equals_single": bool(ok.item()), "peer_form_equals_nccl_form": bool(okp.item()),
             "equality_instance": f"{ns} reads per rank over {ids} loci vs rank 0's single-GPU table of the concatenation"}
 
 

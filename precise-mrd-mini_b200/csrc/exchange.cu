@@ -80,8 +80,7 @@ int32_t k18_owner_rekey(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n, int32_t log2
 // (cudaIpcOpenMemHandle, pmrd_peer_open) and the cut writes record i of a tile to
 //     peer[owner].keys[ base[owner] + tile_off[owner][tile] + (stable rank of i among the tile's reads of that owner) ]
 // where base[owner] = reads that lower ranks send to that owner (one small all-gather of the count matrix on the host side).
-// A warp's reads of one owner land on consecutive addresses (the ranks are stable), so the NVLink stores are runs of up to
-// 32 x 8 bytes.  Same order at the owner as the NCCL form: source rank, then arrival.
+// Same order at the owner as the NCCL form: source rank, then arrival.
 #define OX_THREADS 256
 #define OX_ITEMS 16
 #define OX_TILE (OX_THREADS * OX_ITEMS)
@@ -144,15 +143,28 @@ struct OwnerPeers {
     unsigned long long base[OX_MAX_WORLD];
 };
 
+struct OxSmem {
+    uint64_t key[OX_TILE];
+    uint32_t pl[OX_TILE];
+    unsigned long long delta[OX_MAX_WORLD];                       // position in the tile -> position at the owner
+    uint32_t run[OX_THREADS / 32][OX_MAX_WORLD];                  // first: reads of (warp, owner); then: where that run starts in the tile
+};
+
+// The tile is first put in owner order in shared memory and then streamed out position by position, so that a warp's
+// store is 32 consecutive records of ONE owner (256 + 128 bytes): at 8 ranks a direct store from the ranking registers
+// would leave a warp with ~4 lanes per owner, 32-byte NVLink writes.
 __global__ void __launch_bounds__(OX_THREADS, 3)
 owner_scatter_peer_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ payload, int64_t n, int log2_world, int64_t n_tiles,
                           const uint32_t* __restrict__ tile_off /*[world][n_tiles]*/, OwnerPeers P) {
     constexpr int WARPS = OX_THREADS / 32;
-    __shared__ unsigned long long s_run[WARPS][OX_MAX_WORLD];      // first: reads of (warp, owner); then: where that run starts at the owner
+    extern __shared__ __align__(16) unsigned char ox_raw[];
+    OxSmem& S = *reinterpret_cast<OxSmem*>(ox_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, lt = lanemask_lt();
     const uint32_t mask = (1u << log2_world) - 1u;
-    if (threadIdx.x < WARPS * OX_MAX_WORLD) (&s_run[0][0])[threadIdx.x] = 0ull;
-    const int64_t base = (int64_t)blockIdx.x * OX_TILE + (int64_t)warp * (OX_TILE / WARPS);
+    if (threadIdx.x < WARPS * OX_MAX_WORLD) (&S.run[0][0])[threadIdx.x] = 0u;
+    const int64_t tile_base = (int64_t)blockIdx.x * OX_TILE;
+    const int64_t base = tile_base + (int64_t)warp * (OX_TILE / WARPS);
+    const int tile_n = n - tile_base < OX_TILE ? (int)(n - tile_base) : OX_TILE;
     uint64_t key[OX_ITEMS];
     uint32_t pl[OX_ITEMS];
 #pragma unroll
@@ -177,25 +189,29 @@ owner_scatter_peer_kernel(const uint64_t* __restrict__ keys, const uint32_t* __r
         }
         const uint32_t before = __popc(m & lt);
         const int leader = __ffs((int)m) - 1;
-        unsigned long long old = 0ull;
+        uint32_t old = 0u;
         if (valid && before == 0) {
-            old = s_run[warp][d];                                   // (only this warp touches its row: no atomics)
-            s_run[warp][d] = old + (unsigned long long)__popc(m);
+            old = S.run[warp][d];                                   // (only this warp touches its row: no atomics)
+            S.run[warp][d] = old + (uint32_t)__popc(m);
         }
         __syncwarp();
         old = __shfl_sync(0xffffffffu, old, leader);
-        const uint32_t r = (uint32_t)old + before;
+        const uint32_t r = old + before;
         if (i & 1) rank2[i >> 1] |= r << 16;
         else rank2[i >> 1] = r;
     }
     __syncthreads();
-    if (threadIdx.x <= mask) {
-        unsigned long long run = P.base[threadIdx.x] + tile_off[(int64_t)threadIdx.x * n_tiles + blockIdx.x];
+    if (threadIdx.x == 0) {
+        // owner runs of the tile, owner 0 first; inside a run the warps in order
+        uint32_t at = 0u;
+        for (uint32_t o = 0; o <= mask; ++o) {
+            S.delta[o] = P.base[o] + tile_off[(int64_t)o * n_tiles + blockIdx.x] - at;
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const unsigned long long c = s_run[w][threadIdx.x];
-            s_run[w][threadIdx.x] = run;
-            run += c;
+            for (int w = 0; w < WARPS; ++w) {
+                const uint32_t c = S.run[w][o];
+                S.run[w][o] = at;
+                at += c;
+            }
         }
     }
     __syncthreads();
@@ -205,9 +221,21 @@ owner_scatter_peer_kernel(const uint64_t* __restrict__ keys, const uint32_t* __r
         if (j < n) {
             const uint32_t d = (uint32_t)(key[i] >> 32) & mask;
             const uint32_t r = (i & 1) ? rank2[i >> 1] >> 16 : rank2[i >> 1] & 0xffffu;
-            const unsigned long long at = s_run[warp][d] + r;
-            P.keys[d][at] = key[i];
-            P.payload[d][at] = pl[i];
+            const uint32_t at = S.run[warp][d] + r;
+            S.key[at] = key[i];
+            S.pl[at] = pl[i];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < OX_ITEMS; ++i) {
+        const int j = i * OX_THREADS + (int)threadIdx.x;
+        if (j < tile_n) {
+            const uint64_t k = S.key[j];
+            const uint32_t d = (uint32_t)(k >> 32) & mask;
+            const unsigned long long at = S.delta[d] + (unsigned long long)j;
+            P.keys[d][at] = k;
+            P.payload[d][at] = S.pl[j];
         }
     }
 }
@@ -245,7 +273,8 @@ int32_t k18_owner_scatter_peer(pmrd_ctx* ctx, const uint64_t* d_keys, const uint
         P.base[r] = (unsigned long long)h_base[r];
     }
     const int64_t n_tiles = (n + OX_TILE - 1) / OX_TILE;
-    PMRD_LAUNCH(ctx, owner_scatter_peer_kernel, (int)n_tiles, OX_THREADS, 0, d_keys, d_payload, n, (int)log2_world, n_tiles, d_tile_off, P);
+    PMRD_CUDA(ctx, cudaFuncSetAttribute(owner_scatter_peer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(OxSmem)));
+    PMRD_LAUNCH(ctx, owner_scatter_peer_kernel, (int)n_tiles, OX_THREADS, sizeof(OxSmem), d_keys, d_payload, n, (int)log2_world, n_tiles, d_tile_off, P);
     return PMRD_OK;
 }
 
