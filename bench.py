@@ -481,6 +481,12 @@ def exchange_leg(ctx, args, k0, p0, P, n, n_loci, rank, world, local_rank, barri
     from precise_mrd.distributed import collapse_reads_exchanged
 
     dev = torch.device("cuda", local_rank)
+    # weak scaling of ONE sample: N x 1.25e8 reads over N x 1e5 loci, every rank holding a stripe that covers all of them
+    # (~1250 reads per locus in total, ~1250 / N of them on each rank), so an owner ends up with the single-GPU problem
+    n_loci = n_loci * world
+    kx, px = external_reads(77_000 + rank, n, n_loci)
+    k0, p0 = torch.from_numpy(kx.view(np.int64)).to(dev), torch.from_numpy(px.view(np.int32)).to(dev)
+    del kx, px
     # (1) equality on a small instance: rank 0 collapses the concatenation on its own
     ns, ids = 200_000, 4096
     ks, ps = external_reads(1000 + rank, ns, ids)
@@ -541,11 +547,11 @@ def exchange_leg(ctx, args, k0, p0, P, n, n_loci, rank, world, local_rank, barri
                        "exchange_GBps_per_gpu": (int(f[1].item()) / world * 12 / 1e9) / (xm * 1e-3) if xm > 0 else None,
                        "families": int(f[0].item()), "gpu_launches_per_step": (ctx.launch_count - launches0) // max(args.steps, 1)}
     peer.close()
-    return {"what": "the ranks' reads as stripes of ONE sample -> every locus has an owner rank (locus mod N) -> per-locus table of all N x 1.25e8 "
-                    "reads, rows held by their owners.  nccl: pmrd_owner_partition_dev -> all_to_all_single -> pmrd_owner_rekey_dev + "
+    return {"what": "ONE sample of N x 1.25e8 reads over N x 1e5 loci, striped over the ranks in arrival order (every rank holds reads of every "
+                    "locus) -> every locus has an owner rank (locus mod N) -> per-locus table of all reads, rows held by their owners.  nccl: pmrd_owner_partition_dev -> all_to_all_single -> pmrd_owner_rekey_dev + "
                     "pmrd_collapse_reads_dev; peer: pmrd_owner_tiles_dev -> pmrd_owner_scatter_peer_dev (the cut stores into the owners' "
                     "IPC-mapped receive arrays over NVLink: no staging copy, no all-to-all) -> the same owner-side collapse",
-            "scaling": "weak", "value": forms["peer"]["value"], "unit": UNIT, "ms_per_step": forms["peer"]["ms_per_step"], "forms": forms,
+            "scaling": "weak", "value": forms["peer"]["value"], "unit": UNIT, "ms_per_step": forms["peer"]["ms_per_step"], "loci": int(n_loci), "forms": forms,
             "exchanged_equals_single": bool(ok.item()), "peer_form_equals_nccl_form": bool(okp.item()),
             "equality_instance": f"{ns} reads per rank over {ids} loci vs rank 0's single-GPU table of the concatenation"}
 
