@@ -222,7 +222,7 @@ int32_t pmrd_owner_rekey_dev(pmrd_ctx* ctx, uint64_t* d_keys, int64_t n_reads, i
  *     64-byte handle is what the ranks exchange.  pmrd_peer_open / pmrd_peer_close: map / unmap a peer's array.
  *   pmrd_owner_tiles_dev: per 4096-read tile, where the tile's reads of each owner start inside this rank's run for that
  *     owner: d_tile_off[owner * n_tiles + tile], n_tiles = ceil(n_reads / 4096); h_counts[r] = reads bound for rank r.
- *   pmrd_owner_scatter_peer_dev: the cut itself; read i goes to
+ *   pmrd_owner_scatter_peer_dev: the cut itself; read i goes, with its group already divided by 2^k (no pmrd_owner_rekey_dev), to
  *       peer_keys[owner][ h_base[owner] + d_tile_off[owner][tile] + stable rank of i among the tile's reads of that owner ],
  *     h_base[owner] = reads that LOWER ranks send to that owner (the host all-gathers the count matrix), so an owner holds
  *     the runs in source-rank order, as all_to_all would deliver them.  peer_keys / peer_payload: HOST arrays of the 2^k

@@ -234,7 +234,8 @@ owner_scatter_peer_kernel(const uint64_t* __restrict__ keys, const uint32_t* __r
             const uint64_t k = S.key[j];
             const uint32_t d = (uint32_t)(k >> 32) & mask;
             const unsigned long long at = S.delta[d] + (unsigned long long)j;
-            P.keys[d][at] = k;
+            // stored with the owner's dense group id (group / world): no separate re-keying pass over the received reads
+            P.keys[d][at] = (((k >> 32) >> log2_world) << 32) | (k & 0xffffffffull);
             P.payload[d][at] = S.pl[j];
         }
     }

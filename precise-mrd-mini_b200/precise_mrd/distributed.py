@@ -308,7 +308,8 @@ def collapse_reads_exchanged(ctx, keys, payload, params, n_ids: int, group=None,
         ev[2].record()
     n_local_ids = (int(n_ids) - rank + world - 1) // world if n_ids > rank else 0
     if n_recv:
-        ops.owner_rekey(rk, log2w)
+        if not fused:                                               # (the peer-memory cut stores the dense ids itself)
+            ops.owner_rekey(rk, log2w)
         rkt = torch.empty(n_recv, dtype=torch.int64, device=keys.device)
         rpt = torch.empty(n_recv, dtype=torch.int32, device=keys.device)
         nf, tab = ops.collapse_groups(rk, rp, rkt, rpt, params, n_local_ids + 16)
