@@ -278,8 +278,9 @@ def collapse_reads_exchanged(ctx, keys, payload, params, n_ids: int, group=None,
         mat = mat.view(world, world).cpu().numpy()                 # mat[r][o]: reads rank r sends to owner o
         base = mat[:rank].sum(axis=0).tolist()
         n_recv = int(mat[:, rank].sum())
-        if n_recv > peer.capacity:
-            raise RuntimeError(f"PeerExchange capacity {peer.capacity} reads < {n_recv} reads bound for rank {rank}")
+        if int(mat.sum(axis=0).max()) > peer.capacity:             # (every rank sees the whole matrix: all of them raise, none waits)
+            o = int(mat.sum(axis=0).argmax())
+            raise RuntimeError(f"PeerExchange capacity {peer.capacity} reads < {int(mat[:, o].sum())} reads bound for rank {o}")
         if ev:
             ev[1].record()
         dist.barrier(group)                                        # every owner has consumed what its arrays held
