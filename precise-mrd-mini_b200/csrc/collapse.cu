@@ -1010,7 +1010,7 @@ template <int ITEMS>
 __global__ void __launch_bounds__(SC_THREADS)
 small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__ cells, int n_cells, pmrd_umi_params P, int64_t cell0,
                   const uint8_t* __restrict__ alt_allele, unsigned long long* __restrict__ o_fam, unsigned long long* __restrict__ o_tot,
-                  unsigned long long* __restrict__ o_var) {
+                  unsigned long long* __restrict__ o_var, int sort_bits /* 16: two ranked passes + peel; 24: three */) {
     constexpr int CAP = SC_THREADS * ITEMS, WARPS = SC_THREADS / 32, PER_WARP = CAP / WARPS;
     __shared__ __align__(16) uint64_t s_rec[CAP];
     __shared__ __align__(16) unsigned char s_raw[4 * SC_THREADS * sizeof(double)];   // ranking counters, then the votes' allele sums
@@ -1035,8 +1035,11 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
         const int loc = (int)warp * PER_WARP + i * 32 + (int)lane;
         key[i] = loc < n ? src[loc] : 0xffffffffull;        // filler: UMI word 0xFFFFFFFF sorts last and is no 12-mer
     }
+    // (sort_bits = 16: a cell of <= 4096 reads has < 1000 families over 65 536 values of the low 16 bits, so a run of equal low
+    // bits is one family but for ~1 % of the runs -- those are separated by the vote below, cp_sweep_first / _chain, and the
+    // third ranked pass is not made)
 #pragma unroll 1
-    for (int shift = 0; shift < 24; shift += 8) {
+    for (int shift = 0; shift < sort_bits; shift += 8) {
         for (int i = threadIdx.x; i < WARPS * 256; i += SC_THREADS) (&s_cnt[0][0])[i] = 0u;
         __syncthreads();
         uint32_t rank2[ITEMS / 2 > 0 ? (ITEMS + 1) / 2 : 1];
@@ -1073,11 +1076,12 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
             s_rec[s_base[d] + s_cnt[warp][d] + r] = key[i];
         }
         __syncthreads();
-        if (shift < 16) {
+        if (shift + 8 < sort_bits) {
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) key[i] = s_rec[warp * PER_WARP + i * 32 + lane];
         }
     }
+    const uint32_t run_mask = sort_bits >= 24 ? 0xffffffffu : (1u << sort_bits) - 1u;
     // sorted: real reads occupy [0, n).  The family heads are compacted into a list first (a warp's 32 consecutive
     // records hold ~6 heads: voting in place would leave 26 lanes idle), then one thread votes one family.
     constexpr bool LIST = ITEMS <= 12;                       // (the list must fit the 48 KB of static shared memory)
@@ -1090,7 +1094,28 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
     auto vote_family = [&](int i) {
         const uint32_t umi = (uint32_t)s_rec[i];
         int len = 1;
-        while (i + len < n && (uint32_t)s_rec[i + len] == umi) ++len;
+        bool pure = true;
+        for (; i + len < n; ++len) {
+            const uint32_t u = (uint32_t)s_rec[i + len];
+            if ((u ^ umi) & run_mask) break;
+            pure &= u == umi;
+        }
+        if (!pure) {
+            // several families in the run (they differ in the unsorted high byte): swept as in cell_consensus_peel_kernel
+            auto hp_at = [&](int c) -> uint32_t {
+                const uint64_t r = s_rec[i + c];
+                return (((uint32_t)r >> 8) & 0xff00u) | ((uint32_t)(r >> 32) & 0xffu);
+            };
+            uint32_t key1, n1, n2;
+            if (P.consensus_threshold > 0.5) {
+                cp_sweep_first<true>(len, hp_at, alt, s_wt, P, key1, n1, n2, n_fam, n_tot, n_var);
+                cp_sweep_chain<true>(len, hp_at, hp_at(0) >> 8, n1, key1, false, alt, s_wt, P, n_fam, n_tot, n_var);
+            } else {
+                cp_sweep_first<false>(len, hp_at, alt, s_wt, P, key1, n1, n2, n_fam, n_tot, n_var);
+                cp_sweep_chain<false>(len, hp_at, hp_at(0) >> 8, n1, key1, false, alt, s_wt, P, n_fam, n_tot, n_var);
+            }
+            return;
+        }
         int best = -1;
         if (P.consensus_threshold > 0.5) {
             FoldVote2<true> v;
@@ -1107,7 +1132,7 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
     if (LIST) {
         for (int i0 = 0; i0 < n; i0 += SC_THREADS) {
             const int i = i0 + (int)threadIdx.x;
-            const bool head = i < n && (i == 0 || (uint32_t)s_rec[i - 1] != (uint32_t)s_rec[i]);
+            const bool head = i < n && (i == 0 || (((uint32_t)s_rec[i - 1] ^ (uint32_t)s_rec[i]) & run_mask) != 0u);
             const uint32_t hm = __ballot_sync(0xffffffffu, head);
             uint32_t pos = 0;
             if (lane == 0 && hm) pos = atomicAdd(&s_nheads, (uint32_t)__popc(hm));
@@ -1119,7 +1144,7 @@ small_cell_kernel(const uint64_t* __restrict__ rec, const ReadCell* __restrict__
         for (int h = threadIdx.x; h < n_heads; h += SC_THREADS) vote_family((int)s_list[h]);
     } else {
         for (int i = threadIdx.x; i < n; i += SC_THREADS)
-            if (i == 0 || (uint32_t)s_rec[i - 1] != (uint32_t)s_rec[i]) vote_family(i);
+            if (i == 0 || (((uint32_t)s_rec[i - 1] ^ (uint32_t)s_rec[i]) & run_mask) != 0u) vote_family(i);
     }
     n_fam = warp_sum(n_fam); n_tot = warp_sum(n_tot); n_var = warp_sum(n_var);
     if (lane == 0) {
@@ -1142,11 +1167,13 @@ int32_t k5_collapse_counts_small(pmrd_ctx* ctx, const uint64_t* d_rec, const Rea
     if (n_cells <= 0) return PMRD_OK;
     PMRD_ARG(ctx, max_cell_reads <= 4096, "small-cell collapse: a cell holds more than 4096 reads");
     unsigned long long *f = (unsigned long long*)d_o_fam, *t = (unsigned long long*)d_o_tot, *v = (unsigned long long*)d_o_var;
+    const char* sb = getenv("PMRD_SMALL_SORT_BITS");                // 24: three ranked passes, every run is a family
+    const int sort_bits = sb && atoi(sb) == 24 ? 24 : 16;
     // records per thread: the smallest that holds the largest cell (a slot beyond the cell's reads still costs a rank)
 #define SC_CASE(I) \
     if (max_cell_reads <= (int64_t)SC_THREADS * (I)) {                                                                          \
         PMRD_LAUNCH_NAMED(ctx, "small_cell_kernel", small_cell_kernel<I>, (int)n_cells, SC_THREADS, 0, d_rec, d_cells, (int)n_cells, \
-                          *params, cell0, d_alt_allele, f, t, v);                                                                \
+                          *params, cell0, d_alt_allele, f, t, v, sort_bits);                                                     \
         return PMRD_OK;                                                                                                          \
     }
     SC_CASE(1) SC_CASE(2) SC_CASE(3) SC_CASE(4) SC_CASE(5) SC_CASE(6) SC_CASE(7) SC_CASE(8) SC_CASE(10) SC_CASE(12) SC_CASE(14) SC_CASE(16)
@@ -1459,6 +1486,14 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
         key[i] = loc < n ? (((uint64_t)payload[lo + loc] << 32) | (uint32_t)keys[lo + loc]) : 0xffffffffull;
     }
     if (threadIdx.x == 0) s_nheads = 0u;
+    // ROWS = false (only the group's row is wanted, and a row does not depend on the order of the families): from three
+    // rounds up the LAST ranked round is not made.  A run of equal sorted bits is then one family but for the ~1 % of runs
+    // in which two UMIs share their low 16 (24) bits; the thread that owns such a run puts it in order itself (stable
+    // insertion sort of a handful of records) before it votes.
+    const bool partial = !ROWS && n_rounds >= 3 && n_rounds < 16;     // (n_rounds + 16: every round is made -- PMRD_GROUP_PARTIAL=0)
+    n_rounds &= 15;
+    if (partial) --n_rounds;
+    const uint32_t run_mask = partial ? (1u << (8 * n_rounds)) - 1u : 0xffffffffu;
 #pragma unroll 1
     for (int rd = 0; rd < n_rounds; ++rd) {
         const int shift = rd * 8;
@@ -1515,7 +1550,7 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int i = (int)warp * PER_WARP + it * 32 + (int)lane;
-        const bool head = i < n && (i == 0 || (uint32_t)s_rec[i - 1] != (uint32_t)s_rec[i]);
+        const bool head = i < n && (i == 0 || (((uint32_t)s_rec[i - 1] ^ (uint32_t)s_rec[i]) & run_mask) != 0u);
         hm[it] = __ballot_sync(0xffffffffu, head);
         n_mine += __popc(hm[it]);
     }
@@ -1538,9 +1573,31 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
     const int n_heads = (int)s_nheads;
     const uint64_t ghi = keys[lo] & 0xffffffff00000000ull;
     uint32_t a_fc = 0, a_alt = 0, a_tot = 0, a_c0 = 0, a_c1 = 0, a_c2 = 0, a_c3 = 0;      // ROWS = false: this thread's share of the group row
+    uint32_t a_nfam = 0;
     for (int h = threadIdx.x; h < n_heads; h += GR_THREADS) {
-        const int i = (int)s_list[h];
-        const int end = h + 1 < n_heads ? (int)s_list[h + 1] : n;
+        int i = (int)s_list[h];
+        const int run_end = h + 1 < n_heads ? (int)s_list[h + 1] : n;
+        int end = run_end;
+        if (partial) {
+            // the first family of the run; if it is not the whole run, order the run on the full UMI and take its families in turn
+            const uint32_t u0 = (uint32_t)s_rec[i];
+            int f1 = i + 1;
+            while (f1 < run_end && (uint32_t)s_rec[f1] == u0) ++f1;
+            if (f1 < run_end) {
+                for (int a = i + 1; a < run_end; ++a) {
+                    const uint64_t rec = s_rec[a];
+                    int b = a;
+                    while (b > i && (uint32_t)s_rec[b - 1] > (uint32_t)rec) { s_rec[b] = s_rec[b - 1]; --b; }
+                    s_rec[b] = rec;
+                }
+                f1 = i + 1;
+                const uint32_t u1 = (uint32_t)s_rec[i];
+                while (f1 < run_end && (uint32_t)s_rec[f1] == u1) ++f1;
+            }
+            end = f1;
+        }
+    next_family:
+        ++a_nfam;
         uint32_t n_alt, consensus, qsum_best, n_best, flags;
         family_row<MODE>((uint32_t)(end - i), [&](uint32_t r) -> uint32_t { return (uint32_t)(s_rec[i + r] >> 32); }, P, s_wt, n_alt,
                          consensus, qsum_best, n_best, flags);
@@ -1562,19 +1619,28 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
                 a_c0 += a == 0; a_c1 += a == 1; a_c2 += a == 2; a_c3 += a == 3;
             }
         }
+        if (partial && end < run_end) {                          // the run's next family
+            i = end;
+            const uint32_t u = (uint32_t)s_rec[i];
+            end = i + 1;
+            while (end < run_end && (uint32_t)s_rec[end] == u) ++end;
+            goto next_family;
+        }
     }
     if (ROWS) {
         if (threadIdx.x == 0) fam_cnt[g] = (uint32_t)n_heads;
         return;
     }
-    __shared__ uint32_t s_red[7];
-    if (threadIdx.x < 7) s_red[threadIdx.x] = 0u;
+    __shared__ uint32_t s_red[8];
+    if (threadIdx.x < 8) s_red[threadIdx.x] = 0u;
     __syncthreads();
     a_fc = warp_sum(a_fc); a_alt = warp_sum(a_alt); a_tot = warp_sum(a_tot);
     a_c0 = warp_sum(a_c0); a_c1 = warp_sum(a_c1); a_c2 = warp_sum(a_c2); a_c3 = warp_sum(a_c3);
+    a_nfam = warp_sum(a_nfam);
     if (lane == 0) {
         atomicAdd(&s_red[0], a_fc); atomicAdd(&s_red[1], a_alt); atomicAdd(&s_red[2], a_tot);
         atomicAdd(&s_red[3], a_c0); atomicAdd(&s_red[4], a_c1); atomicAdd(&s_red[5], a_c2); atomicAdd(&s_red[6], a_c3);
+        atomicAdd(&s_red[7], a_nfam);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1585,7 +1651,7 @@ group_rows_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict_
         G.total_count[row] = s_red[2];
         G.consensus_count[row * 4 + 0] = s_red[3]; G.consensus_count[row * 4 + 1] = s_red[4];
         G.consensus_count[row * 4 + 2] = s_red[5]; G.consensus_count[row * 4 + 3] = s_red[6];
-        atomicAdd(n_fam_total, (unsigned long long)n_heads);
+        atomicAdd(n_fam_total, (unsigned long long)s_red[7]);
     }
 }
 
@@ -1743,8 +1809,10 @@ static int32_t k5_collapse_groups_fast(pmrd_ctx* ctx, uint64_t* d_keys, uint32_t
     *done = true;
     int ubits = 0;
     while (ubits < 32 && (varying & 0xffffffffull) >> ubits) ++ubits;
-    const int n_rounds = (ubits + 7) / 8;
+    int n_rounds = (ubits + 7) / 8;
     const bool rows = d_fam && d_fam->key;
+    const char* gp = getenv("PMRD_GROUP_PARTIAL");              // 0: the counts-only form makes every ranked round too
+    if (gp && atoi(gp) == 0) n_rounds += 16;
     if (!rows) {
         // group table only: every block reduces its group's row; row of an id = number of non-empty ids before it
         PMRD_ARG(ctx, d_grp != nullptr, "neither a family table nor a group table was asked for");

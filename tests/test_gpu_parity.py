@@ -372,6 +372,24 @@ def test_collapse_external_reads_group_major_path(ctx, native, monkeypatch):
     og4 = cport.collapse_groups(keys4, pl4, 100_000, 3, 1000, 20, 0.6)
     assert (ga["family_count"] == og4["family_count"][ga["group"]]).all() and (ga["consensus_count"] == og4["consensus_count"][ga["group"]]).all()
     assert len(fa["key"]) == og4["total_families"]
+    # the counts-only form makes one ranked round fewer and leaves the high UMI byte to the vote.  Adversarial input for
+    # that: UMIs that share their low 16 bits by the dozen (3 low values x 80 high bytes per locus), so EVERY run is mixed
+    keys5, pl5 = _panel_reads(rng, 200_000, 500, 80)
+    u5 = keys5 & np.uint64(0xFFFFFFFF)
+    keys5 = (keys5 & np.uint64(0xFFFFFFFF00000000)) | ((u5 % np.uint64(80)) << np.uint64(16)) | (u5 % np.uint64(3))
+    for mode in (0, 1, 2):
+        P5 = _params(native, min_family_size=2, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6, mode=mode)
+        f5, g5 = ctx.collapse_reads(keys5, pl5, P5)
+        i5, go5 = ctx.collapse_reads(keys5, pl5, P5, want_families=False)
+        monkeypatch.setenv("PMRD_GROUP_PARTIAL", "0")
+        i6, go6 = ctx.collapse_reads(keys5, pl5, P5, want_families=False)
+        monkeypatch.delenv("PMRD_GROUP_PARTIAL")
+        assert i5["n_families"] == len(f5["key"]) == i6["n_families"]
+        for k in g5:
+            assert (go5[k] == g5[k]).all() and (go6[k] == g5[k]).all(), (mode, k)
+    og5 = cport.collapse_groups(keys5, pl5, 500, 2, 1000, 20, 0.6)
+    _, go5 = ctx.collapse_reads(keys5, pl5, _params(native, min_family_size=2, max_family_size=1000, quality_threshold=20, consensus_threshold=0.6, mode=native.MODE_WEIGHTED), want_families=False)
+    assert (go5["family_count"] == og5["family_count"]).all() and (go5["consensus_count"] == og5["consensus_count"]).all()
     # 3e6 reads over 20 000 loci: both paths, every mode
     keys3, pl3 = _panel_reads(rng, 3_000_000, 20_000, 40)
     for mode in (0, 1, 2):

@@ -556,6 +556,17 @@ def test_small_cells_are_sorted_and_voted_inside_one_block(ctx, native, monkeypa
         np.add.at(n_fam, (fam["key"] >> np.uint64(32)).astype(np.int64), 1)
         r = out[flag][0]
         assert (r["n_total"] == n_total).all() and (r["n_variants"] == n_var).all() and (r["n_families"] == n_fam).all(), flag
+    # the block sorts the low 16 UMI bits (two ranked passes) and separates the ~1 % of runs that hold several families in
+    # the vote; PMRD_SMALL_SORT_BITS=24 makes the third pass instead: the same table
+    monkeypatch.setenv("PMRD_SMALL_CELLS", "1")
+    monkeypatch.setenv("PMRD_SMALL_SORT_BITS", "24")
+    plan = native.Plan(ctx, cid, af, nf, sp, up)
+    plan.run()
+    full_sort = plan.results()
+    plan.close()
+    monkeypatch.delenv("PMRD_SMALL_SORT_BITS")
+    for k_ in ("n_reads", "n_families", "n_total", "n_variants", "p_value", "p_adjusted", "significant"):
+        assert (full_sort[k_] == a[k_]).all(), k_
     # streamed through many compact chunks: nothing changes
     monkeypatch.setenv("PMRD_SMALL_CELLS", "1")
     plan = native.Plan(ctx, cid, af, nf, _sp(native, family_model=1, mean_family_size=5.0, collision_rate=2e-3, chunk_log2=16), up)
