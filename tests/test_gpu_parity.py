@@ -435,6 +435,66 @@ def test_collapse_reads_dev_on_device_arrays_odd_length_and_alignment_contract(c
         ctx.collapse_reads_dev(kbuf[1:].data_ptr(), pbuf.data_ptr(), ktmp[1:].data_ptr(), ptmp.data_ptr(), n, P, None, 0, grp_p, gcap)
 
 
+@pytest.mark.parametrize("log2w", [1, 2, 3])
+def test_owner_cut_kernels_emulating_the_ranks_on_one_gpu(ctx, native, log2w):
+    """The device steps of the multi-GPU exchange (csrc/exchange.cu) with all "ranks" on ONE GPU: every rank's reads are cut
+    by owner (group mod 2^k) -- the partitioned-copy form (pmrd_owner_partition_dev) and the store-into-the-owner form
+    (pmrd_owner_tiles_dev + pmrd_owner_scatter_peer_dev, here with ordinary device arrays as the "peer" arrays) -- and each
+    owner must end up with exactly the concatenation, in rank order, of the ranks' reads it owns in arrival order, group ids
+    divided by 2^k.  (The real thing over NCCL / IPC: tests/test_gpu_distributed.py.)"""
+    torch = pytest.importorskip("torch")
+    world = 1 << log2w
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(40 + log2w)
+    parts = [_panel_reads(rng, 50_000 + 4097 * r + (r == 1), 3000, 40) for r in range(world)]       # odd sizes, partial tiles
+    parts[world - 1] = (parts[world - 1][0][:5], parts[world - 1][1][:5])                             # one rank with 5 reads
+    mask = np.uint64(world - 1)
+    want_k, want_p = [], []
+    for o in range(world):
+        ks = [k[((k >> np.uint64(32)) & mask) == o] for k, _ in parts]
+        ps = [p[((k >> np.uint64(32)) & mask) == o] for k, p in parts]
+        kk = np.concatenate(ks)
+        want_k.append((((kk >> np.uint64(32)) >> np.uint64(log2w)) << np.uint64(32)) | (kk & np.uint64(0xFFFFFFFF)))
+        want_p.append(np.concatenate(ps))
+    counts = np.array([[int((((k >> np.uint64(32)) & mask) == o).sum()) for o in range(world)] for k, _ in parts])   # [rank][owner]
+    # ---- partitioned-copy form
+    got = [[] for _ in range(world)]
+    for r, (k, p) in enumerate(parts):
+        n = len(k)
+        dk, dp = torch.from_numpy(k.view(np.int64)).to(dev), torch.from_numpy(p.view(np.int32)).to(dev)
+        dkt, dpt = torch.empty_like(dk), torch.empty_like(dp)
+        torch.cuda.synchronize()
+        c, in_tmp = ctx.owner_partition_dev(dk.data_ptr(), dp.data_ptr(), dkt.data_ptr(), dpt.data_ptr(), n, log2w)
+        assert c == counts[r].tolist()
+        sk, sp = (dkt, dpt) if in_tmp else (dk, dp)
+        ctx.owner_rekey_dev(sk.data_ptr(), n, log2w)
+        ctx.sync()
+        hk, hp = sk.cpu().numpy().view(np.uint64), sp.cpu().numpy().view(np.uint32)
+        at = 0
+        for o in range(world):
+            got[o].append((hk[at:at + c[o]], hp[at:at + c[o]]))
+            at += c[o]
+    for o in range(world):
+        assert (np.concatenate([a for a, _ in got[o]]) == want_k[o]).all() and (np.concatenate([b for _, b in got[o]]) == want_p[o]).all(), o
+    # ---- store-into-the-owner form: "peer" arrays = this GPU's own arrays
+    rk = [torch.full((int(counts[:, o].sum()) + 8,), -1, dtype=torch.int64, device=dev) for o in range(world)]
+    rp = [torch.full((int(counts[:, o].sum()) + 8,), -1, dtype=torch.int32, device=dev) for o in range(world)]
+    for r, (k, p) in enumerate(parts):
+        n = len(k)
+        dk, dp = torch.from_numpy(k.view(np.int64)).to(dev), torch.from_numpy(p.view(np.int32)).to(dev)
+        tile_off = torch.empty(world * ((n + 4095) // 4096), dtype=torch.int32, device=dev)
+        torch.cuda.synchronize()
+        c = ctx.owner_tiles_dev(dk.data_ptr(), n, log2w, tile_off.data_ptr())
+        assert c == counts[r].tolist()
+        base = counts[:r].sum(axis=0).tolist()
+        ctx.owner_scatter_peer_dev(dk.data_ptr(), dp.data_ptr(), n, log2w, tile_off.data_ptr(), [t.data_ptr() for t in rk], [t.data_ptr() for t in rp], base)
+        ctx.sync()
+    for o in range(world):
+        m = int(counts[:, o].sum())
+        assert (rk[o][:m].cpu().numpy().view(np.uint64) == want_k[o]).all() and (rp[o][:m].cpu().numpy().view(np.uint32) == want_p[o]).all(), o
+        assert (rk[o][m:] == -1).all() and (rp[o][m:] == -1).all()                    # nothing written past an owner's reads
+
+
 @pytest.mark.parametrize("d", [1, 2])
 def test_collapse_gb_greedy_clusters_vs_reference(ctx, golden, native, d):
     """K6 greedy (max_edit_distance > 0, the reference's default): the device clusters equal the reference's
