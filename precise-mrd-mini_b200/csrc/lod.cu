@@ -537,6 +537,104 @@ __device__ __noinline__ double lmw_enorm(double v, int start, int n, double agia
     return x3max * sqrt(s3);
 }
 
+// TWO norms for the price of one: a curve has at most 16 points here, so half of the warp idles.  Lanes 0-15 carry
+// vector A, lanes 16-31 vector B (point i on lane i of either half), every shuffle is confined to its half (width 16) and
+// each half folds ITS 16 operands -- one instruction stream, two norms.  The path (plain sum of squares / small components
+// only / general) is chosen for the warp as a whole, the more general one when the halves differ: all three give the same
+// bits where they apply.  Returns the norm of the caller's half.  m <= 16.
+__device__ __noinline__ double lmw_enorm_pair(double v, int start, int n, double agiant, LmwRow* row) {
+    const double rdwarf = 3.834e-20;
+    double s1 = 0, s2 = 0, s3 = 0, x1max = 0, x3max = 0;
+    const int lane = threadIdx.x & 31, sl = lane & 15, hb = lane & 16, end = start + n;
+    const bool in = sl >= start && sl < end;
+    const double xa = fabs(v);
+    const bool mid = xa > rdwarf && xa < agiant;
+    double x[16];
+    if (__all_sync(LMW_FULL, mid || !in)) {
+        row->a[lane] = xa;
+        __syncwarp();
+        LMW_LOAD16(x, row->a, hb)
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i >= start && i < end) s2 = fma(x[i], x[i], s2);
+        __syncwarp();
+        return s2 != 0.0 ? sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3))) : 0.0;
+    }
+    const bool sml = in && !mid && xa <= rdwarf;
+    const bool big = in && !mid && !sml;
+    double m3 = sml ? xa : 0.0, m1 = (big && xa == xa) ? xa : 0.0;
+    for (int d = 1; d < end; d <<= 1) {
+        const double t3 = __shfl_up_sync(LMW_FULL, m3, d, 16), t1 = __shfl_up_sync(LMW_FULL, m1, d, 16);
+        if (sl >= d) {
+            m3 = fmax(m3, t3);
+            m1 = fmax(m1, t1);
+        }
+    }
+    double e3 = __shfl_up_sync(LMW_FULL, m3, 1, 16), e1 = __shfl_up_sync(LMW_FULL, m1, 1, 16);
+    if (sl == 0) e3 = e1 = 0.0;
+    double t = xa;
+    int op = 0;
+    if (in) {
+        if (mid) {
+            op = 1;
+        } else if (sml) {
+            if (xa > e3) {
+                t = e3 / xa;
+                op = 2;
+            } else if (xa != 0.0) {
+                t = xa / e3;
+                op = 3;
+            }
+        } else {
+            if (xa > e1) {
+                t = e1 / xa;
+                op = 4;
+            } else {
+                t = xa / e1;
+                op = 5;
+            }
+        }
+    }
+    row->a[lane] = t;
+    const unsigned a1 = __ballot_sync(LMW_FULL, op == 1), a2 = __ballot_sync(LMW_FULL, op == 2), a3 = __ballot_sync(LMW_FULL, op == 3),
+                   a4 = __ballot_sync(LMW_FULL, op == 4), a5 = __ballot_sync(LMW_FULL, op == 5);
+    const unsigned b1 = (a1 >> hb) & 0xffffu, b2 = (a2 >> hb) & 0xffffu, b3 = (a3 >> hb) & 0xffffu, b4 = (a4 >> hb) & 0xffffu,
+                   b5 = (a5 >> hb) & 0xffffu;
+    __syncwarp();
+    LMW_LOAD16(x, row->a, hb)
+    if ((a1 | a4 | a5) == 0u) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const unsigned bit = 1u << i;
+            const double ti = x[i];
+            const double r2 = fma(s3, ti * ti, 1.0), r3 = fma(ti, ti, s3);
+            s3 = (b2 & bit) ? r2 : (b3 & bit) ? r3 : s3;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const unsigned bit = 1u << i;
+            const double ti = x[i];
+            if (b1 & bit) s2 = fma(ti, ti, s2);
+            if (b2 & bit) s3 = fma(s3, ti * ti, 1.0);
+            if (b3 & bit) s3 = fma(ti, ti, s3);
+            if (b4 & bit) s1 = fma(s1, ti * ti, 1.0);
+            if (b5 & bit) s1 = fma(ti, ti, s1);
+        }
+    }
+    __syncwarp();
+    if (n > 0) {
+        x3max = __shfl_sync(LMW_FULL, m3, end - 1, 16);
+        x1max = __shfl_sync(LMW_FULL, m1, end - 1, 16);
+    }
+    if (s1 != 0.0) return x1max * sqrt(s1 + (s2 / x1max) / x1max);
+    if (s2 != 0.0) {
+        if (s2 >= x3max) return sqrt(s2 * (1.0 + (x3max / s2) * (x3max * s3)));
+        return sqrt(x3max * ((s2 / x3max) + (x3max * s3)));
+    }
+    return x3max * sqrt(s3);
+}
+
 // sum_{i = start}^{m-1} a[i] * b[i], in index order
 __device__ __noinline__ double lmw_dot(double a, double b, int start, int m, LmwRow* row) {
     const int lane = threadIdx.x & 31;
@@ -785,13 +883,32 @@ __device__ static int lmw_lmdif2(int m, int lane, double px, double py, double* 
     double diag0 = 0.0, diag1 = 0.0;
     int info = 0, nfev = 0;
     const double ag_m = 1.304e19 / (double)m, ag_m1 = 1.304e19 / (double)(m - 1);      // enorm's agiant for n = m, m - 1
+    const double px2 = __shfl_sync(LMW_FULL, px, lane & 15), py2 = __shfl_sync(LMW_FULL, py, lane & 15);   // the curve, on both halves
     fvec = lmw_fcn2(px, py, x0, x1);
     nfev = 1;
     double fnorm = lmw_enorm(fvec, 0, m, ag_m, row);
     double par = 0.0, delta = 0.0, xnorm = 0.0, gnorm = 0.0;
     int iter = 1;
     for (;;) {
-        {
+        double acnorm0, acnorm1;
+        if (m <= 16) {
+            // both forward differences at once, column 0 on lanes 0-15 and column 1 on lanes 16-31 (which hold a copy of
+            // the curve), and both column norms by one pass of lmw_enorm_pair
+            const double eps = sqrt(epsmch);
+            const bool up = lane >= 16;
+            const double temp = up ? x1 : x0;
+            double h = eps * fabs(temp);
+            if (h == 0.0) h = eps;
+            const double f2 = __shfl_sync(LMW_FULL, fvec, lane & 15);
+            const double val = lmw_fcn2(px2, py2, up ? x0 : temp + h, up ? temp + h : x1);
+            const double d = (val - f2) / h;
+            const double nrm = lmw_enorm_pair(d, 0, m, ag_m, row);
+            c0 = __shfl_sync(LMW_FULL, d, lane & 15);
+            c1 = __shfl_sync(LMW_FULL, d, (lane & 15) | 16);
+            acnorm0 = __shfl_sync(LMW_FULL, nrm, 0);
+            acnorm1 = __shfl_sync(LMW_FULL, nrm, 16);
+            nfev += LM_N;
+        } else {
             const double eps = sqrt(epsmch);
             {
                 const double temp = x0;
@@ -808,13 +925,13 @@ __device__ static int lmw_lmdif2(int m, int lane, double px, double py, double* 
                 c1 = (wa4v - fvec) / h;
             }
             nfev += LM_N;
-        }
-        // qrfac (lmw_qrfac with the pivot order as one bit)
-        double rdiag0, rdiag1, acnorm0, acnorm1, qw1;
-        bool sw = false;
-        {
             acnorm0 = lmw_enorm(c0, 0, m, ag_m, row);
             acnorm1 = lmw_enorm(c1, 0, m, ag_m, row);
+        }
+        // qrfac (lmw_qrfac with the pivot order as one bit)
+        double rdiag0, rdiag1, qw1;
+        bool sw = false;
+        {
             rdiag0 = acnorm0;
             rdiag1 = qw1 = acnorm1;
             if (rdiag1 > rdiag0) {
