@@ -871,6 +871,22 @@ __device__ __forceinline__ void lm2_lmpar(double r00, double r01, double r11, bo
     }
 }
 
+// two dot products over the points at once: lanes 0-15 take sum a[i] b[i] of the values on THEIR half, lanes 16-31 of theirs
+__device__ __noinline__ double lmw_dot_pair(double a, double b, int start, int m, LmwRow* row) {
+    const int lane = threadIdx.x & 31, hb = lane & 16;
+    row->a[lane] = a;
+    row->b[lane] = b;
+    __syncwarp();
+    double sum = 0.0, x[16], y[16];
+    LMW_LOAD16(x, row->a, hb)
+    LMW_LOAD16(y, row->b, hb)
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (i >= start && i < m) sum = fma(x[i], y[i], sum);
+    __syncwarp();
+    return sum;
+}
+
 __device__ __noinline__ double lmw_fcn2(double px, double py, double a, double b) {
     return 1.0 / (1.0 + exp(-(a * px + b))) - py;
 }
@@ -929,8 +945,8 @@ __device__ static int lmw_lmdif2(int m, int lane, double px, double py, double* 
             acnorm1 = lmw_enorm(c1, 0, m, ag_m, row);
         }
         // qrfac (lmw_qrfac with the pivot order as one bit)
-        double rdiag0, rdiag1, qw1;
-        bool sw = false;
+        double rdiag0, rdiag1, qw1, sum_qf = 0.0;
+        bool sw = false, have_qf = false, have_aj = false;
         {
             rdiag0 = acnorm0;
             rdiag1 = qw1 = acnorm1;
@@ -945,7 +961,17 @@ __device__ static int lmw_lmdif2(int m, int lane, double px, double py, double* 
                 if (lmw_get(c0, 0) < 0.0) ajnorm = -ajnorm;
                 if (lane < m) c0 /= ajnorm;
                 if (lane == 0) c0 += 1.0;
-                const double sum = lmw_dot(c0, c1, 0, m, row);
+                double sum;
+                if (m <= 16) {
+                    // this dot product and the one Q^T f needs of the same column (below), one per half-warp
+                    const double c0m = __shfl_sync(LMW_FULL, c0, lane & 15), fm = __shfl_sync(LMW_FULL, fvec, lane & 15);   // (all lanes shuffle)
+                    const double pr = lmw_dot_pair(c0m, lane < 16 ? c1 : fm, 0, m, row);
+                    sum = __shfl_sync(LMW_FULL, pr, 0);
+                    sum_qf = __shfl_sync(LMW_FULL, pr, 16);
+                    have_qf = true;
+                } else {
+                    sum = lmw_dot(c0, c1, 0, m, row);
+                }
                 const double temp = sum / lmw_get(c0, 0);
                 if (lane < m) c1 -= temp * c0;
                 if (rdiag1 != 0.0) {
@@ -955,11 +981,12 @@ __device__ static int lmw_lmdif2(int m, int lane, double px, double py, double* 
                     if (0.05 * (t * t) <= epsmch) {
                         rdiag1 = lmw_enorm(c1, 1, m - 1, ag_m1, row);
                         qw1 = rdiag1;
+                        have_aj = true;                             // the very norm the next step asks for
                     }
                 }
             }
             rdiag0 = -ajnorm;
-            ajnorm = lmw_enorm(c1, 1, m - 1, ag_m1, row);
+            ajnorm = have_aj ? rdiag1 : lmw_enorm(c1, 1, m - 1, ag_m1, row);
             if (ajnorm != 0.0) {
                 if (lmw_get(c1, 1) < 0.0) ajnorm = -ajnorm;
                 if (lane >= 1 && lane < m) c1 /= ajnorm;
@@ -981,7 +1008,7 @@ __device__ static int lmw_lmdif2(int m, int lane, double px, double py, double* 
         {   // j = 0
             const double ajj = lmw_get(c0, 0);
             if (ajj != 0.0) {
-                const double sum = lmw_dot(c0, wa4v, 0, m, row);
+                const double sum = have_qf ? sum_qf : lmw_dot(c0, wa4v, 0, m, row);
                 const double temp = -sum / ajj;
                 if (lane < m) wa4v += c0 * temp;
             }
