@@ -166,7 +166,8 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
             S.tile_b = 0u;
         } else {
             S.tile_a = window_tile(w0, S.cell_n, inv_full, sp.shuffle, S.tile0);
-            S.tile_b = window_tile(w0 + 1u, S.cell_n, inv_full, sp.shuffle, S.tile0);
+            // (the next window's tile only matters to a family that reaches into it: 1 in 800 at five reads per family)
+            S.tile_b = S.cell_off % SHUF_WINDOW + size > SHUF_WINDOW ? window_tile(w0 + 1u, S.cell_n, inv_full, sp.shuffle, S.tile0) : 0u;
         }
         if (tile_hist) {
             // By-product for the collapse stage: the first radix pass needs, per 4096-slot tile of the
@@ -198,17 +199,19 @@ reads_gen_kernel(uint64_t seed, const ReadCell* __restrict__ cells, const int64_
     __syncthreads();
     const uint32_t le = lanemask_lt() | (1u << lane);
     const bool hopping = sp.hop_rate > 0.0 && n_cells > 1;
+    uint32_t before = 0;                             // families whose first read lies before this step
     for (uint32_t k0 = 0; k0 < total; k0 += 32) {
         const uint32_t k = k0 + lane;
         // owner of read k = (number of families whose first read is <= k) - 1.  Lane s still holds
         // family s's first read `loc` (ascending, distinct: every family has >= 1 read): the
-        // families that started before this step are counted by one ballot, those that start inside
-        // it are marked in a 32-bit mask by one warp OR-reduction, and a popcount finishes the job.
+        // families that start inside this step are marked in a 32-bit mask by one warp OR-reduction,
+        // those that started before it are the running sum of the earlier steps' marks, and a popcount finishes the job.
         const uint32_t rel = loc - k0;
-        const uint32_t before = __popc(__ballot_sync(0xffffffffu, loc < k0));
         const uint32_t heads = __reduce_or_sync(0xffffffffu, rel < 32u ? 1u << rel : 0u);
+        const uint32_t before_now = before;
+        before += __popc(heads);
         if (k >= total) continue;
-        const uint32_t lo = before + __popc(heads & le) - 1u;
+        const uint32_t lo = before_now + __popc(heads & le) - 1u;
         const FamSlot& S = s_slot[warp][lo];
         const uint4 sa = *reinterpret_cast<const uint4*>(&S.local_off);   // local_off, cell_off, tile_a, tile_b
         const uint4 sb = *reinterpret_cast<const uint4*>(&S.key);         // key, ctr_hi, fam, word
