@@ -414,7 +414,7 @@ def run_external(args, rank, world, local_rank, emit):
     # ---- N > 1: the SAME reads taken as stripes of ONE sample -> loci shared by all ranks -> the exchange of SURVEY.md §8e
     # (owner cut on the device, all-to-all over NCCL, owner-side collapse; precise_mrd.distributed.collapse_reads_exchanged)
     exchange = None
-    if world > 1:
+    if world in (2, 4, 8):                                            # (owner = locus mod N needs a power of two; PeerExchange serves one node)
         exchange = exchange_leg(ctx, args, k0, p0, P, n, n_loci, rank, world, local_rank, barrier)
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
