@@ -6,10 +6,15 @@
 
 Group options come BEFORE the sub-command; artifacts go to ``reports/`` and ``data/`` under the
 current directory; every command ends by echoing a JSON summary.  ``--engine grid`` switches the
-``eval-*`` commands from the parity engine to the read-level fused device plan."""
+``eval-*`` commands from the parity engine to the read-level fused device plan.
+
+Several GPUs: launch the same command line under ``python -m torch.distributed.run --nproc-per-node N -m precise_mrd.cli
+--engine grid eval-lod ...``; the group joins the NCCL process group, the grid engine shards its cells over the ranks
+(``distributed.run_cells_sharded``: the table is the single-GPU one bit for bit) and rank 0 alone writes the artifacts."""
 from __future__ import annotations
 
 import json
+import os
 import shutil
 from dataclasses import dataclass
 from datetime import datetime
@@ -104,6 +109,29 @@ def _run_smoke_pipeline(config: PipelineConfig, seed: int, output_dir: Path, con
 def main(ctx: click.Context, seed: int, config_path: Optional[Path], engine: str) -> None:
     """Precise MRD (B200): deterministic MRD analytics with hardened artifact contracts."""
     ctx.obj = CLIContext(seed=seed, config_override=config_path, engine=engine)
+    if engine == "grid" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        _join_process_group()
+
+
+def _join_process_group() -> None:
+    """Under ``torch.distributed.run``: one process per GPU over NCCL (the grid engine shards its cells over the ranks)."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.is_initialized():
+        return
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import atexit
+
+    atexit.register(lambda: dist.is_initialized() and dist.destroy_process_group())
+
+
+def _is_writer() -> bool:
+    """Rank 0 of a multi-process launch (every rank holds the same tables), or the only process."""
+    return int(os.environ.get("RANK", "0")) == 0 or int(os.environ.get("WORLD_SIZE", "1")) <= 1
 
 
 @main.command("smoke")
@@ -158,8 +186,9 @@ def eval_lob_cmd(ctx: CLIContext, n_blank: int) -> None:
     """Estimate the Limit of Blank."""
     an = _analyzer(ctx)
     an.estimate_lob(n_blank_runs=n_blank)
-    an.generate_reports(str(REPORTS_DIR))
-    _echo("eval-lob", ctx, lob=REPORTS_DIR / "lob.json")
+    if _is_writer():
+        an.generate_reports(str(REPORTS_DIR))
+        _echo("eval-lob", ctx, lob=REPORTS_DIR / "lob.json")
 
 
 @main.command("eval-lod")
@@ -170,8 +199,9 @@ def eval_lod_cmd(ctx: CLIContext, replicates: int) -> None:
     an = _analyzer(ctx)
     an.estimate_lob(n_blank_runs=max(10, replicates // 2))
     an.estimate_lod(n_replicates=replicates)
-    an.generate_reports(str(REPORTS_DIR))
-    _echo("eval-lod", ctx, lob=REPORTS_DIR / "lob.json", lod_table=REPORTS_DIR / "lod_table.csv", lod_curves=REPORTS_DIR / "lod_curves.png")
+    if _is_writer():
+        an.generate_reports(str(REPORTS_DIR))
+        _echo("eval-lod", ctx, lob=REPORTS_DIR / "lob.json", lod_table=REPORTS_DIR / "lod_table.csv", lod_curves=REPORTS_DIR / "lod_curves.png")
 
 
 @main.command("eval-loq")
@@ -182,8 +212,9 @@ def eval_loq_cmd(ctx: CLIContext, replicates: int) -> None:
     an = _analyzer(ctx)
     an.estimate_lob(n_blank_runs=max(10, replicates // 2))
     an.estimate_loq(n_replicates=replicates)
-    an.generate_reports(str(REPORTS_DIR))
-    _echo("eval-loq", ctx, lob=REPORTS_DIR / "lob.json", loq_table=REPORTS_DIR / "loq_table.csv")
+    if _is_writer():
+        an.generate_reports(str(REPORTS_DIR))
+        _echo("eval-loq", ctx, lob=REPORTS_DIR / "lob.json", loq_table=REPORTS_DIR / "loq_table.csv")
 
 
 @main.command("eval-contamination")
