@@ -175,3 +175,22 @@ def test_exchanged_collapse_refuses_three_ranks_and_cpu_reads_without_ops():
 
     with pytest.raises(RuntimeError, match="CUDA tensors"):           # no CPU fallback: the product path is the GPU's
         collapse_reads_exchanged(None, torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int32), None, 8)
+
+
+def test_exchanged_collapse_single_process_is_the_plain_collapse():
+    """No process group: the exchange degenerates to the local collapse (one owner, nothing sent)."""
+    import torch
+
+    sys.path.insert(0, str(ROOT))
+    from oracle import cport
+    from precise_mrd.distributed import collapse_reads_exchanged
+
+    keys, pl = _striped_reads(0, 20_000, 300)
+    t = {}
+    tab = collapse_reads_exchanged(None, torch.from_numpy(keys.view(np.int64).copy()), torch.from_numpy(pl.view(np.int32).copy()),
+                                   (3, 1000, 20, 0.6), 300, ops=_NumpyExchangeOps(), timings=t)
+    og = cport.collapse_groups(keys, pl, 301, 3, 1000, 20, 0.6)
+    ids = np.unique((keys >> np.uint64(32)).astype(np.int64))
+    assert (tab["group"] == ids).all() and tab["n_families"] == og["total_families"]
+    assert (tab["family_count"] == og["family_count"][ids]).all() and (tab["consensus_count"] == og["consensus_count"][ids]).all()
+    assert t == {}                                   # (device timings only exist for CUDA tensors)
